@@ -1,0 +1,168 @@
+"""Deterministic synthetic frequency tables and subject files (shared by the golden generator,
+the parity tests and bench.py).  Shapes follow SURVEY.md section 8(d): C2 (single population,
+fully typed, unambiguous), C3 (multi-population with race fields), C4 (ambiguous / missing
+loci / unknown alleles)."""
+import numpy as np
+
+LOCI5 = ["A", "B", "C", "DQB1", "DRB1"]
+
+
+# --------------------------------------------------------------------------- tables
+def parse_hpf(text):
+    """-> list of (hap, pop, freq_str) without the header."""
+    rows = []
+    for line in text.splitlines():
+        if not line or line.startswith("hap,"):
+            continue
+        hap, pop, freq = line.split(",")
+        rows.append((hap, pop, freq))
+    return rows
+
+
+def multipop_hpf(base_text, pops, seed, zero_frac=0.4):
+    """Perturbed copy of a single-population hpf: freq * LogNormal(0,1), zero_frac of the
+    (hap, pop) entries dropped, renormalised per population.  Returns (hpf_text, counts_text)."""
+    rng = np.random.RandomState(seed)
+    base = parse_hpf(base_text)
+    haps = [h for h, _p, _f in base]
+    f0 = np.array([float(f) for _h, _p, f in base])
+    lines = ["hap,pop,freq\n"]
+    for p in pops:
+        f = f0 * rng.lognormal(0.0, 1.0, size=len(f0))
+        f[rng.rand(len(f0)) < zero_frac] = 0.0
+        f = f / f.sum()
+        for h, x in zip(haps, f):
+            if x > 0:
+                lines.append("%s,%s,%s\n" % (h, p, repr(float(x))))
+    counts = 1000.0 / np.arange(1, len(pops) + 1) ** 1.1
+    tot = counts.sum()
+    ctext = "".join("%s,%s,%s\n" % (p, repr(float(c)), repr(float(c / tot))) for p, c in zip(pops, counts))
+    return "".join(lines), ctext
+
+
+def zipf_table(n_full, n_alleles, seed, loci=LOCI5, pops=("CAU",)):
+    """Synthetic table: each haplotype is an independent Zipf(s=1.1) draw per locus, frequency
+    proportional to 1/rank, normalised.  Returns hpf text."""
+    rng = np.random.RandomState(seed)
+    cols = []
+    for loc, na in zip(loci, n_alleles):
+        w = 1.0 / np.arange(1, na + 1) ** 1.1
+        w /= w.sum()
+        cols.append(rng.choice(na, size=int(n_full * 1.3), p=w))
+    tup = np.stack(cols, axis=1)
+    _u, first = np.unique(tup, axis=0, return_index=True)
+    tup = tup[np.sort(first)][:n_full]
+    n = len(tup)
+    lines = ["hap,pop,freq\n"]
+    for p_i, p in enumerate(pops):
+        f = 1.0 / np.arange(1, n + 1)
+        if p_i:
+            f = f * rng.lognormal(0.0, 1.0, size=n)
+        f /= f.sum()
+        names = ["~".join("%s*%02d:%02d" % (loc, a // 60 + 1, a % 60 + 1) for loc, a in zip(loci, row)) for row in tup]
+        lines.extend("%s,%s,%s\n" % (h, p, repr(float(x))) for h, x in zip(names, f))
+    return "".join(lines)
+
+
+class Table:
+    """Sampling helper over one population column of an hpf text."""
+
+    def __init__(self, hpf_text, pop=None, loci=LOCI5):
+        rows = parse_hpf(hpf_text)
+        if pop is None:
+            pop = rows[0][1]
+        self.loci = loci
+        self.haps = []
+        f = []
+        for h, p, x in rows:
+            if p == pop:
+                al = {a.split("*")[0]: a for a in h.split("~")}
+                self.haps.append([al[l] for l in loci])
+                f.append(float(x))
+        f = np.array(f)
+        self.p = f / f.sum()
+        self.alleles = [sorted({h[i] for h in self.haps}) for i in range(len(loci))]
+
+
+# --------------------------------------------------------------------------- subjects
+def _gl(loci_sides):
+    return "^".join("/".join(a) + "+" + "/".join(b) for a, b in loci_sides)
+
+
+def typed_subjects(table, n, seed, races=None, prefix="S"):
+    """Fully typed, unambiguous; the two haplotypes are drawn proportional to frequency so
+    Plan A hits (C2).  races: None, or a list of race-field generators cycled per subject."""
+    rng = np.random.RandomState(seed)
+    idx = rng.choice(len(table.haps), size=(n, 2), p=table.p)
+    flip = rng.rand(n, len(table.loci)) < 0.5
+    out = []
+    for s in range(n):
+        h1, h2 = table.haps[idx[s, 0]], table.haps[idx[s, 1]]
+        sides = []
+        for l in range(len(table.loci)):
+            a, b = (h2[l], h1[l]) if flip[s, l] else (h1[l], h2[l])
+            sides.append(([a], [b]))
+        line = "%s%d,%s" % (prefix, s, _gl(sides))
+        if races is not None:
+            line += "," + races[s % len(races)]
+        out.append(line + "\n")
+    return out
+
+
+def messy_subjects(table, n, seed, max_amb=4, p_missing=0.25, p_unknown=0.05, p_random=0.15,
+                   races=None, prefix="M"):
+    """Ambiguous / missing-loci / unknown-allele subjects (C4-like, small enough for the CPU
+    oracle): each locus side lists the true allele plus up to max_amb-1 others; loci are
+    dropped with probability p_missing (at least one kept); alleles are replaced by a name
+    absent from the table with probability p_unknown; with probability p_random a side is a
+    random allele instead of one from a table haplotype (pushes subjects into Plan B/C)."""
+    rng = np.random.RandomState(seed)
+    out = []
+    nl = len(table.loci)
+    for s in range(n):
+        i1, i2 = rng.choice(len(table.haps), size=2, p=table.p)
+        h1, h2 = list(table.haps[i1]), list(table.haps[i2])
+        keep = rng.rand(nl) >= p_missing
+        if not keep.any():
+            keep[rng.randint(nl)] = True
+        sides = []
+        for l in range(nl):
+            if not keep[l]:
+                continue
+            pair = []
+            for h in (h1, h2):
+                a = h[l]
+                if rng.rand() < p_random:
+                    a = table.alleles[l][rng.randint(len(table.alleles[l]))]
+                if rng.rand() < p_unknown:
+                    a = "%s*99:%02d" % (table.loci[l], rng.randint(1, 4))
+                lst = [a]
+                for _ in range(rng.randint(0, max_amb)):
+                    b = table.alleles[l][rng.randint(len(table.alleles[l]))]
+                    if b not in lst:
+                        lst.append(b)
+                rng.shuffle(lst)
+                pair.append(lst)
+            if rng.rand() < 0.5:
+                pair.reverse()
+            sides.append((pair[0], pair[1]))
+        line = "%s%d,%s" % (prefix, s, _gl(sides))
+        if races is not None:
+            line += "," + races[rng.randint(len(races))]
+        out.append(line + "\n")
+    return out
+
+
+def race_fields(pops):
+    """A small cycle of race1,race2 field shapes: both known, one ';' list,
+    unknown code, empty."""
+    p = list(pops)
+    k = len(p)
+    return [
+        "%s,%s" % (p[0], p[1 % k]),
+        "%s;%s,%s" % (p[0], p[2 % k], p[1 % k]),
+        "%s,%s" % (p[1 % k], p[1 % k]),
+        "XXX,%s" % p[2 % k],
+        ",",
+        "%s,XXX;YYY" % p[0],
+    ]
