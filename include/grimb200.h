@@ -1,0 +1,193 @@
+/*
+ * grimb200.h -- C ABI of libgrimb200.so, the B200 (sm_100a) implementation of the GRIM
+ * per-subject imputation hot path.
+ *
+ * The reference (nmdp-bioinformatics/py-graph-imputation) has no FFI: its seams are Python
+ * call signatures.  Each entry point below names the reference interface it stands in for
+ * (paths relative to the reference root).  The Python host in
+ * py-graph-imputation_b200/grim/ binds these with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a
+ * negative GRIMB_E_* code (text via grimb_last_error()); no C++ exception crosses the
+ * boundary; per-subject failures are status codes in the result arrays, never call failures.
+ * The caller owns every buffer it passes; the library owns GrimbTables and GrimbEngine.
+ */
+#ifndef GRIMB200_H
+#define GRIMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRIMB_ABI_VERSION 1
+#define GRIMB_MAX_LOCI 9
+#define GRIMB_MAX_ROWS 16
+#define GRIMB_MAX_BLOCKS 9
+
+/* error codes */
+#define GRIMB_OK 0
+#define GRIMB_E_ARG (-1)      /* bad argument */
+#define GRIMB_E_CUDA (-2)     /* CUDA runtime error (no device, launch failure, ...) */
+#define GRIMB_E_NOMEM (-3)
+#define GRIMB_E_LAYOUT (-4)   /* allele ids do not fit the packed key */
+#define GRIMB_E_CAPACITY (-5) /* caller-provided result buffers too small; see grimb_impute_* */
+
+/* per-subject status (GrimbResults.status) */
+#define GRIMB_ST_OK 0          /* rows written (possibly zero rows: reference writes .miss) */
+#define GRIMB_ST_FAULT 2       /* the reference raises inside this subject -> raw line in .problem */
+#define GRIMB_ST_WORKSPACE 3   /* per-CTA workspace too small: re-issue with a bigger workspace */
+#define GRIMB_ST_SKIPPED 4     /* not processed (host marked it unparsable: .problem "i,id") */
+
+/* plan that produced the rows (impute.py:216,1638,1702), per output kind */
+#define GRIMB_PLAN_NONE 0
+#define GRIMB_PLAN_A 1
+#define GRIMB_PLAN_B 2
+#define GRIMB_PLAN_C 3
+
+typedef struct GrimbTables GrimbTables; /* device-resident frequency store (one per device) */
+typedef struct GrimbEngine GrimbEngine; /* per-device workspaces + stream for imputation    */
+
+/* ------------------------------------------------------------------------------------------
+ * Frequency store.  Replaces graph_generation/generate_neo4j_multi_hpf.py:209-486
+ * (generate_graph: marginal nodes, sequential sums, top links, parent edges) and
+ * grim/imputation/networkx_graph.py:42-213 (Graph.build_graph: dicts + CSR), including the
+ * CSR sentinel quirk at networkx_graph.py:195-196.  Node ids equal the reference's
+ * haplotypeId column.  Input = the unique full haplotypes of hpf.csv after trimming, in
+ * first-appearance order, as allele ids (1-based per locus, locus order = loci_map index).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t n_loci;                         /* L, 1..GRIMB_MAX_LOCI                             */
+  int32_t n_pops;                         /* P                                                */
+  int64_t n_full;                         /* number of full haplotypes                        */
+  const uint16_t* full_alleles;           /* [n_full][L] host, ids 1..n_alleles[l]            */
+  const double* full_freqs;               /* [n_full][P] host                                 */
+  int32_t n_alleles[GRIMB_MAX_LOCI];      /* table alleles per locus                          */
+  int32_t key_bits[GRIMB_MAX_LOCI];       /* packed-key field width per locus (sum <= 63)     */
+  int32_t last_parent_locus;              /* locus whose connector is created last (T1), or -1 to derive L-2 */
+  int32_t device;                         /* CUDA device ordinal                              */
+} GrimbTableDesc;
+
+int grimb_abi_version(void);
+const char* grimb_last_error(void);
+
+int grimb_tables_build(const GrimbTableDesc* desc, GrimbTables** out);
+int grimb_tables_free(GrimbTables* t);
+
+/* Sizes, for tests / export / broadcast: n_nodes, n_full, n_toplinks, n_conn_edges, n_slots */
+typedef struct {
+  int32_t n_loci, n_pops;
+  int64_t n_nodes, n_full, n_toplinks, n_conn_edges, n_slots, device_bytes;
+} GrimbTableInfo;
+int grimb_tables_info(const GrimbTables* t, GrimbTableInfo* info);
+
+/* Copies table arrays to host buffers (any pointer may be NULL).  node_key: packed alleles of
+ * node id i; node_freq [n_nodes][P]; tl_start/tl_cnt [n_nodes] and tl_adj [n_toplinks] = top
+ * links (networkx_graph.py:253-278 view); cn_start/cn_cnt [n_nodes][L] and cn_adj = connector
+ * parents for (child node, added locus) (networkx_graph.py:280-307 view); label_first/count
+ * [1<<L] node-id range per locus-subset mask (haps_by_label, networkx_graph.py:215-236). */
+int grimb_tables_export(const GrimbTables* t, uint64_t* node_key, double* node_freq,
+                        uint32_t* tl_start, uint32_t* tl_cnt, uint32_t* tl_adj,
+                        uint32_t* cn_start, uint32_t* cn_cnt, uint32_t* cn_adj,
+                        uint32_t* label_first, uint32_t* label_count);
+
+/* Raw device image of the tables for replication across GPUs (one ncclBroadcast of this
+ * buffer per peer): size, then copy out / build from an image on another device. */
+int grimb_tables_image_size(const GrimbTables* t, int64_t* bytes);
+int grimb_tables_image_ptr(const GrimbTables* t, void** dev_ptr);        /* device pointer */
+int grimb_tables_from_image(const void* dev_image, int64_t bytes, int device, GrimbTables** out);
+
+/* ------------------------------------------------------------------------------------------
+ * Imputation.  Replaces Imputation.impute_one / comp_cand and everything below them
+ * (grim/imputation/impute.py:1584-1724, 1940-1983) for a batch of already-tokenised subjects,
+ * plus the top-N selection of write_best_prob / write_best_prob_genotype (impute.py:24-76).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  /* run_impute_def.py:63-129 keys */
+  double epsilon;                     /* "epsilon"                                            */
+  double factor_missing_pow[GRIMB_MAX_LOCI + 1]; /* factor_missing_data ** k, k = 0..L (host pow) */
+  int64_t options_threshold;          /* "number_of_options_threshold"                        */
+  int32_t max_haps_in_phase;          /* "max_haplotypes_number_in_phase" (<= 512)            */
+  int32_t n_results;                  /* "number_of_results"                                  */
+  int32_t n_pop_results;              /* "number_of_pop_results"                              */
+  int32_t planb;                      /* "planb"                                              */
+  int32_t output_umug;                /* "output_MUUG"                                        */
+  int32_t output_pmug;                /* "output_haplotypes"                                  */
+  int32_t save_space;                 /* "save_space_mode"                                    */
+  int32_t compensated_sum;            /* 1: Python's sum() of floats is Neumaier-compensated (CPython >= 3.12),
+                                         0: plain left-to-right adds (older CPython); affects
+                                         allel_to_SR (impute.py:1260-1262) and save-space pruning (:1053) */
+  /* "Plan_B_Matrix": rows of blocks, each block a locus bitmask (bit l = loci_map index l+1) */
+  int32_t n_rows;
+  int32_t row_blocks[GRIMB_MAX_ROWS];
+  uint16_t block_mask[GRIMB_MAX_ROWS][GRIMB_MAX_BLOCKS];
+  uint8_t row_is_plan_a[GRIMB_MAX_ROWS]; /* impute.py:1118: block 0 == list(set(loci indices)) */
+} GrimbConfig;
+
+/* A batch of subjects, tokenised by the host (replaces the string handling of
+ * clean_up_gl / gl2haps, impute.py:105-118,246-272).  All pointers are DEVICE pointers for
+ * grimb_impute_device and HOST pointers for grimb_impute_host. */
+typedef struct {
+  int64_t n_subjects;
+  const uint16_t* typed_mask;   /* [S] bit l set = locus l typed; 0 = skip subject (GRIMB_ST_SKIPPED) */
+  const uint16_t* counts;       /* [S][L][2] alleles listed per locus and chromosome side           */
+  const uint32_t* allele_off;   /* [S+1] offset of the subject's allele ids in `alleles`            */
+  const uint16_t* alleles;      /* ids, per subject: locus ascending, side 0 then 1; ids > n_alleles[l]
+                                   are subject-local names of alleles absent from the table        */
+  int64_t n_alleles_total;      /* allele_off[S]                                                    */
+  const uint32_t* prior_index;  /* [S] row of `priors`                                              */
+  const double* priors;         /* [n_priors][P][P] prior matrices (impute.py:1844-1924,1956-1959)  */
+  int32_t n_priors;
+} GrimbBatch;
+
+/* Result rows.  A hap row is two packed keys + probability: for UMUG the per-locus (min id,
+ * max id) pair of the genotype (impute.py:497-504; the host orders each pair as strings), for
+ * PMUG the two haplotypes in first-seen orientation (impute.py:28-38,651). */
+typedef struct { uint64_t a, b; double prob; } GrimbHapRow;
+typedef struct { uint16_t pop_a, pop_b; uint32_t pad; double prob; } GrimbPopRow;
+
+typedef struct {
+  /* per subject, [S] */
+  uint8_t* status;        /* GRIMB_ST_*                                                  */
+  uint8_t* plan_umug;     /* GRIMB_PLAN_*                                                */
+  uint8_t* plan_pmug;
+  uint32_t* n_umug;       /* rows written (<= n_results)                                 */
+  uint32_t* n_pmug;
+  uint32_t* n_umug_pops;  /* rows written (<= n_pop_results); 0xFFFFFFFF = the Plan-C "all_pops" row */
+  uint32_t* n_pmug_pops;
+  uint32_t* tot_umug;     /* len(res_muugs["Haps"]) before top-N (the count the reference prints) */
+  uint32_t* tot_pmug;     /* len(res_haps["Haps"])                                       */
+  uint64_t* hap_off;      /* first UMUG row in hap_rows; PMUG rows follow                */
+  uint64_t* pop_off;      /* first UMUG pop row in pop_rows; PMUG pop rows follow        */
+  uint64_t* pair_evals;   /* iterations reaching impute.py:464/573 (metric numerator)    */
+  /* packed rows */
+  GrimbHapRow* hap_rows;  int64_t hap_capacity;
+  GrimbPopRow* pop_rows;  int64_t pop_capacity;
+  /* totals written by the call (host memory, always): rows needed; > capacity => GRIMB_E_CAPACITY */
+  int64_t* hap_rows_needed;
+  int64_t* pop_rows_needed;
+} GrimbResults;
+
+int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes_per_cta, GrimbEngine** out);
+int grimb_engine_free(GrimbEngine* e);
+
+/* Device-pointer form: batch and result arrays already in HBM; asynchronous on `cuda_stream`
+ * (a cudaStream_t, 0 = engine stream) except for the two *_needed totals, which are read back
+ * (one 16-byte copy) before returning. */
+int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch,
+                        GrimbResults* res, void* cuda_stream);
+
+/* Host-pointer form: copies the batch in, runs, copies the results out (pinned staging owned
+ * by the engine).  This is the call the Python drop-in makes per chunk of input lines. */
+int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch,
+                      GrimbResults* res);
+
+/* Number of kernel launches issued by this engine so far (bench.py's gpu_launches). */
+int64_t grimb_engine_launches(const GrimbEngine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRIMB200_H */

@@ -1,0 +1,813 @@
+// grimb200.cu -- libgrimb200.so: C ABI (include/grimb200.h), device table build (K0) and the
+// imputation kernel launcher.  Compile for sm_100a with -fmad=false (FP64 operation order must
+// match the reference's Python floats; see grimb_subject.h).
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "grimb_plan.h"
+
+using namespace grimb;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(GRIMB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+  } while (0)
+
+extern "C" int grimb_abi_version(void) { return GRIMB_ABI_VERSION; }
+extern "C" const char* grimb_last_error(void) { return g_err.c_str(); }
+
+// ------------------------------------------------------------------------------------------
+// table image: one device allocation = header + arrays (so one broadcast replicates it)
+// ------------------------------------------------------------------------------------------
+struct ImageHeader {
+  uint64_t magic;
+  int32_t L, P;
+  uint32_t n_nodes, n_full;
+  uint8_t shift[9];
+  uint8_t width[9];
+  uint32_t n_alleles[9];
+  uint64_t n_toplinks, n_conn_edges, n_slots, bytes;
+  // byte offsets from the image base
+  uint64_t o_label_first, o_label_count, o_ht_off, o_ht_mask, o_slots, o_node_key, o_freq, o_tl_start,
+      o_tl_cnt, o_tl_adj, o_cn_start, o_cn_cnt, o_cn_adj;
+};
+static const uint64_t IMAGE_MAGIC = 0x4752494d42323030ULL;  // "GRIMB200"
+
+struct GrimbTables {
+  int device;
+  char* image;  // device
+  ImageHeader h;
+  TablesView view;
+};
+
+static void make_view(GrimbTables* t) {
+  const ImageHeader& h = t->h;
+  TablesView& v = t->view;
+  v.L = h.L;
+  v.P = h.P;
+  v.n_nodes = h.n_nodes;
+  v.n_full = h.n_full;
+  memcpy(v.shift, h.shift, 9);
+  memcpy(v.width, h.width, 9);
+  memcpy(v.n_alleles, h.n_alleles, sizeof(h.n_alleles));
+  char* b = t->image;
+  v.label_first = (const uint32_t*)(b + h.o_label_first);
+  v.label_count = (const uint32_t*)(b + h.o_label_count);
+  v.ht_off = (const uint64_t*)(b + h.o_ht_off);
+  v.ht_mask = (const uint32_t*)(b + h.o_ht_mask);
+  v.slots = (const HSlot*)(b + h.o_slots);
+  v.node_key = (const uint64_t*)(b + h.o_node_key);
+  v.freq = (const double*)(b + h.o_freq);
+  v.tl_start = (const uint32_t*)(b + h.o_tl_start);
+  v.tl_cnt = (const uint32_t*)(b + h.o_tl_cnt);
+  v.tl_adj = (const uint32_t*)(b + h.o_tl_adj);
+  v.cn_start = (const uint32_t*)(b + h.o_cn_start);
+  v.cn_cnt = (const uint32_t*)(b + h.o_cn_cnt);
+  v.cn_adj = (const uint32_t*)(b + h.o_cn_adj);
+}
+
+// ------------------------------------------------------------------------------------------
+// K0: table build kernels
+// ------------------------------------------------------------------------------------------
+__global__ void k_pack_full(const uint16_t* al, int L, const uint8_t* shift, uint64_t n, uint64_t* keys) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t k = 0;
+  for (int l = 0; l < L; ++l) k |= (uint64_t)al[i * L + l] << shift[l];
+  keys[i] = k;
+}
+
+__global__ void k_project(const uint64_t* keys, uint64_t mask, uint32_t base, uint32_t n, uint64_t* out, uint32_t* idx) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = keys[i] & mask;
+  idx[i] = base + i;
+}
+
+__global__ void k_heads(const uint64_t* sorted, uint32_t n, uint32_t* flag) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  flag[i] = (i == 0 || sorted[i] != sorted[i - 1]) ? 1u : 0u;
+}
+
+// segment s (in key-sorted order) starts at position head_pos[s]; its first member's rank orders
+// the label's nodes (first appearance in hpf order)
+__global__ void k_seg_heads(const uint32_t* flag, const uint32_t* seg_of, const uint32_t* sorted_idx, uint32_t n,
+                            uint32_t* head_pos, uint32_t* first_rank, uint32_t* seg_iota) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  uint32_t s = seg_of[i];
+  head_pos[s] = i;
+  first_rank[s] = sorted_idx[i];
+  seg_iota[s] = s;
+}
+
+// node r of the label (r = rank of the segment by first appearance): key, top-link range and the
+// SEQUENTIAL sum of the members' frequency vectors in hpf order (generate_neo4j_multi_hpf.py:405)
+__global__ void k_label_nodes(const uint32_t* seg_by_rank, const uint32_t* head_pos, uint32_t nseg, uint32_t n,
+                              const uint64_t* sorted_keys, const uint32_t* sorted_idx, const double* full_freq, int P,
+                              uint32_t node_base, uint32_t tl_base, uint64_t* node_key, double* freq,
+                              uint32_t* tl_start, uint32_t* tl_cnt) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nseg * (uint32_t)P) return;
+  uint32_t r = q / P, p = q % P;
+  uint32_t s = seg_by_rank[r];
+  uint32_t b0 = head_pos[s], b1 = (s + 1 < nseg) ? head_pos[s + 1] : n;
+  double acc = 0.0 + full_freq[(uint64_t)sorted_idx[b0] * P + p];
+  for (uint32_t i = b0 + 1; i < b1; ++i) acc = acc + full_freq[(uint64_t)sorted_idx[i] * P + p];
+  uint32_t node = node_base + r;
+  freq[(uint64_t)node * P + p] = acc;
+  if (p == 0) {
+    node_key[node] = sorted_keys[b0];
+    tl_start[node] = tl_base + b0;
+    tl_cnt[node] = b1 - b0;
+  }
+}
+
+__global__ void k_full_nodes(const uint64_t* keys, const double* full_freq, uint32_t n, int P, uint64_t* node_key,
+                             double* freq, uint32_t* tl_start, uint32_t* tl_cnt) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  node_key[i] = keys[i];
+  tl_start[i] = 0;
+  tl_cnt[i] = 0;
+  for (int p = 0; p < P; ++p) freq[(uint64_t)i * P + p] = full_freq[(uint64_t)i * P + p];
+}
+
+__global__ void k_init_slots(HSlot* s, uint64_t n) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  s[i].key = ~0ull;
+  s[i].node = GRIMB_NONE;
+  s[i].pad = 0;
+}
+
+__global__ void k_insert(HSlot* slots, uint64_t off, uint32_t mask, const uint64_t* node_key, uint32_t first, uint32_t cnt) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cnt) return;
+  uint32_t node = first + i;
+  uint64_t key = node_key[node];
+  HSlot* base = slots + off;
+  uint32_t h = (uint32_t)mix64(key) & mask;
+  for (;;) {
+    unsigned long long old = atomicCAS((unsigned long long*)&base[h].key, ~0ull, (unsigned long long)key);
+    if (old == ~0ull) {
+      base[h].node = node;
+      return;
+    }
+    h = (h + 1) & mask;
+  }
+}
+
+// connector segments: child key -> (child node, added locus) CSR entry
+__global__ void k_conn_heads(const uint32_t* flag, const uint64_t* sorted_child, uint32_t n, TablesView T, uint32_t child_label,
+                             int locus, uint32_t cn_base, uint32_t* cn_start, uint32_t* cn_cnt, const uint32_t* next_head,
+                             unsigned int* n_conn) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  uint32_t child = ht_lookup(T, child_label, sorted_child[i]);
+  if (child == GRIMB_NONE) return;  // cannot happen: every projection of a node is a node
+  uint32_t end = next_head[i];
+  cn_start[(uint64_t)child * T.L + locus] = cn_base + i;
+  cn_cnt[(uint64_t)child * T.L + locus] = end - i;
+  atomicAdd(n_conn, 1u);
+}
+
+// next_head[i] for head positions: position of the following head (or n)
+__global__ void k_next_head(const uint32_t* flag, uint32_t n, uint32_t* next_head) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  uint32_t j = i + 1;
+  while (j < n && !flag[j]) ++j;
+  next_head[i] = j;
+}
+
+__global__ void k_add_u32(uint32_t* a, uint32_t n, uint32_t v) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] += v;
+}
+
+static inline unsigned nblk(uint64_t n, unsigned t = 256) { return (unsigned)((n + t - 1) / t); }
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+};
+
+static std::vector<uint32_t> label_order(int L) {
+  // full label, then subsets of decreasing size in itertools.combinations order
+  // (generate_neo4j_multi_hpf.py:105-110)
+  std::vector<uint32_t> out;
+  out.push_back((1u << L) - 1u);
+  for (int r = L - 1; r >= 1; --r) {
+    std::vector<int> c(r);
+    for (int i = 0; i < r; ++i) c[i] = i;
+    for (;;) {
+      uint32_t m = 0;
+      for (int i = 0; i < r; ++i) m |= 1u << c[i];
+      out.push_back(m);
+      int i = r - 1;
+      while (i >= 0 && c[i] == L - r + i) --i;
+      if (i < 0) break;
+      ++c[i];
+      for (int j = i + 1; j < r; ++j) c[j] = c[j - 1] + 1;
+    }
+  }
+  return out;
+}
+
+static uint64_t host_key_mask(const ImageHeader& h, uint32_t label) {
+  uint64_t m = 0;
+  for (int l = 0; l < h.L; ++l)
+    if (label >> l & 1u) m |= ((1ull << h.width[l]) - 1ull) << h.shift[l];
+  return m;
+}
+
+// reference quirk: the closing CSR sentinel is len(Vertices) (networkx_graph.py:195-196)
+static uint32_t sentinel_count(uint64_t own, uint64_t n_edges, uint64_t n_vertices) {
+  uint64_t start = n_edges - own;
+  if (n_vertices <= start) return 0;
+  if (n_vertices > n_edges) return GRIMB_ADJ_FAULT;
+  return (uint32_t)(n_vertices - start);
+}
+
+extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
+  if (!d || !out) return fail(GRIMB_E_ARG, "null argument");
+  const int L = d->n_loci, P = d->n_pops;
+  if (L < 1 || L > GRIMB_MAX_LOCI || P < 1) return fail(GRIMB_E_ARG, "bad n_loci / n_pops");
+  if (d->n_full < 0 || d->n_full > 0x7FFFFFF0ll) return fail(GRIMB_E_ARG, "bad n_full");
+  int bits = 0;
+  for (int l = 0; l < L; ++l) {
+    if (d->key_bits[l] < 1 || d->key_bits[l] > 16) return fail(GRIMB_E_LAYOUT, "key_bits must be 1..16");
+    if ((1ll << d->key_bits[l]) <= d->n_alleles[l]) return fail(GRIMB_E_LAYOUT, "allele ids do not fit key_bits");
+    bits += d->key_bits[l];
+  }
+  if (bits > 63) return fail(GRIMB_E_LAYOUT, "packed key exceeds 63 bits");
+  CK(cudaSetDevice(d->device));
+  const uint32_t N = (uint32_t)d->n_full;
+  const uint32_t NL = 1u << L;
+
+  GrimbTables* t = new GrimbTables();
+  t->device = d->device;
+  t->image = nullptr;
+  ImageHeader& h = t->h;
+  memset(&h, 0, sizeof(h));
+  h.magic = IMAGE_MAGIC;
+  h.L = L;
+  h.P = P;
+  h.n_full = N;
+  int sh = 0;
+  for (int l = 0; l < L; ++l) {
+    h.shift[l] = (uint8_t)sh;
+    h.width[l] = (uint8_t)d->key_bits[l];
+    h.n_alleles[l] = (uint32_t)d->n_alleles[l];
+    sh += d->key_bits[l];
+  }
+
+  // ---- stage inputs
+  DevBuf b_al, b_ff, b_keys, b_shift;
+  cudaError_t e;
+#define CKB(call)                                                                                 \
+  do {                                                                                            \
+    e = (call);                                                                                   \
+    if (e != cudaSuccess) {                                                                       \
+      delete t;                                                                                   \
+      return fail(GRIMB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e));               \
+    }                                                                                             \
+  } while (0)
+  CKB(b_al.reserve((size_t)N * L * 2));
+  CKB(b_ff.reserve((size_t)N * P * 8));
+  CKB(b_keys.reserve((size_t)N * 8));
+  CKB(b_shift.reserve(16));
+  CKB(cudaMemcpy(b_al.p, d->full_alleles, (size_t)N * L * 2, cudaMemcpyHostToDevice));
+  CKB(cudaMemcpy(b_ff.p, d->full_freqs, (size_t)N * P * 8, cudaMemcpyHostToDevice));
+  CKB(cudaMemcpy(b_shift.p, h.shift, 9, cudaMemcpyHostToDevice));
+  if (N) k_pack_full<<<nblk(N), 256>>>((const uint16_t*)b_al.p, L, (const uint8_t*)b_shift.p, N, (uint64_t*)b_keys.p);
+  CKB(cudaGetLastError());
+
+  // ---- pass 1 over labels: sort projections, count nodes, keep per-label results
+  const std::vector<uint32_t> order = label_order(L);
+  struct PerLabel {
+    uint32_t nseg = 0;
+    uint64_t* keys = nullptr;   // [nseg] node keys in node order
+    double* freq = nullptr;     // [nseg][P]
+    uint32_t* tls = nullptr;    // [nseg] top-link start relative to the label's block
+    uint32_t* tlc = nullptr;    // [nseg]
+    uint32_t* adj = nullptr;    // [N] sorted full ids
+  };
+  std::vector<PerLabel> pl(order.size());
+  auto free_pl = [&]() {
+    for (auto& x : pl) {
+      cudaFree(x.keys);
+      cudaFree(x.freq);
+      cudaFree(x.tls);
+      cudaFree(x.tlc);
+      cudaFree(x.adj);
+    }
+  };
+  DevBuf b_pk, b_pi, b_sk, b_si, b_flag, b_seg, b_head, b_rank, b_iota, b_rank2, b_iota2, b_tmp, b_tmp2;
+  CKB(b_pk.reserve((size_t)N * 8));
+  CKB(b_pi.reserve((size_t)N * 4));
+  CKB(b_sk.reserve((size_t)N * 8));
+  CKB(b_si.reserve((size_t)N * 4));
+  CKB(b_flag.reserve((size_t)N * 4));
+  CKB(b_seg.reserve((size_t)N * 4));
+  CKB(b_head.reserve((size_t)N * 4));
+  CKB(b_rank.reserve((size_t)N * 4));
+  CKB(b_iota.reserve((size_t)N * 4));
+  CKB(b_rank2.reserve((size_t)N * 4));
+  CKB(b_iota2.reserve((size_t)N * 4));
+  size_t tb1 = 0, tb2 = 0, tb3 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb1, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)N);
+  cub::DeviceRadixSort::SortPairs(nullptr, tb2, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)N);
+  cub::DeviceScan::ExclusiveSum(nullptr, tb3, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)N);
+  size_t tb = tb1 > tb2 ? tb1 : tb2;
+  tb = tb > tb3 ? tb : tb3;
+  CKB(b_tmp.reserve(tb + 16));
+
+  uint64_t n_nodes = N;
+  for (size_t li = 1; li < order.size() && N > 0; ++li) {
+    const uint64_t km = host_key_mask(h, order[li]);
+    k_project<<<nblk(N), 256>>>((const uint64_t*)b_keys.p, km, 0u, N, (uint64_t*)b_pk.p, (uint32_t*)b_pi.p);
+    size_t tbx = b_tmp.cap;
+    CKB(cub::DeviceRadixSort::SortPairs(b_tmp.p, tbx, (uint64_t*)b_pk.p, (uint64_t*)b_sk.p, (uint32_t*)b_pi.p,
+                                        (uint32_t*)b_si.p, (int)N, 0, sh));
+    k_heads<<<nblk(N), 256>>>((const uint64_t*)b_sk.p, N, (uint32_t*)b_flag.p);
+    tbx = b_tmp.cap;
+    CKB(cub::DeviceScan::ExclusiveSum(b_tmp.p, tbx, (uint32_t*)b_flag.p, (uint32_t*)b_seg.p, (int)N));
+    uint32_t last_flag = 0, last_seg = 0;
+    CKB(cudaMemcpy(&last_flag, (uint32_t*)b_flag.p + (N - 1), 4, cudaMemcpyDeviceToHost));
+    CKB(cudaMemcpy(&last_seg, (uint32_t*)b_seg.p + (N - 1), 4, cudaMemcpyDeviceToHost));
+    const uint32_t nseg = last_seg + last_flag;
+    PerLabel& x = pl[li];
+    x.nseg = nseg;
+    k_seg_heads<<<nblk(N), 256>>>((const uint32_t*)b_flag.p, (const uint32_t*)b_seg.p, (const uint32_t*)b_si.p, N,
+                                  (uint32_t*)b_head.p, (uint32_t*)b_rank.p, (uint32_t*)b_iota.p);
+    tbx = b_tmp.cap;
+    CKB(cub::DeviceRadixSort::SortPairs(b_tmp.p, tbx, (uint32_t*)b_rank.p, (uint32_t*)b_rank2.p, (uint32_t*)b_iota.p,
+                                        (uint32_t*)b_iota2.p, (int)nseg));
+    CKB(cudaMalloc(&x.keys, (size_t)nseg * 8));
+    CKB(cudaMalloc(&x.freq, (size_t)nseg * P * 8));
+    CKB(cudaMalloc(&x.tls, (size_t)nseg * 4));
+    CKB(cudaMalloc(&x.tlc, (size_t)nseg * 4));
+    CKB(cudaMalloc(&x.adj, (size_t)N * 4));
+    k_label_nodes<<<nblk((uint64_t)nseg * P), 256>>>((const uint32_t*)b_iota2.p, (const uint32_t*)b_head.p, nseg, N,
+                                                     (const uint64_t*)b_sk.p, (const uint32_t*)b_si.p,
+                                                     (const double*)b_ff.p, P, 0u, 0u, x.keys, x.freq, x.tls, x.tlc);
+    CKB(cudaMemcpy(x.adj, b_si.p, (size_t)N * 4, cudaMemcpyDeviceToDevice));
+    CKB(cudaGetLastError());
+    n_nodes += nseg;
+  }
+  if (n_nodes > 0x7FFFFFF0ull) {
+    free_pl();
+    delete t;
+    return fail(GRIMB_E_ARG, "too many nodes");
+  }
+  h.n_nodes = (uint32_t)n_nodes;
+  h.n_toplinks = (uint64_t)N * (order.size() - 1);
+
+  // ---- hash region sizes, connector edge count
+  std::vector<uint32_t> lfirst(NL, 0), lcount(NL, 0), hmask(NL, 1);
+  std::vector<uint64_t> hoff(NL, 0);
+  {
+    uint32_t nb = 0;
+    for (size_t li = 0; li < order.size(); ++li) {
+      uint32_t c = li == 0 ? N : pl[li].nseg;
+      lfirst[order[li]] = nb;
+      lcount[order[li]] = c;
+      nb += c;
+    }
+    uint64_t so = 0;
+    for (uint32_t m = 0; m < NL; ++m) {
+      uint32_t sz = 2;
+      while (sz < 2 * (uint64_t)lcount[m]) sz <<= 1;
+      hmask[m] = sz - 1;
+      hoff[m] = so;
+      so += sz;
+    }
+    h.n_slots = so;
+  }
+  uint64_t n_cn = 0;
+  for (uint32_t m = 1; m < NL; ++m)
+    if (__builtin_popcount(m) >= 2) n_cn += (uint64_t)__builtin_popcount(m) * lcount[m];
+  h.n_conn_edges = n_cn;
+
+  // ---- image layout
+  auto al16 = [](uint64_t x) { return (x + 255ull) & ~255ull; };
+  uint64_t o = al16(sizeof(ImageHeader));
+  h.o_label_first = o; o = al16(o + (uint64_t)NL * 4);
+  h.o_label_count = o; o = al16(o + (uint64_t)NL * 4);
+  h.o_ht_off = o; o = al16(o + (uint64_t)NL * 8);
+  h.o_ht_mask = o; o = al16(o + (uint64_t)NL * 4);
+  h.o_slots = o; o = al16(o + h.n_slots * sizeof(HSlot));
+  h.o_node_key = o; o = al16(o + n_nodes * 8);
+  h.o_freq = o; o = al16(o + n_nodes * P * 8);
+  h.o_tl_start = o; o = al16(o + n_nodes * 4);
+  h.o_tl_cnt = o; o = al16(o + n_nodes * 4);
+  h.o_tl_adj = o; o = al16(o + (h.n_toplinks ? h.n_toplinks : 1) * 4);
+  h.o_cn_start = o; o = al16(o + n_nodes * L * 4);
+  h.o_cn_cnt = o; o = al16(o + n_nodes * L * 4);
+  h.o_cn_adj = o; o = al16(o + (n_cn ? n_cn : 1) * 4);
+  h.bytes = o;
+  e = cudaMalloc((void**)&t->image, h.bytes);
+  if (e != cudaSuccess) {
+    free_pl();
+    delete t;
+    return fail(GRIMB_E_NOMEM, std::string("table image: ") + cudaGetErrorString(e));
+  }
+  make_view(t);
+  TablesView& v = t->view;
+#define CKT(call)                                                                   \
+  do {                                                                              \
+    e = (call);                                                                     \
+    if (e != cudaSuccess) {                                                         \
+      free_pl();                                                                    \
+      cudaFree(t->image);                                                           \
+      delete t;                                                                     \
+      return fail(GRIMB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e)); \
+    }                                                                               \
+  } while (0)
+  CKT(cudaMemset(t->image, 0, h.bytes));
+  CKT(cudaMemcpy((void*)v.label_first, lfirst.data(), (size_t)NL * 4, cudaMemcpyHostToDevice));
+  CKT(cudaMemcpy((void*)v.label_count, lcount.data(), (size_t)NL * 4, cudaMemcpyHostToDevice));
+  CKT(cudaMemcpy((void*)v.ht_off, hoff.data(), (size_t)NL * 8, cudaMemcpyHostToDevice));
+  CKT(cudaMemcpy((void*)v.ht_mask, hmask.data(), (size_t)NL * 4, cudaMemcpyHostToDevice));
+
+  // ---- assemble node arrays
+  if (N)
+    k_full_nodes<<<nblk(N), 256>>>((const uint64_t*)b_keys.p, (const double*)b_ff.p, N, P, (uint64_t*)v.node_key,
+                                   (double*)v.freq, (uint32_t*)v.tl_start, (uint32_t*)v.tl_cnt);
+  {
+    uint64_t tl_base = 0;
+    for (size_t li = 1; li < order.size() && N > 0; ++li) {
+      PerLabel& x = pl[li];
+      uint32_t nb = lfirst[order[li]];
+      CKT(cudaMemcpy((uint64_t*)v.node_key + nb, x.keys, (size_t)x.nseg * 8, cudaMemcpyDeviceToDevice));
+      CKT(cudaMemcpy((double*)v.freq + (uint64_t)nb * P, x.freq, (size_t)x.nseg * P * 8, cudaMemcpyDeviceToDevice));
+      CKT(cudaMemcpy((uint32_t*)v.tl_cnt + nb, x.tlc, (size_t)x.nseg * 4, cudaMemcpyDeviceToDevice));
+      CKT(cudaMemcpy((uint32_t*)v.tl_adj + tl_base, x.adj, (size_t)N * 4, cudaMemcpyDeviceToDevice));
+      // starts are relative to the label's block: copy, then rebase
+      CKT(cudaMemcpy((uint32_t*)v.tl_start + nb, x.tls, (size_t)x.nseg * 4, cudaMemcpyDeviceToDevice));
+      if (tl_base) k_add_u32<<<nblk(x.nseg), 256>>>((uint32_t*)v.tl_start + nb, x.nseg, (uint32_t)tl_base);
+      tl_base += N;
+    }
+  }
+  CKT(cudaGetLastError());
+  free_pl();
+
+  // ---- hash insert
+  k_init_slots<<<nblk(h.n_slots), 256>>>((HSlot*)v.slots, h.n_slots);
+  for (uint32_t m = 1; m < NL; ++m)
+    if (lcount[m])
+      k_insert<<<nblk(lcount[m]), 256>>>((HSlot*)v.slots, hoff[m], hmask[m], v.node_key, lfirst[m], lcount[m]);
+  CKT(cudaGetLastError());
+  CKT(cudaDeviceSynchronize());
+
+  // ---- connectors: for every label B (>= 2 loci) and locus l in B, group B's nodes by B \ l
+  unsigned int* d_nconn = nullptr;
+  CKT(cudaMalloc(&d_nconn, 4));
+  CKT(cudaMemset(d_nconn, 0, 4));
+  {
+    uint64_t cn_base = 0;
+    for (size_t li = 0; li < order.size(); ++li) {
+      const uint32_t B = order[li];
+      const uint32_t nB = lcount[B];
+      if (__builtin_popcount(B) < 2 || nB == 0) continue;
+      for (int l = 0; l < L; ++l) {
+        if (!(B >> l & 1u)) continue;
+        const uint32_t A = B & ~(1u << l);
+        const uint64_t km = host_key_mask(h, A);
+        k_project<<<nblk(nB), 256>>>(v.node_key + lfirst[B], km, lfirst[B], nB, (uint64_t*)b_pk.p, (uint32_t*)b_pi.p);
+        size_t tbx = b_tmp.cap;
+        CKT(cub::DeviceRadixSort::SortPairs(b_tmp.p, tbx, (uint64_t*)b_pk.p, (uint64_t*)b_sk.p, (uint32_t*)b_pi.p,
+                                            (uint32_t*)b_si.p, (int)nB, 0, sh));
+        k_heads<<<nblk(nB), 256>>>((const uint64_t*)b_sk.p, nB, (uint32_t*)b_flag.p);
+        k_next_head<<<nblk(nB), 256>>>((const uint32_t*)b_flag.p, nB, (uint32_t*)b_head.p);
+        k_conn_heads<<<nblk(nB), 256>>>((const uint32_t*)b_flag.p, (const uint64_t*)b_sk.p, nB, v, A, l, (uint32_t)cn_base,
+                                        (uint32_t*)v.cn_start, (uint32_t*)v.cn_cnt, (const uint32_t*)b_head.p, d_nconn);
+        CKT(cudaMemcpy((uint32_t*)v.cn_adj + cn_base, b_si.p, (size_t)nB * 4, cudaMemcpyDeviceToDevice));
+        cn_base += nB;
+      }
+    }
+  }
+  CKT(cudaGetLastError());
+  CKT(cudaDeviceSynchronize());
+  unsigned int n_conn = 0;
+  CKT(cudaMemcpy(&n_conn, d_nconn, 4, cudaMemcpyDeviceToHost));
+  cudaFree(d_nconn);
+
+  // ---- reference CSR sentinel quirk (networkx_graph.py:195-196; SURVEY trap T1)
+  if (n_nodes > N && N > 0) {
+    const uint32_t last = (uint32_t)n_nodes - 1;
+    uint32_t deg = 0;
+    CKT(cudaMemcpy(&deg, v.tl_cnt + last, 4, cudaMemcpyDeviceToHost));
+    uint32_t nc = sentinel_count(deg, h.n_toplinks, n_nodes);
+    CKT(cudaMemcpy((uint32_t*)v.tl_cnt + last, &nc, 4, cudaMemcpyHostToDevice));
+    if (L >= 2) {
+      int pl_locus = d->last_parent_locus >= 0 ? d->last_parent_locus : L - 2;
+      uint64_t idx = (uint64_t)last * L + pl_locus;
+      CKT(cudaMemcpy(&deg, v.cn_cnt + idx, 4, cudaMemcpyDeviceToHost));
+      nc = sentinel_count(deg, (uint64_t)n_conn + n_cn, n_nodes + n_conn);
+      CKT(cudaMemcpy((uint32_t*)v.cn_cnt + idx, &nc, 4, cudaMemcpyHostToDevice));
+    }
+  }
+  CKT(cudaMemcpy(t->image, &h, sizeof(h), cudaMemcpyHostToDevice));
+  CKT(cudaDeviceSynchronize());
+  *out = t;
+  return GRIMB_OK;
+}
+
+
+extern "C" int grimb_tables_free(GrimbTables* t) {
+  if (!t) return GRIMB_OK;
+  cudaSetDevice(t->device);
+  cudaFree(t->image);
+  delete t;
+  return GRIMB_OK;
+}
+
+extern "C" int grimb_tables_info(const GrimbTables* t, GrimbTableInfo* info) {
+  if (!t || !info) return fail(GRIMB_E_ARG, "null argument");
+  info->n_loci = t->h.L;
+  info->n_pops = t->h.P;
+  info->n_nodes = t->h.n_nodes;
+  info->n_full = t->h.n_full;
+  info->n_toplinks = (int64_t)t->h.n_toplinks;
+  info->n_conn_edges = (int64_t)t->h.n_conn_edges;
+  info->n_slots = (int64_t)t->h.n_slots;
+  info->device_bytes = (int64_t)t->h.bytes;
+  return GRIMB_OK;
+}
+
+extern "C" int grimb_tables_export(const GrimbTables* t, uint64_t* node_key, double* node_freq, uint32_t* tl_start,
+                                   uint32_t* tl_cnt, uint32_t* tl_adj, uint32_t* cn_start, uint32_t* cn_cnt,
+                                   uint32_t* cn_adj, uint32_t* label_first, uint32_t* label_count) {
+  if (!t) return fail(GRIMB_E_ARG, "null argument");
+  CK(cudaSetDevice(t->device));
+  const ImageHeader& h = t->h;
+  const TablesView& v = t->view;
+  const uint64_t n = h.n_nodes;
+  if (node_key) CK(cudaMemcpy(node_key, v.node_key, n * 8, cudaMemcpyDeviceToHost));
+  if (node_freq) CK(cudaMemcpy(node_freq, v.freq, n * h.P * 8, cudaMemcpyDeviceToHost));
+  if (tl_start) CK(cudaMemcpy(tl_start, v.tl_start, n * 4, cudaMemcpyDeviceToHost));
+  if (tl_cnt) CK(cudaMemcpy(tl_cnt, v.tl_cnt, n * 4, cudaMemcpyDeviceToHost));
+  if (tl_adj) CK(cudaMemcpy(tl_adj, v.tl_adj, h.n_toplinks * 4, cudaMemcpyDeviceToHost));
+  if (cn_start) CK(cudaMemcpy(cn_start, v.cn_start, n * h.L * 4, cudaMemcpyDeviceToHost));
+  if (cn_cnt) CK(cudaMemcpy(cn_cnt, v.cn_cnt, n * h.L * 4, cudaMemcpyDeviceToHost));
+  if (cn_adj) CK(cudaMemcpy(cn_adj, v.cn_adj, h.n_conn_edges * 4, cudaMemcpyDeviceToHost));
+  if (label_first) CK(cudaMemcpy(label_first, v.label_first, (size_t)(1u << h.L) * 4, cudaMemcpyDeviceToHost));
+  if (label_count) CK(cudaMemcpy(label_count, v.label_count, (size_t)(1u << h.L) * 4, cudaMemcpyDeviceToHost));
+  return GRIMB_OK;
+}
+
+extern "C" int grimb_tables_image_size(const GrimbTables* t, int64_t* bytes) {
+  if (!t || !bytes) return fail(GRIMB_E_ARG, "null argument");
+  *bytes = (int64_t)t->h.bytes;
+  return GRIMB_OK;
+}
+
+extern "C" int grimb_tables_image_ptr(const GrimbTables* t, void** dev_ptr) {
+  if (!t || !dev_ptr) return fail(GRIMB_E_ARG, "null argument");
+  *dev_ptr = t->image;
+  return GRIMB_OK;
+}
+
+extern "C" int grimb_tables_from_image(const void* dev_image, int64_t bytes, int device, GrimbTables** out) {
+  if (!dev_image || !out || bytes < (int64_t)sizeof(ImageHeader)) return fail(GRIMB_E_ARG, "bad image");
+  CK(cudaSetDevice(device));
+  GrimbTables* t = new GrimbTables();
+  t->device = device;
+  t->image = nullptr;
+  cudaError_t e = cudaMemcpy(&t->h, dev_image, sizeof(ImageHeader), cudaMemcpyDefault);
+  if (e != cudaSuccess || t->h.magic != IMAGE_MAGIC || (int64_t)t->h.bytes != bytes) {
+    delete t;
+    return fail(GRIMB_E_ARG, "not a grimb200 table image");
+  }
+  e = cudaMalloc((void**)&t->image, (size_t)bytes);
+  if (e != cudaSuccess) {
+    delete t;
+    return fail(GRIMB_E_NOMEM, cudaGetErrorString(e));
+  }
+  e = cudaMemcpy(t->image, dev_image, (size_t)bytes, cudaMemcpyDefault);
+  if (e != cudaSuccess) {
+    cudaFree(t->image);
+    delete t;
+    return fail(GRIMB_E_CUDA, cudaGetErrorString(e));
+  }
+  make_view(t);
+  *out = t;
+  return GRIMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// imputation kernel: persistent CTAs, one subject per CTA at a time, dynamic work fetch
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MAXT)
+k_impute(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O, char* arena, uint64_t arena_per_cta,
+         const double* ones, unsigned long long* work) {
+  __shared__ Shared sh;
+  Subject S;
+  S.g.tid = threadIdx.x;
+  S.g.n = blockDim.x;
+  S.g.scratch = sh.scratch;
+  S.sh = &sh;
+  S.T = T;
+  S.cfg = cfg;
+  S.ones = ones;
+  S.ar_base = arena + (uint64_t)blockIdx.x * arena_per_cta;
+  S.ar_cap = arena_per_cta;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) sh.work = (uint32_t)atomicAdd(work, 1ull);
+    __syncthreads();
+    const uint64_t s = sh.work;
+    if (s >= (uint64_t)B.n_subjects) break;
+    run_subject(S, B, O, s);
+  }
+}
+
+struct GrimbEngine {
+  const GrimbTables* tables;
+  int device;
+  int threads;
+  int n_ctas;
+  uint64_t arena_per_cta;
+  char* arena = nullptr;
+  double* ones = nullptr;
+  GrimbConfig* d_cfg = nullptr;
+  unsigned long long* d_counters = nullptr;  // [0] work, [1] hap rows, [2] pop rows
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  // staging for the host-pointer form (grow-only)
+  DevBuf in[6], outb[14];
+};
+
+extern "C" int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes_per_cta, GrimbEngine** out) {
+  if (!t || !out || workspace_bytes_per_cta < (1 << 16)) return fail(GRIMB_E_ARG, "bad engine arguments");
+  CK(cudaSetDevice(t->device));
+  GrimbEngine* e = new GrimbEngine();
+  e->tables = t;
+  e->device = t->device;
+  e->threads = 128;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, t->device));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_impute, e->threads, 0));
+  if (per_sm < 1) per_sm = 1;
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  int64_t n = (int64_t)prop.multiProcessorCount * per_sm;
+  e->arena_per_cta = ((uint64_t)workspace_bytes_per_cta + 255ull) & ~255ull;
+  while (n > prop.multiProcessorCount && (uint64_t)n * e->arena_per_cta > free_b / 2) n -= prop.multiProcessorCount;
+  while (n > 1 && (uint64_t)n * e->arena_per_cta > free_b / 2) n /= 2;
+  e->n_ctas = (int)n;
+  cudaError_t ce = cudaMalloc((void**)&e->arena, (uint64_t)e->n_ctas * e->arena_per_cta);
+  if (ce != cudaSuccess) {
+    delete e;
+    return fail(GRIMB_E_NOMEM, std::string("engine arena: ") + cudaGetErrorString(ce));
+  }
+  const int P = t->h.P;
+  std::vector<double> one((size_t)P * P, 1.0);
+  CK(cudaMalloc((void**)&e->ones, one.size() * 8));
+  CK(cudaMemcpy(e->ones, one.data(), one.size() * 8, cudaMemcpyHostToDevice));
+  CK(cudaMalloc((void**)&e->d_cfg, sizeof(GrimbConfig)));
+  CK(cudaMalloc((void**)&e->d_counters, 32));
+  CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  *out = e;
+  return GRIMB_OK;
+}
+
+extern "C" int grimb_engine_free(GrimbEngine* e) {
+  if (!e) return GRIMB_OK;
+  cudaSetDevice(e->device);
+  cudaFree(e->arena);
+  cudaFree(e->ones);
+  cudaFree(e->d_cfg);
+  cudaFree(e->d_counters);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return GRIMB_OK;
+}
+
+extern "C" int64_t grimb_engine_launches(const GrimbEngine* e) { return e ? e->launches : 0; }
+
+static int check_cfg(const GrimbConfig* c, const GrimbTables* t) {
+  if (!(c->epsilon > 0)) return fail(GRIMB_E_ARG, "epsilon must be > 0");
+  if (c->max_haps_in_phase < 1 || c->max_haps_in_phase > 512) return fail(GRIMB_E_ARG, "max_haps_in_phase must be 1..512");
+  if (c->n_results < 0 || c->n_pop_results < 0) return fail(GRIMB_E_ARG, "negative result limits");
+  if (c->options_threshold < 1 || c->options_threshold > (1ll << 31)) return fail(GRIMB_E_ARG, "options_threshold out of range");
+  if (c->n_rows < 0 || c->n_rows > GRIMB_MAX_ROWS) return fail(GRIMB_E_ARG, "too many Plan_B_Matrix rows");
+  for (int r = 0; r < c->n_rows; ++r)
+    if (c->row_blocks[r] < 0 || c->row_blocks[r] > GRIMB_MAX_BLOCKS) return fail(GRIMB_E_ARG, "too many blocks in a row");
+  (void)t;
+  return GRIMB_OK;
+}
+
+extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch, GrimbResults* res,
+                                   void* cuda_stream) {
+  if (!e || !cfg || !batch || !res) return fail(GRIMB_E_ARG, "null argument");
+  int rc = check_cfg(cfg, e->tables);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+  CK(cudaMemcpyAsync(e->d_cfg, cfg, sizeof(GrimbConfig), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(e->d_counters, 0, 32, st));
+  OutArrays O;
+  O.r = *res;
+  O.hap_counter = e->d_counters + 1;
+  O.pop_counter = e->d_counters + 2;
+  if (batch->n_subjects > 0) {
+    int grid = e->n_ctas;
+    if ((int64_t)grid > batch->n_subjects) grid = (int)batch->n_subjects;
+    k_impute<<<grid, e->threads, 0, st>>>(e->tables->view, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones,
+                                         e->d_counters);
+    CK(cudaGetLastError());
+    e->launches += 1;
+  }
+  unsigned long long cnt[4];
+  CK(cudaMemcpyAsync(cnt, e->d_counters, 32, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *res->hap_rows_needed = (int64_t)cnt[1];
+  *res->pop_rows_needed = (int64_t)cnt[2];
+  if ((int64_t)cnt[1] > res->hap_capacity || (int64_t)cnt[2] > res->pop_capacity)
+    return fail(GRIMB_E_CAPACITY, "result row buffers too small");
+  return GRIMB_OK;
+}
+
+extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* b, GrimbResults* r) {
+  if (!e || !cfg || !b || !r) return fail(GRIMB_E_ARG, "null argument");
+  CK(cudaSetDevice(e->device));
+  const int L = e->tables->h.L, P = e->tables->h.P;
+  const int64_t S = b->n_subjects;
+  cudaStream_t st = e->stream;
+  const size_t in_bytes[6] = {(size_t)S * 2, (size_t)S * L * 2 * 2, (size_t)(S + 1) * 4, (size_t)b->n_alleles_total * 2,
+                              (size_t)S * 4, (size_t)b->n_priors * P * P * 8};
+  const void* in_src[6] = {b->typed_mask, b->counts, b->allele_off, b->alleles, b->prior_index, b->priors};
+  for (int i = 0; i < 6; ++i) {
+    CK(e->in[i].reserve(in_bytes[i] + 16));
+    CK(cudaMemcpyAsync(e->in[i].p, in_src[i], in_bytes[i], cudaMemcpyHostToDevice, st));
+  }
+  GrimbBatch db = *b;
+  db.typed_mask = (const uint16_t*)e->in[0].p;
+  db.counts = (const uint16_t*)e->in[1].p;
+  db.allele_off = (const uint32_t*)e->in[2].p;
+  db.alleles = (const uint16_t*)e->in[3].p;
+  db.prior_index = (const uint32_t*)e->in[4].p;
+  db.priors = (const double*)e->in[5].p;
+  const size_t ob[14] = {(size_t)S,     (size_t)S,     (size_t)S,     (size_t)S * 4, (size_t)S * 4, (size_t)S * 4, (size_t)S * 4,
+                         (size_t)S * 4, (size_t)S * 4, (size_t)S * 8, (size_t)S * 8, (size_t)S * 8,
+                         (size_t)r->hap_capacity * sizeof(GrimbHapRow), (size_t)r->pop_capacity * sizeof(GrimbPopRow)};
+  for (int i = 0; i < 14; ++i) CK(e->outb[i].reserve(ob[i] + 16));
+  GrimbResults dr = *r;
+  dr.status = (uint8_t*)e->outb[0].p;
+  dr.plan_umug = (uint8_t*)e->outb[1].p;
+  dr.plan_pmug = (uint8_t*)e->outb[2].p;
+  dr.n_umug = (uint32_t*)e->outb[3].p;
+  dr.n_pmug = (uint32_t*)e->outb[4].p;
+  dr.n_umug_pops = (uint32_t*)e->outb[5].p;
+  dr.n_pmug_pops = (uint32_t*)e->outb[6].p;
+  dr.tot_umug = (uint32_t*)e->outb[7].p;
+  dr.tot_pmug = (uint32_t*)e->outb[8].p;
+  dr.hap_off = (uint64_t*)e->outb[9].p;
+  dr.pop_off = (uint64_t*)e->outb[10].p;
+  dr.pair_evals = (uint64_t*)e->outb[11].p;
+  dr.hap_rows = (GrimbHapRow*)e->outb[12].p;
+  dr.pop_rows = (GrimbPopRow*)e->outb[13].p;
+  int rc = grimb_impute_device(e, cfg, &db, &dr, st);
+  if (rc != GRIMB_OK && rc != GRIMB_E_CAPACITY) return rc;
+  void* dst[12] = {r->status, r->plan_umug, r->plan_pmug, r->n_umug, r->n_pmug, r->n_umug_pops, r->n_pmug_pops,
+                   r->tot_umug, r->tot_pmug, r->hap_off, r->pop_off, r->pair_evals};
+  for (int i = 0; i < 12; ++i) CK(cudaMemcpyAsync(dst[i], e->outb[i].p, ob[i], cudaMemcpyDeviceToHost, st));
+  if (rc == GRIMB_OK) {
+    CK(cudaMemcpyAsync(r->hap_rows, e->outb[12].p, (size_t)*r->hap_rows_needed * sizeof(GrimbHapRow), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(r->pop_rows, e->outb[13].p, (size_t)*r->pop_rows_needed * sizeof(GrimbPopRow), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  return rc;
+}

@@ -1,0 +1,598 @@
+// grimb_subject.h -- the per-subject imputation algorithm, executed by one thread group (CTA).
+//
+// What it reproduces (reference = nmdp-bioinformatics/py-graph-imputation, file
+// grim/imputation/impute.py unless another file is named):
+//   phases            gen_phases :274-303
+//   opening           open_phases :914-989 + cutils.pyx:6-31 (mixed-radix decode, never
+//                     materialised) and cutils.pyx:35-51 (filter of a label's haplotypes)
+//   Plan A probe      comp_hap_prob :353 -> Graph.adjs_query networkx_graph.py:253-278
+//   flatten + cap     convert_list_to_one_dim :424-442 (streaming stable top-K)
+//   pair evaluation   calc_haps_pairs :444-548 / calc_haps_pairs_haplotype :550-658
+//   epsilon schedule  call_comp_phase_prob :1658-1724
+//   Plan B            comp_phase_prob_plan_b :1392-1570 and helpers :994-1258
+//   Plan C            comp_phase_prob_plan_c :1313-1389, comp_hap_prob_plan_c :1264-1311
+//   reductions        reduce_phase_to_valid_allels :864-879, ..._commons_alleles :881-912
+//   top-N             write_best_prob :24-58, write_best_prob_genotype :61-76
+//
+// Ordering contract: the reference's results are Python dicts in first-encounter order of a
+// sequential (phase, h, k) traversal, summed with += in that order and ranked with stable
+// descending sorts.  Here every accepted pair carries its encounter rank; duplicates are
+// resolved with atomicMin on the rank, sums run sequentially in rank order inside each group,
+// and all sorts use (value, rank) as a total order, so results are bit-identical for any thread
+// interleaving.  FP64 expressions keep the reference's operation order; the translation unit
+// must be compiled without FMA contraction (-fmad=false / -ffp-contract=off).
+#pragma once
+#include "../../include/grimb200.h"
+#include "grimb_tables.h"
+
+namespace grimb {
+
+constexpr int MAXT = 256;   // max threads per group
+constexpr int MAXL = GRIMB_MAX_LOCI;
+constexpr int MAXPH = 256;  // 2^(MAXL-1)
+constexpr int NVAR = 4;
+constexpr int VAR_ORIG = 0, VAR_VALID = 1, VAR_C10 = 2, VAR_C1 = 3;
+constexpr uint32_t NEVER_ROW = 10;  // impute.py:1410
+
+struct SelItem {
+  uint64_t wkey;  // ~orderable(weight): ascending = weight descending
+  uint64_t ord;   // encounter order inside the side's list
+  double f;
+  uint64_t hap;
+  uint32_t pop;
+  uint32_t pad;
+};
+struct TopItem {
+  double f;
+  uint64_t hap;
+  uint32_t pop;
+  uint32_t pad;
+};
+struct Entry {
+  uint64_t h1, h2;
+  double prob;
+  uint16_t p1, p2;
+  uint32_t pad;
+};
+struct SlotDesc {
+  uint64_t ncand;
+  const uint32_t* filt;  // filter mode: candidate node ids
+  uint8_t var;           // which list variant the slot uses
+  uint8_t mode;          // 0 Cartesian, 1 filter
+  uint8_t valid;         // phase opened (both sides non-empty)
+  uint8_t pad;
+  uint32_t first_row;    // Plan B: first matrix row that returned anything (NEVER_ROW)
+  uint32_t cached_row;   // row whose top list is currently stored (0xFFFFFFFF none)
+};
+
+struct Shared {
+  uint32_t scratch[80];
+  uint32_t sel_n;
+  uint32_t fault;
+  uint32_t cnt[8];
+  uint32_t chunk_node[MAXT];
+  uint32_t chunk_off[MAXT];
+  const uint16_t* lptr[NVAR][MAXL][2];
+  uint16_t lcnt[NVAR][MAXL][2];
+  uint8_t lexist[NVAR][MAXL][2];
+  uint8_t lhave[NVAR];
+  uint16_t ph[MAXPH];
+  uint16_t kbreak[512];
+  uint32_t work;
+  uint32_t nonempty;  // the side evaluation in progress returned a non-empty dict
+  double dmax;
+};
+
+struct OutArrays {  // device pointers of GrimbResults + global row counters
+  GrimbResults r;
+  unsigned long long* hap_counter;
+  unsigned long long* pop_counter;
+};
+
+GD uint64_t order_key_desc(double w) {
+  w = w + 0.0;
+  uint64_t u = dbits(w);
+  u = (u >> 63) ? ~u : (u | (1ull << 63));
+  return ~u;
+}
+
+struct Ctx {
+  Grp g;
+  Shared* sh;
+  TablesView T;
+  const GrimbConfig* cfg;
+  const double* ones;  // [P*P] all-ones prior
+  // arena (bump allocator; every thread mirrors the same offsets)
+  char* ar_base;
+  uint64_t ar_cap, ar_used;
+  bool ws_fail;
+  // subject
+  int n;             // typed loci
+  int loc[MAXL];     // locus index of typed position t
+  uint32_t typed;    // label mask of the typed loci
+  uint32_t full;     // label mask of all loci
+  const double* M;   // current prior matrix [P][P]
+  int nph;           // kept phases (sh->ph)
+  SlotDesc* slots;   // [2*nph]
+  TopItem* top;      // [2*nph][K]
+  uint32_t* top_n;   // [2*nph]
+  uint32_t* slot_ne; // [2*nph] last evaluation of the slot returned a non-empty dict
+  int K;
+  // selector
+  SelItem* sel;
+  SelItem* sel2;
+  uint32_t* sel_idx;
+  uint32_t capsel;
+  bool thr_on;
+  uint64_t thr;
+  // entries of the current evaluation
+  Entry* ent;
+  uint32_t ent_cap, ent_n;
+  uint64_t pair_evals;
+  bool plan_c_single;  // P_eff = 1 (Plan C: vectors summed over populations)
+
+  template <class X>
+  GD X* alloc(uint64_t count) {
+    uint64_t bytes = (count * sizeof(X) + 15ull) & ~15ull;
+    if (ar_used + bytes > ar_cap) {
+      ws_fail = true;
+      return reinterpret_cast<X*>(ar_base);
+    }
+    X* p = reinterpret_cast<X*>(ar_base + ar_used);
+    ar_used += bytes;
+    return p;
+  }
+
+  GD int side_of(int slot, int t) const { return ((sh->ph[slot >> 1] >> t) & 1) ^ (slot & 1); }
+
+  // ---------------------------------------------------------------- candidates
+  GD void decode(const SlotDesc& sd, int slot, uint64_t c, uint16_t* ids) const {
+    if (sd.mode) {
+      uint64_t k = T.node_key[sd.filt[c]];
+      for (int t = 0; t < n; ++t) ids[t] = (uint16_t)key_field(T, k, loc[t]);
+    } else {
+      for (int t = n - 1; t >= 0; --t) {
+        int x = side_of(slot, t);
+        uint32_t cn = sh->lcnt[sd.var][t][x];
+        uint32_t d = (uint32_t)(c % cn);
+        c /= cn;
+        ids[t] = sh->lptr[sd.var][t][x][d];
+      }
+    }
+  }
+
+  // pack the ids at the typed positions selected by posmask; false if an id is not a table allele
+  GD bool pack(const uint16_t* ids, uint32_t posmask, uint64_t& key, uint32_t& label) const {
+    key = 0;
+    label = 0;
+    bool known = true;
+    for (int t = 0; t < n; ++t)
+      if (posmask >> t & 1u) {
+        int l = loc[t];
+        if (ids[t] > T.n_alleles[l] || ids[t] == 0) known = false;
+        key |= (uint64_t)ids[t] << T.shift[l];
+        label |= 1u << l;
+      }
+    return known;
+  }
+
+  // ---------------------------------------------------------------- streaming stable top-K
+  GD void sel_begin() {
+    g.sync();
+    if (g.tid == 0) {
+      sh->sel_n = 0;
+      sh->nonempty = 0;
+    }
+    thr_on = false;
+    thr = 0;
+    g.sync();
+  }
+
+  GD void sel_compact() {
+    uint32_t cnt = sh->sel_n;
+    for (uint32_t i = g.tid; i < cnt; i += g.n) sel_idx[i] = i;
+    g.sync();
+    SelItem* s = sel;
+    uint32_t* ix = sel_idx;
+    group_sort(
+        g, cnt,
+        [=](uint32_t a, uint32_t b) {
+          const SelItem& x = s[ix[a]];
+          const SelItem& y = s[ix[b]];
+          return x.wkey < y.wkey || (x.wkey == y.wkey && x.ord < y.ord);
+        },
+        [=](uint32_t a, uint32_t b) {
+          uint32_t t = ix[a];
+          ix[a] = ix[b];
+          ix[b] = t;
+        });
+    uint32_t keep = cnt < (uint32_t)K ? cnt : (uint32_t)K;
+    for (uint32_t i = g.tid; i < keep; i += g.n) sel2[i] = sel[sel_idx[i]];
+    g.sync();
+    SelItem* tmp = sel;
+    sel = sel2;
+    sel2 = tmp;
+    if (g.tid == 0) sh->sel_n = keep;
+    if (cnt >= (uint32_t)K) {
+      thr_on = true;
+      thr = sel[K - 1].wkey;
+    }
+    g.sync();
+  }
+
+  // call before every batch of at most g.n pushes (uniform)
+  GD void sel_reserve() {
+    g.sync();
+    if (sh->sel_n + (uint32_t)g.n > capsel) sel_compact();
+  }
+
+  GD void sel_push(double w, uint64_t ord, double f, uint64_t hap, uint32_t pop) {
+    uint64_t wk = order_key_desc(w);
+    if (thr_on && !(wk < thr)) return;
+    uint32_t p = atom_add(&sh->sel_n, 1u);
+    SelItem it;
+    it.wkey = wk;
+    it.ord = ord;
+    it.f = f;
+    it.hap = hap;
+    it.pop = pop;
+    it.pad = 0;
+    sel[p] = it;
+  }
+
+  GD void sel_finish(int slot) {
+    g.sync();
+    sel_compact();
+    uint32_t cnt = sh->sel_n;
+    TopItem* dst = top + (uint64_t)slot * K;
+    for (uint32_t i = g.tid; i < cnt; i += g.n) {
+      TopItem t;
+      t.f = sel[i].f;
+      t.hap = sel[i].hap;
+      t.pop = sel[i].pop;
+      t.pad = 0;
+      dst[i] = t;
+    }
+    if (g.tid == 0) {
+      top_n[slot] = cnt;
+      slot_ne[slot] = sh->nonempty;
+    }
+    g.sync();
+  }
+
+  // Expand a chunk of (node, degree) pairs held in sh->chunk_* into selector items:
+  // node itself when `self`, else its CSR neighbours `adj[start[node]+t]`; hap key = node key |
+  // extra[owner]; frequency scaled by `scale` when scaled.
+  template <class Extra>
+  GD void expand_chunk(uint32_t total, uint64_t base, bool self, const uint32_t* start, const uint32_t* adj,
+                       Extra extra, bool scaled, double scale) {
+    const int P = T.P;
+    uint64_t items = (uint64_t)total * (uint64_t)P;
+    for (uint64_t q0 = 0; q0 < items; q0 += g.n) {
+      sel_reserve();
+      uint64_t q = q0 + g.tid;
+      if (q < items) {
+        uint32_t hit = (uint32_t)(q / P);
+        uint32_t j = (uint32_t)(q % P);
+        int lo = 0, hi = g.n - 1;  // largest i with chunk_off[i] <= hit
+        while (lo < hi) {
+          int mid = (lo + hi + 1) >> 1;
+          if (sh->chunk_off[mid] <= hit) lo = mid; else hi = mid - 1;
+        }
+        uint32_t node = sh->chunk_node[lo];
+        uint32_t t = hit - sh->chunk_off[lo];
+        uint32_t fn = self ? node : adj[start[node] + t];
+        double f = T.freq[(uint64_t)fn * P + j];
+        if (scaled) f = f * scale;
+        if (f > 0) {
+          double w = f * M[j * P + j];
+          sel_push(w, ((base + (uint64_t)lo) << 32) | ((uint64_t)t * P + j), f, T.node_key[fn] | extra(lo), j);
+        }
+      }
+    }
+    g.sync();
+  }
+
+  // Plan A probe of one side (adjs_query): full-label node -> itself, partial -> top links.
+  GD void slot_plan_a(int slot) {
+    const SlotDesc sd = slots[slot];
+    sel_begin();
+    const bool isfull = (typed == full);
+    for (uint64_t base = 0; base < sd.ncand; base += g.n) {
+      uint64_t c = base + g.tid;
+      uint32_t node = GRIMB_NONE, deg = 0;
+      if (c < sd.ncand) {
+        if (sd.mode) {
+          node = sd.filt[c];
+        } else {
+          uint16_t ids[MAXL];
+          decode(sd, slot, c, ids);
+          uint64_t key;
+          uint32_t label;
+          if (pack(ids, (1u << n) - 1u, key, label)) node = ht_lookup(T, label, key);
+        }
+        if (node != GRIMB_NONE) {
+          deg = isfull ? 1u : T.tl_cnt[node];
+          if (deg == GRIMB_ADJ_FAULT) {
+            sh->fault = 1;
+            deg = 0;
+          }
+        }
+      }
+      uint32_t total;
+      uint32_t off = g.scan_excl(deg, total);
+      sh->chunk_node[g.tid] = node;
+      sh->chunk_off[g.tid] = off;
+      if (total && g.tid == 0) sh->nonempty = 1;
+      g.sync();
+      expand_chunk(total, base, isfull, T.tl_start, T.tl_adj, [](int) { return (uint64_t)0; }, false, 1.0);
+    }
+    sel_finish(slot);
+  }
+
+  // ---------------------------------------------------------------- pair evaluation
+  // Appends the accepted pairs of every opened phase, in (phase, h, k) order, to ent[].
+  GD void gen_entries(double eps) {
+    const int P = plan_c_single ? 1 : T.P;
+    ent_n = 0;
+    for (int p = 0; p < nph; ++p) {
+      if (!slots[2 * p].valid) continue;
+      const uint32_t n1 = top_n[2 * p], n2 = top_n[2 * p + 1];
+      if (n1 == 0 || n2 == 0) continue;
+      const TopItem* T1 = top + (uint64_t)(2 * p) * K;
+      const TopItem* T2 = top + (uint64_t)(2 * p + 1) * K;
+      uint64_t evals = 0;
+      for (uint32_t h = g.tid; h < n1; h += g.n) {
+        double x = eps / T1[h].f;
+        uint32_t k = 0;
+        while (k < n2 && T2[k].f >= x) ++k;
+        sh->kbreak[h] = (uint16_t)k;
+        evals += (k < n2) ? k + 1 : n2;
+      }
+      pair_evals += evals;  // per-thread partial; reduced at the end of the subject
+      g.sync();
+      const uint64_t npairs = (uint64_t)n1 * n2;
+      for (uint64_t q0 = 0; q0 < npairs; q0 += g.n) {
+        uint64_t q = q0 + g.tid;
+        bool acc = false;
+        Entry e;
+        if (q < npairs) {
+          uint32_t h = (uint32_t)(q / n2), k = (uint32_t)(q % n2);
+          if (k < sh->kbreak[h]) {
+            const TopItem a = T1[h], b = T2[k];
+            double x = eps / a.f;
+            double m = M[a.pop * P + b.pop];
+            if (m > 0) {
+              double mf = m * b.f;
+              bool same = a.hap == b.hap;
+              if ((!same && mf >= x) || (same && mf >= x * 2)) {
+                acc = true;
+                e.h1 = a.hap;
+                e.h2 = b.hap;
+                e.p1 = (uint16_t)a.pop;
+                e.p2 = (uint16_t)b.pop;
+                e.pad = 0;
+                double pr = a.f * b.f * m;
+                if (!same) pr = pr * 2;
+                e.prob = pr;
+              }
+            }
+          }
+        }
+        uint32_t total;
+        uint32_t pos = g.scan_excl(acc ? 1u : 0u, total);
+        if (acc) {
+          if (ent_n + pos < ent_cap) ent[ent_n + pos] = e;
+        }
+        ent_n += total;
+      }
+      g.sync();
+    }
+    if (ent_n > ent_cap) ws_fail = true;
+  }
+
+  // geno_seen (impute.py:508-513): keep the first entry of every unordered {(hap,pop),(hap,pop)}.
+  // Compacts ent[] in place (order preserved); returns MaxProb over the kept entries.
+  GD double dedup_entries() {
+    if (ent_n == 0 || ws_fail) return 0.0;
+    uint64_t mark = ar_used;
+    uint32_t tsz = 2;
+    while (tsz < 2 * ent_n) tsz <<= 1;
+    uint32_t* tab = alloc<uint32_t>(tsz);
+    uint32_t* where = alloc<uint32_t>(ent_n);
+    Entry* tmp = alloc<Entry>(ent_n);
+    if (ws_fail) return 0.0;
+    for (uint32_t i = g.tid; i < tsz; i += g.n) tab[i] = GRIMB_NONE;
+    g.sync();
+    const Entry* E = ent;
+    auto canon = [=](uint32_t i, uint64_t& ha, uint32_t& pa, uint64_t& hb, uint32_t& pb) {
+      const Entry& e = E[i];
+      bool sw = e.h1 > e.h2 || (e.h1 == e.h2 && e.p1 > e.p2);
+      ha = sw ? e.h2 : e.h1;
+      pa = sw ? e.p2 : e.p1;
+      hb = sw ? e.h1 : e.h2;
+      pb = sw ? e.p1 : e.p2;
+    };
+    for (uint32_t i = g.tid; i < ent_n; i += g.n) {
+      uint64_t ha, hb;
+      uint32_t pa, pb;
+      canon(i, ha, pa, hb, pb);
+      uint32_t h = (uint32_t)mix64(ha ^ mix64(hb + 0x9e3779b97f4a7c15ULL) ^ ((uint64_t)pa << 17) ^ ((uint64_t)pb << 41)) & (tsz - 1);
+      for (;;) {
+        uint32_t cur = tab[h];
+        if (cur == GRIMB_NONE) {
+          cur = atom_cas(&tab[h], GRIMB_NONE, i);
+          if (cur == GRIMB_NONE) break;
+        }
+        uint64_t xa, xb;
+        uint32_t qa, qb;
+        canon(cur, xa, qa, xb, qb);
+        if (xa == ha && xb == hb && qa == pa && qb == pb) {
+          atom_min(&tab[h], i);
+          break;
+        }
+        h = (h + 1) & (tsz - 1);
+      }
+      where[i] = h;
+    }
+    g.sync();
+    double mx = 0.0;
+    uint32_t kept = 0;
+    for (uint32_t i0 = 0; i0 < ent_n; i0 += g.n) {
+      uint32_t i = i0 + g.tid;
+      bool keep = i < ent_n && tab[where[i]] == i;
+      uint32_t total;
+      uint32_t pos = g.scan_excl(keep ? 1u : 0u, total);
+      if (keep) {
+        tmp[kept + pos] = ent[i];
+        if (ent[i].prob > mx) mx = ent[i].prob;
+      }
+      kept += total;
+    }
+    g.sync();
+    for (uint32_t i = g.tid; i < kept; i += g.n) ent[i] = tmp[i];
+    ent_n = kept;
+    mx = g.maxd(mx);
+    g.sync();
+    ar_used = mark;
+    return mx;
+  }
+
+  // ---------------------------------------------------------------- aggregation + top-N
+  // kind 0: UMUG genotype (per-locus unordered pairs)   impute.py:497-504,529-533
+  // kind 1: PMUG haplotype pair, first-seen orientation  impute.py:24-38
+  // kind 2: population pair                               impute.py:535-543 / :24-38
+  GD void group_key(int kind, const Entry& e, uint64_t& a, uint64_t& b) const {
+    if (kind == 0) {
+      uint64_t lo = 0, hi = 0;
+      for (int l = 0; l < T.L; ++l) {
+        uint64_t x = key_field(T, e.h1, l), y = key_field(T, e.h2, l);
+        uint64_t mn = x < y ? x : y, mxv = x < y ? y : x;
+        lo |= mn << T.shift[l];
+        hi |= mxv << T.shift[l];
+      }
+      a = lo;
+      b = hi;
+    } else if (kind == 1) {
+      a = e.h1 < e.h2 ? e.h1 : e.h2;
+      b = e.h1 < e.h2 ? e.h2 : e.h1;
+    } else {
+      a = e.p1 < e.p2 ? e.p1 : e.p2;
+      b = e.p1 < e.p2 ? e.p2 : e.p1;
+    }
+  }
+
+  // Groups ent[0..ent_n) by `kind`, sums probabilities per group in encounter order, ranks the
+  // groups by (sum desc, first encounter asc) and writes the best `limit` rows.  Returns the
+  // number of groups; *n_rows = rows written.  Rows: kind 0 -> (lo,hi); kind 1 -> (h1,h2) of
+  // the first member; kind 2 -> pops of the first member (orientation as encountered).
+  GD uint32_t aggregate(int kind, uint32_t limit, GrimbHapRow* hap_rows, GrimbPopRow* pop_rows, uint32_t* n_rows) {
+    if (g.tid == 0) *n_rows = 0;
+    if (ent_n == 0 || ws_fail) return 0;
+    uint64_t mark = ar_used;
+    uint32_t tsz = 2;
+    while (tsz < 2 * ent_n) tsz <<= 1;
+    uint32_t* tab = alloc<uint32_t>(tsz);
+    uint32_t* where = alloc<uint32_t>(ent_n);
+    uint64_t* srt = alloc<uint64_t>(ent_n);
+    uint32_t* ghead = alloc<uint32_t>(ent_n);   // position in srt of each group's head
+    double* gsum = alloc<double>(ent_n);
+    uint32_t* gord = alloc<uint32_t>(ent_n);
+    if (ws_fail) return 0;
+    for (uint32_t i = g.tid; i < tsz; i += g.n) tab[i] = GRIMB_NONE;
+    g.sync();
+    const Entry* E = ent;
+    for (uint32_t i = g.tid; i < ent_n; i += g.n) {
+      uint64_t a, b;
+      group_key(kind, E[i], a, b);
+      uint32_t h = (uint32_t)mix64(a ^ mix64(b + 0x9e3779b97f4a7c15ULL)) & (tsz - 1);
+      for (;;) {
+        uint32_t cur = tab[h];
+        if (cur == GRIMB_NONE) {
+          cur = atom_cas(&tab[h], GRIMB_NONE, i);
+          if (cur == GRIMB_NONE) break;
+        }
+        uint64_t xa, xb;
+        group_key(kind, E[cur], xa, xb);
+        if (xa == a && xb == b) {
+          atom_min(&tab[h], i);
+          break;
+        }
+        h = (h + 1) & (tsz - 1);
+      }
+      where[i] = h;
+    }
+    g.sync();
+    for (uint32_t i = g.tid; i < ent_n; i += g.n) srt[i] = ((uint64_t)tab[where[i]] << 32) | i;
+    g.sync();
+    {
+      uint64_t* s = srt;
+      group_sort(
+          g, ent_n, [=](uint32_t a, uint32_t b) { return s[a] < s[b]; },
+          [=](uint32_t a, uint32_t b) {
+            uint64_t t = s[a];
+            s[a] = s[b];
+            s[b] = t;
+          });
+    }
+    // group heads, in first-encounter order
+    uint32_t ng = 0;
+    for (uint32_t i0 = 0; i0 < ent_n; i0 += g.n) {
+      uint32_t i = i0 + g.tid;
+      bool head = i < ent_n && (i == 0 || (srt[i] >> 32) != (srt[i - 1] >> 32));
+      uint32_t total;
+      uint32_t pos = g.scan_excl(head ? 1u : 0u, total);
+      if (head) ghead[ng + pos] = i;
+      ng += total;
+    }
+    g.sync();
+    for (uint32_t gi = g.tid; gi < ng; gi += g.n) {
+      uint32_t b0 = ghead[gi], b1 = (gi + 1 < ng) ? ghead[gi + 1] : ent_n;
+      double s = E[(uint32_t)srt[b0]].prob;
+      for (uint32_t q = b0 + 1; q < b1; ++q) s = s + E[(uint32_t)srt[q]].prob;  // += in encounter order
+      gsum[gi] = s;
+      gord[gi] = gi;
+    }
+    g.sync();
+    {
+      const double* gs = gsum;
+      uint32_t* go = gord;
+      group_sort(
+          g, ng,
+          [=](uint32_t a, uint32_t b) {
+            double x = gs[go[a]], y = gs[go[b]];
+            return x > y || (x == y && go[a] < go[b]);
+          },
+          [=](uint32_t a, uint32_t b) {
+            uint32_t t = go[a];
+            go[a] = go[b];
+            go[b] = t;
+          });
+    }
+    uint32_t rows = ng < limit ? ng : limit;
+    for (uint32_t r = g.tid; r < rows; r += g.n) {
+      uint32_t gi = gord[r];
+      const Entry& e = E[(uint32_t)(srt[ghead[gi]])];
+      if (kind == 2) {
+        GrimbPopRow o;
+        o.pop_a = e.p1;
+        o.pop_b = e.p2;
+        o.pad = 0;
+        o.prob = gsum[gi];
+        pop_rows[r] = o;
+      } else {
+        GrimbHapRow o;
+        if (kind == 0) group_key(0, e, o.a, o.b);
+        else { o.a = e.h1; o.b = e.h2; }
+        o.prob = gsum[gi];
+        hap_rows[r] = o;
+      }
+    }
+    if (g.tid == 0) *n_rows = rows;
+    g.sync();
+    ar_used = mark;
+    return ng;
+  }
+};
+
+}  // namespace grimb

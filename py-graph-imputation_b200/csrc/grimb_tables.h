@@ -1,0 +1,85 @@
+// grimb_tables.h -- device view of the frequency store and the probe primitives.
+//
+// Layout in HBM (DESIGN.md "Data layout"):
+//   slots      open-addressing hash table, one region per locus-subset label (so the
+//              full-label region of a 1M-haplotype table is 32 MB and stays L2-resident);
+//              16-byte slots {packed key, node id}, load factor <= 0.5, linear probing, one
+//              128-bit load per probe (two slots per 32-byte sector).
+//   node_key   packed allele ids of node i (0 in the fields of absent loci)
+//   freq       [n_nodes][P] FP64 frequency vectors, reference node-id order
+//   tl_*       CSR: partial node -> full nodes containing it (ascending id)   [adjs_query]
+//   cn_*       CSR: (child node, added locus) -> parents one locus longer     [adjs_query_by_color]
+//   label_*    node-id range of every label                                   [haps_by_label]
+#pragma once
+#include "grimb_group.h"
+
+namespace grimb {
+
+#define GRIMB_NONE 0xFFFFFFFFu
+#define GRIMB_ADJ_FAULT 0xFFFFFFFFu  // tl_cnt/cn_cnt: the reference raises IndexError here (T1)
+
+struct HSlot {
+  uint64_t key;
+  uint32_t node;
+  uint32_t pad;
+};
+
+struct TablesView {
+  int32_t L, P;
+  uint32_t n_nodes, n_full;
+  uint8_t shift[9];
+  uint8_t width[9];
+  uint32_t n_alleles[9];
+  const uint32_t* label_first;  // [1<<L]
+  const uint32_t* label_count;  // [1<<L]
+  const uint64_t* ht_off;       // [1<<L] first slot of the label's region
+  const uint32_t* ht_mask;      // [1<<L] region size - 1 (power of two)
+  const HSlot* slots;
+  const uint64_t* node_key;
+  const double* freq;
+  const uint32_t* tl_start;
+  const uint32_t* tl_cnt;
+  const uint32_t* tl_adj;
+  const uint32_t* cn_start;     // [n_nodes][L]
+  const uint32_t* cn_cnt;
+  const uint32_t* cn_adj;
+};
+
+GD uint64_t key_field(const TablesView& T, uint64_t key, int locus) {
+  return (key >> T.shift[locus]) & ((1ull << T.width[locus]) - 1ull);
+}
+
+GD uint64_t key_mask_of(const TablesView& T, uint32_t label) {
+  uint64_t m = 0;
+  for (int l = 0; l < T.L; ++l)
+    if (label >> l & 1u) m |= ((1ull << T.width[l]) - 1ull) << T.shift[l];
+  return m;
+}
+
+GD HSlot load_slot(const HSlot* p) {
+#if GRIMB_DEVICE
+  uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  HSlot s;
+  s.key = (uint64_t)v.x | ((uint64_t)v.y << 32);
+  s.node = v.z;
+  s.pad = v.w;
+  return s;
+#else
+  return *p;
+#endif
+}
+
+// One probe: hash, then linear scan of 16-byte slots until the key or an empty slot.
+GD uint32_t ht_lookup(const TablesView& T, uint32_t label, uint64_t key) {
+  const uint32_t mask = T.ht_mask[label];
+  const HSlot* base = T.slots + T.ht_off[label];
+  uint32_t h = (uint32_t)mix64(key) & mask;
+  for (;;) {
+    HSlot s = load_slot(base + h);
+    if (s.node == GRIMB_NONE) return GRIMB_NONE;
+    if (s.key == key) return s.node;
+    h = (h + 1) & mask;
+  }
+}
+
+}  // namespace grimb

@@ -1,0 +1,119 @@
+"""ctypes binding of libgrimb200.so (include/grimb200.h).
+
+There is no CPU path: if the CUDA library is missing or no device is present every entry point
+raises.  The library is built in-tree by py-graph-imputation_b200/csrc/build.sh (or
+__graft_entry__.build())."""
+import ctypes as C
+import os
+
+MAX_LOCI = 9
+MAX_ROWS = 16
+MAX_BLOCKS = 9
+
+ST_OK, ST_FAULT, ST_WORKSPACE, ST_SKIPPED, ST_NO_PHASES = 0, 2, 3, 4, 5
+PLAN_NONE, PLAN_A, PLAN_B, PLAN_C = 0, 1, 2, 3
+E_CAPACITY = -5
+ALL_POPS = 0xFFFF
+
+
+class TableDesc(C.Structure):
+    _fields_ = [
+        ("n_loci", C.c_int32), ("n_pops", C.c_int32), ("n_full", C.c_int64),
+        ("full_alleles", C.c_void_p), ("full_freqs", C.c_void_p),
+        ("n_alleles", C.c_int32 * MAX_LOCI), ("key_bits", C.c_int32 * MAX_LOCI),
+        ("last_parent_locus", C.c_int32), ("device", C.c_int32),
+    ]
+
+
+class TableInfo(C.Structure):
+    _fields_ = [
+        ("n_loci", C.c_int32), ("n_pops", C.c_int32), ("n_nodes", C.c_int64), ("n_full", C.c_int64),
+        ("n_toplinks", C.c_int64), ("n_conn_edges", C.c_int64), ("n_slots", C.c_int64),
+        ("device_bytes", C.c_int64),
+    ]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("epsilon", C.c_double), ("factor_missing_pow", C.c_double * (MAX_LOCI + 1)),
+        ("options_threshold", C.c_int64), ("max_haps_in_phase", C.c_int32), ("n_results", C.c_int32),
+        ("n_pop_results", C.c_int32), ("planb", C.c_int32), ("output_umug", C.c_int32),
+        ("output_pmug", C.c_int32), ("save_space", C.c_int32), ("compensated_sum", C.c_int32),
+        ("n_rows", C.c_int32),
+        ("row_blocks", C.c_int32 * MAX_ROWS), ("block_mask", (C.c_uint16 * MAX_BLOCKS) * MAX_ROWS),
+        ("row_is_plan_a", C.c_uint8 * MAX_ROWS),
+    ]
+
+
+class Batch(C.Structure):
+    _fields_ = [
+        ("n_subjects", C.c_int64), ("typed_mask", C.c_void_p), ("counts", C.c_void_p),
+        ("allele_off", C.c_void_p), ("alleles", C.c_void_p), ("n_alleles_total", C.c_int64),
+        ("prior_index", C.c_void_p), ("priors", C.c_void_p), ("n_priors", C.c_int32),
+    ]
+
+
+class Results(C.Structure):
+    _fields_ = [
+        ("status", C.c_void_p), ("plan_umug", C.c_void_p), ("plan_pmug", C.c_void_p),
+        ("n_umug", C.c_void_p), ("n_pmug", C.c_void_p), ("n_umug_pops", C.c_void_p),
+        ("n_pmug_pops", C.c_void_p), ("tot_umug", C.c_void_p), ("tot_pmug", C.c_void_p),
+        ("hap_off", C.c_void_p), ("pop_off", C.c_void_p), ("pair_evals", C.c_void_p),
+        ("hap_rows", C.c_void_p), ("hap_capacity", C.c_int64),
+        ("pop_rows", C.c_void_p), ("pop_capacity", C.c_int64),
+        ("hap_rows_needed", C.c_void_p), ("pop_rows_needed", C.c_void_p),
+    ]
+
+
+_LIB = None
+
+
+def lib_path():
+    here = os.path.dirname(os.path.abspath(__file__))
+    return os.path.normpath(os.path.join(here, "..", "..", "csrc", "libgrimb200.so"))
+
+
+def load():
+    """Loads libgrimb200.so or raises: the product has no fallback."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            "libgrimb200.so not built (%s): run py-graph-imputation_b200/csrc/build.sh; "
+            "there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    lib.grimb_abi_version.restype = C.c_int
+    lib.grimb_last_error.restype = C.c_char_p
+    lib.grimb_tables_build.argtypes = [C.POINTER(TableDesc), C.POINTER(C.c_void_p)]
+    lib.grimb_tables_free.argtypes = [C.c_void_p]
+    lib.grimb_tables_info.argtypes = [C.c_void_p, C.POINTER(TableInfo)]
+    lib.grimb_tables_export.argtypes = [C.c_void_p] + [C.c_void_p] * 10
+    lib.grimb_tables_image_size.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    lib.grimb_tables_image_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.grimb_tables_from_image.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_void_p)]
+    lib.grimb_engine_create.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
+    lib.grimb_engine_free.argtypes = [C.c_void_p]
+    lib.grimb_engine_launches.argtypes = [C.c_void_p]
+    lib.grimb_engine_launches.restype = C.c_int64
+    lib.grimb_impute_device.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Batch), C.POINTER(Results), C.c_void_p]
+    lib.grimb_impute_host.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Batch), C.POINTER(Results)]
+    if lib.grimb_abi_version() != 1:
+        raise RuntimeError("libgrimb200.so ABI mismatch")
+    _LIB = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().grimb_last_error().decode("utf8", "replace")
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, msg))
+
+
+EXPORTED = [
+    "grimb_abi_version", "grimb_last_error", "grimb_tables_build", "grimb_tables_free",
+    "grimb_tables_info", "grimb_tables_export", "grimb_tables_image_size", "grimb_tables_image_ptr",
+    "grimb_tables_from_image", "grimb_engine_create", "grimb_engine_free", "grimb_engine_launches",
+    "grimb_impute_device", "grimb_impute_host",
+]

@@ -1,0 +1,452 @@
+"""Host side of the B200 imputation path: class Imputation keeps the reference's name and
+entry points (grim/imputation/impute.py:121 `Imputation`, :1985 `impute_file`, :1940
+`impute_one` in the reference) but only tokenises GL strings, ships batches through the C ABI
+(include/grimb200.h) and formats the packed result rows into the six output files.
+
+Everything numeric happens on the GPU; the one exception is the P x P population prior
+(impute.py:1844-1924 of the reference), which depends only on the (race1, race2) fields, is
+memoised per distinct pair and computed with the same numpy operation order so it is
+bit-identical."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+from . import _lib
+
+H_OK, H_PROBLEM, H_FAULT = 0, 1, 2   # host-side classification of an input line
+
+
+def clean_up_gl(gl):
+    # same observable behaviour as the reference's clean_up_gl (impute.py:105-118)
+    gl = gl.replace("g", "").replace("L", "")
+    parts = gl.split("^")
+    for bad in [p for p in parts if p.strip("U") != p]:
+        parts.remove(bad)
+    return "^".join(parts)
+
+
+def make_config(conf, loci, n_pops):
+    """run_impute_def-style config dict -> GrimbConfig."""
+    L = len(loci)
+    c = _lib.Config()
+    c.epsilon = float(conf["epsilon"])
+    if not c.epsilon > 0:
+        raise ValueError("epsilon must be > 0")
+    fmd = conf["factor_missing_data"]
+    for k in range(L + 1):
+        c.factor_missing_pow[k] = float(fmd ** k)
+    c.options_threshold = int(conf["number_of_options_threshold"])
+    c.max_haps_in_phase = int(conf["max_haplotypes_number_in_phase"])
+    c.n_results = int(conf["number_of_results"])
+    c.n_pop_results = int(conf["number_of_pop_results"])
+    c.planb = 1 if conf["planb"] else 0
+    c.output_umug = 1 if conf["output_MUUG"] else 0
+    c.output_pmug = 1 if conf["output_haplotypes"] else 0
+    c.save_space = 1 if conf["save_mode"] else 0
+    # the reference calls Python's sum() on frequency vectors; CPython >= 3.12 compensates it
+    c.compensated_sum = 1 if sys.version_info >= (3, 12) else 0
+    matrix = conf["matrix_planb"]
+    if len(matrix) > _lib.MAX_ROWS:
+        raise NotImplementedError("Plan_B_Matrix has more than %d rows" % _lib.MAX_ROWS)
+    all_indices = list(set(range(1, L + 1)))  # impute.py:1118 of the reference
+    c.n_rows = len(matrix)
+    for r, row in enumerate(matrix):
+        if len(row) > _lib.MAX_BLOCKS:
+            raise NotImplementedError("Plan_B_Matrix row with more than %d blocks" % _lib.MAX_BLOCKS)
+        c.row_blocks[r] = len(row)
+        for b, blk in enumerate(row):
+            if list(blk) != sorted(blk) or any(i < 1 or i > L for i in blk):
+                raise NotImplementedError("Plan_B_Matrix blocks must list loci indices in ascending order")
+            m = 0
+            for i in blk:
+                m |= 1 << (i - 1)
+            c.block_mask[r][b] = m
+        c.row_is_plan_a[r] = 1 if (len(row) > 0 and list(row[0]) == all_indices) else 0
+    return c
+
+
+class Imputation(object):
+    def __init__(self, net=None, config=None, count_by_prob=None, verbose=False):
+        self.netGraph = net
+        self.config = config
+        self.verbose = verbose
+        self.populations = list(config["pops"])
+        self.loci = net.loci
+        self.L = len(self.loci)
+        self.P = len(self.populations)
+        self.unk_priors = config["UNK_priors"]
+        self.priority = config["priority"]
+        if count_by_prob is None:
+            self.count_by_prob = np.ones(self.P)
+            if config.get("use_pops_count_file"):
+                with open(config["pops_count_file"]) as f:
+                    for i, line in enumerate(f):
+                        self.count_by_prob[i] = float(line.strip().split(",")[2])
+        else:
+            self.count_by_prob = count_by_prob
+        self.cfg = make_config(config, self.loci, self.P)
+        self.locus_index = {n: i for i, n in enumerate(self.loci)}
+        self.batch_size = int(os.environ.get("GRIMB_BATCH", "65536"))
+        self.workspace = int(os.environ.get("GRIMB_WORKSPACE", str(8 << 20)))
+        self.big_workspace = int(os.environ.get("GRIMB_BIG_WORKSPACE", str(1 << 30)))
+        self._prior_index = {}
+        self._priors = []
+        self._backend = self._run_gpu
+        self.stats = {"subjects": 0, "pair_evals": 0, "plan": {0: 0, 1: 0, 2: 0, 3: 0}, "workspace_retries": 0}
+
+    # ------------------------------------------------------------------ prior matrices
+    def _prior_matrix(self, races1, races2):
+        # same arithmetic, in the same order, as calc_priority_matrix (impute.py:1844-1924)
+        pr = self.priority
+        n = self.P
+        M = np.zeros((n, n))
+        eye = np.identity(n)
+        for a in races1:
+            for b in races2:
+                if a == "" and b == "":
+                    continue
+                T = np.zeros((n, n))
+                if a == "" or b == "":
+                    r = self.populations.index(b) if a == "" else self.populations.index(a)
+                    for i in range(n):
+                        T[r, i] = T[r, i] + pr["gamma"] * 2
+                    T = T + T.transpose()
+                    T[r, r] -= pr["gamma"] * 2
+                else:
+                    r1 = self.populations.index(a)
+                    r2 = self.populations.index(b)
+                    for i in range(n):
+                        T[r1, i] = T[r1, i] + pr["gamma"]
+                        T[i, r2] = T[i, r2] + pr["gamma"]
+                    T[r1, r2] -= pr["gamma"]
+                    T[r1, r2] = T[r1, r2] + pr["alpha"]
+                    if r1 != r2:
+                        T = T + T.transpose()
+                        T[r1, r1] -= pr["gamma"]
+                        T[r2, r2] -= pr["gamma"]
+                    T[r1, r1] += pr["delta"]
+                    if r1 != r2:
+                        T[r2, r2] += pr["delta"]
+                T = pr["eta"] * np.ones((n, n)) + T + pr["beta"] * eye
+                M += T
+        total = 0
+        for i in range(n):
+            for j in range(n):
+                M[i][j] = M[i][j] * self.count_by_prob[i] * self.count_by_prob[j]
+                total += M[i][j]
+        return M / total
+
+    def _prior_for(self, race1, race2):
+        """Index of the prior matrix for these race fields (impute.py:1956-1975)."""
+        key = (race1, race2)
+        idx = self._prior_index.get(key)
+        if idx is not None:
+            return idx
+        n = self.P
+        M = np.ones((n, n)) if self.unk_priors == "MR" else np.identity(n)
+        if race1 or race2:
+            known = False
+            r1 = race1.split(";")
+            for i, r in enumerate(r1):
+                if r not in self.populations:
+                    r1[i] = ""
+                else:
+                    known = True
+            r2 = race2.split(";")
+            for i, r in enumerate(r2):
+                if r not in self.populations:
+                    r2[i] = ""
+                else:
+                    known = True
+            if known:
+                M = self._prior_matrix(r1, r2)
+        idx = len(self._priors)
+        self._priors.append(np.ascontiguousarray(M, dtype=np.float64))
+        self._prior_index[key] = idx
+        return idx
+
+    # ------------------------------------------------------------------ tokeniser
+    def _encode_gl(self, gl):
+        """GL string -> (class, typed_mask, counts [L][2], allele ids, unknown-name map).
+        Mirrors clean_up_gl + gl2haps (impute.py:105-118,246-272)."""
+        L = self.L
+        gl = clean_up_gl(gl)
+        if gl == "" or gl == " ":
+            return H_PROBLEM, None
+        t1, t2 = [], []
+        for chunk in gl.split("^"):
+            if chunk == "":
+                return H_FAULT, None          # IndexError on chunk[0] in the reference
+            if chunk[0] == "+":
+                chunk = chunk[1:]
+            sides = chunk.split("+")
+            if len(sides) == 1:
+                if sides == [""]:
+                    continue
+                return H_PROBLEM, None        # a locus without '+': gl2haps returns []
+            t1.append(sides[0])
+            t2.append(sides[1])
+        if not t1:
+            return H_FAULT, None              # 2 ** (0 - 1) phases: TypeError in the reference
+        t1.sort()
+        t2.sort()
+        counts = np.zeros((L, 2), dtype=np.uint16)
+        per_locus = [None] * L
+        unknown = None
+        ids_of = self.netGraph.allele_id
+        n_tab = [len(a) for a in self.netGraph.alleles]
+        cap = [(1 << b) - 1 for b in self.netGraph.key_bits]
+        for a, b in zip(t1, t2):
+            la = a.split("/")
+            lb = b.split("/")
+            l = self.locus_index.get(la[0].split("*")[0])
+            if l is None or per_locus[l] is not None:
+                return (H_FAULT if self.config["planb"] else H_OK), "foreign"
+            local = {}
+            pair = []
+            for lst in (la, lb):
+                out = []
+                for name in lst:
+                    if name.split("*")[0] != self.loci[l]:
+                        return (H_FAULT if self.config["planb"] else H_OK), "foreign"
+                    i = ids_of[l].get(name)
+                    if i is None:
+                        i = local.get(name)
+                        if i is None:
+                            i = n_tab[l] + 1 + len(local)
+                            if i > cap[l]:
+                                return H_FAULT, None
+                            local[name] = i
+                    if i not in out:
+                        out.append(i)
+                pair.append(out)
+            if local:
+                if unknown is None:
+                    unknown = {}
+                for name, i in local.items():
+                    unknown[(l, i)] = name
+            per_locus[l] = pair
+        mask = 0
+        flat = []
+        for l in range(L):
+            if per_locus[l] is not None:
+                mask |= 1 << l
+                for x in range(2):
+                    counts[l, x] = len(per_locus[l][x])
+                    flat.extend(per_locus[l][x])
+        return H_OK, (mask, counts, flat, unknown)
+
+    # ------------------------------------------------------------------ batch execution
+    def _run_gpu(self, cfg, batch, res, workspace):
+        lib = _lib.load()
+        eng = self.netGraph.engine(workspace)
+        return lib.grimb_impute_host(eng, C.byref(cfg), C.byref(batch), C.byref(res))
+
+    def _run_batch(self, enc, workspace):
+        """enc: list of (mask, counts, flat ids, prior index).  -> dict of numpy result arrays."""
+        S, L = len(enc), self.L
+        typed = np.zeros(S, np.uint16)
+        counts = np.zeros((S, L, 2), np.uint16)
+        off = np.zeros(S + 1, np.uint32)
+        pri = np.zeros(S, np.uint32)
+        flat = []
+        for s, (mask, cn, ids, p) in enumerate(enc):
+            typed[s] = mask
+            if mask:
+                counts[s] = cn
+                flat.extend(ids)
+            off[s + 1] = len(flat)
+            pri[s] = p
+        alle = np.array(flat if flat else [0], dtype=np.uint16)
+        priors = np.ascontiguousarray(np.stack(self._priors)) if self._priors else np.ones((1, self.P, self.P))
+        b = _lib.Batch()
+        b.n_subjects = S
+        b.typed_mask, b.counts, b.allele_off = typed.ctypes.data, counts.ctypes.data, off.ctypes.data
+        b.alleles, b.n_alleles_total = alle.ctypes.data, int(off[S])
+        b.prior_index, b.priors, b.n_priors = pri.ctypes.data, priors.ctypes.data, priors.shape[0]
+        out = {
+            "status": np.zeros(S, np.uint8), "plan_umug": np.zeros(S, np.uint8), "plan_pmug": np.zeros(S, np.uint8),
+            "n_umug": np.zeros(S, np.uint32), "n_pmug": np.zeros(S, np.uint32),
+            "n_umug_pops": np.zeros(S, np.uint32), "n_pmug_pops": np.zeros(S, np.uint32),
+            "tot_umug": np.zeros(S, np.uint32), "tot_pmug": np.zeros(S, np.uint32),
+            "hap_off": np.zeros(S, np.uint64), "pop_off": np.zeros(S, np.uint64), "pair_evals": np.zeros(S, np.uint64),
+        }
+        hap_cap = max(1024, S * 2 * min(self.cfg.n_results, 16))
+        pop_cap = max(1024, S * 2 * min(self.cfg.n_pop_results, 4))
+        needed = np.zeros(2, np.int64)
+        while True:
+            hap_rows = np.zeros(hap_cap, dtype=[("a", np.uint64), ("b", np.uint64), ("prob", np.float64)])
+            pop_rows = np.zeros(pop_cap, dtype=[("pa", np.uint16), ("pb", np.uint16), ("pad", np.uint32), ("prob", np.float64)])
+            r = _lib.Results()
+            for k in ("status", "plan_umug", "plan_pmug", "n_umug", "n_pmug", "n_umug_pops", "n_pmug_pops",
+                      "tot_umug", "tot_pmug", "hap_off", "pop_off", "pair_evals"):
+                setattr(r, k, out[k].ctypes.data)
+            r.hap_rows, r.hap_capacity = hap_rows.ctypes.data, hap_cap
+            r.pop_rows, r.pop_capacity = pop_rows.ctypes.data, pop_cap
+            r.hap_rows_needed = needed[0:].ctypes.data
+            r.pop_rows_needed = needed[1:].ctypes.data
+            rc = self._backend(self.cfg, b, r, workspace)
+            if rc == _lib.E_CAPACITY:
+                hap_cap = max(hap_cap, int(needed[0]))
+                pop_cap = max(pop_cap, int(needed[1]))
+                continue
+            if rc != 0:
+                _lib.check(rc, "grimb_impute_host")
+            break
+        out["hap_rows"], out["pop_rows"] = hap_rows, pop_rows
+        return out
+
+    # ------------------------------------------------------------------ formatting
+    def _allele_name(self, l, i, unknown):
+        al = self.netGraph.alleles[l]
+        if 1 <= i <= len(al):
+            return al[i - 1]
+        return unknown[(l, i)]
+
+    def _decode(self, key, unknown):
+        g = self.netGraph
+        out = []
+        for l in range(self.L):
+            i = (int(key) >> g.shift[l]) & ((1 << g.key_bits[l]) - 1)
+            if i:
+                out.append(self._allele_name(l, i, unknown))
+            else:
+                out.append(None)
+        return out
+
+    def _pop_name(self, p):
+        return "all_pops" if p == _lib.ALL_POPS else self.populations[p]
+
+    def _format_subject(self, sid, res, s, unknown, files):
+        cfgd = self.config
+        ho, po = int(res["hap_off"][s]), int(res["pop_off"][s])
+        nu, np_, nup, npp = (int(res[k][s]) for k in ("n_umug", "n_pmug", "n_umug_pops", "n_pmug_pops"))
+        hr, pr = res["hap_rows"], res["pop_rows"]
+        if cfgd["output_haplotypes"]:
+            rows = files["pmug"]
+            for k in range(np_):
+                row = hr[ho + nu + k]
+                h1 = "~".join(x for x in self._decode(row["a"], unknown) if x is not None)
+                h2 = "~".join(x for x in self._decode(row["b"], unknown) if x is not None)
+                rows.append(sid + "," + h1 + "+" + h2 + "," + str(float(row["prob"])) + "," + str(k) + "\n")
+            rows = files["pmug_pops"]
+            for k in range(npp):
+                row = pr[po + nup + k]
+                rows.append(sid + "," + self._pop_name(int(row["pa"])) + "," + self._pop_name(int(row["pb"])) + ","
+                            + str(float(row["prob"])) + "," + str(k) + "\n")
+        if cfgd["output_MUUG"]:
+            rows = files["umug"]
+            for k in range(nu):
+                row = hr[ho + k]
+                a = self._decode(row["a"], unknown)
+                b = self._decode(row["b"], unknown)
+                geno = "^".join("+".join(sorted([x, y])) for x, y in zip(a, b) if x is not None)
+                rows.append(sid + "," + geno + "," + str(float(row["prob"])) + "," + str(k) + "\n")
+            rows = files["umug_pops"]
+            planc = int(res["plan_umug"][s]) == _lib.PLAN_C
+            for k in range(nup):
+                row = pr[po + k]
+                names = sorted([self._pop_name(int(row["pa"])), self._pop_name(int(row["pb"]))])
+                prob = str(float(row["prob"]))
+                if planc and int(res["tot_umug"][s]) == 0:
+                    prob = "0"  # sum() of an empty dict is the int 0 (impute.py:1376)
+                rows.append(sid + "," + names[0] + "," + names[1] + "," + prob + "," + str(k) + "\n")
+
+    # ------------------------------------------------------------------ public entry points
+    def impute_lines(self, lines, first_index=0):
+        """Imputes an iterable of input lines; returns the six output texts as lists of rows."""
+        files = {k: [] for k in ("umug", "umug_pops", "pmug", "pmug_pops", "miss", "problem")}
+        pending = []
+        for i, raw in enumerate(lines, first_index):
+            pending.append((i, raw))
+            if len(pending) >= self.batch_size:
+                self._process(pending, files)
+                pending = []
+        if pending:
+            self._process(pending, files)
+        return files
+
+    def _process(self, pending, files):
+        cfgd = self.config
+        meta = []   # (line index, id, raw, host class, unknown map)
+        enc = []
+        for i, raw in pending:
+            raw = raw.rstrip()
+            fields = raw.split(",") if "," in raw else raw.split("%")
+            sid = fields[0]
+            hclass, unknown, item = H_OK, None, (0, None, None, 0)
+            if len(fields) < 2 or len(fields) == 3:
+                hclass = H_FAULT                       # IndexError in the reference's line parser
+            else:
+                gl = fields[1]
+                race1 = race2 = None
+                if len(fields) > 2:
+                    race1, race2 = fields[2], fields[3]
+                pidx = self._prior_for(race1, race2)
+                if not gl:
+                    hclass = H_PROBLEM
+                else:
+                    hclass, payload = self._encode_gl(gl)
+                    if hclass == H_OK and payload != "foreign":
+                        mask, counts, flat, unknown = payload
+                        item = (mask, counts, flat, pidx)
+            meta.append((i, sid, raw, hclass, unknown))
+            enc.append(item)
+        res = self._run_batch(enc, self.workspace)
+        retry = [s for s in range(len(enc)) if res["status"][s] == _lib.ST_WORKSPACE]
+        big = None
+        if retry:
+            self.stats["workspace_retries"] += len(retry)
+            big = self._run_batch([enc[s] for s in retry], self.big_workspace)
+            if any(big["status"][k] == _lib.ST_WORKSPACE for k in range(len(retry))):
+                raise MemoryError("subject exceeds GRIMB_BIG_WORKSPACE; raise it and rerun")
+        retry_pos = {s: k for k, s in enumerate(retry)}
+        for s, (i, sid, raw, hclass, unknown) in enumerate(meta):
+            self.stats["subjects"] += 1
+            if hclass == H_PROBLEM:
+                files["problem"].append(str(i) + "," + str(sid) + "\n")
+                continue
+            if hclass == H_FAULT:
+                files["problem"].append(raw + "\n")
+                continue
+            r, k = (res, s) if s not in retry_pos else (big, retry_pos[s])
+            st = int(r["status"][k])
+            self.stats["pair_evals"] += int(r["pair_evals"][k])
+            if st == _lib.ST_FAULT:
+                files["problem"].append(raw + "\n")
+                continue
+            if st == _lib.ST_NO_PHASES:
+                # nothing opens (reference: defaults returned, the PMUG writer then raises)
+                if cfgd["output_haplotypes"]:
+                    files["problem"].append(raw + "\n")
+                continue
+            tot_u, tot_p = int(r["tot_umug"][k]), int(r["tot_pmug"][k])
+            self.stats["plan"][int(r["plan_umug"][k] if cfgd["output_MUUG"] else r["plan_pmug"][k])] += 1
+            pm_empty = (tot_p == 0) if cfgd["output_haplotypes"] else False
+            if pm_empty and tot_u == 0:
+                files["miss"].append(str(i) + "," + str(sid) + "\n")
+            self._format_subject(sid, r, k, unknown, files)
+
+    def impute_file(self, config, planb=None, em_mr=False, em=False):
+        """Reads config["imputation_input_file"], writes the six output files
+        (impute.py:1985-2155 of the reference)."""
+        if em_mr or em:
+            raise NotImplementedError("EM output modes are outside the B200 hot path (SURVEY 8f-4)")
+        if os.path.isfile(config.get("bin_imputation_input_file", "None")):
+            raise NotImplementedError("per-subject phase masks are outside the B200 hot path (SURVEY 8f-4)")
+        if planb is not None and bool(planb) != bool(config["planb"]):
+            self.cfg.planb = 1 if planb else 0
+        with open(config["imputation_input_file"]) as f:
+            files = self.impute_lines(f)
+        targets = {"miss": "imputation_out_miss_file", "problem": "imputation_out_problem_file"}
+        if config["output_MUUG"]:
+            targets["umug"] = "imputation_out_umug_freq_file"
+            targets["umug_pops"] = "imputation_out_umug_pops_file"
+        if config["output_haplotypes"]:
+            targets["pmug"] = "imputation_out_hap_freq_file"
+            targets["pmug_pops"] = "imputation_out_hap_pops_file"
+        for k, ck in targets.items():
+            with open(config[ck], "w") as f:
+                f.writelines(files[k])

@@ -1,0 +1,105 @@
+"""Configuration + driver of the B200 build: same JSON keys, defaults and output file layout
+as grim/run_impute_def.py:41-211 of the reference; the Graph is built on the GPU from
+`freq_file` (hpf.csv) instead of being loaded from the nodes/edges/top_links CSV files."""
+import json
+import pathlib
+from pathlib import Path
+
+from .imputation.impute import Imputation
+from .imputation.networkx_graph import Graph
+
+
+def full_path(output, original_path):
+    # <dir of original_path>/<output>/<file name>, as the reference places its outputs
+    p = Path(original_path)
+    return str(p.parent / output / p.name)
+
+
+def load_config(json_conf, project_dir_graph="", project_dir_in_file=""):
+    """JSON -> config dict (keys and defaults of the reference, run_impute_def.py:63-129, plus the
+    graph-side keys freq_file / freq_trim_threshold the table build needs)."""
+    graph_files_path = json_conf.get("graph_files_path", "output/csv/")
+    if graph_files_path[-1] != "/":
+        graph_files_path += "/"
+    output_dir = json_conf.get("imputation_out_path", "output")
+    if output_dir[-1] != "/":
+        output_dir += "/"
+    g = json_conf.get
+    config = {
+        "planb": g("planb", True),
+        "pops": g("populations"),
+        "priority": g("priority"),
+        "epsilon": g("epsilon", 1e-3),
+        "number_of_results": g("number_of_results", 1000),
+        "number_of_pop_results": g("number_of_pop_results", 100),
+        "output_MUUG": g("output_MUUG", True),
+        "output_haplotypes": g("output_haplotypes", False),
+        "node_file": project_dir_graph + graph_files_path + g("node_csv_file", "nodes.csv"),
+        "top_links_file": project_dir_graph + graph_files_path + g("top_links_csv_file", "top_links.csv"),
+        "edges_file": project_dir_graph + graph_files_path + g("edges_csv_file", "edges.csv"),
+        "imputation_input_file": project_dir_in_file + g("imputation_in_file", ""),
+        "imputation_out_umug_freq_file": full_path(output_dir, g("imputation_out_umug_freq_filename", "out.umug")),
+        "imputation_out_umug_pops_file": full_path(output_dir, g("imputation_out_umug_pops_filename", "out.umug.pops")),
+        "imputation_out_hap_freq_file": full_path(output_dir, g("imputation_out_hap_freq_filename", "out.pmug")),
+        "imputation_out_hap_pops_file": full_path(output_dir, g("imputation_out_hap_pops_filename", "out.pmug.pops")),
+        "imputation_out_miss_file": full_path(output_dir, g("imputation_out_miss_filename", "out.miss")),
+        "imputation_out_problem_file": full_path(output_dir, g("imputation_out_problem_filename", "out.problem")),
+        "factor_missing_data": g("factor_missing_data", 0.01),
+        "loci_map": g("loci_map", {"A": 1, "B": 3, "C": 2, "DQB1": 4, "DRB1": 5}),
+        "matrix_planb": g(
+            "Plan_B_Matrix",
+            [
+                [[1, 2, 3, 4, 5]],
+                [[1, 2, 3], [4, 5]],
+                [[1], [2, 3], [4, 5]],
+                [[1, 2, 3], [4], [5]],
+                [[1], [2, 3], [4], [5]],
+                [[1], [2], [3], [4], [5]],
+            ],
+        ),
+        "pops_count_file": project_dir_graph + g("pops_count_file", ""),
+        "use_pops_count_file": g("pops_count_file", False),
+        "number_of_options_threshold": g("number_of_options_threshold", 100000),
+        "max_haplotypes_number_in_phase": g("max_haplotypes_number_in_phase", 100),
+        "bin_imputation_input_file": project_dir_in_file + g("bin_imputation_in_file", "None"),
+        "nodes_for_plan_A": g("Plan_A_Matrix", []),
+        "save_mode": g("save_space_mode", False),
+        "UNK_priors": g("UNK_priors", "MR"),
+        # graph-side keys (generate_neo4j_multi_hpf.py:243-256 of the reference)
+        "freq_file": project_dir_graph + g("freq_file", "output/hpf.csv"),
+        "freq_trim_threshold": g("freq_trim_threshold", 1e-5),
+        "imputation_out_path": output_dir,
+    }
+    if config["nodes_for_plan_A"]:
+        raise NotImplementedError("Plan_A_Matrix label restriction is outside the B200 hot path (SURVEY 8f-3)")
+    all_loci = {str(v) for v in config["loci_map"].values()}
+    config["full_loci"] = "".join(sorted(all_loci))
+    return config
+
+
+def run_impute(conf_file="../conf/minimal-configuration.json", project_dir_graph="", project_dir_in_file="",
+               hap_pop_pair=False, graph=None, device=0):
+    with open(conf_file) as f:
+        json_conf = json.load(f)
+    config = load_config(json_conf, project_dir_graph, project_dir_in_file)
+    print("*" * 100)
+    print("Performing imputation based on:")
+    for label, key in (("Population", "pops"), ("Priority", "priority"), ("UNK priority", "UNK_priors"),
+                       ("Epsilon", "epsilon"), ("Plan B", "planb"), ("Number of Results", "number_of_results"),
+                       ("Number of Population Results", "number_of_pop_results"), ("Freq File", "freq_file"),
+                       ("Input File", "imputation_input_file"), ("Output UMUG Format", "output_MUUG"),
+                       ("Output Haplotype Format", "output_haplotypes"), ("Factor Missing Data", "factor_missing_data"),
+                       ("Loci Map", "loci_map"), ("Plan B Matrix", "matrix_planb"),
+                       ("Pops Count File", "pops_count_file"),
+                       ("Number of Options Threshold", "number_of_options_threshold"),
+                       ("Max Number of haplotypes in phase", "max_haplotypes_number_in_phase"),
+                       ("Save space mode", "save_mode")):
+        print("\t{}: {}".format(label, config[key]))
+    print("*" * 100)
+    if graph is None:
+        graph = Graph(config, device=device)
+        graph.build_graph(config["node_file"], config["top_links_file"], config["edges_file"])
+    imputation = Imputation(graph, config)
+    pathlib.Path(config["imputation_out_path"]).mkdir(parents=False, exist_ok=True)
+    imputation.impute_file(config, em_mr=hap_pop_pair)
+    return graph
