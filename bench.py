@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: subjects/sec (+ hap-pair evals/sec) of the per-subject
+imputation hot path on N B200s, beside the CPU port of the reference on the host cores.
+
+Workload (BASELINE.json configs[1], SURVEY 8(d) "C2"): S = 2^20 synthetic, fully typed,
+unambiguous 5-locus subjects, one population, haplotypes drawn proportional to frequency from
+a synthetic Zipf table of N_full = 1M haplotypes (alleles/locus 700/1200/600/250/700, seed
+20261018; subjects seed 1), minimal-configuration keys with number_of_results 10, UMUG + PMUG
+outputs, Plan B on.  One step = one pass of the hot path over the whole batch.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--subjects S] [--haps H]
+
+value  : subjects/s, batch already resident in HBM, CUDA-event timed (max over ranks)
+e2e    : same through grimb_impute_host with pinned HOST buffers (H2D + kernel + D2H per step)
+roofline / cpu_baseline: see DESIGN.md "Measurement".
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "py-graph-imputation_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+LOCI = ["A", "B", "C", "DQB1", "DRB1"]
+N_ALLELES = [700, 1200, 600, 250, 700]
+TABLE_SEED = 20261018
+SUBJECT_SEED = 1
+
+
+# --------------------------------------------------------------------------- workload
+def make_table(n_full):
+    """-> (allele names per locus, full_alleles uint16 [N][5] (1-based ids), freqs [N][1])."""
+    rng = np.random.RandomState(TABLE_SEED)
+    cols = []
+    for na in N_ALLELES:
+        w = 1.0 / np.arange(1, na + 1) ** 1.1
+        w /= w.sum()
+        cols.append(rng.choice(na, size=int(n_full * 1.25) + 1000, p=w))
+    tup = np.stack(cols, axis=1).astype(np.int64)
+    packed = np.zeros(len(tup), np.int64)
+    for l in range(5):
+        packed = packed * 2048 + tup[:, l]
+    _u, first = np.unique(packed, return_index=True)
+    tup = tup[np.sort(first)][:n_full]
+    n = len(tup)
+    f = 1.0 / np.arange(1, n + 1)
+    f /= f.sum()
+    names = [["%s*%02d:%02d" % (loc, a // 60 + 1, a % 60 + 1) for a in range(na)] for loc, na in zip(LOCI, N_ALLELES)]
+    return names, (tup + 1).astype(np.uint16), f.reshape(n, 1).astype(np.float64)
+
+
+def make_subjects(full_alleles, freqs, n_subj, seed):
+    """Encoded batch (GrimbBatch arrays) of fully typed unambiguous subjects."""
+    rng = np.random.RandomState(seed)
+    p = freqs[:, 0] / freqs[:, 0].sum()
+    idx = rng.choice(len(p), size=(n_subj, 2), p=p)
+    flip = rng.rand(n_subj, 5) < 0.5
+    h1 = full_alleles[idx[:, 0]]
+    h2 = full_alleles[idx[:, 1]]
+    a = np.where(flip, h2, h1)
+    b = np.where(flip, h1, h2)
+    alleles = np.stack([a, b], axis=2).astype(np.uint16)          # [S][L][2]
+    batch = {
+        "typed_mask": np.full(n_subj, 31, np.uint16),
+        "counts": np.ones((n_subj, 5, 2), np.uint16),
+        "allele_off": (np.arange(n_subj + 1, dtype=np.uint64) * 10).astype(np.uint32),
+        "alleles": np.ascontiguousarray(alleles.reshape(-1)),
+        "prior_index": np.zeros(n_subj, np.uint32),
+        "priors": np.ones((1, 1, 1), np.float64),
+    }
+    return batch, alleles
+
+
+def subject_lines(names, alleles, lo, hi):
+    out = []
+    for s in range(lo, hi):
+        gl = "^".join(names[l][alleles[s, l, 0] - 1] + "+" + names[l][alleles[s, l, 1] - 1] for l in range(5))
+        out.append("S%d,%s,CAU,CAU\n" % (s, gl))
+    return out
+
+
+def base_conf():
+    conf = json.load(open(os.path.join(ROOT, "tests", "golden", "data", "base_conf.json")))
+    conf["number_of_results"] = 10
+    return conf
+
+
+# --------------------------------------------------------------------------- CPU port (oracle)
+class _FullOnlyGraph(object):
+    """Oracle-side store holding only what fully typed subjects probe (the full-label dict).
+    The reference's Graph would hold every marginal too (~30x more nodes); for this workload
+    Plan A always hits, so per-subject CPU work is identical and the (untimed) build stays
+    feasible in pure Python."""
+
+    def __init__(self, names, full_alleles, freqs):
+        import grim_oracle as go
+        self.full_label = "12345"
+        self.pops = ["CAU"]
+        self.node = {}
+        self.names = []
+        cols = [np.array(names[l], dtype=object)[full_alleles[:, l] - 1] for l in range(5)]
+        for i in range(len(full_alleles)):
+            nm = "~".join(c[i] for c in cols)
+            self.node[nm] = ("12345", [float(freqs[i, 0])], i)
+        self.adjs_query = go.OracleGraph.adjs_query.__get__(self)
+        self.node_probs = go.OracleGraph.node_probs.__get__(self)
+        self.toplinks = {}
+        self.conn = {}
+        self.by_label = {}
+
+
+def cpu_port_rate(names, full_alleles, freqs, alleles, n_sample, procs):
+    """subjects/s of the oracle port on `procs` forked processes over the first n_sample subjects."""
+    import multiprocessing as mp
+
+    import grim_oracle as go
+    g = _FullOnlyGraph(names, full_alleles, freqs)
+    cfg = go.load_config(base_conf())
+    lines = subject_lines(names, alleles, 0, n_sample)
+    chunks = [lines[i::procs] for i in range(procs)]
+
+    def work(ch, q):
+        imp = go.OracleImputation(g, cfg, np.ones(1))
+        t = time.time()
+        out = imp.impute_lines(ch)
+        q.put((time.time() - t, imp.pair_evals, out["umug"].count("\n"), out["problem"].count("\n")))
+
+    q = mp.Queue()
+    t0 = time.time()
+    ps = [mp.Process(target=work, args=(ch, q)) for ch in chunks]
+    for p_ in ps:
+        p_.start()
+    res = [q.get() for _ in ps]
+    for p_ in ps:
+        p_.join()
+    wall = time.time() - t0
+    evals = sum(r[1] for r in res)
+    return n_sample / wall, evals / wall, wall, sum(r[3] for r in res)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu = gpu
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].startswith("Active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons}
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    names, fa, ff = make_table(args.haps)
+    _batch, alleles = make_subjects(fa, ff, args.subjects, SUBJECT_SEED)
+    cores = os.cpu_count() or 1
+    n_sample = min(args.subjects, args.ref_sample * cores)
+    vals = []
+    for _ in range(args.warmup + args.steps):
+        rate, erate, wall, prob = cpu_port_rate(names, fa, ff, alleles, n_sample, cores)
+        vals.append((rate, erate, wall))
+    vals = vals[args.warmup:]
+    rate = float(np.mean([v[0] for v in vals]))
+    line = {
+        "impl": "reference", "metric": "subjects_per_sec", "value": rate, "unit": "subjects/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * float(np.mean([v[2] for v in vals])),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "pair_evals_per_sec": float(np.mean([v[1] for v in vals])),
+        "config": workload_config(args),
+        "cpu_baseline": {"value": rate, "unit": "subjects/s", "cores": cores, "kind": "port",
+                         "sample": "first %d of the %d subjects, %d forked processes (oracle/grim_oracle.py; the "
+                                   "reference is pure Python and cannot travel to the GPU box)" % (n_sample, args.subjects, cores)},
+        "e2e": {"value": rate, "unit": "subjects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": "C2: %d fully typed unambiguous 5-locus subjects, 1 population, synthetic Zipf table of %d "
+                        "haplotypes, UMUG+PMUG top-10, Plan B on" % (args.subjects, args.haps),
+            "subjects_per_gpu": args.subjects, "table_haplotypes": args.haps,
+            "l2": "inputs + tables exceed L2 (no flush needed)"}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--subjects", type=int, default=1 << 20)
+    ap.add_argument("--haps", type=int, default=1000000)
+    ap.add_argument("--ref-sample", type=int, default=2500, help="CPU port: subjects per core per step")
+    ap.add_argument("--cpu-sample", type=int, default=12000, help="cpu_baseline: subjects on 1 core")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from grim.imputation import _lib
+    from grim.imputation.impute import make_config
+    from grim.imputation.networkx_graph import Graph
+    from grim.run_impute_def import load_config
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    conf = load_config(base_conf())
+    names, fa, ff = make_table(args.haps)
+
+    # ---- tables: built once on rank 0, replicated with one NCCL broadcast of the device image
+    g = Graph(conf, device=local)
+    t_build = time.time()
+    if rank == 0:
+        g.from_arrays(names, fa, ff)
+    if world > 1:
+        size = torch.zeros(1, dtype=torch.int64, device=dev)
+        if rank == 0:
+            nbytes = C.c_int64()
+            _lib.check(lib.grimb_tables_image_size(g.handle, C.byref(nbytes)), "image_size")
+            size[0] = nbytes.value
+        dist.broadcast(size, 0)
+        nb = int(size.item())
+        if rank == 0:
+            ptr = C.c_void_p()
+            _lib.check(lib.grimb_tables_image_ptr(g.handle, C.byref(ptr)), "image_ptr")
+
+            class _View(object):
+                __cuda_array_interface__ = {"shape": (nb,), "typestr": "|u1", "data": (ptr.value, False), "version": 2}
+            img = torch.as_tensor(_View(), device=dev)
+        else:
+            img = torch.empty(nb, dtype=torch.uint8, device=dev)
+        dist.broadcast(img, 0)
+        torch.cuda.synchronize()
+        if rank != 0:
+            g.alleles = names
+            g.allele_id = [{a: i + 1 for i, a in enumerate(al)} for al in names]
+            from grim.imputation.networkx_graph import key_layout
+            g.key_bits = key_layout([len(a) for a in names])
+            g.shift = [int(sum(g.key_bits[:l])) for l in range(5)]
+            h = C.c_void_p()
+            _lib.check(lib.grimb_tables_from_image(C.c_void_p(img.data_ptr()), nb, local, C.byref(h)), "from_image")
+            g.handle = h
+            del img
+    t_build = time.time() - t_build
+    info = g.info()
+
+    # ---- subjects: every rank imputes its own shard (weak scaling: S per GPU)
+    batch, alleles = make_subjects(fa, ff, args.subjects, SUBJECT_SEED + rank)
+    S = args.subjects
+    cfg = make_config(conf, LOCI, 1)
+    eng = g.engine(8 << 20)
+
+    def tens(a, pin=False):
+        t = torch.from_numpy(a)
+        return t.pin_memory() if pin else t
+
+    keys_in = ["typed_mask", "counts", "allele_off", "alleles", "prior_index", "priors"]
+    out_spec = [("status", np.uint8), ("plan_umug", np.uint8), ("plan_pmug", np.uint8), ("n_umug", np.uint32),
+                ("n_pmug", np.uint32), ("n_umug_pops", np.uint32), ("n_pmug_pops", np.uint32), ("tot_umug", np.uint32),
+                ("tot_pmug", np.uint32), ("hap_off", np.uint64), ("pop_off", np.uint64), ("pair_evals", np.uint64)]
+    hap_cap, pop_cap = S * 8, S * 4
+    needed = np.zeros(2, np.int64)
+
+    def make_structs(inputs, outputs, hap_rows, pop_rows):
+        b = _lib.Batch()
+        b.n_subjects = S
+        for k in keys_in:
+            setattr(b, k, inputs[k].data_ptr())
+        b.n_alleles_total = S * 10
+        b.n_priors = 1
+        r = _lib.Results()
+        for k, _ in out_spec:
+            setattr(r, k, outputs[k].data_ptr())
+        r.hap_rows, r.hap_capacity = hap_rows.data_ptr(), hap_cap
+        r.pop_rows, r.pop_capacity = pop_rows.data_ptr(), pop_cap
+        r.hap_rows_needed = needed[0:].ctypes.data
+        r.pop_rows_needed = needed[1:].ctypes.data
+        return b, r
+
+    # device-resident leg
+    d_in = {k: tens(batch[k].view(np.int16) if batch[k].dtype == np.uint16 else
+                    batch[k].view(np.int32) if batch[k].dtype == np.uint32 else batch[k]).to(dev) for k in keys_in}
+    d_out = {k: torch.zeros(S * np.dtype(dt).itemsize, dtype=torch.uint8, device=dev) for k, dt in out_spec}
+    d_hap = torch.zeros(hap_cap * 24, dtype=torch.uint8, device=dev)
+    d_pop = torch.zeros(pop_cap * 16, dtype=torch.uint8, device=dev)
+    db, dr = make_structs(d_in, d_out, d_hap, d_pop)
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        rc = lib.grimb_impute_device(eng, C.byref(cfg), C.byref(db), C.byref(dr), C.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "grimb_impute_device")
+
+    # host leg (pinned buffers; copies inside the timed region)
+    h_in = {k: tens(batch[k].view(np.int16) if batch[k].dtype == np.uint16 else
+                    batch[k].view(np.int32) if batch[k].dtype == np.uint32 else batch[k], pin=True) for k in keys_in}
+    h_out = {k: torch.zeros(S * np.dtype(dt).itemsize, dtype=torch.uint8).pin_memory() for k, dt in out_spec}
+    h_hap = torch.zeros(hap_cap * 24, dtype=torch.uint8).pin_memory()
+    h_pop = torch.zeros(pop_cap * 16, dtype=torch.uint8).pin_memory()
+    hb, hr = make_structs(h_in, h_out, h_hap, h_pop)
+
+    def step_host():
+        rc = lib.grimb_impute_host(eng, C.byref(cfg), C.byref(hb), C.byref(hr))
+        _lib.check(rc, "grimb_impute_host")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record(stream)
+        for i in range(steps):
+            fn()
+            ev[i + 1].record(stream)
+        barrier()
+        ms = ev[0].elapsed_time(ev[steps])
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.grimb_engine_launches(eng)
+    ms_dev = timed(step_device, args.steps, args.warmup)
+    launches = lib.grimb_engine_launches(eng) - launches0 - args.warmup
+    hap_rows_n, pop_rows_n = int(needed[0]), int(needed[1])
+    evals = int(d_out["pair_evals"].view(torch.int64).sum().item())
+    status = d_out["status"].cpu().numpy()
+    hits = int(d_out["tot_pmug"].view(torch.int32).sum().item())
+    ms_host = timed(step_host, args.steps, args.warmup)
+    sampler.stop_flag = True
+
+    # ---- spot parity against the oracle on the first subjects of rank 0 (not timed)
+    parity = None
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        import grim_oracle as go
+        from grim.imputation.impute import Imputation
+        n_c = min(S, args.cpu_sample)
+        lines = subject_lines(names, alleles, 0, n_c)
+        og = _FullOnlyGraph(names, fa, ff)
+        oimp = go.OracleImputation(og, go.load_config(base_conf()), np.ones(1))
+        t0 = time.time()
+        ref = oimp.impute_lines(lines)
+        t_cpu = time.time() - t0
+        imp = Imputation(g, conf, np.ones(1))
+        mine = {k: "".join(v) for k, v in imp.impute_lines(lines).items()}
+        parity = all(mine[k] == ref[k] for k in ref)
+        cpu = {"value": n_c / t_cpu, "unit": "subjects/s", "cores": 1, "kind": "port",
+               "sample": "first %d of the %d subjects through oracle/grim_oracle.py on one core; outputs "
+                         "compared with the CUDA path: %s" % (n_c, S, "identical" if parity else "DIFFERENT"),
+               "pair_evals_per_sec": oimp.pair_evals / t_cpu}
+
+    if rank == 0:
+        total = S * world
+        # algorithmic bytes per launch (DESIGN.md "Measurement"): per subject 36 B of input, 2^L = 32
+        # probes x one 32 B sector, per hit a 32 B frequency sector, 51 B result header, plus the rows written
+        algo = S * (36 + 32 * 32 + 51) + hits * 2 * 32 + hap_rows_n * 24 + pop_rows_n * 16
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = algo / (ms_dev * 1e-3) / 1e9
+        h2d = sum(batch[k].nbytes for k in keys_in)
+        d2h = sum(S * np.dtype(dt).itemsize for _, dt in out_spec) + hap_rows_n * 24 + pop_rows_n * 16
+        line = {
+            "metric": "subjects_per_sec", "value": total / (ms_dev * 1e-3), "unit": "subjects/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "pair_evals_per_sec": evals * world / (ms_dev * 1e-3),
+            "e2e": {"value": total / (ms_host * 1e-3), "unit": "subjects/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_host},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
+                         "algorithmic_bytes_per_launch": algo, "kernel": "k_impute"},
+            "cpu_baseline": cpu,
+            "clocks": sampler.summary(),
+            "table": {"n_nodes": info["n_nodes"], "device_bytes": info["device_bytes"], "build_s": t_build},
+            "status_counts": {str(i): int(c) for i, c in enumerate(np.bincount(status, minlength=6)) if c},
+            "parity_sample_identical": parity,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

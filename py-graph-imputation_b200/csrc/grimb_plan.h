@@ -74,7 +74,7 @@ struct Subject : Ctx {
 
   // reduce_phase_to_valid_allels :864-879 (VALID), reduce_phase_to_commons_alleles :881-912
   // (C10: ten best, C1: the best) -- a function of the original list and the prior diagonal.
-  GD void make_variant(int var) {
+  GDN void make_variant(int var) {
     uint32_t total = 0;
     for (int t = 0; t < n; ++t) total += sh->lcnt[VAR_ORIG][t][0] + sh->lcnt[VAR_ORIG][t][1];
     uint16_t* buf = alloc<uint16_t>(total);
@@ -148,7 +148,7 @@ struct Subject : Ctx {
   }
 
   // Returns the number of opened phases.
-  GD int open_all() {
+  GDN int open_all() {
     g.sync();
     const uint64_t thr_opt = (uint64_t)cfg->options_threshold;
     for (int slot = 0; slot < 2 * nph; ++slot) {
@@ -219,7 +219,7 @@ struct Subject : Ctx {
   // ------------------------------------------------------------------ Plan B side evaluation
   // One block of a matrix row -> ordered list of nodes (impute.py:1015-1039, 1207-1216,
   // networkx_graph.py:280-321).  Returns false if the side result must be empty.
-  GD bool build_block(int slot, uint32_t bm, bool first_block, BlockList& out) {
+  GDN bool build_block(int slot, uint32_t bm, bool first_block, BlockList& out) {
     const SlotDesc sd = slots[slot];
     const uint32_t tp = bm & typed, up = bm & ~typed;
     out.ids = nullptr;
@@ -398,7 +398,7 @@ struct Subject : Ctx {
 
   // find_option_freq (impute.py:1072-1115) for one side and one matrix row, streamed into the
   // top-K selector.
-  GD void slot_plan_b_row(int slot, int row) {
+  GDN void slot_plan_b_row(int slot, int row) {
     const int P = T.P;
     const uint64_t mark = ar_used;
     const int nb = cfg->row_blocks[row];
@@ -539,7 +539,7 @@ struct Subject : Ctx {
 
   // find_option_freq_missing_data (impute.py:1142-1172): alleles of the loci in `nid` are not in
   // the table; look the rest up, re-insert them, scale by factor_missing_data^|nid|.
-  GD void slot_missing_data(int slot, uint32_t nid) {
+  GDN void slot_missing_data(int slot, uint32_t nid) {
     const SlotDesc sd = slots[slot];
     sel_begin();
     const uint32_t have = typed & ~nid, want = full & ~nid, up = want & ~have;
@@ -613,7 +613,7 @@ struct Subject : Ctx {
   }
 
   // comp_phase_prob_plan_b (impute.py:1392-1570), evaluated at epsilon = 0
-  GD void plan_b() {
+  GDN void plan_b() {
     g.sync();
     const uint32_t nid1 = not_in_data(0, -1), nid2 = not_in_data(1, -1);
     g.sync();
@@ -709,7 +709,7 @@ struct Subject : Ctx {
   // loci filled with every node of the untyped label.
   GD double sr_sum(uint32_t node) const { return py_sum(T.freq + (uint64_t)node * T.P, T.P); }
 
-  GD void slot_plan_c(int slot) {
+  GDN void slot_plan_c(int slot) {
     const SlotDesc sd = slots[slot];
     const uint32_t ul = full & ~typed;
     const uint32_t ufirst = ul ? T.label_first[ul] : 0, ucnt = ul ? T.label_count[ul] : 0;
@@ -754,19 +754,16 @@ struct Subject : Ctx {
       for (uint64_t b = 0; b < sd.ncand; b += g.n) {
         uint64_t c = b + g.tid;
         bool in = c < sd.ncand && cval[c] >= 0;
+        double v = in ? cval[c] : 0.0;
+        uint64_t k = in ? ckey[c] : 0ull;
         uint32_t total;
-        uint32_t pos = g.scan_excl(in ? 1u : 0u, total);
-        g.sync();
+        uint32_t pos = g.scan_excl(in ? 1u : 0u, total);  // barriers inside: all reads are done
         if (in) {
-          double v = cval[c];
-          uint64_t k = ckey[c];
-          g.sync();
           cval[nc + pos] = v;
           ckey[nc + pos] = k;
-        } else {
-          g.sync();
         }
         nc += total;
+        g.sync();
       }
       g.sync();
       if (ul && ucnt && nc) {
@@ -838,7 +835,7 @@ struct Subject : Ctx {
   }
 
   // comp_phase_prob_plan_c (impute.py:1313-1389): epsilon 0, prior all ones, one pseudo-population
-  GD void plan_c() {
+  GDN void plan_c() {
     g.sync();
     if (g.tid == 0)
       for (int s = 0; s < 2 * nph; ++s) {
@@ -863,7 +860,7 @@ struct Subject : Ctx {
   // ------------------------------------------------------------------ epsilon schedule
   // call_comp_phase_prob (impute.py:1658-1724).  Leaves the final (deduplicated) accepted
   // pairs in ent[0..ent_n) and returns the plan that produced them.
-  GD int evaluate() {
+  GDN int evaluate() {
     g.sync();
     if (g.tid == 0)
       for (int s = 0; s < 2 * nph; ++s) {
@@ -915,7 +912,7 @@ struct Subject : Ctx {
   }
 
   // ------------------------------------------------------------------ emission
-  GD void emit(int which, bool planc, uint32_t* tot_out) {
+  GDN void emit(int which, bool planc, uint32_t* tot_out) {
     // which 0: UMUG (+ sorted pops), 1: PMUG (+ first-seen pops)
     uint32_t rows = 0;
     uint32_t ng = aggregate(which == 0 ? 0 : 1, (uint32_t)cfg->n_results, st_hap[which], nullptr, &st_cnt[which]);
@@ -1071,8 +1068,11 @@ GD void run_subject(Subject& S, const GrimbBatch& B, const OutArrays& O, uint64_
         S.ent_cap = (uint32_t)cap;
         S.ent = S.alloc<Entry>(S.ent_cap);
         bool reduced = false, faulted = false;
+        uint64_t shared_evals = 0;
         if (cfg->output_umug) {
+          const uint64_t e0 = S.pair_evals;
           plan_u = (uint8_t)S.evaluate();
+          shared_evals = S.pair_evals - e0;
           if (!S.ws_fail && cfg->planb && S.ent_n == 0) {
             plan_u = GRIMB_PLAN_C;
             S.make_variant(VAR_C1);  // prior is all ones here
@@ -1088,7 +1088,10 @@ GD void run_subject(Subject& S, const GrimbBatch& B, const OutArrays& O, uint64_
         }
         if (cfg->output_pmug && !S.ws_fail && !faulted) {
           if (!cfg->output_umug || reduced) plan_p = (uint8_t)S.evaluate();
-          else plan_p = plan_u;
+          else {
+            plan_p = plan_u;
+            S.pair_evals += shared_evals;  // the reference evaluates again for the haplotype output
+          }
           if (!S.ws_fail && cfg->planb && S.ent_n == 0) {
             plan_p = GRIMB_PLAN_C;
             if (!reduced) {

@@ -188,7 +188,7 @@ struct Ctx {
     g.sync();
   }
 
-  GD void sel_compact() {
+  GDN void sel_compact() {
     uint32_t cnt = sh->sel_n;
     for (uint32_t i = g.tid; i < cnt; i += g.n) sel_idx[i] = i;
     g.sync();
@@ -294,7 +294,7 @@ struct Ctx {
   }
 
   // Plan A probe of one side (adjs_query): full-label node -> itself, partial -> top links.
-  GD void slot_plan_a(int slot) {
+  GDN void slot_plan_a(int slot) {
     const SlotDesc sd = slots[slot];
     sel_begin();
     const bool isfull = (typed == full);
@@ -332,7 +332,7 @@ struct Ctx {
 
   // ---------------------------------------------------------------- pair evaluation
   // Appends the accepted pairs of every opened phase, in (phase, h, k) order, to ent[].
-  GD void gen_entries(double eps) {
+  GDN void gen_entries(double eps) {
     const int P = plan_c_single ? 1 : T.P;
     ent_n = 0;
     for (int p = 0; p < nph; ++p) {
@@ -393,7 +393,7 @@ struct Ctx {
 
   // geno_seen (impute.py:508-513): keep the first entry of every unordered {(hap,pop),(hap,pop)}.
   // Compacts ent[] in place (order preserved); returns MaxProb over the kept entries.
-  GD double dedup_entries() {
+  GDN double dedup_entries() {
     if (ent_n == 0 || ws_fail) return 0.0;
     uint64_t mark = ar_used;
     uint32_t tsz = 2;
@@ -486,7 +486,7 @@ struct Ctx {
   // groups by (sum desc, first encounter asc) and writes the best `limit` rows.  Returns the
   // number of groups; *n_rows = rows written.  Rows: kind 0 -> (lo,hi); kind 1 -> (h1,h2) of
   // the first member; kind 2 -> pops of the first member (orientation as encountered).
-  GD uint32_t aggregate(int kind, uint32_t limit, GrimbHapRow* hap_rows, GrimbPopRow* pop_rows, uint32_t* n_rows) {
+  GDN uint32_t aggregate(int kind, uint32_t limit, GrimbHapRow* hap_rows, GrimbPopRow* pop_rows, uint32_t* n_rows) {
     if (g.tid == 0) *n_rows = 0;
     if (ent_n == 0 || ws_fail) return 0;
     uint64_t mark = ar_used;
