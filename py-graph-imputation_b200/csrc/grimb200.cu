@@ -628,9 +628,10 @@ extern "C" int grimb_tables_from_image(const void* dev_image, int64_t bytes, int
 // ------------------------------------------------------------------------------------------
 // imputation kernel: persistent CTAs, one subject per CTA at a time, dynamic work fetch
 // ------------------------------------------------------------------------------------------
+// `worklist` (optional): subject indices left over by k_impute_fast, count in *worklist_n.
 __global__ void __launch_bounds__(MAXT)
 k_impute(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O, char* arena, uint64_t arena_per_cta,
-         const double* ones, unsigned long long* work) {
+         const double* ones, unsigned long long* work, const uint32_t* worklist, const unsigned int* worklist_n) {
   __shared__ Shared sh;
   Subject S;
   S.g.tid = threadIdx.x;
@@ -642,13 +643,219 @@ k_impute(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArr
   S.ones = ones;
   S.ar_base = arena + (uint64_t)blockIdx.x * arena_per_cta;
   S.ar_cap = arena_per_cta;
+  const uint64_t n_work = worklist ? (uint64_t)*worklist_n : (uint64_t)B.n_subjects;
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) sh.work = (uint32_t)atomicAdd(work, 1ull);
     __syncthreads();
-    const uint64_t s = sh.work;
-    if (s >= (uint64_t)B.n_subjects) break;
-    run_subject(S, B, O, s);
+    const uint64_t w = sh.work;
+    if (w >= n_work) break;
+    run_subject(S, B, O, worklist ? (uint64_t)worklist[w] : w);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fast path: one WARP per subject for the common case of BASELINE config 2 -- every locus
+// typed, one allele per chromosome side, one population (L <= 5 so the 2^L side haplotypes map
+// onto the 32 lanes).  Lane v probes the haplotype that takes side bit_l(v) at locus l; phase i
+// (lane i < 2^(L-1)) pairs lane i with lane 2^L-1-i (gen_phases, impute.py:274-303).  The epsilon
+// schedule (impute.py:1658-1693) is a loop of ballots over the same 16 registers; sums run in
+// phase order, ranks by (probability desc, phase asc), exactly as the general kernel does.
+// Subjects that are not of this shape, or for which Plan A finds nothing (-> Plan B/C), are
+// appended to `worklist` and handled by k_impute.  Result rows are allocated with one atomicAdd
+// per CTA (8 subjects).
+// ------------------------------------------------------------------------------------------
+constexpr int FAST_WARPS = 8;
+
+__global__ void __launch_bounds__(FAST_WARPS * 32)
+k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O, uint32_t* worklist,
+              unsigned int* worklist_n) {
+  __shared__ uint32_t s_hap[FAST_WARPS], s_pop[FAST_WARPS];
+  __shared__ unsigned long long s_base[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int L = T.L;
+  const uint32_t full = (1u << L) - 1u;
+  const int nphase = 1 << (L - 1);
+  GrimbResults& R = O.r;
+  const bool want_u = cfg->output_umug != 0, want_p = cfg->output_pmug != 0;
+  const uint32_t lim_r = (uint32_t)cfg->n_results, lim_p = (uint32_t)cfg->n_pop_results;
+  const uint64_t n_groups = ((uint64_t)B.n_subjects + FAST_WARPS - 1) / FAST_WARPS;
+  for (uint64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const uint64_t s = grp * FAST_WARPS + warp;
+    bool done = false;             // handled here (rows or an empty result)
+    bool active = s < (uint64_t)B.n_subjects;
+    uint32_t typed = 0;
+    uint32_t acc_mask = 0;
+    uint64_t key = 0, key2 = 0, glo = 0, ghi = 0;
+    double prob = 0.0, total = 0.0;
+    uint32_t rank = 0, n_acc = 0;
+    uint64_t evals = 0;
+    if (active) {
+      typed = B.typed_mask[s];
+      bool shape = typed == full;
+      const uint16_t* cn = B.counts + s * (uint64_t)L * 2;
+      uint16_t c = lane < 2 * L ? cn[lane] : (uint16_t)1;
+      shape = __all_sync(0xffffffffu, c == 1) && shape;
+      if (shape) {
+        const uint16_t* al = B.alleles + B.allele_off[s];
+        const uint32_t mine = lane < 2 * L ? al[lane] : 0u;  // lane 2l+x = allele of locus l, side x
+        bool known = true;
+        uint32_t het = 0;
+        for (int l = 0; l < L; ++l) {
+          const uint32_t a0 = __shfl_sync(0xffffffffu, mine, 2 * l), a1 = __shfl_sync(0xffffffffu, mine, 2 * l + 1);
+          const uint32_t pick = (lane >> l & 1) ? a1 : a0;
+          if (pick == 0 || pick > T.n_alleles[l]) known = false;
+          key |= (uint64_t)pick << T.shift[l];
+          if (a0 != a1) het |= 1u << l;
+          const uint32_t mn = a0 < a1 ? a0 : a1, mx = a0 < a1 ? a1 : a0;
+          glo |= (uint64_t)mn << T.shift[l];
+          ghi |= (uint64_t)mx << T.shift[l];
+        }
+        double f = 0.0;
+        if (lane < (1 << L) && known) {
+          const uint32_t node = ht_lookup(T, full, key);
+          if (node != GRIMB_NONE) f = T.freq[node];  // P == 1
+        }
+        const int partner = (int)full - lane;
+        const double f2 = __shfl_sync(0xffffffffu, f, partner & 31);
+        key2 = __shfl_sync(0xffffffffu, key, partner & 31);
+        const uint32_t low = het & ((uint32_t)nphase - 1u);
+        const bool last_het = (het >> (L - 1)) & 1u;
+        const bool kept = lane < nphase && !((uint32_t)lane & ~low) && (last_het || (uint32_t)lane <= (low ^ (uint32_t)lane));
+        const bool cand = kept && f > 0 && f2 > 0;
+        const uint32_t cand_mask = __ballot_sync(0xffffffffu, cand);
+        const double m = B.priors[(uint64_t)B.prior_index[s]];
+        const bool same = key == key2;
+        if (cand) {
+          prob = f * f2 * m;
+          if (!same) prob = prob * 2;
+        }
+        // epsilon schedule
+        double eps = cfg->epsilon;
+        bool last = false;
+        while (eps > 0) {
+          eps /= 10;
+          if (eps < 1.0e-9) eps = 0.0;
+          bool a = false;
+          if (cand) {
+            const double x = eps / f;
+            a = f2 >= x && m > 0 && (same ? (m * f2 >= x * 2) : (m * f2 >= x));
+          }
+          evals += __popc(cand_mask);
+          acc_mask = __ballot_sync(0xffffffffu, a);
+          if (acc_mask) {
+            if (eps > 0) {
+              double mx = a ? prob : 0.0;
+              for (int d = 16; d > 0; d >>= 1) {
+                const double o = __shfl_xor_sync(0xffffffffu, mx, d);
+                mx = o > mx ? o : mx;
+              }
+              eps = mx / 100000;
+              last = true;
+            }
+            break;
+          }
+        }
+        if (last) {
+          bool a = false;
+          if (cand) {
+            const double x = eps / f;
+            a = f2 >= x && m > 0 && (same ? (m * f2 >= x * 2) : (m * f2 >= x));
+          }
+          evals += __popc(cand_mask);
+          acc_mask = __ballot_sync(0xffffffffu, a);
+        }
+        if (acc_mask == 0 && cfg->planb) {
+          shape = false;  // Plan B / C: general kernel
+        } else {
+          done = true;
+          n_acc = __popc(acc_mask);
+          // sum in phase order; rank by (prob desc, phase asc)
+          bool first = true;
+          for (uint32_t mm = acc_mask; mm; mm &= mm - 1) {
+            const int j = __ffs(mm) - 1;
+            const double pj = __shfl_sync(0xffffffffu, prob, j);
+            if (first) { total = pj; first = false; }
+            else total = total + pj;
+            if ((acc_mask >> lane & 1u) && (pj > prob || (pj == prob && j < lane))) ++rank;
+          }
+          if (want_u && want_p) evals *= 2;  // the reference evaluates once per output kind
+        }
+      }
+      if (!shape) {
+        if (typed != 0) {
+          if (lane == 0) worklist[atomicAdd(worklist_n, 1u)] = (uint32_t)s;
+        } else {
+          done = true;  // GRIMB_ST_SKIPPED
+        }
+      }
+    }
+    // ---- rows of the 8 subjects of this CTA: one atomicAdd per kind
+    const uint32_t nu = (done && typed && want_u && n_acc) ? (lim_r < 1u ? lim_r : 1u) : 0u;
+    const uint32_t np = (done && typed && want_p) ? (n_acc < lim_r ? n_acc : lim_r) : 0u;
+    const uint32_t nup = (done && typed && want_u && n_acc) ? (lim_p < 1u ? lim_p : 1u) : 0u;
+    const uint32_t npp = (done && typed && want_p && n_acc) ? (lim_p < 1u ? lim_p : 1u) : 0u;
+    if (lane == 0) {
+      s_hap[warp] = nu + np;
+      s_pop[warp] = nup + npp;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t th = 0, tp = 0;
+      for (int w = 0; w < FAST_WARPS; ++w) {
+        th += s_hap[w];
+        tp += s_pop[w];
+      }
+      s_base[0] = th ? atomicAdd(O.hap_counter, (unsigned long long)th) : 0ull;
+      s_base[1] = tp ? atomicAdd(O.pop_counter, (unsigned long long)tp) : 0ull;
+    }
+    __syncthreads();
+    uint64_t hb = s_base[0], pb = s_base[1];
+    for (int w = 0; w < warp; ++w) {
+      hb += s_hap[w];
+      pb += s_pop[w];
+    }
+    __syncthreads();
+    if (active && done) {
+      if (lane == 0) {
+        R.status[s] = typed ? GRIMB_ST_OK : GRIMB_ST_SKIPPED;
+        R.plan_umug[s] = (typed && want_u) ? GRIMB_PLAN_A : GRIMB_PLAN_NONE;
+        R.plan_pmug[s] = (typed && want_p) ? GRIMB_PLAN_A : GRIMB_PLAN_NONE;
+        R.n_umug[s] = nu;
+        R.n_pmug[s] = np;
+        R.n_umug_pops[s] = nup;
+        R.n_pmug_pops[s] = npp;
+        R.tot_umug[s] = (want_u && n_acc) ? 1u : 0u;
+        R.tot_pmug[s] = want_p ? n_acc : 0u;
+        R.hap_off[s] = hb;
+        R.pop_off[s] = pb;
+        R.pair_evals[s] = evals;
+      }
+      if ((int64_t)(hb + nu + np) <= R.hap_capacity) {
+        if (lane == 0 && nu) {
+          GrimbHapRow o;
+          o.a = glo;
+          o.b = ghi;
+          o.prob = total;
+          R.hap_rows[hb] = o;
+        }
+        if ((acc_mask >> lane & 1u) && rank < np) {
+          GrimbHapRow o;
+          o.a = key;
+          o.b = key2;
+          o.prob = prob;
+          R.hap_rows[hb + nu + rank] = o;
+        }
+      }
+      if ((int64_t)(pb + nup + npp) <= R.pop_capacity && lane < (int)(nup + npp)) {
+        GrimbPopRow o;
+        o.pop_a = 0;
+        o.pop_b = 0;
+        o.pad = 0;
+        o.prob = total;
+        R.pop_rows[pb + lane] = o;
+      }
+    }
   }
 }
 
@@ -666,6 +873,9 @@ struct GrimbEngine {
   int64_t launches = 0;
   // staging for the host-pointer form (grow-only)
   DevBuf in[6], outb[14];
+  DevBuf worklist;   // subjects the fast kernel hands to the general kernel
+  int sm_count = 0;
+  int fast_path = 1; // GRIMB_FAST=0 disables the warp-per-subject kernel (debugging / A-B runs)
 };
 
 extern "C" int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes_per_cta, GrimbEngine** out) {
@@ -699,6 +909,14 @@ extern "C" int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes
   CK(cudaMalloc((void**)&e->d_cfg, sizeof(GrimbConfig)));
   CK(cudaMalloc((void**)&e->d_counters, 32));
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  e->sm_count = prop.multiProcessorCount;
+  const char* fp = getenv("GRIMB_FAST");
+  if (fp && fp[0] == '0') e->fast_path = 0;
+  const char* th = getenv("GRIMB_THREADS");
+  if (th) {
+    int v = atoi(th);
+    if (v >= 32 && v <= MAXT && v % 32 == 0) e->threads = v;
+  }
   *out = e;
   return GRIMB_OK;
 }
@@ -743,10 +961,26 @@ extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const
   O.hap_counter = e->d_counters + 1;
   O.pop_counter = e->d_counters + 2;
   if (batch->n_subjects > 0) {
+    const TablesView& tv = e->tables->view;
+    const uint32_t* wl = nullptr;
+    const unsigned int* wl_n = nullptr;
+    if (e->fast_path && tv.L <= 5 && tv.P == 1) {
+      // warp-per-subject kernel first; what it cannot finish goes through the general kernel
+      CK(e->worklist.reserve((size_t)batch->n_subjects * 4 + 16));
+      unsigned int* cnt = (unsigned int*)(e->d_counters + 3);
+      const uint64_t groups = ((uint64_t)batch->n_subjects + FAST_WARPS - 1) / FAST_WARPS;
+      uint64_t fg = (uint64_t)e->sm_count * 8;
+      if (fg > groups) fg = groups;
+      k_impute_fast<<<(unsigned)fg, FAST_WARPS * 32, 0, st>>>(tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt);
+      CK(cudaGetLastError());
+      e->launches += 1;
+      wl = (const uint32_t*)e->worklist.p;
+      wl_n = cnt;
+    }
     int grid = e->n_ctas;
     if ((int64_t)grid > batch->n_subjects) grid = (int)batch->n_subjects;
-    k_impute<<<grid, e->threads, 0, st>>>(e->tables->view, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones,
-                                         e->d_counters);
+    k_impute<<<grid, e->threads, 0, st>>>(tv, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones, e->d_counters, wl,
+                                         wl_n);
     CK(cudaGetLastError());
     e->launches += 1;
   }
