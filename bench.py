@@ -297,13 +297,10 @@ def main():
         return t.pin_memory() if pin else t
 
     keys_in = ["typed_mask", "counts", "allele_off", "alleles", "prior_index", "priors"]
-    out_spec = [("status", np.uint8), ("plan_umug", np.uint8), ("plan_pmug", np.uint8), ("n_umug", np.uint32),
-                ("n_pmug", np.uint32), ("n_umug_pops", np.uint32), ("n_pmug_pops", np.uint32), ("tot_umug", np.uint32),
-                ("tot_pmug", np.uint32), ("hap_off", np.uint64), ("pop_off", np.uint64), ("pair_evals", np.uint64)]
     hap_cap, pop_cap = S * 8, S * 4
     needed = np.zeros(2, np.int64)
 
-    def make_structs(inputs, outputs, hap_rows, pop_rows):
+    def make_structs(inputs, subj, hap_rows, pop_rows):
         b = _lib.Batch()
         b.n_subjects = S
         for k in keys_in:
@@ -311,8 +308,7 @@ def main():
         b.n_alleles_total = S * 10
         b.n_priors = 1
         r = _lib.Results()
-        for k, _ in out_spec:
-            setattr(r, k, outputs[k].data_ptr())
+        r.subjects = subj.data_ptr()
         r.hap_rows, r.hap_capacity = hap_rows.data_ptr(), hap_cap
         r.pop_rows, r.pop_capacity = pop_rows.data_ptr(), pop_cap
         r.hap_rows_needed = needed[0:].ctypes.data
@@ -322,10 +318,10 @@ def main():
     # device-resident leg
     d_in = {k: tens(batch[k].view(np.int16) if batch[k].dtype == np.uint16 else
                     batch[k].view(np.int32) if batch[k].dtype == np.uint32 else batch[k]).to(dev) for k in keys_in}
-    d_out = {k: torch.zeros(S * np.dtype(dt).itemsize, dtype=torch.uint8, device=dev) for k, dt in out_spec}
+    d_subj = torch.zeros(S * 48, dtype=torch.uint8, device=dev)
     d_hap = torch.zeros(hap_cap * 24, dtype=torch.uint8, device=dev)
     d_pop = torch.zeros(pop_cap * 16, dtype=torch.uint8, device=dev)
-    db, dr = make_structs(d_in, d_out, d_hap, d_pop)
+    db, dr = make_structs(d_in, d_subj, d_hap, d_pop)
     stream = torch.cuda.current_stream()
 
     def step_device():
@@ -335,10 +331,10 @@ def main():
     # host leg (pinned buffers; copies inside the timed region)
     h_in = {k: tens(batch[k].view(np.int16) if batch[k].dtype == np.uint16 else
                     batch[k].view(np.int32) if batch[k].dtype == np.uint32 else batch[k], pin=True) for k in keys_in}
-    h_out = {k: torch.zeros(S * np.dtype(dt).itemsize, dtype=torch.uint8).pin_memory() for k, dt in out_spec}
+    h_subj = torch.zeros(S * 48, dtype=torch.uint8).pin_memory()
     h_hap = torch.zeros(hap_cap * 24, dtype=torch.uint8).pin_memory()
     h_pop = torch.zeros(pop_cap * 16, dtype=torch.uint8).pin_memory()
-    hb, hr = make_structs(h_in, h_out, h_hap, h_pop)
+    hb, hr = make_structs(h_in, h_subj, h_hap, h_pop)
 
     def step_host():
         rc = lib.grimb_impute_host(eng, C.byref(cfg), C.byref(hb), C.byref(hr))
@@ -370,11 +366,12 @@ def main():
         sampler.start()
     launches0 = lib.grimb_engine_launches(eng)
     ms_dev = timed(step_device, args.steps, args.warmup)
-    launches = lib.grimb_engine_launches(eng) - launches0 - args.warmup
+    launches = (lib.grimb_engine_launches(eng) - launches0) * args.steps // (args.steps + args.warmup)
     hap_rows_n, pop_rows_n = int(needed[0]), int(needed[1])
-    evals = int(d_out["pair_evals"].view(torch.int64).sum().item())
-    status = d_out["status"].cpu().numpy()
-    hits = int(d_out["tot_pmug"].view(torch.int32).sum().item())
+    subj = d_subj.cpu().numpy().view(_lib.SUBJECT_DTYPE)
+    evals = int(subj["pair_evals"].astype(np.int64).sum())
+    status = subj["status"]
+    hits = int(subj["tot_pmug"].astype(np.int64).sum())
     ms_host = timed(step_host, args.steps, args.warmup)
     sampler.stop_flag = True
 
@@ -402,8 +399,8 @@ def main():
     if rank == 0:
         total = S * world
         # algorithmic bytes per launch (DESIGN.md "Measurement"): per subject 36 B of input, 2^L = 32
-        # probes x one 32 B sector, per hit a 32 B frequency sector, 51 B result header, plus the rows written
-        algo = S * (36 + 32 * 32 + 51) + hits * 2 * 32 + hap_rows_n * 24 + pop_rows_n * 16
+        # probes x one 32 B sector, per hit a 32 B frequency sector, 48 B result record, plus the rows written
+        algo = S * (36 + 32 * 32 + 48) + hits * 2 * 32 + hap_rows_n * 24 + pop_rows_n * 16
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -412,7 +409,7 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = algo / (ms_dev * 1e-3) / 1e9
         h2d = sum(batch[k].nbytes for k in keys_in)
-        d2h = sum(S * np.dtype(dt).itemsize for _, dt in out_spec) + hap_rows_n * 24 + pop_rows_n * 16
+        d2h = S * 48 + hap_rows_n * 24 + pop_rows_n * 16
         line = {
             "metric": "subjects_per_sec", "value": total / (ms_dev * 1e-3), "unit": "subjects/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,

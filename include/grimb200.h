@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define GRIMB_ABI_VERSION 1
+#define GRIMB_ABI_VERSION 2
 #define GRIMB_MAX_LOCI 9
 #define GRIMB_MAX_ROWS 16
 #define GRIMB_MAX_BLOCKS 9
@@ -40,6 +40,8 @@ extern "C" {
 #define GRIMB_ST_FAULT 2       /* the reference raises inside this subject -> raw line in .problem */
 #define GRIMB_ST_WORKSPACE 3   /* per-CTA workspace too small: re-issue with a bigger workspace */
 #define GRIMB_ST_SKIPPED 4     /* not processed (host marked it unparsable: .problem "i,id") */
+#define GRIMB_ST_NO_PHASES 5   /* nothing opens after both reductions (impute.py:1620-1629): the reference
+                                  returns its defaults; the host reproduces the writer's behaviour */
 
 /* plan that produced the rows (impute.py:216,1638,1702), per output kind */
 #define GRIMB_PLAN_NONE 0
@@ -148,21 +150,25 @@ typedef struct {
 typedef struct { uint64_t a, b; double prob; } GrimbHapRow;
 typedef struct { uint16_t pop_a, pop_b; uint32_t pad; double prob; } GrimbPopRow;
 
+/* One record per subject (48 bytes, 16-byte aligned: written with three 128-bit stores). */
 typedef struct {
-  /* per subject, [S] */
-  uint8_t* status;        /* GRIMB_ST_*                                                  */
-  uint8_t* plan_umug;     /* GRIMB_PLAN_*                                                */
-  uint8_t* plan_pmug;
-  uint32_t* n_umug;       /* rows written (<= n_results)                                 */
-  uint32_t* n_pmug;
-  uint32_t* n_umug_pops;  /* rows written (<= n_pop_results); 0xFFFFFFFF = the Plan-C "all_pops" row */
-  uint32_t* n_pmug_pops;
-  uint32_t* tot_umug;     /* len(res_muugs["Haps"]) before top-N (the count the reference prints) */
-  uint32_t* tot_pmug;     /* len(res_haps["Haps"])                                       */
-  uint64_t* hap_off;      /* first UMUG row in hap_rows; PMUG rows follow                */
-  uint64_t* pop_off;      /* first UMUG pop row in pop_rows; PMUG pop rows follow        */
-  uint64_t* pair_evals;   /* iterations reaching impute.py:464/573 (metric numerator)    */
-  /* packed rows */
+  uint8_t status;        /* GRIMB_ST_*                                                   */
+  uint8_t plan_umug;     /* GRIMB_PLAN_*                                                 */
+  uint8_t plan_pmug;
+  uint8_t reserved;
+  uint32_t n_umug;       /* rows written (<= n_results)                                  */
+  uint32_t n_pmug;
+  uint32_t n_umug_pops;  /* rows written (<= n_pop_results)                              */
+  uint32_t n_pmug_pops;
+  uint32_t tot_umug;     /* len(res_muugs["Haps"]) before top-N (the count the reference prints) */
+  uint32_t tot_pmug;     /* len(res_haps["Haps"])                                        */
+  uint32_t pair_evals;   /* iterations reaching impute.py:464/573 (metric numerator; saturates) */
+  uint64_t hap_off;      /* first UMUG row in hap_rows; the PMUG rows follow             */
+  uint64_t pop_off;      /* first UMUG pop row in pop_rows; the PMUG pop rows follow     */
+} GrimbSubjectResult;
+
+typedef struct {
+  GrimbSubjectResult* subjects; /* [S]                                                   */
   GrimbHapRow* hap_rows;  int64_t hap_capacity;
   GrimbPopRow* pop_rows;  int64_t pop_capacity;
   /* totals written by the call (host memory, always): rows needed; > capacity => GRIMB_E_CAPACITY */

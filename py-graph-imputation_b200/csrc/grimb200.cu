@@ -666,118 +666,167 @@ k_impute(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArr
 // per CTA (8 subjects).
 // ------------------------------------------------------------------------------------------
 constexpr int FAST_WARPS = 8;
+constexpr int FAST_MAX_ROUNDS = 40;
+
+// accept test of calc_haps_pairs (impute.py:458-491) for one candidate pair with P == 1:
+//   x = eps / f1;  f2 >= x  and  m > 0  and  m*f2 >= x (x2 if the two haplotypes are equal)
+// <=> m > 0 and fl(eps/f1) <= t with t = min(f2, m*f2 [/2]).  With b = fl(f1*t): eps <= b(1-2^-50)
+// proves it and eps >= b(1+2^-50) refutes it, so the FP64 division only runs inside that band.
+struct FastPair {
+  double f, f2, y, lo, hi;
+  bool same, mpos;
+  __device__ __forceinline__ bool accept(double e) const {
+    if (!mpos) return false;
+    if (e <= lo) return true;
+    if (e >= hi) return false;
+    const double x = e / f;
+    return f2 >= x && (same ? (y >= x * 2) : (y >= x));
+  }
+};
 
 __global__ void __launch_bounds__(FAST_WARPS * 32)
 k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O, uint32_t* worklist,
               unsigned int* worklist_n) {
-  __shared__ uint32_t s_hap[FAST_WARPS], s_pop[FAST_WARPS];
-  __shared__ unsigned long long s_base[2];
+  __shared__ uint32_t s_hap[2][FAST_WARPS], s_pop[2][FAST_WARPS];
+  __shared__ unsigned long long s_base[2][2];
+  __shared__ double s_chain[FAST_MAX_ROUNDS];
+  __shared__ int s_nchain;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int L = T.L;
   const uint32_t full = (1u << L) - 1u;
   const int nphase = 1 << (L - 1);
   GrimbResults& R = O.r;
-  const bool want_u = cfg->output_umug != 0, want_p = cfg->output_pmug != 0;
+  const bool want_u = cfg->output_umug != 0, want_p = cfg->output_pmug != 0, planb = cfg->planb != 0;
   const uint32_t lim_r = (uint32_t)cfg->n_results, lim_p = (uint32_t)cfg->n_pop_results;
+  if (threadIdx.x == 0) {
+    // epsilon chain of call_comp_phase_prob (impute.py:1665-1673): repeated FP64 /= 10
+    double e = cfg->epsilon;
+    int n = 0;
+    while (e > 0 && n < FAST_MAX_ROUNDS) {
+      e /= 10;
+      if (e < 1.0e-9) e = 0.0;
+      s_chain[n++] = e;
+    }
+    s_nchain = (e > 0) ? -1 : n;  // -1: schedule too long for this kernel -> general kernel
+  }
+  __syncthreads();
+  const int nchain = s_nchain;
   const uint64_t n_groups = ((uint64_t)B.n_subjects + FAST_WARPS - 1) / FAST_WARPS;
-  for (uint64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+  int buf = 0;
+  for (uint64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, buf ^= 1) {
     const uint64_t s = grp * FAST_WARPS + warp;
-    bool done = false;             // handled here (rows or an empty result)
-    bool active = s < (uint64_t)B.n_subjects;
-    uint32_t typed = 0;
-    uint32_t acc_mask = 0;
-    uint64_t key = 0, key2 = 0, glo = 0, ghi = 0;
+    const bool active = s < (uint64_t)B.n_subjects;
+    bool done = false;  // finished here (rows, an empty result, or a skipped subject)
+    uint32_t typed = 0, acc_mask = 0, rank = 0, n_acc = 0, evals = 0;
+    uint32_t pairs[5] = {0, 0, 0, 0, 0};
+    uint64_t key = 0, key2 = 0;
     double prob = 0.0, total = 0.0;
-    uint32_t rank = 0, n_acc = 0;
-    uint64_t evals = 0;
     if (active) {
       typed = B.typed_mask[s];
-      bool shape = typed == full;
-      const uint16_t* cn = B.counts + s * (uint64_t)L * 2;
-      uint16_t c = lane < 2 * L ? cn[lane] : (uint16_t)1;
-      shape = __all_sync(0xffffffffu, c == 1) && shape;
+      bool shape = typed == full && nchain >= 0;
+      const uint32_t off = B.allele_off[s];
+      {
+        // every listed count must be 1: the counts of one subject are 2L uint16 = L aligned uint32
+        const uint32_t* c32 = reinterpret_cast<const uint32_t*>(B.counts + s * (uint64_t)L * 2);
+        const uint32_t c = lane < L ? c32[lane] : 0x00010001u;
+        shape = __all_sync(0xffffffffu, c == 0x00010001u) && shape;
+      }
       if (shape) {
-        const uint16_t* al = B.alleles + B.allele_off[s];
-        const uint32_t mine = lane < 2 * L ? al[lane] : 0u;  // lane 2l+x = allele of locus l, side x
+        const uint16_t* al = B.alleles + off;
+        if ((off & 1u) == 0) {
+          const uint32_t* a32 = reinterpret_cast<const uint32_t*>(al);
+#pragma unroll
+          for (int l = 0; l < 5; ++l)
+            if (l < L) pairs[l] = a32[l];
+        } else {
+#pragma unroll
+          for (int l = 0; l < 5; ++l)
+            if (l < L) pairs[l] = (uint32_t)al[2 * l] | ((uint32_t)al[2 * l + 1] << 16);
+        }
         bool known = true;
         uint32_t het = 0;
-        for (int l = 0; l < L; ++l) {
-          const uint32_t a0 = __shfl_sync(0xffffffffu, mine, 2 * l), a1 = __shfl_sync(0xffffffffu, mine, 2 * l + 1);
-          const uint32_t pick = (lane >> l & 1) ? a1 : a0;
-          if (pick == 0 || pick > T.n_alleles[l]) known = false;
-          key |= (uint64_t)pick << T.shift[l];
-          if (a0 != a1) het |= 1u << l;
-          const uint32_t mn = a0 < a1 ? a0 : a1, mx = a0 < a1 ? a1 : a0;
-          glo |= (uint64_t)mn << T.shift[l];
-          ghi |= (uint64_t)mx << T.shift[l];
-        }
+#pragma unroll
+        for (int l = 0; l < 5; ++l)
+          if (l < L) {
+            const uint32_t a0 = pairs[l] & 0xffffu, a1 = pairs[l] >> 16;
+            const uint32_t pick = (lane >> l & 1) ? a1 : a0;
+            known = known && (pick - 1u) < T.n_alleles[l];
+            key |= (uint64_t)pick << T.shift[l];
+            if (a0 != a1) het |= 1u << l;
+          }
         double f = 0.0;
         if (lane < (1 << L) && known) {
           const uint32_t node = ht_lookup(T, full, key);
-          if (node != GRIMB_NONE) f = T.freq[node];  // P == 1
+          if (node != GRIMB_NONE) f = __ldg(T.freq + node);  // P == 1
         }
-        const int partner = (int)full - lane;
-        const double f2 = __shfl_sync(0xffffffffu, f, partner & 31);
-        key2 = __shfl_sync(0xffffffffu, key, partner & 31);
+        const int partner = ((int)full - lane) & 31;
+        FastPair pr;
+        pr.f = f;
+        pr.f2 = __shfl_sync(0xffffffffu, f, partner);
+        key2 = __shfl_sync(0xffffffffu, key, partner);
         const uint32_t low = het & ((uint32_t)nphase - 1u);
         const bool last_het = (het >> (L - 1)) & 1u;
         const bool kept = lane < nphase && !((uint32_t)lane & ~low) && (last_het || (uint32_t)lane <= (low ^ (uint32_t)lane));
-        const bool cand = kept && f > 0 && f2 > 0;
+        const bool cand = kept && pr.f > 0 && pr.f2 > 0;
         const uint32_t cand_mask = __ballot_sync(0xffffffffu, cand);
-        const double m = B.priors[(uint64_t)B.prior_index[s]];
-        const bool same = key == key2;
+        const double m = __ldg(B.priors + B.prior_index[s]);
+        pr.same = key == key2;
+        pr.mpos = m > 0;
+        pr.y = m * pr.f2;
+        {
+          const double t = fmin(pr.f2, pr.same ? pr.y * 0.5 : pr.y);
+          const double b = pr.f * t;
+          const bool tiny = !(b > 1.0e-280);
+          pr.lo = tiny ? -1.0 : b * (1.0 - 0x1p-50);
+          pr.hi = tiny ? __longlong_as_double(0x7ff0000000000000LL) : b * (1.0 + 0x1p-50);
+        }
         if (cand) {
-          prob = f * f2 * m;
-          if (!same) prob = prob * 2;
+          prob = pr.f * pr.f2 * m;
+          if (!pr.same) prob = prob * 2;
         }
-        // epsilon schedule
-        double eps = cfg->epsilon;
-        bool last = false;
-        while (eps > 0) {
-          eps /= 10;
-          if (eps < 1.0e-9) eps = 0.0;
-          bool a = false;
-          if (cand) {
-            const double x = eps / f;
-            a = f2 >= x && m > 0 && (same ? (m * f2 >= x * 2) : (m * f2 >= x));
-          }
-          evals += __popc(cand_mask);
-          acc_mask = __ballot_sync(0xffffffffu, a);
-          if (acc_mask) {
-            if (eps > 0) {
-              double mx = a ? prob : 0.0;
-              for (int d = 16; d > 0; d >>= 1) {
-                const double o = __shfl_xor_sync(0xffffffffu, mx, d);
-                mx = o > mx ? o : mx;
-              }
-              eps = mx / 100000;
-              last = true;
-            }
-            break;
-          }
+        // first round of the schedule at which this pair is accepted (acceptance is monotone in eps)
+        uint32_t r_mine = 99;
+        if (cand) {
+          int r = 0;
+          while (r < nchain && !pr.accept(s_chain[r])) ++r;
+          if (r < nchain) r_mine = (uint32_t)r;
         }
-        if (last) {
-          bool a = false;
-          if (cand) {
-            const double x = eps / f;
-            a = f2 >= x && m > 0 && (same ? (m * f2 >= x * 2) : (m * f2 >= x));
+        const uint32_t r_star = __reduce_min_sync(0xffffffffu, r_mine);
+        const uint32_t ncand = __popc(cand_mask);
+        if (r_star == 99) {
+          evals = ncand * (uint32_t)nchain;
+        } else {
+          evals = ncand * (r_star + 1);
+          bool a = r_mine <= r_star;
+          if (s_chain[r_star] > 0) {
+            // MaxProb of that round -> epsilon = MaxProb / 100000, one more evaluation (impute.py:1683-1693)
+            const uint32_t hi = a ? (uint32_t)__double2hiint(prob) : 0u;
+            const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+            const uint32_t lo = (a && hi == mh) ? (uint32_t)__double2loint(prob) : 0u;
+            const uint32_t ml = __reduce_max_sync(0xffffffffu, lo);
+            const double eps = __hiloint2double((int)mh, (int)ml) / 100000;
+            a = cand && pr.accept(eps);
+            evals += ncand;
           }
-          evals += __popc(cand_mask);
           acc_mask = __ballot_sync(0xffffffffu, a);
         }
-        if (acc_mask == 0 && cfg->planb) {
+        if (acc_mask == 0 && planb) {
           shape = false;  // Plan B / C: general kernel
         } else {
           done = true;
           n_acc = __popc(acc_mask);
-          // sum in phase order; rank by (prob desc, phase asc)
+          // += in phase order; rank by (probability desc, phase asc)
           bool first = true;
           for (uint32_t mm = acc_mask; mm; mm &= mm - 1) {
             const int j = __ffs(mm) - 1;
             const double pj = __shfl_sync(0xffffffffu, prob, j);
-            if (first) { total = pj; first = false; }
-            else total = total + pj;
-            if ((acc_mask >> lane & 1u) && (pj > prob || (pj == prob && j < lane))) ++rank;
+            if (first) {
+              total = pj;
+              first = false;
+            } else {
+              total = total + pj;
+            }
+            if (pj > prob || (pj == prob && j < lane)) ++rank;
           }
           if (want_u && want_p) evals *= 2;  // the reference evaluates once per output kind
         }
@@ -790,49 +839,65 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
         }
       }
     }
-    // ---- rows of the 8 subjects of this CTA: one atomicAdd per kind
-    const uint32_t nu = (done && typed && want_u && n_acc) ? (lim_r < 1u ? lim_r : 1u) : 0u;
-    const uint32_t np = (done && typed && want_p) ? (n_acc < lim_r ? n_acc : lim_r) : 0u;
-    const uint32_t nup = (done && typed && want_u && n_acc) ? (lim_p < 1u ? lim_p : 1u) : 0u;
-    const uint32_t npp = (done && typed && want_p && n_acc) ? (lim_p < 1u ? lim_p : 1u) : 0u;
+    // ---- rows of the 8 subjects of this CTA: one atomicAdd per kind (double-buffered: 2 barriers)
+    const bool rows = done && typed != 0 && n_acc != 0;
+    const uint32_t nu = (rows && want_u) ? (lim_r < 1u ? lim_r : 1u) : 0u;
+    const uint32_t np = (rows && want_p) ? (n_acc < lim_r ? n_acc : lim_r) : 0u;
+    const uint32_t nup = (rows && want_u) ? (lim_p < 1u ? lim_p : 1u) : 0u;
+    const uint32_t npp = (rows && want_p) ? (lim_p < 1u ? lim_p : 1u) : 0u;
     if (lane == 0) {
-      s_hap[warp] = nu + np;
-      s_pop[warp] = nup + npp;
+      s_hap[buf][warp] = nu + np;
+      s_pop[buf][warp] = nup + npp;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
       uint32_t th = 0, tp = 0;
+#pragma unroll
       for (int w = 0; w < FAST_WARPS; ++w) {
-        th += s_hap[w];
-        tp += s_pop[w];
+        th += s_hap[buf][w];
+        tp += s_pop[buf][w];
       }
-      s_base[0] = th ? atomicAdd(O.hap_counter, (unsigned long long)th) : 0ull;
-      s_base[1] = tp ? atomicAdd(O.pop_counter, (unsigned long long)tp) : 0ull;
-    }
-    __syncthreads();
-    uint64_t hb = s_base[0], pb = s_base[1];
-    for (int w = 0; w < warp; ++w) {
-      hb += s_hap[w];
-      pb += s_pop[w];
+      s_base[buf][0] = th ? atomicAdd(O.hap_counter, (unsigned long long)th) : 0ull;
+      s_base[buf][1] = tp ? atomicAdd(O.pop_counter, (unsigned long long)tp) : 0ull;
     }
     __syncthreads();
     if (active && done) {
+      uint64_t hb = s_base[buf][0], pb = s_base[buf][1];
+      for (int w = 0; w < warp; ++w) {
+        hb += s_hap[buf][w];
+        pb += s_pop[buf][w];
+      }
       if (lane == 0) {
-        R.status[s] = typed ? GRIMB_ST_OK : GRIMB_ST_SKIPPED;
-        R.plan_umug[s] = (typed && want_u) ? GRIMB_PLAN_A : GRIMB_PLAN_NONE;
-        R.plan_pmug[s] = (typed && want_p) ? GRIMB_PLAN_A : GRIMB_PLAN_NONE;
-        R.n_umug[s] = nu;
-        R.n_pmug[s] = np;
-        R.n_umug_pops[s] = nup;
-        R.n_pmug_pops[s] = npp;
-        R.tot_umug[s] = (want_u && n_acc) ? 1u : 0u;
-        R.tot_pmug[s] = want_p ? n_acc : 0u;
-        R.hap_off[s] = hb;
-        R.pop_off[s] = pb;
-        R.pair_evals[s] = evals;
+        uint4 w0, w1, w2;
+        w0.x = (typed ? GRIMB_ST_OK : GRIMB_ST_SKIPPED) | ((typed && want_u) ? (GRIMB_PLAN_A << 8) : 0) |
+               ((typed && want_p) ? (GRIMB_PLAN_A << 16) : 0);
+        w0.y = nu;
+        w0.z = np;
+        w0.w = nup;
+        w1.x = npp;
+        w1.y = (want_u && n_acc) ? 1u : 0u;
+        w1.z = want_p ? n_acc : 0u;
+        w1.w = evals;
+        w2.x = (uint32_t)hb;
+        w2.y = (uint32_t)(hb >> 32);
+        w2.z = (uint32_t)pb;
+        w2.w = (uint32_t)(pb >> 32);
+        uint4* dst = reinterpret_cast<uint4*>(R.subjects + s);
+        dst[0] = w0;
+        dst[1] = w1;
+        dst[2] = w2;
       }
       if ((int64_t)(hb + nu + np) <= R.hap_capacity) {
         if (lane == 0 && nu) {
+          // the single UMUG genotype: per-locus (min, max) of the two typed alleles
+          uint64_t glo = 0, ghi = 0;
+#pragma unroll
+          for (int l = 0; l < 5; ++l)
+            if (l < L) {
+              const uint32_t a0 = pairs[l] & 0xffffu, a1 = pairs[l] >> 16;
+              glo |= (uint64_t)(a0 < a1 ? a0 : a1) << T.shift[l];
+              ghi |= (uint64_t)(a0 < a1 ? a1 : a0) << T.shift[l];
+            }
           GrimbHapRow o;
           o.a = glo;
           o.b = ghi;
@@ -872,7 +937,7 @@ struct GrimbEngine {
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
   // staging for the host-pointer form (grow-only)
-  DevBuf in[6], outb[14];
+  DevBuf in[6], outb[3];
   DevBuf worklist;   // subjects the fast kernel hands to the general kernel
   int sm_count = 0;
   int fast_path = 1; // GRIMB_FAST=0 disables the warp-per-subject kernel (debugging / A-B runs)
@@ -1014,33 +1079,19 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
   db.alleles = (const uint16_t*)e->in[3].p;
   db.prior_index = (const uint32_t*)e->in[4].p;
   db.priors = (const double*)e->in[5].p;
-  const size_t ob[14] = {(size_t)S,     (size_t)S,     (size_t)S,     (size_t)S * 4, (size_t)S * 4, (size_t)S * 4, (size_t)S * 4,
-                         (size_t)S * 4, (size_t)S * 4, (size_t)S * 8, (size_t)S * 8, (size_t)S * 8,
-                         (size_t)r->hap_capacity * sizeof(GrimbHapRow), (size_t)r->pop_capacity * sizeof(GrimbPopRow)};
-  for (int i = 0; i < 14; ++i) CK(e->outb[i].reserve(ob[i] + 16));
+  const size_t ob[3] = {(size_t)S * sizeof(GrimbSubjectResult), (size_t)r->hap_capacity * sizeof(GrimbHapRow),
+                        (size_t)r->pop_capacity * sizeof(GrimbPopRow)};
+  for (int i = 0; i < 3; ++i) CK(e->outb[i].reserve(ob[i] + 16));
   GrimbResults dr = *r;
-  dr.status = (uint8_t*)e->outb[0].p;
-  dr.plan_umug = (uint8_t*)e->outb[1].p;
-  dr.plan_pmug = (uint8_t*)e->outb[2].p;
-  dr.n_umug = (uint32_t*)e->outb[3].p;
-  dr.n_pmug = (uint32_t*)e->outb[4].p;
-  dr.n_umug_pops = (uint32_t*)e->outb[5].p;
-  dr.n_pmug_pops = (uint32_t*)e->outb[6].p;
-  dr.tot_umug = (uint32_t*)e->outb[7].p;
-  dr.tot_pmug = (uint32_t*)e->outb[8].p;
-  dr.hap_off = (uint64_t*)e->outb[9].p;
-  dr.pop_off = (uint64_t*)e->outb[10].p;
-  dr.pair_evals = (uint64_t*)e->outb[11].p;
-  dr.hap_rows = (GrimbHapRow*)e->outb[12].p;
-  dr.pop_rows = (GrimbPopRow*)e->outb[13].p;
+  dr.subjects = (GrimbSubjectResult*)e->outb[0].p;
+  dr.hap_rows = (GrimbHapRow*)e->outb[1].p;
+  dr.pop_rows = (GrimbPopRow*)e->outb[2].p;
   int rc = grimb_impute_device(e, cfg, &db, &dr, st);
   if (rc != GRIMB_OK && rc != GRIMB_E_CAPACITY) return rc;
-  void* dst[12] = {r->status, r->plan_umug, r->plan_pmug, r->n_umug, r->n_pmug, r->n_umug_pops, r->n_pmug_pops,
-                   r->tot_umug, r->tot_pmug, r->hap_off, r->pop_off, r->pair_evals};
-  for (int i = 0; i < 12; ++i) CK(cudaMemcpyAsync(dst[i], e->outb[i].p, ob[i], cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(r->subjects, e->outb[0].p, ob[0], cudaMemcpyDeviceToHost, st));
   if (rc == GRIMB_OK) {
-    CK(cudaMemcpyAsync(r->hap_rows, e->outb[12].p, (size_t)*r->hap_rows_needed * sizeof(GrimbHapRow), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(r->pop_rows, e->outb[13].p, (size_t)*r->pop_rows_needed * sizeof(GrimbPopRow), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(r->hap_rows, e->outb[1].p, (size_t)*r->hap_rows_needed * sizeof(GrimbHapRow), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(r->pop_rows, e->outb[2].p, (size_t)*r->pop_rows_needed * sizeof(GrimbPopRow), cudaMemcpyDeviceToHost, st));
   }
   CK(cudaStreamSynchronize(st));
   return rc;

@@ -6,7 +6,6 @@
 
 namespace grimb {
 
-#define GRIMB_ST_NO_PHASES 5  // nothing opens after both reductions; host decides
 
 struct BlockList {
   const uint32_t* ids;  // nullptr: implicit node-id range
@@ -1131,18 +1130,21 @@ GD void run_subject(Subject& S, const GrimbBatch& B, const OutArrays& O, uint64_
     unsigned long long hb = 0, pb = 0;
     if (nu + np) hb = atom_add64(O.hap_counter, (unsigned long long)(nu + np));
     if (nup + npp) pb = atom_add64(O.pop_counter, (unsigned long long)(nup + npp));
-    R.status[s] = status;
-    R.plan_umug[s] = plan_u;
-    R.plan_pmug[s] = plan_p;
-    R.n_umug[s] = nu;
-    R.n_pmug[s] = np;
-    R.n_umug_pops[s] = nup;
-    R.n_pmug_pops[s] = npp;
-    R.tot_umug[s] = sh->cnt[4];
-    R.tot_pmug[s] = sh->cnt[5];
-    R.hap_off[s] = hb;
-    R.pop_off[s] = pb;
-    R.pair_evals[s] = evals;
+    GrimbSubjectResult o;
+    o.status = status;
+    o.plan_umug = plan_u;
+    o.plan_pmug = plan_p;
+    o.reserved = 0;
+    o.n_umug = nu;
+    o.n_pmug = np;
+    o.n_umug_pops = nup;
+    o.n_pmug_pops = npp;
+    o.tot_umug = sh->cnt[4];
+    o.tot_pmug = sh->cnt[5];
+    o.pair_evals = evals > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)evals;
+    o.hap_off = hb;
+    o.pop_off = pb;
+    R.subjects[s] = o;
     sh->cnt[6] = (uint32_t)(hb & 0xFFFFFFFFu);
     sh->cnt[7] = (uint32_t)(hb >> 32);
     sh->cnt[0] = (uint32_t)(pb & 0xFFFFFFFFu);

@@ -53,12 +53,18 @@ class Batch(C.Structure):
     ]
 
 
+SUBJECT_DTYPE = [
+    ("status", "u1"), ("plan_umug", "u1"), ("plan_pmug", "u1"), ("reserved", "u1"),
+    ("n_umug", "<u4"), ("n_pmug", "<u4"), ("n_umug_pops", "<u4"), ("n_pmug_pops", "<u4"),
+    ("tot_umug", "<u4"), ("tot_pmug", "<u4"), ("pair_evals", "<u4"), ("hap_off", "<u8"), ("pop_off", "<u8"),
+]  # GrimbSubjectResult, 48 bytes
+HAP_ROW_DTYPE = [("a", "<u8"), ("b", "<u8"), ("prob", "<f8")]
+POP_ROW_DTYPE = [("pa", "<u2"), ("pb", "<u2"), ("pad", "<u4"), ("prob", "<f8")]
+
+
 class Results(C.Structure):
     _fields_ = [
-        ("status", C.c_void_p), ("plan_umug", C.c_void_p), ("plan_pmug", C.c_void_p),
-        ("n_umug", C.c_void_p), ("n_pmug", C.c_void_p), ("n_umug_pops", C.c_void_p),
-        ("n_pmug_pops", C.c_void_p), ("tot_umug", C.c_void_p), ("tot_pmug", C.c_void_p),
-        ("hap_off", C.c_void_p), ("pop_off", C.c_void_p), ("pair_evals", C.c_void_p),
+        ("subjects", C.c_void_p),
         ("hap_rows", C.c_void_p), ("hap_capacity", C.c_int64),
         ("pop_rows", C.c_void_p), ("pop_capacity", C.c_int64),
         ("hap_rows_needed", C.c_void_p), ("pop_rows_needed", C.c_void_p),
@@ -99,7 +105,7 @@ def load():
     lib.grimb_engine_launches.restype = C.c_int64
     lib.grimb_impute_device.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Batch), C.POINTER(Results), C.c_void_p]
     lib.grimb_impute_host.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Batch), C.POINTER(Results)]
-    if lib.grimb_abi_version() != 1:
+    if lib.grimb_abi_version() != 2:
         raise RuntimeError("libgrimb200.so ABI mismatch")
     _LIB = lib
     return lib

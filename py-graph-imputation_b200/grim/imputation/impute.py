@@ -266,23 +266,15 @@ class Imputation(object):
         b.typed_mask, b.counts, b.allele_off = typed.ctypes.data, counts.ctypes.data, off.ctypes.data
         b.alleles, b.n_alleles_total = alle.ctypes.data, int(off[S])
         b.prior_index, b.priors, b.n_priors = pri.ctypes.data, priors.ctypes.data, priors.shape[0]
-        out = {
-            "status": np.zeros(S, np.uint8), "plan_umug": np.zeros(S, np.uint8), "plan_pmug": np.zeros(S, np.uint8),
-            "n_umug": np.zeros(S, np.uint32), "n_pmug": np.zeros(S, np.uint32),
-            "n_umug_pops": np.zeros(S, np.uint32), "n_pmug_pops": np.zeros(S, np.uint32),
-            "tot_umug": np.zeros(S, np.uint32), "tot_pmug": np.zeros(S, np.uint32),
-            "hap_off": np.zeros(S, np.uint64), "pop_off": np.zeros(S, np.uint64), "pair_evals": np.zeros(S, np.uint64),
-        }
+        subj = np.zeros(S, dtype=_lib.SUBJECT_DTYPE)
         hap_cap = max(1024, S * 2 * min(self.cfg.n_results, 16))
         pop_cap = max(1024, S * 2 * min(self.cfg.n_pop_results, 4))
         needed = np.zeros(2, np.int64)
         while True:
-            hap_rows = np.zeros(hap_cap, dtype=[("a", np.uint64), ("b", np.uint64), ("prob", np.float64)])
-            pop_rows = np.zeros(pop_cap, dtype=[("pa", np.uint16), ("pb", np.uint16), ("pad", np.uint32), ("prob", np.float64)])
+            hap_rows = np.zeros(hap_cap, dtype=_lib.HAP_ROW_DTYPE)
+            pop_rows = np.zeros(pop_cap, dtype=_lib.POP_ROW_DTYPE)
             r = _lib.Results()
-            for k in ("status", "plan_umug", "plan_pmug", "n_umug", "n_pmug", "n_umug_pops", "n_pmug_pops",
-                      "tot_umug", "tot_pmug", "hap_off", "pop_off", "pair_evals"):
-                setattr(r, k, out[k].ctypes.data)
+            r.subjects = subj.ctypes.data
             r.hap_rows, r.hap_capacity = hap_rows.ctypes.data, hap_cap
             r.pop_rows, r.pop_capacity = pop_rows.ctypes.data, pop_cap
             r.hap_rows_needed = needed[0:].ctypes.data
@@ -295,6 +287,7 @@ class Imputation(object):
             if rc != 0:
                 _lib.check(rc, "grimb_impute_host")
             break
+        out = {k: subj[k] for k, _ in _lib.SUBJECT_DTYPE}
         out["hap_rows"], out["pop_rows"] = hap_rows, pop_rows
         return out
 
