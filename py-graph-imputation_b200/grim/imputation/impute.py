@@ -10,6 +10,7 @@ bit-identical."""
 import ctypes as C
 import os
 import sys
+import time
 
 import numpy as np
 
@@ -279,7 +280,9 @@ class Imputation(object):
             r.pop_rows, r.pop_capacity = pop_rows.ctypes.data, pop_cap
             r.hap_rows_needed = needed[0:].ctypes.data
             r.pop_rows_needed = needed[1:].ctypes.data
+            t0 = time.perf_counter()
             rc = self._backend(self.cfg, b, r, workspace)
+            self.stats["abi_seconds"] = self.stats.get("abi_seconds", 0.0) + time.perf_counter() - t0
             if rc == _lib.E_CAPACITY:
                 hap_cap = max(hap_cap, int(needed[0]))
                 pop_cap = max(pop_cap, int(needed[1]))

@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Throughput + parity of the BASELINE.json parity-test configurations through the product's
+Python API on one GPU (not bench lines: bench.py measures configs[1]).  For each configuration:
+subjects/s end to end through Imputation.impute_lines (tokeniser + C ABI + formatter), the share
+spent inside the C ABI call, and a byte-for-byte comparison of the six output texts with the CPU
+oracle on the first `sample` subjects.  Writes one JSON line per configuration.
+
+    python tools/run_configs.py > profiles/rNN_configs.jsonl
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "py-graph-imputation_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+import goldenlib  # noqa: E402
+import grim_oracle as go  # noqa: E402
+import synth  # noqa: E402
+from grim.imputation.impute import Imputation  # noqa: E402
+from grim.imputation.networkx_graph import Graph  # noqa: E402
+from grim.run_impute_def import load_config  # noqa: E402
+
+
+def run(name, conf, hpf_text, counts_text, lines, sample, tmp):
+    hpf = os.path.join(tmp, name + "_hpf.csv")
+    cnt = os.path.join(tmp, name + "_counts.txt")
+    open(hpf, "w").write(hpf_text)
+    open(cnt, "w").write(counts_text)
+    conf = dict(conf)
+    conf["freq_file"], conf["pops_count_file"] = hpf, cnt
+    cfg = load_config(conf)
+    t = time.time()
+    g = Graph(cfg).build_graph()
+    t_build = time.time() - t
+    imp = Imputation(g, cfg)
+    imp.impute_lines(lines[:64])                      # warm-up (engine creation)
+    imp = Imputation(g, cfg)
+    t = time.time()
+    out = imp.impute_lines(lines)
+    dt = time.time() - t
+    mine = {k: "".join(v) for k, v in imp.impute_lines(lines[:sample]).items()}
+    t = time.time()
+    ref, _ = go.impute_file(conf, lines=lines[:sample])
+    t_cpu = time.time() - t                            # includes the oracle's graph build
+    og = go.graph_from_config(conf)
+    oimp = go.OracleImputation(og, go.load_config(conf), go.count_by_prob_from_file(len(conf["populations"]), cnt))
+    t = time.time()
+    oimp.impute_lines(lines[:sample])
+    t_cpu = time.time() - t
+    info = g.info()
+    rec = {
+        "config": name, "subjects": len(lines), "gpu_subjects_per_s": len(lines) / dt,
+        "gpu_abi_seconds": imp.stats.get("abi_seconds"), "gpu_total_seconds": dt,
+        "pair_evals": imp.stats["pair_evals"], "plans": imp.stats["plan"],
+        "workspace_retries": imp.stats["workspace_retries"],
+        "cpu_port_subjects_per_s_1core": sample / t_cpu, "cpu_sample": sample,
+        "parity_identical_on_sample": all(mine[k] == ref[k] for k in ref),
+        "rows": {k: len(v) for k, v in out.items()},
+        "table": {"n_full": info["n_full"], "n_nodes": info["n_nodes"], "pops": len(conf["populations"]), "build_s": t_build},
+    }
+    print(json.dumps(rec), flush=True)
+    g.close()
+
+
+def main():
+    import tempfile
+    tmp = tempfile.mkdtemp()
+    base = json.load(open(os.path.join(goldenlib.GOLD, "data", "base_conf.json")))
+    cau = open(os.path.join(goldenlib.GOLD, "data", "cau_hpf.csv")).read()
+    cau_cnt = open(os.path.join(goldenlib.GOLD, "data", "cau_pop_counts.txt")).read()
+    tab = synth.Table(cau)
+    scale = float(os.environ.get("CONFIG_SCALE", "1"))
+    # C1: the README example
+    run("C1_readme_donor", base, cau, cau_cnt, open(os.path.join(goldenlib.GOLD, "data", "donor.csv")).readlines(), 1, tmp)
+    # C2 on the CAU table, through the Python host
+    run("C2_cau_typed", base, cau, cau_cnt, synth.typed_subjects(tab, int(200000 * scale), 1, ["CAU,CAU"]), 2000, tmp)
+    # C3: 21 populations, race fields, top-100 population results
+    pops = ["P%02d" % i for i in range(21)]
+    hpf21, cnt21 = synth.multipop_hpf(cau, pops, 21)
+    c3 = dict(base)
+    c3.update({"populations": pops, "UNK_priors": "MR", "number_of_pop_results": 100})
+    tab21 = synth.Table(hpf21, "P00")
+    run("C3_21pops_typed", c3, hpf21, cnt21, synth.typed_subjects(tab21, int(20000 * scale), 3, synth.race_fields(pops)), 300, tmp)
+    # C4: ambiguous / missing / unknown, incl. subjects over a lowered options threshold
+    run("C4_messy", base, cau, cau_cnt, synth.messy_subjects(tab, int(3000 * scale), 4, max_amb=6), 100, tmp)
+    c4 = dict(base)
+    c4["number_of_options_threshold"] = 200
+    run("C4_messy_threshold200", c4, cau, cau_cnt, synth.messy_subjects(tab, int(3000 * scale), 5, max_amb=6), 100, tmp)
+    run("C3_21pops_messy", c3, hpf21, cnt21, synth.messy_subjects(tab21, int(1000 * scale), 6, races=synth.race_fields(pops)), 60, tmp)
+
+
+if __name__ == "__main__":
+    main()
