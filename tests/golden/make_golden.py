@@ -114,10 +114,47 @@ def ambiguous_lines(tab, per_locus, n_missing, seed, sid):
     return "%s,%s,CAU,CAU\n" % (sid, "^".join(x + "+" + y for x, y in pairs))
 
 
+LOCI9 = ["A", "B", "C", "DPA1", "DPB1", "DQA1", "DQB1", "DRB1", "DRBX"]
+NINE_OVER = {
+    "populations": ["AAA", "BBB"], "UNK_priors": "MR", "freq_trim_threshold": 1e-9,
+    "loci_map": {l: i + 1 for i, l in enumerate(LOCI9)},
+    "Plan_B_Matrix": [[[1, 2, 3, 4, 5, 6, 7, 8, 9]], [[1, 2, 3], [4, 5], [6, 7, 8, 9]],
+                      [[1], [2, 3], [4, 5], [6, 7], [8, 9]], [[1], [2], [3], [4], [5], [6], [7], [8], [9]]],
+}
+
+
+def nine_table(n_full, seed):
+    """Small synthetic 9-locus table (BASELINE config 5 shape: 256 phases, 510 marginal labels)."""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    na = [12, 20, 10, 4, 9, 5, 7, 11, 3]
+    seen, haps = set(), []
+    while len(haps) < n_full:
+        h = tuple(min(int(rng.zipf(1.6)) - 1, n - 1) for n in na)
+        if h not in seen:
+            seen.add(h)
+            haps.append(h)
+    out = ["hap,pop,freq\n"]
+    for p in NINE_OVER["populations"]:
+        f = rng.rand(n_full) ** 3
+        f /= f.sum()
+        for h, x in zip(haps, f):
+            if rng.rand() < 0.85:
+                name = "~".join("%s*%02d:01" % (l, a + 1) for l, a in zip(LOCI9, h))
+                out.append("%s,%s,%s\n" % (name, p, repr(float(x))))
+    return "".join(out), "AAA,100.0,0.5\nBBB,100.0,0.5\n"
+
+
 def main():
     os.makedirs(DATA, exist_ok=True)
-    make_tables()
-    shutil.rmtree(CASES, ignore_errors=True)
+    only = sys.argv[1:]
+    if not only:
+        make_tables()
+        shutil.rmtree(CASES, ignore_errors=True)
+    if not os.path.exists(os.path.join(DATA, "nine_hpf.csv")):
+        h9, c9 = nine_table(150, 5)
+        open(os.path.join(DATA, "nine_hpf.csv"), "w").write(h9)
+        open(os.path.join(DATA, "nine_pop_counts.txt"), "w").write(c9)
     base = json.load(open(os.path.join(DATA, "base_conf.json")))
     cau = open(os.path.join(DATA, "cau_hpf.csv")).read()
     cau_cnt = open(os.path.join(DATA, "cau_pop_counts.txt")).read()
@@ -130,8 +167,15 @@ def main():
     conf3 = dict(base)
     conf3["populations"] = POPS3
     conf3["UNK_priors"] = "MR"
+    hpf9 = open(os.path.join(DATA, "nine_hpf.csv")).read()
+    cnt9 = open(os.path.join(DATA, "nine_pop_counts.txt")).read()
+    conf9 = dict(base)
+    conf9.update(NINE_OVER)
+    tab9 = synth.Table(hpf9, "AAA", LOCI9)
     sessions = {"cau": RefSession(base, cau, cau_cnt), "pop3": RefSession(conf3, hpf3, cnt3)}
-    base_over = {"cau": {}, "pop3": {"populations": POPS3, "UNK_priors": "MR"}}
+    if not only or any(o.startswith("g6") for o in only):
+        sessions["nine"] = RefSession(conf9, hpf9, cnt9)
+    base_over = {"cau": {}, "pop3": {"populations": POPS3, "UNK_priors": "MR"}, "nine": NINE_OVER}
 
     cases = [
         ("g1_readme_donor", "cau", {}, open(os.path.join(DATA, "donor.csv")).readlines()),
@@ -161,10 +205,16 @@ def main():
         ("g5_messy_cau", "cau", {}, synth.messy_subjects(tab, 120, 42)),
         ("g5_typed_nores1000", "cau", {"number_of_results": 1000, "epsilon": 1e-2},
          synth.typed_subjects(tab, 60, 43)),
+        ("g6_nine_loci", "nine", {},
+         synth.typed_subjects(tab9, 8, 1, ["AAA,BBB", ",", "AAA;BBB,XXX"])
+         + synth.messy_subjects(tab9, 14, 2, max_amb=2, p_missing=0.3, races=["AAA,BBB", ","])),
     ]
     for name, table, over, lines in cases:
+        if only and name not in only:
+            continue
         res = sessions[table].run(lines, **over)
         d = os.path.join(CASES, name)
+        shutil.rmtree(d, ignore_errors=True)
         os.makedirs(d)
         o = dict(base_over[table])
         o.update(over)
