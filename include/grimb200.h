@@ -99,7 +99,8 @@ int grimb_tables_export(const GrimbTables* t, uint64_t* node_key, double* node_f
  * buffer per peer): size, then copy out / build from an image on another device. */
 int grimb_tables_image_size(const GrimbTables* t, int64_t* bytes);
 int grimb_tables_image_ptr(const GrimbTables* t, void** dev_ptr);        /* device pointer */
-int grimb_tables_from_image(const void* dev_image, int64_t bytes, int device, GrimbTables** out);
+int grimb_tables_image_copy(const GrimbTables* t, void* dst);            /* dst: host or device, image_size bytes */
+int grimb_tables_from_image(const void* image, int64_t bytes, int device, GrimbTables** out); /* image: host or device */
 
 /* ------------------------------------------------------------------------------------------
  * Imputation.  Replaces Imputation.impute_one / comp_cand and everything below them

@@ -598,6 +598,13 @@ extern "C" int grimb_tables_image_ptr(const GrimbTables* t, void** dev_ptr) {
   return GRIMB_OK;
 }
 
+extern "C" int grimb_tables_image_copy(const GrimbTables* t, void* dst) {
+  if (!t || !dst) return fail(GRIMB_E_ARG, "null argument");
+  CK(cudaSetDevice(t->device));
+  CK(cudaMemcpy(dst, t->image, t->h.bytes, cudaMemcpyDefault));
+  return GRIMB_OK;
+}
+
 extern "C" int grimb_tables_from_image(const void* dev_image, int64_t bytes, int device, GrimbTables** out) {
   if (!dev_image || !out || bytes < (int64_t)sizeof(ImageHeader)) return fail(GRIMB_E_ARG, "bad image");
   CK(cudaSetDevice(device));

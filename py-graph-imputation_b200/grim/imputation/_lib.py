@@ -98,6 +98,7 @@ def load():
     lib.grimb_tables_export.argtypes = [C.c_void_p] + [C.c_void_p] * 10
     lib.grimb_tables_image_size.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     lib.grimb_tables_image_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.grimb_tables_image_copy.argtypes = [C.c_void_p, C.c_void_p]
     lib.grimb_tables_from_image.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_void_p)]
     lib.grimb_engine_create.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
     lib.grimb_engine_free.argtypes = [C.c_void_p]
@@ -120,6 +121,6 @@ def check(rc, what):
 EXPORTED = [
     "grimb_abi_version", "grimb_last_error", "grimb_tables_build", "grimb_tables_free",
     "grimb_tables_info", "grimb_tables_export", "grimb_tables_image_size", "grimb_tables_image_ptr",
-    "grimb_tables_from_image", "grimb_engine_create", "grimb_engine_free", "grimb_engine_launches",
+    "grimb_tables_image_copy", "grimb_tables_from_image", "grimb_engine_create", "grimb_engine_free", "grimb_engine_launches",
     "grimb_impute_device", "grimb_impute_host",
 ]

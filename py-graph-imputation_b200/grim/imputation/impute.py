@@ -90,8 +90,8 @@ class Imputation(object):
         self.cfg = make_config(config, self.loci, self.P)
         self.locus_index = {n: i for i, n in enumerate(self.loci)}
         self.batch_size = int(os.environ.get("GRIMB_BATCH", "65536"))
-        self.workspace = int(os.environ.get("GRIMB_WORKSPACE", str(8 << 20)))
-        self.big_workspace = int(os.environ.get("GRIMB_BIG_WORKSPACE", str(1 << 30)))
+        self.workspaces = [int(x) for x in os.environ.get(
+            "GRIMB_WORKSPACES", "%d,%d,%d" % (8 << 20, 128 << 20, 2 << 30)).split(",")]
         self._prior_index = {}
         self._priors = []
         self._backend = self._run_gpu
@@ -390,15 +390,23 @@ class Imputation(object):
                         item = (mask, counts, flat, pidx)
             meta.append((i, sid, raw, hclass, unknown))
             enc.append(item)
-        res = self._run_batch(enc, self.workspace)
-        retry = [s for s in range(len(enc)) if res["status"][s] == _lib.ST_WORKSPACE]
-        big = None
-        if retry:
-            self.stats["workspace_retries"] += len(retry)
-            big = self._run_batch([enc[s] for s in retry], self.big_workspace)
-            if any(big["status"][k] == _lib.ST_WORKSPACE for k in range(len(retry))):
-                raise MemoryError("subject exceeds GRIMB_BIG_WORKSPACE; raise it and rerun")
-        retry_pos = {s: k for k, s in enumerate(retry)}
+        # per-CTA workspace tiers: subjects that overflow one tier are re-issued on the next
+        where = {}
+        todo = list(range(len(enc)))
+        for tier in self.workspaces:
+            out = self._run_batch([enc[s] for s in todo], tier)
+            again = []
+            for k, s in enumerate(todo):
+                if out["status"][k] == _lib.ST_WORKSPACE:
+                    again.append(s)
+                else:
+                    where[s] = (out, k)
+            if not again:
+                break
+            self.stats["workspace_retries"] += len(again)
+            todo = again
+        else:
+            raise MemoryError("a subject exceeds the largest workspace tier (GRIMB_WORKSPACES)")
         for s, (i, sid, raw, hclass, unknown) in enumerate(meta):
             self.stats["subjects"] += 1
             if hclass == H_PROBLEM:
@@ -407,7 +415,7 @@ class Imputation(object):
             if hclass == H_FAULT:
                 files["problem"].append(raw + "\n")
                 continue
-            r, k = (res, s) if s not in retry_pos else (big, retry_pos[s])
+            r, k = where[s]
             st = int(r["status"][k])
             self.stats["pair_evals"] += int(r["pair_evals"][k])
             if st == _lib.ST_FAULT:

@@ -119,11 +119,57 @@ class Graph(object):
         self._engines = {}
 
     def build_graph(self, nodesFile=None, edgesFile=None, allEdgesFile=None):
+        """Tables from config["freq_file"] (hpf.csv); if that file is absent but a GRIM graph
+        directory exists (nodesFile = nodes.csv written by the reference or by write_csv), from
+        its full-haplotype rows."""
         cfg = self.config
-        alleles, fa, ff = read_hpf(cfg["freq_file"], self.pops, self.loci, cfg["freq_trim_threshold"],
-                                   cfg.get("pops_count_file") if cfg.get("use_pops_count_file") else None)
+        if os.path.isfile(cfg.get("freq_file", "")):
+            alleles, fa, ff = read_hpf(cfg["freq_file"], self.pops, self.loci, cfg["freq_trim_threshold"],
+                                       cfg.get("pops_count_file") if cfg.get("use_pops_count_file") else None)
+        elif nodesFile and os.path.isfile(nodesFile):
+            from .graph_io import read_nodes_csv
+            alleles, fa, ff = read_nodes_csv(nodesFile, self.loci, self.full_loci)
+        else:
+            raise FileNotFoundError("neither freq_file (%s) nor a nodes csv (%s) exists"
+                                    % (cfg.get("freq_file"), nodesFile))
         self.from_arrays(alleles, fa, ff)
         return self
+
+    def _set_dictionaries(self, alleles):
+        self.alleles = [list(a) for a in alleles]
+        self.allele_id = [{a: i + 1 for i, a in enumerate(al)} for al in self.alleles]
+        self.key_bits = key_layout([len(a) for a in self.alleles])
+        self.shift = [int(sum(self.key_bits[:l])) for l in range(len(self.alleles))]
+
+    def image_to_host(self):
+        """The device image of the tables as a host uint8 array (binary cache / replication)."""
+        lib = _lib.load()
+        n = C.c_int64()
+        _lib.check(lib.grimb_tables_image_size(self.handle, C.byref(n)), "grimb_tables_image_size")
+        img = np.empty(n.value, dtype=np.uint8)
+        _lib.check(lib.grimb_tables_image_copy(self.handle, img.ctypes.data), "grimb_tables_image_copy")
+        return img
+
+    def from_image_host(self, img, alleles):
+        lib = _lib.load()
+        self._set_dictionaries(alleles)
+        h = C.c_void_p()
+        _lib.check(lib.grimb_tables_from_image(img.ctypes.data, img.nbytes, self.device, C.byref(h)),
+                   "grimb_tables_from_image")
+        self.handle = h
+        return self
+
+    def write_csv(self, out_dir, **names):
+        from .graph_io import write_csv
+        write_csv(self, out_dir, **names)
+
+    def save_cache(self, path):
+        from .graph_io import save_cache
+        save_cache(self, path)
+
+    def load_cache(self, path):
+        from .graph_io import load_cache
+        return load_cache(self, path)
 
     def from_arrays(self, alleles, full_alleles, full_freqs):
         lib = _lib.load()
