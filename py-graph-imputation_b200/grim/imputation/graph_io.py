@@ -79,7 +79,12 @@ def write_csv(graph, out_dir, node_csv="nodes.csv", edges_csv="edges.csv", top_l
     # the true degree is recomputed for it.
     tl_cnt = a["tl_cnt"].astype(np.int64).copy()
     if n > n_full:
-        tl_cnt[n - 1] = len(a["tl_adj"]) - int(a["tl_start"][n - 1])
+        lm = int(label_of[n - 1])
+        km = 0
+        for l in range(L):
+            if lm >> l & 1:
+                km |= ((1 << graph.key_bits[l]) - 1) << graph.shift[l]
+        tl_cnt[n - 1] = int(np.count_nonzero((a["node_key"][:n_full] & np.uint64(km)) == a["node_key"][n - 1]))
     with open(os.path.join(out_dir, top_links_csv), "w", newline="") as f:
         w = csv.writer(f)
         w.writerow([":START_ID(HAPLOTYPE)", ":END_ID(HAPLOTYPE)", ":TYPE"])
