@@ -194,6 +194,59 @@ int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* 
 /* Number of kernel launches issued by this engine so far (bench.py's gpu_launches). */
 int64_t grimb_engine_launches(const GrimbEngine* e);
 
+/* ------------------------------------------------------------------------------------------
+ * Text pipeline (host C++, multi-threaded): the steps either side of the kernels.  Replaces the
+ * per-line work of Imputation.impute_file (impute.py:2019-2144): line split, clean_up_gl /
+ * gl2haps tokenising (:105-118,246-272), the race -> prior matrix step (:1956-1975,1844-1924),
+ * the .miss / .problem classification (:2061-2068,2141-2144) and the row text of
+ * write_best_prob / write_best_prob_genotype (:24-76) with Python's str(float) layout.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct GrimbText GrimbText;
+
+typedef struct {
+  int32_t n_loci, n_pops;
+  const char* const* locus_names;    /* [L] in loci_map index order                               */
+  const char* const* allele_names;   /* table alleles, locus 0 first; id = position in its locus + 1 */
+  const int32_t* allele_counts;      /* [L]                                                       */
+  const char* const* pop_names;      /* [P] "populations"                                         */
+  const double* count_by_prob;       /* [P] column 3 of pops_count_file, or ones (impute.py:205-212) */
+  double alpha, eta, beta, gamma, delta; /* "priority"                                            */
+  int32_t unk_priors_mr;             /* "UNK_priors" == "MR" (ones) else identity                 */
+  int32_t key_bits[GRIMB_MAX_LOCI];  /* the tables' packed-key layout                             */
+  int32_t n_threads;                 /* 0 = hardware concurrency                                  */
+} GrimbTextDesc;
+
+/* the six output texts of one call; pointers stay valid until the next call on the same GrimbText */
+#define GRIMB_OUT_UMUG 0
+#define GRIMB_OUT_UMUG_POPS 1
+#define GRIMB_OUT_PMUG 2
+#define GRIMB_OUT_PMUG_POPS 3
+#define GRIMB_OUT_MISS 4
+#define GRIMB_OUT_PROBLEM 5
+typedef struct {
+  const char* data[6];
+  int64_t size[6];
+  int64_t n_lines, pair_evals, workspace_retries;
+  int64_t plan_count[4];
+  double seconds_tokenise, seconds_gpu, seconds_format;
+} GrimbTextOut;
+
+int grimb_text_create(const GrimbTextDesc* d, GrimbText** out);
+int grimb_text_free(GrimbText* t);
+
+/* Two host-only halves (no CUDA calls; also what the CPU tests drive):
+ *   tokenise: input lines -> a GrimbBatch (host arrays owned by `t`) + per-line bookkeeping
+ *   format  : GrimbResults for that batch -> the six texts                                   */
+int grimb_text_tokenise(GrimbText* t, const GrimbConfig* cfg, const char* text, int64_t len,
+                        int64_t first_line_index, GrimbBatch* batch_out);
+int grimb_text_format(GrimbText* t, const GrimbConfig* cfg, const GrimbResults* res, GrimbTextOut* out);
+
+/* tokenise -> grimb_impute_host (subjects that overflow a workspace tier are re-issued on the
+ * next engine of `engines`) -> format.  This is what grim.grim.impute() calls per chunk of the
+ * input file. */
+int grimb_impute_text(GrimbText* t, GrimbEngine* const* engines, int32_t n_engines, const GrimbConfig* cfg,
+                      const char* text, int64_t len, int64_t first_line_index, GrimbTextOut* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,28 @@ class Results(C.Structure):
     ]
 
 
+class TextDesc(C.Structure):
+    _fields_ = [
+        ("n_loci", C.c_int32), ("n_pops", C.c_int32),
+        ("locus_names", C.POINTER(C.c_char_p)), ("allele_names", C.POINTER(C.c_char_p)),
+        ("allele_counts", C.POINTER(C.c_int32)), ("pop_names", C.POINTER(C.c_char_p)),
+        ("count_by_prob", C.POINTER(C.c_double)),
+        ("alpha", C.c_double), ("eta", C.c_double), ("beta", C.c_double), ("gamma", C.c_double), ("delta", C.c_double),
+        ("unk_priors_mr", C.c_int32), ("key_bits", C.c_int32 * MAX_LOCI), ("n_threads", C.c_int32),
+    ]
+
+
+class TextOut(C.Structure):
+    _fields_ = [
+        ("data", C.c_void_p * 6), ("size", C.c_int64 * 6),
+        ("n_lines", C.c_int64), ("pair_evals", C.c_int64), ("workspace_retries", C.c_int64),
+        ("plan_count", C.c_int64 * 4),
+        ("seconds_tokenise", C.c_double), ("seconds_gpu", C.c_double), ("seconds_format", C.c_double),
+    ]
+
+
+OUT_KEYS = ("umug", "umug_pops", "pmug", "pmug_pops", "miss", "problem")  # GRIMB_OUT_* order
+
 _LIB = None
 
 
@@ -106,6 +128,12 @@ def load():
     lib.grimb_engine_launches.restype = C.c_int64
     lib.grimb_impute_device.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Batch), C.POINTER(Results), C.c_void_p]
     lib.grimb_impute_host.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Batch), C.POINTER(Results)]
+    lib.grimb_text_create.argtypes = [C.POINTER(TextDesc), C.POINTER(C.c_void_p)]
+    lib.grimb_text_free.argtypes = [C.c_void_p]
+    lib.grimb_text_tokenise.argtypes = [C.c_void_p, C.POINTER(Config), C.c_char_p, C.c_int64, C.c_int64, C.POINTER(Batch)]
+    lib.grimb_text_format.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Results), C.POINTER(TextOut)]
+    lib.grimb_impute_text.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(Config), C.c_char_p,
+                                      C.c_int64, C.c_int64, C.POINTER(TextOut)]
     if lib.grimb_abi_version() != 2:
         raise RuntimeError("libgrimb200.so ABI mismatch")
     _LIB = lib
@@ -123,4 +151,5 @@ EXPORTED = [
     "grimb_tables_info", "grimb_tables_export", "grimb_tables_image_size", "grimb_tables_image_ptr",
     "grimb_tables_image_copy", "grimb_tables_from_image", "grimb_engine_create", "grimb_engine_free", "grimb_engine_launches",
     "grimb_impute_device", "grimb_impute_host",
+    "grimb_text_create", "grimb_text_free", "grimb_text_tokenise", "grimb_text_format", "grimb_impute_text",
 ]

@@ -433,6 +433,79 @@ class Imputation(object):
                 files["miss"].append(str(i) + "," + str(sid) + "\n")
             self._format_subject(sid, r, k, unknown, files)
 
+    # ------------------------------------------------------------------ native text pipeline
+    def _text_handle(self):
+        """GrimbText: dictionaries + priority parameters for the C++ tokeniser / formatter."""
+        if getattr(self, "_text", None) is not None:
+            return self._text
+        lib = _lib.load()
+        g = self.netGraph
+        d = _lib.TextDesc()
+        d.n_loci, d.n_pops = self.L, self.P
+        keep = []
+
+        def cstrings(items):
+            arr = (C.c_char_p * max(1, len(items)))(*[s.encode("utf8") for s in items])
+            keep.append(arr)
+            return arr
+
+        d.locus_names = cstrings(self.loci)
+        d.allele_names = cstrings([a for l in range(self.L) for a in g.alleles[l]])
+        counts = (C.c_int32 * self.L)(*[len(g.alleles[l]) for l in range(self.L)])
+        cbp = (C.c_double * self.P)(*[float(x) for x in self.count_by_prob])
+        keep.extend([counts, cbp])
+        d.allele_counts, d.pop_names, d.count_by_prob = counts, cstrings(self.populations), cbp
+        pr = self.priority
+        d.alpha, d.eta, d.beta, d.gamma, d.delta = (float(pr[k]) for k in ("alpha", "eta", "beta", "gamma", "delta"))
+        d.unk_priors_mr = 1 if self.unk_priors == "MR" else 0
+        for l in range(self.L):
+            d.key_bits[l] = g.key_bits[l]
+        d.n_threads = int(os.environ.get("GRIMB_HOST_THREADS", "0"))
+        h = C.c_void_p()
+        _lib.check(lib.grimb_text_create(C.byref(d), C.byref(h)), "grimb_text_create")
+        self._text = h
+        return h
+
+    def _line_chunks(self, f, max_lines=None):
+        """Yields (bytes of whole lines, index of the first line)."""
+        max_lines = max_lines or int(os.environ.get("GRIMB_TEXT_BATCH", "262144"))
+        first = 0
+        buf = []
+        for line in f:
+            buf.append(line)
+            if len(buf) >= max_lines:
+                yield b"".join(buf), first
+                first += len(buf)
+                buf = []
+        if buf:
+            yield b"".join(buf), first
+
+    def impute_text(self, data, first_index=0):
+        """bytes of input lines -> dict of the six output texts (bytes), through grimb_impute_text."""
+        lib = _lib.load()
+        t = self._text_handle()
+        engines = (C.c_void_p * len(self.workspaces))(*[self.netGraph.engine(w) for w in self.workspaces[:1]])
+        # engines of the bigger tiers are created lazily: pass only what exists, retry on overflow
+        n_eng = 1
+        out = _lib.TextOut()
+        while True:
+            rc = lib.grimb_impute_text(t, engines, n_eng, C.byref(self.cfg), data, len(data), first_index, C.byref(out))
+            if rc == -3 and n_eng < len(self.workspaces):   # GRIMB_E_NOMEM: a subject overflowed the last tier
+                engines[n_eng] = self.netGraph.engine(self.workspaces[n_eng])
+                n_eng += 1
+                continue
+            _lib.check(rc, "grimb_impute_text")
+            break
+        self.stats["subjects"] += out.n_lines
+        self.stats["pair_evals"] += out.pair_evals
+        self.stats["workspace_retries"] += out.workspace_retries
+        for k in range(4):
+            self.stats["plan"][k] += out.plan_count[k]
+        for k, v in (("tokenise_seconds", out.seconds_tokenise), ("abi_seconds", out.seconds_gpu),
+                     ("format_seconds", out.seconds_format)):
+            self.stats[k] = self.stats.get(k, 0.0) + v
+        return {k: C.string_at(out.data[i], out.size[i]) for i, k in enumerate(_lib.OUT_KEYS)}
+
     def impute_file(self, config, planb=None, em_mr=False, em=False):
         """Reads config["imputation_input_file"], writes the six output files
         (impute.py:1985-2155 of the reference)."""
@@ -442,9 +515,28 @@ class Imputation(object):
             raise NotImplementedError("per-subject phase masks are outside the B200 hot path (SURVEY 8f-4)")
         if planb is not None and bool(planb) != bool(config["planb"]):
             self.cfg.planb = 1 if planb else 0
+        targets = {"miss": "imputation_out_miss_file", "problem": "imputation_out_problem_file"}
+        if os.environ.get("GRIMB_PY_HOST") != "1":
+            # native host pipeline: C++ tokeniser / formatter around the kernels (grimb_impute_text)
+            if config["output_MUUG"]:
+                targets["umug"] = "imputation_out_umug_freq_file"
+                targets["umug_pops"] = "imputation_out_umug_pops_file"
+            if config["output_haplotypes"]:
+                targets["pmug"] = "imputation_out_hap_freq_file"
+                targets["pmug_pops"] = "imputation_out_hap_pops_file"
+            outs = {k: open(config[ck], "wb") for k, ck in targets.items()}
+            try:
+                with open(config["imputation_input_file"], "rb") as f:
+                    for chunk, first in self._line_chunks(f):
+                        texts = self.impute_text(chunk, first)
+                        for k, fo in outs.items():
+                            fo.write(texts[k])
+            finally:
+                for fo in outs.values():
+                    fo.close()
+            return
         with open(config["imputation_input_file"]) as f:
             files = self.impute_lines(f)
-        targets = {"miss": "imputation_out_miss_file", "problem": "imputation_out_problem_file"}
         if config["output_MUUG"]:
             targets["umug"] = "imputation_out_umug_freq_file"
             targets["umug_pops"] = "imputation_out_umug_pops_file"

@@ -185,3 +185,35 @@ def emu_imputation(emu_graph, config, count_by_prob=None, arena=64 << 20):
 
     imp._backend = backend
     return imp
+
+
+def emu_impute_text(imp, emu_graph, data, first_index=0, arena=64 << 20):
+    """The C++ text pipeline's two host halves (grimb_text_tokenise / grimb_text_format from
+    libgrimb200.so -- no CUDA calls) around the emulated kernel source.  CPU test aid."""
+    import numpy as np
+    lib = _lib.load()
+    t = imp._text_handle()
+    b = _lib.Batch()
+    _lib.check(lib.grimb_text_tokenise(t, C.byref(imp.cfg), data, len(data), first_index, C.byref(b)), "tokenise")
+    S = b.n_subjects
+    subj = np.zeros(max(1, S), dtype=_lib.SUBJECT_DTYPE)
+    hap_cap, pop_cap = 4096, 4096
+    needed = np.zeros(2, np.int64)
+    while True:
+        hap = np.zeros(hap_cap, dtype=_lib.HAP_ROW_DTYPE)
+        pop = np.zeros(pop_cap, dtype=_lib.POP_ROW_DTYPE)
+        r = _lib.Results()
+        r.subjects = subj.ctypes.data
+        r.hap_rows, r.hap_capacity = hap.ctypes.data, hap_cap
+        r.pop_rows, r.pop_capacity = pop.ctypes.data, pop_cap
+        r.hap_rows_needed = needed[0:].ctypes.data
+        r.pop_rows_needed = needed[1:].ctypes.data
+        rc = emu_graph.lib.grimb_emu_impute(C.byref(emu_graph.tables), C.byref(imp.cfg), C.byref(b), C.byref(r), arena)
+        if rc == _lib.E_CAPACITY:
+            hap_cap, pop_cap = max(hap_cap, int(needed[0])), max(pop_cap, int(needed[1]))
+            continue
+        assert rc == 0
+        break
+    out = _lib.TextOut()
+    _lib.check(lib.grimb_text_format(t, C.byref(imp.cfg), C.byref(r), C.byref(out)), "format")
+    return {k: C.string_at(out.data[i], out.size[i]).decode("utf8") for i, k in enumerate(_lib.OUT_KEYS)}

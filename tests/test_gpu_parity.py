@@ -140,3 +140,50 @@ def test_full_size_properties():
     # idempotence / batch-split independence on a slice
     imp2_out, _ = _run_gpu("cau", conf, lines[:5000])
     assert imp2_out["umug"] == "".join(x + "\n" for x in rows[:5000])
+
+
+@pytest.mark.parametrize("name", goldenlib.case_names())
+def test_native_text_path_matches_reference_files(name):
+    """Same cases through grimb_impute_text (C++ tokeniser / formatter around the kernels)."""
+    from grim.imputation.impute import Imputation
+    from grim.run_impute_def import load_config
+    table, conf, lines, exp = goldenlib.load_case(name)
+    imp = Imputation(_graph(table, conf), load_config(conf))
+    out = imp.impute_text("".join(lines).encode("utf8"))
+    for k in goldenlib.KEYS:
+        assert out[k].decode("utf8") == exp[k], "%s: %s differs" % (name, k)
+
+
+def test_public_api_impute_writes_reference_files(tmp_path):
+    """grim.grim.impute(conf_file) end to end: JSON config in, six files out (README flow)."""
+    import json
+    from grim import grim
+    table, conf, lines, exp = goldenlib.load_case("g2_edges")
+    conf = dict(conf)
+    d = str(tmp_path)
+    open(d + "/subjects.csv", "w").writelines(lines)
+    conf["imputation_in_file"] = d + "/subjects.csv"
+    conf["imputation_out_path"] = d + "/out"
+    names = {"umug": "imputation_out_umug_freq_filename", "umug_pops": "imputation_out_umug_pops_filename",
+             "pmug": "imputation_out_hap_freq_filename", "pmug_pops": "imputation_out_hap_pops_filename",
+             "miss": "imputation_out_miss_filename", "problem": "imputation_out_problem_filename"}
+    for k, ck in names.items():
+        conf[ck] = "x." + k
+    json.dump(conf, open(d + "/conf.json", "w"))
+    g = grim.impute(conf_file=d + "/conf.json")
+    for k in names:
+        assert open(d + "/out/x." + k).read() == exp[k], k
+    g2 = grim.impute(conf_file=d + "/conf.json", graph=g)     # graph reuse, as in the reference
+    assert g2 is g
+
+
+def test_native_text_path_large_batch_equals_python_host_path():
+    _, conf, _, _ = goldenlib.load_case("g3_pop3_typed")
+    hpf = open(conf["freq_file"]).read()
+    tab = synth.Table(hpf, "AAA")
+    lines = synth.typed_subjects(tab, 20000, 77, synth.race_fields(conf["populations"])) + \
+        synth.messy_subjects(tab, 300, 78, races=synth.race_fields(conf["populations"]))
+    out_py, imp = _run_gpu("pop3", conf, lines)
+    out_native = imp.impute_text("".join(lines).encode("utf8"))
+    for k in goldenlib.KEYS:
+        assert out_native[k].decode("utf8") == out_py[k], k

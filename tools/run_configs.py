@@ -40,10 +40,12 @@ def run(name, conf, hpf_text, counts_text, lines, sample, tmp):
     imp = Imputation(g, cfg)
     imp.impute_lines(lines[:64])                      # warm-up (engine creation)
     imp = Imputation(g, cfg)
+    data = "".join(lines).encode("utf8")
     t = time.time()
-    out = imp.impute_lines(lines)
+    texts = imp.impute_text(data)
     dt = time.time() - t
-    mine = {k: "".join(v) for k, v in imp.impute_lines(lines[:sample]).items()}
+    out = {k: v.splitlines() for k, v in texts.items()}
+    mine = {k: v.decode("utf8") for k, v in imp.impute_text("".join(lines[:sample]).encode("utf8")).items()}
     t = time.time()
     ref, _ = go.impute_file(conf, lines=lines[:sample])
     t_cpu = time.time() - t                            # includes the oracle's graph build
@@ -56,6 +58,7 @@ def run(name, conf, hpf_text, counts_text, lines, sample, tmp):
     rec = {
         "config": name, "subjects": len(lines), "gpu_subjects_per_s": len(lines) / dt,
         "gpu_abi_seconds": imp.stats.get("abi_seconds"), "gpu_total_seconds": dt,
+        "tokenise_seconds": imp.stats.get("tokenise_seconds"), "format_seconds": imp.stats.get("format_seconds"),
         "pair_evals": imp.stats["pair_evals"], "plans": imp.stats["plan"],
         "workspace_retries": imp.stats["workspace_retries"],
         "cpu_port_subjects_per_s_1core": sample / t_cpu, "cpu_sample": sample,
@@ -78,14 +81,14 @@ def main():
     # C1: the README example
     run("C1_readme_donor", base, cau, cau_cnt, open(os.path.join(goldenlib.GOLD, "data", "donor.csv")).readlines(), 1, tmp)
     # C2 on the CAU table, through the Python host
-    run("C2_cau_typed", base, cau, cau_cnt, synth.typed_subjects(tab, int(200000 * scale), 1, ["CAU,CAU"]), 2000, tmp)
+    run("C2_cau_typed", base, cau, cau_cnt, synth.typed_subjects(tab, int(1000000 * scale), 1, ["CAU,CAU"]), 2000, tmp)
     # C3: 21 populations, race fields, top-100 population results
     pops = ["P%02d" % i for i in range(21)]
     hpf21, cnt21 = synth.multipop_hpf(cau, pops, 21)
     c3 = dict(base)
     c3.update({"populations": pops, "UNK_priors": "MR", "number_of_pop_results": 100})
     tab21 = synth.Table(hpf21, "P00")
-    run("C3_21pops_typed", c3, hpf21, cnt21, synth.typed_subjects(tab21, int(20000 * scale), 3, synth.race_fields(pops)), 300, tmp)
+    run("C3_21pops_typed", c3, hpf21, cnt21, synth.typed_subjects(tab21, int(100000 * scale), 3, synth.race_fields(pops)), 300, tmp)
     # C4: ambiguous / missing / unknown, incl. subjects over a lowered options threshold
     run("C4_messy", base, cau, cau_cnt, synth.messy_subjects(tab, int(3000 * scale), 4, max_amb=6), 100, tmp)
     c4 = dict(base)
