@@ -226,6 +226,7 @@ def main():
     ap.add_argument("--haps", type=int, default=1000000)
     ap.add_argument("--ref-sample", type=int, default=2500, help="CPU port: subjects per core per step")
     ap.add_argument("--cpu-sample", type=int, default=12000, help="cpu_baseline: subjects on 1 core")
+    ap.add_argument("--text-subjects", type=int, default=1 << 18, help="subjects of the text-to-text measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -384,6 +385,7 @@ def main():
     # ---- spot parity against the oracle on the first subjects of rank 0 (not timed)
     parity = None
     cpu = None
+    e2e_text = None
     if rank == 0 and not args.no_cpu_baseline:
         import grim_oracle as go
         from grim.imputation.impute import Imputation
@@ -395,8 +397,22 @@ def main():
         ref = oimp.impute_lines(lines)
         t_cpu = time.time() - t0
         imp = Imputation(g, conf, np.ones(1))
-        mine = {k: "".join(v) for k, v in imp.impute_lines(lines).items()}
+        mine = {k: v.decode("utf8") for k, v in imp.impute_text("".join(lines).encode("utf8")).items()}
         parity = all(mine[k] == ref[k] for k in ref)
+        # text in -> six texts out through grimb_impute_text (C++ tokeniser/formatter + kernels),
+        # i.e. what grim.grim.impute(conf_file) does per chunk of the input file (not the headline)
+        n_t = min(S, args.text_subjects)
+        data = "".join(subject_lines(names, alleles, 0, n_t)).encode("utf8")
+        imp.impute_text(data[: len(data) // 8])
+        imp2 = Imputation(g, conf, np.ones(1))
+        imp2._text = imp._text
+        t0 = time.time()
+        texts = imp2.impute_text(data)
+        t_text = time.time() - t0
+        e2e_text = {"value": n_t / t_text, "unit": "subjects/s", "subjects": n_t, "in_bytes": len(data),
+                    "out_bytes": sum(len(v) for v in texts.values()),
+                    "tokenise_s": imp2.stats.get("tokenise_seconds"), "abi_s": imp2.stats.get("abi_seconds"),
+                    "format_s": imp2.stats.get("format_seconds")}
         cpu = {"value": n_c / t_cpu, "unit": "subjects/s", "cores": 1, "kind": "port",
                "sample": "first %d of the %d subjects through oracle/grim_oracle.py on one core; outputs "
                          "compared with the CUDA path: %s" % (n_c, S, "identical" if parity else "DIFFERENT"),
@@ -433,6 +449,7 @@ def main():
             "table": {"n_nodes": info["n_nodes"], "device_bytes": info["device_bytes"], "build_s": t_build},
             "status_counts": {str(i): int(c) for i, c in enumerate(np.bincount(status, minlength=6)) if c},
             "parity_sample_identical": parity,
+            "e2e_text": e2e_text,
         }
         print(json.dumps(line))
     if world > 1:

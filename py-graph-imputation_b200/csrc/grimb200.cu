@@ -28,6 +28,19 @@ static int fail(int code, const std::string& msg) {
   } while (0)
 
 extern "C" int grimb_abi_version(void) { return GRIMB_ABI_VERSION; }
+
+// page-locked host staging for the text pipeline (internal; nullptr when there is no device)
+extern "C" void* grimb_pinned_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+extern "C" void grimb_pinned_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
 extern "C" const char* grimb_last_error(void) { return g_err.c_str(); }
 
 // ------------------------------------------------------------------------------------------
@@ -162,7 +175,7 @@ __global__ void k_insert(HSlot* slots, uint64_t off, uint32_t mask, const uint64
   uint32_t node = first + i;
   uint64_t key = node_key[node];
   HSlot* base = slots + off;
-  uint32_t h = (uint32_t)mix64(key) & mask;
+  uint32_t h = ht_home(key, mask);
   for (;;) {
     unsigned long long old = atomicCAS((unsigned long long*)&base[h].key, ~0ull, (unsigned long long)key);
     if (old == ~0ull) {
@@ -405,8 +418,11 @@ extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
     }
     uint64_t so = 0;
     for (uint32_t m = 0; m < NL; ++m) {
+      // load factor <= 0.5; <= 0.25 for the full-haplotype label, which takes the bulk of the
+      // probes (2^L per fully typed subject, mostly misses: a miss scans until an empty slot)
+      const uint64_t want = (m == NL - 1 ? 4ull : 2ull) * (uint64_t)lcount[m];
       uint32_t sz = 2;
-      while (sz < 2 * (uint64_t)lcount[m]) sz <<= 1;
+      while (sz < want) sz <<= 1;
       hmask[m] = sz - 1;
       hoff[m] = so;
       so += sz;
@@ -674,6 +690,9 @@ k_impute(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArr
 // ------------------------------------------------------------------------------------------
 constexpr int FAST_WARPS = 8;
 constexpr int FAST_MAX_ROUNDS = 40;
+#ifndef FAST_MIN_BLOCKS
+#define FAST_MIN_BLOCKS 4
+#endif
 
 // accept test of calc_haps_pairs (impute.py:458-491) for one candidate pair with P == 1:
 //   x = eps / f1;  f2 >= x  and  m > 0  and  m*f2 >= x (x2 if the two haplotypes are equal)
@@ -691,11 +710,40 @@ struct FastPair {
   }
 };
 
-__global__ void __launch_bounds__(FAST_WARPS * 32)
+// Inputs of one subject, loaded one loop iteration ahead so that the dependent chain
+// allele_off -> alleles and prior_index -> prior overlaps the previous subject's work.
+struct FastIn {
+  uint32_t typed, c, off;
+  uint32_t pairs[5];
+  double m;
+};
+
+__device__ __forceinline__ void fast_load(FastIn& in, const GrimbBatch& B, uint64_t s, int L, int lane) {
+  in.typed = B.typed_mask[s];
+  in.off = B.allele_off[s];
+  // every listed count must be 1: the counts of one subject are 2L uint16 = L aligned uint32
+  const uint32_t* c32 = reinterpret_cast<const uint32_t*>(B.counts + s * (uint64_t)L * 2);
+  in.c = lane < L ? c32[lane] : 0x00010001u;
+  const uint16_t* al = B.alleles + in.off;
+  if ((in.off & 1u) == 0) {
+    const uint32_t* a32 = reinterpret_cast<const uint32_t*>(al);
+#pragma unroll
+    for (int l = 0; l < 5; ++l) in.pairs[l] = l < L ? a32[l] : 0u;
+  } else {
+#pragma unroll
+    for (int l = 0; l < 5; ++l) in.pairs[l] = l < L ? ((uint32_t)al[2 * l] | ((uint32_t)al[2 * l + 1] << 16)) : 0u;
+  }
+  in.m = __ldg(B.priors + B.prior_index[s]);
+}
+
+// Row space is claimed per WARP in chunks (one global atomicAdd per FAST_CHUNK rows), so the
+// kernel has no CTA barrier and no per-subject global atomic; the unused tail of a chunk is a
+// hole in the row arrays (offsets are explicit per subject, so holes are harmless).
+constexpr uint32_t FAST_CHUNK = 64;
+
+__global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_BLOCKS)
 k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O, uint32_t* worklist,
               unsigned int* worklist_n) {
-  __shared__ uint32_t s_hap[2][FAST_WARPS], s_pop[2][FAST_WARPS];
-  __shared__ unsigned long long s_base[2][2];
   __shared__ double s_chain[FAST_MAX_ROUNDS];
   __shared__ int s_nchain;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -718,215 +766,197 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
   }
   __syncthreads();
   const int nchain = s_nchain;
-  const uint64_t n_groups = ((uint64_t)B.n_subjects + FAST_WARPS - 1) / FAST_WARPS;
-  int buf = 0;
-  for (uint64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, buf ^= 1) {
-    const uint64_t s = grp * FAST_WARPS + warp;
-    const bool active = s < (uint64_t)B.n_subjects;
+  const uint64_t S = (uint64_t)B.n_subjects;
+  const uint64_t stride = (uint64_t)gridDim.x * FAST_WARPS;
+  uint64_t hap_base = 0, pop_base = 0;   // this warp's current chunks (lane-uniform)
+  uint32_t hap_left = 0, pop_left = 0;
+  uint64_t s = (uint64_t)blockIdx.x * FAST_WARPS + warp;
+  FastIn nxt;
+  if (s < S) fast_load(nxt, B, s, L, lane);
+  for (; s < S; s += stride) {
+    const FastIn in = nxt;
+    if (s + stride < S) fast_load(nxt, B, s + stride, L, lane);
     bool done = false;  // finished here (rows, an empty result, or a skipped subject)
-    uint32_t typed = 0, acc_mask = 0, rank = 0, n_acc = 0, evals = 0;
-    uint32_t pairs[5] = {0, 0, 0, 0, 0};
+    uint32_t acc_mask = 0, rank = 0, n_acc = 0, evals = 0;
     uint64_t key = 0, key2 = 0;
     double prob = 0.0, total = 0.0;
-    if (active) {
-      typed = B.typed_mask[s];
-      bool shape = typed == full && nchain >= 0;
-      const uint32_t off = B.allele_off[s];
+    const uint32_t typed = in.typed;
+    bool shape = typed == full && nchain >= 0;
+    shape = __all_sync(0xffffffffu, in.c == 0x00010001u) && shape;
+    if (shape) {
+      bool known = true;
+      uint32_t het = 0;
+#pragma unroll
+      for (int l = 0; l < 5; ++l)
+        if (l < L) {
+          const uint32_t a0 = in.pairs[l] & 0xffffu, a1 = in.pairs[l] >> 16;
+          const uint32_t pick = (lane >> l & 1) ? a1 : a0;
+          known = known && (pick - 1u) < T.n_alleles[l];
+          key |= (uint64_t)pick << T.shift[l];
+          if (a0 != a1) het |= 1u << l;
+        }
+      double f = 0.0;
+      if (lane < (1 << L) && known) {
+        const uint32_t node = ht_lookup(T, full, key);
+        if (node != GRIMB_NONE) f = __ldg(T.freq + node);  // P == 1
+      }
+      const int partner = ((int)full - lane) & 31;
+      FastPair pr;
+      pr.f = f;
+      pr.f2 = __shfl_sync(0xffffffffu, f, partner);
+      key2 = __shfl_sync(0xffffffffu, key, partner);
+      const uint32_t low = het & ((uint32_t)nphase - 1u);
+      const bool last_het = (het >> (L - 1)) & 1u;
+      const bool kept = lane < nphase && !((uint32_t)lane & ~low) && (last_het || (uint32_t)lane <= (low ^ (uint32_t)lane));
+      const bool cand = kept && pr.f > 0 && pr.f2 > 0;
+      const uint32_t cand_mask = __ballot_sync(0xffffffffu, cand);
+      const double m = in.m;
+      pr.same = key == key2;
+      pr.mpos = m > 0;
+      pr.y = m * pr.f2;
       {
-        // every listed count must be 1: the counts of one subject are 2L uint16 = L aligned uint32
-        const uint32_t* c32 = reinterpret_cast<const uint32_t*>(B.counts + s * (uint64_t)L * 2);
-        const uint32_t c = lane < L ? c32[lane] : 0x00010001u;
-        shape = __all_sync(0xffffffffu, c == 0x00010001u) && shape;
+        const double t = fmin(pr.f2, pr.same ? pr.y * 0.5 : pr.y);
+        const double b = pr.f * t;
+        const bool tiny = !(b > 1.0e-280);
+        pr.lo = tiny ? -1.0 : b * (1.0 - 0x1p-50);
+        pr.hi = tiny ? __longlong_as_double(0x7ff0000000000000LL) : b * (1.0 + 0x1p-50);
       }
-      if (shape) {
-        const uint16_t* al = B.alleles + off;
-        if ((off & 1u) == 0) {
-          const uint32_t* a32 = reinterpret_cast<const uint32_t*>(al);
-#pragma unroll
-          for (int l = 0; l < 5; ++l)
-            if (l < L) pairs[l] = a32[l];
-        } else {
-#pragma unroll
-          for (int l = 0; l < 5; ++l)
-            if (l < L) pairs[l] = (uint32_t)al[2 * l] | ((uint32_t)al[2 * l + 1] << 16);
-        }
-        bool known = true;
-        uint32_t het = 0;
-#pragma unroll
-        for (int l = 0; l < 5; ++l)
-          if (l < L) {
-            const uint32_t a0 = pairs[l] & 0xffffu, a1 = pairs[l] >> 16;
-            const uint32_t pick = (lane >> l & 1) ? a1 : a0;
-            known = known && (pick - 1u) < T.n_alleles[l];
-            key |= (uint64_t)pick << T.shift[l];
-            if (a0 != a1) het |= 1u << l;
-          }
-        double f = 0.0;
-        if (lane < (1 << L) && known) {
-          const uint32_t node = ht_lookup(T, full, key);
-          if (node != GRIMB_NONE) f = __ldg(T.freq + node);  // P == 1
-        }
-        const int partner = ((int)full - lane) & 31;
-        FastPair pr;
-        pr.f = f;
-        pr.f2 = __shfl_sync(0xffffffffu, f, partner);
-        key2 = __shfl_sync(0xffffffffu, key, partner);
-        const uint32_t low = het & ((uint32_t)nphase - 1u);
-        const bool last_het = (het >> (L - 1)) & 1u;
-        const bool kept = lane < nphase && !((uint32_t)lane & ~low) && (last_het || (uint32_t)lane <= (low ^ (uint32_t)lane));
-        const bool cand = kept && pr.f > 0 && pr.f2 > 0;
-        const uint32_t cand_mask = __ballot_sync(0xffffffffu, cand);
-        const double m = __ldg(B.priors + B.prior_index[s]);
-        pr.same = key == key2;
-        pr.mpos = m > 0;
-        pr.y = m * pr.f2;
-        {
-          const double t = fmin(pr.f2, pr.same ? pr.y * 0.5 : pr.y);
-          const double b = pr.f * t;
-          const bool tiny = !(b > 1.0e-280);
-          pr.lo = tiny ? -1.0 : b * (1.0 - 0x1p-50);
-          pr.hi = tiny ? __longlong_as_double(0x7ff0000000000000LL) : b * (1.0 + 0x1p-50);
-        }
-        if (cand) {
-          prob = pr.f * pr.f2 * m;
-          if (!pr.same) prob = prob * 2;
-        }
-        // first round of the schedule at which this pair is accepted (acceptance is monotone in eps)
-        uint32_t r_mine = 99;
-        if (cand) {
-          int r = 0;
-          while (r < nchain && !pr.accept(s_chain[r])) ++r;
-          if (r < nchain) r_mine = (uint32_t)r;
-        }
-        const uint32_t r_star = __reduce_min_sync(0xffffffffu, r_mine);
-        const uint32_t ncand = __popc(cand_mask);
-        if (r_star == 99) {
-          evals = ncand * (uint32_t)nchain;
-        } else {
-          evals = ncand * (r_star + 1);
-          bool a = r_mine <= r_star;
-          if (s_chain[r_star] > 0) {
-            // MaxProb of that round -> epsilon = MaxProb / 100000, one more evaluation (impute.py:1683-1693)
-            const uint32_t hi = a ? (uint32_t)__double2hiint(prob) : 0u;
-            const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
-            const uint32_t lo = (a && hi == mh) ? (uint32_t)__double2loint(prob) : 0u;
-            const uint32_t ml = __reduce_max_sync(0xffffffffu, lo);
-            const double eps = __hiloint2double((int)mh, (int)ml) / 100000;
-            a = cand && pr.accept(eps);
-            evals += ncand;
-          }
-          acc_mask = __ballot_sync(0xffffffffu, a);
-        }
-        if (acc_mask == 0 && planb) {
-          shape = false;  // Plan B / C: general kernel
-        } else {
-          done = true;
-          n_acc = __popc(acc_mask);
-          // += in phase order; rank by (probability desc, phase asc)
-          bool first = true;
-          for (uint32_t mm = acc_mask; mm; mm &= mm - 1) {
-            const int j = __ffs(mm) - 1;
-            const double pj = __shfl_sync(0xffffffffu, prob, j);
-            if (first) {
-              total = pj;
-              first = false;
-            } else {
-              total = total + pj;
-            }
-            if (pj > prob || (pj == prob && j < lane)) ++rank;
-          }
-          if (want_u && want_p) evals *= 2;  // the reference evaluates once per output kind
-        }
+      if (cand) {
+        prob = pr.f * pr.f2 * m;
+        if (!pr.same) prob = prob * 2;
       }
-      if (!shape) {
-        if (typed != 0) {
-          if (lane == 0) worklist[atomicAdd(worklist_n, 1u)] = (uint32_t)s;
-        } else {
-          done = true;  // GRIMB_ST_SKIPPED
+      // first round of the schedule at which this pair is accepted (acceptance is monotone in eps)
+      uint32_t r_mine = 99;
+      if (cand) {
+        int r = 0;
+        while (r < nchain && !pr.accept(s_chain[r])) ++r;
+        if (r < nchain) r_mine = (uint32_t)r;
+      }
+      const uint32_t r_star = __reduce_min_sync(0xffffffffu, r_mine);
+      const uint32_t ncand = __popc(cand_mask);
+      if (r_star == 99) {
+        evals = ncand * (uint32_t)nchain;
+      } else {
+        evals = ncand * (r_star + 1);
+        bool a = r_mine <= r_star;
+        if (s_chain[r_star] > 0) {
+          // MaxProb of that round -> epsilon = MaxProb / 100000, one more evaluation (impute.py:1683-1693)
+          const uint32_t hi = a ? (uint32_t)__double2hiint(prob) : 0u;
+          const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+          const uint32_t lo = (a && hi == mh) ? (uint32_t)__double2loint(prob) : 0u;
+          const uint32_t ml = __reduce_max_sync(0xffffffffu, lo);
+          const double eps = __hiloint2double((int)mh, (int)ml) / 100000;
+          a = cand && pr.accept(eps);
+          evals += ncand;
         }
+        acc_mask = __ballot_sync(0xffffffffu, a);
+      }
+      if (acc_mask == 0 && planb) {
+        shape = false;  // Plan B / C: general kernel
+      } else {
+        done = true;
+        n_acc = __popc(acc_mask);
+        // += in phase order; rank by (probability desc, phase asc)
+        bool first = true;
+        for (uint32_t mm = acc_mask; mm; mm &= mm - 1) {
+          const int j = __ffs(mm) - 1;
+          const double pj = __shfl_sync(0xffffffffu, prob, j);
+          if (first) {
+            total = pj;
+            first = false;
+          } else {
+            total = total + pj;
+          }
+          if (pj > prob || (pj == prob && j < lane)) ++rank;
+        }
+        if (want_u && want_p) evals *= 2;  // the reference evaluates once per output kind
       }
     }
-    // ---- rows of the 8 subjects of this CTA: one atomicAdd per kind (double-buffered: 2 barriers)
-    const bool rows = done && typed != 0 && n_acc != 0;
+    if (!shape) {
+      if (typed != 0) {
+        if (lane == 0) worklist[atomicAdd(worklist_n, 1u)] = (uint32_t)s;
+      } else {
+        done = true;  // GRIMB_ST_SKIPPED
+      }
+    }
+    if (!done) continue;
+    const bool rows = typed != 0 && n_acc != 0;
     const uint32_t nu = (rows && want_u) ? (lim_r < 1u ? lim_r : 1u) : 0u;
     const uint32_t np = (rows && want_p) ? (n_acc < lim_r ? n_acc : lim_r) : 0u;
     const uint32_t nup = (rows && want_u) ? (lim_p < 1u ? lim_p : 1u) : 0u;
     const uint32_t npp = (rows && want_p) ? (lim_p < 1u ? lim_p : 1u) : 0u;
+    const uint32_t nh = nu + np, npop = nup + npp;
+    if (nh > hap_left) {  // lane-uniform: refill this warp's chunk
+      unsigned long long b = 0;
+      const uint32_t take = nh > FAST_CHUNK ? nh : FAST_CHUNK;
+      if (lane == 0) b = atomicAdd(O.hap_counter, (unsigned long long)take);
+      hap_base = __shfl_sync(0xffffffffu, b, 0);
+      hap_left = take;
+    }
+    if (npop > pop_left) {
+      unsigned long long b = 0;
+      const uint32_t take = npop > FAST_CHUNK ? npop : FAST_CHUNK;
+      if (lane == 0) b = atomicAdd(O.pop_counter, (unsigned long long)take);
+      pop_base = __shfl_sync(0xffffffffu, b, 0);
+      pop_left = take;
+    }
+    const uint64_t hb = hap_base, pb = pop_base;
+    hap_base += nh;
+    hap_left -= nh;
+    pop_base += npop;
+    pop_left -= npop;
     if (lane == 0) {
-      s_hap[buf][warp] = nu + np;
-      s_pop[buf][warp] = nup + npp;
+      uint4 w0, w1, w2;
+      w0.x = (typed ? GRIMB_ST_OK : GRIMB_ST_SKIPPED) | ((typed && want_u) ? (GRIMB_PLAN_A << 8) : 0) |
+             ((typed && want_p) ? (GRIMB_PLAN_A << 16) : 0);
+      w0.y = nu;
+      w0.z = np;
+      w0.w = nup;
+      w1.x = npp;
+      w1.y = (want_u && n_acc) ? 1u : 0u;
+      w1.z = want_p ? n_acc : 0u;
+      w1.w = evals;
+      w2.x = (uint32_t)hb;
+      w2.y = (uint32_t)(hb >> 32);
+      w2.z = (uint32_t)pb;
+      w2.w = (uint32_t)(pb >> 32);
+      uint4* dst = reinterpret_cast<uint4*>(R.subjects + s);
+      dst[0] = w0;
+      dst[1] = w1;
+      dst[2] = w2;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t th = 0, tp = 0;
+    if ((int64_t)(hb + nh) <= R.hap_capacity) {
+      if (lane == 0 && nu) {
+        // the single UMUG genotype: per-locus (min, max) of the two typed alleles
+        uint64_t glo = 0, ghi = 0;
 #pragma unroll
-      for (int w = 0; w < FAST_WARPS; ++w) {
-        th += s_hap[buf][w];
-        tp += s_pop[buf][w];
-      }
-      s_base[buf][0] = th ? atomicAdd(O.hap_counter, (unsigned long long)th) : 0ull;
-      s_base[buf][1] = tp ? atomicAdd(O.pop_counter, (unsigned long long)tp) : 0ull;
-    }
-    __syncthreads();
-    if (active && done) {
-      uint64_t hb = s_base[buf][0], pb = s_base[buf][1];
-      for (int w = 0; w < warp; ++w) {
-        hb += s_hap[buf][w];
-        pb += s_pop[buf][w];
-      }
-      if (lane == 0) {
-        uint4 w0, w1, w2;
-        w0.x = (typed ? GRIMB_ST_OK : GRIMB_ST_SKIPPED) | ((typed && want_u) ? (GRIMB_PLAN_A << 8) : 0) |
-               ((typed && want_p) ? (GRIMB_PLAN_A << 16) : 0);
-        w0.y = nu;
-        w0.z = np;
-        w0.w = nup;
-        w1.x = npp;
-        w1.y = (want_u && n_acc) ? 1u : 0u;
-        w1.z = want_p ? n_acc : 0u;
-        w1.w = evals;
-        w2.x = (uint32_t)hb;
-        w2.y = (uint32_t)(hb >> 32);
-        w2.z = (uint32_t)pb;
-        w2.w = (uint32_t)(pb >> 32);
-        uint4* dst = reinterpret_cast<uint4*>(R.subjects + s);
-        dst[0] = w0;
-        dst[1] = w1;
-        dst[2] = w2;
-      }
-      if ((int64_t)(hb + nu + np) <= R.hap_capacity) {
-        if (lane == 0 && nu) {
-          // the single UMUG genotype: per-locus (min, max) of the two typed alleles
-          uint64_t glo = 0, ghi = 0;
-#pragma unroll
-          for (int l = 0; l < 5; ++l)
-            if (l < L) {
-              const uint32_t a0 = pairs[l] & 0xffffu, a1 = pairs[l] >> 16;
-              glo |= (uint64_t)(a0 < a1 ? a0 : a1) << T.shift[l];
-              ghi |= (uint64_t)(a0 < a1 ? a1 : a0) << T.shift[l];
-            }
-          GrimbHapRow o;
-          o.a = glo;
-          o.b = ghi;
-          o.prob = total;
-          R.hap_rows[hb] = o;
-        }
-        if ((acc_mask >> lane & 1u) && rank < np) {
-          GrimbHapRow o;
-          o.a = key;
-          o.b = key2;
-          o.prob = prob;
-          R.hap_rows[hb + nu + rank] = o;
-        }
-      }
-      if ((int64_t)(pb + nup + npp) <= R.pop_capacity && lane < (int)(nup + npp)) {
-        GrimbPopRow o;
-        o.pop_a = 0;
-        o.pop_b = 0;
-        o.pad = 0;
+        for (int l = 0; l < 5; ++l)
+          if (l < L) {
+            const uint32_t a0 = in.pairs[l] & 0xffffu, a1 = in.pairs[l] >> 16;
+            glo |= (uint64_t)(a0 < a1 ? a0 : a1) << T.shift[l];
+            ghi |= (uint64_t)(a0 < a1 ? a1 : a0) << T.shift[l];
+          }
+        GrimbHapRow o;
+        o.a = glo;
+        o.b = ghi;
         o.prob = total;
-        R.pop_rows[pb + lane] = o;
+        R.hap_rows[hb] = o;
       }
+      if ((acc_mask >> lane & 1u) && rank < np) {
+        GrimbHapRow o;
+        o.a = key;
+        o.b = key2;
+        o.prob = prob;
+        R.hap_rows[hb + nu + rank] = o;
+      }
+    }
+    if ((int64_t)(pb + npop) <= R.pop_capacity && lane < (int)npop) {
+      GrimbPopRow o;
+      o.pop_a = 0;
+      o.pop_b = 0;
+      o.pad = 0;
+      o.prob = total;
+      R.pop_rows[pb + lane] = o;
     }
   }
 }
@@ -1041,7 +1071,7 @@ extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const
       CK(e->worklist.reserve((size_t)batch->n_subjects * 4 + 16));
       unsigned int* cnt = (unsigned int*)(e->d_counters + 3);
       const uint64_t groups = ((uint64_t)batch->n_subjects + FAST_WARPS - 1) / FAST_WARPS;
-      uint64_t fg = (uint64_t)e->sm_count * 8;
+      uint64_t fg = (uint64_t)e->sm_count * FAST_MIN_BLOCKS;  // resident CTAs only: each warp strides over subjects
       if (fg > groups) fg = groups;
       k_impute_fast<<<(unsigned)fg, FAST_WARPS * 32, 0, st>>>(tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt);
       CK(cudaGetLastError());

@@ -69,16 +69,24 @@ GD HSlot load_slot(const HSlot* p) {
 #endif
 }
 
-// One probe: hash, then linear scan of 16-byte slots until the key or an empty slot.
+// Home slot of a key: always the first slot of a 32-byte sector (two 16-byte slots), so a probe
+// reads whole sectors -- both slots of a sector are fetched by two adjacent 128-bit loads that
+// resolve to one memory transaction.
+GD uint32_t ht_home(uint64_t key, uint32_t mask) { return (uint32_t)mix64(key) & mask & ~1u; }
+
+// One probe: hash, then linear scan, a sector (two slots) per step, until the key or an empty slot.
 GD uint32_t ht_lookup(const TablesView& T, uint32_t label, uint64_t key) {
   const uint32_t mask = T.ht_mask[label];
   const HSlot* base = T.slots + T.ht_off[label];
-  uint32_t h = (uint32_t)mix64(key) & mask;
+  uint32_t h = ht_home(key, mask);
   for (;;) {
-    HSlot s = load_slot(base + h);
-    if (s.node == GRIMB_NONE) return GRIMB_NONE;
-    if (s.key == key) return s.node;
-    h = (h + 1) & mask;
+    const HSlot s0 = load_slot(base + h);
+    const HSlot s1 = load_slot(base + h + 1);
+    if (s0.node == GRIMB_NONE) return GRIMB_NONE;
+    if (s0.key == key) return s0.node;
+    if (s1.node == GRIMB_NONE) return GRIMB_NONE;
+    if (s1.key == key) return s1.node;
+    h = (h + 2) & mask;
   }
 }
 

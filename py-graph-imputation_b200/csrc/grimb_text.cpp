@@ -18,6 +18,9 @@
 
 #include "../../include/grimb200.h"
 
+extern "C" void* grimb_pinned_alloc(size_t bytes);  // grimb200.cu: cudaMallocHost or nullptr
+extern "C" void grimb_pinned_free(void* p);
+
 namespace {
 
 using sv = std::string_view;
@@ -170,8 +173,33 @@ struct GrimbText {
   std::vector<uint16_t> b_typed, b_counts, b_alleles;
   std::vector<uint32_t> b_off, b_prior;
   std::string out[6];
-  // results of impute_text (kept for format)
-  std::vector<GrimbSubjectResult> r_subj;
+  // pinned staging for grimb_impute_text (grow-only) and the adaptive row-capacity estimate
+  struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+    void* reserve(size_t bytes) {
+      if (bytes <= cap && p) return p;
+      release();
+      size_t want = bytes + bytes / 4 + 4096;
+      p = grimb_pinned_alloc(want);
+      pinned = p != nullptr;
+      if (!p) p = malloc(want);
+      cap = p ? want : 0;
+      return p;
+    }
+    void release() {
+      if (p) {
+        if (pinned) grimb_pinned_free(p);
+        else free(p);
+      }
+      p = nullptr;
+      cap = 0;
+    }
+    ~HostBuf() { release(); }
+  };
+  HostBuf hb_subj, hb_hap, hb_pop;
+  double hap_per_subject = 3.0, pop_per_subject = 2.5;
 
   template <class F>
   void parallel(size_t n, F f) const {
@@ -700,7 +728,9 @@ extern "C" int grimb_impute_text(GrimbText* t, GrimbEngine* const* engines, int3
   const size_t S = (size_t)b.n_subjects;
   const int L = t->L;
   // final per-subject records + rows, re-based as tiers complete
-  std::vector<GrimbSubjectResult> subj(S);
+  std::vector<GrimbSubjectResult> subj;
+  subj.reserve(S);
+  subj.resize(S);
   std::vector<GrimbHapRow> hap;
   std::vector<GrimbPopRow> pop;
   std::vector<uint32_t> todo(S);
@@ -740,20 +770,22 @@ extern "C" int grimb_impute_text(GrimbText* t, GrimbEngine* const* engines, int3
       sb.n_alleles_total = (int64_t)tot;
       sb.prior_index = g_prior.data();
     }
-    std::vector<GrimbSubjectResult> rs(n);
-    int64_t hap_cap = std::max<int64_t>(1024, (int64_t)n * 2 * std::min(cfg->n_results, 16));
-    int64_t pop_cap = std::max<int64_t>(1024, (int64_t)n * 2 * std::min(cfg->n_pop_results, 4));
-    std::vector<GrimbHapRow> rh;
-    std::vector<GrimbPopRow> rp;
+    // pinned, grow-only staging; row capacity follows the rows/subject seen so far (+25 %)
+    GrimbSubjectResult* rs = (GrimbSubjectResult*)t->hb_subj.reserve(n * sizeof(GrimbSubjectResult));
+    int64_t hap_cap = std::max<int64_t>(1024, (int64_t)((double)n * t->hap_per_subject * 1.25) + 64);
+    int64_t pop_cap = std::max<int64_t>(1024, (int64_t)((double)n * t->pop_per_subject * 1.25) + 64);
+    GrimbHapRow* rh = nullptr;
+    GrimbPopRow* rp = nullptr;
     int64_t need_h = 0, need_p = 0;
     for (;;) {
-      rh.resize((size_t)hap_cap);
-      rp.resize((size_t)pop_cap);
+      rh = (GrimbHapRow*)t->hb_hap.reserve((size_t)hap_cap * sizeof(GrimbHapRow));
+      rp = (GrimbPopRow*)t->hb_pop.reserve((size_t)pop_cap * sizeof(GrimbPopRow));
+      if (!rs || !rh || !rp) return tfail(GRIMB_E_NOMEM, "host staging allocation failed");
       GrimbResults r;
-      r.subjects = rs.data();
-      r.hap_rows = rh.data();
+      r.subjects = rs;
+      r.hap_rows = rh;
       r.hap_capacity = hap_cap;
-      r.pop_rows = rp.data();
+      r.pop_rows = rp;
       r.pop_capacity = pop_cap;
       r.hap_rows_needed = &need_h;
       r.pop_rows_needed = &need_p;
@@ -766,9 +798,13 @@ extern "C" int grimb_impute_text(GrimbText* t, GrimbEngine* const* engines, int3
       if (rc) return rc;
       break;
     }
+    if (tier == 0 && n > 0) {
+      t->hap_per_subject = std::max(1.0, (double)need_h / (double)n);
+      t->pop_per_subject = std::max(1.0, (double)need_p / (double)n);
+    }
     const uint64_t hbase = hap.size(), pbase = pop.size();
-    hap.insert(hap.end(), rh.begin(), rh.begin() + need_h);
-    pop.insert(pop.end(), rp.begin(), rp.begin() + need_p);
+    hap.insert(hap.end(), rh, rh + need_h);
+    pop.insert(pop.end(), rp, rp + need_p);
     std::vector<uint32_t> again;
     for (size_t k = 0; k < n; ++k) {
       if (rs[k].status == GRIMB_ST_WORKSPACE) {

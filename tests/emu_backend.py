@@ -112,7 +112,7 @@ def arrays_from_oracle(g, loci):
     so = 0
     for m in range(1 << L):
         sz = 2
-        while sz < 2 * int(label_count[m]):
+        while sz < (4 if m == (1 << L) - 1 else 2) * int(label_count[m]):
             sz <<= 1
         ht_off[m] = so
         ht_mask[m] = sz - 1
@@ -123,7 +123,7 @@ def arrays_from_oracle(g, loci):
     for i in range(n):
         m = int(node_label[i])
         k = int(node_key[i])
-        h = mix64(k) & 0xFFFFFFFF & int(ht_mask[m])
+        h = mix64(k) & 0xFFFFFFFF & int(ht_mask[m]) & ~1      # ht_home(): sector-aligned
         base = int(ht_off[m])
         while slots["node"][base + h] != 0xFFFFFFFF:
             h = (h + 1) & int(ht_mask[m])
