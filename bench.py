@@ -403,7 +403,7 @@ def main():
         # i.e. what grim.grim.impute(conf_file) does per chunk of the input file (not the headline)
         n_t = min(S, args.text_subjects)
         data = "".join(subject_lines(names, alleles, 0, n_t)).encode("utf8")
-        imp.impute_text(data[: len(data) // 8])
+        imp.impute_text(data)           # warm-up at full size (pinned staging + device buffers grow once)
         imp2 = Imputation(g, conf, np.ones(1))
         imp2._text = imp._text
         t0 = time.time()

@@ -96,10 +96,58 @@ def run_impute(conf_file="../conf/minimal-configuration.json", project_dir_graph
                        ("Save space mode", "save_mode")):
         print("\t{}: {}".format(label, config[key]))
     print("*" * 100)
+    dist = _process_group()
+    if dist is not None and dist.get_world_size() > 1:
+        return _run_impute_sharded(dist, config, hap_pop_pair, graph)
     if graph is None:
         graph = Graph(config, device=device)
         graph.build_graph(config["node_file"], config["top_links_file"], config["edges_file"])
     imputation = Imputation(graph, config)
     pathlib.Path(config["imputation_out_path"]).mkdir(parents=False, exist_ok=True)
     imputation.impute_file(config, em_mr=hap_pop_pair)
+    return graph
+
+
+def _process_group():
+    """torch.distributed, if the caller started one process per GPU (torchrun); else None."""
+    import sys
+    if "torch" not in sys.modules:
+        return None
+    import torch.distributed as dist
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+def _run_impute_sharded(dist, config, hap_pop_pair, graph):
+    """One process per GPU: tables built on rank 0 and replicated by one NCCL broadcast, input
+    lines sharded by contiguous ranges, rank 0 writes the six files in input order."""
+    import os
+    from .imputation import multi_gpu
+    if hap_pop_pair:
+        raise NotImplementedError("EM output modes are outside the B200 hot path (SURVEY 8f-4)")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    device = int(os.environ.get("LOCAL_RANK", rank))
+    if graph is None:
+        if rank == 0:
+            graph = Graph(config, device=device)
+            graph.build_graph(config["node_file"], config["top_links_file"], config["edges_file"])
+        graph = multi_gpu.broadcast_graph(graph, config, device, src=0)
+    imputation = Imputation(graph, config)
+    with open(config["imputation_input_file"], "rb") as f:
+        lines = f.readlines()
+    lo, hi = multi_gpu.shard_range(len(lines), rank, world)
+    mine = imputation.impute_text(b"".join(lines[lo:hi]), first_index=lo)
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(mine, parts, dst=0)
+    if rank == 0:
+        pathlib.Path(config["imputation_out_path"]).mkdir(parents=False, exist_ok=True)
+        targets = {"miss": "imputation_out_miss_file", "problem": "imputation_out_problem_file"}
+        if config["output_MUUG"]:
+            targets.update(umug="imputation_out_umug_freq_file", umug_pops="imputation_out_umug_pops_file")
+        if config["output_haplotypes"]:
+            targets.update(pmug="imputation_out_hap_freq_file", pmug_pops="imputation_out_hap_pops_file")
+        for k, ck in targets.items():
+            with open(config[ck], "wb") as f:
+                for part in parts:          # rank order == input order
+                    f.write(part[k])
+    dist.barrier()
     return graph
