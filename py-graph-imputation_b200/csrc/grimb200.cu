@@ -718,12 +718,12 @@ struct FastIn {
   double m;
 };
 
-__device__ __forceinline__ void fast_load(FastIn& in, const GrimbBatch& B, uint64_t s, int L, int lane) {
+__device__ __forceinline__ void fast_load(FastIn& in, const GrimbBatch& B, uint64_t s, int L, int i) {
   in.typed = B.typed_mask[s];
   in.off = B.allele_off[s];
   // every listed count must be 1: the counts of one subject are 2L uint16 = L aligned uint32
   const uint32_t* c32 = reinterpret_cast<const uint32_t*>(B.counts + s * (uint64_t)L * 2);
-  in.c = lane < L ? c32[lane] : 0x00010001u;
+  in.c = i < L ? c32[i] : 0x00010001u;
   const uint16_t* al = B.alleles + in.off;
   if ((in.off & 1u) == 0) {
     const uint32_t* a32 = reinterpret_cast<const uint32_t*>(al);
@@ -736,17 +736,80 @@ __device__ __forceinline__ void fast_load(FastIn& in, const GrimbBatch& B, uint6
   in.m = __ldg(B.priors + B.prior_index[s]);
 }
 
-// Row space is claimed per WARP in chunks (one global atomicAdd per FAST_CHUNK rows), so the
+// Two independent probes of the full-label region; the first sector of each is requested before
+// either is examined (the common case resolves both in that one round trip).
+__device__ __forceinline__ void ht_lookup2(const TablesView& T, uint32_t label, uint64_t k1, bool p1, uint64_t k2, bool p2,
+                                           uint32_t& n1, uint32_t& n2) {
+  const uint32_t mask = T.ht_mask[label];
+  const HSlot* base = T.slots + T.ht_off[label];
+  uint32_t h1 = ht_home(k1, mask), h2 = ht_home(k2, mask);
+  n1 = n2 = GRIMB_NONE;
+  HSlot a0, a1, b0, b1;
+  a0.node = a1.node = b0.node = b1.node = GRIMB_NONE;
+  a0.key = a1.key = b0.key = b1.key = 0;
+  if (p1) {
+    a0 = load_slot(base + h1);
+    a1 = load_slot(base + h1 + 1);
+  }
+  if (p2) {
+    b0 = load_slot(base + h2);
+    b1 = load_slot(base + h2 + 1);
+  }
+  bool more1 = false, more2 = false;
+  if (p1) {
+    if (a0.node == GRIMB_NONE) {}
+    else if (a0.key == k1) n1 = a0.node;
+    else if (a1.node == GRIMB_NONE) {}
+    else if (a1.key == k1) n1 = a1.node;
+    else more1 = true;
+  }
+  if (p2) {
+    if (b0.node == GRIMB_NONE) {}
+    else if (b0.key == k2) n2 = b0.node;
+    else if (b1.node == GRIMB_NONE) {}
+    else if (b1.key == k2) n2 = b1.node;
+    else more2 = true;
+  }
+  while (more1) {
+    h1 = (h1 + 2) & mask;
+    a0 = load_slot(base + h1);
+    a1 = load_slot(base + h1 + 1);
+    more1 = false;
+    if (a0.node == GRIMB_NONE) {}
+    else if (a0.key == k1) n1 = a0.node;
+    else if (a1.node == GRIMB_NONE) {}
+    else if (a1.key == k1) n1 = a1.node;
+    else more1 = true;
+  }
+  while (more2) {
+    h2 = (h2 + 2) & mask;
+    b0 = load_slot(base + h2);
+    b1 = load_slot(base + h2 + 1);
+    more2 = false;
+    if (b0.node == GRIMB_NONE) {}
+    else if (b0.key == k2) n2 = b0.node;
+    else if (b1.node == GRIMB_NONE) {}
+    else if (b1.key == k2) n2 = b1.node;
+    else more2 = true;
+  }
+}
+
+// Row space is claimed per HALF-WARP in chunks (one global atomicAdd per FAST_CHUNK rows), so the
 // kernel has no CTA barrier and no per-subject global atomic; the unused tail of a chunk is a
 // hole in the row arrays (offsets are explicit per subject, so holes are harmless).
 constexpr uint32_t FAST_CHUNK = 64;
 
+// Half-warp per subject: lane i (0..15) of a half owns phase i and probes both of its haplotypes
+// (side choice i and its complement), so a warp imputes two subjects at once and nothing has to
+// be shuffled between the two sides of a phase.  All votes / reductions use the half's lane mask.
 __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_BLOCKS)
 k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O, uint32_t* worklist,
               unsigned int* worklist_n) {
   __shared__ double s_chain[FAST_MAX_ROUNDS];
   __shared__ int s_nchain;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = lane >> 4, i = lane & 15, hbase = half << 4;
+  const uint32_t hmask = 0xFFFFu << hbase;
   const int L = T.L;
   const uint32_t full = (1u << L) - 1u;
   const int nphase = 1 << (L - 1);
@@ -767,49 +830,49 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
   __syncthreads();
   const int nchain = s_nchain;
   const uint64_t S = (uint64_t)B.n_subjects;
-  const uint64_t stride = (uint64_t)gridDim.x * FAST_WARPS;
-  uint64_t hap_base = 0, pop_base = 0;   // this warp's current chunks (lane-uniform)
+  const uint64_t stride = (uint64_t)gridDim.x * FAST_WARPS * 2;
+  uint64_t hap_base = 0, pop_base = 0;   // this half-warp's current chunks (uniform within the half)
   uint32_t hap_left = 0, pop_left = 0;
-  uint64_t s = (uint64_t)blockIdx.x * FAST_WARPS + warp;
+  uint64_t s = ((uint64_t)blockIdx.x * FAST_WARPS + warp) * 2 + half;
   FastIn nxt;
-  if (s < S) fast_load(nxt, B, s, L, lane);
-  for (; s < S; s += stride) {
+  if (s < S) fast_load(nxt, B, s, L, i);
+  for (; s < S; s += stride) {   // the two halves may leave the loop one iteration apart
     const FastIn in = nxt;
-    if (s + stride < S) fast_load(nxt, B, s + stride, L, lane);
+    if (s + stride < S) fast_load(nxt, B, s + stride, L, i);
     bool done = false;  // finished here (rows, an empty result, or a skipped subject)
-    uint32_t acc_mask = 0, rank = 0, n_acc = 0, evals = 0;
+    uint32_t acc = 0, rank = 0, n_acc = 0, evals = 0;
     uint64_t key = 0, key2 = 0;
     double prob = 0.0, total = 0.0;
     const uint32_t typed = in.typed;
     bool shape = typed == full && nchain >= 0;
-    shape = __all_sync(0xffffffffu, in.c == 0x00010001u) && shape;
+    shape = __all_sync(hmask, in.c == 0x00010001u) && shape;
     if (shape) {
-      bool known = true;
+      bool known1 = true, known2 = true;
       uint32_t het = 0;
 #pragma unroll
       for (int l = 0; l < 5; ++l)
         if (l < L) {
           const uint32_t a0 = in.pairs[l] & 0xffffu, a1 = in.pairs[l] >> 16;
-          const uint32_t pick = (lane >> l & 1) ? a1 : a0;
-          known = known && (pick - 1u) < T.n_alleles[l];
-          key |= (uint64_t)pick << T.shift[l];
+          const bool bit = (i >> l) & 1;      // the last locus never flips: bit L-1 of i < 2^(L-1) is 0
+          const uint32_t p1 = bit ? a1 : a0, p2 = bit ? a0 : a1;
+          known1 = known1 && (p1 - 1u) < T.n_alleles[l];
+          known2 = known2 && (p2 - 1u) < T.n_alleles[l];
+          key |= (uint64_t)p1 << T.shift[l];
+          key2 |= (uint64_t)p2 << T.shift[l];
           if (a0 != a1) het |= 1u << l;
         }
-      double f = 0.0;
-      if (lane < (1 << L) && known) {
-        const uint32_t node = ht_lookup(T, full, key);
-        if (node != GRIMB_NONE) f = __ldg(T.freq + node);  // P == 1
-      }
-      const int partner = ((int)full - lane) & 31;
-      FastPair pr;
-      pr.f = f;
-      pr.f2 = __shfl_sync(0xffffffffu, f, partner);
-      key2 = __shfl_sync(0xffffffffu, key, partner);
       const uint32_t low = het & ((uint32_t)nphase - 1u);
       const bool last_het = (het >> (L - 1)) & 1u;
-      const bool kept = lane < nphase && !((uint32_t)lane & ~low) && (last_het || (uint32_t)lane <= (low ^ (uint32_t)lane));
+      const bool kept = i < nphase && !((uint32_t)i & ~low) && (last_het || (uint32_t)i <= (low ^ (uint32_t)i));
+      // side 2 is only probed when side 1 exists (comp_phase_prob_*: `if len(Prob1) > 0`); probing
+      // both at once returns the same lists
+      uint32_t n1, n2;
+      ht_lookup2(T, full, key, kept && known1, key2, kept && known2, n1, n2);
+      FastPair pr;
+      pr.f = n1 != GRIMB_NONE ? __ldg(T.freq + n1) : 0.0;   // P == 1
+      pr.f2 = n2 != GRIMB_NONE ? __ldg(T.freq + n2) : 0.0;
       const bool cand = kept && pr.f > 0 && pr.f2 > 0;
-      const uint32_t cand_mask = __ballot_sync(0xffffffffu, cand);
+      const uint32_t ncand = __popc(__ballot_sync(hmask, cand));
       const double m = in.m;
       pr.same = key == key2;
       pr.mpos = m > 0;
@@ -832,8 +895,7 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
         while (r < nchain && !pr.accept(s_chain[r])) ++r;
         if (r < nchain) r_mine = (uint32_t)r;
       }
-      const uint32_t r_star = __reduce_min_sync(0xffffffffu, r_mine);
-      const uint32_t ncand = __popc(cand_mask);
+      const uint32_t r_star = __reduce_min_sync(hmask, r_mine);
       if (r_star == 99) {
         evals = ncand * (uint32_t)nchain;
       } else {
@@ -842,39 +904,39 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
         if (s_chain[r_star] > 0) {
           // MaxProb of that round -> epsilon = MaxProb / 100000, one more evaluation (impute.py:1683-1693)
           const uint32_t hi = a ? (uint32_t)__double2hiint(prob) : 0u;
-          const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+          const uint32_t mh = __reduce_max_sync(hmask, hi);
           const uint32_t lo = (a && hi == mh) ? (uint32_t)__double2loint(prob) : 0u;
-          const uint32_t ml = __reduce_max_sync(0xffffffffu, lo);
+          const uint32_t ml = __reduce_max_sync(hmask, lo);
           const double eps = __hiloint2double((int)mh, (int)ml) / 100000;
           a = cand && pr.accept(eps);
           evals += ncand;
         }
-        acc_mask = __ballot_sync(0xffffffffu, a);
+        acc = (__ballot_sync(hmask, a) >> hbase) & 0xFFFFu;
       }
-      if (acc_mask == 0 && planb) {
+      if (acc == 0 && planb) {
         shape = false;  // Plan B / C: general kernel
       } else {
         done = true;
-        n_acc = __popc(acc_mask);
+        n_acc = __popc(acc);
         // += in phase order; rank by (probability desc, phase asc)
         bool first = true;
-        for (uint32_t mm = acc_mask; mm; mm &= mm - 1) {
+        for (uint32_t mm = acc; mm; mm &= mm - 1) {
           const int j = __ffs(mm) - 1;
-          const double pj = __shfl_sync(0xffffffffu, prob, j);
+          const double pj = __shfl_sync(hmask, prob, hbase + j);
           if (first) {
             total = pj;
             first = false;
           } else {
             total = total + pj;
           }
-          if (pj > prob || (pj == prob && j < lane)) ++rank;
+          if (pj > prob || (pj == prob && j < i)) ++rank;
         }
         if (want_u && want_p) evals *= 2;  // the reference evaluates once per output kind
       }
     }
     if (!shape) {
       if (typed != 0) {
-        if (lane == 0) worklist[atomicAdd(worklist_n, 1u)] = (uint32_t)s;
+        if (i == 0) worklist[atomicAdd(worklist_n, 1u)] = (uint32_t)s;
       } else {
         done = true;  // GRIMB_ST_SKIPPED
       }
@@ -886,18 +948,18 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
     const uint32_t nup = (rows && want_u) ? (lim_p < 1u ? lim_p : 1u) : 0u;
     const uint32_t npp = (rows && want_p) ? (lim_p < 1u ? lim_p : 1u) : 0u;
     const uint32_t nh = nu + np, npop = nup + npp;
-    if (nh > hap_left) {  // lane-uniform: refill this warp's chunk
+    if (nh > hap_left) {  // uniform within the half: refill its chunk
       unsigned long long b = 0;
       const uint32_t take = nh > FAST_CHUNK ? nh : FAST_CHUNK;
-      if (lane == 0) b = atomicAdd(O.hap_counter, (unsigned long long)take);
-      hap_base = __shfl_sync(0xffffffffu, b, 0);
+      if (i == 0) b = atomicAdd(O.hap_counter, (unsigned long long)take);
+      hap_base = __shfl_sync(hmask, b, hbase);
       hap_left = take;
     }
     if (npop > pop_left) {
       unsigned long long b = 0;
       const uint32_t take = npop > FAST_CHUNK ? npop : FAST_CHUNK;
-      if (lane == 0) b = atomicAdd(O.pop_counter, (unsigned long long)take);
-      pop_base = __shfl_sync(0xffffffffu, b, 0);
+      if (i == 0) b = atomicAdd(O.pop_counter, (unsigned long long)take);
+      pop_base = __shfl_sync(hmask, b, hbase);
       pop_left = take;
     }
     const uint64_t hb = hap_base, pb = pop_base;
@@ -905,7 +967,7 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
     hap_left -= nh;
     pop_base += npop;
     pop_left -= npop;
-    if (lane == 0) {
+    if (i == 0) {
       uint4 w0, w1, w2;
       w0.x = (typed ? GRIMB_ST_OK : GRIMB_ST_SKIPPED) | ((typed && want_u) ? (GRIMB_PLAN_A << 8) : 0) |
              ((typed && want_p) ? (GRIMB_PLAN_A << 16) : 0);
@@ -926,7 +988,7 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
       dst[2] = w2;
     }
     if ((int64_t)(hb + nh) <= R.hap_capacity) {
-      if (lane == 0 && nu) {
+      if (i == 0 && nu) {
         // the single UMUG genotype: per-locus (min, max) of the two typed alleles
         uint64_t glo = 0, ghi = 0;
 #pragma unroll
@@ -942,7 +1004,7 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
         o.prob = total;
         R.hap_rows[hb] = o;
       }
-      if ((acc_mask >> lane & 1u) && rank < np) {
+      if ((acc >> i & 1u) && rank < np) {
         GrimbHapRow o;
         o.a = key;
         o.b = key2;
@@ -950,13 +1012,13 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
         R.hap_rows[hb + nu + rank] = o;
       }
     }
-    if ((int64_t)(pb + npop) <= R.pop_capacity && lane < (int)npop) {
+    if ((int64_t)(pb + npop) <= R.pop_capacity && i < (int)npop) {
       GrimbPopRow o;
       o.pop_a = 0;
       o.pop_b = 0;
       o.pad = 0;
       o.prob = total;
-      R.pop_rows[pb + lane] = o;
+      R.pop_rows[pb + i] = o;
     }
   }
 }
@@ -1070,7 +1132,7 @@ extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const
       // warp-per-subject kernel first; what it cannot finish goes through the general kernel
       CK(e->worklist.reserve((size_t)batch->n_subjects * 4 + 16));
       unsigned int* cnt = (unsigned int*)(e->d_counters + 3);
-      const uint64_t groups = ((uint64_t)batch->n_subjects + FAST_WARPS - 1) / FAST_WARPS;
+      const uint64_t groups = ((uint64_t)batch->n_subjects + FAST_WARPS * 2 - 1) / (FAST_WARPS * 2);
       uint64_t fg = (uint64_t)e->sm_count * FAST_MIN_BLOCKS;  // resident CTAs only: each warp strides over subjects
       if (fg > groups) fg = groups;
       k_impute_fast<<<(unsigned)fg, FAST_WARPS * 32, 0, st>>>(tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt);
