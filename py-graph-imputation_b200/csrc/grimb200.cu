@@ -651,10 +651,40 @@ extern "C" int grimb_tables_from_image(const void* dev_image, int64_t bytes, int
 // ------------------------------------------------------------------------------------------
 // imputation kernel: persistent CTAs, one subject per CTA at a time, dynamic work fetch
 // ------------------------------------------------------------------------------------------
-// `worklist` (optional): subject indices left over by k_impute_fast, count in *worklist_n.
+// Work for the general kernel is handed out heaviest first (longest-processing-time order): a
+// classify pass sorts the pending subjects into GRIMB_BUCKETS cost buckets, and the persistent
+// CTAs draw tickets that walk bucket 0 (heaviest) to bucket 3.  Without it a 50 ms subject that
+// happens to sit at the end of the batch becomes the tail of the whole launch.
+constexpr int GRIMB_BUCKETS = 4;
+
+__global__ void k_classify(GrimbBatch B, int L, const uint32_t* list, const unsigned int* list_n, uint32_t* buckets,
+                           unsigned int* bucket_n, uint64_t stride) {
+  const uint64_t n = list ? (uint64_t)*list_n : (uint64_t)B.n_subjects;
+  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n; w += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t s = list ? list[w] : (uint32_t)w;
+    const uint32_t typed = B.typed_mask[s];
+    const uint16_t* cn = B.counts + (uint64_t)s * L * 2;
+    // candidates per phase ~ product of the listed alleles; phases = 2^(typed-1); an untyped
+    // locus multiplies the hits (top links / whole-label scans in Plan B)
+    float a = 1.f, b = 1.f;
+    int nt = 0;
+    for (int l = 0; l < L; ++l)
+      if (typed >> l & 1u) {
+        a *= (float)cn[2 * l];
+        b *= (float)cn[2 * l + 1];
+        ++nt;
+      }
+    float cost = (a + b) * (float)(1u << (nt > 0 ? nt - 1 : 0));
+    if (nt < L) cost *= 16.f;
+    const int k = cost >= 32768.f ? 0 : cost >= 2048.f ? 1 : cost >= 128.f ? 2 : 3;
+    buckets[(uint64_t)k * stride + atomicAdd(&bucket_n[k], 1u)] = s;
+  }
+}
+
 __global__ void __launch_bounds__(MAXT)
 k_impute(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O, char* arena, uint64_t arena_per_cta,
-         const double* ones, unsigned long long* work, const uint32_t* worklist, const unsigned int* worklist_n) {
+         const double* ones, unsigned long long* work, const uint32_t* buckets, const unsigned int* bucket_n,
+         uint64_t stride) {
   __shared__ Shared sh;
   Subject S;
   S.g.tid = threadIdx.x;
@@ -666,14 +696,18 @@ k_impute(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArr
   S.ones = ones;
   S.ar_base = arena + (uint64_t)blockIdx.x * arena_per_cta;
   S.ar_cap = arena_per_cta;
-  const uint64_t n_work = worklist ? (uint64_t)*worklist_n : (uint64_t)B.n_subjects;
+  uint64_t bound[GRIMB_BUCKETS + 1];
+  bound[0] = 0;
+  for (int k = 0; k < GRIMB_BUCKETS; ++k) bound[k + 1] = bound[k] + bucket_n[k];
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) sh.work = (uint32_t)atomicAdd(work, 1ull);
     __syncthreads();
     const uint64_t w = sh.work;
-    if (w >= n_work) break;
-    run_subject(S, B, O, worklist ? (uint64_t)worklist[w] : w);
+    if (w >= bound[GRIMB_BUCKETS]) break;
+    int k = 0;
+    while (w >= bound[k + 1]) ++k;
+    run_subject(S, B, O, (uint64_t)buckets[(uint64_t)k * stride + (w - bound[k])]);
   }
 }
 
@@ -1038,6 +1072,7 @@ struct GrimbEngine {
   // staging for the host-pointer form (grow-only)
   DevBuf in[6], outb[3];
   DevBuf worklist;   // subjects the fast kernel hands to the general kernel
+  DevBuf buckets;    // the general kernel's work, by cost bucket (heaviest first)
   int sm_count = 0;
   int fast_path = 1; // GRIMB_FAST=0 disables the warp-per-subject kernel (debugging / A-B runs)
 };
@@ -1071,7 +1106,7 @@ extern "C" int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes
   CK(cudaMalloc((void**)&e->ones, one.size() * 8));
   CK(cudaMemcpy(e->ones, one.data(), one.size() * 8, cudaMemcpyHostToDevice));
   CK(cudaMalloc((void**)&e->d_cfg, sizeof(GrimbConfig)));
-  CK(cudaMalloc((void**)&e->d_counters, 32));
+  CK(cudaMalloc((void**)&e->d_counters, 64));
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   e->sm_count = prop.multiProcessorCount;
   const char* fp = getenv("GRIMB_FAST");
@@ -1119,7 +1154,7 @@ extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const
   CK(cudaSetDevice(e->device));
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
   CK(cudaMemcpyAsync(e->d_cfg, cfg, sizeof(GrimbConfig), cudaMemcpyHostToDevice, st));
-  CK(cudaMemsetAsync(e->d_counters, 0, 32, st));
+  CK(cudaMemsetAsync(e->d_counters, 0, 64, st));
   OutArrays O;
   O.r = *res;
   O.hap_counter = e->d_counters + 1;
@@ -1128,6 +1163,9 @@ extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const
     const TablesView& tv = e->tables->view;
     const uint32_t* wl = nullptr;
     const unsigned int* wl_n = nullptr;
+    const uint64_t stride = (uint64_t)batch->n_subjects;
+    CK(e->buckets.reserve((size_t)stride * 4 * GRIMB_BUCKETS + 16));
+    unsigned int* bucket_n = (unsigned int*)(e->d_counters + 4);
     if (e->fast_path && tv.L <= 5 && tv.P == 1) {
       // warp-per-subject kernel first; what it cannot finish goes through the general kernel
       CK(e->worklist.reserve((size_t)batch->n_subjects * 4 + 16));
@@ -1141,10 +1179,17 @@ extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const
       wl = (const uint32_t*)e->worklist.p;
       wl_n = cnt;
     }
+    {
+      uint64_t cg = (stride + 255) / 256;
+      if (cg > (uint64_t)e->sm_count * 4) cg = (uint64_t)e->sm_count * 4;
+      k_classify<<<(unsigned)cg, 256, 0, st>>>(*batch, tv.L, wl, wl_n, (uint32_t*)e->buckets.p, bucket_n, stride);
+      CK(cudaGetLastError());
+      e->launches += 1;
+    }
     int grid = e->n_ctas;
     if ((int64_t)grid > batch->n_subjects) grid = (int)batch->n_subjects;
-    k_impute<<<grid, e->threads, 0, st>>>(tv, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones, e->d_counters, wl,
-                                         wl_n);
+    k_impute<<<grid, e->threads, 0, st>>>(tv, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones, e->d_counters,
+                                         (const uint32_t*)e->buckets.p, bucket_n, stride);
     CK(cudaGetLastError());
     e->launches += 1;
   }

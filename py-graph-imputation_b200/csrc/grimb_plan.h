@@ -7,6 +7,8 @@
 namespace grimb {
 
 
+constexpr uint32_t SEL_IPT = 8;  // items per thread between two selector barriers in the streaming loops
+
 struct BlockList {
   const uint32_t* ids;  // nullptr: implicit node-id range
   uint32_t first;
@@ -417,9 +419,10 @@ struct Subject : Ctx {
         return;
       }
       const uint64_t items = ntot * P;
-      for (uint64_t q0 = 0; q0 < items; q0 += g.n) {
-        sel_reserve();
-        uint64_t q = q0 + g.tid;
+      for (uint64_t q0 = 0; q0 < items; q0 += (uint64_t)g.n * SEL_IPT) {
+        sel_reserve(SEL_IPT);   // one barrier per SEL_IPT items per thread
+        for (uint32_t u = 0; u < SEL_IPT; ++u) {
+        uint64_t q = q0 + (uint64_t)u * g.n + g.tid;
         if (q < items) {
           uint64_t c = q / P;
           uint32_t j = (uint32_t)(q % P);
@@ -438,6 +441,7 @@ struct Subject : Ctx {
             sh->nonempty = 1;
             sel_push(v * M[j * P + j], q, v, hap, j);
           }
+        }
         }
       }
     } else if (ok) {
@@ -800,9 +804,10 @@ struct Subject : Ctx {
       }
     } else if (ul && ucnt) {
       const uint64_t items = sd.ncand * (uint64_t)ucnt;
-      for (uint64_t q0 = 0; q0 < items; q0 += g.n) {
-        sel_reserve();
-        uint64_t q = q0 + g.tid;
+      for (uint64_t q0 = 0; q0 < items; q0 += (uint64_t)g.n * SEL_IPT) {
+        sel_reserve(SEL_IPT);
+        for (uint32_t u2 = 0; u2 < SEL_IPT; ++u2) {
+        uint64_t q = q0 + (uint64_t)u2 * g.n + g.tid;
         if (q < items) {
           uint64_t c = q / ucnt;
           uint32_t u = (uint32_t)(q % ucnt);
@@ -814,6 +819,7 @@ struct Subject : Ctx {
               sel_push(f * M[0], q, f, ckey[c] | T.node_key[ufirst + u], 0);
             }
           }
+        }
         }
       }
     } else if (!ul) {
@@ -1011,8 +1017,8 @@ GD void run_subject(Subject& S, const GrimbBatch& B, const OutArrays& O, uint64_
     S.top = S.alloc<TopItem>((uint64_t)ns * S.K);
     S.top_n = S.alloc<uint32_t>(ns);
     S.slot_ne = S.alloc<uint32_t>(ns);
-    S.capsel = (uint32_t)(2 * S.K + 2 * g.n);
-    if (S.capsel < 1024) S.capsel = 1024;
+    S.capsel = (uint32_t)(2 * S.K + (int)SEL_IPT * g.n + 64);
+    if (S.capsel < 2048) S.capsel = 2048;
     S.sel = S.alloc<SelItem>(S.capsel);
     S.sel2 = S.alloc<SelItem>(S.capsel);
     S.sel_idx = S.alloc<uint32_t>(S.capsel);

@@ -220,10 +220,10 @@ struct Ctx {
     g.sync();
   }
 
-  // call before every batch of at most g.n pushes (uniform)
-  GD void sel_reserve() {
+  // call before every batch of at most g.n * per_thread pushes (uniform)
+  GD void sel_reserve(uint32_t per_thread = 1) {
     g.sync();
-    if (sh->sel_n + (uint32_t)g.n > capsel) sel_compact();
+    if (sh->sel_n + (uint32_t)g.n * per_thread > capsel) sel_compact();
   }
 
   GD void sel_push(double w, uint64_t ord, double f, uint64_t hap, uint32_t pop) {
@@ -331,64 +331,151 @@ struct Ctx {
   }
 
   // ---------------------------------------------------------------- pair evaluation
+  // accept test of calc_haps_pairs (impute.py:458-491) for one (h, k) pair; fills e when accepted
+  GD bool pair_accept(const TopItem& a, const TopItem& b, double eps, int P, Entry& e) const {
+    const double x = eps / a.f;
+    const double m = M[a.pop * P + b.pop];
+    if (!(m > 0)) return false;
+    const double mf = m * b.f;
+    const bool same = a.hap == b.hap;
+    if (!((!same && mf >= x) || (same && mf >= x * 2))) return false;
+    e.h1 = a.hap;
+    e.h2 = b.hap;
+    e.p1 = (uint16_t)a.pop;
+    e.p2 = (uint16_t)b.pop;
+    e.pad = 0;
+    double pr = a.f * b.f * m;
+    if (!same) pr = pr * 2;
+    e.prob = pr;
+    return true;
+  }
+
   // Appends the accepted pairs of every opened phase, in (phase, h, k) order, to ent[].
+  // All pairs of all phases form one index space; every thread owns a contiguous range of it, so
+  // thread order == encounter order and one scan over the per-thread counts places the entries
+  // (pass 1 counts, pass 2 writes): a handful of barriers per evaluation instead of one scan per
+  // chunk of pairs.
   GDN void gen_entries(double eps) {
     const int P = plan_c_single ? 1 : T.P;
     ent_n = 0;
-    for (int p = 0; p < nph; ++p) {
-      if (!slots[2 * p].valid) continue;
-      const uint32_t n1 = top_n[2 * p], n2 = top_n[2 * p + 1];
-      if (n1 == 0 || n2 == 0) continue;
-      const TopItem* T1 = top + (uint64_t)(2 * p) * K;
-      const TopItem* T2 = top + (uint64_t)(2 * p + 1) * K;
-      uint64_t evals = 0;
-      for (uint32_t h = g.tid; h < n1; h += g.n) {
-        double x = eps / T1[h].f;
-        uint32_t k = 0;
-        while (k < n2 && T2[k].f >= x) ++k;
-        sh->kbreak[h] = (uint16_t)k;
-        evals += (k < n2) ? k + 1 : n2;
+    const uint64_t mark = ar_used;
+    uint32_t* ph_id = alloc<uint32_t>(nph);
+    uint64_t* ph_off = alloc<uint64_t>(nph + 1);
+    uint32_t* row_off = alloc<uint32_t>(nph + 1);
+    if (ws_fail) return;
+    g.sync();
+    if (g.tid == 0) {
+      uint32_t np = 0, roff = 0;
+      uint64_t off = 0;
+      for (int p = 0; p < nph; ++p) {
+        if (!slots[2 * p].valid) continue;
+        const uint32_t n1 = top_n[2 * p], n2 = top_n[2 * p + 1];
+        if (n1 == 0 || n2 == 0) continue;
+        ph_id[np] = (uint32_t)p;
+        ph_off[np] = off;
+        row_off[np] = roff;
+        off += (uint64_t)n1 * n2;
+        roff += n1;
+        ++np;
       }
-      pair_evals += evals;  // per-thread partial; reduced at the end of the subject
-      g.sync();
-      const uint64_t npairs = (uint64_t)n1 * n2;
-      for (uint64_t q0 = 0; q0 < npairs; q0 += g.n) {
-        uint64_t q = q0 + g.tid;
-        bool acc = false;
-        Entry e;
-        if (q < npairs) {
-          uint32_t h = (uint32_t)(q / n2), k = (uint32_t)(q % n2);
-          if (k < sh->kbreak[h]) {
-            const TopItem a = T1[h], b = T2[k];
-            double x = eps / a.f;
-            double m = M[a.pop * P + b.pop];
-            if (m > 0) {
-              double mf = m * b.f;
-              bool same = a.hap == b.hap;
-              if ((!same && mf >= x) || (same && mf >= x * 2)) {
-                acc = true;
-                e.h1 = a.hap;
-                e.h2 = b.hap;
-                e.p1 = (uint16_t)a.pop;
-                e.p2 = (uint16_t)b.pop;
-                e.pad = 0;
-                double pr = a.f * b.f * m;
-                if (!same) pr = pr * 2;
-                e.prob = pr;
+      ph_off[np] = off;
+      row_off[np] = roff;
+      sh->cnt[0] = np;
+    }
+    g.sync();
+    const uint32_t np = sh->cnt[0];
+    if (np == 0) {
+      ar_used = mark;
+      return;
+    }
+    const uint64_t total_pairs = ph_off[np];
+    const uint32_t total_rows = row_off[np];
+    uint16_t* kb = alloc<uint16_t>(total_rows);
+    if (ws_fail) return;
+    // the `break` of the k loop: first k with f2 < eps / f1 (impute.py:464,545-546)
+    uint64_t evals = 0;
+    for (uint32_t r = g.tid; r < total_rows; r += g.n) {
+      uint32_t lo = 0, hi = np - 1;
+      while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (row_off[mid] <= r) lo = mid; else hi = mid - 1;
+      }
+      const uint32_t p = ph_id[lo], h = r - row_off[lo];
+      const uint32_t n2 = top_n[2 * p + 1];
+      const TopItem* T2 = top + (uint64_t)(2 * p + 1) * K;
+      const double x = eps / top[(uint64_t)(2 * p) * K + h].f;
+      uint32_t k = 0;
+      while (k < n2 && T2[k].f >= x) ++k;
+      kb[r] = (uint16_t)k;
+      evals += (k < n2) ? k + 1 : n2;
+    }
+    pair_evals += evals;  // per-thread partial; reduced at the end of the subject
+    g.sync();
+    const uint64_t per = (total_pairs + g.n - 1) / g.n;
+    uint64_t q0 = per * g.tid, q1 = q0 + per;
+    if (q0 > total_pairs) q0 = total_pairs;
+    if (q1 > total_pairs) q1 = total_pairs;
+    uint32_t my_cnt = 0, my_off = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      if (q0 < q1) {
+        uint32_t lo = 0, hi = np - 1;
+        while (lo < hi) {
+          uint32_t mid = (lo + hi + 1) >> 1;
+          if (ph_off[mid] <= q0) lo = mid; else hi = mid - 1;
+        }
+        uint32_t j = lo, p = ph_id[j];
+        uint32_t n1 = top_n[2 * p], n2 = top_n[2 * p + 1];
+        const TopItem* T1 = top + (uint64_t)(2 * p) * K;
+        const TopItem* T2 = top + (uint64_t)(2 * p + 1) * K;
+        uint64_t rem = q0 - ph_off[j];
+        uint32_t h = (uint32_t)(rem / n2), k = (uint32_t)(rem % n2);
+        uint32_t w = my_off;
+        uint64_t q = q0;
+        while (q < q1) {
+          const uint32_t kbreak = kb[row_off[j] + h];
+          if (k < kbreak) {
+            Entry e;
+            if (pair_accept(T1[h], T2[k], eps, P, e)) {
+              if (pass == 0) ++my_cnt;
+              else {
+                if (w < ent_cap) ent[w] = e;
+                ++w;
+              }
+            }
+            ++q;
+            ++k;
+          } else {
+            const uint64_t skip = (uint64_t)(n2 - k);  // the rest of this h row is past the break
+            q += skip;
+            k = n2;
+          }
+          if (k >= n2) {
+            k = 0;
+            if (++h >= n1) {
+              h = 0;
+              if (++j < np) {
+                p = ph_id[j];
+                n1 = top_n[2 * p];
+                n2 = top_n[2 * p + 1];
+                T1 = top + (uint64_t)(2 * p) * K;
+                T2 = top + (uint64_t)(2 * p + 1) * K;
+              } else {
+                break;
               }
             }
           }
         }
-        uint32_t total;
-        uint32_t pos = g.scan_excl(acc ? 1u : 0u, total);
-        if (acc) {
-          if (ent_n + pos < ent_cap) ent[ent_n + pos] = e;
-        }
-        ent_n += total;
       }
-      g.sync();
+      if (pass == 0) {
+        uint32_t total;
+        my_off = g.scan_excl(my_cnt, total);
+        ent_n = total;
+        if (total == 0) break;
+      }
     }
+    g.sync();
     if (ent_n > ent_cap) ws_fail = true;
+    ar_used = mark;
   }
 
   // geno_seen (impute.py:508-513): keep the first entry of every unordered {(hap,pop),(hap,pop)}.
@@ -486,16 +573,23 @@ struct Ctx {
   // groups by (sum desc, first encounter asc) and writes the best `limit` rows.  Returns the
   // number of groups; *n_rows = rows written.  Rows: kind 0 -> (lo,hi); kind 1 -> (h1,h2) of
   // the first member; kind 2 -> pops of the first member (orientation as encountered).
+  //
+  // No sort of the entries: a hash table (atomicMin on the entry index) names each group by its
+  // first member; groups are numbered in first-encounter order by a scan over the heads; then
+  // every thread walks ALL entries in encounter order and adds those whose group it owns
+  // (group id mod #threads), so each group's += chain runs in the reference's order without
+  // ordering anything.  Top-N is a repeated block arg-max when N is small, a bitonic sort of the
+  // group list otherwise.
   GDN uint32_t aggregate(int kind, uint32_t limit, GrimbHapRow* hap_rows, GrimbPopRow* pop_rows, uint32_t* n_rows) {
     if (g.tid == 0) *n_rows = 0;
     if (ent_n == 0 || ws_fail) return 0;
     uint64_t mark = ar_used;
     uint32_t tsz = 2;
     while (tsz < 2 * ent_n) tsz <<= 1;
-    uint32_t* tab = alloc<uint32_t>(tsz);
-    uint32_t* where = alloc<uint32_t>(ent_n);
-    uint64_t* srt = alloc<uint64_t>(ent_n);
-    uint32_t* ghead = alloc<uint32_t>(ent_n);   // position in srt of each group's head
+    uint32_t* tab = alloc<uint32_t>(tsz);        // slot -> first member (entry index)
+    uint32_t* slot_gid = alloc<uint32_t>(tsz);   // slot -> group id
+    uint32_t* where = alloc<uint32_t>(ent_n);    // entry -> slot, later entry -> group id
+    uint32_t* ghead = alloc<uint32_t>(ent_n);    // group -> first member
     double* gsum = alloc<double>(ent_n);
     uint32_t* gord = alloc<uint32_t>(ent_n);
     if (ws_fail) return 0;
@@ -523,56 +617,88 @@ struct Ctx {
       where[i] = h;
     }
     g.sync();
-    for (uint32_t i = g.tid; i < ent_n; i += g.n) srt[i] = ((uint64_t)tab[where[i]] << 32) | i;
-    g.sync();
-    {
-      uint64_t* s = srt;
-      group_sort(
-          g, ent_n, [=](uint32_t a, uint32_t b) { return s[a] < s[b]; },
-          [=](uint32_t a, uint32_t b) {
-            uint64_t t = s[a];
-            s[a] = s[b];
-            s[b] = t;
-          });
-    }
-    // group heads, in first-encounter order
+    // heads in encounter order -> group ids
     uint32_t ng = 0;
     for (uint32_t i0 = 0; i0 < ent_n; i0 += g.n) {
       uint32_t i = i0 + g.tid;
-      bool head = i < ent_n && (i == 0 || (srt[i] >> 32) != (srt[i - 1] >> 32));
+      bool head = i < ent_n && tab[where[i]] == i;
       uint32_t total;
       uint32_t pos = g.scan_excl(head ? 1u : 0u, total);
-      if (head) ghead[ng + pos] = i;
+      if (head) {
+        ghead[ng + pos] = i;
+        slot_gid[where[i]] = ng + pos;
+        gsum[ng + pos] = E[i].prob;
+        gord[ng + pos] = ng + pos;
+      }
       ng += total;
     }
     g.sync();
-    for (uint32_t gi = g.tid; gi < ng; gi += g.n) {
-      uint32_t b0 = ghead[gi], b1 = (gi + 1 < ng) ? ghead[gi + 1] : ent_n;
-      double s = E[(uint32_t)srt[b0]].prob;
-      for (uint32_t q = b0 + 1; q < b1; ++q) s = s + E[(uint32_t)srt[q]].prob;  // += in encounter order
-      gsum[gi] = s;
-      gord[gi] = gi;
-    }
+    for (uint32_t i = g.tid; i < ent_n; i += g.n) where[i] = slot_gid[where[i]];
     g.sync();
-    {
-      const double* gs = gsum;
-      uint32_t* go = gord;
-      group_sort(
-          g, ng,
-          [=](uint32_t a, uint32_t b) {
-            double x = gs[go[a]], y = gs[go[b]];
-            return x > y || (x == y && go[a] < go[b]);
-          },
-          [=](uint32_t a, uint32_t b) {
-            uint32_t t = go[a];
-            go[a] = go[b];
-            go[b] = t;
-          });
+    if (ng < ent_n) {
+      // += in encounter order: thread t owns the groups with (id & tmask) == t
+      uint32_t tpow = 1;
+      while (tpow * 2 <= (uint32_t)g.n) tpow <<= 1;
+      if ((uint32_t)g.tid < tpow) {
+        const uint32_t tmask = tpow - 1, me = (uint32_t)g.tid;
+        for (uint32_t i = 0; i < ent_n; ++i) {
+          const uint32_t gi = where[i];
+          if ((gi & tmask) == me && ghead[gi] != i) gsum[gi] = gsum[gi] + E[i].prob;
+        }
+      }
+      g.sync();
     }
     uint32_t rows = ng < limit ? ng : limit;
+    if (rows <= 64 && ng > 1024) {
+      // repeated arg-max over (sum desc, group id asc); taken groups are marked in gord
+      for (uint32_t r = 0; r < rows; ++r) {
+        double best = -1.0;
+        uint32_t bi = GRIMB_NONE;
+        for (uint32_t gi = g.tid; gi < ng; gi += g.n)
+          if (gord[gi] != GRIMB_NONE) {
+            const double v = gsum[gi];
+            if (v > best) {   // strided scan visits ids in ascending order: first maximum wins
+              best = v;
+              bi = gi;
+            }
+          }
+        const double top = g.maxd(best);
+        uint32_t cand = (bi != GRIMB_NONE && best == top) ? bi : GRIMB_NONE;
+        // smallest group id among the threads holding the maximum
+        g.sync();
+        if (g.tid == 0) sh->cnt[0] = GRIMB_NONE;
+        g.sync();
+        if (cand != GRIMB_NONE) atom_min(&sh->cnt[0], cand);
+        g.sync();
+        const uint32_t win = sh->cnt[0];
+        g.sync();
+        if (g.tid == 0) {
+          gord[win] = GRIMB_NONE;
+          slot_gid[r] = win;     // slot_gid is free now: reuse as the ranked list
+        }
+      }
+      g.sync();
+    } else {
+      const double* gs = gsum;
+      uint32_t* go = gord;
+      if (ng > rows || ng > 1)
+        group_sort(
+            g, ng,
+            [=](uint32_t a, uint32_t b) {
+              double x = gs[go[a]], y = gs[go[b]];
+              return x > y || (x == y && go[a] < go[b]);
+            },
+            [=](uint32_t a, uint32_t b) {
+              uint32_t t = go[a];
+              go[a] = go[b];
+              go[b] = t;
+            });
+      for (uint32_t r = g.tid; r < rows; r += g.n) slot_gid[r] = gord[r];
+      g.sync();
+    }
     for (uint32_t r = g.tid; r < rows; r += g.n) {
-      uint32_t gi = gord[r];
-      const Entry& e = E[(uint32_t)(srt[ghead[gi]])];
+      uint32_t gi = slot_gid[r];
+      const Entry& e = E[ghead[gi]];
       if (kind == 2) {
         GrimbPopRow o;
         o.pop_a = e.p1;

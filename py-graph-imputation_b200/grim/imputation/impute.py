@@ -91,7 +91,7 @@ class Imputation(object):
         self.locus_index = {n: i for i, n in enumerate(self.loci)}
         self.batch_size = int(os.environ.get("GRIMB_BATCH", "65536"))
         self.workspaces = [int(x) for x in os.environ.get(
-            "GRIMB_WORKSPACES", "%d,%d,%d" % (8 << 20, 128 << 20, 2 << 30)).split(",")]
+            "GRIMB_WORKSPACES", "%d,%d,%d" % (32 << 20, 512 << 20, 4 << 30)).split(",")]
         self._prior_index = {}
         self._priors = []
         self._backend = self._run_gpu
