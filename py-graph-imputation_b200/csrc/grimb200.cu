@@ -1075,6 +1075,8 @@ struct GrimbEngine {
   DevBuf buckets;    // the general kernel's work, by cost bucket (heaviest first)
   int sm_count = 0;
   int fast_path = 1; // GRIMB_FAST=0 disables the warp-per-subject kernel (debugging / A-B runs)
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // [0,1] around k_impute_fast, [2,3] around k_impute
+  int ev_valid[2] = {0, 0};
 };
 
 extern "C" int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes_per_cta, GrimbEngine** out) {
@@ -1108,6 +1110,7 @@ extern "C" int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes
   CK(cudaMalloc((void**)&e->d_cfg, sizeof(GrimbConfig)));
   CK(cudaMalloc((void**)&e->d_counters, 64));
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&e->ev[i]));
   e->sm_count = prop.multiProcessorCount;
   const char* fp = getenv("GRIMB_FAST");
   if (fp && fp[0] == '0') e->fast_path = 0;
@@ -1133,6 +1136,18 @@ extern "C" int grimb_engine_free(GrimbEngine* e) {
 }
 
 extern "C" int64_t grimb_engine_launches(const GrimbEngine* e) { return e ? e->launches : 0; }
+
+// Device time (CUDA events on the launching stream) of the last launch of k_impute_fast (which = 0)
+// or k_impute (which = 1); valid after the call that launched it has returned.  < 0 if not launched.
+extern "C" double grimb_engine_kernel_ms(const GrimbEngine* e, int which) {
+  if (!e || which < 0 || which > 1 || !e->ev_valid[which]) return -1.0;
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, e->ev[2 * which], e->ev[2 * which + 1]) != cudaSuccess) {
+    cudaGetLastError();
+    return -1.0;
+  }
+  return (double)ms;
+}
 
 static int check_cfg(const GrimbConfig* c, const GrimbTables* t) {
   if (!(c->epsilon > 0)) return fail(GRIMB_E_ARG, "epsilon must be > 0");
@@ -1173,8 +1188,11 @@ extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const
       const uint64_t groups = ((uint64_t)batch->n_subjects + FAST_WARPS * 2 - 1) / (FAST_WARPS * 2);
       uint64_t fg = (uint64_t)e->sm_count * FAST_MIN_BLOCKS;  // resident CTAs only: each warp strides over subjects
       if (fg > groups) fg = groups;
+      CK(cudaEventRecord(e->ev[0], st));
       k_impute_fast<<<(unsigned)fg, FAST_WARPS * 32, 0, st>>>(tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt);
       CK(cudaGetLastError());
+      CK(cudaEventRecord(e->ev[1], st));
+      e->ev_valid[0] = 1;
       e->launches += 1;
       wl = (const uint32_t*)e->worklist.p;
       wl_n = cnt;
@@ -1188,9 +1206,12 @@ extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const
     }
     int grid = e->n_ctas;
     if ((int64_t)grid > batch->n_subjects) grid = (int)batch->n_subjects;
+    CK(cudaEventRecord(e->ev[2], st));
     k_impute<<<grid, e->threads, 0, st>>>(tv, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones, e->d_counters,
                                          (const uint32_t*)e->buckets.p, bucket_n, stride);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(e->ev[3], st));
+    e->ev_valid[1] = 1;
     e->launches += 1;
   }
   unsigned long long cnt[4];

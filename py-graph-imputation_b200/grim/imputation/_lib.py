@@ -126,6 +126,8 @@ def load():
     lib.grimb_engine_free.argtypes = [C.c_void_p]
     lib.grimb_engine_launches.argtypes = [C.c_void_p]
     lib.grimb_engine_launches.restype = C.c_int64
+    lib.grimb_engine_kernel_ms.argtypes = [C.c_void_p, C.c_int]
+    lib.grimb_engine_kernel_ms.restype = C.c_double
     lib.grimb_impute_device.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Batch), C.POINTER(Results), C.c_void_p]
     lib.grimb_impute_host.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Batch), C.POINTER(Results)]
     lib.grimb_text_create.argtypes = [C.POINTER(TextDesc), C.POINTER(C.c_void_p)]
@@ -149,7 +151,7 @@ def check(rc, what):
 EXPORTED = [
     "grimb_abi_version", "grimb_last_error", "grimb_tables_build", "grimb_tables_free",
     "grimb_tables_info", "grimb_tables_export", "grimb_tables_image_size", "grimb_tables_image_ptr",
-    "grimb_tables_image_copy", "grimb_tables_from_image", "grimb_engine_create", "grimb_engine_free", "grimb_engine_launches",
+    "grimb_tables_image_copy", "grimb_tables_from_image", "grimb_engine_create", "grimb_engine_free", "grimb_engine_launches", "grimb_engine_kernel_ms",
     "grimb_impute_device", "grimb_impute_host",
     "grimb_text_create", "grimb_text_free", "grimb_text_tokenise", "grimb_text_format", "grimb_impute_text",
 ]
