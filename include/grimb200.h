@@ -148,7 +148,14 @@ typedef struct {
 /* Result rows.  A hap row is two packed keys + probability: for UMUG the per-locus (min id,
  * max id) pair of the genotype (impute.py:497-504; the host orders each pair as strings), for
  * PMUG the two haplotypes in first-seen orientation (impute.py:28-38,651). */
+#ifndef GRIMB_KEY_WORDS
+#define GRIMB_KEY_WORDS 1   /* 1: libgrimb200.so (packed key <= 63 bits); 2: libgrimb200w.so (<= 127 bits) */
+#endif
+#if GRIMB_KEY_WORDS == 1
 typedef struct { uint64_t a, b; double prob; } GrimbHapRow;
+#else
+typedef struct { uint64_t a[2], b[2]; double prob; } GrimbHapRow; /* little-endian words: [0] = low 64 bits */
+#endif
 typedef struct { uint16_t pop_a, pop_b; uint32_t pad; double prob; } GrimbPopRow;
 
 /* One record per subject (48 bytes, 16-byte aligned: written with three 128-bit stores). */

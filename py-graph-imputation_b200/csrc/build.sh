@@ -1,9 +1,14 @@
 #!/bin/sh
-# Builds libgrimb200.so for sm_100a, in-tree (the .so travels to the GPU box with the snapshot).
+# Builds the C-ABI libraries for sm_100a, in-tree (the .so files travel to the GPU box with the snapshot).
 #   grimb200.cu    CUDA kernels + C ABI (FP64 operation order: -fmad=false)
 #   grimb_text.cpp host text pipeline (no FP contraction either: prior matrices must be bit-exact)
+# libgrimb200.so : 64-bit packed haplotype keys (<= 63 key bits: every 5/6-locus table, small 9-locus ones)
+# libgrimb200w.so: 128-bit packed keys (wide 9-locus tables); same ABI with GRIMB_KEY_WORDS = 2
 set -e
 cd "$(dirname "$0")"
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false \
-     --extended-lambda -Xcompiler -fPIC,-ffp-contract=off,-pthread -shared \
-     -o libgrimb200.so grimb200.cu grimb_text.cpp "$@"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false --extended-lambda \
+ -Xcompiler -fPIC,-ffp-contract=off,-pthread -shared"
+nvcc $FLAGS -DGRIMB_KW=1 -DGRIMB_KEY_WORDS=1 -o libgrimb200.so grimb200.cu grimb_text.cpp "$@" &
+nvcc $FLAGS -DGRIMB_KW=2 -DGRIMB_KEY_WORDS=2 -o libgrimb200w.so grimb200.cu grimb_text.cpp "$@" &
+wait
+test -f libgrimb200.so && test -f libgrimb200w.so

@@ -58,7 +58,7 @@ struct ImageHeader {
   uint64_t o_label_first, o_label_count, o_ht_off, o_ht_mask, o_slots, o_node_key, o_freq, o_tl_start,
       o_tl_cnt, o_tl_adj, o_cn_start, o_cn_cnt, o_cn_adj;
 };
-static const uint64_t IMAGE_MAGIC = 0x4752494d42323030ULL;  // "GRIMB200"
+static const uint64_t IMAGE_MAGIC = 0x4752494d42323030ULL + (GRIMB_KW - 1);  // "GRIMB200" (+1: 128-bit keys)
 
 struct GrimbTables {
   int device;
@@ -83,7 +83,7 @@ static void make_view(GrimbTables* t) {
   v.ht_off = (const uint64_t*)(b + h.o_ht_off);
   v.ht_mask = (const uint32_t*)(b + h.o_ht_mask);
   v.slots = (const HSlot*)(b + h.o_slots);
-  v.node_key = (const uint64_t*)(b + h.o_node_key);
+  v.node_key = (const hkey*)(b + h.o_node_key);
   v.freq = (const double*)(b + h.o_freq);
   v.tl_start = (const uint32_t*)(b + h.o_tl_start);
   v.tl_cnt = (const uint32_t*)(b + h.o_tl_cnt);
@@ -96,22 +96,22 @@ static void make_view(GrimbTables* t) {
 // ------------------------------------------------------------------------------------------
 // K0: table build kernels
 // ------------------------------------------------------------------------------------------
-__global__ void k_pack_full(const uint16_t* al, int L, const uint8_t* shift, uint64_t n, uint64_t* keys) {
+__global__ void k_pack_full(const uint16_t* al, int L, const uint8_t* shift, uint64_t n, hkey* keys) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint64_t k = 0;
-  for (int l = 0; l < L; ++l) k |= (uint64_t)al[i * L + l] << shift[l];
+  hkey k = 0;
+  for (int l = 0; l < L; ++l) k |= (hkey)al[i * L + l] << shift[l];
   keys[i] = k;
 }
 
-__global__ void k_project(const uint64_t* keys, uint64_t mask, uint32_t base, uint32_t n, uint64_t* out, uint32_t* idx) {
+__global__ void k_project(const hkey* keys, hkey mask, uint32_t base, uint32_t n, hkey* out, uint32_t* idx) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   out[i] = keys[i] & mask;
   idx[i] = base + i;
 }
 
-__global__ void k_heads(const uint64_t* sorted, uint32_t n, uint32_t* flag) {
+__global__ void k_heads(const hkey* sorted, uint32_t n, uint32_t* flag) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   flag[i] = (i == 0 || sorted[i] != sorted[i - 1]) ? 1u : 0u;
@@ -132,8 +132,8 @@ __global__ void k_seg_heads(const uint32_t* flag, const uint32_t* seg_of, const 
 // node r of the label (r = rank of the segment by first appearance): key, top-link range and the
 // SEQUENTIAL sum of the members' frequency vectors in hpf order (generate_neo4j_multi_hpf.py:405)
 __global__ void k_label_nodes(const uint32_t* seg_by_rank, const uint32_t* head_pos, uint32_t nseg, uint32_t n,
-                              const uint64_t* sorted_keys, const uint32_t* sorted_idx, const double* full_freq, int P,
-                              uint32_t node_base, uint32_t tl_base, uint64_t* node_key, double* freq,
+                              const hkey* sorted_keys, const uint32_t* sorted_idx, const double* full_freq, int P,
+                              uint32_t node_base, uint32_t tl_base, hkey* node_key, double* freq,
                               uint32_t* tl_start, uint32_t* tl_cnt) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nseg * (uint32_t)P) return;
@@ -151,7 +151,7 @@ __global__ void k_label_nodes(const uint32_t* seg_by_rank, const uint32_t* head_
   }
 }
 
-__global__ void k_full_nodes(const uint64_t* keys, const double* full_freq, uint32_t n, int P, uint64_t* node_key,
+__global__ void k_full_nodes(const hkey* keys, const double* full_freq, uint32_t n, int P, hkey* node_key,
                              double* freq, uint32_t* tl_start, uint32_t* tl_cnt) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -164,22 +164,26 @@ __global__ void k_full_nodes(const uint64_t* keys, const double* full_freq, uint
 __global__ void k_init_slots(HSlot* s, uint64_t n) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  s[i].key = ~0ull;
-  s[i].node = GRIMB_NONE;
-  s[i].pad = 0;
+  HSlot e;
+  memset(&e, 0, sizeof(e));
+  e.key = ~(hkey)0;
+  e.node = GRIMB_NONE;
+  s[i] = e;
 }
 
-__global__ void k_insert(HSlot* slots, uint64_t off, uint32_t mask, const uint64_t* node_key, uint32_t first, uint32_t cnt) {
+// All keys of a region are distinct, so an insert only has to claim an empty slot (CAS on the node
+// field); lookups run in later launches.
+__global__ void k_insert(HSlot* slots, uint64_t off, uint32_t mask, const hkey* node_key, uint32_t first, uint32_t cnt) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cnt) return;
   uint32_t node = first + i;
-  uint64_t key = node_key[node];
+  hkey key = node_key[node];
   HSlot* base = slots + off;
   uint32_t h = ht_home(key, mask);
   for (;;) {
-    unsigned long long old = atomicCAS((unsigned long long*)&base[h].key, ~0ull, (unsigned long long)key);
-    if (old == ~0ull) {
-      base[h].node = node;
+    unsigned int old = atomicCAS(&base[h].node, GRIMB_NONE, node);
+    if (old == GRIMB_NONE) {
+      base[h].key = key;
       return;
     }
     h = (h + 1) & mask;
@@ -187,7 +191,7 @@ __global__ void k_insert(HSlot* slots, uint64_t off, uint32_t mask, const uint64
 }
 
 // connector segments: child key -> (child node, added locus) CSR entry
-__global__ void k_conn_heads(const uint32_t* flag, const uint64_t* sorted_child, uint32_t n, TablesView T, uint32_t child_label,
+__global__ void k_conn_heads(const uint32_t* flag, const hkey* sorted_child, uint32_t n, TablesView T, uint32_t child_label,
                              int locus, uint32_t cn_base, uint32_t* cn_start, uint32_t* cn_cnt, const uint32_t* next_head,
                              unsigned int* n_conn) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -255,12 +259,75 @@ static std::vector<uint32_t> label_order(int L) {
   return out;
 }
 
-static uint64_t host_key_mask(const ImageHeader& h, uint32_t label) {
-  uint64_t m = 0;
+static hkey host_key_mask(const ImageHeader& h, uint32_t label) {
+  hkey m = 0;
   for (int l = 0; l < h.L; ++l)
-    if (label >> l & 1u) m |= ((1ull << h.width[l]) - 1ull) << h.shift[l];
+    if (label >> l & 1u) m |= (hkey)((1ull << h.width[l]) - 1ull) << h.shift[l];
   return m;
 }
+
+// Stable sort of (key, idx) pairs by the low `bits` bits of the key.  64-bit keys: one CUB radix
+// sort.  128-bit keys: two stable LSD passes (low word, then high word) over a position
+// permutation, then one gather.
+#if GRIMB_KW == 2
+__global__ void k_key_word(const hkey* keys, const uint32_t* pos, int word, uint32_t n, uint64_t* out, uint32_t* iota) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const hkey k = keys[pos ? pos[i] : i];
+  out[i] = word ? (uint64_t)(k >> 64) : (uint64_t)k;
+  if (iota) iota[i] = i;
+}
+__global__ void k_gather_pairs(const hkey* kin, const uint32_t* iin, const uint32_t* pos, uint32_t n, hkey* kout, uint32_t* iout) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  kout[i] = kin[pos[i]];
+  iout[i] = iin[pos[i]];
+}
+#endif
+struct SortScratch {
+  DevBuf tmp, w0, w1, p0, p1, p2;
+  cudaError_t reserve(uint32_t n) {
+    size_t tb1 = 0, tb2 = 0, tb3 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb1, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
+    cub::DeviceRadixSort::SortPairs(nullptr, tb2, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb3, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
+    size_t tb = tb1 > tb2 ? tb1 : tb2;
+    tb = tb > tb3 ? tb : tb3;
+    cudaError_t e = tmp.reserve(tb + 16);
+#if GRIMB_KW == 2
+    if (e == cudaSuccess) e = w0.reserve((size_t)n * 8);
+    if (e == cudaSuccess) e = w1.reserve((size_t)n * 8);
+    if (e == cudaSuccess) e = p0.reserve((size_t)n * 4);
+    if (e == cudaSuccess) e = p1.reserve((size_t)n * 4);
+    if (e == cudaSuccess) e = p2.reserve((size_t)n * 4);
+#endif
+    return e;
+  }
+  cudaError_t sort(const hkey* kin, hkey* kout, const uint32_t* iin, uint32_t* iout, uint32_t n, int bits) {
+    size_t tbx = tmp.cap;
+#if GRIMB_KW == 1
+    return cub::DeviceRadixSort::SortPairs(tmp.p, tbx, kin, kout, iin, iout, (int)n, 0, bits);
+#else
+    if (n == 0) return cudaSuccess;
+    const unsigned g = (n + 255) / 256;
+    k_key_word<<<g, 256>>>(kin, nullptr, 0, n, (uint64_t*)w0.p, (uint32_t*)p0.p);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp.p, tbx, (uint64_t*)w0.p, (uint64_t*)w1.p, (uint32_t*)p0.p,
+                                                    (uint32_t*)p1.p, (int)n, 0, bits < 64 ? bits : 64);
+    if (e != cudaSuccess) return e;
+    const uint32_t* pos = (const uint32_t*)p1.p;
+    if (bits > 64) {
+      k_key_word<<<g, 256>>>(kin, (const uint32_t*)p1.p, 1, n, (uint64_t*)w0.p, nullptr);
+      tbx = tmp.cap;
+      e = cub::DeviceRadixSort::SortPairs(tmp.p, tbx, (uint64_t*)w0.p, (uint64_t*)w1.p, (uint32_t*)p1.p, (uint32_t*)p2.p,
+                                          (int)n, 0, bits - 64);
+      if (e != cudaSuccess) return e;
+      pos = (const uint32_t*)p2.p;
+    }
+    k_gather_pairs<<<g, 256>>>(kin, iin, pos, n, kout, iout);
+    return cudaGetLastError();
+#endif
+  }
+};
 
 // reference quirk: the closing CSR sentinel is len(Vertices) (networkx_graph.py:195-196)
 static uint32_t sentinel_count(uint64_t own, uint64_t n_edges, uint64_t n_vertices) {
@@ -281,7 +348,9 @@ extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
     if ((1ll << d->key_bits[l]) <= d->n_alleles[l]) return fail(GRIMB_E_LAYOUT, "allele ids do not fit key_bits");
     bits += d->key_bits[l];
   }
-  if (bits > 63) return fail(GRIMB_E_LAYOUT, "packed key exceeds 63 bits");
+  if (bits > 64 * GRIMB_KW - 1)
+    return fail(GRIMB_E_LAYOUT, GRIMB_KW == 1 ? "packed key exceeds 63 bits (use libgrimb200w.so: 128-bit keys)"
+                                              : "packed key exceeds 127 bits");
   CK(cudaSetDevice(d->device));
   const uint32_t N = (uint32_t)d->n_full;
   const uint32_t NL = 1u << L;
@@ -316,19 +385,19 @@ extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
   } while (0)
   CKB(b_al.reserve((size_t)N * L * 2));
   CKB(b_ff.reserve((size_t)N * P * 8));
-  CKB(b_keys.reserve((size_t)N * 8));
+  CKB(b_keys.reserve((size_t)N * sizeof(hkey)));
   CKB(b_shift.reserve(16));
   CKB(cudaMemcpy(b_al.p, d->full_alleles, (size_t)N * L * 2, cudaMemcpyHostToDevice));
   CKB(cudaMemcpy(b_ff.p, d->full_freqs, (size_t)N * P * 8, cudaMemcpyHostToDevice));
   CKB(cudaMemcpy(b_shift.p, h.shift, 9, cudaMemcpyHostToDevice));
-  if (N) k_pack_full<<<nblk(N), 256>>>((const uint16_t*)b_al.p, L, (const uint8_t*)b_shift.p, N, (uint64_t*)b_keys.p);
+  if (N) k_pack_full<<<nblk(N), 256>>>((const uint16_t*)b_al.p, L, (const uint8_t*)b_shift.p, N, (hkey*)b_keys.p);
   CKB(cudaGetLastError());
 
   // ---- pass 1 over labels: sort projections, count nodes, keep per-label results
   const std::vector<uint32_t> order = label_order(L);
   struct PerLabel {
     uint32_t nseg = 0;
-    uint64_t* keys = nullptr;   // [nseg] node keys in node order
+    hkey* keys = nullptr;       // [nseg] node keys in node order
     double* freq = nullptr;     // [nseg][P]
     uint32_t* tls = nullptr;    // [nseg] top-link start relative to the label's block
     uint32_t* tlc = nullptr;    // [nseg]
@@ -344,10 +413,12 @@ extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
       cudaFree(x.adj);
     }
   };
-  DevBuf b_pk, b_pi, b_sk, b_si, b_flag, b_seg, b_head, b_rank, b_iota, b_rank2, b_iota2, b_tmp, b_tmp2;
-  CKB(b_pk.reserve((size_t)N * 8));
+  DevBuf b_pk, b_pi, b_sk, b_si, b_flag, b_seg, b_head, b_rank, b_iota, b_rank2, b_iota2;
+  SortScratch ss;
+  DevBuf& b_tmp = ss.tmp;
+  CKB(b_pk.reserve((size_t)N * sizeof(hkey)));
   CKB(b_pi.reserve((size_t)N * 4));
-  CKB(b_sk.reserve((size_t)N * 8));
+  CKB(b_sk.reserve((size_t)N * sizeof(hkey)));
   CKB(b_si.reserve((size_t)N * 4));
   CKB(b_flag.reserve((size_t)N * 4));
   CKB(b_seg.reserve((size_t)N * 4));
@@ -356,23 +427,15 @@ extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
   CKB(b_iota.reserve((size_t)N * 4));
   CKB(b_rank2.reserve((size_t)N * 4));
   CKB(b_iota2.reserve((size_t)N * 4));
-  size_t tb1 = 0, tb2 = 0, tb3 = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tb1, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)N);
-  cub::DeviceRadixSort::SortPairs(nullptr, tb2, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)N);
-  cub::DeviceScan::ExclusiveSum(nullptr, tb3, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)N);
-  size_t tb = tb1 > tb2 ? tb1 : tb2;
-  tb = tb > tb3 ? tb : tb3;
-  CKB(b_tmp.reserve(tb + 16));
+  CKB(ss.reserve(N));
 
   uint64_t n_nodes = N;
   for (size_t li = 1; li < order.size() && N > 0; ++li) {
-    const uint64_t km = host_key_mask(h, order[li]);
-    k_project<<<nblk(N), 256>>>((const uint64_t*)b_keys.p, km, 0u, N, (uint64_t*)b_pk.p, (uint32_t*)b_pi.p);
+    const hkey km = host_key_mask(h, order[li]);
+    k_project<<<nblk(N), 256>>>((const hkey*)b_keys.p, km, 0u, N, (hkey*)b_pk.p, (uint32_t*)b_pi.p);
+    CKB(ss.sort((const hkey*)b_pk.p, (hkey*)b_sk.p, (const uint32_t*)b_pi.p, (uint32_t*)b_si.p, N, sh));
+    k_heads<<<nblk(N), 256>>>((const hkey*)b_sk.p, N, (uint32_t*)b_flag.p);
     size_t tbx = b_tmp.cap;
-    CKB(cub::DeviceRadixSort::SortPairs(b_tmp.p, tbx, (uint64_t*)b_pk.p, (uint64_t*)b_sk.p, (uint32_t*)b_pi.p,
-                                        (uint32_t*)b_si.p, (int)N, 0, sh));
-    k_heads<<<nblk(N), 256>>>((const uint64_t*)b_sk.p, N, (uint32_t*)b_flag.p);
-    tbx = b_tmp.cap;
     CKB(cub::DeviceScan::ExclusiveSum(b_tmp.p, tbx, (uint32_t*)b_flag.p, (uint32_t*)b_seg.p, (int)N));
     uint32_t last_flag = 0, last_seg = 0;
     CKB(cudaMemcpy(&last_flag, (uint32_t*)b_flag.p + (N - 1), 4, cudaMemcpyDeviceToHost));
@@ -385,13 +448,13 @@ extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
     tbx = b_tmp.cap;
     CKB(cub::DeviceRadixSort::SortPairs(b_tmp.p, tbx, (uint32_t*)b_rank.p, (uint32_t*)b_rank2.p, (uint32_t*)b_iota.p,
                                         (uint32_t*)b_iota2.p, (int)nseg));
-    CKB(cudaMalloc(&x.keys, (size_t)nseg * 8));
+    CKB(cudaMalloc(&x.keys, (size_t)nseg * sizeof(hkey)));
     CKB(cudaMalloc(&x.freq, (size_t)nseg * P * 8));
     CKB(cudaMalloc(&x.tls, (size_t)nseg * 4));
     CKB(cudaMalloc(&x.tlc, (size_t)nseg * 4));
     CKB(cudaMalloc(&x.adj, (size_t)N * 4));
     k_label_nodes<<<nblk((uint64_t)nseg * P), 256>>>((const uint32_t*)b_iota2.p, (const uint32_t*)b_head.p, nseg, N,
-                                                     (const uint64_t*)b_sk.p, (const uint32_t*)b_si.p,
+                                                     (const hkey*)b_sk.p, (const uint32_t*)b_si.p,
                                                      (const double*)b_ff.p, P, 0u, 0u, x.keys, x.freq, x.tls, x.tlc);
     CKB(cudaMemcpy(x.adj, b_si.p, (size_t)N * 4, cudaMemcpyDeviceToDevice));
     CKB(cudaGetLastError());
@@ -442,7 +505,7 @@ extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
   h.o_ht_off = o; o = al16(o + (uint64_t)NL * 8);
   h.o_ht_mask = o; o = al16(o + (uint64_t)NL * 4);
   h.o_slots = o; o = al16(o + h.n_slots * sizeof(HSlot));
-  h.o_node_key = o; o = al16(o + n_nodes * 8);
+  h.o_node_key = o; o = al16(o + n_nodes * sizeof(hkey));
   h.o_freq = o; o = al16(o + n_nodes * P * 8);
   h.o_tl_start = o; o = al16(o + n_nodes * 4);
   h.o_tl_cnt = o; o = al16(o + n_nodes * 4);
@@ -477,14 +540,14 @@ extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
 
   // ---- assemble node arrays
   if (N)
-    k_full_nodes<<<nblk(N), 256>>>((const uint64_t*)b_keys.p, (const double*)b_ff.p, N, P, (uint64_t*)v.node_key,
+    k_full_nodes<<<nblk(N), 256>>>((const hkey*)b_keys.p, (const double*)b_ff.p, N, P, (hkey*)v.node_key,
                                    (double*)v.freq, (uint32_t*)v.tl_start, (uint32_t*)v.tl_cnt);
   {
     uint64_t tl_base = 0;
     for (size_t li = 1; li < order.size() && N > 0; ++li) {
       PerLabel& x = pl[li];
       uint32_t nb = lfirst[order[li]];
-      CKT(cudaMemcpy((uint64_t*)v.node_key + nb, x.keys, (size_t)x.nseg * 8, cudaMemcpyDeviceToDevice));
+      CKT(cudaMemcpy((hkey*)v.node_key + nb, x.keys, (size_t)x.nseg * sizeof(hkey), cudaMemcpyDeviceToDevice));
       CKT(cudaMemcpy((double*)v.freq + (uint64_t)nb * P, x.freq, (size_t)x.nseg * P * 8, cudaMemcpyDeviceToDevice));
       CKT(cudaMemcpy((uint32_t*)v.tl_cnt + nb, x.tlc, (size_t)x.nseg * 4, cudaMemcpyDeviceToDevice));
       CKT(cudaMemcpy((uint32_t*)v.tl_adj + tl_base, x.adj, (size_t)N * 4, cudaMemcpyDeviceToDevice));
@@ -518,14 +581,12 @@ extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
       for (int l = 0; l < L; ++l) {
         if (!(B >> l & 1u)) continue;
         const uint32_t A = B & ~(1u << l);
-        const uint64_t km = host_key_mask(h, A);
-        k_project<<<nblk(nB), 256>>>(v.node_key + lfirst[B], km, lfirst[B], nB, (uint64_t*)b_pk.p, (uint32_t*)b_pi.p);
-        size_t tbx = b_tmp.cap;
-        CKT(cub::DeviceRadixSort::SortPairs(b_tmp.p, tbx, (uint64_t*)b_pk.p, (uint64_t*)b_sk.p, (uint32_t*)b_pi.p,
-                                            (uint32_t*)b_si.p, (int)nB, 0, sh));
-        k_heads<<<nblk(nB), 256>>>((const uint64_t*)b_sk.p, nB, (uint32_t*)b_flag.p);
+        const hkey km = host_key_mask(h, A);
+        k_project<<<nblk(nB), 256>>>(v.node_key + lfirst[B], km, lfirst[B], nB, (hkey*)b_pk.p, (uint32_t*)b_pi.p);
+        CKT(ss.sort((const hkey*)b_pk.p, (hkey*)b_sk.p, (const uint32_t*)b_pi.p, (uint32_t*)b_si.p, nB, sh));
+        k_heads<<<nblk(nB), 256>>>((const hkey*)b_sk.p, nB, (uint32_t*)b_flag.p);
         k_next_head<<<nblk(nB), 256>>>((const uint32_t*)b_flag.p, nB, (uint32_t*)b_head.p);
-        k_conn_heads<<<nblk(nB), 256>>>((const uint32_t*)b_flag.p, (const uint64_t*)b_sk.p, nB, v, A, l, (uint32_t)cn_base,
+        k_conn_heads<<<nblk(nB), 256>>>((const uint32_t*)b_flag.p, (const hkey*)b_sk.p, nB, v, A, l, (uint32_t)cn_base,
                                         (uint32_t*)v.cn_start, (uint32_t*)v.cn_cnt, (const uint32_t*)b_head.p, d_nconn);
         CKT(cudaMemcpy((uint32_t*)v.cn_adj + cn_base, b_si.p, (size_t)nB * 4, cudaMemcpyDeviceToDevice));
         cn_base += nB;
@@ -589,7 +650,7 @@ extern "C" int grimb_tables_export(const GrimbTables* t, uint64_t* node_key, dou
   const ImageHeader& h = t->h;
   const TablesView& v = t->view;
   const uint64_t n = h.n_nodes;
-  if (node_key) CK(cudaMemcpy(node_key, v.node_key, n * 8, cudaMemcpyDeviceToHost));
+  if (node_key) CK(cudaMemcpy(node_key, v.node_key, n * sizeof(hkey), cudaMemcpyDeviceToHost));
   if (node_freq) CK(cudaMemcpy(node_freq, v.freq, n * h.P * 8, cudaMemcpyDeviceToHost));
   if (tl_start) CK(cudaMemcpy(tl_start, v.tl_start, n * 4, cudaMemcpyDeviceToHost));
   if (tl_cnt) CK(cudaMemcpy(tl_cnt, v.tl_cnt, n * 4, cudaMemcpyDeviceToHost));
@@ -722,6 +783,7 @@ k_impute(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArr
 // appended to `worklist` and handled by k_impute.  Result rows are allocated with one atomicAdd
 // per CTA (8 subjects).
 // ------------------------------------------------------------------------------------------
+#if GRIMB_KW == 1
 constexpr int FAST_WARPS = 8;
 constexpr int FAST_MAX_ROUNDS = 40;
 #ifndef FAST_MIN_BLOCKS
@@ -1057,6 +1119,8 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
   }
 }
 
+#endif  // GRIMB_KW == 1
+
 struct GrimbEngine {
   const GrimbTables* tables;
   int device;
@@ -1181,6 +1245,7 @@ extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const
     const uint64_t stride = (uint64_t)batch->n_subjects;
     CK(e->buckets.reserve((size_t)stride * 4 * GRIMB_BUCKETS + 16));
     unsigned int* bucket_n = (unsigned int*)(e->d_counters + 4);
+#if GRIMB_KW == 1
     if (e->fast_path && tv.L <= 5 && tv.P == 1) {
       // warp-per-subject kernel first; what it cannot finish goes through the general kernel
       CK(e->worklist.reserve((size_t)batch->n_subjects * 4 + 16));
@@ -1197,6 +1262,7 @@ extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const
       wl = (const uint32_t*)e->worklist.p;
       wl_n = cnt;
     }
+#endif
     {
       uint64_t cg = (stride + 255) / 256;
       if (cg > (uint64_t)e->sm_count * 4) cg = (uint64_t)e->sm_count * 4;

@@ -20,7 +20,20 @@
 #define GDN inline
 #endif
 
+// Packed haplotype key: one bit-field per locus.  GRIMB_KW = 1: 64-bit keys (<= 63 bits in use;
+// libgrimb200.so); GRIMB_KW = 2: 128-bit keys for wide 9-locus tables (libgrimb200w.so, same ABI
+// with GRIMB_KEY_WORDS = 2).
+#ifndef GRIMB_KW
+#define GRIMB_KW 1
+#endif
+
 namespace grimb {
+
+#if GRIMB_KW == 1
+typedef uint64_t hkey;
+#else
+typedef unsigned __int128 hkey;
+#endif
 
 struct Grp {
   int tid;             // index of this thread in the group
@@ -161,6 +174,23 @@ GD uint64_t dbits(double x) {
 GD uint64_t mix64(uint64_t k) {
   k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
   return k;
+}
+
+GD uint64_t hash_key(hkey k) {
+#if GRIMB_KW == 1
+  return mix64(k);
+#else
+  return mix64((uint64_t)k ^ mix64((uint64_t)(k >> 64) + 0x9e3779b97f4a7c15ULL));
+#endif
+}
+
+// 64-bit digest of a key for the per-subject scratch hash tables (identity for 64-bit keys)
+GD uint64_t fold_key(hkey k) {
+#if GRIMB_KW == 1
+  return k;
+#else
+  return (uint64_t)k ^ mix64((uint64_t)(k >> 64));
+#endif
 }
 
 GD int popc16(uint32_t m) {

@@ -16,7 +16,7 @@ struct BlockList {
 };
 
 struct Subject : Ctx {
-  uint64_t* chunk_extra;  // [g.n] arena: key bits re-inserted by the missing-data path
+  hkey* chunk_extra;  // [g.n] arena: key bits re-inserted by the missing-data path
   GrimbHapRow* st_hap[2];
   GrimbPopRow* st_pop[2];
   uint32_t* st_cnt;       // [4] arena: rows staged (umug, pmug, umug pops, pmug pops)
@@ -55,7 +55,7 @@ struct Subject : Ctx {
 
   GD bool allele_node(int l, uint32_t id, uint32_t& node) const {
     if (id == 0 || id > T.n_alleles[l]) return false;
-    node = ht_lookup(T, 1u << l, (uint64_t)id << T.shift[l]);
+    node = ht_lookup(T, 1u << l, (hkey)id << T.shift[l]);
     return node != GRIMB_NONE;
   }
 
@@ -135,7 +135,7 @@ struct Subject : Ctx {
 
   // ------------------------------------------------------------------ opening (open_phases)
   GD bool node_in_lists(uint32_t node, int slot, int var) const {
-    uint64_t k = T.node_key[node];
+    hkey k = T.node_key[node];
     for (int t = 0; t < n; ++t) {
       uint16_t id = (uint16_t)key_field(T, k, loc[t]);
       int x = side_of(slot, t);
@@ -239,7 +239,7 @@ struct Subject : Ctx {
     int uploc = 0;
     for (int l = 0; l < T.L; ++l)
       if (up >> l & 1u) uploc = l;
-    const uint64_t km = key_mask_of(T, tp);
+    const hkey km = key_mask_of(T, tp);
     // distinct block strings in first-occurrence order
     uint64_t ncomb;
     uint32_t* dd_first = nullptr;  // filter mode: candidate index of each distinct block string
@@ -259,8 +259,8 @@ struct Subject : Ctx {
       for (uint32_t i = g.tid; i < tsz; i += g.n) tab[i] = GRIMB_NONE;
       g.sync();
       for (uint32_t c = g.tid; c < nc; c += g.n) {
-        uint64_t k = T.node_key[sd.filt[c]] & km;
-        uint32_t h = (uint32_t)mix64(k) & (tsz - 1);
+        hkey k = T.node_key[sd.filt[c]] & km;
+        uint32_t h = (uint32_t)mix64(fold_key(k)) & (tsz - 1);
         for (;;) {
           uint32_t cur = tab[h];
           if (cur == GRIMB_NONE) {
@@ -297,7 +297,7 @@ struct Subject : Ctx {
         uint64_t q = base + g.tid;
         uint32_t node = GRIMB_NONE, deg = 0;
         if (q < ncomb) {
-          uint64_t key = 0;
+          hkey key = 0;
           bool known = true;
           if (sd.mode == 0) {
             uint64_t c = q;
@@ -308,7 +308,7 @@ struct Subject : Ctx {
                 uint16_t id = sh->lptr[sd.var][t][x][c % cn];
                 c /= cn;
                 if (id == 0 || id > T.n_alleles[loc[t]]) known = false;
-                key |= (uint64_t)id << T.shift[loc[t]];
+                key |= (hkey)id << T.shift[loc[t]];
               }
           } else {
             key = T.node_key[sd.filt[dd_first[q]]] & km;
@@ -354,7 +354,7 @@ struct Subject : Ctx {
   // save_space_mode (impute.py:1048-1059): an operand with more than 10 entries keeps the 10
   // with the largest sum over populations (ascending stable sort, delete from the front = the
   // ten largest by (sum, position)); original order preserved.  pe = vector length.
-  GD uint32_t prune10(uint64_t* keys, double* vecs, uint32_t cnt, int pe) {
+  GD uint32_t prune10(hkey* keys, double* vecs, uint32_t cnt, int pe) {
     if (cnt <= 10) return cnt;
     g.sync();
     if (g.tid == 0) {
@@ -432,7 +432,7 @@ struct Subject : Ctx {
             c /= bl[b].n;
           }
           double v = T.freq[(uint64_t)nd[0] * P + j];
-          uint64_t hap = T.node_key[nd[0]];
+          hkey hap = T.node_key[nd[0]];
           for (int b = 1; b < nb; ++b) {
             v = v * T.freq[(uint64_t)nd[b] * P + j] * 0.0001;
             hap |= T.node_key[nd[b]];
@@ -448,9 +448,9 @@ struct Subject : Ctx {
       // save_space_mode: materialise, pruning both operands to 10 entries before every product
       uint32_t cnt = bl[0].n;
       uint32_t cap0 = cnt > 100 ? cnt : 100;
-      uint64_t* keys = alloc<uint64_t>(cap0);
+      hkey* keys = alloc<hkey>(cap0);
       double* vecs = alloc<double>((uint64_t)cap0 * P);
-      uint64_t* keys2 = alloc<uint64_t>(100);
+      hkey* keys2 = alloc<hkey>(100);
       double* vecs2 = alloc<double>(100ull * P);
       if (ws_fail) return;
       for (uint32_t i = g.tid; i < cnt; i += g.n) {
@@ -461,7 +461,7 @@ struct Subject : Ctx {
       g.sync();
       for (int b = 1; b < nb && cnt > 0; ++b) {
         uint32_t nn = bl[b].n;
-        uint64_t* nk = alloc<uint64_t>(nn);
+        hkey* nk = alloc<hkey>(nn);
         double* nv = alloc<double>((uint64_t)nn * P);
         if (ws_fail) return;
         for (uint32_t i = g.tid; i < nn; i += g.n) {
@@ -515,7 +515,7 @@ struct Subject : Ctx {
   }
 
   // Expand sh->chunk_* through the connector CSR (or the node itself) into selector items.
-  GD void expand_chunk_cn(uint32_t total, uint64_t base, bool self, int uploc, const uint64_t* extra, double scale) {
+  GD void expand_chunk_cn(uint32_t total, uint64_t base, bool self, int uploc, const hkey* extra, double scale) {
     const int P = T.P;
     uint64_t items = (uint64_t)total * (uint64_t)P;
     for (uint64_t q0 = 0; q0 < items; q0 += g.n) {
@@ -558,15 +558,15 @@ struct Subject : Ctx {
       for (uint64_t base = 0; base < sd.ncand; base += g.n) {
         uint64_t c = base + g.tid;
         uint32_t node = GRIMB_NONE, deg = 0;
-        uint64_t ex = 0;
+        hkey ex = 0;
         if (c < sd.ncand) {
           uint16_t ids[MAXL];
           decode(sd, slot, c, ids);
-          uint64_t key;
+          hkey key;
           uint32_t label;
           if (pack(ids, keepmask, key, label)) node = ht_lookup(T, label, key);
           for (int t = 0; t < n; ++t)
-            if (!(keepmask >> t & 1u)) ex |= (uint64_t)ids[t] << T.shift[loc[t]];
+            if (!(keepmask >> t & 1u)) ex |= (hkey)ids[t] << T.shift[loc[t]];
           if (node != GRIMB_NONE) {
             if (nup == 0) deg = 1;
             else if (nup == 1) {
@@ -719,7 +719,7 @@ struct Subject : Ctx {
     const uint64_t mark = ar_used;
     // pass 1: value + key per candidate
     double* cval = alloc<double>(sd.ncand);
-    uint64_t* ckey = alloc<uint64_t>(sd.ncand);
+    hkey* ckey = alloc<hkey>(sd.ncand);
     if (ws_fail) return;
     for (uint64_t c = g.tid; c < sd.ncand; c += g.n) {
       uint16_t ids[MAXL];
@@ -727,9 +727,9 @@ struct Subject : Ctx {
       double v = 0;
       bool have = false, dead = false;
       int miss = 0;
-      uint64_t key = 0;
+      hkey key = 0;
       for (int t = 0; t < n && !dead; ++t) {
-        key |= (uint64_t)ids[t] << T.shift[loc[t]];
+        key |= (hkey)ids[t] << T.shift[loc[t]];
         uint32_t node;
         if (!allele_node(loc[t], ids[t], node)) {
           ++miss;
@@ -758,7 +758,7 @@ struct Subject : Ctx {
         uint64_t c = b + g.tid;
         bool in = c < sd.ncand && cval[c] >= 0;
         double v = in ? cval[c] : 0.0;
-        uint64_t k = in ? ckey[c] : 0ull;
+        hkey k = in ? ckey[c] : (hkey)0;
         uint32_t total;
         uint32_t pos = g.scan_excl(in ? 1u : 0u, total);  // barriers inside: all reads are done
         if (in) {
@@ -770,7 +770,7 @@ struct Subject : Ctx {
       }
       g.sync();
       if (ul && ucnt && nc) {
-        uint64_t* uk = alloc<uint64_t>(ucnt);
+        hkey* uk = alloc<hkey>(ucnt);
         double* uv = alloc<double>(ucnt);
         if (ws_fail) return;
         for (uint32_t u = g.tid; u < ucnt; u += g.n) {
@@ -1022,7 +1022,7 @@ GD void run_subject(Subject& S, const GrimbBatch& B, const OutArrays& O, uint64_
     S.sel = S.alloc<SelItem>(S.capsel);
     S.sel2 = S.alloc<SelItem>(S.capsel);
     S.sel_idx = S.alloc<uint32_t>(S.capsel);
-    S.chunk_extra = S.alloc<uint64_t>(g.n);
+    S.chunk_extra = S.alloc<hkey>(g.n);
     S.st_hap[0] = S.alloc<GrimbHapRow>(cfg->n_results);
     S.st_hap[1] = S.alloc<GrimbHapRow>(cfg->n_results);
     S.st_pop[0] = S.alloc<GrimbPopRow>(cfg->n_pop_results > 0 ? cfg->n_pop_results : 1);

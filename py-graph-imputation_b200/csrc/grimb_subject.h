@@ -38,18 +38,18 @@ struct SelItem {
   uint64_t wkey;  // ~orderable(weight): ascending = weight descending
   uint64_t ord;   // encounter order inside the side's list
   double f;
-  uint64_t hap;
+  hkey hap;
   uint32_t pop;
   uint32_t pad;
 };
 struct TopItem {
   double f;
-  uint64_t hap;
+  hkey hap;
   uint32_t pop;
   uint32_t pad;
 };
 struct Entry {
-  uint64_t h1, h2;
+  hkey h1, h2;
   double prob;
   uint16_t p1, p2;
   uint32_t pad;
@@ -88,6 +88,21 @@ struct OutArrays {  // device pointers of GrimbResults + global row counters
   unsigned long long* hap_counter;
   unsigned long long* pop_counter;
 };
+
+GD GrimbHapRow make_hap_row(hkey a, hkey b, double prob) {
+  GrimbHapRow o;
+#if GRIMB_KW == 1
+  o.a = a;
+  o.b = b;
+#else
+  o.a[0] = (uint64_t)a;
+  o.a[1] = (uint64_t)(a >> 64);
+  o.b[0] = (uint64_t)b;
+  o.b[1] = (uint64_t)(b >> 64);
+#endif
+  o.prob = prob;
+  return o;
+}
 
 GD uint64_t order_key_desc(double w) {
   w = w + 0.0;
@@ -148,7 +163,7 @@ struct Ctx {
   // ---------------------------------------------------------------- candidates
   GD void decode(const SlotDesc& sd, int slot, uint64_t c, uint16_t* ids) const {
     if (sd.mode) {
-      uint64_t k = T.node_key[sd.filt[c]];
+      hkey k = T.node_key[sd.filt[c]];
       for (int t = 0; t < n; ++t) ids[t] = (uint16_t)key_field(T, k, loc[t]);
     } else {
       for (int t = n - 1; t >= 0; --t) {
@@ -162,7 +177,7 @@ struct Ctx {
   }
 
   // pack the ids at the typed positions selected by posmask; false if an id is not a table allele
-  GD bool pack(const uint16_t* ids, uint32_t posmask, uint64_t& key, uint32_t& label) const {
+  GD bool pack(const uint16_t* ids, uint32_t posmask, hkey& key, uint32_t& label) const {
     key = 0;
     label = 0;
     bool known = true;
@@ -170,7 +185,7 @@ struct Ctx {
       if (posmask >> t & 1u) {
         int l = loc[t];
         if (ids[t] > T.n_alleles[l] || ids[t] == 0) known = false;
-        key |= (uint64_t)ids[t] << T.shift[l];
+        key |= (hkey)ids[t] << T.shift[l];
         label |= 1u << l;
       }
     return known;
@@ -226,7 +241,7 @@ struct Ctx {
     if (sh->sel_n + (uint32_t)g.n * per_thread > capsel) sel_compact();
   }
 
-  GD void sel_push(double w, uint64_t ord, double f, uint64_t hap, uint32_t pop) {
+  GD void sel_push(double w, uint64_t ord, double f, hkey hap, uint32_t pop) {
     uint64_t wk = order_key_desc(w);
     if (thr_on && !(wk < thr)) return;
     uint32_t p = atom_add(&sh->sel_n, 1u);
@@ -307,7 +322,7 @@ struct Ctx {
         } else {
           uint16_t ids[MAXL];
           decode(sd, slot, c, ids);
-          uint64_t key;
+          hkey key;
           uint32_t label;
           if (pack(ids, (1u << n) - 1u, key, label)) node = ht_lookup(T, label, key);
         }
@@ -325,7 +340,7 @@ struct Ctx {
       sh->chunk_off[g.tid] = off;
       if (total && g.tid == 0) sh->nonempty = 1;
       g.sync();
-      expand_chunk(total, base, isfull, T.tl_start, T.tl_adj, [](int) { return (uint64_t)0; }, false, 1.0);
+      expand_chunk(total, base, isfull, T.tl_start, T.tl_adj, [](int) { return (hkey)0; }, false, 1.0);
     }
     sel_finish(slot);
   }
@@ -492,7 +507,7 @@ struct Ctx {
     for (uint32_t i = g.tid; i < tsz; i += g.n) tab[i] = GRIMB_NONE;
     g.sync();
     const Entry* E = ent;
-    auto canon = [=](uint32_t i, uint64_t& ha, uint32_t& pa, uint64_t& hb, uint32_t& pb) {
+    auto canon = [=](uint32_t i, hkey& ha, uint32_t& pa, hkey& hb, uint32_t& pb) {
       const Entry& e = E[i];
       bool sw = e.h1 > e.h2 || (e.h1 == e.h2 && e.p1 > e.p2);
       ha = sw ? e.h2 : e.h1;
@@ -501,17 +516,17 @@ struct Ctx {
       pb = sw ? e.p1 : e.p2;
     };
     for (uint32_t i = g.tid; i < ent_n; i += g.n) {
-      uint64_t ha, hb;
+      hkey ha, hb;
       uint32_t pa, pb;
       canon(i, ha, pa, hb, pb);
-      uint32_t h = (uint32_t)mix64(ha ^ mix64(hb + 0x9e3779b97f4a7c15ULL) ^ ((uint64_t)pa << 17) ^ ((uint64_t)pb << 41)) & (tsz - 1);
+      uint32_t h = (uint32_t)mix64(fold_key(ha) ^ mix64(fold_key(hb) + 0x9e3779b97f4a7c15ULL) ^ ((uint64_t)pa << 17) ^ ((uint64_t)pb << 41)) & (tsz - 1);
       for (;;) {
         uint32_t cur = tab[h];
         if (cur == GRIMB_NONE) {
           cur = atom_cas(&tab[h], GRIMB_NONE, i);
           if (cur == GRIMB_NONE) break;
         }
-        uint64_t xa, xb;
+        hkey xa, xb;
         uint32_t qa, qb;
         canon(cur, xa, qa, xb, qb);
         if (xa == ha && xb == hb && qa == pa && qb == pb) {
@@ -549,14 +564,14 @@ struct Ctx {
   // kind 0: UMUG genotype (per-locus unordered pairs)   impute.py:497-504,529-533
   // kind 1: PMUG haplotype pair, first-seen orientation  impute.py:24-38
   // kind 2: population pair                               impute.py:535-543 / :24-38
-  GD void group_key(int kind, const Entry& e, uint64_t& a, uint64_t& b) const {
+  GD void group_key(int kind, const Entry& e, hkey& a, hkey& b) const {
     if (kind == 0) {
-      uint64_t lo = 0, hi = 0;
+      hkey lo = 0, hi = 0;
       for (int l = 0; l < T.L; ++l) {
         uint64_t x = key_field(T, e.h1, l), y = key_field(T, e.h2, l);
         uint64_t mn = x < y ? x : y, mxv = x < y ? y : x;
-        lo |= mn << T.shift[l];
-        hi |= mxv << T.shift[l];
+        lo |= (hkey)mn << T.shift[l];
+        hi |= (hkey)mxv << T.shift[l];
       }
       a = lo;
       b = hi;
@@ -597,16 +612,16 @@ struct Ctx {
     g.sync();
     const Entry* E = ent;
     for (uint32_t i = g.tid; i < ent_n; i += g.n) {
-      uint64_t a, b;
+      hkey a, b;
       group_key(kind, E[i], a, b);
-      uint32_t h = (uint32_t)mix64(a ^ mix64(b + 0x9e3779b97f4a7c15ULL)) & (tsz - 1);
+      uint32_t h = (uint32_t)mix64(fold_key(a) ^ mix64(fold_key(b) + 0x9e3779b97f4a7c15ULL)) & (tsz - 1);
       for (;;) {
         uint32_t cur = tab[h];
         if (cur == GRIMB_NONE) {
           cur = atom_cas(&tab[h], GRIMB_NONE, i);
           if (cur == GRIMB_NONE) break;
         }
-        uint64_t xa, xb;
+        hkey xa, xb;
         group_key(kind, E[cur], xa, xb);
         if (xa == a && xb == b) {
           atom_min(&tab[h], i);
@@ -707,11 +722,9 @@ struct Ctx {
         o.prob = gsum[gi];
         pop_rows[r] = o;
       } else {
-        GrimbHapRow o;
-        if (kind == 0) group_key(0, e, o.a, o.b);
-        else { o.a = e.h1; o.b = e.h2; }
-        o.prob = gsum[gi];
-        hap_rows[r] = o;
+        hkey ka = e.h1, kb = e.h2;
+        if (kind == 0) group_key(0, e, ka, kb);
+        hap_rows[r] = make_hap_row(ka, kb, gsum[gi]);
       }
     }
     if (g.tid == 0) *n_rows = rows;

@@ -4,7 +4,8 @@
 //   slots      open-addressing hash table, one region per locus-subset label (so the
 //              full-label region of a 1M-haplotype table is 32 MB and stays L2-resident);
 //              16-byte slots {packed key, node id}, load factor <= 0.5, linear probing, one
-//              128-bit load per probe (two slots per 32-byte sector).
+//              128-bit load per probe (two slots per 32-byte sector); 32-byte slots when the
+//              packed key is 128 bits wide (GRIMB_KW = 2).
 //   node_key   packed allele ids of node i (0 in the fields of absent loci)
 //   freq       [n_nodes][P] FP64 frequency vectors, reference node-id order
 //   tl_*       CSR: partial node -> full nodes containing it (ascending id)   [adjs_query]
@@ -18,11 +19,19 @@ namespace grimb {
 #define GRIMB_NONE 0xFFFFFFFFu
 #define GRIMB_ADJ_FAULT 0xFFFFFFFFu  // tl_cnt/cn_cnt: the reference raises IndexError here (T1)
 
-struct HSlot {
-  uint64_t key;
+#if GRIMB_KW == 1
+struct HSlot {   // 16 bytes: two slots per 32-byte sector
+  hkey key;
   uint32_t node;
   uint32_t pad;
 };
+#else
+struct HSlot {   // 32 bytes: one slot per sector
+  hkey key;
+  uint32_t node;
+  uint32_t pad[3];
+};
+#endif
 
 struct TablesView {
   int32_t L, P;
@@ -35,7 +44,7 @@ struct TablesView {
   const uint64_t* ht_off;       // [1<<L] first slot of the label's region
   const uint32_t* ht_mask;      // [1<<L] region size - 1 (power of two)
   const HSlot* slots;
-  const uint64_t* node_key;
+  const hkey* node_key;
   const double* freq;
   const uint32_t* tl_start;
   const uint32_t* tl_cnt;
@@ -45,14 +54,14 @@ struct TablesView {
   const uint32_t* cn_adj;
 };
 
-GD uint64_t key_field(const TablesView& T, uint64_t key, int locus) {
-  return (key >> T.shift[locus]) & ((1ull << T.width[locus]) - 1ull);
+GD uint64_t key_field(const TablesView& T, hkey key, int locus) {
+  return (uint64_t)(key >> T.shift[locus]) & ((1ull << T.width[locus]) - 1ull);
 }
 
-GD uint64_t key_mask_of(const TablesView& T, uint32_t label) {
-  uint64_t m = 0;
+GD hkey key_mask_of(const TablesView& T, uint32_t label) {
+  hkey m = 0;
   for (int l = 0; l < T.L; ++l)
-    if (label >> l & 1u) m |= ((1ull << T.width[l]) - 1ull) << T.shift[l];
+    if (label >> l & 1u) m |= (hkey)((1ull << T.width[l]) - 1ull) << T.shift[l];
   return m;
 }
 
@@ -60,9 +69,16 @@ GD HSlot load_slot(const HSlot* p) {
 #if GRIMB_DEVICE
   uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
   HSlot s;
+#if GRIMB_KW == 1
   s.key = (uint64_t)v.x | ((uint64_t)v.y << 32);
   s.node = v.z;
   s.pad = v.w;
+#else
+  uint4 w = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  s.key = (hkey)((uint64_t)v.x | ((uint64_t)v.y << 32)) | ((hkey)((uint64_t)v.z | ((uint64_t)v.w << 32)) << 64);
+  s.node = w.x;
+  s.pad[0] = s.pad[1] = s.pad[2] = 0;
+#endif
   return s;
 #else
   return *p;
@@ -72,10 +88,11 @@ GD HSlot load_slot(const HSlot* p) {
 // Home slot of a key: always the first slot of a 32-byte sector (two 16-byte slots), so a probe
 // reads whole sectors -- both slots of a sector are fetched by two adjacent 128-bit loads that
 // resolve to one memory transaction.
-GD uint32_t ht_home(uint64_t key, uint32_t mask) { return (uint32_t)mix64(key) & mask & ~1u; }
+#if GRIMB_KW == 1
+GD uint32_t ht_home(hkey key, uint32_t mask) { return (uint32_t)hash_key(key) & mask & ~1u; }
 
 // One probe: hash, then linear scan, a sector (two slots) per step, until the key or an empty slot.
-GD uint32_t ht_lookup(const TablesView& T, uint32_t label, uint64_t key) {
+GD uint32_t ht_lookup(const TablesView& T, uint32_t label, hkey key) {
   const uint32_t mask = T.ht_mask[label];
   const HSlot* base = T.slots + T.ht_off[label];
   uint32_t h = ht_home(key, mask);
@@ -89,5 +106,21 @@ GD uint32_t ht_lookup(const TablesView& T, uint32_t label, uint64_t key) {
     h = (h + 2) & mask;
   }
 }
+#else
+GD uint32_t ht_home(hkey key, uint32_t mask) { return (uint32_t)hash_key(key) & mask; }
+
+// One probe: hash, then linear scan, a sector (one 32-byte slot) per step.
+GD uint32_t ht_lookup(const TablesView& T, uint32_t label, hkey key) {
+  const uint32_t mask = T.ht_mask[label];
+  const HSlot* base = T.slots + T.ht_off[label];
+  uint32_t h = ht_home(key, mask);
+  for (;;) {
+    const HSlot s0 = load_slot(base + h);
+    if (s0.node == GRIMB_NONE) return GRIMB_NONE;
+    if (s0.key == key) return s0.node;
+    h = (h + 1) & mask;
+  }
+}
+#endif
 
 }  // namespace grimb

@@ -441,10 +441,22 @@ struct GrimbText {
     return "?";
   }
 
-  void put_hap(uint64_t key, const Line& ln, std::string& o) const {
+  // allele id of locus l inside a packed key (GRIMB_KEY_WORDS little-endian 64-bit words)
+#if GRIMB_KEY_WORDS == 1
+  typedef uint64_t keyref;
+  uint32_t field(keyref key, int l) const { return (uint32_t)((key >> shift[l]) & ((1ull << key_bits[l]) - 1ull)); }
+#else
+  typedef const uint64_t* keyref;
+  uint32_t field(keyref key, int l) const {
+    const unsigned __int128 k = (unsigned __int128)key[0] | ((unsigned __int128)key[1] << 64);
+    return (uint32_t)((uint64_t)(k >> shift[l]) & ((1ull << key_bits[l]) - 1ull));
+  }
+#endif
+
+  void put_hap(keyref key, const Line& ln, std::string& o) const {
     bool first = true;
     for (int l = 0; l < L; ++l) {
-      uint32_t id = (uint32_t)((key >> shift[l]) & ((1ull << key_bits[l]) - 1ull));
+      uint32_t id = field(key, l);
       if (!id) continue;
       if (!first) o += '~';
       first = false;
@@ -494,8 +506,7 @@ struct GrimbText {
         s += ',';
         bool first = true;
         for (int l = 0; l < L; ++l) {
-          uint32_t a = (uint32_t)((row.a >> shift[l]) & ((1ull << key_bits[l]) - 1ull));
-          uint32_t b = (uint32_t)((row.b >> shift[l]) & ((1ull << key_bits[l]) - 1ull));
+          uint32_t a = field(row.a, l), b = field(row.b, l);
           if (!a) continue;
           sv x = allele_name(l, a, ln), y = allele_name(l, b, ln);
           if (y < x) std::swap(x, y);

@@ -1,7 +1,12 @@
-"""ctypes binding of libgrimb200.so (include/grimb200.h).
+"""ctypes binding of libgrimb200.so / libgrimb200w.so (include/grimb200.h).
+
+Two builds of the same ABI: libgrimb200.so packs a haplotype into a 64-bit key (GRIMB_KEY_WORDS
+= 1; every table whose per-locus allele-id fields fit 63 bits), libgrimb200w.so into a 128-bit
+key (GRIMB_KEY_WORDS = 2; wide 9-locus tables).  `load(kw)` picks one; Graph chooses kw from the
+allele dictionary sizes.
 
 There is no CPU path: if the CUDA library is missing or no device is present every entry point
-raises.  The library is built in-tree by py-graph-imputation_b200/csrc/build.sh (or
+raises.  The libraries are built in-tree by py-graph-imputation_b200/csrc/build.sh (or
 __graft_entry__.build())."""
 import ctypes as C
 import os
@@ -58,7 +63,12 @@ SUBJECT_DTYPE = [
     ("n_umug", "<u4"), ("n_pmug", "<u4"), ("n_umug_pops", "<u4"), ("n_pmug_pops", "<u4"),
     ("tot_umug", "<u4"), ("tot_pmug", "<u4"), ("pair_evals", "<u4"), ("hap_off", "<u8"), ("pop_off", "<u8"),
 ]  # GrimbSubjectResult, 48 bytes
-HAP_ROW_DTYPE = [("a", "<u8"), ("b", "<u8"), ("prob", "<f8")]
+HAP_ROW_DTYPE = [("a", "<u8"), ("b", "<u8"), ("prob", "<f8")]                    # GrimbHapRow, GRIMB_KEY_WORDS = 1
+HAP_ROW_DTYPE_W = [("a", "<u8", (2,)), ("b", "<u8", (2,)), ("prob", "<f8")]      # GRIMB_KEY_WORDS = 2
+
+
+def hap_row_dtype(kw=1):
+    return HAP_ROW_DTYPE if kw == 1 else HAP_ROW_DTYPE_W
 POP_ROW_DTYPE = [("pa", "<u2"), ("pb", "<u2"), ("pad", "<u4"), ("prob", "<f8")]
 
 
@@ -93,25 +103,27 @@ class TextOut(C.Structure):
 
 OUT_KEYS = ("umug", "umug_pops", "pmug", "pmug_pops", "miss", "problem")  # GRIMB_OUT_* order
 
-_LIB = None
+_LIB = {}
 
 
-def lib_path():
+def lib_path(kw=1):
     here = os.path.dirname(os.path.abspath(__file__))
-    return os.path.normpath(os.path.join(here, "..", "..", "csrc", "libgrimb200.so"))
+    name = "libgrimb200.so" if kw == 1 else "libgrimb200w.so"
+    return os.path.normpath(os.path.join(here, "..", "..", "csrc", name))
 
 
-def load():
-    """Loads libgrimb200.so or raises: the product has no fallback."""
-    global _LIB
-    if _LIB is not None:
-        return _LIB
-    path = lib_path()
+def load(kw=1):
+    """Loads libgrimb200.so (kw = 1) or libgrimb200w.so (kw = 2), or raises: the product has no
+    fallback."""
+    if kw in _LIB:
+        return _LIB[kw]
+    path = lib_path(kw)
     if not os.path.exists(path):
         raise RuntimeError(
-            "libgrimb200.so not built (%s): run py-graph-imputation_b200/csrc/build.sh; "
-            "there is no CPU fallback" % path)
+            "%s not built (%s): run py-graph-imputation_b200/csrc/build.sh; "
+            "there is no CPU fallback" % (os.path.basename(path), path))
     lib = C.CDLL(path)
+    lib.key_words = kw
     lib.grimb_abi_version.restype = C.c_int
     lib.grimb_last_error.restype = C.c_char_p
     lib.grimb_tables_build.argtypes = [C.POINTER(TableDesc), C.POINTER(C.c_void_p)]
@@ -138,13 +150,13 @@ def load():
                                       C.c_int64, C.c_int64, C.POINTER(TextOut)]
     if lib.grimb_abi_version() != 2:
         raise RuntimeError("libgrimb200.so ABI mismatch")
-    _LIB = lib
+    _LIB[kw] = lib
     return lib
 
 
-def check(rc, what):
+def check(rc, what, lib=None):
     if rc != 0:
-        msg = load().grimb_last_error().decode("utf8", "replace")
+        msg = (lib or load()).grimb_last_error().decode("utf8", "replace")
         raise RuntimeError("%s failed (%d): %s" % (what, rc, msg))
 
 

@@ -40,13 +40,27 @@ def _label_order(L):
     return out
 
 
+def _kfield(keys, shift, bits):
+    """Allele-id field of packed keys: uint64 array (64-bit keys) or object array of ints (128-bit)."""
+    if keys.dtype == object:
+        m = (1 << bits) - 1
+        return np.array([(int(k) >> shift) & m for k in keys], dtype=np.int64)
+    return ((keys >> np.uint64(shift)) & np.uint64((1 << bits) - 1)).astype(np.int64)
+
+
+def _kand(keys, mask):
+    if keys.dtype == object:
+        return np.array([int(k) & mask for k in keys], dtype=object)
+    return keys & np.uint64(mask)
+
+
 def node_names(graph, arrays):
     """Name of every node id, from the packed keys."""
     L = len(graph.loci)
     keys = arrays["node_key"]
     cols = []
     for l in range(L):
-        ids = ((keys >> np.uint64(graph.shift[l])) & np.uint64((1 << graph.key_bits[l]) - 1)).astype(np.int64)
+        ids = _kfield(keys, graph.shift[l], graph.key_bits[l])
         names = np.array([""] + list(graph.alleles[l]), dtype=object)
         cols.append(names[ids])
     out = []
@@ -84,7 +98,7 @@ def write_csv(graph, out_dir, node_csv="nodes.csv", edges_csv="edges.csv", top_l
         for l in range(L):
             if lm >> l & 1:
                 km |= ((1 << graph.key_bits[l]) - 1) << graph.shift[l]
-        tl_cnt[n - 1] = int(np.count_nonzero((a["node_key"][:n_full] & np.uint64(km)) == a["node_key"][n - 1]))
+        tl_cnt[n - 1] = int(np.count_nonzero(_kand(a["node_key"][:n_full], km) == a["node_key"][n - 1]))
     with open(os.path.join(out_dir, top_links_csv), "w", newline="") as f:
         w = csv.writer(f)
         w.writerow([":START_ID(HAPLOTYPE)", ":END_ID(HAPLOTYPE)", ":TYPE"])

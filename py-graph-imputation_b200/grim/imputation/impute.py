@@ -241,7 +241,7 @@ class Imputation(object):
 
     # ------------------------------------------------------------------ batch execution
     def _run_gpu(self, cfg, batch, res, workspace):
-        lib = _lib.load()
+        lib = self.netGraph.lib
         eng = self.netGraph.engine(workspace)
         return lib.grimb_impute_host(eng, C.byref(cfg), C.byref(batch), C.byref(res))
 
@@ -272,7 +272,7 @@ class Imputation(object):
         pop_cap = max(1024, S * 2 * min(self.cfg.n_pop_results, 4))
         needed = np.zeros(2, np.int64)
         while True:
-            hap_rows = np.zeros(hap_cap, dtype=_lib.HAP_ROW_DTYPE)
+            hap_rows = np.zeros(hap_cap, dtype=_lib.hap_row_dtype(self.netGraph.kw))
             pop_rows = np.zeros(pop_cap, dtype=_lib.POP_ROW_DTYPE)
             r = _lib.Results()
             r.subjects = subj.ctypes.data
@@ -288,7 +288,7 @@ class Imputation(object):
                 pop_cap = max(pop_cap, int(needed[1]))
                 continue
             if rc != 0:
-                _lib.check(rc, "grimb_impute_host")
+                _lib.check(rc, "grimb_impute_host", self.netGraph.lib)
             break
         out = {k: subj[k] for k, _ in _lib.SUBJECT_DTYPE}
         out["hap_rows"], out["pop_rows"] = hap_rows, pop_rows
@@ -303,9 +303,10 @@ class Imputation(object):
 
     def _decode(self, key, unknown):
         g = self.netGraph
+        key = int(key) if g.kw == 1 else int(key[0]) | (int(key[1]) << 64)
         out = []
         for l in range(self.L):
-            i = (int(key) >> g.shift[l]) & ((1 << g.key_bits[l]) - 1)
+            i = (key >> g.shift[l]) & ((1 << g.key_bits[l]) - 1)
             if i:
                 out.append(self._allele_name(l, i, unknown))
             else:
@@ -438,8 +439,8 @@ class Imputation(object):
         """GrimbText: dictionaries + priority parameters for the C++ tokeniser / formatter."""
         if getattr(self, "_text", None) is not None:
             return self._text
-        lib = _lib.load()
         g = self.netGraph
+        lib = g.lib
         d = _lib.TextDesc()
         d.n_loci, d.n_pops = self.L, self.P
         keep = []
@@ -462,7 +463,7 @@ class Imputation(object):
             d.key_bits[l] = g.key_bits[l]
         d.n_threads = int(os.environ.get("GRIMB_HOST_THREADS", "0"))
         h = C.c_void_p()
-        _lib.check(lib.grimb_text_create(C.byref(d), C.byref(h)), "grimb_text_create")
+        _lib.check(lib.grimb_text_create(C.byref(d), C.byref(h)), "grimb_text_create", lib)
         self._text = h
         return h
 
@@ -482,7 +483,7 @@ class Imputation(object):
 
     def impute_text(self, data, first_index=0):
         """bytes of input lines -> dict of the six output texts (bytes), through grimb_impute_text."""
-        lib = _lib.load()
+        lib = self.netGraph.lib
         t = self._text_handle()
         engines = (C.c_void_p * len(self.workspaces))(*[self.netGraph.engine(w) for w in self.workspaces[:1]])
         # engines of the bigger tiers are created lazily: pass only what exists, retry on overflow
@@ -494,7 +495,7 @@ class Imputation(object):
                 engines[n_eng] = self.netGraph.engine(self.workspaces[n_eng])
                 n_eng += 1
                 continue
-            _lib.check(rc, "grimb_impute_text")
+            _lib.check(rc, "grimb_impute_text", lib)
             break
         self.stats["subjects"] += out.n_lines
         self.stats["pair_evals"] += out.pair_evals

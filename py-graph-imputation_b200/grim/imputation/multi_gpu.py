@@ -8,7 +8,7 @@ torch is used for the process group and the broadcast only (plumbing)."""
 import ctypes as C
 
 from . import _lib
-from .networkx_graph import Graph, key_layout
+from .networkx_graph import Graph
 
 FILE_KEYS = ("umug", "umug_pops", "pmug", "pmug_pops", "miss", "problem")
 
@@ -30,19 +30,19 @@ def broadcast_graph(graph, config, device, src=0):
     Graph; elsewhere it may be None.  Returns this rank's Graph."""
     import torch
     import torch.distributed as dist
-    lib = _lib.load()
     rank = dist.get_rank()
     dev = torch.device("cuda", device)
     meta = [None]
     if rank == src:
+        lib = graph.lib
         nbytes = C.c_int64()
-        _lib.check(lib.grimb_tables_image_size(graph.handle, C.byref(nbytes)), "grimb_tables_image_size")
+        _lib.check(lib.grimb_tables_image_size(graph.handle, C.byref(nbytes)), "grimb_tables_image_size", lib)
         meta = [(nbytes.value, graph.alleles)]
     dist.broadcast_object_list(meta, src=src)
     nbytes, alleles = meta[0]
     if rank == src:
         ptr = C.c_void_p()
-        _lib.check(lib.grimb_tables_image_ptr(graph.handle, C.byref(ptr)), "grimb_tables_image_ptr")
+        _lib.check(lib.grimb_tables_image_ptr(graph.handle, C.byref(ptr)), "grimb_tables_image_ptr", lib)
         img = torch.as_tensor(_DeviceView(ptr.value, nbytes), device=dev)
     else:
         img = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -51,13 +51,11 @@ def broadcast_graph(graph, config, device, src=0):
     if rank == src:
         return graph
     g = Graph(config, device=device)
-    g.alleles = alleles
-    g.allele_id = [{a: i + 1 for i, a in enumerate(al)} for al in alleles]
-    g.key_bits = key_layout([len(a) for a in alleles])
-    g.shift = [int(sum(g.key_bits[:l])) for l in range(len(alleles))]
+    g._set_dictionaries(alleles)
+    lib = g.lib
     h = C.c_void_p()
     _lib.check(lib.grimb_tables_from_image(C.c_void_p(img.data_ptr()), nbytes, device, C.byref(h)),
-               "grimb_tables_from_image")
+               "grimb_tables_from_image", lib)
     g.handle = h
     return g
 

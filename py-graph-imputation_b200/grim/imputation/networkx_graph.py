@@ -91,13 +91,21 @@ def read_hpf(freq_file, pops, loci, freq_trim, pops_count_file=None):
 
 def key_layout(n_alleles):
     """Field width per locus: enough for the table ids plus the subject-local ids of alleles
-    absent from the table; spare bits of the 63 are shared out evenly (max 16 per locus)."""
+    absent from the table; spare bits of the 63 (64-bit keys) or 127 (128-bit keys, when the
+    ids alone need more than 63) are shared out evenly (max 16 per locus)."""
     L = len(n_alleles)
     base = [max(1, int(n + 1).bit_length()) for n in n_alleles]
-    if sum(base) > 63:
-        raise NotImplementedError("packed key needs more than 63 bits (128-bit keys: next round)")
-    spare = (63 - sum(base)) // L
+    wide = os.environ.get("GRIMB_KEY_WORDS", "") == "2"   # force the 128-bit build (tests)
+    total = 63 if (sum(base) <= 63 and not wide) else 127
+    if sum(base) > total:
+        raise NotImplementedError("packed key needs more than 127 bits")
+    spare = (total - sum(base)) // L
     return [min(16, b + spare) for b in base]
+
+
+def key_words(key_bits):
+    """1: libgrimb200.so (64-bit packed keys), 2: libgrimb200w.so (128-bit)."""
+    return 1 if sum(key_bits) <= 63 else 2
 
 
 class Graph(object):
@@ -116,6 +124,8 @@ class Graph(object):
         self.allele_id = None
         self.key_bits = None
         self.shift = None
+        self.kw = 1           # key words: which of the two library builds serves this table
+        self.lib = None
         self._engines = {}
 
     def build_graph(self, nodesFile=None, edgesFile=None, allEdgesFile=None):
@@ -140,22 +150,24 @@ class Graph(object):
         self.allele_id = [{a: i + 1 for i, a in enumerate(al)} for al in self.alleles]
         self.key_bits = key_layout([len(a) for a in self.alleles])
         self.shift = [int(sum(self.key_bits[:l])) for l in range(len(self.alleles))]
+        self.kw = key_words(self.key_bits)
+        self.lib = _lib.load(self.kw)
 
     def image_to_host(self):
         """The device image of the tables as a host uint8 array (binary cache / replication)."""
-        lib = _lib.load()
+        lib = self.lib
         n = C.c_int64()
-        _lib.check(lib.grimb_tables_image_size(self.handle, C.byref(n)), "grimb_tables_image_size")
+        _lib.check(lib.grimb_tables_image_size(self.handle, C.byref(n)), "grimb_tables_image_size", lib)
         img = np.empty(n.value, dtype=np.uint8)
-        _lib.check(lib.grimb_tables_image_copy(self.handle, img.ctypes.data), "grimb_tables_image_copy")
+        _lib.check(lib.grimb_tables_image_copy(self.handle, img.ctypes.data), "grimb_tables_image_copy", lib)
         return img
 
     def from_image_host(self, img, alleles):
-        lib = _lib.load()
         self._set_dictionaries(alleles)
+        lib = self.lib
         h = C.c_void_p()
         _lib.check(lib.grimb_tables_from_image(img.ctypes.data, img.nbytes, self.device, C.byref(h)),
-                   "grimb_tables_from_image")
+                   "grimb_tables_from_image", lib)
         self.handle = h
         return self
 
@@ -172,12 +184,9 @@ class Graph(object):
         return load_cache(self, path)
 
     def from_arrays(self, alleles, full_alleles, full_freqs):
-        lib = _lib.load()
         L, P = len(self.loci), len(self.pops)
-        self.alleles = alleles
-        self.allele_id = [{a: i + 1 for i, a in enumerate(al)} for al in alleles]
-        self.key_bits = key_layout([len(a) for a in alleles])
-        self.shift = [int(sum(self.key_bits[:l])) for l in range(L)]
+        self._set_dictionaries(alleles)
+        lib = self.lib
         fa = np.ascontiguousarray(full_alleles, dtype=np.uint16)
         ff = np.ascontiguousarray(full_freqs, dtype=np.float64)
         d = _lib.TableDesc()
@@ -193,13 +202,13 @@ class Graph(object):
         d.last_parent_locus = others[-1] if others else -1
         d.device = self.device
         h = C.c_void_p()
-        _lib.check(lib.grimb_tables_build(C.byref(d), C.byref(h)), "grimb_tables_build")
+        _lib.check(lib.grimb_tables_build(C.byref(d), C.byref(h)), "grimb_tables_build", lib)
         self.handle = h
         return self
 
     def info(self):
         i = _lib.TableInfo()
-        _lib.check(_lib.load().grimb_tables_info(self.handle, C.byref(i)), "grimb_tables_info")
+        _lib.check(self.lib.grimb_tables_info(self.handle, C.byref(i)), "grimb_tables_info", self.lib)
         return {k: getattr(i, k) for k, _ in _lib.TableInfo._fields_}
 
     def export(self):
@@ -207,7 +216,7 @@ class Graph(object):
         i = self.info()
         L, P, n = i["n_loci"], i["n_pops"], i["n_nodes"]
         out = {
-            "node_key": np.zeros(n, np.uint64), "node_freq": np.zeros((n, P), np.float64),
+            "node_key": np.zeros(n * self.kw, np.uint64), "node_freq": np.zeros((n, P), np.float64),
             "tl_start": np.zeros(n, np.uint32), "tl_cnt": np.zeros(n, np.uint32),
             "tl_adj": np.zeros(max(1, i["n_toplinks"]), np.uint32),
             "cn_start": np.zeros((n, L), np.uint32), "cn_cnt": np.zeros((n, L), np.uint32),
@@ -216,21 +225,26 @@ class Graph(object):
         }
         order = ["node_key", "node_freq", "tl_start", "tl_cnt", "tl_adj", "cn_start", "cn_cnt", "cn_adj",
                  "label_first", "label_count"]
-        _lib.check(_lib.load().grimb_tables_export(self.handle, *[out[k].ctypes.data for k in order]),
-                   "grimb_tables_export")
+        _lib.check(self.lib.grimb_tables_export(self.handle, *[out[k].ctypes.data for k in order]),
+                   "grimb_tables_export", self.lib)
+        if self.kw == 2:   # 128-bit keys: Python ints (little-endian word pairs)
+            w = out["node_key"].reshape(n, 2)
+            out["node_key"] = np.array([int(lo) | (int(hi) << 64) for lo, hi in w], dtype=object)
         return out
 
     def engine(self, workspace_bytes):
         e = self._engines.get(workspace_bytes)
         if e is None:
             e = C.c_void_p()
-            _lib.check(_lib.load().grimb_engine_create(self.handle, workspace_bytes, C.byref(e)),
-                       "grimb_engine_create")
+            _lib.check(self.lib.grimb_engine_create(self.handle, workspace_bytes, C.byref(e)),
+                       "grimb_engine_create", self.lib)
             self._engines[workspace_bytes] = e
         return e
 
     def close(self):
-        lib = _lib.load()
+        lib = self.lib
+        if lib is None:
+            return
         for e in self._engines.values():
             lib.grimb_engine_free(e)
         self._engines = {}

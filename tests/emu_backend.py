@@ -173,14 +173,16 @@ class EmuGraph(object):
             a[k] = np.ascontiguousarray(a[k])
             setattr(t, k, a[k].ctypes.data)
         self.tables = t
-        self.lib = build_emu()
+        self.emu = build_emu()
+        self.kw = 1
+        self.lib = _lib.load(1)   # host-only halves of the text pipeline (no CUDA calls)
 
 
 def emu_imputation(emu_graph, config, count_by_prob=None, arena=64 << 20):
     imp = Imputation(emu_graph, config, count_by_prob)
 
     def backend(cfg, batch, res, workspace):
-        return emu_graph.lib.grimb_emu_impute(C.byref(emu_graph.tables), C.byref(cfg), C.byref(batch),
+        return emu_graph.emu.grimb_emu_impute(C.byref(emu_graph.tables), C.byref(cfg), C.byref(batch),
                                               C.byref(res), arena)
 
     imp._backend = backend
@@ -208,7 +210,7 @@ def emu_impute_text(imp, emu_graph, data, first_index=0, arena=64 << 20):
         r.pop_rows, r.pop_capacity = pop.ctypes.data, pop_cap
         r.hap_rows_needed = needed[0:].ctypes.data
         r.pop_rows_needed = needed[1:].ctypes.data
-        rc = emu_graph.lib.grimb_emu_impute(C.byref(emu_graph.tables), C.byref(imp.cfg), C.byref(b), C.byref(r), arena)
+        rc = emu_graph.emu.grimb_emu_impute(C.byref(emu_graph.tables), C.byref(imp.cfg), C.byref(b), C.byref(r), arena)
         if rc == _lib.E_CAPACITY:
             hap_cap, pop_cap = max(hap_cap, int(needed[0])), max(pop_cap, int(needed[1]))
             continue

@@ -18,11 +18,12 @@ def _declared():
     return sorted(set(re.findall(r"\b(grimb_[a-z_]+)\s*\(", text)))
 
 
-@pytest.fixture(scope="module")
-def lib():
-    if not os.path.exists(_lib.lib_path()):
+@pytest.fixture(scope="module", params=[1, 2], ids=["keys64", "keys128"])
+def lib(request):
+    kw = request.param
+    if not os.path.exists(_lib.lib_path(kw)):
         subprocess.run(["sh", os.path.join(ROOT, "py-graph-imputation_b200", "csrc", "build.sh")], check=True)
-    return ctypes.CDLL(_lib.lib_path())
+    return ctypes.CDLL(_lib.lib_path(kw))
 
 
 def test_header_symbols_exported(lib):
@@ -41,7 +42,8 @@ def test_abi_version_and_struct_sizes(lib):
     lib.grimb_abi_version.restype = ctypes.c_int
     assert lib.grimb_abi_version() == 2
     assert np.dtype(_lib.SUBJECT_DTYPE).itemsize == 48
-    assert np.dtype(_lib.HAP_ROW_DTYPE).itemsize == 24
+    assert np.dtype(_lib.hap_row_dtype(1)).itemsize == 24
+    assert np.dtype(_lib.hap_row_dtype(2)).itemsize == 40
     assert np.dtype(_lib.POP_ROW_DTYPE).itemsize == 16
 
 
