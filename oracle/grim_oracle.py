@@ -62,7 +62,11 @@ class OracleGraph:
     edges) fused with nxg.py:42-213 (dict + CSR load, including the sentinel quirk at
     :195-196), without going through the CSV files."""
 
-    def __init__(self, hpf_lines, pops, loci_map, freq_trim, pop_count_lines=None):
+    def __init__(self, hpf_lines, pops, loci_map, freq_trim, pop_count_lines=None, marginals=True):
+        # marginals=False (checker speed only, not a reference feature): keep just the full
+        # haplotype label.  Exact for subjects typed at every locus whose Plan A succeeds -- the
+        # only queries are full-label lookups (nxg.py:262-266) -- which is how the big 9-locus
+        # configuration is sampled; callers must check that every sampled subject used Plan A.
         self.pops = list(pops)
         self.loci_map = {k: int(v) for k, v in loci_map.items()}
         nloc = len(self.loci_map)
@@ -73,6 +77,8 @@ class OracleGraph:
         self.labels = [full]
         for r in range(len(full) - 1, 0, -1):
             self.labels.extend("".join(c) for c in itertools.combinations(full, r))
+        if not marginals:
+            self.labels = [full]
 
         # gen.py:259-266 trim threshold per population
         trim = {}
@@ -145,7 +151,7 @@ class OracleGraph:
         # nxg.py:91-130 connectors: (parent label, child name) -> parents (ascending id)
         conn = defaultdict(list)
         for lab in self.labels:
-            if len(lab) < 2:
+            if len(lab) < 2 or not marginals:
                 continue
             for name in self.by_label[lab]:
                 al = name.split("~")
@@ -256,7 +262,7 @@ def load_config(json_conf):
     }
 
 
-def graph_from_config(json_conf, base_dir=""):
+def graph_from_config(json_conf, base_dir="", marginals=True):
     """hpf.csv (+ pop counts file) -> OracleGraph, following gen.py:240-266."""
     with open(os.path.join(base_dir, json_conf["freq_file"])) as f:
         hpf = f.readlines()
@@ -271,6 +277,7 @@ def graph_from_config(json_conf, base_dir=""):
         json_conf.get("loci_map"),
         json_conf["freq_trim_threshold"],
         pc,
+        marginals,
     )
 
 

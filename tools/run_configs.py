@@ -26,7 +26,7 @@ from grim.imputation.networkx_graph import Graph  # noqa: E402
 from grim.run_impute_def import load_config  # noqa: E402
 
 
-def run(name, conf, hpf_text, counts_text, lines, sample, tmp):
+def run(name, conf, hpf_text, counts_text, lines, sample, tmp, oracle_marginals=True):
     hpf = os.path.join(tmp, name + "_hpf.csv")
     cnt = os.path.join(tmp, name + "_counts.txt")
     open(hpf, "w").write(hpf_text)
@@ -46,14 +46,15 @@ def run(name, conf, hpf_text, counts_text, lines, sample, tmp):
     dt = time.time() - t
     out = {k: v.splitlines() for k, v in texts.items()}
     mine = {k: v.decode("utf8") for k, v in imp.impute_text("".join(lines[:sample]).encode("utf8")).items()}
-    t = time.time()
-    ref, _ = go.impute_file(conf, lines=lines[:sample])
-    t_cpu = time.time() - t                            # includes the oracle's graph build
-    og = go.graph_from_config(conf)
+    og = go.graph_from_config(conf, marginals=oracle_marginals)
     oimp = go.OracleImputation(og, go.load_config(conf), go.count_by_prob_from_file(len(conf["populations"]), cnt))
     t = time.time()
-    oimp.impute_lines(lines[:sample])
+    ref = oimp.impute_lines(lines[:sample])
     t_cpu = time.time() - t
+    if not oracle_marginals:
+        # full-label-only oracle graph: exact only while every sampled subject is served by Plan A
+        only_a = imp.stats["plan"]
+        assert only_a[2] == 0 and only_a[3] == 0, "sample left Plan A: %s" % only_a
     info = g.info()
     rec = {
         "config": name, "subjects": len(lines), "gpu_subjects_per_s": len(lines) / dt,
@@ -64,7 +65,8 @@ def run(name, conf, hpf_text, counts_text, lines, sample, tmp):
         "cpu_port_subjects_per_s_1core": sample / t_cpu, "cpu_sample": sample,
         "parity_identical_on_sample": all(mine[k] == ref[k] for k in ref),
         "rows": {k: len(v) for k, v in out.items()},
-        "table": {"n_full": info["n_full"], "n_nodes": info["n_nodes"], "pops": len(conf["populations"]), "build_s": t_build},
+        "table": {"n_full": info["n_full"], "n_nodes": info["n_nodes"], "pops": len(conf["populations"]), "build_s": t_build,
+                  "device_bytes": info["device_bytes"], "key_words": g.kw, "key_bits": sum(g.key_bits)},
     }
     print(json.dumps(rec), flush=True)
     g.close()
@@ -97,5 +99,31 @@ def main():
     run("C3_21pops_messy", c3, hpf21, cnt21, synth.messy_subjects(tab21, int(1000 * scale), 6, races=synth.race_fields(pops)), 60, tmp)
 
 
+def c5(tmp, scale):
+    """C5: 9 loci (256 phases, 511 labels), 5 populations, allele dictionaries wide enough that the
+    packed key needs the 128-bit build; the table is sized to be HBM-resident and L2-hostile."""
+    base = json.load(open(os.path.join(goldenlib.GOLD, "data", "base_conf.json")))
+    loci = ["A", "B", "C", "DPA1", "DPB1", "DQA1", "DQB1", "DRB1", "DRBX"]
+    n_all = [700, 1200, 600, 40, 300, 60, 250, 700, 100]
+    pops = ["Q%d" % i for i in range(5)]
+    n_full = int(float(os.environ.get("C5_HAPLOTYPES", "300000")) * scale)
+    hpf = synth.zipf_table(n_full, n_all, 20261018, loci=loci, pops=pops)
+    counts = 1000.0 / np.arange(1, 6) ** 1.1
+    cnt = "".join("%s,%s,%s\n" % (p, repr(float(c)), repr(float(c / counts.sum()))) for p, c in zip(pops, counts))
+    c = dict(base)
+    c.update({"populations": pops, "UNK_priors": "MR", "number_of_pop_results": 100,
+              "loci_map": {l: i + 1 for i, l in enumerate(loci)},
+              "freq_trim_threshold": 1e-30,
+              "Plan_B_Matrix": [[[1, 2, 3, 4, 5, 6, 7, 8, 9]], [[1, 2, 3], [4, 5], [6, 7, 8, 9]],
+                                [[1], [2, 3], [4, 5], [6, 7], [8, 9]], [[1], [2], [3], [4], [5], [6], [7], [8], [9]]]})
+    tab = synth.Table(hpf, pops[0], loci=loci)
+    lines = synth.typed_subjects(tab, int(100000 * scale), 9, synth.race_fields(pops))
+    run("C5_nine_loci_typed", c, hpf, cnt, lines, 200, tmp, oracle_marginals=False)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "c5":
+        import tempfile
+        c5(tempfile.mkdtemp(), float(os.environ.get("CONFIG_SCALE", "1")))
+        sys.exit(0)
     main()
