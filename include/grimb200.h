@@ -200,8 +200,9 @@ int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* 
 
 /* Number of kernel launches issued by this engine so far (bench.py's gpu_launches). */
 int64_t grimb_engine_launches(const GrimbEngine* e);
-/* Device time in ms (CUDA events on the launching stream) of the last k_impute_fast (which = 0) or
- * k_impute (which = 1) launch of this engine; negative if that kernel was not launched. */
+/* Device time in ms (CUDA events on the launching stream) of the last k_impute_fast (which = 0),
+ * k_impute (which = 1) or k_impute_typed (which = 2) launch of this engine; negative if that kernel
+ * was not launched. */
 double grimb_engine_kernel_ms(const GrimbEngine* e, int which);
 
 /* ------------------------------------------------------------------------------------------

@@ -1121,6 +1121,406 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
 
 #endif  // GRIMB_KW == 1
 
+// ------------------------------------------------------------------------------------------
+// Typed path: one WARP per subject for fully typed, unambiguous, heterozygous subjects with any
+// number of populations P <= 32, any number of loci and either key width (BASELINE configs 3
+// and 5).  What the general kernel does with CTA-wide barriers over a global-memory arena is done
+// here with the 32 lanes and ~6-10 KB of shared memory per warp:
+//   probes      16 phases per pass: lane v < 16 probes the side-1 haplotype of phase base+v, lane
+//               16+v its complement (gen_phases, impute.py:274-303; adjs_query, nxg.py:253-278)
+//   side lists  lane j = population j: (f, pop) with f > 0, ranked by f*M[j][j] descending, ties by
+//               population (convert_list_to_one_dim, impute.py:424-442), capped at K
+//   pair test   lane k = position in the side-2 list, loop over h: x = eps / f1[h]; the `break` of
+//               the k loop (impute.py:464,545-546) is a prefix-minimum of f2 compared with x
+//   schedule    rounds of call_comp_phase_prob (impute.py:1658-1693) until one accepts, MaxProb/1e5
+//   sums        hap_total / per-phase PMUG sums in (phase, h, k) order; population-pair sums in
+//               shared memory (within one h step the pairs are distinct, so lanes add in parallel and
+//               steps are sequential: the reference's += order)
+// Subjects of any other shape -- or with more than TY_VP phases whose two haplotypes are both in
+// the table, or for which Plan A finds nothing -- go to `worklist` for k_impute.  There is no
+// geno_seen de-duplication to do: distinct kept phases of a heterozygous subject are distinct
+// unordered haplotype pairs.
+// ------------------------------------------------------------------------------------------
+constexpr int TY_WARPS = 8;
+constexpr int TY_VP = 4;
+constexpr int TY_MAX_ROUNDS = 40;
+
+struct __align__(16) TyLists {
+  hkey hk[TY_VP][2];
+  double f1s[TY_VP][32];
+  double f2s[TY_VP][32];
+  double pm2[TY_VP][32];
+  double xs[32];
+  uint8_t p1s[TY_VP][32];
+  uint8_t p2s[TY_VP][32];
+  uint8_t n1[TY_VP], n2[TY_VP];
+};
+
+static inline size_t ty_bytes_per_warp(int P) {
+  const size_t G = (size_t)P * (P + 1) / 2;
+  return (sizeof(TyLists) + G * 12 + 15) & ~(size_t)15;
+}
+
+__global__ void __launch_bounds__(TY_WARPS * 32)
+k_impute_typed(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O, uint32_t* worklist,
+               unsigned int* worklist_n, uint32_t per_warp) {
+  extern __shared__ __align__(16) unsigned char ty_smem[];
+  __shared__ double s_chain[TY_MAX_ROUNDS];
+  __shared__ int s_nchain;
+  const uint32_t FULLM = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int L = T.L, P = T.P;
+  const int G = P * (P + 1) / 2;
+  TyLists& W = *reinterpret_cast<TyLists*>(ty_smem + (size_t)warp * per_warp);
+  double* gsum = reinterpret_cast<double*>(ty_smem + (size_t)warp * per_warp + sizeof(TyLists));
+  uint16_t* gslot = reinterpret_cast<uint16_t*>(gsum + G);
+  uint16_t* gpair = gslot + G;
+  GrimbResults& R = O.r;
+  const bool want_u = cfg->output_umug != 0, want_p = cfg->output_pmug != 0;
+  const uint32_t lim_r = (uint32_t)cfg->n_results, lim_p = (uint32_t)cfg->n_pop_results;
+  const int K = cfg->max_haps_in_phase;
+  if (threadIdx.x == 0) {
+    double e = cfg->epsilon;   // epsilon chain of call_comp_phase_prob (impute.py:1665-1673)
+    int n = 0;
+    while (e > 0 && n < TY_MAX_ROUNDS) {
+      e /= 10;
+      if (e < 1.0e-9) e = 0.0;
+      s_chain[n++] = e;
+    }
+    s_nchain = (e > 0) ? -1 : n;
+  }
+  __syncthreads();
+  const int nchain = s_nchain;
+  const uint32_t full = (1u << L) - 1u;
+  const uint32_t nphase = 1u << (L - 1);
+  const uint64_t S = (uint64_t)B.n_subjects;
+  for (uint64_t s = (uint64_t)blockIdx.x * TY_WARPS + warp; s < S; s += (uint64_t)gridDim.x * TY_WARPS) {
+    const uint32_t typed = B.typed_mask[s];
+    if (typed == 0) {   // GRIMB_ST_SKIPPED
+      if (lane == 0) {
+        uint4 z = make_uint4(0, 0, 0, 0);
+        uint4 w0 = z;
+        w0.x = GRIMB_ST_SKIPPED;
+        uint4* dst = reinterpret_cast<uint4*>(R.subjects + s);
+        dst[0] = w0;
+        dst[1] = z;
+        dst[2] = z;
+      }
+      continue;
+    }
+    bool shape = typed == full && nchain >= 0;
+    {
+      const uint16_t* cn = B.counts + s * (uint64_t)L * 2;
+      bool ones = true;
+      for (int q = lane; q < 2 * L; q += 32) ones = ones && cn[q] == 1;
+      shape = __all_sync(FULLM, ones) && shape;
+    }
+    uint32_t pairs[GRIMB_MAX_LOCI];
+    uint32_t het = 0;
+    if (shape) {
+      const uint16_t* al = B.alleles + B.allele_off[s];
+#pragma unroll
+      for (int l = 0; l < GRIMB_MAX_LOCI; ++l) {
+        pairs[l] = 0;
+        if (l < L) {
+          const uint32_t a0 = al[2 * l], a1 = al[2 * l + 1];
+          pairs[l] = a0 | (a1 << 16);
+          if (a0 != a1) het |= 1u << l;
+        }
+      }
+      if (het == 0) shape = false;   // both haplotypes equal: the general kernel's geno_seen path
+    }
+    int nvp = 0;
+    bool punt = !shape;
+    const double* M = B.priors + (uint64_t)B.prior_index[s] * P * P;
+    if (!punt) {
+      const double mdiag = lane < P ? __ldg(M + lane * P + lane) : 0.0;
+      const uint32_t low = het & (nphase - 1u);
+      const bool last_het = (het >> (L - 1)) & 1u;
+      for (uint32_t base = 0; base < nphase && !punt; base += 16) {
+        const uint32_t v = lane & 15, side = lane >> 4, i = base + v;
+        const bool kept = i < nphase && !(i & ~low) && (last_het || i <= (low ^ i));
+        hkey key = 0;
+        bool known = true;
+#pragma unroll
+        for (int l = 0; l < GRIMB_MAX_LOCI; ++l)
+          if (l < L) {
+            const uint32_t a0 = pairs[l] & 0xffffu, a1 = pairs[l] >> 16;
+            const uint32_t a = (((i >> l) & 1u) ^ side) ? a1 : a0;   // the last locus never flips
+            known = known && (a - 1u) < T.n_alleles[l];
+            key |= (hkey)a << T.shift[l];
+          }
+        const uint32_t node = (kept && known) ? ht_lookup(T, full, key) : GRIMB_NONE;
+        const uint32_t hits = __ballot_sync(FULLM, node != GRIMB_NONE);
+        uint32_t both = hits & (hits >> 16) & 0xFFFFu;
+        while (both) {
+          const int b = __ffs(both) - 1;
+          both &= both - 1;
+          if (nvp == TY_VP) {
+            punt = true;
+            break;
+          }
+          const uint32_t nd1 = __shfl_sync(FULLM, node, b), nd2 = __shfl_sync(FULLM, node, 16 + b);
+          double f1 = 0.0, f2 = 0.0;
+          if (lane < P) {
+            f1 = __ldg(T.freq + (uint64_t)nd1 * P + lane);
+            f2 = __ldg(T.freq + (uint64_t)nd2 * P + lane);
+          }
+          const double w1 = f1 * mdiag, w2 = f2 * mdiag;
+          const bool v1 = f1 > 0, v2 = f2 > 0;
+          const uint32_t vm1 = __ballot_sync(FULLM, v1), vm2 = __ballot_sync(FULLM, v2);
+          int n1 = __popc(vm1), n2 = __popc(vm2);
+          n1 = n1 < K ? n1 : K;
+          n2 = n2 < K ? n2 : K;
+          if (n1 == 0 || n2 == 0) continue;   // the phase yields no pairs
+          int r1 = 0, r2 = 0;
+          for (int j = 0; j < P; ++j) {
+            const double u1 = __shfl_sync(FULLM, w1, j), u2 = __shfl_sync(FULLM, w2, j);
+            if (((vm1 >> j) & 1u) && (u1 > w1 || (u1 == w1 && j < lane))) ++r1;
+            if (((vm2 >> j) & 1u) && (u2 > w2 || (u2 == w2 && j < lane))) ++r2;
+          }
+          if (v1 && r1 < n1) {
+            W.f1s[nvp][r1] = f1;
+            W.p1s[nvp][r1] = (uint8_t)lane;
+          }
+          if (v2 && r2 < n2) {
+            W.f2s[nvp][r2] = f2;
+            W.p2s[nvp][r2] = (uint8_t)lane;
+          }
+          if (lane == b) W.hk[nvp][0] = key;
+          if (lane == 16 + b) W.hk[nvp][1] = key;
+          __syncwarp();
+          double pmv = lane < n2 ? W.f2s[nvp][lane] : 0.0;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const double o = __shfl_up_sync(FULLM, pmv, d);
+            if (lane >= d && o < pmv) pmv = o;
+          }
+          if (lane < n2) W.pm2[nvp][lane] = pmv;
+          if (lane == 0) {
+            W.n1[nvp] = (uint8_t)n1;
+            W.n2[nvp] = (uint8_t)n2;
+          }
+          ++nvp;
+        }
+      }
+      __syncwarp();
+      if (nvp == 0) punt = true;   // Plan A has no candidates: Plan B / C
+    }
+    // ---- epsilon schedule: rounds until one accepts (impute.py:1665-1681)
+    uint32_t evals = 0;
+    double eps_final = 0.0;
+    bool count_final = false;
+    if (!punt) {
+      int rstar = -1;
+      double mx = 0.0;
+      for (int r = 0; r < nchain && rstar < 0; ++r) {
+        const double eps = s_chain[r];
+        bool any = false;
+        double lmx = 0.0;
+        for (int vp = 0; vp < nvp; ++vp) {
+          const int n1 = W.n1[vp], n2 = W.n2[vp];
+          __syncwarp();
+          if (lane < n1) W.xs[lane] = eps / W.f1s[vp][lane];
+          __syncwarp();
+          const double f2 = lane < n2 ? W.f2s[vp][lane] : 0.0;
+          const double pm = lane < n2 ? W.pm2[vp][lane] : -1.0;
+          const uint32_t p2 = W.p2s[vp][lane];
+          for (int h = 0; h < n1; ++h) {
+            const double x = W.xs[h];
+            const bool reach = pm >= x;
+            const int cnt = __popc(__ballot_sync(FULLM, reach));
+            evals += cnt < n2 ? cnt + 1 : n2;
+            if (reach) {
+              const double m = __ldg(M + (uint32_t)W.p1s[vp][h] * P + p2);
+              if (m > 0 && m * f2 >= x) {
+                any = true;
+                double pr = W.f1s[vp][h] * f2 * m;
+                pr = pr * 2;
+                if (pr > lmx) lmx = pr;
+              }
+            }
+          }
+        }
+        if (__any_sync(FULLM, any)) {
+          rstar = r;
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) {
+            const double o = __shfl_xor_sync(FULLM, lmx, d);
+            lmx = o > lmx ? o : lmx;
+          }
+          mx = lmx;
+        }
+      }
+      if (rstar < 0) punt = true;
+      else if (s_chain[rstar] > 0) {
+        eps_final = mx / 100000;   // impute.py:1683-1693: one more evaluation at MaxProb / 100000
+        count_final = true;
+      }
+    }
+    // ---- final evaluation with accumulation in (phase, h, k) order
+    uint32_t E = 0, ng = 0, nrows = 0;
+    double total = 0.0, my_sum = 0.0;
+    int my_vp = 0;
+    if (!punt) {
+      for (int g = lane; g < G; g += 32) gslot[g] = 0xFFFFu;
+      bool have_total = false;
+      for (int vp = 0; vp < nvp; ++vp) {
+        const int n1 = W.n1[vp], n2 = W.n2[vp];
+        __syncwarp();
+        if (lane < n1) W.xs[lane] = eps_final / W.f1s[vp][lane];
+        __syncwarp();
+        const double f2 = lane < n2 ? W.f2s[vp][lane] : 0.0;
+        const double pm = lane < n2 ? W.pm2[vp][lane] : -1.0;
+        const uint32_t p2 = W.p2s[vp][lane];
+        double psum = 0.0;
+        bool have_p = false;
+        for (int h = 0; h < n1; ++h) {
+          const double x = W.xs[h];
+          const bool reach = pm >= x;
+          if (count_final) {
+            const int cnt = __popc(__ballot_sync(FULLM, reach));
+            evals += cnt < n2 ? cnt + 1 : n2;
+          }
+          const uint32_t p1 = W.p1s[vp][h];
+          bool a = false;
+          double pr = 0.0;
+          if (reach) {
+            const double m = __ldg(M + p1 * P + p2);
+            if (m > 0 && m * f2 >= x) {
+              a = true;
+              pr = W.f1s[vp][h] * f2 * m;
+              pr = pr * 2;
+            }
+          }
+          const uint32_t A = __ballot_sync(FULLM, a);
+          if (A) {
+            E += __popc(A);
+            // population pair sums (impute.py:535-543): pairs of one h step are distinct
+            uint32_t g = 0, slot = 0;
+            bool fresh = false;
+            if (a) {
+              const uint32_t lo = p1 < p2 ? p1 : p2, hi = p1 < p2 ? p2 : p1;
+              g = hi * (hi + 1) / 2 + lo;
+              slot = gslot[g];
+              fresh = slot == 0xFFFFu;
+            }
+            const uint32_t Fm = __ballot_sync(FULLM, fresh);
+            if (a) {
+              if (fresh) {
+                slot = ng + __popc(Fm & ((1u << lane) - 1u));
+                gslot[g] = (uint16_t)slot;
+                gsum[slot] = pr;
+                gpair[slot] = (uint16_t)((p1 << 8) | p2);
+              } else {
+                gsum[slot] = gsum[slot] + pr;
+              }
+            }
+            ng += __popc(Fm);
+            // hap_total (impute.py:529-533) and the per-phase haplotype-pair sum, k ascending
+            for (uint32_t mm = A; mm; mm &= mm - 1) {
+              const int j = __ffs(mm) - 1;
+              const double pj = __shfl_sync(FULLM, pr, j);
+              total = have_total ? total + pj : pj;
+              have_total = true;
+              psum = have_p ? psum + pj : pj;
+              have_p = true;
+            }
+            __syncwarp();
+          }
+        }
+        if (have_p) {
+          if (lane == (int)nrows) {
+            my_sum = psum;
+            my_vp = vp;
+          }
+          ++nrows;
+        }
+      }
+      if (E == 0) punt = true;   // nothing survives MaxProb / 100000: Plan B
+    }
+    if (punt) {
+      if (lane == 0) worklist[atomicAdd(worklist_n, 1u)] = (uint32_t)s;
+      continue;
+    }
+    // ---- publish
+    const uint32_t nu = want_u ? (lim_r < 1u ? lim_r : 1u) : 0u;
+    const uint32_t np = want_p ? (nrows < lim_r ? nrows : lim_r) : 0u;
+    const uint32_t npg = ng < lim_p ? ng : lim_p;
+    const uint32_t nup = want_u ? npg : 0u, npp = want_p ? npg : 0u;
+    const uint32_t nh = nu + np, npop = nup + npp;
+    unsigned long long hb = 0, pb = 0;
+    if (lane == 0) {
+      if (nh) hb = atomicAdd(O.hap_counter, (unsigned long long)nh);
+      if (npop) pb = atomicAdd(O.pop_counter, (unsigned long long)npop);
+    }
+    hb = __shfl_sync(FULLM, hb, 0);
+    pb = __shfl_sync(FULLM, pb, 0);
+    if (want_u && want_p) evals *= 2;   // the reference evaluates once per output kind
+    if (lane == 0) {
+      uint4 w0, w1, w2;
+      w0.x = GRIMB_ST_OK | (want_u ? (GRIMB_PLAN_A << 8) : 0) | (want_p ? (GRIMB_PLAN_A << 16) : 0);
+      w0.y = nu;
+      w0.z = np;
+      w0.w = nup;
+      w1.x = npp;
+      w1.y = want_u ? 1u : 0u;
+      w1.z = want_p ? E : 0u;
+      w1.w = evals;
+      w2.x = (uint32_t)hb;
+      w2.y = (uint32_t)(hb >> 32);
+      w2.z = (uint32_t)pb;
+      w2.w = (uint32_t)(pb >> 32);
+      uint4* dst = reinterpret_cast<uint4*>(R.subjects + s);
+      dst[0] = w0;
+      dst[1] = w1;
+      dst[2] = w2;
+    }
+    if ((int64_t)(hb + nh) <= R.hap_capacity) {
+      if (lane == 0 && nu) {
+        hkey glo = 0, ghi = 0;   // the single UMUG genotype: per-locus (min, max)
+#pragma unroll
+        for (int l = 0; l < GRIMB_MAX_LOCI; ++l)
+          if (l < L) {
+            const uint32_t a0 = pairs[l] & 0xffffu, a1 = pairs[l] >> 16;
+            glo |= (hkey)(a0 < a1 ? a0 : a1) << T.shift[l];
+            ghi |= (hkey)(a0 < a1 ? a1 : a0) << T.shift[l];
+          }
+        R.hap_rows[hb] = make_hap_row(glo, ghi, total);
+      }
+      // PMUG rows: one per phase with accepted pairs, by (sum desc, phase asc)
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < nrows; ++j) {
+        const double sj = __shfl_sync(FULLM, my_sum, (int)j);
+        if (sj > my_sum || (sj == my_sum && (int)j < lane)) ++rank;
+      }
+      if (lane < (int)nrows && rank < np) R.hap_rows[hb + nu + rank] = make_hap_row(W.hk[my_vp][0], W.hk[my_vp][1], my_sum);
+    }
+    __syncwarp();
+    if ((int64_t)(pb + npop) <= R.pop_capacity && npg) {
+      // population rows by (sum desc, first encounter asc); same rows for both output kinds
+      for (uint32_t t = lane; t < ng; t += 32) {
+        const double vt = gsum[t];
+        uint32_t rank = 0;
+        for (uint32_t u = 0; u < ng; ++u) {
+          const double vu = gsum[u];
+          if (vu > vt || (vu == vt && u < t)) ++rank;
+        }
+        if (rank < npg) {
+          GrimbPopRow o;
+          o.pop_a = (uint16_t)(gpair[t] >> 8);
+          o.pop_b = (uint16_t)(gpair[t] & 0xffu);
+          o.pad = 0;
+          o.prob = vt;
+          if (nup) R.pop_rows[pb + rank] = o;
+          if (npp) R.pop_rows[pb + nup + rank] = o;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 struct GrimbEngine {
   const GrimbTables* tables;
   int device;
@@ -1139,8 +1539,12 @@ struct GrimbEngine {
   DevBuf buckets;    // the general kernel's work, by cost bucket (heaviest first)
   int sm_count = 0;
   int fast_path = 1; // GRIMB_FAST=0 disables the warp-per-subject kernel (debugging / A-B runs)
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // [0,1] around k_impute_fast, [2,3] around k_impute
-  int ev_valid[2] = {0, 0};
+  // CUDA events around the last launch of k_impute_fast [0,1], k_impute [2,3], k_impute_typed [4,5]
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int ev_valid[3] = {0, 0, 0};
+  double last_worklist = -1; // subjects the last call handed from a warp-per-subject kernel to k_impute
+  int typed_ctas = 0;        // resident CTAs of k_impute_typed on this device (0: P > 32, kernel unused)
+  uint32_t typed_per_warp = 0;
 };
 
 extern "C" int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes_per_cta, GrimbEngine** out) {
@@ -1174,8 +1578,18 @@ extern "C" int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes
   CK(cudaMalloc((void**)&e->d_cfg, sizeof(GrimbConfig)));
   CK(cudaMalloc((void**)&e->d_counters, 64));
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&e->ev[i]));
+  for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&e->ev[i]));
   e->sm_count = prop.multiProcessorCount;
+  if (P <= 32) {
+    e->typed_per_warp = (uint32_t)ty_bytes_per_warp(P);
+    const size_t dyn = (size_t)e->typed_per_warp * TY_WARPS;
+    // the attribute is per function, not per engine: always allow the largest layout (P = 32)
+    CK(cudaFuncSetAttribute(k_impute_typed, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(ty_bytes_per_warp(32) * TY_WARPS)));
+    int tb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tb, k_impute_typed, TY_WARPS * 32, dyn));
+    e->typed_ctas = (tb < 1 ? 1 : tb) * prop.multiProcessorCount;
+  }
   const char* fp = getenv("GRIMB_FAST");
   if (fp && fp[0] == '0') e->fast_path = 0;
   const char* th = getenv("GRIMB_THREADS");
@@ -1201,10 +1615,12 @@ extern "C" int grimb_engine_free(GrimbEngine* e) {
 
 extern "C" int64_t grimb_engine_launches(const GrimbEngine* e) { return e ? e->launches : 0; }
 
-// Device time (CUDA events on the launching stream) of the last launch of k_impute_fast (which = 0)
-// or k_impute (which = 1); valid after the call that launched it has returned.  < 0 if not launched.
+// Device time (CUDA events on the launching stream) of the last launch of k_impute_fast (which = 0),
+// k_impute (which = 1) or k_impute_typed (which = 2); valid after the call that launched it has
+// returned.  < 0 if not launched.
 extern "C" double grimb_engine_kernel_ms(const GrimbEngine* e, int which) {
-  if (!e || which < 0 || which > 1 || !e->ev_valid[which]) return -1.0;
+  if (e && which == 3) return e->last_worklist;   // diagnostic: subjects handed to k_impute by the last call
+  if (!e || which < 0 || which > 2 || !e->ev_valid[which]) return -1.0;
   float ms = -1.f;
   if (cudaEventElapsedTime(&ms, e->ev[2 * which], e->ev[2 * which + 1]) != cudaSuccess) {
     cudaGetLastError();
@@ -1261,8 +1677,24 @@ extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const
       e->launches += 1;
       wl = (const uint32_t*)e->worklist.p;
       wl_n = cnt;
-    }
+    } else
 #endif
+    if (e->fast_path && e->typed_ctas > 0) {
+      // warp-per-subject kernel for fully typed unambiguous subjects, any P <= 32 / L / key width
+      CK(e->worklist.reserve((size_t)batch->n_subjects * 4 + 16));
+      unsigned int* cnt = (unsigned int*)(e->d_counters + 3);
+      uint64_t tg = ((uint64_t)batch->n_subjects + TY_WARPS - 1) / TY_WARPS;
+      if (tg > (uint64_t)e->typed_ctas) tg = (uint64_t)e->typed_ctas;
+      CK(cudaEventRecord(e->ev[4], st));
+      k_impute_typed<<<(unsigned)tg, TY_WARPS * 32, (size_t)e->typed_per_warp * TY_WARPS, st>>>(
+          tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt, e->typed_per_warp);
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(e->ev[5], st));
+      e->ev_valid[2] = 1;
+      e->launches += 1;
+      wl = (const uint32_t*)e->worklist.p;
+      wl_n = cnt;
+    }
     {
       uint64_t cg = (stride + 255) / 256;
       if (cg > (uint64_t)e->sm_count * 4) cg = (uint64_t)e->sm_count * 4;
@@ -1283,6 +1715,7 @@ extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const
   unsigned long long cnt[4];
   CK(cudaMemcpyAsync(cnt, e->d_counters, 32, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  e->last_worklist = (double)(unsigned int)(cnt[3] & 0xFFFFFFFFull);
   *res->hap_rows_needed = (int64_t)cnt[1];
   *res->pop_rows_needed = (int64_t)cnt[2];
   if ((int64_t)cnt[1] > res->hap_capacity || (int64_t)cnt[2] > res->pop_capacity)

@@ -47,6 +47,9 @@ def main():
     imp.impute_text(data)
     dt = time.time() - t
     print(kind, n, "subjects", round(n / dt), "subj/s total; abi", imp.stats.get("abi_seconds"), "retries", imp.stats["workspace_retries"])
+    eng = g.engine(imp.workspaces[0])
+    print("last call: k_impute_fast %.3f ms, k_impute %.3f ms, k_impute_typed %.3f ms, handed to k_impute: %d subjects"
+          % tuple(g.lib.grimb_engine_kernel_ms(eng, w) for w in (0, 1, 2, 3)))
 
 
 if __name__ == "__main__" and sys.argv[1] not in ("each", "heavy"):
