@@ -807,37 +807,31 @@ struct FastPair {
 };
 
 // Inputs of one subject, loaded one loop iteration ahead so that the dependent chain
-// allele_off -> alleles and prior_index -> prior overlaps the previous subject's work.
+// allele_off -> alleles and prior_index -> prior overlaps the previous subject's work.  Lane l < L of
+// the half-warp holds locus l (its allele pair and listed counts); every lane holds the scalars.
 struct FastIn {
-  uint32_t typed, c, off;
-  uint32_t pairs[5];
+  uint32_t typed, c, pair;
   double m;
 };
 
 __device__ __forceinline__ void fast_load(FastIn& in, const GrimbBatch& B, uint64_t s, int L, int i) {
   in.typed = B.typed_mask[s];
-  in.off = B.allele_off[s];
-  // every listed count must be 1: the counts of one subject are 2L uint16 = L aligned uint32
+  const uint32_t off = B.allele_off[s];
+  // the listed counts of one subject are 2L uint16 = L aligned uint32; every count must be 1
   const uint32_t* c32 = reinterpret_cast<const uint32_t*>(B.counts + s * (uint64_t)L * 2);
   in.c = i < L ? c32[i] : 0x00010001u;
-  const uint16_t* al = B.alleles + in.off;
-  if ((in.off & 1u) == 0) {
-    const uint32_t* a32 = reinterpret_cast<const uint32_t*>(al);
-#pragma unroll
-    for (int l = 0; l < 5; ++l) in.pairs[l] = l < L ? a32[l] : 0u;
-  } else {
-#pragma unroll
-    for (int l = 0; l < 5; ++l) in.pairs[l] = l < L ? ((uint32_t)al[2 * l] | ((uint32_t)al[2 * l + 1] << 16)) : 0u;
+  in.pair = 0;
+  if (i < L) {
+    const uint16_t* al = B.alleles + off + 2 * i;
+    in.pair = (off & 1u) ? ((uint32_t)al[0] | ((uint32_t)al[1] << 16)) : *reinterpret_cast<const uint32_t*>(al);
   }
   in.m = __ldg(B.priors + B.prior_index[s]);
 }
 
 // Two independent probes of the full-label region; the first sector of each is requested before
 // either is examined (the common case resolves both in that one round trip).
-__device__ __forceinline__ void ht_lookup2(const TablesView& T, uint32_t label, uint64_t k1, bool p1, uint64_t k2, bool p2,
-                                           uint32_t& n1, uint32_t& n2) {
-  const uint32_t mask = T.ht_mask[label];
-  const HSlot* base = T.slots + T.ht_off[label];
+__device__ __forceinline__ void ht_lookup2(const HSlot* __restrict__ base, uint32_t mask, uint64_t k1, bool p1, uint64_t k2,
+                                           bool p2, uint32_t& n1, uint32_t& n2) {
   uint32_t h1 = ht_home(k1, mask), h2 = ht_home(k2, mask);
   n1 = n2 = GRIMB_NONE;
   HSlot a0, a1, b0, b1;
@@ -890,14 +884,22 @@ __device__ __forceinline__ void ht_lookup2(const TablesView& T, uint32_t label, 
   }
 }
 
+__device__ __forceinline__ uint64_t half_or64(uint32_t hmask, uint64_t v) {
+  const uint32_t lo = __reduce_or_sync(hmask, (uint32_t)v), hi = __reduce_or_sync(hmask, (uint32_t)(v >> 32));
+  return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+
 // Row space is claimed per HALF-WARP in chunks (one global atomicAdd per FAST_CHUNK rows), so the
 // kernel has no CTA barrier and no per-subject global atomic; the unused tail of a chunk is a
 // hole in the row arrays (offsets are explicit per subject, so holes are harmless).
 constexpr uint32_t FAST_CHUNK = 64;
 
 // Half-warp per subject: lane i (0..15) of a half owns phase i and probes both of its haplotypes
-// (side choice i and its complement), so a warp imputes two subjects at once and nothing has to
-// be shuffled between the two sides of a phase.  All votes / reductions use the half's lane mask.
+// (side choice i and its complement), so a warp imputes two subjects at once.  Keys are built
+// cooperatively: lane l < L shifts the two alleles of locus l into place, two OR-reductions give
+// k0 (all side-0 alleles) and k1 (all side-1 alleles), and phase i's haplotypes are
+// k0 ^ (D & M_i) and its complement, with D = k0 ^ k1 and M_i the field mask of the loci i flips
+// (a per-lane constant).  All votes / reductions use the half's lane mask.
 __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_BLOCKS)
 k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O, uint32_t* worklist,
               unsigned int* worklist_n) {
@@ -925,6 +927,15 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
   }
   __syncthreads();
   const int nchain = s_nchain;
+  // per-lane constants: this lane's locus (shift, dictionary size) and its phase's flip mask
+  const uint32_t my_shift = i < L ? T.shift[i] : 0u;
+  const uint32_t my_nal = i < L ? T.n_alleles[i] : 0u;
+  uint64_t Mi = 0;
+  for (int l = 0; l < L; ++l)
+    if ((i >> l) & 1) Mi |= ((1ull << T.width[l]) - 1ull) << T.shift[l];
+  const uint64_t Mlast = ((1ull << T.width[L - 1]) - 1ull) << T.shift[L - 1];
+  const uint32_t ht_mask = T.ht_mask[full];
+  const HSlot* __restrict__ ht_base = T.slots + T.ht_off[full];
   const uint64_t S = (uint64_t)B.n_subjects;
   const uint64_t stride = (uint64_t)gridDim.x * FAST_WARPS * 2;
   uint64_t hap_base = 0, pop_base = 0;   // this half-warp's current chunks (uniform within the half)
@@ -936,41 +947,40 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
     const FastIn in = nxt;
     if (s + stride < S) fast_load(nxt, B, s + stride, L, i);
     bool done = false;  // finished here (rows, an empty result, or a skipped subject)
-    uint32_t acc = 0, rank = 0, n_acc = 0, evals = 0;
-    uint64_t key = 0, key2 = 0;
+    uint32_t acc = 0, rank = 0, n_acc = 0, evals = 0, gsel = 0;
+    uint64_t key = 0, key2 = 0, D = 0;
     double prob = 0.0, total = 0.0;
     const uint32_t typed = in.typed;
     bool shape = typed == full && nchain >= 0;
     shape = __all_sync(hmask, in.c == 0x00010001u) && shape;
     if (shape) {
-      bool known1 = true, known2 = true;
-      uint32_t het = 0;
-#pragma unroll
-      for (int l = 0; l < 5; ++l)
-        if (l < L) {
-          const uint32_t a0 = in.pairs[l] & 0xffffu, a1 = in.pairs[l] >> 16;
-          const bool bit = (i >> l) & 1;      // the last locus never flips: bit L-1 of i < 2^(L-1) is 0
-          const uint32_t p1 = bit ? a1 : a0, p2 = bit ? a0 : a1;
-          known1 = known1 && (p1 - 1u) < T.n_alleles[l];
-          known2 = known2 && (p2 - 1u) < T.n_alleles[l];
-          key |= (uint64_t)p1 << T.shift[l];
-          key2 |= (uint64_t)p2 << T.shift[l];
-          if (a0 != a1) het |= 1u << l;
-        }
+      const uint32_t a0 = in.pair & 0xffffu, a1 = in.pair >> 16;   // lanes >= L hold 0, 0
+      const uint64_t k0 = half_or64(hmask, (uint64_t)a0 << my_shift);
+      const uint64_t k1 = half_or64(hmask, (uint64_t)a1 << my_shift);
+      const uint32_t unk0 = (__ballot_sync(hmask, i < L && (a0 - 1u) >= my_nal) >> hbase) & 0xFFFFu;
+      const uint32_t unk1 = (__ballot_sync(hmask, i < L && (a1 - 1u) >= my_nal) >> hbase) & 0xFFFFu;
+      const uint32_t het = (__ballot_sync(hmask, a0 != a1) >> hbase) & 0xFFFFu;
+      gsel = (__ballot_sync(hmask, a0 > a1) >> hbase) & 0xFFFFu;
+      D = k0 ^ k1;
+      key = k0 ^ (D & Mi);    // side 1 of phase i takes the side-1 allele at the loci i flips
+      key2 = key ^ D;
+      const uint32_t ib = (uint32_t)i;
+      const bool known1 = ((unk0 & ~ib) | (unk1 & ib)) == 0, known2 = ((unk1 & ~ib) | (unk0 & ib)) == 0;
       const uint32_t low = het & ((uint32_t)nphase - 1u);
       const bool last_het = (het >> (L - 1)) & 1u;
-      const bool kept = i < nphase && !((uint32_t)i & ~low) && (last_het || (uint32_t)i <= (low ^ (uint32_t)i));
+      // the last locus never flips: phases are i < 2^(L-1); homozygous loci collapse phases
+      const bool kept = i < nphase && !(ib & ~low) && (last_het || ib <= (low ^ ib));
       // side 2 is only probed when side 1 exists (comp_phase_prob_*: `if len(Prob1) > 0`); probing
       // both at once returns the same lists
       uint32_t n1, n2;
-      ht_lookup2(T, full, key, kept && known1, key2, kept && known2, n1, n2);
+      ht_lookup2(ht_base, ht_mask, key, kept && known1, key2, kept && known2, n1, n2);
       FastPair pr;
       pr.f = n1 != GRIMB_NONE ? __ldg(T.freq + n1) : 0.0;   // P == 1
       pr.f2 = n2 != GRIMB_NONE ? __ldg(T.freq + n2) : 0.0;
       const bool cand = kept && pr.f > 0 && pr.f2 > 0;
       const uint32_t ncand = __popc(__ballot_sync(hmask, cand));
       const double m = in.m;
-      pr.same = key == key2;
+      pr.same = D == 0;
       pr.mpos = m > 0;
       pr.y = m * pr.f2;
       {
@@ -986,8 +996,11 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
       }
       // first round of the schedule at which this pair is accepted (acceptance is monotone in eps)
       uint32_t r_mine = 99;
-      if (cand) {
+      if (cand && pr.mpos) {
+        // rounds whose epsilon is above the proven band are rejections; the exact test only runs
+        // for an epsilon inside the band
         int r = 0;
+        while (r < nchain && s_chain[r] >= pr.hi) ++r;
         while (r < nchain && !pr.accept(s_chain[r])) ++r;
         if (r < nchain) r_mine = (uint32_t)r;
       }
@@ -1084,19 +1097,13 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
       dst[2] = w2;
     }
     if ((int64_t)(hb + nh) <= R.hap_capacity) {
-      if (i == 0 && nu) {
-        // the single UMUG genotype: per-locus (min, max) of the two typed alleles
-        uint64_t glo = 0, ghi = 0;
-#pragma unroll
-        for (int l = 0; l < 5; ++l)
-          if (l < L) {
-            const uint32_t a0 = in.pairs[l] & 0xffffu, a1 = in.pairs[l] >> 16;
-            glo |= (uint64_t)(a0 < a1 ? a0 : a1) << T.shift[l];
-            ghi |= (uint64_t)(a0 < a1 ? a1 : a0) << T.shift[l];
-          }
+      // the single UMUG genotype, per-locus (min, max) of the two typed alleles: the lane whose
+      // phase flips exactly the loci with a0 > a1 already holds it, up to the last locus
+      if (nu && (uint32_t)i == (gsel & ((uint32_t)nphase - 1u))) {
+        const uint64_t fix = ((gsel >> (L - 1)) & 1u) ? (D & Mlast) : 0ull;
         GrimbHapRow o;
-        o.a = glo;
-        o.b = ghi;
+        o.a = key ^ fix;
+        o.b = key2 ^ fix;
         o.prob = total;
         R.hap_rows[hb] = o;
       }

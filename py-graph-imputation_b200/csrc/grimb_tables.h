@@ -89,7 +89,7 @@ GD HSlot load_slot(const HSlot* p) {
 // reads whole sectors -- both slots of a sector are fetched by two adjacent 128-bit loads that
 // resolve to one memory transaction.
 #if GRIMB_KW == 1
-GD uint32_t ht_home(hkey key, uint32_t mask) { return (uint32_t)hash_key(key) & mask & ~1u; }
+GD uint32_t ht_home(hkey key, uint32_t mask) { return hash_key(key) & mask & ~1u; }
 
 // One probe: hash, then linear scan, a sector (two slots) per step, until the key or an empty slot.
 GD uint32_t ht_lookup(const TablesView& T, uint32_t label, hkey key) {
@@ -107,7 +107,7 @@ GD uint32_t ht_lookup(const TablesView& T, uint32_t label, hkey key) {
   }
 }
 #else
-GD uint32_t ht_home(hkey key, uint32_t mask) { return (uint32_t)hash_key(key) & mask; }
+GD uint32_t ht_home(hkey key, uint32_t mask) { return hash_key(key) & mask; }
 
 // One probe: hash, then linear scan, a sector (one 32-byte slot) per step.
 GD uint32_t ht_lookup(const TablesView& T, uint32_t label, hkey key) {

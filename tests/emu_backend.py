@@ -18,13 +18,16 @@ EMU_SO = os.path.join(HERE, "emu", "libgrimb_emu.so")
 M64 = (1 << 64) - 1
 
 
-def mix64(k):
-    k ^= k >> 33
-    k = (k * 0xff51afd7ed558ccd) & M64
-    k ^= k >> 33
-    k = (k * 0xc4ceb9fe1a85ec53) & M64
-    k ^= k >> 33
-    return k
+def hash_key(k):
+    """grimb_group.h hash_key() for 64-bit keys."""
+    M32 = 0xFFFFFFFF
+    h = (k & M32) ^ (((k >> 32) * 0x9E3779B1) & M32)
+    h ^= h >> 16
+    h = (h * 0x85ebca6b) & M32
+    h ^= h >> 13
+    h = (h * 0xc2b2ae35) & M32
+    h ^= h >> 16
+    return h
 
 
 class EmuTables(C.Structure):
@@ -123,7 +126,7 @@ def arrays_from_oracle(g, loci):
     for i in range(n):
         m = int(node_label[i])
         k = int(node_key[i])
-        h = mix64(k) & 0xFFFFFFFF & int(ht_mask[m]) & ~1      # ht_home(): sector-aligned
+        h = hash_key(k) & int(ht_mask[m]) & ~1      # ht_home(): sector-aligned
         base = int(ht_off[m])
         while slots["node"][base + h] != 0xFFFFFFFF:
             h = (h + 1) & int(ht_mask[m])
