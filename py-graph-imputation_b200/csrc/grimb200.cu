@@ -892,7 +892,10 @@ __device__ __forceinline__ uint64_t half_or64(uint32_t hmask, uint64_t v) {
 // Row space is claimed per HALF-WARP in chunks (one global atomicAdd per FAST_CHUNK rows), so the
 // kernel has no CTA barrier and no per-subject global atomic; the unused tail of a chunk is a
 // hole in the row arrays (offsets are explicit per subject, so holes are harmless).
-constexpr uint32_t FAST_CHUNK = 64;
+#ifndef GRIMB_FAST_CHUNK
+#define GRIMB_FAST_CHUNK 16
+#endif
+constexpr uint32_t FAST_CHUNK = GRIMB_FAST_CHUNK;
 
 // Half-warp per subject: lane i (0..15) of a half owns phase i and probes both of its haplotypes
 // (side choice i and its complement), so a warp imputes two subjects at once.  Keys are built
@@ -1528,6 +1531,8 @@ k_impute_typed(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, 
   }
 }
 
+constexpr int GRIMB_MAX_CHUNKS = 64;
+
 struct GrimbEngine {
   const GrimbTables* tables;
   int device;
@@ -1539,6 +1544,10 @@ struct GrimbEngine {
   GrimbConfig* d_cfg = nullptr;
   unsigned long long* d_counters = nullptr;  // [0] work, [1] hap rows, [2] pop rows
   cudaStream_t stream = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;   // copy-in / copy-out streams of the pipelined host call
+  cudaEvent_t ev_in[GRIMB_MAX_CHUNKS], ev_k[GRIMB_MAX_CHUNKS];
+  unsigned long long* h_cnt = nullptr;            // pinned: counters after every chunk [GRIMB_MAX_CHUNKS][4]
+  int64_t host_chunk = 131072;                    // subjects per pipeline chunk (GRIMB_HOST_CHUNK)
   int64_t launches = 0;
   // staging for the host-pointer form (grow-only)
   DevBuf in[6], outb[3];
@@ -1585,6 +1594,17 @@ extern "C" int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes
   CK(cudaMalloc((void**)&e->d_cfg, sizeof(GrimbConfig)));
   CK(cudaMalloc((void**)&e->d_counters, 64));
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < GRIMB_MAX_CHUNKS; ++i) {
+    CK(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_k[i], cudaEventDisableTiming));
+  }
+  CK(cudaMallocHost((void**)&e->h_cnt, GRIMB_MAX_CHUNKS * 4 * sizeof(unsigned long long)));
+  if (const char* hc = getenv("GRIMB_HOST_CHUNK")) {
+    const long long v = atoll(hc);
+    if (v >= 1024) e->host_chunk = v;
+  }
   for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&e->ev[i]));
   e->sm_count = prop.multiProcessorCount;
   if (P <= 32) {
@@ -1616,6 +1636,13 @@ extern "C" int grimb_engine_free(GrimbEngine* e) {
   cudaFree(e->d_cfg);
   cudaFree(e->d_counters);
   if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->s_in) cudaStreamDestroy(e->s_in);
+  if (e->s_out) cudaStreamDestroy(e->s_out);
+  for (int i = 0; i < GRIMB_MAX_CHUNKS; ++i) {
+    if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
+    if (e->ev_k[i]) cudaEventDestroy(e->ev_k[i]);
+  }
+  if (e->h_cnt) cudaFreeHost(e->h_cnt);
   delete e;
   return GRIMB_OK;
 }
@@ -1648,20 +1675,10 @@ static int check_cfg(const GrimbConfig* c, const GrimbTables* t) {
   return GRIMB_OK;
 }
 
-extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch, GrimbResults* res,
-                                   void* cuda_stream) {
-  if (!e || !cfg || !batch || !res) return fail(GRIMB_E_ARG, "null argument");
-  int rc = check_cfg(cfg, e->tables);
-  if (rc) return rc;
-  CK(cudaSetDevice(e->device));
-  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
-  CK(cudaMemcpyAsync(e->d_cfg, cfg, sizeof(GrimbConfig), cudaMemcpyHostToDevice, st));
-  CK(cudaMemsetAsync(e->d_counters, 0, 64, st));
-  OutArrays O;
-  O.r = *res;
-  O.hap_counter = e->d_counters + 1;
-  O.pop_counter = e->d_counters + 2;
-  if (batch->n_subjects > 0) {
+// Launches the kernels for one batch view (device pointers) on `st`; no synchronisation.  The row
+// counters d_counters[1..2] keep running across calls of one ABI call (chunks of one host batch).
+static int launch_kernels(GrimbEngine* e, const GrimbBatch* batch, const OutArrays& O, cudaStream_t st) {
+  if (batch->n_subjects <= 0) return GRIMB_OK;
     const TablesView& tv = e->tables->view;
     const uint32_t* wl = nullptr;
     const unsigned int* wl_n = nullptr;
@@ -1718,7 +1735,24 @@ extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const
     CK(cudaEventRecord(e->ev[3], st));
     e->ev_valid[1] = 1;
     e->launches += 1;
-  }
+  return GRIMB_OK;
+}
+
+extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch, GrimbResults* res,
+                                   void* cuda_stream) {
+  if (!e || !cfg || !batch || !res) return fail(GRIMB_E_ARG, "null argument");
+  int rc = check_cfg(cfg, e->tables);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+  CK(cudaMemcpyAsync(e->d_cfg, cfg, sizeof(GrimbConfig), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(e->d_counters, 0, 64, st));
+  OutArrays O;
+  O.r = *res;
+  O.hap_counter = e->d_counters + 1;
+  O.pop_counter = e->d_counters + 2;
+  rc = launch_kernels(e, batch, O, st);
+  if (rc) return rc;
   unsigned long long cnt[4];
   CK(cudaMemcpyAsync(cnt, e->d_counters, 32, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -1730,26 +1764,22 @@ extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const
   return GRIMB_OK;
 }
 
+// Host-pointer form.  Large batches are pipelined in chunks over three streams: while chunk c is
+// imputed, chunk c+1 is copied in and the rows of chunk c-1 are copied out (PCIe is full duplex),
+// so the call costs about max(H2D, kernels, D2H) instead of their sum.  Rows of one chunk occupy
+// one contiguous range of the row arrays (launches of one stream serialise and the row counters
+// keep running), so each chunk's D2H is three plain copies once its counters are known.
 extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* b, GrimbResults* r) {
   if (!e || !cfg || !b || !r) return fail(GRIMB_E_ARG, "null argument");
+  int rc = check_cfg(cfg, e->tables);
+  if (rc) return rc;
   CK(cudaSetDevice(e->device));
   const int L = e->tables->h.L, P = e->tables->h.P;
   const int64_t S = b->n_subjects;
   cudaStream_t st = e->stream;
   const size_t in_bytes[6] = {(size_t)S * 2, (size_t)S * L * 2 * 2, (size_t)(S + 1) * 4, (size_t)b->n_alleles_total * 2,
                               (size_t)S * 4, (size_t)b->n_priors * P * P * 8};
-  const void* in_src[6] = {b->typed_mask, b->counts, b->allele_off, b->alleles, b->prior_index, b->priors};
-  for (int i = 0; i < 6; ++i) {
-    CK(e->in[i].reserve(in_bytes[i] + 16));
-    CK(cudaMemcpyAsync(e->in[i].p, in_src[i], in_bytes[i], cudaMemcpyHostToDevice, st));
-  }
-  GrimbBatch db = *b;
-  db.typed_mask = (const uint16_t*)e->in[0].p;
-  db.counts = (const uint16_t*)e->in[1].p;
-  db.allele_off = (const uint32_t*)e->in[2].p;
-  db.alleles = (const uint16_t*)e->in[3].p;
-  db.prior_index = (const uint32_t*)e->in[4].p;
-  db.priors = (const double*)e->in[5].p;
+  for (int i = 0; i < 6; ++i) CK(e->in[i].reserve(in_bytes[i] + 16));
   const size_t ob[3] = {(size_t)S * sizeof(GrimbSubjectResult), (size_t)r->hap_capacity * sizeof(GrimbHapRow),
                         (size_t)r->pop_capacity * sizeof(GrimbPopRow)};
   for (int i = 0; i < 3; ++i) CK(e->outb[i].reserve(ob[i] + 16));
@@ -1757,13 +1787,77 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
   dr.subjects = (GrimbSubjectResult*)e->outb[0].p;
   dr.hap_rows = (GrimbHapRow*)e->outb[1].p;
   dr.pop_rows = (GrimbPopRow*)e->outb[2].p;
-  int rc = grimb_impute_device(e, cfg, &db, &dr, st);
-  if (rc != GRIMB_OK && rc != GRIMB_E_CAPACITY) return rc;
-  CK(cudaMemcpyAsync(r->subjects, e->outb[0].p, ob[0], cudaMemcpyDeviceToHost, st));
-  if (rc == GRIMB_OK) {
-    CK(cudaMemcpyAsync(r->hap_rows, e->outb[1].p, (size_t)*r->hap_rows_needed * sizeof(GrimbHapRow), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(r->pop_rows, e->outb[2].p, (size_t)*r->pop_rows_needed * sizeof(GrimbPopRow), cudaMemcpyDeviceToHost, st));
+  OutArrays O;
+  O.hap_counter = e->d_counters + 1;
+  O.pop_counter = e->d_counters + 2;
+  // chunking
+  int64_t chunk = e->host_chunk;
+  if (S > chunk * GRIMB_MAX_CHUNKS) chunk = (S + GRIMB_MAX_CHUNKS - 1) / GRIMB_MAX_CHUNKS;
+  const int nch = S > 0 ? (int)((S + chunk - 1) / chunk) : 0;
+  CK(cudaMemcpyAsync(e->d_cfg, cfg, sizeof(GrimbConfig), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(e->d_counters, 0, 64, st));
+  if (in_bytes[5]) CK(cudaMemcpyAsync(e->in[5].p, b->priors, in_bytes[5], cudaMemcpyHostToDevice, st));
+  for (int c = 0; c < nch; ++c) {
+    const int64_t s0 = (int64_t)c * chunk, s1 = s0 + chunk < S ? s0 + chunk : S, n = s1 - s0;
+    const uint32_t a0 = b->allele_off[s0], a1 = b->allele_off[s1];
+    cudaStream_t si = nch > 1 ? e->s_in : st;
+    CK(cudaMemcpyAsync((uint16_t*)e->in[0].p + s0, b->typed_mask + s0, (size_t)n * 2, cudaMemcpyHostToDevice, si));
+    CK(cudaMemcpyAsync((uint16_t*)e->in[1].p + s0 * L * 2, b->counts + s0 * L * 2, (size_t)n * L * 4, cudaMemcpyHostToDevice, si));
+    CK(cudaMemcpyAsync((uint32_t*)e->in[2].p + s0, b->allele_off + s0, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, si));
+    if (a1 > a0)
+      CK(cudaMemcpyAsync((uint16_t*)e->in[3].p + a0, b->alleles + a0, (size_t)(a1 - a0) * 2, cudaMemcpyHostToDevice, si));
+    CK(cudaMemcpyAsync((uint32_t*)e->in[4].p + s0, b->prior_index + s0, (size_t)n * 4, cudaMemcpyHostToDevice, si));
+    if (nch > 1) {
+      CK(cudaEventRecord(e->ev_in[c], si));
+      CK(cudaStreamWaitEvent(st, e->ev_in[c], 0));
+    }
+    GrimbBatch db = *b;
+    db.n_subjects = n;
+    db.typed_mask = (const uint16_t*)e->in[0].p + s0;
+    db.counts = (const uint16_t*)e->in[1].p + s0 * L * 2;
+    db.allele_off = (const uint32_t*)e->in[2].p + s0;   // offsets stay absolute into `alleles`
+    db.alleles = (const uint16_t*)e->in[3].p;
+    db.prior_index = (const uint32_t*)e->in[4].p + s0;
+    db.priors = (const double*)e->in[5].p;
+    O.r = dr;
+    O.r.subjects = dr.subjects + s0;
+    if (c > 0) {   // per-chunk counters: work tickets, worklist size, cost buckets (row counters keep running)
+      CK(cudaMemsetAsync(e->d_counters, 0, 8, st));
+      CK(cudaMemsetAsync(e->d_counters + 3, 0, 40, st));
+    }
+    rc = launch_kernels(e, &db, O, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(e->h_cnt + 4 * c, e->d_counters, 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(e->ev_k[c], st));
   }
+  // copy-out: chunk by chunk as its counters arrive
+  unsigned long long hap_prev = 0, pop_prev = 0, hap_end = 0, pop_end = 0;
+  double wl = 0;
+  for (int c = 0; c < nch; ++c) {
+    const int64_t s0 = (int64_t)c * chunk, s1 = s0 + chunk < S ? s0 + chunk : S, n = s1 - s0;
+    CK(cudaEventSynchronize(e->ev_k[c]));
+    hap_end = e->h_cnt[4 * c + 1];
+    pop_end = e->h_cnt[4 * c + 2];
+    wl += (double)(unsigned int)(e->h_cnt[4 * c + 3] & 0xFFFFFFFFull);
+    cudaStream_t so = nch > 1 ? e->s_out : st;
+    CK(cudaMemcpyAsync(r->subjects + s0, dr.subjects + s0, (size_t)n * sizeof(GrimbSubjectResult), cudaMemcpyDeviceToHost, so));
+    const unsigned long long hcap = (unsigned long long)r->hap_capacity, pcap = (unsigned long long)r->pop_capacity;
+    const unsigned long long h1 = hap_end < hcap ? hap_end : hcap, p1 = pop_end < pcap ? pop_end : pcap;
+    if (h1 > hap_prev)
+      CK(cudaMemcpyAsync(r->hap_rows + hap_prev, dr.hap_rows + hap_prev, (size_t)(h1 - hap_prev) * sizeof(GrimbHapRow),
+                         cudaMemcpyDeviceToHost, so));
+    if (p1 > pop_prev)
+      CK(cudaMemcpyAsync(r->pop_rows + pop_prev, dr.pop_rows + pop_prev, (size_t)(p1 - pop_prev) * sizeof(GrimbPopRow),
+                         cudaMemcpyDeviceToHost, so));
+    hap_prev = h1 > hap_prev ? h1 : hap_prev;
+    pop_prev = p1 > pop_prev ? p1 : pop_prev;
+  }
+  if (nch > 1) CK(cudaStreamSynchronize(e->s_out));
   CK(cudaStreamSynchronize(st));
-  return rc;
+  e->last_worklist = wl;
+  *r->hap_rows_needed = (int64_t)hap_end;
+  *r->pop_rows_needed = (int64_t)pop_end;
+  if ((int64_t)hap_end > r->hap_capacity || (int64_t)pop_end > r->pop_capacity)
+    return fail(GRIMB_E_CAPACITY, "result row buffers too small");
+  return GRIMB_OK;
 }

@@ -107,6 +107,9 @@ _LIB = {}
 
 
 def lib_path(kw=1):
+    override = os.environ.get("GRIMB_LIB" if kw == 1 else "GRIMB_LIB_W")   # A/B runs of kernel variants
+    if override:
+        return override
     here = os.path.dirname(os.path.abspath(__file__))
     name = "libgrimb200.so" if kw == 1 else "libgrimb200w.so"
     return os.path.normpath(os.path.join(here, "..", "..", "csrc", name))
