@@ -893,7 +893,7 @@ __device__ __forceinline__ uint64_t half_or64(uint32_t hmask, uint64_t v) {
 // kernel has no CTA barrier and no per-subject global atomic; the unused tail of a chunk is a
 // hole in the row arrays (offsets are explicit per subject, so holes are harmless).
 #ifndef GRIMB_FAST_CHUNK
-#define GRIMB_FAST_CHUNK 16
+#define GRIMB_FAST_CHUNK 32
 #endif
 constexpr uint32_t FAST_CHUNK = GRIMB_FAST_CHUNK;
 
