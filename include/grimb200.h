@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define GRIMB_ABI_VERSION 2
+#define GRIMB_ABI_VERSION 3
 #define GRIMB_MAX_LOCI 9
 #define GRIMB_MAX_ROWS 16
 #define GRIMB_MAX_BLOCKS 9
@@ -127,6 +127,13 @@ typedef struct {
   int32_t row_blocks[GRIMB_MAX_ROWS];
   uint16_t block_mask[GRIMB_MAX_ROWS][GRIMB_MAX_BLOCKS];
   uint8_t row_is_plan_a[GRIMB_MAX_ROWS]; /* impute.py:1118: block 0 == list(set(loci indices)) */
+  /* EM-facing modes */
+  int32_t hap_pop_pair;               /* grim.impute(hap_pop_pair=True) / impute_file(em_mr=True), impute.py:79-99,
+                                         2079-2088: the PMUG rows are the n_results best single (haplotype;pop,
+                                         haplotype;pop) pairs, not merged; each PMUG hap row k has a companion
+                                         GrimbPopRow with its two populations at
+                                         pop_rows[pop_off + n_umug_pops + n_pmug_pops + k]; one PMUG pop row   */
+  int32_t em;                         /* impute_file(em=True): no Plan C for the haplotype output (impute.py:1648) */
 } GrimbConfig;
 
 /* A batch of subjects, tokenised by the host (replaces the string handling of
@@ -143,6 +150,9 @@ typedef struct {
   const uint32_t* prior_index;  /* [S] row of `priors`                                              */
   const double* priors;         /* [n_priors][P][P] prior matrices (impute.py:1844-1924,1956-1959)  */
   int32_t n_priors;
+  const uint16_t* phase_mask;   /* optional [S] (NULL = none): bit m set = the m-th TYPED locus may switch
+                                   sides when phases are enumerated (bin_imputation_in_file,
+                                   impute.py:277-290,2001-2005,2030-2032)                              */
 } GrimbBatch;
 
 /* Result rows.  A hap row is two packed keys + probability: for UMUG the per-locus (min id,

@@ -259,6 +259,8 @@ def load_config(json_conf):
         "max_haplotypes_number_in_phase": c.get("max_haplotypes_number_in_phase", 100),
         "save_mode": c.get("save_space_mode", False),
         "UNK_priors": c.get("UNK_priors", "MR"),
+        # run_impute_def.py:124-125: optional JSON {subject id: [0/1 per typed position]} phase masks
+        "bin_imputation_input_file": c.get("bin_imputation_in_file", "None"),
     }
 
 
@@ -339,6 +341,8 @@ class OracleImputation:
         self.save_space = config["save_mode"]
         self.plan = "a"
         self.pair_evals = 0  # instrumentation: iterations reaching impute.py:464 / :573
+        self.binary = None   # per-subject phase mask of the subject in flight (impute.py:2030-2032)
+        self.em = False      # impute_file(em=True): no Plan C for the haplotype output (impute.py:1648)
 
     # ---- GL string -> phases ----
     def gl2haps(self, gl):
@@ -361,11 +365,14 @@ class OracleImputation:
             t2.append(sides[1])
         return {"Genotype": [sorted(t1), sorted(t2)], "N_Loc": n - empty}
 
-    def gen_phases(self, gen, n_loci):
-        # impute.py:274-303 (no per-subject phase mask)
+    def gen_phases(self, gen, n_loci, b_phases=None):
+        # impute.py:274-303; b_phases: positions whose flip is allowed (impute.py:277-290)
         out, seen = [], set()
+        allowed = None if b_phases is None else [i for i, e in enumerate(b_phases) if e == 1]
         for i in range(2 ** (n_loci - 1)):
             pick = [(i >> m) & 1 for m in range(n_loci)]
+            if allowed is not None:
+                pick = [v if (v == 0 or m in allowed) else 0 for m, v in enumerate(pick)]
             h1 = [gen[pick[k]][k] for k in range(n_loci)]
             h2 = [gen[1 - pick[k]][k] for k in range(n_loci)]
             a = "~".join(h1) + "^" + "~".join(h2)
@@ -800,7 +807,7 @@ class OracleImputation:
         if chrom == []:
             return None, None
         n_loci = chrom["N_Loc"]
-        pmags = self.gen_phases(chrom["Genotype"], n_loci)
+        pmags = self.gen_phases(chrom["Genotype"], n_loci, self.binary)
         if pmags == []:
             return None, None
         res_muugs = {"MaxProb": 0, "Haps": {}, "Pops": {}}
@@ -825,7 +832,7 @@ class OracleImputation:
                 self.M = saved
             if self.cfg["output_haplotypes"]:
                 res_haps = self.evaluate(phases, False)
-                if planb and len(res_haps["Haps"]) == 0:
+                if planb and len(res_haps["Haps"]) == 0 and not self.em:
                     self._reduce_common(pmags, n_loci, 1, True)
                     phases = self.open_phases(pmags, n_loci)
                     res_haps = self.plan_c(phases, False)
@@ -899,16 +906,26 @@ class OracleImputation:
         return None, None
 
     # ---- subject loop + writers (impute.py:1985-2155, :24-76) ----
-    def impute_lines(self, lines):
+    def impute_lines(self, lines, em_mr=False, em=False):
+        """em_mr: grim.grim.impute(hap_pop_pair=True) (impute.py:2079-2088); em: impute_file(em=True)."""
         out = {k: [] for k in ("umug", "umug_pops", "pmug", "pmug_pops", "miss", "problem")}
         n_res = self.cfg["number_of_results"]
         n_pop = self.cfg["number_of_pop_results"]
+        self.em = em
+        f_bin = None
+        bin_path = self.cfg.get("bin_imputation_input_file", "None")
+        if os.path.isfile(bin_path):          # impute.py:2001-2005
+            with open(bin_path) as f:
+                f_bin = json.load(f)
         for i, raw in enumerate(lines):
             try:
                 raw = raw.rstrip()
                 fields = raw.split(",") if "," in raw else raw.split("%")
                 sid = fields[0]
                 gl = fields[1]
+                self.binary = [1] * (len(self.full_label) - 1)     # impute.py:2030-2032
+                if f_bin is not None:
+                    self.binary = f_bin[sid]
                 race1 = race2 = None
                 if len(fields) > 2:
                     race1 = fields[2]
@@ -920,7 +937,10 @@ class OracleImputation:
                     continue
                 if (len(res_haps["Haps"]) == 0 or res_haps["Haps"] == "NaN") and len(res_muugs["Haps"]) == 0:
                     out["miss"].append(str(i) + "," + str(sid) + "\n")
-                if self.cfg["output_haplotypes"]:
+                if self.cfg["output_haplotypes"] and em_mr:
+                    _write_hap_race_pairs(sid, res_haps["Haps"], res_haps["Pops"], res_haps["Probs"], n_res, out["pmug"])
+                    _write_pairs(sid, res_haps["Pops"], res_haps["Probs"], 1, out["pmug_pops"], ",")
+                elif self.cfg["output_haplotypes"]:
                     _write_pairs(sid, res_haps["Haps"], res_haps["Probs"], n_res, out["pmug"], "+")
                     _write_pairs(sid, res_haps["Pops"], res_haps["Probs"], n_pop, out["pmug_pops"], ",")
                 if self.cfg["output_MUUG"]:
@@ -950,6 +970,16 @@ def _write_pairs(sid, res, probs, limit, rows, sign):
         rows.append(sid + "," + str(ranked[k][0]) + "," + str(ranked[k][1]) + "," + str(k) + "\n")
 
 
+def _write_hap_race_pairs(sid, haps, pops, probs, limit, rows):
+    # impute.py:79-99 write_best_hap_race_pairs: every (haplotype;population) pair on its own, no merging
+    allr = []
+    for k in range(len(probs)):
+        allr.append([probs[k], haps[k][0] + ";" + pops[k][0] + "," + haps[k][1] + ";" + pops[k][1]])
+    allr.sort(key=lambda x: x[0], reverse=True)
+    for k in range(min(limit, len(allr))):
+        rows.append(sid + "," + str(allr[k][1]) + "," + str(allr[k][0]) + "," + str(k) + "\n")
+
+
 def _write_dict(sid, res, limit, rows):
     # impute.py:61-76 write_best_prob_genotype
     ranked = sorted(res.items(), key=lambda kv: kv[1], reverse=True)
@@ -960,7 +990,7 @@ def _write_dict(sid, res, limit, rows):
 # ---------------------------------------------------------------------------------------------
 # File-level driver (grim/grim.py:57-74 + run_impute_def.py:41-211), used by tests and bench
 # ---------------------------------------------------------------------------------------------
-def impute_file(json_conf, base_dir="", graph=None, lines=None):
+def impute_file(json_conf, base_dir="", graph=None, lines=None, em_mr=False, em=False):
     """Returns (dict of the six file texts, graph)."""
     if graph is None:
         graph = graph_from_config(json_conf, base_dir)
@@ -973,7 +1003,7 @@ def impute_file(json_conf, base_dir="", graph=None, lines=None):
     if lines is None:
         with open(os.path.join(base_dir, json_conf["imputation_in_file"])) as f:
             lines = f.readlines()
-    return imp.impute_lines(lines), graph
+    return imp.impute_lines(lines, em_mr=em_mr, em=em), graph
 
 
 def impute_conf_file(conf_path, base_dir=""):

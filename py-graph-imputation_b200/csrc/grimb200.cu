@@ -1550,7 +1550,7 @@ struct GrimbEngine {
   int64_t host_chunk = 131072;                    // subjects per pipeline chunk (GRIMB_HOST_CHUNK)
   int64_t launches = 0;
   // staging for the host-pointer form (grow-only)
-  DevBuf in[6], outb[3];
+  DevBuf in[6], outb[3], in_mask;
   DevBuf worklist;   // subjects the fast kernel hands to the general kernel
   DevBuf buckets;    // the general kernel's work, by cost bucket (heaviest first)
   int sm_count = 0;
@@ -1677,8 +1677,11 @@ static int check_cfg(const GrimbConfig* c, const GrimbTables* t) {
 
 // Launches the kernels for one batch view (device pointers) on `st`; no synchronisation.  The row
 // counters d_counters[1..2] keep running across calls of one ABI call (chunks of one host batch).
-static int launch_kernels(GrimbEngine* e, const GrimbBatch* batch, const OutArrays& O, cudaStream_t st) {
+static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch, const OutArrays& O,
+                          cudaStream_t st) {
   if (batch->n_subjects <= 0) return GRIMB_OK;
+  // the warp-per-subject kernels implement the default phase enumeration and row layout only
+  const bool warp_kernels = e->fast_path && !batch->phase_mask && !cfg->hap_pop_pair;
     const TablesView& tv = e->tables->view;
     const uint32_t* wl = nullptr;
     const unsigned int* wl_n = nullptr;
@@ -1686,7 +1689,7 @@ static int launch_kernels(GrimbEngine* e, const GrimbBatch* batch, const OutArra
     CK(e->buckets.reserve((size_t)stride * 4 * GRIMB_BUCKETS + 16));
     unsigned int* bucket_n = (unsigned int*)(e->d_counters + 4);
 #if GRIMB_KW == 1
-    if (e->fast_path && tv.L <= 5 && tv.P == 1) {
+    if (warp_kernels && tv.L <= 5 && tv.P == 1) {
       // warp-per-subject kernel first; what it cannot finish goes through the general kernel
       CK(e->worklist.reserve((size_t)batch->n_subjects * 4 + 16));
       unsigned int* cnt = (unsigned int*)(e->d_counters + 3);
@@ -1703,7 +1706,7 @@ static int launch_kernels(GrimbEngine* e, const GrimbBatch* batch, const OutArra
       wl_n = cnt;
     } else
 #endif
-    if (e->fast_path && e->typed_ctas > 0) {
+    if (warp_kernels && e->typed_ctas > 0) {
       // warp-per-subject kernel for fully typed unambiguous subjects, any P <= 32 / L / key width
       CK(e->worklist.reserve((size_t)batch->n_subjects * 4 + 16));
       unsigned int* cnt = (unsigned int*)(e->d_counters + 3);
@@ -1751,7 +1754,7 @@ extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const
   O.r = *res;
   O.hap_counter = e->d_counters + 1;
   O.pop_counter = e->d_counters + 2;
-  rc = launch_kernels(e, batch, O, st);
+  rc = launch_kernels(e, cfg, batch, O, st);
   if (rc) return rc;
   unsigned long long cnt[4];
   CK(cudaMemcpyAsync(cnt, e->d_counters, 32, cudaMemcpyDeviceToHost, st));
@@ -1780,6 +1783,7 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
   const size_t in_bytes[6] = {(size_t)S * 2, (size_t)S * L * 2 * 2, (size_t)(S + 1) * 4, (size_t)b->n_alleles_total * 2,
                               (size_t)S * 4, (size_t)b->n_priors * P * P * 8};
   for (int i = 0; i < 6; ++i) CK(e->in[i].reserve(in_bytes[i] + 16));
+  if (b->phase_mask) CK(e->in_mask.reserve((size_t)S * 2 + 16));
   const size_t ob[3] = {(size_t)S * sizeof(GrimbSubjectResult), (size_t)r->hap_capacity * sizeof(GrimbHapRow),
                         (size_t)r->pop_capacity * sizeof(GrimbPopRow)};
   for (int i = 0; i < 3; ++i) CK(e->outb[i].reserve(ob[i] + 16));
@@ -1807,6 +1811,8 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
     if (a1 > a0)
       CK(cudaMemcpyAsync((uint16_t*)e->in[3].p + a0, b->alleles + a0, (size_t)(a1 - a0) * 2, cudaMemcpyHostToDevice, si));
     CK(cudaMemcpyAsync((uint32_t*)e->in[4].p + s0, b->prior_index + s0, (size_t)n * 4, cudaMemcpyHostToDevice, si));
+    if (b->phase_mask)
+      CK(cudaMemcpyAsync((uint16_t*)e->in_mask.p + s0, b->phase_mask + s0, (size_t)n * 2, cudaMemcpyHostToDevice, si));
     if (nch > 1) {
       CK(cudaEventRecord(e->ev_in[c], si));
       CK(cudaStreamWaitEvent(st, e->ev_in[c], 0));
@@ -1819,13 +1825,14 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
     db.alleles = (const uint16_t*)e->in[3].p;
     db.prior_index = (const uint32_t*)e->in[4].p + s0;
     db.priors = (const double*)e->in[5].p;
+    db.phase_mask = b->phase_mask ? (const uint16_t*)e->in_mask.p + s0 : nullptr;
     O.r = dr;
     O.r.subjects = dr.subjects + s0;
     if (c > 0) {   // per-chunk counters: work tickets, worklist size, cost buckets (row counters keep running)
       CK(cudaMemsetAsync(e->d_counters, 0, 8, st));
       CK(cudaMemsetAsync(e->d_counters + 3, 0, 40, st));
     }
-    rc = launch_kernels(e, &db, O, st);
+    rc = launch_kernels(e, cfg, &db, O, st);
     if (rc) return rc;
     CK(cudaMemcpyAsync(e->h_cnt + 4 * c, e->d_counters, 32, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(e->ev_k[c], st));

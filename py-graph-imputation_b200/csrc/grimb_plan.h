@@ -19,6 +19,7 @@ struct Subject : Ctx {
   hkey* chunk_extra;  // [g.n] arena: key bits re-inserted by the missing-data path
   GrimbHapRow* st_hap[2];
   GrimbPopRow* st_pop[2];
+  GrimbPopRow* st_pair;   // hap_pop_pair mode: populations of the staged PMUG rows
   uint32_t* st_cnt;       // [4] arena: rows staged (umug, pmug, umug pops, pmug pops)
   const double* Msubj;
 
@@ -917,13 +918,63 @@ struct Subject : Ctx {
   }
 
   // ------------------------------------------------------------------ emission
+  // write_best_hap_race_pairs (impute.py:79-99): the `limit` most probable single entries, ranked by
+  // (probability desc, encounter asc), nothing merged; the populations of row k go to pair_rows[k].
+  GDN uint32_t top_entries(uint32_t limit, GrimbHapRow* hap_rows, GrimbPopRow* pair_rows, uint32_t* n_rows) {
+    if (g.tid == 0) *n_rows = 0;
+    if (ent_n == 0 || ws_fail) return 0;
+    const uint64_t mark = ar_used;
+    uint32_t* ord = alloc<uint32_t>(ent_n);
+    if (ws_fail) return 0;
+    for (uint32_t i = g.tid; i < ent_n; i += g.n) ord[i] = i;
+    g.sync();
+    const Entry* E = ent;
+    group_sort(
+        g, ent_n,
+        [=](uint32_t a, uint32_t b) {
+          const double x = E[ord[a]].prob, y = E[ord[b]].prob;
+          return x > y || (x == y && ord[a] < ord[b]);
+        },
+        [=](uint32_t a, uint32_t b) {
+          uint32_t t = ord[a];
+          ord[a] = ord[b];
+          ord[b] = t;
+        });
+    const uint32_t rows = ent_n < limit ? ent_n : limit;
+    for (uint32_t r = g.tid; r < rows; r += g.n) {
+      const Entry& e = E[ord[r]];
+      hap_rows[r] = make_hap_row(e.h1, e.h2, e.prob);
+      GrimbPopRow o;
+      o.pop_a = e.p1;
+      o.pop_b = e.p2;
+      o.pad = 0;
+      o.prob = e.prob;
+      pair_rows[r] = o;
+    }
+    if (g.tid == 0) *n_rows = rows;
+    g.sync();
+    ar_used = mark;
+    return ent_n;
+  }
+
   GDN void emit(int which, bool planc, uint32_t* tot_out) {
     // which 0: UMUG (+ sorted pops), 1: PMUG (+ first-seen pops)
-    uint32_t rows = 0;
-    uint32_t ng = aggregate(which == 0 ? 0 : 1, (uint32_t)cfg->n_results, st_hap[which], nullptr, &st_cnt[which]);
-    (void)rows;
+    const bool pairs = which == 1 && cfg->hap_pop_pair;
+    uint32_t ng;
+    if (pairs) {
+      ng = top_entries((uint32_t)cfg->n_results, st_hap[1], st_pair, &st_cnt[1]);
+      if (planc) {   // Plan C reports populations as "all_pops" (impute.py:1375-1382)
+        for (uint32_t r = g.tid; r < st_cnt[1]; r += g.n) {
+          st_pair[r].pop_a = 0xFFFF;
+          st_pair[r].pop_b = 0xFFFF;
+        }
+        g.sync();
+      }
+    }
+    else ng = aggregate(which == 0 ? 0 : 1, (uint32_t)cfg->n_results, st_hap[which], nullptr, &st_cnt[which]);
     if (g.tid == 0) *tot_out = which == 0 ? ng : ent_n;
-    aggregate(2, (uint32_t)cfg->n_pop_results, nullptr, st_pop[which], &st_cnt[2 + which]);
+    // write_best_prob(subject_id, pops, probs, 1, ...) in the hap_pop_pair mode (impute.py:2088)
+    aggregate(2, pairs ? 1u : (uint32_t)cfg->n_pop_results, nullptr, st_pop[which], &st_cnt[2 + which]);
     g.sync();
     if (planc && g.tid == 0) {
       // populations are reported as "all_pops" (impute.py:1375-1382); UMUG keeps the row even
@@ -1001,10 +1052,16 @@ GD void run_subject(Subject& S, const GrimbBatch& B, const OutArrays& O, uint64_
       }
       const uint32_t low = het & ((1u << (n - 1)) - 1u);
       const bool last_het = het >> (n - 1) & 1u;
+      // per-subject phase mask (impute.py:277-290): only the positions in pm may switch sides.  The
+      // first index producing a flip set c is c itself; its mirror image (c ^ low, both
+      // orientations equal when the last locus is homozygous) is only ever produced if low fits pm.
+      const uint32_t pm = B.phase_mask ? (uint32_t)B.phase_mask[s] : 0xFFFFu;
+      const uint32_t eff = low & pm;
+      const bool mirror = !last_het && (low & ~pm) == 0;
       int k = 0;
       for (uint32_t i = 0; i < (1u << (n - 1)); ++i) {
-        if (i & ~low) continue;
-        if (!last_het && i > (low ^ i)) continue;
+        if (i & ~eff) continue;
+        if (mirror && i > (low ^ i)) continue;
         sh->ph[k++] = (uint16_t)i;
       }
       sh->cnt[0] = k;
@@ -1027,6 +1084,7 @@ GD void run_subject(Subject& S, const GrimbBatch& B, const OutArrays& O, uint64_
     S.st_hap[1] = S.alloc<GrimbHapRow>(cfg->n_results);
     S.st_pop[0] = S.alloc<GrimbPopRow>(cfg->n_pop_results > 0 ? cfg->n_pop_results : 1);
     S.st_pop[1] = S.alloc<GrimbPopRow>(cfg->n_pop_results > 0 ? cfg->n_pop_results : 1);
+    S.st_pair = S.alloc<GrimbPopRow>(cfg->hap_pop_pair ? (cfg->n_results > 0 ? cfg->n_results : 1) : 1);
     S.st_cnt = S.alloc<uint32_t>(4);
     S.Msubj = B.priors + (uint64_t)B.prior_index[s] * P * P;
     S.M = S.Msubj;
@@ -1097,7 +1155,7 @@ GD void run_subject(Subject& S, const GrimbBatch& B, const OutArrays& O, uint64_
             plan_p = plan_u;
             S.pair_evals += shared_evals;  // the reference evaluates again for the haplotype output
           }
-          if (!S.ws_fail && cfg->planb && S.ent_n == 0) {
+          if (!S.ws_fail && cfg->planb && S.ent_n == 0 && !cfg->em) {
             plan_p = GRIMB_PLAN_C;
             if (!reduced) {
               S.make_variant(VAR_C1);
@@ -1132,10 +1190,11 @@ GD void run_subject(Subject& S, const GrimbBatch& B, const OutArrays& O, uint64_
     nup = S.st_cnt[2];
     npp = S.st_cnt[3];
   }
+  const uint32_t npair = cfg->hap_pop_pair ? np : 0u;   // companion population rows of the PMUG rows
   if (g.tid == 0) {
     unsigned long long hb = 0, pb = 0;
     if (nu + np) hb = atom_add64(O.hap_counter, (unsigned long long)(nu + np));
-    if (nup + npp) pb = atom_add64(O.pop_counter, (unsigned long long)(nup + npp));
+    if (nup + npp + npair) pb = atom_add64(O.pop_counter, (unsigned long long)(nup + npp + npair));
     GrimbSubjectResult o;
     o.status = status;
     o.plan_umug = plan_u;
@@ -1163,9 +1222,10 @@ GD void run_subject(Subject& S, const GrimbBatch& B, const OutArrays& O, uint64_
     for (uint32_t i = g.tid; i < nu; i += g.n) R.hap_rows[hb + i] = S.st_hap[0][i];
     for (uint32_t i = g.tid; i < np; i += g.n) R.hap_rows[hb + nu + i] = S.st_hap[1][i];
   }
-  if ((int64_t)(pb + nup + npp) <= R.pop_capacity) {
+  if ((int64_t)(pb + nup + npp + npair) <= R.pop_capacity) {
     for (uint32_t i = g.tid; i < nup; i += g.n) R.pop_rows[pb + i] = S.st_pop[0][i];
     for (uint32_t i = g.tid; i < npp; i += g.n) R.pop_rows[pb + nup + i] = S.st_pop[1][i];
+    for (uint32_t i = g.tid; i < npair; i += g.n) R.pop_rows[pb + nup + npp + i] = S.st_pair[i];
   }
   g.sync();
 }

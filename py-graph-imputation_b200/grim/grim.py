@@ -14,14 +14,18 @@ def graph_freqs(conf_file="", for_em=False, em_pop=None, device=0):
     """Builds the frequency store for `conf_file` on the GPU and returns it (the reference writes
     nodes/edges/top_links CSV files here; this build keeps the tables in HBM and `impute(...,
     graph=g)` reuses them)."""
-    if for_em or em_pop:
-        raise NotImplementedError("EM graph variants are outside the B200 hot path (SURVEY 8f-4)")
     project = ""
     if conf_file == "":
         conf_file = _DEFAULT_CONF
         project = _PKG_ROOT + "/"
     with open(conf_file) as f:
         config = load_config(json.load(f), project, project)
+    # EM variants (generate_neo4j_multi_hpf.py:249-261 of the reference): em_pop replaces the
+    # population list; for_em ignores the population counts file when trimming
+    if em_pop:
+        config["pops"] = list(em_pop)
+    if for_em:
+        config["use_pops_count_file"] = False
     return graph_instance(config, device=device)
 
 

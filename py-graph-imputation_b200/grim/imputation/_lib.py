@@ -47,6 +47,7 @@ class Config(C.Structure):
         ("n_rows", C.c_int32),
         ("row_blocks", C.c_int32 * MAX_ROWS), ("block_mask", (C.c_uint16 * MAX_BLOCKS) * MAX_ROWS),
         ("row_is_plan_a", C.c_uint8 * MAX_ROWS),
+        ("hap_pop_pair", C.c_int32), ("em", C.c_int32),
     ]
 
 
@@ -55,6 +56,7 @@ class Batch(C.Structure):
         ("n_subjects", C.c_int64), ("typed_mask", C.c_void_p), ("counts", C.c_void_p),
         ("allele_off", C.c_void_p), ("alleles", C.c_void_p), ("n_alleles_total", C.c_int64),
         ("prior_index", C.c_void_p), ("priors", C.c_void_p), ("n_priors", C.c_int32),
+        ("phase_mask", C.c_void_p),
     ]
 
 
@@ -151,7 +153,7 @@ def load(kw=1):
     lib.grimb_text_format.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Results), C.POINTER(TextOut)]
     lib.grimb_impute_text.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(Config), C.c_char_p,
                                       C.c_int64, C.c_int64, C.POINTER(TextOut)]
-    if lib.grimb_abi_version() != 2:
+    if lib.grimb_abi_version() != 3:
         raise RuntimeError("libgrimb200.so ABI mismatch")
     _LIB[kw] = lib
     return lib

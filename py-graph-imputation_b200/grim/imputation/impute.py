@@ -95,6 +95,14 @@ class Imputation(object):
         self._prior_index = {}
         self._priors = []
         self._backend = self._run_gpu
+        # per-subject phase masks (bin_imputation_in_file; impute.py:2001-2005 of the reference)
+        self.phase_masks = None
+        bin_path = config.get("bin_imputation_input_file", "None")
+        if bin_path and os.path.isfile(bin_path):
+            import json
+            with open(bin_path) as f:
+                self.phase_masks = json.load(f)
+        self._em_mr = False
         self.stats = {"subjects": 0, "pair_evals": 0, "plan": {0: 0, 1: 0, 2: 0, 3: 0}, "workspace_retries": 0}
 
     # ------------------------------------------------------------------ prior matrices
@@ -246,15 +254,17 @@ class Imputation(object):
         return lib.grimb_impute_host(eng, C.byref(cfg), C.byref(batch), C.byref(res))
 
     def _run_batch(self, enc, workspace):
-        """enc: list of (mask, counts, flat ids, prior index).  -> dict of numpy result arrays."""
+        """enc: list of (mask, counts, flat ids, prior index, phase mask).  -> dict of numpy result arrays."""
         S, L = len(enc), self.L
         typed = np.zeros(S, np.uint16)
         counts = np.zeros((S, L, 2), np.uint16)
         off = np.zeros(S + 1, np.uint32)
         pri = np.zeros(S, np.uint32)
+        pmask = np.zeros(S, np.uint16)
         flat = []
-        for s, (mask, cn, ids, p) in enumerate(enc):
+        for s, (mask, cn, ids, p, pm) in enumerate(enc):
             typed[s] = mask
+            pmask[s] = pm
             if mask:
                 counts[s] = cn
                 flat.extend(ids)
@@ -267,9 +277,12 @@ class Imputation(object):
         b.typed_mask, b.counts, b.allele_off = typed.ctypes.data, counts.ctypes.data, off.ctypes.data
         b.alleles, b.n_alleles_total = alle.ctypes.data, int(off[S])
         b.prior_index, b.priors, b.n_priors = pri.ctypes.data, priors.ctypes.data, priors.shape[0]
+        b.phase_mask = pmask.ctypes.data if self.phase_masks is not None else None
         subj = np.zeros(S, dtype=_lib.SUBJECT_DTYPE)
         hap_cap = max(1024, S * 2 * min(self.cfg.n_results, 16))
         pop_cap = max(1024, S * 2 * min(self.cfg.n_pop_results, 4))
+        if self._em_mr:
+            pop_cap += S * min(self.cfg.n_results, 16)
         needed = np.zeros(2, np.int64)
         while True:
             hap_rows = np.zeros(hap_cap, dtype=_lib.hap_row_dtype(self.netGraph.kw))
@@ -327,6 +340,13 @@ class Imputation(object):
                 row = hr[ho + nu + k]
                 h1 = "~".join(x for x in self._decode(row["a"], unknown) if x is not None)
                 h2 = "~".join(x for x in self._decode(row["b"], unknown) if x is not None)
+                if self._em_mr:
+                    # write_best_hap_race_pairs (impute.py:79-99): "hap;pop,hap;pop"; the populations of PMUG
+                    # row k are the companion row after the regular population rows
+                    pp = pr[po + nup + npp + k]
+                    rows.append(sid + "," + h1 + ";" + self._pop_name(int(pp["pa"])) + "," + h2 + ";"
+                                + self._pop_name(int(pp["pb"])) + "," + str(float(row["prob"])) + "," + str(k) + "\n")
+                    continue
                 rows.append(sid + "," + h1 + "+" + h2 + "," + str(float(row["prob"])) + "," + str(k) + "\n")
             rows = files["pmug_pops"]
             for k in range(npp):
@@ -352,8 +372,13 @@ class Imputation(object):
                 rows.append(sid + "," + names[0] + "," + names[1] + "," + prob + "," + str(k) + "\n")
 
     # ------------------------------------------------------------------ public entry points
-    def impute_lines(self, lines, first_index=0):
-        """Imputes an iterable of input lines; returns the six output texts as lists of rows."""
+    def impute_lines(self, lines, first_index=0, em_mr=False, em=False):
+        """Imputes an iterable of input lines; returns the six output texts as lists of rows.
+        em_mr: the hap_pop_pair output mode of grim.grim.impute (impute.py:2079-2088); em: no Plan C for
+        the haplotype output (impute.py:1648)."""
+        self._em_mr = bool(em_mr)
+        self.cfg.hap_pop_pair = 1 if em_mr else 0
+        self.cfg.em = 1 if em else 0
         files = {k: [] for k in ("umug", "umug_pops", "pmug", "pmug_pops", "miss", "problem")}
         pending = []
         for i, raw in enumerate(lines, first_index):
@@ -373,8 +398,18 @@ class Imputation(object):
             raw = raw.rstrip()
             fields = raw.split(",") if "," in raw else raw.split("%")
             sid = fields[0]
-            hclass, unknown, item = H_OK, None, (0, None, None, 0)
-            if len(fields) < 2 or len(fields) == 3:
+            hclass, unknown, item = H_OK, None, (0, None, None, 0, 0xFFFF)
+            pm = 0xFFFF
+            if self.phase_masks is not None and len(fields) >= 2:
+                bits = self.phase_masks.get(sid)
+                if bits is None:
+                    hclass = H_FAULT                   # KeyError f_bin[subject_id] -> raw line in .problem
+                else:
+                    pm = 0
+                    for m, e in enumerate(bits):
+                        if e == 1 and m < 16:
+                            pm |= 1 << m
+            if len(fields) < 2 or len(fields) == 3 or hclass == H_FAULT:
                 hclass = H_FAULT                       # IndexError in the reference's line parser
             else:
                 gl = fields[1]
@@ -388,7 +423,7 @@ class Imputation(object):
                     hclass, payload = self._encode_gl(gl)
                     if hclass == H_OK and payload != "foreign":
                         mask, counts, flat, unknown = payload
-                        item = (mask, counts, flat, pidx)
+                        item = (mask, counts, flat, pidx, pm)
             meta.append((i, sid, raw, hclass, unknown))
             enc.append(item)
         # per-CTA workspace tiers: subjects that overflow one tier are re-issued on the next
@@ -433,6 +468,73 @@ class Imputation(object):
             if pm_empty and tot_u == 0:
                 files["miss"].append(str(i) + "," + str(sid) + "\n")
             self._format_subject(sid, r, k, unknown, files)
+
+    # ------------------------------------------------------------------ EM helpers (host only)
+    # open_gl_string / open_phases_for_em (impute.py:305-351 of the reference) are list-building
+    # utilities the EM driver calls around imputation; they involve no frequency lookup, so they are
+    # plain host code here as well.  Same return structure: [[ [opened haplotypes of side 1] ],
+    # [ [opened haplotypes of side 2] ]] per phase, each haplotype a list of allele names.
+    @staticmethod
+    def _gl2haps_names(gl_string):
+        if gl_string == "" or gl_string == " ":
+            return []
+        t1, t2, n = [], [], 0
+        for chunk in gl_string.split("^"):
+            if chunk[0] == "+":
+                chunk = chunk[1:]
+            cur = chunk.split("+")
+            if len(cur) == 1:
+                if cur == [""]:
+                    continue
+                return []
+            t1.append(cur[0])
+            t2.append(cur[1])
+            n += 1
+        return {"Genotype": [sorted(t1), sorted(t2)], "N_Loc": n}
+
+    @staticmethod
+    def gen_phases(gen, n_loci, b_phases=None):
+        """Host restatement of the phase enumeration the kernels perform (names instead of ids)."""
+        allowed = None if b_phases is None else {i for i, e in enumerate(b_phases) if e == 1}
+        out, seen = [], set()
+        for i in range(2 ** (n_loci - 1)):
+            pick = [(i >> m) & 1 if (allowed is None or m in allowed) else 0 for m in range(n_loci)]
+            h1 = [gen[pick[k]][k] for k in range(n_loci)]
+            h2 = [gen[1 - pick[k]][k] for k in range(n_loci)]
+            a, b = "~".join(h1) + "^" + "~".join(h2), "~".join(h2) + "^" + "~".join(h1)
+            if a not in seen or b not in seen:
+                seen.add(a)
+                seen.add(b)
+                out.append([h1, h2])
+        return out
+
+    def open_gl_string(self, gl_string, cutoff):
+        chrom = self._gl2haps_names(gl_string)
+        if chrom == []:
+            return None
+        phases = self.gen_phases(chrom["Genotype"], chrom["N_Loc"], None)
+        if phases == []:
+            return None
+        return self.open_phases_for_em(phases, chrom["N_Loc"], cutoff)
+
+    def open_phases_for_em(self, haps, N_Loc, cutoff):
+        import itertools
+        phases = []
+        for pair in haps:
+            sides = []
+            for k in range(2):
+                splits = [tuple(a.split("/")) for a in pair[k]]
+                options = 1
+                for i in range(N_Loc):
+                    options *= len(splits[i])
+                if options < cutoff:
+                    # Cartesian product, first locus slowest (cutils.open_ambiguities order)
+                    sides.append([[list(c) for c in itertools.product(*splits[:N_Loc])]])
+                else:
+                    sides.append([])
+            if sides[0] and sides[1]:
+                phases.append([sides[0], sides[1]])
+        return phases
 
     # ------------------------------------------------------------------ native text pipeline
     def _text_handle(self):
@@ -510,14 +612,16 @@ class Imputation(object):
     def impute_file(self, config, planb=None, em_mr=False, em=False):
         """Reads config["imputation_input_file"], writes the six output files
         (impute.py:1985-2155 of the reference)."""
-        if em_mr or em:
-            raise NotImplementedError("EM output modes are outside the B200 hot path (SURVEY 8f-4)")
-        if os.path.isfile(config.get("bin_imputation_input_file", "None")):
-            raise NotImplementedError("per-subject phase masks are outside the B200 hot path (SURVEY 8f-4)")
         if planb is not None and bool(planb) != bool(config["planb"]):
             self.cfg.planb = 1 if planb else 0
         targets = {"miss": "imputation_out_miss_file", "problem": "imputation_out_problem_file"}
-        if os.environ.get("GRIMB_PY_HOST") != "1":
+        # the EM-facing modes (hap_pop_pair rows, em, per-subject phase masks) go through the numpy
+        # host front end; the C++ text pipeline serves the default mode
+        special = bool(em_mr or em or self.phase_masks is not None)
+        self._em_mr = False
+        self.cfg.hap_pop_pair = 0
+        self.cfg.em = 0
+        if os.environ.get("GRIMB_PY_HOST") != "1" and not special:
             # native host pipeline: C++ tokeniser / formatter around the kernels (grimb_impute_text)
             if config["output_MUUG"]:
                 targets["umug"] = "imputation_out_umug_freq_file"
@@ -537,7 +641,7 @@ class Imputation(object):
                     fo.close()
             return
         with open(config["imputation_input_file"]) as f:
-            files = self.impute_lines(f)
+            files = self.impute_lines(f, em_mr=em_mr, em=em)
         if config["output_MUUG"]:
             targets["umug"] = "imputation_out_umug_freq_file"
             targets["umug_pops"] = "imputation_out_umug_pops_file"

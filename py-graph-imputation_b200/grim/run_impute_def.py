@@ -122,8 +122,6 @@ def _run_impute_sharded(dist, config, hap_pop_pair, graph):
     lines sharded by contiguous ranges, rank 0 writes the six files in input order."""
     import os
     from .imputation import multi_gpu
-    if hap_pop_pair:
-        raise NotImplementedError("EM output modes are outside the B200 hot path (SURVEY 8f-4)")
     rank, world = dist.get_rank(), dist.get_world_size()
     device = int(os.environ.get("LOCAL_RANK", rank))
     if graph is None:
@@ -135,7 +133,12 @@ def _run_impute_sharded(dist, config, hap_pop_pair, graph):
     with open(config["imputation_input_file"], "rb") as f:
         lines = f.readlines()
     lo, hi = multi_gpu.shard_range(len(lines), rank, world)
-    mine = imputation.impute_text(b"".join(lines[lo:hi]), first_index=lo)
+    if hap_pop_pair or imputation.phase_masks is not None:
+        # EM-facing modes go through the numpy host front end (see Imputation.impute_file)
+        rows = imputation.impute_lines([l.decode("utf8") for l in lines[lo:hi]], first_index=lo, em_mr=hap_pop_pair)
+        mine = {k: "".join(v).encode("utf8") for k, v in rows.items()}
+    else:
+        mine = imputation.impute_text(b"".join(lines[lo:hi]), first_index=lo)
     parts = [None] * world if rank == 0 else None
     dist.gather_object(mine, parts, dst=0)
     if rank == 0:

@@ -209,16 +209,45 @@ def main():
          synth.typed_subjects(tab9, 8, 1, ["AAA,BBB", ",", "AAA;BBB,XXX"])
          + synth.messy_subjects(tab9, 14, 2, max_amb=2, p_missing=0.3, races=["AAA,BBB", ","])),
     ]
+    # per-subject phase masks (bin_imputation_in_file) and the hap_pop_pair output mode
+    import numpy as np
+    rng = np.random.RandomState(77)
+    mask_lines = synth.typed_subjects(tab3, 40, 71, races3) + synth.messy_subjects(tab3, 40, 72, max_amb=3, races=races3)
+    masks = {}
+    for ln in mask_lines:
+        sid = ln.split(",")[0]
+        masks[sid] = [int(x) for x in rng.randint(0, 2, size=4)]
+    masks[mask_lines[0].split(",")[0]] = [1, 1, 1, 1]
+    masks[mask_lines[1].split(",")[0]] = [0, 0, 0, 0]
+    del masks[mask_lines[2].split(",")[0]]          # unknown subject id: KeyError -> raw line in .problem
+    extra = {
+        "g7_phase_masks": {"phase_masks": masks},
+        "g7_hap_pop_pair": {"hap_pop_pair": True},
+        "g7_hap_pop_pair_cau": {"hap_pop_pair": True},
+    }
+    cases += [
+        ("g7_phase_masks", "pop3", {}, mask_lines),
+        ("g7_hap_pop_pair", "pop3", {"number_of_results": 7},
+         synth.typed_subjects(tab3, 40, 73, races3) + synth.messy_subjects(tab3, 50, 74, races=races3)),
+        ("g7_hap_pop_pair_cau", "cau", {}, edge_lines(tab) + synth.messy_subjects(tab, 40, 75)),
+    ]
     for name, table, over, lines in cases:
         if only and name not in only:
             continue
-        res = sessions[table].run(lines, **over)
+        run_kw = extra.get(name, {})
+        res = sessions[table].run(lines, **run_kw, **over)
         d = os.path.join(CASES, name)
         shutil.rmtree(d, ignore_errors=True)
         os.makedirs(d)
         o = dict(base_over[table])
         o.update(over)
-        json.dump({"table": table, "overrides": o}, open(os.path.join(d, "case.json"), "w"), indent=1)
+        meta = {"table": table, "overrides": o}
+        if run_kw.get("hap_pop_pair"):
+            meta["hap_pop_pair"] = True
+        if run_kw.get("phase_masks") is not None:
+            json.dump(run_kw["phase_masks"], open(os.path.join(d, "phase_masks.json"), "w"))
+            meta["phase_masks"] = "phase_masks.json"
+        json.dump(meta, open(os.path.join(d, "case.json"), "w"), indent=1)
         open(os.path.join(d, "subjects.csv"), "w").writelines(lines)
         for k, v in res.items():
             open(os.path.join(d, "exp." + k), "w").write(v)

@@ -76,10 +76,16 @@ class RefSession:
         with open(self.conf_path, "w") as f:
             json.dump(self.conf, f)
 
-    def run(self, subject_lines, **overrides):
-        """subject_lines: list of str (with newlines).  overrides: config keys for this run."""
+    def run(self, subject_lines, hap_pop_pair=False, phase_masks=None, **overrides):
+        """subject_lines: list of str (with newlines).  overrides: config keys for this run.
+        hap_pop_pair: grim.impute(hap_pop_pair=True); phase_masks: {subject id: [0/1, ...]} written
+        as the bin_imputation_in_file JSON."""
         saved = dict(self.conf)
         self.conf.update(overrides)
+        if phase_masks is not None:
+            self.conf["bin_imputation_in_file"] = os.path.join(self.dir, "phase_masks.json")
+            with open(self.conf["bin_imputation_in_file"], "w") as f:
+                json.dump(phase_masks, f)
         self._write_conf()
         with open(self.conf["imputation_in_file"], "w") as f:
             f.writelines(subject_lines)
@@ -89,7 +95,7 @@ class RefSession:
         os.chdir(self.dir)  # full_path() makes outputs relative to cwd
         try:
             with contextlib.redirect_stdout(io.StringIO()):
-                self.graph = self.ref_grim.impute(conf_file=self.conf_path, graph=self.graph)
+                self.graph = self.ref_grim.impute(conf_file=self.conf_path, hap_pop_pair=hap_pop_pair, graph=self.graph)
         finally:
             os.chdir(cwd)
         res = {}

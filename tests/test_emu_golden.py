@@ -25,7 +25,7 @@ def run_case(name):
     og, eg = _setup(table, conf)
     cfg = load_config(conf)
     imp = emu_imputation(eg, cfg)
-    files = imp.impute_lines(lines)
+    files = imp.impute_lines(lines, em_mr=conf["_hap_pop_pair"])
     return {k: "".join(v) for k, v in files.items()}, exp
 
 

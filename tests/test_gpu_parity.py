@@ -35,7 +35,7 @@ def _run_gpu(table, conf, lines):
     from grim.run_impute_def import load_config
     cfg = load_config(conf)
     imp = Imputation(_graph(table, conf), cfg)
-    files = imp.impute_lines(lines)
+    files = imp.impute_lines(lines, em_mr=conf.get("_hap_pop_pair", False))
     return {k: "".join(v) for k, v in files.items()}, imp
 
 
@@ -142,7 +142,7 @@ def test_full_size_properties():
     assert imp2_out["umug"] == "".join(x + "\n" for x in rows[:5000])
 
 
-@pytest.mark.parametrize("name", goldenlib.case_names())
+@pytest.mark.parametrize("name", goldenlib.text_case_names())
 def test_native_text_path_matches_reference_files(name):
     """Same cases through grimb_impute_text (C++ tokeniser / formatter around the kernels)."""
     from grim.imputation.impute import Imputation

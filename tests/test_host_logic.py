@@ -105,3 +105,17 @@ def test_config_defaults_match_reference():
     assert cfg["factor_missing_data"] == 0.01 and cfg["number_of_options_threshold"] == 100000
     assert cfg["max_haplotypes_number_in_phase"] == 100 and cfg["UNK_priors"] == "MR" and cfg["save_mode"] is False
     assert len(cfg["matrix_planb"]) == 6 and cfg["full_loci"] == "12345"
+
+
+def test_open_gl_string_matches_reference_fixture():
+    """EM helper: Imputation.open_gl_string vs the fixture written by the unmodified
+    reference (tests/golden/make_open_gl.py)."""
+    import json
+    import os
+    import goldenlib
+    from grim.imputation.impute import Imputation
+    imp = object.__new__(Imputation)          # host-only helper: needs no tables
+    cases = json.load(open(os.path.join(goldenlib.GOLD, "data", "open_gl_string.json")))
+    assert len(cases) >= 7
+    for c in cases:
+        assert imp.open_gl_string(c["gl"], c["cutoff"]) == c["phases"], c["gl"]

@@ -17,7 +17,7 @@ def _graph(table, conf):
 @pytest.mark.parametrize("name", goldenlib.case_names())
 def test_oracle_matches_reference_files(name):
     table, conf, lines, exp = goldenlib.load_case(name)
-    out, _ = go.impute_file(conf, graph=_graph(table, conf), lines=lines)
+    out, _ = go.impute_file(conf, graph=_graph(table, conf), lines=lines, em_mr=conf["_hap_pop_pair"])
     for k in goldenlib.KEYS:
         assert out[k] == exp[k], "%s: %s differs" % (name, k)
 

@@ -24,7 +24,7 @@ def _setup(table, conf):
     return _cache[table]
 
 
-@pytest.mark.parametrize("name", goldenlib.case_names())
+@pytest.mark.parametrize("name", goldenlib.text_case_names())
 def test_native_tokeniser_and_formatter_match_reference_files(name):
     table, conf, lines, exp = goldenlib.load_case(name)
     eg = _setup(table, conf)
