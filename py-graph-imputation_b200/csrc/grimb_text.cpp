@@ -655,6 +655,7 @@ extern "C" int grimb_text_tokenise(GrimbText* t, const GrimbConfig* cfg, const c
   b->prior_index = t->b_prior.data();
   b->priors = t->priors.data();
   b->n_priors = (int32_t)(t->priors.size() / ((size_t)t->P * t->P));
+  b->phase_mask = nullptr;   // default phase enumeration; masks are served by the numpy host front end
   return GRIMB_OK;
 }
 
