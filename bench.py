@@ -276,11 +276,7 @@ def main():
         dist.broadcast(img, 0)
         torch.cuda.synchronize()
         if rank != 0:
-            g.alleles = names
-            g.allele_id = [{a: i + 1 for i, a in enumerate(al)} for al in names]
-            from grim.imputation.networkx_graph import key_layout
-            g.key_bits = key_layout([len(a) for a in names])
-            g.shift = [int(sum(g.key_bits[:l])) for l in range(5)]
+            g._set_dictionaries(names)
             h = C.c_void_p()
             _lib.check(lib.grimb_tables_from_image(C.c_void_p(img.data_ptr()), nb, local, C.byref(h)), "from_image")
             g.handle = h
@@ -438,7 +434,7 @@ def main():
         achieved = algo / (ms_kernel * 1e-3) / 1e9
         traffic = None   # DRAM bytes per launch from the committed ncu --set full capture of this kernel
         try:
-            txt = open(os.path.join(ROOT, "profiles", "r01_ncu_summary_k_impute_fast_v4.txt")).read().splitlines()
+            txt = open(os.path.join(ROOT, "profiles", "r01_ncu_summary_k_impute_fast_v5.txt")).read().splitlines()
             rd = [l for l in txt if l.startswith("dram__bytes_read.sum")][0].split()
             wr = [l for l in txt if l.startswith("dram__bytes_write.sum")][0].split()
             unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
