@@ -1147,12 +1147,15 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
 //               shared memory (within one h step the pairs are distinct, so lanes add in parallel and
 //               steps are sequential: the reference's += order)
 // Subjects of any other shape -- or with more than TY_VP phases whose two haplotypes are both in
-// the table, or for which Plan A finds nothing -- go to `worklist` for k_impute.  There is no
-// geno_seen de-duplication to do: distinct kept phases of a heterozygous subject are distinct
-// unordered haplotype pairs.
+// the table, or for which Plan A finds nothing -- go to `worklist` for k_impute.  geno_seen
+// de-duplication only matters for a fully homozygous subject (one phase, both haplotypes equal):
+// distinct kept phases of a heterozygous subject are distinct unordered haplotype pairs.
 // ------------------------------------------------------------------------------------------
 constexpr int TY_WARPS = 8;
 constexpr int TY_VP = 4;
+#ifndef TY_MIN_BLOCKS
+#define TY_MIN_BLOCKS 3
+#endif
 constexpr int TY_MAX_ROUNDS = 40;
 
 struct __align__(16) TyLists {
@@ -1171,7 +1174,7 @@ static inline size_t ty_bytes_per_warp(int P) {
   return (sizeof(TyLists) + G * 12 + 15) & ~(size_t)15;
 }
 
-__global__ void __launch_bounds__(TY_WARPS * 32)
+__global__ void __launch_bounds__(TY_WARPS * 32, TY_MIN_BLOCKS)
 k_impute_typed(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O, uint32_t* worklist,
                unsigned int* worklist_n, uint32_t per_warp) {
   extern __shared__ __align__(16) unsigned char ty_smem[];
@@ -1238,8 +1241,11 @@ k_impute_typed(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, 
           if (a0 != a1) het |= 1u << l;
         }
       }
-      if (het == 0) shape = false;   // both haplotypes equal: the general kernel's geno_seen path
     }
+    // het == 0: one phase whose two haplotypes are equal.  Its two side lists are identical, pair
+    // (h, k) and pair (k, h) are the same unordered {(hap,pop),(hap,pop)} and geno_seen keeps the
+    // first one met (impute.py:508-513); equal haplotypes are not doubled and need m*f2 >= 2x.
+    const bool same = het == 0;
     int nvp = 0;
     bool punt = !shape;
     const double* M = B.priors + (uint64_t)B.prior_index[s] * P * P;
@@ -1343,11 +1349,19 @@ k_impute_typed(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, 
             evals += cnt < n2 ? cnt + 1 : n2;
             if (reach) {
               const double m = __ldg(M + (uint32_t)W.p1s[vp][h] * P + p2);
-              if (m > 0 && m * f2 >= x) {
-                any = true;
-                double pr = W.f1s[vp][h] * f2 * m;
-                pr = pr * 2;
-                if (pr > lmx) lmx = pr;
+              if (m > 0 && m * f2 >= (same ? x * 2 : x)) {
+                bool dup = false;
+                if (same && lane < h) {   // the mirror pair (k, h) comes first: accepted -> this one is a duplicate
+                  const double xk = W.xs[lane];
+                  const double mk = __ldg(M + p2 * P + (uint32_t)W.p1s[vp][h]);
+                  dup = W.pm2[vp][h] >= xk && mk > 0 && mk * W.f2s[vp][h] >= xk * 2;
+                }
+                if (!dup) {
+                  any = true;
+                  double pr = W.f1s[vp][h] * f2 * m;
+                  if (!same) pr = pr * 2;
+                  if (pr > lmx) lmx = pr;
+                }
               }
             }
           }
@@ -1397,10 +1411,18 @@ k_impute_typed(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, 
           double pr = 0.0;
           if (reach) {
             const double m = __ldg(M + p1 * P + p2);
-            if (m > 0 && m * f2 >= x) {
-              a = true;
-              pr = W.f1s[vp][h] * f2 * m;
-              pr = pr * 2;
+            if (m > 0 && m * f2 >= (same ? x * 2 : x)) {
+              bool dup = false;
+              if (same && lane < h) {
+                const double xk = W.xs[lane];
+                const double mk = __ldg(M + p2 * P + p1);
+                dup = W.pm2[vp][h] >= xk && mk > 0 && mk * W.f2s[vp][h] >= xk * 2;
+              }
+              if (!dup) {
+                a = true;
+                pr = W.f1s[vp][h] * f2 * m;
+                if (!same) pr = pr * 2;
+              }
             }
           }
           const uint32_t A = __ballot_sync(FULLM, a);
@@ -1509,21 +1531,34 @@ k_impute_typed(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, 
     __syncwarp();
     if ((int64_t)(pb + npop) <= R.pop_capacity && npg) {
       // population rows by (sum desc, first encounter asc); same rows for both output kinds
-      for (uint32_t t = lane; t < ng; t += 32) {
-        const double vt = gsum[t];
-        uint32_t rank = 0;
+      // each lane ranks up to 4 groups per sweep over the list (one shared-memory read per comparand)
+      for (uint32_t t0 = lane; t0 < ng; t0 += 128) {
+        double vt[4];
+        uint32_t rk[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t t = t0 + 32u * q;
+          vt[q] = t < ng ? gsum[t] : 0.0;
+          rk[q] = 0;
+        }
         for (uint32_t u = 0; u < ng; ++u) {
           const double vu = gsum[u];
-          if (vu > vt || (vu == vt && u < t)) ++rank;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (vu > vt[q] || (vu == vt[q] && u < t0 + 32u * q)) ++rk[q];
         }
-        if (rank < npg) {
-          GrimbPopRow o;
-          o.pop_a = (uint16_t)(gpair[t] >> 8);
-          o.pop_b = (uint16_t)(gpair[t] & 0xffu);
-          o.pad = 0;
-          o.prob = vt;
-          if (nup) R.pop_rows[pb + rank] = o;
-          if (npp) R.pop_rows[pb + nup + rank] = o;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t t = t0 + 32u * q;
+          if (t < ng && rk[q] < npg) {
+            GrimbPopRow o;
+            o.pop_a = (uint16_t)(gpair[t] >> 8);
+            o.pop_b = (uint16_t)(gpair[t] & 0xffu);
+            o.pad = 0;
+            o.prob = vt[q];
+            if (nup) R.pop_rows[pb + rk[q]] = o;
+            if (npp) R.pop_rows[pb + nup + rk[q]] = o;
+          }
         }
       }
     }

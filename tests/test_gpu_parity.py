@@ -187,3 +187,27 @@ def test_native_text_path_large_batch_equals_python_host_path():
     out_native = imp.impute_text("".join(lines).encode("utf8"))
     for k in goldenlib.KEYS:
         assert out_native[k].decode("utf8") == out_py[k], k
+
+
+def test_homozygous_subjects_multi_population_match_oracle():
+    """Both haplotypes equal: one phase, identical side lists, geno_seen drops the mirrored
+    (population-swapped) pair (impute.py:508-513) -- the typed warp kernel's `same` path."""
+    _, conf, _, _ = goldenlib.load_case("g3_pop3_typed")
+    pops = conf["populations"]
+    tab = synth.Table(open(conf["freq_file"]).read(), pops[0])
+    races = synth.race_fields(pops)
+    rng = np.random.RandomState(5)
+    lines = []
+    for s in range(400):
+        h = tab.haps[int(rng.choice(len(tab.haps), p=tab.p))]
+        g = list(h)
+        if s % 3 == 1:      # one heterozygous locus for contrast
+            g2 = list(tab.haps[int(rng.choice(len(tab.haps), p=tab.p))])
+            gl = "^".join("%s+%s" % (a, b if l == 2 else a) for l, (a, b) in enumerate(zip(g, g2)))
+        else:
+            gl = "^".join("%s+%s" % (a, a) for a in g)
+        lines.append("H%d,%s,%s\n" % (s, gl, races[s % len(races)]))
+    out, imp = _run_gpu("pop3", conf, lines)
+    ref, _ = go.impute_file(conf, graph=_oracle_graph("pop3", conf), lines=lines)
+    for k in goldenlib.KEYS:
+        assert out[k] == ref[k], "%s differs" % k
