@@ -153,6 +153,54 @@ def messy_subjects(table, n, seed, max_amb=4, p_missing=0.25, p_unknown=0.05, p_
     return out
 
 
+def heavy_subjects(table, n, seed, sizes=(6, 12, 20, 40), p_missing=(0.4, 0.3, 0.2, 0.1), p_unknown=0.05,
+                   races=None, prefix="H"):
+    """Highly ambiguous subjects: every locus side lists a_l alleles drawn from
+    `sizes` -- the true allele, then alleles sharing its 2-digit family (serology / MAC-like
+    groups), then random ones -- so the product of the list sizes straddles the 100,000-option
+    threshold; 0-3 loci are missing (probabilities p_missing) and p_unknown of the listed
+    alleles are names absent from the table."""
+    rng = np.random.RandomState(seed)
+    nl = len(table.loci)
+    fam = []
+    for l in range(nl):
+        d = {}
+        for a in table.alleles[l]:
+            d.setdefault(a.split(":")[0], []).append(a)
+        fam.append(d)
+    out = []
+    for s in range(n):
+        i1, i2 = rng.choice(len(table.haps), size=2, p=table.p)
+        hh = (table.haps[i1], table.haps[i2])
+        n_miss = int(rng.choice(len(p_missing), p=p_missing))
+        drop = set(rng.choice(nl, size=min(n_miss, nl - 1), replace=False).tolist()) if n_miss else set()
+        sides = []
+        for l in range(nl):
+            if l in drop:
+                continue
+            pair = []
+            for h in hh:
+                want = int(sizes[rng.randint(len(sizes))])
+                lst = [h[l]]
+                pool = [a for a in fam[l][h[l].split(":")[0]] if a != h[l]]
+                rng.shuffle(pool)
+                lst.extend(pool[: want - 1])
+                while len(lst) < min(want, len(table.alleles[l])):
+                    b = table.alleles[l][rng.randint(len(table.alleles[l]))]
+                    if b not in lst:
+                        lst.append(b)
+                lst = [("%s*99:%02d" % (table.loci[l], rng.randint(1, 9)) if rng.rand() < p_unknown else a) for a in lst]
+                lst = list(dict.fromkeys(lst))
+                rng.shuffle(lst)
+                pair.append(lst)
+            sides.append((pair[0], pair[1]))
+        line = "%s%d,%s" % (prefix, s, _gl(sides))
+        if races is not None:
+            line += "," + races[rng.randint(len(races))]
+        out.append(line + "\n")
+    return out
+
+
 def race_fields(pops):
     """A small cycle of race1,race2 field shapes: both known, one ';' list,
     unknown code, empty."""

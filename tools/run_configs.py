@@ -121,7 +121,23 @@ def c5(tmp, scale):
     run("C5_nine_loci_typed", c, hpf, cnt, lines, 200, tmp, oracle_marginals=False)
 
 
+def c4_heavy(tmp, scale):
+    """C4 proper: list sizes 6-40 per locus side, products on both sides of the 100,000-option
+    threshold, 0-3 missing loci, unknown alleles, the full 6-row Plan-B matrix."""
+    base = json.load(open(os.path.join(goldenlib.GOLD, "data", "base_conf.json")))
+    cau = open(os.path.join(goldenlib.GOLD, "data", "cau_hpf.csv")).read()
+    cau_cnt = open(os.path.join(goldenlib.GOLD, "data", "cau_pop_counts.txt")).read()
+    tab = synth.Table(cau)
+    n = int(float(os.environ.get("C4_SUBJECTS", "2000")) * scale)
+    lines = synth.heavy_subjects(tab, n, 44, races=["CAU,CAU"])
+    run("C4_heavy_over_threshold", base, cau, cau_cnt, lines, int(os.environ.get("C4_SAMPLE", "3")), tmp)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "c4heavy":
+        import tempfile
+        c4_heavy(tempfile.mkdtemp(), float(os.environ.get("CONFIG_SCALE", "1")))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "c5":
         import tempfile
         c5(tempfile.mkdtemp(), float(os.environ.get("CONFIG_SCALE", "1")))
