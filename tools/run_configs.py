@@ -56,12 +56,17 @@ def run(name, conf, hpf_text, counts_text, lines, sample, tmp, oracle_marginals=
         only_a = imp.stats["plan"]
         assert only_a[2] == 0 and only_a[3] == 0, "sample left Plan A: %s" % only_a
     info = g.info()
+    eng = g.engine(imp.workspaces[0])
+    kms = [g.lib.grimb_engine_kernel_ms(eng, w) for w in (0, 1, 2, 3)]
     rec = {
         "config": name, "subjects": len(lines), "gpu_subjects_per_s": len(lines) / dt,
         "gpu_abi_seconds": imp.stats.get("abi_seconds"), "gpu_total_seconds": dt,
         "tokenise_seconds": imp.stats.get("tokenise_seconds"), "format_seconds": imp.stats.get("format_seconds"),
         "pair_evals": imp.stats["pair_evals"], "plans": imp.stats["plan"],
         "workspace_retries": imp.stats["workspace_retries"],
+        # device time of the kernels of the LAST ABI call of the first workspace tier (the sample run)
+        "last_call_kernel_ms": {"k_impute_fast": kms[0], "k_impute": kms[1], "k_impute_typed": kms[2],
+                                "subjects_handed_to_k_impute": kms[3], "subjects": sample},
         "cpu_port_subjects_per_s_1core": sample / t_cpu, "cpu_sample": sample,
         "parity_identical_on_sample": all(mine[k] == ref[k] for k in ref),
         "rows": {k: len(v) for k, v in out.items()},
