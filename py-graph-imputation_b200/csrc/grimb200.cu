@@ -481,9 +481,14 @@ extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
     }
     uint64_t so = 0;
     for (uint32_t m = 0; m < NL; ++m) {
-      // load factor <= 0.5; <= 0.25 for the full-haplotype label, which takes the bulk of the
+      // load factor <= 0.5; <= 0.125 for the full-haplotype label, which takes the bulk of the
       // probes (2^L per fully typed subject, mostly misses: a miss scans until an empty slot)
-      const uint64_t want = (m == NL - 1 ? 4ull : 2ull) * (uint64_t)lcount[m];
+      uint64_t full_mult = 8;   // slots per full haplotype (GRIMB_FULL_LOAD_MULT overrides, for A/B runs)
+      if (const char* fm = getenv("GRIMB_FULL_LOAD_MULT")) {
+        const long v = atol(fm);
+        if (v >= 2 && v <= 64) full_mult = (uint64_t)v;
+      }
+      const uint64_t want = (m == NL - 1 ? full_mult : 2ull) * (uint64_t)lcount[m];
       uint32_t sz = 2;
       while (sz < want) sz <<= 1;
       hmask[m] = sz - 1;
