@@ -212,7 +212,8 @@ int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* 
 int64_t grimb_engine_launches(const GrimbEngine* e);
 /* Device time in ms (CUDA events on the launching stream) of the last k_impute_fast (which = 0),
  * k_impute (which = 1) or k_impute_typed (which = 2) launch of this engine; negative if that kernel
- * was not launched. */
+ * was not launched.  which = 3 (diagnostic): number of subjects the warp-per-subject kernels of the
+ * last call handed on to k_impute. */
 double grimb_engine_kernel_ms(const GrimbEngine* e, int which);
 
 /* ------------------------------------------------------------------------------------------

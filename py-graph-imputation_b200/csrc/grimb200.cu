@@ -1722,62 +1722,62 @@ static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBat
   if (batch->n_subjects <= 0) return GRIMB_OK;
   // the warp-per-subject kernels implement the default phase enumeration and row layout only
   const bool warp_kernels = e->fast_path && !batch->phase_mask && !cfg->hap_pop_pair;
-    const TablesView& tv = e->tables->view;
-    const uint32_t* wl = nullptr;
-    const unsigned int* wl_n = nullptr;
-    const uint64_t stride = (uint64_t)batch->n_subjects;
-    CK(e->buckets.reserve((size_t)stride * 4 * GRIMB_BUCKETS + 16));
-    unsigned int* bucket_n = (unsigned int*)(e->d_counters + 4);
+  const TablesView& tv = e->tables->view;
+  const uint32_t* wl = nullptr;
+  const unsigned int* wl_n = nullptr;
+  const uint64_t stride = (uint64_t)batch->n_subjects;
+  CK(e->buckets.reserve((size_t)stride * 4 * GRIMB_BUCKETS + 16));
+  unsigned int* bucket_n = (unsigned int*)(e->d_counters + 4);
 #if GRIMB_KW == 1
-    if (warp_kernels && tv.L <= 5 && tv.P == 1) {
-      // warp-per-subject kernel first; what it cannot finish goes through the general kernel
-      CK(e->worklist.reserve((size_t)batch->n_subjects * 4 + 16));
-      unsigned int* cnt = (unsigned int*)(e->d_counters + 3);
-      const uint64_t groups = ((uint64_t)batch->n_subjects + FAST_WARPS * 2 - 1) / (FAST_WARPS * 2);
-      uint64_t fg = (uint64_t)e->sm_count * FAST_MIN_BLOCKS;  // resident CTAs only: each warp strides over subjects
-      if (fg > groups) fg = groups;
-      CK(cudaEventRecord(e->ev[0], st));
-      k_impute_fast<<<(unsigned)fg, FAST_WARPS * 32, 0, st>>>(tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt);
-      CK(cudaGetLastError());
-      CK(cudaEventRecord(e->ev[1], st));
-      e->ev_valid[0] = 1;
-      e->launches += 1;
-      wl = (const uint32_t*)e->worklist.p;
-      wl_n = cnt;
-    } else
-#endif
-    if (warp_kernels && e->typed_ctas > 0) {
-      // warp-per-subject kernel for fully typed unambiguous subjects, any P <= 32 / L / key width
-      CK(e->worklist.reserve((size_t)batch->n_subjects * 4 + 16));
-      unsigned int* cnt = (unsigned int*)(e->d_counters + 3);
-      uint64_t tg = ((uint64_t)batch->n_subjects + TY_WARPS - 1) / TY_WARPS;
-      if (tg > (uint64_t)e->typed_ctas) tg = (uint64_t)e->typed_ctas;
-      CK(cudaEventRecord(e->ev[4], st));
-      k_impute_typed<<<(unsigned)tg, TY_WARPS * 32, (size_t)e->typed_per_warp * TY_WARPS, st>>>(
-          tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt, e->typed_per_warp);
-      CK(cudaGetLastError());
-      CK(cudaEventRecord(e->ev[5], st));
-      e->ev_valid[2] = 1;
-      e->launches += 1;
-      wl = (const uint32_t*)e->worklist.p;
-      wl_n = cnt;
-    }
-    {
-      uint64_t cg = (stride + 255) / 256;
-      if (cg > (uint64_t)e->sm_count * 4) cg = (uint64_t)e->sm_count * 4;
-      k_classify<<<(unsigned)cg, 256, 0, st>>>(*batch, tv.L, wl, wl_n, (uint32_t*)e->buckets.p, bucket_n, stride);
-      CK(cudaGetLastError());
-      e->launches += 1;
-    }
-    int grid = e->n_ctas;
-    if ((int64_t)grid > batch->n_subjects) grid = (int)batch->n_subjects;
-    CK(cudaEventRecord(e->ev[2], st));
-    k_impute<<<grid, e->threads, 0, st>>>(tv, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones, e->d_counters,
-                                         (const uint32_t*)e->buckets.p, bucket_n, stride);
+  if (warp_kernels && tv.L <= 5 && tv.P == 1) {
+    // warp-per-subject kernel first; what it cannot finish goes through the general kernel
+    CK(e->worklist.reserve((size_t)batch->n_subjects * 4 + 16));
+    unsigned int* cnt = (unsigned int*)(e->d_counters + 3);
+    const uint64_t groups = ((uint64_t)batch->n_subjects + FAST_WARPS * 2 - 1) / (FAST_WARPS * 2);
+    uint64_t fg = (uint64_t)e->sm_count * FAST_MIN_BLOCKS;  // resident CTAs only: each warp strides over subjects
+    if (fg > groups) fg = groups;
+    CK(cudaEventRecord(e->ev[0], st));
+    k_impute_fast<<<(unsigned)fg, FAST_WARPS * 32, 0, st>>>(tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(e->ev[3], st));
-    e->ev_valid[1] = 1;
+    CK(cudaEventRecord(e->ev[1], st));
+    e->ev_valid[0] = 1;
     e->launches += 1;
+    wl = (const uint32_t*)e->worklist.p;
+    wl_n = cnt;
+  } else
+#endif
+  if (warp_kernels && e->typed_ctas > 0) {
+    // warp-per-subject kernel for fully typed unambiguous subjects, any P <= 32 / L / key width
+    CK(e->worklist.reserve((size_t)batch->n_subjects * 4 + 16));
+    unsigned int* cnt = (unsigned int*)(e->d_counters + 3);
+    uint64_t tg = ((uint64_t)batch->n_subjects + TY_WARPS - 1) / TY_WARPS;
+    if (tg > (uint64_t)e->typed_ctas) tg = (uint64_t)e->typed_ctas;
+    CK(cudaEventRecord(e->ev[4], st));
+    k_impute_typed<<<(unsigned)tg, TY_WARPS * 32, (size_t)e->typed_per_warp * TY_WARPS, st>>>(
+        tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt, e->typed_per_warp);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e->ev[5], st));
+    e->ev_valid[2] = 1;
+    e->launches += 1;
+    wl = (const uint32_t*)e->worklist.p;
+    wl_n = cnt;
+  }
+  {
+    uint64_t cg = (stride + 255) / 256;
+    if (cg > (uint64_t)e->sm_count * 4) cg = (uint64_t)e->sm_count * 4;
+    k_classify<<<(unsigned)cg, 256, 0, st>>>(*batch, tv.L, wl, wl_n, (uint32_t*)e->buckets.p, bucket_n, stride);
+    CK(cudaGetLastError());
+    e->launches += 1;
+  }
+  int grid = e->n_ctas;
+  if ((int64_t)grid > batch->n_subjects) grid = (int)batch->n_subjects;
+  CK(cudaEventRecord(e->ev[2], st));
+  k_impute<<<grid, e->threads, 0, st>>>(tv, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones, e->d_counters,
+                                       (const uint32_t*)e->buckets.p, bucket_n, stride);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(e->ev[3], st));
+  e->ev_valid[1] = 1;
+  e->launches += 1;
   return GRIMB_OK;
 }
 
