@@ -691,8 +691,8 @@ struct Ctx {
           gord[win] = GRIMB_NONE;
           slot_gid[r] = win;     // slot_gid is free now: reuse as the ranked list
         }
+        g.sync();                // the next sweep must see the winner marked as taken
       }
-      g.sync();
     } else {
       const double* gs = gsum;
       uint32_t* go = gord;
