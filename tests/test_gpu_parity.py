@@ -211,3 +211,27 @@ def test_homozygous_subjects_multi_population_match_oracle():
     ref, _ = go.impute_file(conf, graph=_oracle_graph("pop3", conf), lines=lines)
     for k in goldenlib.KEYS:
         assert out[k] == ref[k], "%s differs" % k
+
+
+def test_readme_flow_with_packaged_defaults(tmp_path, monkeypatch):
+    """BASELINE config 1, as the reference's README runs it: produce_hpf -> graph_freqs -> impute with
+    the packaged minimal configuration, relative paths resolved against the working directory."""
+    import json
+    import os
+    import shutil
+    from graph_generation import generate_hpf
+    from grim import grim
+    pkg = os.path.dirname(os.path.dirname(os.path.abspath(generate_hpf.__file__)))
+    d = str(tmp_path)
+    shutil.copytree(os.path.join(pkg, "data"), d + "/data")
+    shutil.copytree(os.path.join(pkg, "conf"), d + "/conf")
+    monkeypatch.chdir(d)
+    generate_hpf.produce_hpf("conf/minimal-configuration.json")
+    g = grim.graph_freqs(conf_file="conf/minimal-configuration.json")
+    grim.impute(conf_file="conf/minimal-configuration.json", graph=g)
+    _, _, _, exp = goldenlib.load_case("g1_readme_donor")
+    names = {"umug": "don.umug", "umug_pops": "don.umug.pops", "pmug": "don.pmug", "pmug_pops": "don.pmug.pops",
+             "miss": "don.miss", "problem": "don.problem"}
+    for k, fn in names.items():
+        assert open(os.path.join(d, "output", fn)).read() == exp[k], k
+    g.close()

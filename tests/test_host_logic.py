@@ -119,3 +119,24 @@ def test_open_gl_string_matches_reference_fixture():
     assert len(cases) >= 7
     for c in cases:
         assert imp.open_gl_string(c["gl"], c["cutoff"]) == c["phases"], c["gl"]
+
+
+def test_produce_hpf_matches_reference_output(tmp_path):
+    """README step 1: produce_hpf on the packaged CAU.freqs.gz must write the same hpf.csv and
+    pop_counts_file.txt the reference's produce_hpf wrote (tests/golden/data/cau_*)."""
+    import json
+    import os
+    import goldenlib
+    from graph_generation import generate_hpf
+    pkg = os.path.dirname(os.path.dirname(os.path.abspath(generate_hpf.__file__)))
+    conf = json.load(open(os.path.join(pkg, "conf", "minimal-configuration.json")))
+    assert conf == json.load(open(os.path.join(goldenlib.GOLD, "data", "base_conf.json")))
+    d = str(tmp_path)
+    conf["freq_data_dir"] = os.path.join(pkg, "data", "freqs")
+    conf["graph_files_path"] = d + "/csv/"
+    conf["freq_file"] = d + "/hpf.csv"
+    conf["pops_count_file"] = d + "/pop_counts_file.txt"
+    json.dump(conf, open(d + "/conf.json", "w"))
+    generate_hpf.produce_hpf(d + "/conf.json")
+    assert open(d + "/hpf.csv", newline="").read() == open(os.path.join(goldenlib.GOLD, "data", "cau_hpf.csv"), newline="").read()
+    assert open(d + "/pop_counts_file.txt").read() == open(os.path.join(goldenlib.GOLD, "data", "cau_pop_counts.txt")).read()
