@@ -422,6 +422,10 @@ def main():
         # algorithmic bytes per launch (DESIGN.md "Measurement"): per subject 36 B of input, 2^L = 32
         # probes x one 32 B sector, per hit a 32 B frequency sector, 48 B result record, plus the rows written
         algo = S * (36 + 32 * 32 + 48) + hits * 2 * 32 + hap_rows_n * 24 + pop_rows_n * 16
+        # for transparency: the probes the kernel really issues (homozygous loci collapse phases; SURVEY's
+        # per-subject figure counts all 2^L side haplotypes, and that figure is what `achieved` uses)
+        nhet = (alleles[:, :, 0] != alleles[:, :, 1]).sum(axis=1)
+        probes_issued = float(np.where(nhet > 0, 2.0 ** nhet, 1.0).mean())
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -454,7 +458,8 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback",
-                         "algorithmic_bytes_per_launch": algo, "kernel": "k_impute_fast", "kernel_ms": ms_kernel,
+                         "algorithmic_bytes_per_launch": algo, "probes_per_subject_counted": 32,
+                         "probes_per_subject_issued": probes_issued, "kernel": "k_impute_fast", "kernel_ms": ms_kernel,
                          "kernel_share_of_step": ms_kernel / ms_dev},
             "cpu_baseline": cpu,
             "clocks": sampler.summary(),
