@@ -245,6 +245,10 @@ def main():
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = None
+    if world > 1 and os.environ.get("GRIMB_NUMA_BIND", "1") != "0":
+        from grim.imputation.multi_gpu import bind_to_device_numa_node
+        numa_cpus = bind_to_device_numa_node(local)   # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
@@ -464,6 +468,7 @@ def main():
             "cpu_baseline": cpu,
             "clocks": sampler.summary(),
             "table": {"n_nodes": info["n_nodes"], "device_bytes": info["device_bytes"], "build_s": t_build},
+            "host": {"cpus": os.cpu_count(), "numa_bound_cpus_rank0": (len(numa_cpus) if numa_cpus else None)},
             "status_counts": {str(i): int(c) for i, c in enumerate(np.bincount(status, minlength=6)) if c},
             "parity_sample_identical": parity,
             "e2e_text": e2e_text,

@@ -25,6 +25,34 @@ class _DeviceView(object):
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
+def bind_to_device_numa_node(device):
+    """Pins this process to the CPUs next to GPU `device` (sysfs local_cpulist of its PCI function) so
+    that the pinned staging buffers it allocates afterwards are first-touched on that NUMA node.  One
+    process per GPU on a multi-socket box otherwise funnels every host<->device copy through whichever
+    socket the scheduler happened to pick.  Returns the CPU set used, or None if nothing was changed."""
+    import os
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def broadcast_graph(graph, config, device, src=0):
     """Replicates the tables of rank `src` to every rank's GPU.  On `src`, `graph` is a built
     Graph; elsewhere it may be None.  Returns this rank's Graph."""

@@ -124,6 +124,7 @@ def _run_impute_sharded(dist, config, hap_pop_pair, graph):
     from .imputation import multi_gpu
     rank, world = dist.get_rank(), dist.get_world_size()
     device = int(os.environ.get("LOCAL_RANK", rank))
+    multi_gpu.bind_to_device_numa_node(device)
     if graph is None:
         if rank == 0:
             graph = Graph(config, device=device)
