@@ -569,19 +569,37 @@ class Imputation(object):
         self._text = h
         return h
 
-    def _line_chunks(self, f, max_lines=None):
-        """Yields (bytes of whole lines, index of the first line)."""
-        max_lines = max_lines or int(os.environ.get("GRIMB_TEXT_BATCH", "262144"))
+    @staticmethod
+    def _byte_chunks(f, max_bytes=None):
+        """Yields (bytes of whole lines, number of lines before them) from a binary file, reading big
+        blocks and cutting at the last newline -- no per-line work in Python."""
+        max_bytes = max_bytes or int(os.environ.get("GRIMB_TEXT_BYTES", str(24 << 20)))
         first = 0
-        buf = []
-        for line in f:
-            buf.append(line)
-            if len(buf) >= max_lines:
-                yield b"".join(buf), first
-                first += len(buf)
-                buf = []
-        if buf:
-            yield b"".join(buf), first
+        carry = b""
+        while True:
+            block = f.read(max_bytes)
+            if not block:
+                break
+            data = carry + block if carry else block
+            cut = data.rfind(b"\n")
+            if cut < 0:
+                carry = data
+                continue
+            chunk, carry = data[:cut + 1], data[cut + 1:]
+            yield chunk, first
+            first += chunk.count(b"\n")
+        if carry:
+            yield carry, first
+
+    def impute_text_stream(self, data, first_index=0, max_bytes=None):
+        """impute_text over a large bytes object in bounded pieces; returns the six texts."""
+        import io
+        parts = {k: [] for k in _lib.OUT_KEYS}
+        for chunk, first in self._byte_chunks(io.BytesIO(data), max_bytes):
+            out = self.impute_text(chunk, first_index + first)
+            for k in _lib.OUT_KEYS:
+                parts[k].append(out[k])
+        return {k: b"".join(v) for k, v in parts.items()}
 
     def impute_text(self, data, first_index=0):
         """bytes of input lines -> dict of the six output texts (bytes), through grimb_impute_text."""
@@ -632,7 +650,7 @@ class Imputation(object):
             outs = {k: open(config[ck], "wb") for k, ck in targets.items()}
             try:
                 with open(config["imputation_input_file"], "rb") as f:
-                    for chunk, first in self._line_chunks(f):
+                    for chunk, first in self._byte_chunks(f):
                         texts = self.impute_text(chunk, first)
                         for k, fo in outs.items():
                             fo.write(texts[k])

@@ -130,28 +130,51 @@ def _run_impute_sharded(dist, config, hap_pop_pair, graph):
             graph = Graph(config, device=device)
             graph.build_graph(config["node_file"], config["top_links_file"], config["edges_file"])
         graph = multi_gpu.broadcast_graph(graph, config, device, src=0)
+    # the ranks share the host's cores: split them for the C++ tokeniser / formatter threads
+    os.environ.setdefault("GRIMB_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
     imputation = Imputation(graph, config)
     with open(config["imputation_input_file"], "rb") as f:
-        lines = f.readlines()
-    lo, hi = multi_gpu.shard_range(len(lines), rank, world)
+        data = f.read()
+    # contiguous byte ranges cut at line boundaries; .miss / .problem rows carry global line indices
+    n = len(data)
+
+    def cut(pos):
+        if pos <= 0:
+            return 0
+        if pos >= n:
+            return n
+        j = data.find(b"\n", pos - 1)
+        return n if j < 0 else j + 1
+
+    lo_b, hi_b = cut(n * rank // world), cut(n * (rank + 1) // world)
+    first = data.count(b"\n", 0, lo_b)
     if hap_pop_pair or imputation.phase_masks is not None:
         # EM-facing modes go through the numpy host front end (see Imputation.impute_file)
-        rows = imputation.impute_lines([l.decode("utf8") for l in lines[lo:hi]], first_index=lo, em_mr=hap_pop_pair)
+        lines = data[lo_b:hi_b].decode("utf8").splitlines(True)
+        rows = imputation.impute_lines(lines, first_index=first, em_mr=hap_pop_pair)
         mine = {k: "".join(v).encode("utf8") for k, v in rows.items()}
     else:
-        mine = imputation.impute_text(b"".join(lines[lo:hi]), first_index=lo)
-    parts = [None] * world if rank == 0 else None
-    dist.gather_object(mine, parts, dst=0)
+        mine = imputation.impute_text_stream(data[lo_b:hi_b], first_index=first)
+    del data
+    targets = {"miss": "imputation_out_miss_file", "problem": "imputation_out_problem_file"}
+    if config["output_MUUG"]:
+        targets.update(umug="imputation_out_umug_freq_file", umug_pops="imputation_out_umug_pops_file")
+    if config["output_haplotypes"]:
+        targets.update(pmug="imputation_out_hap_freq_file", pmug_pops="imputation_out_hap_pops_file")
+    # every rank writes its rows straight into the final files at its offset (rank order == input order):
+    # only the sizes are exchanged, not the gigabytes of text
+    sizes = [None] * world
+    dist.all_gather_object(sizes, {k: len(mine[k]) for k in targets})
     if rank == 0:
         pathlib.Path(config["imputation_out_path"]).mkdir(parents=False, exist_ok=True)
-        targets = {"miss": "imputation_out_miss_file", "problem": "imputation_out_problem_file"}
-        if config["output_MUUG"]:
-            targets.update(umug="imputation_out_umug_freq_file", umug_pops="imputation_out_umug_pops_file")
-        if config["output_haplotypes"]:
-            targets.update(pmug="imputation_out_hap_freq_file", pmug_pops="imputation_out_hap_pops_file")
         for k, ck in targets.items():
             with open(config[ck], "wb") as f:
-                for part in parts:          # rank order == input order
-                    f.write(part[k])
+                f.truncate(sum(sz[k] for sz in sizes))
+    dist.barrier()
+    for k, ck in targets.items():
+        if len(mine[k]):
+            with open(config[ck], "r+b") as f:
+                f.seek(sum(sz[k] for sz in sizes[:rank]))
+                f.write(mine[k])
     dist.barrier()
     return graph
