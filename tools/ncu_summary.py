@@ -12,7 +12,11 @@ rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, vals = rows[0], rows[1], rows[2]
+hdr, units = rows[0], rows[1]
+dcol = hdr.index("gpu__time_duration.sum") if "gpu__time_duration.sum" in hdr else None
+cands = [r for r in rows[2:] if len(r) == len(hdr)]
+vals = max(cands, key=lambda r: float(r[dcol].replace(",", "")) if dcol is not None and r[dcol] else 0.0)  # longest launch
+print("launches in report:", len(cands))
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
         "lts__t_sectors.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
