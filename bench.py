@@ -327,11 +327,13 @@ def main():
     stream = torch.cuda.current_stream()
 
     kernel_ms = []
+    score_ms = []
 
     def step_device():
         rc = lib.grimb_impute_device(eng, C.byref(cfg), C.byref(db), C.byref(dr), C.c_void_p(stream.cuda_stream))
         _lib.check(rc, "grimb_impute_device")
-        kernel_ms.append(lib.grimb_engine_kernel_ms(eng, 0))   # k_impute_fast, CUDA events inside the library
+        kernel_ms.append(lib.grimb_engine_kernel_ms(eng, 0))   # probe kernel, CUDA events inside the library
+        score_ms.append(lib.grimb_engine_kernel_ms(eng, 4))    # k_fast_score (negative when the fused kernel runs)
 
     # host leg (pinned buffers; copies inside the timed region)
     h_in = {k: tens(batch[k].view(np.int16) if batch[k].dtype == np.uint16 else
@@ -423,9 +425,14 @@ def main():
 
     if rank == 0:
         total = S * world
-        # algorithmic bytes per launch (DESIGN.md "Measurement"): per subject 36 B of input, 2^L = 32
-        # probes x one 32 B sector, per hit a 32 B frequency sector, 48 B result record, plus the rows written
-        algo = S * (36 + 32 * 32 + 48) + hits * 2 * 32 + hap_rows_n * 24 + pop_rows_n * 16
+        # algorithmic bytes (DESIGN.md "Measurement"): per subject 36 B of input, 2^L = 32 probes x one 32 B
+        # sector, per hit a 32 B frequency sector [the probe kernel]; 48 B result record plus the rows
+        # written [the score kernel].  The 32-80 B hand-over record between the two is not counted.
+        algo_probe = S * (36 + 32 * 32) + hits * 2 * 32
+        algo_path = algo_probe + S * 48 + hap_rows_n * 24 + pop_rows_n * 16
+        s_ms = [x for x in score_ms[args.warmup:args.warmup + args.steps] if x > 0]
+        split = len(s_ms) > 0
+        algo = algo_probe if split else algo_path   # the fused kernel (GRIMB_FAST_SPLIT=0) does both
         # for transparency: the probes the kernel really issues (homozygous loci collapse phases; SURVEY's
         # per-subject figure counts all 2^L side haplotypes, and that figure is what `achieved` uses)
         nhet = (alleles[:, :, 0] != alleles[:, :, 1]).sum(axis=1)
@@ -442,7 +449,8 @@ def main():
         achieved = algo / (ms_kernel * 1e-3) / 1e9
         traffic = None   # DRAM bytes per launch from the committed ncu --set full capture of this kernel
         try:
-            txt = open(os.path.join(ROOT, "profiles", "r01_ncu_summary_k_impute_fast_final.txt")).read().splitlines()
+            txt = open(os.path.join(ROOT, "profiles", "r01_ncu_summary_k_fast_probe_final.txt" if split
+                                    else "r01_ncu_summary_k_impute_fast_final.txt")).read().splitlines()
             rd = [l for l in txt if l.startswith("dram__bytes_read.sum")][0].split()
             wr = [l for l in txt if l.startswith("dram__bytes_write.sum")][0].split()
             unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
@@ -463,8 +471,15 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback",
                          "algorithmic_bytes_per_launch": algo, "probes_per_subject_counted": 32,
-                         "probes_per_subject_issued": probes_issued, "kernel": "k_impute_fast", "kernel_ms": ms_kernel,
-                         "kernel_share_of_step": ms_kernel / ms_dev},
+                         "probes_per_subject_issued": probes_issued,
+                         "kernel": "k_fast_probe" if split else "k_impute_fast", "kernel_ms": ms_kernel,
+                         "kernel_share_of_step": ms_kernel / ms_dev,
+                         # the whole single-population path (probe + score kernels) against the same peak
+                         "path": ({"kernels": "k_fast_probe + k_fast_score", "ms": ms_kernel + float(np.mean(s_ms)),
+                                   "k_fast_score_ms": float(np.mean(s_ms)), "algorithmic_bytes": algo_path,
+                                   "achieved": algo_path / ((ms_kernel + float(np.mean(s_ms))) * 1e-3) / 1e9,
+                                   "frac": algo_path / ((ms_kernel + float(np.mean(s_ms))) * 1e-3) / 1e9 / peak}
+                                  if split else None)},
             "cpu_baseline": cpu,
             "clocks": sampler.summary(),
             "table": {"n_nodes": info["n_nodes"], "device_bytes": info["device_bytes"], "build_s": t_build},

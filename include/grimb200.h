@@ -210,10 +210,11 @@ int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* 
 
 /* Number of kernel launches issued by this engine so far (bench.py's gpu_launches). */
 int64_t grimb_engine_launches(const GrimbEngine* e);
-/* Device time in ms (CUDA events on the launching stream) of the last k_impute_fast (which = 0),
- * k_impute (which = 1) or k_impute_typed (which = 2) launch of this engine; negative if that kernel
- * was not launched.  which = 3 (diagnostic): number of subjects the warp-per-subject kernels of the
- * last call handed on to k_impute. */
+/* Device time in ms (CUDA events on the launching stream) of the last launch of: which = 0 the
+ * single-population probe kernel (k_fast_probe; k_impute_fast when GRIMB_FAST_SPLIT=0), 1 k_impute,
+ * 2 k_impute_typed, 4 k_fast_score; negative if that kernel was not launched.  which = 3
+ * (diagnostic): number of subjects the warp-per-subject kernels of the last call handed on to
+ * k_impute. */
 double grimb_engine_kernel_ms(const GrimbEngine* e, int which);
 
 /* ------------------------------------------------------------------------------------------

@@ -911,9 +911,10 @@ constexpr uint32_t FAST_CHUNK = GRIMB_FAST_CHUNK;
 // k0 (all side-0 alleles) and k1 (all side-1 alleles), and phase i's haplotypes are
 // k0 ^ (D & M_i) and its complement, with D = k0 ^ k1 and M_i the field mask of the loci i flips
 // (a per-lane constant).  All votes / reductions use the half's lane mask.
+template <bool LIST>
 __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_BLOCKS)
 k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O, uint32_t* worklist,
-              unsigned int* worklist_n) {
+              unsigned int* worklist_n, const uint32_t* __restrict__ list, const unsigned int* __restrict__ list_n) {
   __shared__ double s_chain[FAST_MAX_ROUNDS];
   __shared__ int s_nchain;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -947,16 +948,25 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
   const uint64_t Mlast = ((1ull << T.width[L - 1]) - 1ull) << T.shift[L - 1];
   const uint32_t ht_mask = T.ht_mask[full];
   const HSlot* __restrict__ ht_base = T.slots + T.ht_off[full];
-  const uint64_t S = (uint64_t)B.n_subjects;
+  // with `list` the kernel serves the listed subjects only (overflow of the split fast path)
+  const uint64_t S = LIST ? (uint64_t)*list_n : (uint64_t)B.n_subjects;
   const uint64_t stride = (uint64_t)gridDim.x * FAST_WARPS * 2;
   uint64_t hap_base = 0, pop_base = 0;   // this half-warp's current chunks (uniform within the half)
   uint32_t hap_left = 0, pop_left = 0;
   uint64_t s = ((uint64_t)blockIdx.x * FAST_WARPS + warp) * 2 + half;
   FastIn nxt;
-  if (s < S) fast_load(nxt, B, s, L, i);
+  uint64_t sx_next = 0;
+  if (s < S) {
+    sx_next = LIST ? (uint64_t)list[s] : s;
+    fast_load(nxt, B, sx_next, L, i);
+  }
   for (; s < S; s += stride) {   // the two halves may leave the loop one iteration apart
     const FastIn in = nxt;
-    if (s + stride < S) fast_load(nxt, B, s + stride, L, i);
+    const uint64_t sx = sx_next;   // the subject this iteration serves
+    if (s + stride < S) {
+      sx_next = LIST ? (uint64_t)list[s + stride] : s + stride;
+      fast_load(nxt, B, sx_next, L, i);
+    }
     bool done = false;  // finished here (rows, an empty result, or a skipped subject)
     uint32_t acc = 0, rank = 0, n_acc = 0, evals = 0, gsel = 0;
     uint64_t key = 0, key2 = 0, D = 0;
@@ -1056,7 +1066,7 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
     }
     if (!shape) {
       if (typed != 0) {
-        if (i == 0) worklist[atomicAdd(worklist_n, 1u)] = (uint32_t)s;
+        if (i == 0) worklist[atomicAdd(worklist_n, 1u)] = (uint32_t)sx;
       } else {
         done = true;  // GRIMB_ST_SKIPPED
       }
@@ -1102,7 +1112,7 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
       w2.y = (uint32_t)(hb >> 32);
       w2.z = (uint32_t)pb;
       w2.w = (uint32_t)(pb >> 32);
-      uint4* dst = reinterpret_cast<uint4*>(R.subjects + s);
+      uint4* dst = reinterpret_cast<uint4*>(R.subjects + sx);
       dst[0] = w0;
       dst[1] = w1;
       dst[2] = w2;
@@ -1133,6 +1143,371 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
       o.pad = 0;
       o.prob = total;
       R.pop_rows[pb + i] = o;
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Split form of the fast path: k_fast_probe (half-warp per subject: keys, probes, frequency loads)
+// hands the few phases whose two haplotypes are both in the table to k_fast_score (one LANE per
+// subject: epsilon schedule, sums, ranks, result record and rows).  The probe kernel carries no FP64
+// state, so it fits more warps per SM, and the scoring work -- which used 16 lanes per subject for
+// what is typically one or two candidate phases -- shrinks to a few instructions per subject.
+// Hand-over record: 96 bytes per subject in a device buffer owned by the engine.
+// ------------------------------------------------------------------------------------------
+constexpr int FAST_CMAX = 4;   // candidate phases carried per subject; more -> k_impute_fast over an overflow list
+
+struct __align__(16) FastMid {
+  uint64_t k0, k1;       // all side-0 / all side-1 alleles, packed
+  double reserved;
+  uint32_t flags;        // bits 0-1 state (0 not for k_fast_score, 1 ready), 2-4 ncand, 8-12 gsel, 16-31 four phase ids
+  uint32_t typed;
+  double f[FAST_CMAX][2];  // (f1, f2) of the candidate phases, ascending phase
+};
+
+#ifndef FASTPROBE_MIN_BLOCKS
+#define FASTPROBE_MIN_BLOCKS 5
+#endif
+
+// inputs of the probe kernel (no prior: k_fast_score reads it)
+struct ProbeIn {
+  uint32_t typed, c, pair;
+};
+
+__device__ __forceinline__ void probe_load(ProbeIn& in, const GrimbBatch& B, uint32_t s, int L, int i) {
+  in.typed = B.typed_mask[s];
+  const uint32_t off = B.allele_off[s];
+  const uint32_t* c32 = reinterpret_cast<const uint32_t*>(B.counts + (uint64_t)s * L * 2);
+  in.c = i < L ? c32[i] : 0x00010001u;
+  in.pair = 0;
+  if (i < L) {
+    const uint16_t* al = B.alleles + off + 2 * i;
+    in.pair = (off & 1u) ? ((uint32_t)al[0] | ((uint32_t)al[1] << 16)) : *reinterpret_cast<const uint32_t*>(al);
+  }
+}
+
+__global__ void __launch_bounds__(FAST_WARPS * 32, FASTPROBE_MIN_BLOCKS)
+k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid, uint32_t* worklist,
+             unsigned int* worklist_n, uint32_t* overflow, unsigned int* overflow_n, int nchain_ok) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = lane >> 4, i = lane & 15, hbase = half << 4;
+  const uint32_t hmask = 0xFFFFu << hbase;
+  const int L = T.L;
+  const uint32_t full = (1u << L) - 1u;
+  const int nphase = 1 << (L - 1);
+  const uint32_t my_shift = i < L ? T.shift[i] : 0u;
+  const uint32_t my_nal = i < L ? T.n_alleles[i] : 0u;
+  uint64_t Mi = 0;
+  for (int l = 0; l < L; ++l)
+    if ((i >> l) & 1) Mi |= ((1ull << T.width[l]) - 1ull) << T.shift[l];
+  const uint32_t ht_mask = T.ht_mask[full];
+  const HSlot* __restrict__ ht_base = T.slots + T.ht_off[full];
+  const uint32_t S = (uint32_t)B.n_subjects;               // subject indices fit 32 bits (worklists are uint32)
+  const uint32_t stride = gridDim.x * FAST_WARPS * 2;
+  uint32_t s = (blockIdx.x * FAST_WARPS + warp) * 2 + half;
+  ProbeIn nxt;
+  if (s < S) probe_load(nxt, B, s, L, i);
+  for (; s < S; s += stride) {
+    const ProbeIn in = nxt;
+    if (s + stride < S && s + stride > s) probe_load(nxt, B, s + stride, L, i);
+    const uint32_t typed = in.typed;
+    bool shape = typed == full && nchain_ok;
+    shape = __all_sync(hmask, in.c == 0x00010001u) && shape;
+    uint32_t state = 0, ncand = 0, gsel = 0, phases = 0;
+    if (shape) {
+      const uint32_t a0 = in.pair & 0xffffu, a1 = in.pair >> 16;
+      const uint64_t k0 = half_or64(hmask, (uint64_t)a0 << my_shift);
+      const uint64_t k1 = half_or64(hmask, (uint64_t)a1 << my_shift);
+      if (i == 0) {   // first half of the header now: k0 / k1 need not stay live across the probes
+        uint4 h0;
+        h0.x = (uint32_t)k0;
+        h0.y = (uint32_t)(k0 >> 32);
+        h0.z = (uint32_t)k1;
+        h0.w = (uint32_t)(k1 >> 32);
+        reinterpret_cast<uint4*>(mid + s)[0] = h0;
+      }
+      const uint32_t unk0 = (__ballot_sync(hmask, i < L && (a0 - 1u) >= my_nal) >> hbase) & 0xFFFFu;
+      const uint32_t unk1 = (__ballot_sync(hmask, i < L && (a1 - 1u) >= my_nal) >> hbase) & 0xFFFFu;
+      const uint32_t het = (__ballot_sync(hmask, a0 != a1) >> hbase) & 0xFFFFu;
+      gsel = (__ballot_sync(hmask, a0 > a1) >> hbase) & 0xFFFFu;
+      const uint64_t D = k0 ^ k1;
+      const uint64_t key = k0 ^ (D & Mi), key2 = key ^ D;
+      const uint32_t ib = (uint32_t)i;
+      const bool known1 = ((unk0 & ~ib) | (unk1 & ib)) == 0, known2 = ((unk1 & ~ib) | (unk0 & ib)) == 0;
+      const uint32_t low = het & ((uint32_t)nphase - 1u);
+      const bool last_het = (het >> (L - 1)) & 1u;
+      const bool kept = i < nphase && !(ib & ~low) && (last_het || ib <= (low ^ ib));
+      uint32_t n1, n2;
+      ht_lookup2(ht_base, ht_mask, key, kept && known1, key2, kept && known2, n1, n2);
+      const double f1 = n1 != GRIMB_NONE ? __ldg(T.freq + n1) : 0.0;   // P == 1
+      const double f2 = n2 != GRIMB_NONE ? __ldg(T.freq + n2) : 0.0;
+      const bool cand = kept && f1 > 0 && f2 > 0;
+      const uint32_t cmask = (__ballot_sync(hmask, cand) >> hbase) & 0xFFFFu;
+      ncand = __popc(cmask);
+      if (ncand > FAST_CMAX) {
+        // more candidate phases than a hand-over record holds: the fused kernel serves this subject
+        if (i == 0) overflow[atomicAdd(overflow_n, 1u)] = s;
+      } else {
+        state = 1;
+        // phase ids of the candidates, ascending, 4 bits each
+        uint32_t mm = cmask;
+        for (uint32_t q = 0; q < ncand; ++q) {
+          phases |= (uint32_t)(__ffs(mm) - 1) << (4 * q);
+          mm &= mm - 1;
+        }
+        if (cand) {
+          const uint32_t slot = __popc(cmask & ((1u << i) - 1u));
+          double2 v;
+          v.x = f1;
+          v.y = f2;
+          *reinterpret_cast<double2*>(&mid[s].f[slot][0]) = v;
+        }
+      }
+    }
+    if (!shape && typed != 0) {
+      if (i == 0) worklist[atomicAdd(worklist_n, 1u)] = s;
+    }
+    if (i == 0) {
+      if (typed == 0) {   // GRIMB_ST_SKIPPED: finished here
+        uint4 z = make_uint4(0, 0, 0, 0);
+        uint4 w0 = z;
+        w0.x = GRIMB_ST_SKIPPED;
+        uint4* dst = reinterpret_cast<uint4*>(O.r.subjects + s);
+        dst[0] = w0;
+        dst[1] = z;
+        dst[2] = z;
+      }
+      uint4 h1;   // second half of the header: state and candidate bookkeeping
+      h1.x = 0;
+      h1.y = 0;
+      h1.z = state | (ncand << 2) | ((gsel & 31u) << 8) | (phases << 16);
+      h1.w = typed;
+      reinterpret_cast<uint4*>(mid + s)[1] = h1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O,
+             const FastMid* __restrict__ mid, uint32_t* worklist, unsigned int* worklist_n) {
+  __shared__ double s_chain[FAST_MAX_ROUNDS];
+  __shared__ int s_nchain;
+  __shared__ uint64_t s_mask[16];
+  const int lane = threadIdx.x & 31;
+  const int L = T.L;
+  const int nphase = 1 << (L - 1);
+  GrimbResults& R = O.r;
+  const bool want_u = cfg->output_umug != 0, want_p = cfg->output_pmug != 0, planb = cfg->planb != 0;
+  const uint32_t lim_r = (uint32_t)cfg->n_results, lim_p = (uint32_t)cfg->n_pop_results;
+  if (threadIdx.x == 0) {
+    double e = cfg->epsilon;
+    int n = 0;
+    while (e > 0 && n < FAST_MAX_ROUNDS) {
+      e /= 10;
+      if (e < 1.0e-9) e = 0.0;
+      s_chain[n++] = e;
+    }
+    s_nchain = (e > 0) ? -1 : n;
+  }
+  if (threadIdx.x < 16) {   // field mask of the loci phase i flips
+    uint64_t mk = 0;
+    for (int l = 0; l < L; ++l)
+      if ((threadIdx.x >> l) & 1) mk |= ((1ull << T.width[l]) - 1ull) << T.shift[l];
+    s_mask[threadIdx.x] = mk;
+  }
+  __syncthreads();
+  const int nchain = s_nchain;
+  const uint64_t Mlast = ((1ull << T.width[L - 1]) - 1ull) << T.shift[L - 1];
+  const uint64_t S = (uint64_t)B.n_subjects;
+  const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+  // whole warps iterate together (the row-space claim is a warp scan)
+  for (uint64_t s0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; s0 < S; s0 += nthreads) {
+    const uint64_t s = s0 + lane;
+    bool ready = false;
+    uint64_t k0 = 0, k1 = 0;
+    double m = 0.0;
+    uint32_t fl = 0;
+    if (s < S) {
+      const uint4* src = reinterpret_cast<const uint4*>(mid + s);
+      const uint4 h0 = src[0], h1 = src[1];
+      k0 = (uint64_t)h0.x | ((uint64_t)h0.y << 32);
+      k1 = (uint64_t)h0.z | ((uint64_t)h0.w << 32);
+      fl = h1.z;
+      ready = (fl & 3u) == 1u;
+      if (ready) m = __ldg(B.priors + B.prior_index[s]);   // P == 1: one prior per subject
+    }
+    const uint32_t ncand = ready ? ((fl >> 2) & 7u) : 0u;
+    const uint32_t gsel = (fl >> 8) & 31u;
+    const uint64_t D = k0 ^ k1;
+    const bool same = D == 0;
+    const bool mpos = m > 0;
+    double pf[FAST_CMAX], pf2[FAST_CMAX], prob[FAST_CMAX];
+    uint32_t rq[FAST_CMAX];
+    bool acc[FAST_CMAX];
+    uint32_t r_star = 99;
+#pragma unroll
+    for (int q = 0; q < FAST_CMAX; ++q) {
+      pf[q] = pf2[q] = prob[q] = 0.0;
+      rq[q] = 99;
+      acc[q] = false;
+      if ((uint32_t)q < ncand) {
+        const double2 v = *reinterpret_cast<const double2*>(&mid[s].f[q][0]);
+        FastPair pr;
+        pr.f = v.x;
+        pr.f2 = v.y;
+        pr.same = same;
+        pr.mpos = mpos;
+        pr.y = m * pr.f2;
+        const double t = fmin(pr.f2, same ? pr.y * 0.5 : pr.y);
+        const double b = pr.f * t;
+        const bool tiny = !(b > 1.0e-280);
+        pr.lo = tiny ? -1.0 : b * (1.0 - 0x1p-50);
+        pr.hi = tiny ? __longlong_as_double(0x7ff0000000000000LL) : b * (1.0 + 0x1p-50);
+        pf[q] = v.x;
+        pf2[q] = v.y;
+        double p = v.x * v.y * m;
+        if (!same) p = p * 2;
+        prob[q] = p;
+        if (mpos) {
+          int r = 0;
+          while (r < nchain && s_chain[r] >= pr.hi) ++r;
+          while (r < nchain && !pr.accept(s_chain[r])) ++r;
+          if (r < nchain) rq[q] = (uint32_t)r;
+        }
+        r_star = rq[q] < r_star ? rq[q] : r_star;
+      }
+    }
+    uint32_t evals = 0, n_acc = 0;
+    if (r_star == 99) {
+      evals = ncand * (uint32_t)nchain;
+    } else {
+      evals = ncand * (r_star + 1);
+      if (s_chain[r_star] > 0) {
+        // MaxProb of that round -> epsilon = MaxProb / 100000, one more evaluation (impute.py:1683-1693)
+        double mx = 0.0;
+#pragma unroll
+        for (int q = 0; q < FAST_CMAX; ++q)
+          if (rq[q] <= r_star && prob[q] > mx) mx = prob[q];
+        const double eps = mx / 100000;
+#pragma unroll
+        for (int q = 0; q < FAST_CMAX; ++q)
+          if ((uint32_t)q < ncand) {
+            FastPair pr;
+            pr.f = pf[q];
+            pr.f2 = pf2[q];
+            pr.same = same;
+            pr.mpos = mpos;
+            pr.y = m * pr.f2;
+            const double t = fmin(pr.f2, same ? pr.y * 0.5 : pr.y);
+            const double b = pr.f * t;
+            const bool tiny = !(b > 1.0e-280);
+            pr.lo = tiny ? -1.0 : b * (1.0 - 0x1p-50);
+            pr.hi = tiny ? __longlong_as_double(0x7ff0000000000000LL) : b * (1.0 + 0x1p-50);
+            acc[q] = pr.accept(eps);
+          }
+        evals += ncand;
+      } else {
+#pragma unroll
+        for (int q = 0; q < FAST_CMAX; ++q) acc[q] = rq[q] <= r_star;
+      }
+    }
+    double total = 0.0;
+    bool first = true;
+#pragma unroll
+    for (int q = 0; q < FAST_CMAX; ++q)
+      if (acc[q]) {   // += in phase order
+        total = first ? prob[q] : total + prob[q];
+        first = false;
+        ++n_acc;
+      }
+    if (want_u && want_p) evals *= 2;
+    bool done = ready;
+    if (ready && n_acc == 0 && planb) {   // Plan B / C: general kernel
+      worklist[atomicAdd(worklist_n, 1u)] = (uint32_t)s;
+      done = false;
+    }
+    const bool rows = done && n_acc != 0;
+    const uint32_t nu = (rows && want_u) ? (lim_r < 1u ? lim_r : 1u) : 0u;
+    const uint32_t np = (rows && want_p) ? (n_acc < lim_r ? n_acc : lim_r) : 0u;
+    const uint32_t nup = (rows && want_u) ? (lim_p < 1u ? lim_p : 1u) : 0u;
+    const uint32_t npp = (rows && want_p) ? (lim_p < 1u ? lim_p : 1u) : 0u;
+    const uint32_t nh = nu + np, npop = nup + npp;
+    // one claim of row space per warp: inclusive scans of the two counts
+    uint32_t sh_ = nh, sp_ = npop;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, sh_, d), b = __shfl_up_sync(0xFFFFFFFFu, sp_, d);
+      if (lane >= d) {
+        sh_ += a;
+        sp_ += b;
+      }
+    }
+    unsigned long long hbw = 0, pbw = 0;
+    if (lane == 31) {
+      if (sh_) hbw = atomicAdd(O.hap_counter, (unsigned long long)sh_);
+      if (sp_) pbw = atomicAdd(O.pop_counter, (unsigned long long)sp_);
+    }
+    hbw = __shfl_sync(0xFFFFFFFFu, hbw, 31);
+    pbw = __shfl_sync(0xFFFFFFFFu, pbw, 31);
+    if (!done) continue;
+    const uint64_t hb = hbw + (sh_ - nh), pb = pbw + (sp_ - npop);
+    {
+      uint4 w0, w1, w2;
+      w0.x = GRIMB_ST_OK | (want_u ? (GRIMB_PLAN_A << 8) : 0) | (want_p ? (GRIMB_PLAN_A << 16) : 0);
+      w0.y = nu;
+      w0.z = np;
+      w0.w = nup;
+      w1.x = npp;
+      w1.y = (want_u && n_acc) ? 1u : 0u;
+      w1.z = want_p ? n_acc : 0u;
+      w1.w = evals;
+      w2.x = (uint32_t)hb;
+      w2.y = (uint32_t)(hb >> 32);
+      w2.z = (uint32_t)pb;
+      w2.w = (uint32_t)(pb >> 32);
+      uint4* dst = reinterpret_cast<uint4*>(R.subjects + s);
+      dst[0] = w0;
+      dst[1] = w1;
+      dst[2] = w2;
+    }
+    if ((int64_t)(hb + nh) <= R.hap_capacity) {
+      if (nu) {
+        // the single UMUG genotype: per-locus (min, max) of the two typed alleles
+        const uint64_t mg = s_mask[gsel & ((uint32_t)nphase - 1u)] | (((gsel >> (L - 1)) & 1u) ? Mlast : 0ull);
+        GrimbHapRow o;
+        o.a = k0 ^ (D & mg);
+        o.b = o.a ^ D;
+        o.prob = total;
+        R.hap_rows[hb] = o;
+      }
+#pragma unroll
+      for (int q = 0; q < FAST_CMAX; ++q)
+        if (acc[q]) {
+          // rank by (probability desc, phase asc); candidates are stored in ascending phase order
+          uint32_t rank = 0;
+#pragma unroll
+          for (int j = 0; j < FAST_CMAX; ++j)
+            if (acc[j] && (prob[j] > prob[q] || (prob[j] == prob[q] && j < q))) ++rank;
+          if (rank < np) {
+            const uint32_t ph = (fl >> (16 + 4 * q)) & 15u;
+            GrimbHapRow o;
+            o.a = k0 ^ (D & s_mask[ph]);
+            o.b = o.a ^ D;
+            o.prob = prob[q];
+            R.hap_rows[hb + nu + rank] = o;
+          }
+        }
+    }
+    if ((int64_t)(pb + npop) <= R.pop_capacity) {
+      for (uint32_t r = 0; r < npop; ++r) {
+        GrimbPopRow o;
+        o.pop_a = 0;
+        o.pop_b = 0;
+        o.pad = 0;
+        o.prob = total;
+        R.pop_rows[pb + r] = o;
+      }
     }
   }
 }
@@ -1598,6 +1973,11 @@ struct GrimbEngine {
   DevBuf buckets;    // the general kernel's work, by cost bucket (heaviest first)
   int sm_count = 0;
   int fast_path = 1; // GRIMB_FAST=0 disables the warp-per-subject kernel (debugging / A-B runs)
+  int fast_split = 1; // k_fast_probe + k_fast_score (default); GRIMB_FAST_SPLIT=0: the fused k_impute_fast
+  DevBuf mid;         // hand-over records of the split fast path
+  DevBuf overflow;    // subjects with more candidate phases than a hand-over record holds
+  cudaEvent_t ev_score[2] = {nullptr, nullptr};
+  int ev_score_valid = 0;
   // CUDA events around the last launch of k_impute_fast [0,1], k_impute [2,3], k_impute_typed [4,5]
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int ev_valid[3] = {0, 0, 0};
@@ -1662,6 +2042,9 @@ extern "C" int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes
   }
   const char* fp = getenv("GRIMB_FAST");
   if (fp && fp[0] == '0') e->fast_path = 0;
+  const char* fsp = getenv("GRIMB_FAST_SPLIT");
+  if (fsp && fsp[0] == '0') e->fast_split = 0;
+  for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&e->ev_score[i]));
   const char* th = getenv("GRIMB_THREADS");
   if (th) {
     int v = atoi(th);
@@ -1697,6 +2080,14 @@ extern "C" int64_t grimb_engine_launches(const GrimbEngine* e) { return e ? e->l
 // returned.  < 0 if not launched.
 extern "C" double grimb_engine_kernel_ms(const GrimbEngine* e, int which) {
   if (e && which == 3) return e->last_worklist;   // diagnostic: subjects handed to k_impute by the last call
+  if (e && which == 4) {                           // k_fast_score of the split fast path
+    float ms4 = -1.f;
+    if (!e->ev_score_valid || cudaEventElapsedTime(&ms4, e->ev_score[0], e->ev_score[1]) != cudaSuccess) {
+      cudaGetLastError();
+      return -1.0;
+    }
+    return (double)ms4;
+  }
   if (!e || which < 0 || which > 2 || !e->ev_valid[which]) return -1.0;
   float ms = -1.f;
   if (cudaEventElapsedTime(&ms, e->ev[2 * which], e->ev[2 * which + 1]) != cudaSuccess) {
@@ -1739,12 +2130,50 @@ static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBat
     const uint64_t groups = ((uint64_t)batch->n_subjects + FAST_WARPS * 2 - 1) / (FAST_WARPS * 2);
     uint64_t fg = (uint64_t)e->sm_count * FAST_MIN_BLOCKS;  // resident CTAs only: each warp strides over subjects
     if (fg > groups) fg = groups;
+#if GRIMB_KW == 1
+    if (e->fast_split) {
+      CK(e->mid.reserve((size_t)batch->n_subjects * sizeof(FastMid) + 16));
+      double eps = cfg->epsilon;
+      int nr = 0;
+      while (eps > 0 && nr < FAST_MAX_ROUNDS) {
+        eps /= 10;
+        if (eps < 1.0e-9) eps = 0.0;
+        ++nr;
+      }
+      uint64_t fgp = (uint64_t)e->sm_count * FASTPROBE_MIN_BLOCKS;
+      if (fgp > groups) fgp = groups;
+      CK(cudaEventRecord(e->ev[0], st));
+      CK(e->overflow.reserve((size_t)batch->n_subjects * 4 + 16));
+      unsigned int* ovf_n = (unsigned int*)(e->d_counters + 6);
+      k_fast_probe<<<(unsigned)fgp, FAST_WARPS * 32, 0, st>>>(tv, *batch, O, (FastMid*)e->mid.p, (uint32_t*)e->worklist.p,
+                                                            cnt, (uint32_t*)e->overflow.p, ovf_n, eps > 0 ? 0 : 1);
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(e->ev[1], st));
+      uint64_t sg = ((uint64_t)batch->n_subjects + 127) / 128;
+      if (sg > (uint64_t)e->sm_count * 16) sg = (uint64_t)e->sm_count * 16;
+      CK(cudaEventRecord(e->ev_score[0], st));
+      k_fast_score<<<(unsigned)sg, 128, 0, st>>>(tv, e->d_cfg, *batch, O, (const FastMid*)e->mid.p,
+                                                (uint32_t*)e->worklist.p, cnt);
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(e->ev_score[1], st));
+      // subjects with more than FAST_CMAX candidate phases: the fused kernel over the overflow list
+      k_impute_fast<true><<<(unsigned)e->sm_count, FAST_WARPS * 32, 0, st>>>(tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt,
+                                                                     (const uint32_t*)e->overflow.p, ovf_n);
+      CK(cudaGetLastError());
+      e->ev_score_valid = 1;
+      e->ev_valid[0] = 1;
+      e->launches += 3;
+    } else
+#endif
+    {
     CK(cudaEventRecord(e->ev[0], st));
-    k_impute_fast<<<(unsigned)fg, FAST_WARPS * 32, 0, st>>>(tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt);
+    k_impute_fast<false><<<(unsigned)fg, FAST_WARPS * 32, 0, st>>>(tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt, nullptr,
+                                                           nullptr);
     CK(cudaGetLastError());
     CK(cudaEventRecord(e->ev[1], st));
     e->ev_valid[0] = 1;
     e->launches += 1;
+    }
     wl = (const uint32_t*)e->worklist.p;
     wl_n = cnt;
   } else
