@@ -1288,7 +1288,10 @@ k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid,
   }
 }
 
-__global__ void __launch_bounds__(128)
+#ifndef FASTSCORE_MIN_BLOCKS
+#define FASTSCORE_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, FASTSCORE_MIN_BLOCKS)
 k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O,
              const FastMid* __restrict__ mid, uint32_t* worklist, unsigned int* worklist_n) {
   __shared__ double s_chain[FAST_MAX_ROUNDS];
