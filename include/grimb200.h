@@ -142,7 +142,8 @@ typedef struct {
 typedef struct {
   int64_t n_subjects;
   const uint16_t* typed_mask;   /* [S] bit l set = locus l typed; 0 = skip subject (GRIMB_ST_SKIPPED) */
-  const uint16_t* counts;       /* [S][L][2] alleles listed per locus and chromosome side           */
+  const uint16_t* counts;       /* [S][L][2] alleles listed per locus and chromosome side; >= 1 for
+                                   every typed locus (an empty side is one unknown allele), 0 otherwise */
   const uint32_t* allele_off;   /* [S+1] offset of the subject's allele ids in `alleles`            */
   const uint16_t* alleles;      /* ids, per subject: locus ascending, side 0 then 1; ids > n_alleles[l]
                                    are subject-local names of alleles absent from the table        */

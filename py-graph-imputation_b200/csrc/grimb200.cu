@@ -1170,16 +1170,17 @@ struct __align__(16) FastMid {
 #define FASTPROBE_MIN_BLOCKS 5
 #endif
 
-// inputs of the probe kernel (no prior: k_fast_score reads it)
+// inputs of the probe kernel (no prior: k_fast_score reads it).  Every typed locus side lists at least
+// one allele (GrimbBatch.counts >= 1, include/grimb200.h), so "one allele per side at every locus" is
+// allele_off[s+1] - allele_off[s] == 2L and the counts need not be read.
 struct ProbeIn {
-  uint32_t typed, c, pair;
+  uint32_t typed, nall, pair;
 };
 
 __device__ __forceinline__ void probe_load(ProbeIn& in, const GrimbBatch& B, uint32_t s, int L, int i) {
   in.typed = B.typed_mask[s];
   const uint32_t off = B.allele_off[s];
-  const uint32_t* c32 = reinterpret_cast<const uint32_t*>(B.counts + (uint64_t)s * L * 2);
-  in.c = i < L ? c32[i] : 0x00010001u;
+  in.nall = B.allele_off[s + 1] - off;
   in.pair = 0;
   if (i < L) {
     const uint16_t* al = B.alleles + off + 2 * i;
@@ -1212,8 +1213,7 @@ k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid,
     const ProbeIn in = nxt;
     if (s + stride < S && s + stride > s) probe_load(nxt, B, s + stride, L, i);
     const uint32_t typed = in.typed;
-    bool shape = typed == full && nchain_ok;
-    shape = __all_sync(hmask, in.c == 0x00010001u) && shape;
+    const bool shape = typed == full && nchain_ok && in.nall == 2u * (uint32_t)L;   // uniform in the half-warp
     uint32_t state = 0, ncand = 0, gsel = 0, phases = 0;
     if (shape) {
       const uint32_t a0 = in.pair & 0xffffu, a1 = in.pair >> 16;
@@ -1227,10 +1227,14 @@ k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid,
         h0.w = (uint32_t)(k1 >> 32);
         reinterpret_cast<uint4*>(mid + s)[0] = h0;
       }
-      const uint32_t unk0 = (__ballot_sync(hmask, i < L && (a0 - 1u) >= my_nal) >> hbase) & 0xFFFFu;
-      const uint32_t unk1 = (__ballot_sync(hmask, i < L && (a1 - 1u) >= my_nal) >> hbase) & 0xFFFFu;
-      const uint32_t het = (__ballot_sync(hmask, a0 != a1) >> hbase) & 0xFFFFu;
-      gsel = (__ballot_sync(hmask, a0 > a1) >> hbase) & 0xFFFFu;
+      // four per-locus flags in one OR-reduction: byte k of `packed` is the locus mask of flag k
+      uint32_t bits = 0;
+      if (i < L)
+        bits = ((((a0 - 1u) >= my_nal) ? 1u : 0u) | (((a1 - 1u) >= my_nal) ? 0x100u : 0u) | ((a0 != a1) ? 0x10000u : 0u) |
+                ((a0 > a1) ? 0x1000000u : 0u)) << i;
+      const uint32_t packed = __reduce_or_sync(hmask, bits);
+      const uint32_t unk0 = packed & 0xFFu, unk1 = (packed >> 8) & 0xFFu, het = (packed >> 16) & 0xFFu;
+      gsel = packed >> 24;
       const uint64_t D = k0 ^ k1;
       const uint64_t key = k0 ^ (D & Mi), key2 = key ^ D;
       const uint32_t ib = (uint32_t)i;
