@@ -845,14 +845,8 @@ __device__ __forceinline__ void ht_lookup2(const HSlot* __restrict__ base, uint3
   HSlot a0, a1, b0, b1;
   a0.node = a1.node = b0.node = b1.node = GRIMB_NONE;
   a0.key = a1.key = b0.key = b1.key = 0;
-  if (p1) {
-    a0 = load_slot(base + h1);
-    a1 = load_slot(base + h1 + 1);
-  }
-  if (p2) {
-    b0 = load_slot(base + h2);
-    b1 = load_slot(base + h2 + 1);
-  }
+  if (p1) load_sector(base + h1, a0, a1);
+  if (p2) load_sector(base + h2, b0, b1);
   bool more1 = false, more2 = false;
   if (p1) {
     if (a0.node == GRIMB_NONE) {}
@@ -870,8 +864,7 @@ __device__ __forceinline__ void ht_lookup2(const HSlot* __restrict__ base, uint3
   }
   while (more1) {
     h1 = (h1 + 2) & mask;
-    a0 = load_slot(base + h1);
-    a1 = load_slot(base + h1 + 1);
+    load_sector(base + h1, a0, a1);
     more1 = false;
     if (a0.node == GRIMB_NONE) {}
     else if (a0.key == k1) n1 = a0.node;
@@ -881,8 +874,7 @@ __device__ __forceinline__ void ht_lookup2(const HSlot* __restrict__ base, uint3
   }
   while (more2) {
     h2 = (h2 + 2) & mask;
-    b0 = load_slot(base + h2);
-    b1 = load_slot(base + h2 + 1);
+    load_sector(base + h2, b0, b1);
     more2 = false;
     if (b0.node == GRIMB_NONE) {}
     else if (b0.key == k2) n2 = b0.node;

@@ -85,6 +85,27 @@ GD HSlot load_slot(const HSlot* p) {
 #endif
 }
 
+#if GRIMB_KW == 1
+// Both slots of a 32-byte sector with ONE 256-bit load (sm_100: LDG.E.256); p must be sector aligned.
+GD void load_sector(const HSlot* p, HSlot& s0, HSlot& s1) {
+#if GRIMB_DEVICE
+  uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+               : "l"(p));
+  s0.key = (uint64_t)r0 | ((uint64_t)r1 << 32);
+  s0.node = r2;
+  s0.pad = r3;
+  s1.key = (uint64_t)r4 | ((uint64_t)r5 << 32);
+  s1.node = r6;
+  s1.pad = r7;
+#else
+  s0 = p[0];
+  s1 = p[1];
+#endif
+}
+#endif
+
 // Home slot of a key: always the first slot of a 32-byte sector (two 16-byte slots), so a probe
 // reads whole sectors -- both slots of a sector are fetched by two adjacent 128-bit loads that
 // resolve to one memory transaction.
@@ -97,8 +118,8 @@ GD uint32_t ht_lookup(const TablesView& T, uint32_t label, hkey key) {
   const HSlot* base = T.slots + T.ht_off[label];
   uint32_t h = ht_home(key, mask);
   for (;;) {
-    const HSlot s0 = load_slot(base + h);
-    const HSlot s1 = load_slot(base + h + 1);
+    HSlot s0, s1;
+    load_sector(base + h, s0, s1);
     if (s0.node == GRIMB_NONE) return GRIMB_NONE;
     if (s0.key == key) return s0.node;
     if (s1.node == GRIMB_NONE) return GRIMB_NONE;
