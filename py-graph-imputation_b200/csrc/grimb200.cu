@@ -2156,7 +2156,7 @@ static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBat
       CK(cudaGetLastError());
       CK(cudaEventRecord(e->ev_score[1], st));
       // subjects with more than FAST_CMAX candidate phases: the fused kernel over the overflow list
-      k_impute_fast<true><<<(unsigned)e->sm_count, FAST_WARPS * 32, 0, st>>>(tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt,
+      k_impute_fast<true><<<32u, FAST_WARPS * 32, 0, st>>>(tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt,
                                                                      (const uint32_t*)e->overflow.p, ovf_n);
       CK(cudaGetLastError());
       e->ev_score_valid = 1;
