@@ -67,17 +67,22 @@ GD hkey key_mask_of(const TablesView& T, uint32_t label) {
 
 GD HSlot load_slot(const HSlot* p) {
 #if GRIMB_DEVICE
-  uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
   HSlot s;
 #if GRIMB_KW == 1
+  uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
   s.key = (uint64_t)v.x | ((uint64_t)v.y << 32);
   s.node = v.z;
   s.pad = v.w;
 #else
-  uint4 w = __ldg(reinterpret_cast<const uint4*>(p) + 1);
-  s.key = (hkey)((uint64_t)v.x | ((uint64_t)v.y << 32)) | ((hkey)((uint64_t)v.z | ((uint64_t)v.w << 32)) << 64);
-  s.node = w.x;
+  // a 32-byte slot is one sector: one 256-bit load (sm_100: LDG.E.256)
+  uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+               : "l"(p));
+  s.key = (hkey)((uint64_t)r0 | ((uint64_t)r1 << 32)) | ((hkey)((uint64_t)r2 | ((uint64_t)r3 << 32)) << 64);
+  s.node = r4;
   s.pad[0] = s.pad[1] = s.pad[2] = 0;
+  (void)r5; (void)r6; (void)r7;
 #endif
   return s;
 #else
