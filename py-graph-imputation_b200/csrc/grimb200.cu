@@ -1327,14 +1327,19 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
     uint64_t k0 = 0, k1 = 0;
     double m = 0.0;
     uint32_t fl = 0;
+    double2 f0 = make_double2(0.0, 0.0);
     if (s < S) {
+      // everything that does not depend on the header is requested with it: the prior (P == 1: one
+      // double per subject) and the first candidate's frequencies
       const uint4* src = reinterpret_cast<const uint4*>(mid + s);
       const uint4 h0 = src[0], h1 = src[1];
+      const uint32_t pi = B.prior_index[s];
+      f0 = *reinterpret_cast<const double2*>(&mid[s].f[0][0]);   // garbage unless ncand >= 1
+      m = __ldg(B.priors + pi);
       k0 = (uint64_t)h0.x | ((uint64_t)h0.y << 32);
       k1 = (uint64_t)h0.z | ((uint64_t)h0.w << 32);
       fl = h1.z;
       ready = (fl & 3u) == 1u;
-      if (ready) m = __ldg(B.priors + B.prior_index[s]);   // P == 1: one prior per subject
     }
     const uint32_t ncand = ready ? ((fl >> 2) & 7u) : 0u;
     const uint32_t gsel = (fl >> 8) & 31u;
@@ -1351,7 +1356,7 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
       rq[q] = 99;
       acc[q] = false;
       if ((uint32_t)q < ncand) {
-        const double2 v = *reinterpret_cast<const double2*>(&mid[s].f[q][0]);
+        const double2 v = q == 0 ? f0 : *reinterpret_cast<const double2*>(&mid[s].f[q][0]);
         FastPair pr;
         pr.f = v.x;
         pr.f2 = v.y;
