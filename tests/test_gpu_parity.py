@@ -223,7 +223,10 @@ def test_readme_flow_with_packaged_defaults(tmp_path, monkeypatch):
     from grim import grim
     pkg = os.path.dirname(os.path.dirname(os.path.abspath(generate_hpf.__file__)))
     d = str(tmp_path)
-    shutil.copytree(os.path.join(pkg, "data"), d + "/data")
+    os.makedirs(d + "/data/freqs")
+    os.makedirs(d + "/data/subjects")
+    shutil.copy(os.path.join(goldenlib.GOLD, "data", "CAU.freqs.gz"), d + "/data/freqs/CAU.freqs.gz")
+    shutil.copy(os.path.join(goldenlib.GOLD, "data", "donor.csv"), d + "/data/subjects/donor.csv")
     shutil.copytree(os.path.join(pkg, "conf"), d + "/conf")
     monkeypatch.chdir(d)
     generate_hpf.produce_hpf("conf/minimal-configuration.json")

@@ -122,7 +122,7 @@ def test_open_gl_string_matches_reference_fixture():
 
 
 def test_produce_hpf_matches_reference_output(tmp_path):
-    """README step 1: produce_hpf on the packaged CAU.freqs.gz must write the same hpf.csv and
+    """README step 1: produce_hpf on the example CAU.freqs.gz (fixture) must write the same hpf.csv and
     pop_counts_file.txt the reference's produce_hpf wrote (tests/golden/data/cau_*)."""
     import json
     import os
@@ -132,7 +132,7 @@ def test_produce_hpf_matches_reference_output(tmp_path):
     conf = json.load(open(os.path.join(pkg, "conf", "minimal-configuration.json")))
     assert conf == json.load(open(os.path.join(goldenlib.GOLD, "data", "base_conf.json")))
     d = str(tmp_path)
-    conf["freq_data_dir"] = os.path.join(pkg, "data", "freqs")
+    conf["freq_data_dir"] = os.path.join(goldenlib.GOLD, "data")     # CAU.freqs.gz: the README example's input
     conf["graph_files_path"] = d + "/csv/"
     conf["freq_file"] = d + "/hpf.csv"
     conf["pops_count_file"] = d + "/pop_counts_file.txt"
