@@ -167,6 +167,7 @@ struct GrimbText {
   std::string text;   // private copy of the input (string_views point into it)
   int64_t first_index = 0;
   std::vector<Line> lines;
+  std::vector<std::string> fmt_parts;   // per-thread pieces of the six outputs (capacity reused)
   std::vector<std::vector<uint16_t>> t_ids;
   std::vector<std::vector<Unknown>> t_unk;
   std::vector<std::string> t_clean;  // unused placeholder (cleaned GL strings are per-call locals)
@@ -274,7 +275,23 @@ struct GrimbText {
     for (double& m : M) m = m / total;
   }
 
+  // consecutive lines mostly repeat the race fields: remember the last key
+  bool last_has_race = false, last_valid = false;
+  sv last_r1, last_r2;
+  uint32_t last_prior = 0;
+
   uint32_t prior_for(const Line& ln) {
+    if (last_valid && ln.has_race == last_has_race && ln.race1 == last_r1 && ln.race2 == last_r2) return last_prior;
+    const uint32_t idx = prior_lookup(ln);
+    last_valid = true;
+    last_has_race = ln.has_race;
+    last_r1 = ln.race1;      // views into this call's text buffer: reset by grimb_text_tokenise
+    last_r2 = ln.race2;
+    last_prior = idx;
+    return idx;
+  }
+
+  uint32_t prior_lookup(const Line& ln) {
     PriorKey k{ln.has_race, std::string(ln.race1), std::string(ln.race2)};
     auto it = prior_index.find(k);
     if (it != prior_index.end()) return it->second;
@@ -307,7 +324,8 @@ struct GrimbText {
 
   // one input line -> Line (reference impute.py:2022-2036 + clean_up_gl + gl2haps)
   void parse_line(sv raw_line, Line& ln, int thread, bool planb, std::string& clean, std::vector<sv>& f1,
-                  std::vector<sv>& f2, std::vector<sv>& t1, std::vector<sv>& t2) {
+                  std::vector<sv>& f2, std::vector<sv>& t1, std::vector<sv>& t2, std::vector<sv>& names,
+                  std::vector<uint16_t>& scr) {
     size_t e = raw_line.size();
     while (e > 0 && py_space((unsigned char)raw_line[e - 1])) --e;
     sv raw = raw_line.substr(0, e);
@@ -371,7 +389,9 @@ struct GrimbText {
     std::vector<uint16_t>& idv = t_ids[thread];
     std::vector<Unknown>& unk = t_unk[thread];
     const uint32_t ids_off = (uint32_t)idv.size(), unk_off = (uint32_t)unk.size();
-    std::vector<uint16_t> per[GRIMB_MAX_LOCI][2];
+    // the id lists of this line, built in a reused scratch vector: [off, off + cnt) per locus and side
+    scr.clear();
+    uint32_t per_off[GRIMB_MAX_LOCI][2] = {{0}}, per_cnt[GRIMB_MAX_LOCI][2] = {{0}};
     bool used[GRIMB_MAX_LOCI] = {false};
     auto foreign = [&]() {
       idv.resize(ids_off);
@@ -379,7 +399,6 @@ struct GrimbText {
       ln.hclass = planb ? H_FAULT : H_OK;  // mask stays 0: nothing is imputed
       ln.mask = 0;
     };
-    std::vector<sv> names;
     for (size_t k = 0; k < t1.size(); ++k) {
       sv first = t1[k].substr(0, t1[k].find('/'));
       sv prefix = first.substr(0, first.find('*'));
@@ -392,6 +411,8 @@ struct GrimbText {
       std::vector<std::pair<sv, uint16_t>> local;
       for (int x = 0; x < 2; ++x) {
         split(x ? t2[k] : t1[k], '/', names);
+        const uint32_t lst_off = (uint32_t)scr.size();
+        per_off[l][x] = lst_off;
         for (sv name : names) {
           if (name.substr(0, name.find('*')) != sv(loci[l])) return foreign();
           uint16_t id = 0;
@@ -413,9 +434,9 @@ struct GrimbText {
               unk.push_back(Unknown{(uint8_t)l, id, std::string(name)});
             }
           }
-          auto& lst = per[l][x];
-          if (std::find(lst.begin(), lst.end(), id) == lst.end()) lst.push_back(id);
+          if (std::find(scr.begin() + lst_off, scr.end(), id) == scr.end()) scr.push_back(id);
         }
+        per_cnt[l][x] = (uint32_t)scr.size() - lst_off;
       }
     }
     memset(ln.counts, 0, sizeof(ln.counts));
@@ -423,8 +444,8 @@ struct GrimbText {
       if (used[l]) {
         ln.mask |= (uint16_t)(1u << l);
         for (int x = 0; x < 2; ++x) {
-          ln.counts[l * 2 + x] = (uint16_t)per[l][x].size();
-          idv.insert(idv.end(), per[l][x].begin(), per[l][x].end());
+          ln.counts[l * 2 + x] = (uint16_t)per_cnt[l][x];
+          idv.insert(idv.end(), scr.begin() + per_off[l][x], scr.begin() + per_off[l][x] + per_cnt[l][x]);
         }
       }
     ln.ids_off = ids_off;
@@ -607,14 +628,16 @@ extern "C" int grimb_text_tokenise(GrimbText* t, const GrimbConfig* cfg, const c
   t->lines.assign(S, Line());
   t->t_ids.assign((size_t)t->n_threads, {});
   t->t_unk.assign((size_t)t->n_threads, {});
+  t->last_valid = false;   // the remembered race fields point into the previous call's text
   const bool planb = cfg->planb != 0;
   // the cleaned GL strings must outlive the call for unknown-allele names: names are copied
   t->parallel(S, [&](int th, size_t lo, size_t hi) {
     std::string clean;
-    std::vector<sv> f1, f2, t1, t2;
+    std::vector<sv> f1, f2, t1, t2, names;
+    std::vector<uint16_t> scr;
     for (size_t i = lo; i < hi; ++i)
       t->parse_line(sv(t->text.data() + bounds[i].first, bounds[i].second - bounds[i].first), t->lines[i], th, planb,
-                    clean, f1, f2, t1, t2);
+                    clean, f1, f2, t1, t2, names, scr);
   });
   // sequential: prior indices (memoised) + flat batch arrays
   const int L = t->L;
@@ -663,7 +686,10 @@ extern "C" int grimb_text_format(GrimbText* t, const GrimbConfig* cfg, const Gri
   if (!t || !cfg || !res || !out) return tfail(GRIMB_E_ARG, "null argument");
   const size_t S = t->lines.size();
   const int nt = t->n_threads;
-  std::vector<std::string> parts((size_t)nt * 6);
+  // per-thread output pieces live in the GrimbText so their capacity is reused from call to call
+  std::vector<std::string>& parts = t->fmt_parts;
+  parts.resize((size_t)nt * 6);
+  for (auto& ps : parts) ps.clear();
   std::vector<int64_t> evals((size_t)nt, 0);
   std::vector<int64_t> plans((size_t)nt * 4, 0);
   t->parallel(S, [&](int th, size_t lo, size_t hi) {
@@ -711,15 +737,25 @@ extern "C" int grimb_text_format(GrimbText* t, const GrimbConfig* cfg, const Gri
   });
   out->pair_evals = 0;
   for (int k = 0; k < 4; ++k) out->plan_count[k] = 0;
+  // concatenate the pieces of every output in thread order, the copies themselves in parallel
+  std::vector<size_t> offs((size_t)nt * 6, 0);
   for (int k = 0; k < 6; ++k) {
     size_t n = 0;
-    for (int th = 0; th < nt; ++th) n += parts[(size_t)th * 6 + k].size();
-    t->out[k].clear();
-    t->out[k].reserve(n);
-    for (int th = 0; th < nt; ++th) t->out[k] += parts[(size_t)th * 6 + k];
+    for (int th = 0; th < nt; ++th) {
+      offs[(size_t)th * 6 + k] = n;
+      n += parts[(size_t)th * 6 + k].size();
+    }
+    if (t->out[k].size() < n) t->out[k].resize(n);   // grow-only buffer; size[k] carries the valid length
     out->data[k] = t->out[k].data();
-    out->size[k] = (int64_t)t->out[k].size();
+    out->size[k] = (int64_t)n;
   }
+  t->parallel((size_t)nt, [&](int, size_t lo, size_t hi) {
+    for (size_t th = lo; th < hi; ++th)
+      for (int k = 0; k < 6; ++k) {
+        const std::string& ps = parts[th * 6 + k];
+        if (!ps.empty()) memcpy(&t->out[k][offs[th * 6 + k]], ps.data(), ps.size());
+      }
+  });
   for (int th = 0; th < nt; ++th) {
     out->pair_evals += evals[th];
     for (int k = 0; k < 4; ++k) out->plan_count[k] += plans[(size_t)th * 4 + k];
