@@ -22,10 +22,16 @@ BASE_CONF = json.load(open(os.path.join(HERE, "data", "base_conf.json")))
 CAU = open(os.path.join(HERE, "data", "cau_hpf.csv")).read()
 
 
-def compare(tag, sess, hpf, counts, lines, **over):
+def compare(tag, sess, hpf, counts, lines, hap_pop_pair=False, phase_masks=None, **over):
     conf = dict(sess.conf)
     conf.update(over)
-    ref = sess.run(lines, **over)
+    ref = sess.run(lines, hap_pop_pair=hap_pop_pair, phase_masks=phase_masks, **over)
+    if phase_masks is not None:
+        import tempfile
+        fd, path = tempfile.mkstemp(suffix=".json")
+        with os.fdopen(fd, "w") as f:
+            json.dump(phase_masks, f)
+        conf["bin_imputation_in_file"] = path
     t = time.time()
     g = go.OracleGraph(hpf.splitlines(True), conf["populations"], conf["loci_map"],
                        conf["freq_trim_threshold"], counts.splitlines(True) if counts else None)
@@ -35,7 +41,7 @@ def compare(tag, sess, hpf, counts, lines, **over):
         import numpy as np
         cbp = np.array([float(l.split(",")[2]) for l in counts.splitlines()])
     imp = go.OracleImputation(g, cfg, cbp)
-    mine = imp.impute_lines(lines)
+    mine = imp.impute_lines(lines, em_mr=hap_pop_pair)
     dt = time.time() - t
     bad = [k for k in ref if ref[k] != mine[k]]
     print("%-40s %5d subj  %s  (%.1fs oracle)  rows umug=%d pmug=%d miss=%d problem=%d" % (
@@ -95,6 +101,20 @@ def main():
                   number_of_options_threshold=40)
     ok &= compare("pop3 messy eta>0", s3, hpf3, cnt3, synth.messy_subjects(tab3, n, seed + 14, races=races),
                   priority={"alpha": 0.4, "eta": 0.01, "beta": 1e-3, "gamma": 1e-2, "delta": 0.3})
+    # EM-facing modes: hap_pop_pair rows and per-subject phase masks
+    import numpy as np
+    rng = np.random.RandomState(seed + 20)
+
+    def masks_for(lines):
+        return {ln.split(",")[0]: [int(x) for x in rng.randint(0, 2, size=4)] for ln in lines}
+
+    lines = synth.typed_subjects(tab3, n, seed + 15, races) + synth.messy_subjects(tab3, n, seed + 16, races=races)
+    ok &= compare("pop3 hap_pop_pair", s3, hpf3, cnt3, lines, hap_pop_pair=True)
+    ok &= compare("pop3 hap_pop_pair nres=4", s3, hpf3, cnt3, lines, hap_pop_pair=True, number_of_results=4)
+    ok &= compare("pop3 phase masks", s3, hpf3, cnt3, lines, phase_masks=masks_for(lines))
+    lines = synth.messy_subjects(tab3, n, seed + 17, max_amb=3, p_missing=0.4, races=races)
+    ok &= compare("pop3 phase masks missing loci", s3, hpf3, cnt3, lines, phase_masks=masks_for(lines))
+    ok &= compare("pop3 phase masks + hap_pop_pair", s3, hpf3, cnt3, lines, hap_pop_pair=True, phase_masks=masks_for(lines))
     s3.close()
     print("ALL OK" if ok else "SOME MISMATCH")
     return 0 if ok else 1

@@ -238,3 +238,30 @@ def test_readme_flow_with_packaged_defaults(tmp_path, monkeypatch):
     for k, fn in names.items():
         assert open(os.path.join(d, "output", fn)).read() == exp[k], k
     g.close()
+
+
+@pytest.mark.parametrize("mode", ["masks", "hap_pop_pair", "both"])
+def test_em_modes_match_oracle_on_seeded_inputs(mode, tmp_path):
+    """SURVEY 8(f)-4 modes beyond the golden cases: random per-subject phase masks and / or the
+    hap_pop_pair output on seeded typed + messy subjects (3 populations), CUDA path vs oracle."""
+    import json
+    from grim.imputation.impute import Imputation
+    from grim.run_impute_def import load_config
+    _, conf, _, _ = goldenlib.load_case("g3_pop3_typed")
+    conf = dict(conf)
+    pops = conf["populations"]
+    tab = synth.Table(open(conf["freq_file"]).read(), pops[0])
+    races = synth.race_fields(pops)
+    lines = synth.typed_subjects(tab, 200, 301, races) + synth.messy_subjects(tab, 120, 302, max_amb=3, races=races)
+    if mode in ("masks", "both"):
+        rng = np.random.RandomState(303)
+        masks = {ln.split(",")[0]: [int(x) for x in rng.randint(0, 2, size=4)] for ln in lines}
+        path = str(tmp_path / "masks.json")
+        json.dump(masks, open(path, "w"))
+        conf["bin_imputation_in_file"] = path
+    em_mr = mode in ("hap_pop_pair", "both")
+    imp = Imputation(_graph("pop3", conf), load_config(conf))
+    out = {k: "".join(v) for k, v in imp.impute_lines(lines, em_mr=em_mr).items()}
+    ref, _ = go.impute_file(conf, graph=_oracle_graph("pop3", conf), lines=lines, em_mr=em_mr)
+    for k in goldenlib.KEYS:
+        assert out[k] == ref[k], "%s differs" % k
