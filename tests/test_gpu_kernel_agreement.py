@@ -1,7 +1,8 @@
 """GPU, BASELINE-size property: the warp-per-subject kernels (k_impute_fast, k_impute_typed) and the
 general CTA-per-subject kernel (k_impute) are independent implementations of the same path.  The
 general kernel is pinned against the reference on the golden cases; here both are run on large
-seeded batches (sizes the CPU oracle cannot reach) and must produce byte-identical files."""
+seeded batches (2^20 single-population subjects = BASELINE config 2 at full size, 200 k subjects x 21
+populations; sizes the CPU oracle cannot reach) and must produce byte-identical files."""
 import json
 import os
 
@@ -63,7 +64,7 @@ def test_typed_kernel_equals_general_kernel_21_populations(tmp_path, monkeypatch
     conf.update({"populations": pops, "UNK_priors": "MR", "number_of_pop_results": 100})
     tab = synth.Table(hpf, "P00")
     races = synth.race_fields(pops)
-    lines = synth.typed_subjects(tab, 60000, 11, races) + _homozygous(tab, 1500, 12, races)
+    lines = synth.typed_subjects(tab, 200000, 11, races) + _homozygous(tab, 1500, 12, races)
     _both(conf, hpf, cnt, lines, tmp_path, monkeypatch)
 
 
@@ -84,5 +85,6 @@ def test_fast_kernel_equals_general_kernel_single_population(tmp_path, monkeypat
     cau = open(os.path.join(goldenlib.GOLD, "data", "cau_hpf.csv")).read()
     cnt = open(os.path.join(goldenlib.GOLD, "data", "cau_pop_counts.txt")).read()
     tab = synth.Table(cau)
-    lines = synth.typed_subjects(tab, 1 << 17, 15, ["CAU,CAU"]) + _homozygous(tab, 2000, 16, ["CAU,CAU"])
+    # BASELINE config 2 at full size: 2^20 subjects
+    lines = synth.typed_subjects(tab, 1 << 20, 15, ["CAU,CAU"]) + _homozygous(tab, 2000, 16, ["CAU,CAU"])
     _both(dict(base), cau, cnt, lines, tmp_path, monkeypatch)
