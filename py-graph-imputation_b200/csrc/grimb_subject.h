@@ -607,6 +607,7 @@ struct Ctx {
     uint32_t* ghead = alloc<uint32_t>(ent_n);    // group -> first member
     double* gsum = alloc<double>(ent_n);
     uint32_t* gord = alloc<uint32_t>(ent_n);
+    uint8_t* own = alloc<uint8_t>((uint64_t)ent_n + 16);   // entry -> owning thread of its group (0xFF: group head)
     if (ws_fail) return 0;
     for (uint32_t i = g.tid; i < tsz; i += g.n) tab[i] = GRIMB_NONE;
     g.sync();
@@ -651,15 +652,41 @@ struct Ctx {
     for (uint32_t i = g.tid; i < ent_n; i += g.n) where[i] = slot_gid[where[i]];
     g.sync();
     if (ng < ent_n) {
-      // += in encounter order: thread t owns the groups with (id & tmask) == t
+      // += in encounter order: thread t owns the groups with (id & tmask) == t and walks ALL entries in
+      // order, adding the ones it owns.  The walk reads one owner byte per entry, 16 entries per load and
+      // 4 per SIMD compare, so the scan costs ~0.6 instructions per entry and thread instead of 3.
       uint32_t tpow = 1;
-      while (tpow * 2 <= (uint32_t)g.n) tpow <<= 1;
+      while (tpow * 2 <= (uint32_t)g.n && tpow * 2 <= 128u) tpow <<= 1;   // owner ids stay below the 0xFF marker
+      const uint32_t tmask = tpow - 1;
+      for (uint32_t i = g.tid; i < ent_n + 16u; i += g.n)
+        own[i] = (i < ent_n && ghead[where[i]] != i) ? (uint8_t)(where[i] & tmask) : (uint8_t)0xFF;
+      g.sync();
       if ((uint32_t)g.tid < tpow) {
-        const uint32_t tmask = tpow - 1, me = (uint32_t)g.tid;
-        for (uint32_t i = 0; i < ent_n; ++i) {
-          const uint32_t gi = where[i];
-          if ((gi & tmask) == me && ghead[gi] != i) gsum[gi] = gsum[gi] + E[i].prob;
+        const uint32_t me = (uint32_t)g.tid;
+#if GRIMB_DEVICE
+        const uint32_t me4 = me * 0x01010101u;
+        for (uint32_t i0 = 0; i0 < ent_n; i0 += 16) {
+          const uint4 v = *reinterpret_cast<const uint4*>(own + i0);
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint32_t m = __vcmpeq4(w[k], me4);   // 0xFF in every byte that names this thread
+            while (m) {
+              const int b = (__ffs(m) - 1) >> 3;   // lowest byte = lowest entry index first
+              const uint32_t i = i0 + 4u * k + (uint32_t)b;
+              const uint32_t gi = where[i];
+              gsum[gi] = gsum[gi] + E[i].prob;
+              m &= ~(0xFFu << (8 * b));
+            }
+          }
         }
+#else
+        for (uint32_t i = 0; i < ent_n; ++i)
+          if (own[i] == (uint8_t)me) {
+            const uint32_t gi = where[i];
+            gsum[gi] = gsum[gi] + E[i].prob;
+          }
+#endif
       }
       g.sync();
     }
