@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -768,6 +769,7 @@ k_impute(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArr
   uint64_t bound[GRIMB_BUCKETS + 1];
   bound[0] = 0;
   for (int k = 0; k < GRIMB_BUCKETS; ++k) bound[k + 1] = bound[k] + bucket_n[k];
+  if (bound[GRIMB_BUCKETS] == 0) return;   // nothing was handed to the general kernel (uniform over the grid)
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) sh.work = (uint32_t)atomicAdd(work, 1ull);
@@ -909,6 +911,7 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
               unsigned int* worklist_n, const uint32_t* __restrict__ list, const unsigned int* __restrict__ list_n) {
   __shared__ double s_chain[FAST_MAX_ROUNDS];
   __shared__ int s_nchain;
+  if (LIST && *list_n == 0u) return;   // empty overflow list (the usual case): nothing to set up
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int half = lane >> 4, i = lane & 15, hbase = half << 4;
   const uint32_t hmask = 0xFFFFu << hbase;
@@ -1970,6 +1973,9 @@ struct GrimbEngine {
   cudaEvent_t ev_in[GRIMB_MAX_CHUNKS], ev_k[GRIMB_MAX_CHUNKS];
   unsigned long long* h_cnt = nullptr;            // pinned: counters after every chunk [GRIMB_MAX_CHUNKS][4]
   int64_t host_chunk = 131072;                    // subjects per pipeline chunk (GRIMB_HOST_CHUNK)
+  GrimbConfig cfg_host;                           // the configuration d_cfg holds (valid when cfg_sent)
+  int cfg_sent = 0;
+  unsigned long long* h_tail = nullptr;           // pinned: the 8 counters as read by the device-pointer call
   int64_t launches = 0;
   // staging for the host-pointer form (grow-only)
   DevBuf in[6], outb[3], in_mask;
@@ -2028,6 +2034,7 @@ extern "C" int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes
     CK(cudaEventCreateWithFlags(&e->ev_k[i], cudaEventDisableTiming));
   }
   CK(cudaMallocHost((void**)&e->h_cnt, GRIMB_MAX_CHUNKS * 4 * sizeof(unsigned long long)));
+  CK(cudaMallocHost((void**)&e->h_tail, 8 * sizeof(unsigned long long)));
   if (const char* hc = getenv("GRIMB_HOST_CHUNK")) {
     const long long v = atoll(hc);
     if (v >= 1024) e->host_chunk = v;
@@ -2073,6 +2080,7 @@ extern "C" int grimb_engine_free(GrimbEngine* e) {
     if (e->ev_k[i]) cudaEventDestroy(e->ev_k[i]);
   }
   if (e->h_cnt) cudaFreeHost(e->h_cnt);
+  if (e->h_tail) cudaFreeHost(e->h_tail);
   delete e;
   return GRIMB_OK;
 }
@@ -2113,10 +2121,25 @@ static int check_cfg(const GrimbConfig* c, const GrimbTables* t) {
   return GRIMB_OK;
 }
 
+// The configuration lives in device memory for the kernels; it is uploaded only when it differs from
+// the copy the engine last sent (a pageable-memory copy per call otherwise costs more than a launch).
+static int upload_cfg(GrimbEngine* e, const GrimbConfig* cfg, cudaStream_t st) {
+  if (e->cfg_sent && memcmp(&e->cfg_host, cfg, sizeof(GrimbConfig)) == 0) return GRIMB_OK;
+  e->cfg_sent = 0;
+  CK(cudaStreamSynchronize(e->stream));   // an earlier call on the engine stream may still read d_cfg
+  e->cfg_host = *cfg;
+  CK(cudaMemcpyAsync(e->d_cfg, &e->cfg_host, sizeof(GrimbConfig), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  e->cfg_sent = 1;
+  return GRIMB_OK;
+}
+
 // Launches the kernels for one batch view (device pointers) on `st`; no synchronisation.  The row
 // counters d_counters[1..2] keep running across calls of one ABI call (chunks of one host batch).
 static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch, const OutArrays& O,
                           cudaStream_t st) {
+  e->ev_valid[0] = e->ev_valid[1] = e->ev_valid[2] = 0;
+  e->ev_score_valid = 0;
   if (batch->n_subjects <= 0) return GRIMB_OK;
   // the warp-per-subject kernels implement the default phase enumeration and row layout only
   const bool warp_kernels = e->fast_path && !batch->phase_mask && !cfg->hap_pop_pair;
@@ -2160,13 +2183,14 @@ static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBat
                                                 (uint32_t*)e->worklist.p, cnt);
       CK(cudaGetLastError());
       CK(cudaEventRecord(e->ev_score[1], st));
+      e->ev_score_valid = 1;
+      e->ev_valid[0] = 1;
+      e->launches += 2;
       // subjects with more than FAST_CMAX candidate phases: the fused kernel over the overflow list
       k_impute_fast<true><<<32u, FAST_WARPS * 32, 0, st>>>(tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt,
                                                                      (const uint32_t*)e->overflow.p, ovf_n);
       CK(cudaGetLastError());
-      e->ev_score_valid = 1;
-      e->ev_valid[0] = 1;
-      e->launches += 3;
+      e->launches += 1;
     } else
 #endif
     {
@@ -2224,7 +2248,8 @@ extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const
   if (rc) return rc;
   CK(cudaSetDevice(e->device));
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
-  CK(cudaMemcpyAsync(e->d_cfg, cfg, sizeof(GrimbConfig), cudaMemcpyHostToDevice, st));
+  rc = upload_cfg(e, cfg, st);
+  if (rc) return rc;
   CK(cudaMemsetAsync(e->d_counters, 0, 64, st));
   OutArrays O;
   O.r = *res;
@@ -2233,8 +2258,9 @@ extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const
   rc = launch_kernels(e, cfg, batch, O, st);
   if (rc) return rc;
   unsigned long long cnt[4];
-  CK(cudaMemcpyAsync(cnt, e->d_counters, 32, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(e->h_tail, e->d_counters, 32, cudaMemcpyDeviceToHost, st));   // pinned: no staging copy
   CK(cudaStreamSynchronize(st));
+  for (int k = 0; k < 4; ++k) cnt[k] = e->h_tail[k];
   e->last_worklist = (double)(unsigned int)(cnt[3] & 0xFFFFFFFFull);
   *res->hap_rows_needed = (int64_t)cnt[1];
   *res->pop_rows_needed = (int64_t)cnt[2];
@@ -2274,7 +2300,8 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
   int64_t chunk = e->host_chunk;
   if (S > chunk * GRIMB_MAX_CHUNKS) chunk = (S + GRIMB_MAX_CHUNKS - 1) / GRIMB_MAX_CHUNKS;
   const int nch = S > 0 ? (int)((S + chunk - 1) / chunk) : 0;
-  CK(cudaMemcpyAsync(e->d_cfg, cfg, sizeof(GrimbConfig), cudaMemcpyHostToDevice, st));
+  rc = upload_cfg(e, cfg, st);
+  if (rc) return rc;
   CK(cudaMemsetAsync(e->d_counters, 0, 64, st));
   if (in_bytes[5]) CK(cudaMemcpyAsync(e->in[5].p, b->priors, in_bytes[5], cudaMemcpyHostToDevice, st));
   for (int c = 0; c < nch; ++c) {
