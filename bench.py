@@ -457,8 +457,44 @@ def main():
             traffic = float(rd[2]) * unit[rd[1]] + float(wr[2]) * unit[wr[1]]
         except Exception:
             pass
+        # the probe-bound roofline (BASELINE north_star): what the memory system sustains for the probe's own
+        # access shape -- independent random 32-byte sector loads over a table as large as the full-label
+        # region -- measured by tools/sector_peak.cu on this pool's B200 (profiles/r01_sector_peak_b200.jsonl).
+        # Sectors counted for the kernel: one per probe really issued plus one frequency sector per hit
+        # (continuation sectors of longer chains are not counted, so the fraction is a lower bound).
+        probe_bound = None
+        try:
+            mult = int(os.environ.get("GRIMB_FULL_LOAD_MULT", "8"))
+            region = 16
+            while region < 16 * mult * info.get("n_full", args.haps):
+                region *= 2
+            rows = [json.loads(l) for l in open(os.path.join(ROOT, "profiles", "r01_sector_peak_b200.jsonl"))]
+            rows = [r for r in rows if r.get("kind") == "random_sector" and r["table_bytes"] >= region]
+            size = min(r["table_bytes"] for r in rows)
+            pk = max(r["gsectors_per_s"] for r in rows if r["table_bytes"] == size)
+            sectors = S * probes_issued + hits * 2
+            ach = sectors / (ms_kernel * 1e-3) / 1e9
+            probe_bound = {"unit": "G sectors/s (32 B)", "achieved": ach, "peak": pk, "frac": ach / pk,
+                           "sector_loads_per_launch": sectors, "full_label_region_bytes": region,
+                           "peak_table_bytes": size,
+                           "peak_source": "profiles/r01_sector_peak_b200.jsonl (tools/sector_peak.cu: random "
+                                          "32-byte sector loads, 64 warps/SM, best of 1/2/4 loads in flight per thread)"}
+        except Exception:
+            pass
         h2d = sum(batch[k].nbytes for k in keys_in)
         d2h = S * 48 + hap_rows_n * 24 + pop_rows_n * 16
+        # what bounds e2e: the host link.  tools/pcie_peak.py measured, on this pool's B200 boxes, how long
+        # the link alone needs for one step's bytes with both directions busy (profiles/r01_pcie_peak_b200.json)
+        link = None
+        try:
+            pk = json.load(open(os.path.join(ROOT, "profiles", "r01_pcie_peak_b200.json")))
+            floor_ms = pk["duplex_ms"] * max(h2d / pk["h2d_bytes"], d2h / pk["d2h_bytes"])
+            link = {"bound": "pcie", "floor_ms_per_gpu_step": floor_ms, "frac": floor_ms / ms_host,
+                    "d2h_alone_gbs": pk["d2h_alone_gbs"], "h2d_alone_gbs": pk["h2d_alone_gbs"],
+                    "source": "profiles/r01_pcie_peak_b200.json (tools/pcie_peak.py: the same bytes, one pinned "
+                              "copy per direction, both directions at once, no kernels)"}
+        except Exception:
+            pass
         line = {
             "metric": "subjects_per_sec", "value": total / (ms_dev * 1e-3), "unit": "subjects/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
@@ -466,7 +502,7 @@ def main():
             "config": workload_config(args),
             "pair_evals_per_sec": evals * world / (ms_dev * 1e-3),
             "e2e": {"value": total / (ms_host * 1e-3), "unit": "subjects/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_host},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_host, "link": link},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback",
@@ -474,6 +510,7 @@ def main():
                          "probes_per_subject_issued": probes_issued,
                          "kernel": "k_fast_probe" if split else "k_impute_fast", "kernel_ms": ms_kernel,
                          "kernel_share_of_step": ms_kernel / ms_dev,
+                         "probe_bound": probe_bound,
                          # the whole single-population path (probe + score kernels) against the same peak
                          "path": ({"kernels": "k_fast_probe + k_fast_score", "ms": ms_kernel + float(np.mean(s_ms)),
                                    "k_fast_score_ms": float(np.mean(s_ms)), "algorithmic_bytes": algo_path,

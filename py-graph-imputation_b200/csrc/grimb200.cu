@@ -2296,16 +2296,48 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
   OutArrays O;
   O.hap_counter = e->d_counters + 1;
   O.pop_counter = e->d_counters + 2;
-  // chunking
+  // chunking.  Measured on 2^20 config-2 subjects (52 MB in, 135 MB out; the link alone moves those
+  // bytes in 2.58 ms with both directions busy, tools/pcie_peak.py): 3.00 ms at 131,072 subjects per
+  // chunk, 3.08 at 262,144, 3.70 at 65,536, 5.07 at 32,768 (the ~20 API calls per chunk become the
+  // critical path).  Smaller leading chunks and a second copy-out stream were tried and bought nothing.
   int64_t chunk = e->host_chunk;
   if (S > chunk * GRIMB_MAX_CHUNKS) chunk = (S + GRIMB_MAX_CHUNKS - 1) / GRIMB_MAX_CHUNKS;
-  const int nch = S > 0 ? (int)((S + chunk - 1) / chunk) : 0;
+  int64_t bound[GRIMB_MAX_CHUNKS + 1];
+  int nch = 0;
+  bound[0] = 0;
+  while (bound[nch] < S) {
+    bound[nch + 1] = bound[nch] + chunk < S ? bound[nch] + chunk : S;
+    ++nch;
+  }
   rc = upload_cfg(e, cfg, st);
   if (rc) return rc;
   CK(cudaMemsetAsync(e->d_counters, 0, 64, st));
   if (in_bytes[5]) CK(cudaMemcpyAsync(e->in[5].p, b->priors, in_bytes[5], cudaMemcpyHostToDevice, st));
+  unsigned long long hap_prev = 0, pop_prev = 0, hap_end = 0, pop_end = 0;
+  double wl = 0;
+  // copy-out of one chunk, once its counters have arrived (rows of a chunk are one contiguous range)
+  auto copy_out = [&](int c) -> int {
+    const int64_t s0 = bound[c], n = bound[c + 1] - s0;
+    CK(cudaEventSynchronize(e->ev_k[c]));
+    hap_end = e->h_cnt[4 * c + 1];
+    pop_end = e->h_cnt[4 * c + 2];
+    wl += (double)(unsigned int)(e->h_cnt[4 * c + 3] & 0xFFFFFFFFull);
+    cudaStream_t so = nch > 1 ? e->s_out : st;
+    CK(cudaMemcpyAsync(r->subjects + s0, dr.subjects + s0, (size_t)n * sizeof(GrimbSubjectResult), cudaMemcpyDeviceToHost, so));
+    const unsigned long long hcap = (unsigned long long)r->hap_capacity, pcap = (unsigned long long)r->pop_capacity;
+    const unsigned long long h1 = hap_end < hcap ? hap_end : hcap, p1 = pop_end < pcap ? pop_end : pcap;
+    if (h1 > hap_prev)
+      CK(cudaMemcpyAsync(r->hap_rows + hap_prev, dr.hap_rows + hap_prev, (size_t)(h1 - hap_prev) * sizeof(GrimbHapRow),
+                         cudaMemcpyDeviceToHost, so));
+    if (p1 > pop_prev)
+      CK(cudaMemcpyAsync(r->pop_rows + pop_prev, dr.pop_rows + pop_prev, (size_t)(p1 - pop_prev) * sizeof(GrimbPopRow),
+                         cudaMemcpyDeviceToHost, so));
+    hap_prev = h1 > hap_prev ? h1 : hap_prev;
+    pop_prev = p1 > pop_prev ? p1 : pop_prev;
+    return GRIMB_OK;
+  };
   for (int c = 0; c < nch; ++c) {
-    const int64_t s0 = (int64_t)c * chunk, s1 = s0 + chunk < S ? s0 + chunk : S, n = s1 - s0;
+    const int64_t s0 = bound[c], s1 = bound[c + 1], n = s1 - s0;
     const uint32_t a0 = b->allele_off[s0], a1 = b->allele_off[s1];
     cudaStream_t si = nch > 1 ? e->s_in : st;
     CK(cudaMemcpyAsync((uint16_t*)e->in[0].p + s0, b->typed_mask + s0, (size_t)n * 2, cudaMemcpyHostToDevice, si));
@@ -2339,28 +2371,16 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
     if (rc) return rc;
     CK(cudaMemcpyAsync(e->h_cnt + 4 * c, e->d_counters, 32, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(e->ev_k[c], st));
+    // with chunk c in the queue, hand chunk c-1 to the copy-out stream: enqueueing every chunk first
+    // (about 20 API calls each) would hold the first copy-out back by the whole enqueue time
+    if (c > 0) {
+      rc = copy_out(c - 1);
+      if (rc) return rc;
+    }
   }
-  // copy-out: chunk by chunk as its counters arrive
-  unsigned long long hap_prev = 0, pop_prev = 0, hap_end = 0, pop_end = 0;
-  double wl = 0;
-  for (int c = 0; c < nch; ++c) {
-    const int64_t s0 = (int64_t)c * chunk, s1 = s0 + chunk < S ? s0 + chunk : S, n = s1 - s0;
-    CK(cudaEventSynchronize(e->ev_k[c]));
-    hap_end = e->h_cnt[4 * c + 1];
-    pop_end = e->h_cnt[4 * c + 2];
-    wl += (double)(unsigned int)(e->h_cnt[4 * c + 3] & 0xFFFFFFFFull);
-    cudaStream_t so = nch > 1 ? e->s_out : st;
-    CK(cudaMemcpyAsync(r->subjects + s0, dr.subjects + s0, (size_t)n * sizeof(GrimbSubjectResult), cudaMemcpyDeviceToHost, so));
-    const unsigned long long hcap = (unsigned long long)r->hap_capacity, pcap = (unsigned long long)r->pop_capacity;
-    const unsigned long long h1 = hap_end < hcap ? hap_end : hcap, p1 = pop_end < pcap ? pop_end : pcap;
-    if (h1 > hap_prev)
-      CK(cudaMemcpyAsync(r->hap_rows + hap_prev, dr.hap_rows + hap_prev, (size_t)(h1 - hap_prev) * sizeof(GrimbHapRow),
-                         cudaMemcpyDeviceToHost, so));
-    if (p1 > pop_prev)
-      CK(cudaMemcpyAsync(r->pop_rows + pop_prev, dr.pop_rows + pop_prev, (size_t)(p1 - pop_prev) * sizeof(GrimbPopRow),
-                         cudaMemcpyDeviceToHost, so));
-    hap_prev = h1 > hap_prev ? h1 : hap_prev;
-    pop_prev = p1 > pop_prev ? p1 : pop_prev;
+  if (nch > 0) {
+    rc = copy_out(nch - 1);
+    if (rc) return rc;
   }
   if (nch > 1) CK(cudaStreamSynchronize(e->s_out));
   CK(cudaStreamSynchronize(st));
