@@ -1,0 +1,132 @@
+"""Three-way differential fuzz on RANDOM small frequency tables (build container only): the
+unmodified reference, oracle/grim_oracle.py and the emulated kernel source (tests/emu/) must
+write byte-identical files.  fuzz_vs_reference.py / fuzz_emu_vs_oracle.py use the README table
+(3,380 haplotypes, most alleles rare); the tables here are small and dense -- a few alleles per
+locus shared by most haplotypes -- so recombinant phases hit, top-link lists are long, the
+top-K cap and the geno_seen rule bind, and the last-node quirk lands on common alleles.
+
+    python tests/golden/fuzz_random_tables.py [n_tables] [n_subjects_per_case] [seed]
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.join(HERE, "..", "..")
+
+
+def reference_worker(path_in, path_out):
+    """Separate process: the reference's package is also called `grim`, so it cannot share an
+    interpreter with the product's host code."""
+    sys.path.insert(0, HERE)
+    from refrun import RefSession
+    job = json.load(open(path_in))
+    sess = RefSession(job["conf"], job["hpf"], job["counts"])
+    res = []
+    for lines, over in job["cases"]:
+        t0 = time.time()
+        out = sess.run(lines, **over)
+        out["_seconds"] = time.time() - t0
+        res.append(out)
+    sess.close()
+    json.dump(res, open(path_out, "w"))
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "--ref":
+    reference_worker(sys.argv[2], sys.argv[3])
+    sys.exit(0)
+
+for p in (os.path.join(ROOT, "py-graph-imputation_b200"), os.path.join(ROOT, "oracle"), os.path.join(HERE, "..")):
+    sys.path.insert(0, p)
+
+import subprocess  # noqa: E402
+import tempfile  # noqa: E402
+
+import grim_oracle as go  # noqa: E402
+import synth  # noqa: E402
+from emu_backend import EmuGraph, emu_imputation  # noqa: E402
+from grim.run_impute_def import load_config  # noqa: E402
+
+BASE_CONF = json.load(open(os.path.join(HERE, "data", "base_conf.json")))
+KEYS = ("umug", "umug_pops", "pmug", "pmug_pops", "miss", "problem")
+
+
+def first_diff(a, b):
+    a, b = a.splitlines(), b.splitlines()
+    for i in range(max(len(a), len(b))):
+        x = a[i] if i < len(a) else None
+        y = b[i] if i < len(b) else None
+        if x != y:
+            return i, x, y
+    return None
+
+
+def main():
+    n_tables = int(sys.argv[1]) if len(sys.argv) > 1 else 6
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+    seed = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    rng = np.random.RandomState(seed)
+    ok = True
+    for t in range(n_tables):
+        n_full = int(rng.choice([30, 120, 500]))
+        # every other table is dense: 2-5 alleles per locus, so most recombinants exist in the table
+        n_alleles = [int(x) for x in (rng.randint(2, 6, size=5) if t % 2 == 0 else rng.randint(3, 13, size=5))]
+        pops = [["CAU"], ["AAA", "BBB"], ["AAA", "BBB", "CCC", "DDD"]][int(rng.randint(0, 3))]
+        tseed = int(rng.randint(1, 1 << 30))
+        hpf = synth.zipf_table(n_full, n_alleles, tseed, pops=tuple(pops))
+        cnt = 1000.0 / np.arange(1, len(pops) + 1) ** 1.1
+        counts = "".join("%s,%s,%s\n" % (p, repr(float(c)), repr(float(c / cnt.sum()))) for p, c in zip(pops, cnt))
+        conf = dict(BASE_CONF)
+        conf["populations"] = pops
+        conf["UNK_priors"] = "MR" if len(pops) > 1 else conf.get("UNK_priors", "MR")
+        tab = synth.Table(hpf, pops[0])
+        races = synth.race_fields(pops) if len(pops) > 1 else None
+        print("== table %d: %d haplotypes, alleles/locus %s, pops %s (seed %d)" % (t, len(tab.haps), n_alleles, pops, tseed),
+              flush=True)
+        og = go.OracleGraph(hpf.splitlines(True), pops, conf["loci_map"], conf["freq_trim_threshold"],
+                            counts.splitlines(True))
+        eg = EmuGraph(og, conf["loci_map"])
+        cbp = np.array([float(l.split(",")[2]) for l in counts.splitlines()])
+        cases = [
+            ("typed", synth.typed_subjects(tab, n, tseed + 1, races), {}),
+            ("messy", synth.messy_subjects(tab, n, tseed + 2, races=races) if races else synth.messy_subjects(tab, n, tseed + 2), {}),
+            ("messy thr=40 topk=7", synth.messy_subjects(tab, n, tseed + 3, max_amb=5, races=races) if races
+             else synth.messy_subjects(tab, n, tseed + 3, max_amb=5),
+             {"number_of_options_threshold": 40, "max_haplotypes_number_in_phase": 7}),
+            ("unknown heavy nres=3", synth.messy_subjects(tab, n, tseed + 4, p_unknown=0.3, p_random=0.3, races=races) if races
+             else synth.messy_subjects(tab, n, tseed + 4, p_unknown=0.3, p_random=0.3),
+             {"number_of_results": 3, "number_of_pop_results": 2}),
+        ]
+        with tempfile.TemporaryDirectory() as td:
+            json.dump({"conf": conf, "hpf": hpf, "counts": counts, "cases": [[l, o] for _t, l, o in cases]},
+                      open(os.path.join(td, "in.json"), "w"))
+            subprocess.run([sys.executable, os.path.abspath(__file__), "--ref", os.path.join(td, "in.json"),
+                            os.path.join(td, "out.json")], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            refs = json.load(open(os.path.join(td, "out.json")))
+        for (tag, lines, over), ref in zip(cases, refs):
+            c = dict(conf)
+            c.update(over)
+            t_r = ref.pop("_seconds")
+            orc = go.OracleImputation(og, go.load_config(c), cbp).impute_lines(lines)
+            out = emu_imputation(eg, load_config(c), cbp).impute_lines(lines)
+            emu = {k: "".join(v) for k, v in out.items()}
+            bad_o = [k for k in KEYS if ref[k] != orc[k]]
+            bad_e = [k for k in KEYS if ref[k] != emu[k]]
+            print("   %-24s %4d subj  oracle %s  kernel %s  (reference %.1fs)  rows umug=%d pmug=%d miss=%d problem=%d" % (
+                tag, len(lines), "OK" if not bad_o else "MISMATCH " + ",".join(bad_o),
+                "OK" if not bad_e else "MISMATCH " + ",".join(bad_e), t_r, ref["umug"].count("\n"),
+                ref["pmug"].count("\n"), ref["miss"].count("\n"), ref["problem"].count("\n")), flush=True)
+            for who, bad, mine in (("oracle", bad_o, orc), ("kernel", bad_e, emu)):
+                for k in bad:
+                    i, x, y = first_diff(ref[k], mine[k])
+                    print("      first diff (%s) in %s line %d\n        ref : %s\n        mine: %s" % (who, k, i, x, y), flush=True)
+            ok &= not bad_o and not bad_e
+    print("ALL OK" if ok else "SOME MISMATCH")
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -4,8 +4,8 @@ subjects against a 1M-haplotype table, single process or one process per GPU und
 (tables built on rank 0, one NCCL broadcast, subjects sharded, rank 0 writes the six files).  Reports
 wall times and checks the first `--sample` subjects of the written files against the CPU oracle.
 
-    python tools/run_1m_job.py [--subjects N] [--haps H]
-    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/run_1m_job.py
+    python tests/tools/run_1m_job.py [--subjects N] [--haps H]
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tests/tools/run_1m_job.py
 """
 import argparse
 import json
@@ -14,7 +14,7 @@ import sys
 import tempfile
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "py-graph-imputation_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 

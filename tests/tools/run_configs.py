@@ -5,14 +5,14 @@ subjects/s end to end through Imputation.impute_lines (tokeniser + C ABI + forma
 spent inside the C ABI call, and a byte-for-byte comparison of the six output texts with the CPU
 oracle on the first `sample` subjects.  Writes one JSON line per configuration.
 
-    python tools/run_configs.py > profiles/rNN_configs.jsonl
+    python tests/tools/run_configs.py > profiles/rNN_configs.jsonl
 """
 import json
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (os.path.join(ROOT, "py-graph-imputation_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 
