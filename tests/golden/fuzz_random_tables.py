@@ -64,7 +64,78 @@ def first_diff(a, b):
     return None
 
 
+LOCI9 = ["A", "B", "C", "DPA1", "DPB1", "DQA1", "DQB1", "DRB1", "DRBX"]
+NINE_OVER = {
+    "populations": ["AAA", "BBB"], "UNK_priors": "MR", "freq_trim_threshold": 1e-9,
+    "loci_map": {l: i + 1 for i, l in enumerate(LOCI9)},
+    "Plan_B_Matrix": [[[1, 2, 3, 4, 5, 6, 7, 8, 9]], [[1, 2, 3], [4, 5], [6, 7, 8, 9]],
+                      [[1], [2, 3], [4, 5], [6, 7], [8, 9]], [[1], [2], [3], [4], [5], [6], [7], [8], [9]]],
+}
+
+
+def main_nine(n_tables, n, seed):
+    """Nine loci (BASELINE config 5 shape: 256 phases, 510 marginal labels, 9-block Plan-B matrix)."""
+    rng = np.random.RandomState(seed)
+    ok = True
+    for t in range(n_tables):
+        n_full = int(rng.choice([40, 100, 200]))
+        n_alleles = [int(x) for x in (rng.randint(2, 5, size=9) if t % 2 == 0 else rng.randint(3, 15, size=9))]
+        tseed = int(rng.randint(1, 1 << 30))
+        pops = NINE_OVER["populations"]
+        hpf = synth.zipf_table(n_full, n_alleles, tseed, loci=LOCI9, pops=tuple(pops))
+        counts = "AAA,100.0,0.5\nBBB,100.0,0.5\n"
+        conf = dict(BASE_CONF)
+        conf.update(NINE_OVER)
+        tab = synth.Table(hpf, pops[0], loci=LOCI9)
+        print("== nine-locus table %d: %d haplotypes, alleles/locus %s (seed %d)" % (t, len(tab.haps), n_alleles, tseed), flush=True)
+        og = go.OracleGraph(hpf.splitlines(True), pops, conf["loci_map"], conf["freq_trim_threshold"], counts.splitlines(True))
+        eg = EmuGraph(og, conf["loci_map"])
+        cbp = np.array([float(l.split(",")[2]) for l in counts.splitlines()])
+        races = ["AAA,BBB", ",", "AAA;BBB,XXX"]
+        cases = [
+            ("typed", synth.typed_subjects(tab, n, tseed + 1, races), {}),
+            ("messy", synth.messy_subjects(tab, n, tseed + 2, max_amb=2, p_missing=0.3, races=races[:2]), {}),
+            ("messy save_space nres=3", synth.messy_subjects(tab, n, tseed + 3, max_amb=2, p_missing=0.4, races=races[:2]),
+             {"save_space_mode": True, "number_of_results": 3}),
+        ]
+        ok &= run_cases(conf, hpf, counts, cases, og, eg, cbp)
+    print("ALL OK" if ok else "SOME MISMATCH")
+    return 0 if ok else 1
+
+
+def run_cases(conf, hpf, counts, cases, og, eg, cbp):
+    ok = True
+    with tempfile.TemporaryDirectory() as td:
+        json.dump({"conf": conf, "hpf": hpf, "counts": counts, "cases": [[l, o] for _t, l, o in cases]},
+                  open(os.path.join(td, "in.json"), "w"))
+        subprocess.run([sys.executable, os.path.abspath(__file__), "--ref", os.path.join(td, "in.json"),
+                        os.path.join(td, "out.json")], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        refs = json.load(open(os.path.join(td, "out.json")))
+    for (tag, lines, over), ref in zip(cases, refs):
+        c = dict(conf)
+        c.update(over)
+        t_r = ref.pop("_seconds")
+        orc = go.OracleImputation(og, go.load_config(c), cbp).impute_lines(lines)
+        out = emu_imputation(eg, load_config(c), cbp, arena=1 << 30).impute_lines(lines)   # the GPU's largest tier
+        emu = {k: "".join(v) for k, v in out.items()}
+        bad_o = [k for k in KEYS if ref[k] != orc[k]]
+        bad_e = [k for k in KEYS if ref[k] != emu[k]]
+        print("   %-24s %4d subj  oracle %s  kernel %s  (reference %.1fs)  rows umug=%d pmug=%d miss=%d problem=%d" % (
+            tag, len(lines), "OK" if not bad_o else "MISMATCH " + ",".join(bad_o),
+            "OK" if not bad_e else "MISMATCH " + ",".join(bad_e), t_r, ref["umug"].count("\n"),
+            ref["pmug"].count("\n"), ref["miss"].count("\n"), ref["problem"].count("\n")), flush=True)
+        for who, bad, mine in (("oracle", bad_o, orc), ("kernel", bad_e, emu)):
+            for k in bad:
+                i, x, y = first_diff(ref[k], mine[k])
+                print("      first diff (%s) in %s line %d\n        ref : %s\n        mine: %s" % (who, k, i, x, y), flush=True)
+        ok &= not bad_o and not bad_e
+    return ok
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--nine":
+        a = sys.argv[2:]
+        return main_nine(int(a[0]) if a else 4, int(a[1]) if len(a) > 1 else 10, int(a[2]) if len(a) > 2 else 1)
     n_tables = int(sys.argv[1]) if len(sys.argv) > 1 else 6
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 25
     seed = int(sys.argv[3]) if len(sys.argv) > 3 else 1
