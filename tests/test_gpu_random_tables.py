@@ -6,7 +6,8 @@ split fast path (k_fast_probe + k_fast_score), several populations the typed war
 subjects the general kernel.  The same generator, run three-way against the unmodified
 reference on the CPU (tests/golden/fuzz_random_tables.py), pins the oracle on these shapes.
 
-As a script it runs a longer campaign:  python tests/test_gpu_random_tables.py [n_tables] [n_subjects] [seed]
+As a script it runs a longer campaign:  python tests/test_gpu_random_tables.py [--nine] [n_tables] [n_subjects] [seed]
+(GRIMB_KEY_WORDS=2 in the environment forces the 128-bit-key build)
 """
 import json
 import os
@@ -54,23 +55,54 @@ def cases_for(tab, n, tseed, races):
     ]
 
 
-def run_table(t, seed, n, d, verbose=False):
+LOCI9 = ["A", "B", "C", "DPA1", "DPB1", "DQA1", "DQB1", "DRB1", "DRBX"]
+NINE_OVER = {
+    "populations": ["AAA", "BBB"], "UNK_priors": "MR", "freq_trim_threshold": 1e-9,
+    "loci_map": {l: i + 1 for i, l in enumerate(LOCI9)},
+    "Plan_B_Matrix": [[[1, 2, 3, 4, 5, 6, 7, 8, 9]], [[1, 2, 3], [4, 5], [6, 7, 8, 9]],
+                      [[1], [2, 3], [4, 5], [6, 7], [8, 9]], [[1], [2], [3], [4], [5], [6], [7], [8], [9]]],
+}
+
+
+def random_table_nine(rng, t):
+    """Nine loci (BASELINE config 5 shape: 256 phases, 510 marginal labels, 9-block Plan-B matrix)."""
+    n_full = int(rng.choice([40, 100, 200]))
+    n_alleles = [int(x) for x in (rng.randint(2, 5, size=9) if t % 2 == 0 else rng.randint(3, 15, size=9))]
+    tseed = int(rng.randint(1, 1 << 30))
+    pops = NINE_OVER["populations"]
+    hpf = synth.zipf_table(n_full, n_alleles, tseed, loci=LOCI9, pops=tuple(pops))
+    return hpf, "AAA,100.0,0.5\nBBB,100.0,0.5\n", pops, tseed, n_alleles
+
+
+def cases_nine(tab, n, tseed):
+    races = ["AAA,BBB", ",", "AAA;BBB,XXX"]
+    return [
+        ("typed", synth.typed_subjects(tab, 3 * n, tseed + 1, races), {}),
+        ("messy", synth.messy_subjects(tab, n, tseed + 2, max_amb=2, p_missing=0.3, races=races[:2]), {}),
+        ("messy save_space nres=3", synth.messy_subjects(tab, n, tseed + 3, max_amb=2, p_missing=0.4, races=races[:2]),
+         {"save_space_mode": True, "number_of_results": 3}),
+    ]
+
+
+def run_table(t, seed, n, d, verbose=False, nine=False):
     from grim.imputation.impute import Imputation
     from grim.imputation.networkx_graph import Graph
     from grim.run_impute_def import load_config
     rng = np.random.RandomState((seed * 1000 + t) % (1 << 32))
-    hpf, counts, pops, tseed, n_alleles = random_table(rng, t)
+    hpf, counts, pops, tseed, n_alleles = random_table_nine(rng, t) if nine else random_table(rng, t)
     open(os.path.join(d, "hpf.csv"), "w").write(hpf)
     open(os.path.join(d, "cnt.txt"), "w").write(counts)
     conf = json.load(open(os.path.join(goldenlib.GOLD, "data", "base_conf.json")))
     conf.update({"freq_file": os.path.join(d, "hpf.csv"), "pops_count_file": os.path.join(d, "cnt.txt"),
                  "populations": pops, "UNK_priors": "MR"})
-    tab = synth.Table(hpf, pops[0])
+    if nine:
+        conf.update(NINE_OVER)
+    tab = synth.Table(hpf, pops[0], loci=LOCI9 if nine else synth.LOCI5)
     races = synth.race_fields(pops) if len(pops) > 1 else None
     g = Graph(load_config(conf)).build_graph()
     bad = []
     try:
-        for tag, lines, over in cases_for(tab, n, tseed, races):
+        for tag, lines, over in (cases_nine(tab, n, tseed) if nine else cases_for(tab, n, tseed, races)):
             c = dict(conf)
             c.update(over)
             imp = Imputation(g, load_config(c))
@@ -93,13 +125,27 @@ def test_cuda_path_matches_oracle_on_random_tables(t, tmp_path):
     assert run_table(t, 20261018, 12, str(tmp_path)) == []
 
 
+@pytest.mark.parametrize("t", range(2))
+def test_cuda_path_matches_oracle_on_random_nine_locus_tables(t, tmp_path):
+    assert run_table(t, 20261018, 3, str(tmp_path), nine=True) == []
+
+
+@pytest.mark.parametrize("t", range(3))
+def test_wide_key_build_matches_oracle_on_random_tables(t, tmp_path, monkeypatch):
+    monkeypatch.setenv("GRIMB_KEY_WORDS", "2")
+    assert run_table(t, 20261019, 8, str(tmp_path)) == []
+
+
 if __name__ == "__main__":
+    nine = len(sys.argv) > 1 and sys.argv[1] == "--nine"
+    if nine:
+        del sys.argv[1]
     n_tables = int(sys.argv[1]) if len(sys.argv) > 1 else 12
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 25
     seed = int(sys.argv[3]) if len(sys.argv) > 3 else 7
     bad = []
     for t in range(n_tables):
         with tempfile.TemporaryDirectory() as d:
-            bad += run_table(t, seed, n, d, verbose=True)
+            bad += run_table(t, seed, n, d, verbose=True, nine=nine)
     print("ALL OK" if not bad else "MISMATCH %r" % bad)
     sys.exit(1 if bad else 0)
