@@ -26,9 +26,12 @@ def reference_worker(path_in, path_out):
     job = json.load(open(path_in))
     sess = RefSession(job["conf"], job["hpf"], job["counts"])
     res = []
-    for lines, over in job["cases"]:
+    for case in job["cases"]:
+        lines, over = case[0], case[1]
+        hpp = bool(case[2]) if len(case) > 2 else False
+        masks = case[3] if len(case) > 3 else None
         t0 = time.time()
-        out = sess.run(lines, **over)
+        out = sess.run(lines, hap_pop_pair=hpp, phase_masks=masks, **over)
         out["_seconds"] = time.time() - t0
         res.append(out)
     sess.close()
@@ -106,17 +109,28 @@ def main_nine(n_tables, n, seed):
 def run_cases(conf, hpf, counts, cases, og, eg, cbp):
     ok = True
     with tempfile.TemporaryDirectory() as td:
-        json.dump({"conf": conf, "hpf": hpf, "counts": counts, "cases": [[l, o] for _t, l, o in cases]},
+        json.dump({"conf": conf, "hpf": hpf, "counts": counts, "cases": [list(c[1:]) for c in cases]},
                   open(os.path.join(td, "in.json"), "w"))
         subprocess.run([sys.executable, os.path.abspath(__file__), "--ref", os.path.join(td, "in.json"),
                         os.path.join(td, "out.json")], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         refs = json.load(open(os.path.join(td, "out.json")))
-    for (tag, lines, over), ref in zip(cases, refs):
+    for case, ref in zip(cases, refs):
+        tag, lines, over = case[0], case[1], case[2]
+        hpp = bool(case[3]) if len(case) > 3 else False
+        masks = case[4] if len(case) > 4 else None
         c = dict(conf)
         c.update(over)
+        mpath = None
+        if masks is not None:
+            fd, mpath = tempfile.mkstemp(suffix=".json")
+            with os.fdopen(fd, "w") as f:
+                json.dump(masks, f)
+            c["bin_imputation_in_file"] = mpath
         t_r = ref.pop("_seconds")
-        orc = go.OracleImputation(og, go.load_config(c), cbp).impute_lines(lines)
-        out = emu_imputation(eg, load_config(c), cbp, arena=1 << 30).impute_lines(lines)   # the GPU's largest tier
+        orc = go.OracleImputation(og, go.load_config(c), cbp).impute_lines(lines, em_mr=hpp)
+        out = emu_imputation(eg, load_config(c), cbp, arena=1 << 30).impute_lines(lines, em_mr=hpp)   # the GPU's largest tier
+        if mpath:
+            os.unlink(mpath)
         emu = {k: "".join(v) for k, v in out.items()}
         bad_o = [k for k in KEYS if ref[k] != orc[k]]
         bad_e = [k for k in KEYS if ref[k] != emu[k]]
@@ -132,7 +146,58 @@ def run_cases(conf, hpf, counts, cases, og, eg, cbp):
     return ok
 
 
+def main_modes(n_tables, n, seed):
+    """Output modes and configuration switches on random dense five-locus tables."""
+    rng = np.random.RandomState(seed)
+    ok = True
+    for t in range(n_tables):
+        n_full = int(rng.choice([30, 120, 500]))
+        n_alleles = [int(x) for x in (rng.randint(2, 6, size=5) if t % 2 == 0 else rng.randint(3, 13, size=5))]
+        pops = [["CAU"], ["AAA", "BBB"], ["AAA", "BBB", "CCC", "DDD"]][t % 3]
+        tseed = int(rng.randint(1, 1 << 30))
+        hpf = synth.zipf_table(n_full, n_alleles, tseed, pops=tuple(pops))
+        cnt = 1000.0 / np.arange(1, len(pops) + 1) ** 1.1
+        counts = "".join("%s,%s,%s\n" % (p, repr(float(c)), repr(float(c / cnt.sum()))) for p, c in zip(pops, cnt))
+        conf = dict(BASE_CONF)
+        conf["populations"] = pops
+        conf["UNK_priors"] = "MR"
+        tab = synth.Table(hpf, pops[0])
+        races = synth.race_fields(pops) if len(pops) > 1 else None
+        kw = {"races": races} if races else {}
+        print("== modes table %d: %d haplotypes, alleles/locus %s, pops %s (seed %d)" % (t, len(tab.haps), n_alleles, pops, tseed),
+              flush=True)
+        og = go.OracleGraph(hpf.splitlines(True), pops, conf["loci_map"], conf["freq_trim_threshold"], counts.splitlines(True))
+        eg = EmuGraph(og, conf["loci_map"])
+        cbp = np.array([float(l.split(",")[2]) for l in counts.splitlines()])
+        mixed = synth.typed_subjects(tab, n, tseed + 1, races) + synth.messy_subjects(tab, n, tseed + 2, **kw)
+        mrng = np.random.RandomState(tseed % (1 << 31))
+
+        def masks_for(lines):
+            return {ln.split(",")[0]: [int(x) for x in mrng.randint(0, 2, size=4)] for ln in lines}
+
+        cases = [
+            ("planb off", mixed, {"planb": False}),
+            ("umug only", mixed, {"output_haplotypes": False}),
+            ("pmug only", mixed, {"output_MUUG": False}),
+            ("save_space missing", synth.messy_subjects(tab, n, tseed + 3, p_missing=0.4, **kw), {"save_space_mode": True}),
+            ("epsilon 1e-1", mixed, {"epsilon": 1e-1}),
+            ("epsilon 1e-7 nres=1000", mixed, {"epsilon": 1e-7, "number_of_results": 1000}),
+            ("SR priors", mixed, {"UNK_priors": "SR"}),
+            ("priority eta>0", mixed, {"priority": {"alpha": 0.4, "eta": 0.01, "beta": 1e-3, "gamma": 1e-2, "delta": 0.3}}),
+            ("hap_pop_pair", mixed, {}, True),
+            ("hap_pop_pair nres=4", mixed, {"number_of_results": 4}, True),
+            ("phase masks", mixed, {}, False, masks_for(mixed)),
+            ("phase masks + hap_pop_pair", mixed, {}, True, masks_for(mixed)),
+        ]
+        ok &= run_cases(conf, hpf, counts, cases, og, eg, cbp)
+    print("ALL OK" if ok else "SOME MISMATCH")
+    return 0 if ok else 1
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--modes":
+        a = sys.argv[2:]
+        return main_modes(int(a[0]) if a else 4, int(a[1]) if len(a) > 1 else 15, int(a[2]) if len(a) > 2 else 1)
     if len(sys.argv) > 1 and sys.argv[1] == "--nine":
         a = sys.argv[2:]
         return main_nine(int(a[0]) if a else 4, int(a[1]) if len(a) > 1 else 10, int(a[2]) if len(a) > 2 else 1)
