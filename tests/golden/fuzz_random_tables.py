@@ -194,7 +194,36 @@ def main_modes(n_tables, n, seed):
     return 0 if ok else 1
 
 
+def main_heavy(n, seed, rounds):
+    """Highly ambiguous subjects on the README table: 6-40 alleles per locus side, 0-3
+    missing loci, products on both sides of number_of_options_threshold (default 100,000 and 2,000)."""
+    cau = open(os.path.join(HERE, "data", "cau_hpf.csv")).read()
+    counts = "CAU,3380.0,1.0\n"
+    conf = dict(BASE_CONF)
+    tab = synth.Table(cau)
+    og = go.OracleGraph(cau.splitlines(True), conf["populations"], conf["loci_map"], conf["freq_trim_threshold"],
+                        counts.splitlines(True))
+    eg = EmuGraph(og, conf["loci_map"])
+    cbp = np.array([3380.0 / 3380.0])
+    ok = True
+    for r in range(rounds):
+        print("== heavy round %d (seed %d)" % (r, seed + 100 * r), flush=True)
+        cases = [
+            ("heavy thr=100000", synth.heavy_subjects(tab, n, seed + 100 * r), {}),
+            ("heavy thr=2000", synth.heavy_subjects(tab, n, seed + 100 * r + 1, sizes=(3, 6, 12)),
+             {"number_of_options_threshold": 2000}),
+            ("heavy thr=2000 topk=10 nres=5", synth.heavy_subjects(tab, n, seed + 100 * r + 2, sizes=(3, 6, 12)),
+             {"number_of_options_threshold": 2000, "max_haplotypes_number_in_phase": 10, "number_of_results": 5}),
+        ]
+        ok &= run_cases(conf, cau, counts, cases, og, eg, cbp)
+    print("ALL OK" if ok else "SOME MISMATCH")
+    return 0 if ok else 1
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--heavy":
+        a = sys.argv[2:]
+        return main_heavy(int(a[0]) if a else 10, int(a[1]) if len(a) > 1 else 1, int(a[2]) if len(a) > 2 else 1)
     if len(sys.argv) > 1 and sys.argv[1] == "--modes":
         a = sys.argv[2:]
         return main_modes(int(a[0]) if a else 4, int(a[1]) if len(a) > 1 else 15, int(a[2]) if len(a) > 2 else 1)
