@@ -106,7 +106,7 @@ def main_nine(n_tables, n, seed):
     return 0 if ok else 1
 
 
-def run_cases(conf, hpf, counts, cases, og, eg, cbp):
+def run_cases(conf, hpf, counts, cases, og, eg, cbp, text_too=False):
     ok = True
     with tempfile.TemporaryDirectory() as td:
         json.dump({"conf": conf, "hpf": hpf, "counts": counts, "cases": [list(c[1:]) for c in cases]},
@@ -131,6 +131,11 @@ def run_cases(conf, hpf, counts, cases, og, eg, cbp):
         out = emu_imputation(eg, load_config(c), cbp, arena=1 << 30).impute_lines(lines, em_mr=hpp)   # the GPU's largest tier
         if mpath:
             os.unlink(mpath)
+        txt = None
+        if text_too:   # the C++ tokeniser / formatter (grimb_text.cpp) around the same emulated kernel source
+            from emu_backend import emu_impute_text
+            timp = emu_imputation(eg, load_config(c), cbp, arena=1 << 30)
+            txt = emu_impute_text(timp, eg, "".join(lines).encode("utf8"), arena=1 << 30)
         emu = {k: "".join(v) for k, v in out.items()}
         bad_o = [k for k in KEYS if ref[k] != orc[k]]
         bad_e = [k for k in KEYS if ref[k] != emu[k]]
@@ -138,11 +143,14 @@ def run_cases(conf, hpf, counts, cases, og, eg, cbp):
             tag, len(lines), "OK" if not bad_o else "MISMATCH " + ",".join(bad_o),
             "OK" if not bad_e else "MISMATCH " + ",".join(bad_e), t_r, ref["umug"].count("\n"),
             ref["pmug"].count("\n"), ref["miss"].count("\n"), ref["problem"].count("\n")), flush=True)
-        for who, bad, mine in (("oracle", bad_o, orc), ("kernel", bad_e, emu)):
+        bad_t = [k for k in KEYS if txt is not None and ref[k] != txt[k]]
+        if txt is not None:
+            print("   %-24s        C++ text pipeline %s" % ("", "OK" if not bad_t else "MISMATCH " + ",".join(bad_t)), flush=True)
+        for who, bad, mine in (("oracle", bad_o, orc), ("kernel", bad_e, emu), ("text", bad_t, txt)):
             for k in bad:
                 i, x, y = first_diff(ref[k], mine[k])
-                print("      first diff (%s) in %s line %d\n        ref : %s\n        mine: %s" % (who, k, i, x, y), flush=True)
-        ok &= not bad_o and not bad_e
+                print("      first diff (%s) in %s line %d\n        ref : %r\n        mine: %r" % (who, k, i, x, y), flush=True)
+        ok &= not bad_o and not bad_e and not bad_t
     return ok
 
 
@@ -220,7 +228,80 @@ def main_heavy(n, seed, rounds):
     return 0 if ok else 1
 
 
+def dirty(lines, rng, loci, crlf):
+    """Mutations of well-formed subject lines toward what real input files contain (SURVEY 8c edge set)."""
+    out = []
+    for ln in lines:
+        f = ln.rstrip("\n").split(",")
+        sid, gl, race = f[0], f[1], f[2:]
+        loc = gl.split("^")
+        for _ in range(int(rng.randint(0, 3))):
+            m = int(rng.randint(0, 9))
+            if not loc:
+                break
+            k = int(rng.randint(len(loc)))
+            if m == 0:      # 'g' / 'L' suffixes (clean_up_gl deletes the characters)
+                a = loc[k].split("+")
+                a[int(rng.randint(len(a)))] += "gL"[int(rng.randint(2))]
+                loc[k] = "+".join(a)
+            elif m == 1:    # untyped locus written as UUUU
+                name = loc[k].split("*")[0]
+                loc[k] = "%s*UUUU+%s*UUUU" % (name, name)
+            elif m == 2:    # a locus without '+': unparsable
+                loc[k] = loc[k].split("+")[0]
+            elif m == 3:    # loci in another order
+                rng.shuffle(loc)
+            elif m == 4:    # race field variants
+                race = [["", ""], ["XXX", "CAU"], ["CAU"], [], ["CAU;XXX", "CAU"], ["CAU", "CAU", ""], ["AAA;BBB", "XXX"],
+                        ["BBB", ""]][int(rng.randint(8))]
+            elif m == 5:    # fully homozygous
+                loc = ["+".join([x.split("+")[0]] * 2) for x in loc]
+            elif m == 6:    # empty GL string
+                loc = []
+            elif m == 7:    # one side empty
+                loc[k] = loc[k].split("+")[0] + "+"
+            elif m == 8:    # locus dropped
+                if len(loc) > 1:
+                    del loc[k]
+        out.append(",".join([sid, "^".join(loc)] + race) + ("\r\n" if crlf else "\n"))
+    return out
+
+
+def main_dirty(n_tables, n, seed, crlf=False):
+    rng = np.random.RandomState(seed)
+    ok = True
+    for t in range(n_tables):
+        n_full = int(rng.choice([30, 120, 500]))
+        n_alleles = [int(x) for x in (rng.randint(2, 6, size=5) if t % 2 == 0 else rng.randint(3, 13, size=5))]
+        pops = [["CAU"], ["AAA", "BBB"]][t % 2]
+        tseed = int(rng.randint(1, 1 << 30))
+        hpf = synth.zipf_table(n_full, n_alleles, tseed, pops=tuple(pops))
+        cnt = 1000.0 / np.arange(1, len(pops) + 1) ** 1.1
+        counts = "".join("%s,%s,%s\n" % (p, repr(float(c)), repr(float(c / cnt.sum()))) for p, c in zip(pops, cnt))
+        conf = dict(BASE_CONF)
+        conf["populations"] = pops
+        conf["UNK_priors"] = "MR"
+        tab = synth.Table(hpf, pops[0])
+        races = synth.race_fields(pops) if len(pops) > 1 else ["CAU,CAU"]
+        print("== dirty table %d: %d haplotypes, alleles/locus %s, pops %s (seed %d)" % (t, len(tab.haps), n_alleles, pops, tseed),
+              flush=True)
+        og = go.OracleGraph(hpf.splitlines(True), pops, conf["loci_map"], conf["freq_trim_threshold"], counts.splitlines(True))
+        eg = EmuGraph(og, conf["loci_map"])
+        cbp = np.array([float(l.split(",")[2]) for l in counts.splitlines()])
+        base = synth.typed_subjects(tab, n, tseed + 1, races) + synth.messy_subjects(tab, n, tseed + 2, races=races)
+        drng = np.random.RandomState(tseed % (1 << 31))
+        cases = [("dirty", dirty(base, drng, synth.LOCI5, crlf), {}),
+                 ("dirty umug only", dirty(base, drng, synth.LOCI5, crlf), {"output_haplotypes": False})]
+        ok &= run_cases(conf, hpf, counts, cases, og, eg, cbp, text_too=True)
+    print("ALL OK" if ok else "SOME MISMATCH")
+    return 0 if ok else 1
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] in ("--dirty", "--dirty-crlf"):
+        a = sys.argv[2:]
+        return main_dirty(int(a[0]) if a else 4, int(a[1]) if len(a) > 1 else 20, int(a[2]) if len(a) > 2 else 1,
+                          crlf=sys.argv[1] == "--dirty-crlf")
     if len(sys.argv) > 1 and sys.argv[1] == "--heavy":
         a = sys.argv[2:]
         return main_heavy(int(a[0]) if a else 10, int(a[1]) if len(a) > 1 else 1, int(a[2]) if len(a) > 2 else 1)
