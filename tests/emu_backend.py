@@ -13,7 +13,8 @@ from grim.imputation.impute import Imputation
 from grim.imputation.networkx_graph import key_layout, loci_in_order
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-EMU_SO = os.path.join(HERE, "emu", "libgrimb_emu.so")
+# GRIMB_EMU_SO: an alternative build of the same source (e.g. -fsanitize=address,undefined; tests/emu/build.sh asan)
+EMU_SO = os.environ.get("GRIMB_EMU_SO") or os.path.join(HERE, "emu", "libgrimb_emu.so")
 
 M64 = (1 << 64) - 1
 
