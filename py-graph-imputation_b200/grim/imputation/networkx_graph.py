@@ -186,6 +186,7 @@ class Graph(object):
     def from_arrays(self, alleles, full_alleles, full_freqs):
         L, P = len(self.loci), len(self.pops)
         self._set_dictionaries(alleles)
+        self._store = None
         lib = self.lib
         fa = np.ascontiguousarray(full_alleles, dtype=np.uint16)
         ff = np.ascontiguousarray(full_freqs, dtype=np.float64)
@@ -232,6 +233,33 @@ class Graph(object):
             out["node_key"] = np.array([int(lo) | (int(hi) << 64) for lo, hi in w], dtype=object)
         return out
 
+    # ---- store seam: the reference's Graph queries, answered on the host from a copy of the
+    # device arrays (networkx_graph.py:215-321).  The engine never calls these; they serve callers that
+    # inspect the graph.  The copy is made on first use (export(): the whole table image comes back, so
+    # this is for tables of README / NEMO size, not for an HBM-filling nine-locus table).
+    def store_view(self):
+        if getattr(self, "_store", None) is None:
+            from .store_view import StoreView
+            arr = self.export()
+            arr["bits"] = list(self.key_bits)
+            self._store = StoreView(arr, self.loci, self.config["loci_map"], self.alleles)
+        return self._store
+
+    def haps_by_label(self, label):
+        return self.store_view().haps_by_label(label)
+
+    def haps_with_probs_by_label(self, label):
+        return self.store_view().haps_with_probs_by_label(label)
+
+    def adjs_query(self, alleleList):
+        return self.store_view().adjs_query(alleleList)
+
+    def adjs_query_by_color(self, alleleList, labelA, labelB):
+        return self.store_view().adjs_query_by_color(alleleList, labelA, labelB)
+
+    def node_probs(self, nodes, label):
+        return self.store_view().node_probs(nodes, label)
+
     def engine(self, workspace_bytes):
         e = self._engines.get(workspace_bytes)
         if e is None:
@@ -248,6 +276,7 @@ class Graph(object):
         for e in self._engines.values():
             lib.grimb_engine_free(e)
         self._engines = {}
+        self._store = None
         if self.handle is not None:
             lib.grimb_tables_free(self.handle)
             self.handle = None
