@@ -12,7 +12,9 @@ outputs, Plan B on.  One step = one pass of the hot path over the whole batch.
 
 value  : subjects/s, batch already resident in HBM, CUDA-event timed (max over ranks)
 e2e    : same through grimb_impute_host with pinned HOST buffers (H2D + kernel + D2H per step)
-roofline / cpu_baseline: see DESIGN.md "Measurement".
+roofline / cpu_baseline: see DESIGN.md "Measurement".  roofline.probe_bound places the dominant kernel against
+the random 32-byte-sector rate measured by tools/sector_peak.cu (the probe-bound roofline); e2e.link places the
+host-buffer leg against the time the PCIe link alone needs for the same bytes (tools/pcie_peak.py).
 """
 import argparse
 import ctypes as C

@@ -321,6 +321,8 @@ def main():
         # every other table is dense: 2-5 alleles per locus, so most recombinants exist in the table
         n_alleles = [int(x) for x in (rng.randint(2, 6, size=5) if t % 2 == 0 else rng.randint(3, 13, size=5))]
         pops = [["CAU"], ["AAA", "BBB"], ["AAA", "BBB", "CCC", "DDD"]][int(rng.randint(0, 3))]
+        if os.environ.get("FUZZ_POPS"):   # e.g. FUZZ_POPS=21: BASELINE config 3 shape (21 populations, top-100 pop rows)
+            pops = ["P%02d" % i for i in range(int(os.environ["FUZZ_POPS"]))]
         tseed = int(rng.randint(1, 1 << 30))
         hpf = synth.zipf_table(n_full, n_alleles, tseed, pops=tuple(pops))
         cnt = 1000.0 / np.arange(1, len(pops) + 1) ** 1.1
