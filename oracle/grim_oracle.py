@@ -906,8 +906,10 @@ class OracleImputation:
         return None, None
 
     # ---- subject loop + writers (impute.py:1985-2155, :24-76) ----
-    def impute_lines(self, lines, em_mr=False, em=False):
-        """em_mr: grim.grim.impute(hap_pop_pair=True) (impute.py:2079-2088); em: impute_file(em=True)."""
+    def impute_lines(self, lines, em_mr=False, em=False, first_index=0):
+        """em_mr: grim.grim.impute(hap_pop_pair=True) (impute.py:2079-2088); em: impute_file(em=True);
+        first_index: line number of lines[0] in the whole input (checker convenience: lets a test split one
+        input over forked workers; the reference's enumerate() starts at 0)."""
         out = {k: [] for k in ("umug", "umug_pops", "pmug", "pmug_pops", "miss", "problem")}
         n_res = self.cfg["number_of_results"]
         n_pop = self.cfg["number_of_pop_results"]
@@ -917,7 +919,7 @@ class OracleImputation:
         if os.path.isfile(bin_path):          # impute.py:2001-2005
             with open(bin_path) as f:
                 f_bin = json.load(f)
-        for i, raw in enumerate(lines):
+        for i, raw in enumerate(lines, first_index):
             try:
                 raw = raw.rstrip()
                 fields = raw.split(",") if "," in raw else raw.split("%")

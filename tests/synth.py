@@ -214,3 +214,113 @@ def race_fields(pops):
         ",",
         "%s,XXX;YYY" % p[0],
     ]
+
+
+# --------------------------------------------------------------------------- BASELINE-size tables (arrays)
+def multipop_freqs(base_f, n_pops, seed, zero_frac=0.4):
+    """SURVEY 8(d) C3 frequencies for an array table: per population base_f * LogNormal(0, 1) with
+    zero_frac of the (haplotype, population) entries zeroed, renormalised per population.
+    base_f: [N] -> [N][n_pops]."""
+    rng = np.random.RandomState(seed)
+    n = len(base_f)
+    ff = np.empty((n, n_pops), np.float64)
+    for j in range(n_pops):
+        f = base_f * rng.lognormal(0.0, 1.0, size=n)
+        f[rng.rand(n) < zero_frac] = 0.0
+        ff[:, j] = f / f.sum()
+    return ff
+
+
+def pop_counts(pops):
+    """-> (text of a pops_count_file with counts proportional to a Zipf law, the ratio column as floats)."""
+    counts = 1000.0 / np.arange(1, len(pops) + 1) ** 1.1
+    tot = counts.sum()
+    text = "".join("%s,%s,%s\n" % (p, repr(float(c)), repr(float(c / tot))) for p, c in zip(pops, counts))
+    return text, np.array([float(repr(float(c / tot))) for c in counts])
+
+
+def array_subject_lines(names, full_alleles, p, n, seed, races=None, prefix="S", variants=True):
+    """Lines for a table given as arrays (names[l][id-1], full_alleles [N][L]).  Two haplotypes drawn with
+    probabilities p; fully typed, one allele per side.  With `variants`, one subject in eight is changed
+    in one of these ways (cycled): fully homozygous, homozygous at two loci, one allele replaced by a name
+    absent from the table, one allele replaced by a random table allele (recombinant: usually Plan B),
+    both of the last two; so the batch also exercises the hand-over from the warp-per-subject kernels."""
+    rng = np.random.RandomState(seed)
+    L = full_alleles.shape[1]
+    idx = rng.choice(len(p), size=(n, 2), p=p)
+    flip = rng.rand(n, L) < 0.5
+    h1, h2 = full_alleles[idx[:, 0]], full_alleles[idx[:, 1]]
+    a = np.where(flip, h2, h1)
+    b = np.where(flip, h1, h2)
+    loci = [nm[0].split("*")[0] for nm in names]
+    out = []
+    for s in range(n):
+        sa = [names[l][a[s, l] - 1] for l in range(L)]
+        sb = [names[l][b[s, l] - 1] for l in range(L)]
+        if variants and s % 8 == 7:
+            v = (s // 8) % 5
+            if v == 0:
+                sb = list(sa)
+            elif v == 1:
+                for l in rng.choice(L, size=2, replace=False):
+                    sb[l] = sa[l]
+            if v in (2, 4):
+                l = rng.randint(L)
+                sa[l] = "%s*99:%02d" % (loci[l], rng.randint(1, 4))
+            if v in (3, 4):
+                l = rng.randint(L)
+                sb[l] = names[l][rng.randint(len(names[l]))]
+        line = "%s%d,%s" % (prefix, s, "^".join(x + "+" + y for x, y in zip(sa, sb)))
+        if races is not None:
+            line += "," + races[s % len(races)]
+        out.append(line + "\n")
+    return out
+
+
+class _LazyHaps(object):
+    def __init__(self, names, fa):
+        self.names, self.fa = names, fa
+
+    def __len__(self):
+        return len(self.fa)
+
+    def __getitem__(self, i):
+        row = self.fa[i]
+        return [self.names[l][int(row[l]) - 1] for l in range(len(self.names))]
+
+
+class ArrayTable(object):
+    """The sampling interface of `Table` over an array table (no per-haplotype Python lists)."""
+
+    def __init__(self, names, full_alleles, p):
+        self.loci = [nm[0].split("*")[0] for nm in names]
+        self.haps = _LazyHaps(names, full_alleles)
+        self.p = p
+        self.alleles = [list(n) for n in names]
+
+
+def zipf_arrays(n_full, n_alleles, seed, loci):
+    """zipf_table as arrays: -> (names per locus, full_alleles uint16 [N][L] 1-based, base freq [N])."""
+    rng = np.random.RandomState(seed)
+    cols = []
+    for na in n_alleles:
+        w = 1.0 / np.arange(1, na + 1) ** 1.1
+        w /= w.sum()
+        cols.append(rng.choice(na, size=int(n_full * 1.3) + 100, p=w))
+    tup = np.stack(cols, axis=1)
+    _u, first = np.unique(tup, axis=0, return_index=True)
+    tup = tup[np.sort(first)][:n_full]
+    n = len(tup)
+    f = 1.0 / np.arange(1, n + 1)
+    f /= f.sum()
+    names = [["%s*%02d:%02d" % (loc, a // 60 + 1, a % 60 + 1) for a in range(na)] for loc, na in zip(loci, n_alleles)]
+    # only alleles that occur are table alleles: re-index so that ids are dense and names stay sorted
+    fa = np.zeros((n, len(loci)), np.uint16)
+    out_names = []
+    for l in range(len(loci)):
+        used = np.unique(tup[:, l])
+        remap = np.zeros(n_alleles[l], np.int64)
+        remap[used] = np.arange(1, len(used) + 1)
+        fa[:, l] = remap[tup[:, l]]
+        out_names.append([names[l][a] for a in used])
+    return out_names, fa, f
