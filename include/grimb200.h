@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define GRIMB_ABI_VERSION 3
+#define GRIMB_ABI_VERSION 4
 #define GRIMB_MAX_LOCI 9
 #define GRIMB_MAX_ROWS 16
 #define GRIMB_MAX_BLOCKS 9
@@ -143,12 +143,14 @@ typedef struct {
   int64_t n_subjects;
   const uint16_t* typed_mask;   /* [S] bit l set = locus l typed; 0 = skip subject (GRIMB_ST_SKIPPED) */
   const uint16_t* counts;       /* [S][L][2] alleles listed per locus and chromosome side; >= 1 for
-                                   every typed locus (an empty side is one unknown allele), 0 otherwise */
+                                   every typed locus (an empty side is one unknown allele), 0 otherwise.
+                                   NULL (ABI v4) = every typed locus side of every subject of this batch
+                                   lists exactly one allele (saves 4L of the ~10L bytes per subject)  */
   const uint32_t* allele_off;   /* [S+1] offset of the subject's allele ids in `alleles`            */
   const uint16_t* alleles;      /* ids, per subject: locus ascending, side 0 then 1; ids > n_alleles[l]
                                    are subject-local names of alleles absent from the table        */
   int64_t n_alleles_total;      /* allele_off[S]                                                    */
-  const uint32_t* prior_index;  /* [S] row of `priors`                                              */
+  const uint32_t* prior_index;  /* [S] row of `priors`; NULL (ABI v4) = row 0 for every subject         */
   const double* priors;         /* [n_priors][P][P] prior matrices (impute.py:1844-1924,1956-1959)  */
   int32_t n_priors;
   const uint16_t* phase_mask;   /* optional [S] (NULL = none): bit m set = the m-th TYPED locus may switch
@@ -169,7 +171,8 @@ typedef struct { uint64_t a[2], b[2]; double prob; } GrimbHapRow; /* little-endi
 #endif
 typedef struct { uint16_t pop_a, pop_b; uint32_t pad; double prob; } GrimbPopRow;
 
-/* One record per subject (48 bytes, 16-byte aligned: written with three 128-bit stores). */
+/* Record of a GENERAL subject (48 bytes, 16-byte aligned: written with three 128-bit stores); its
+ * rows are hap_rows[hap_off ...] / pop_rows[pop_off ...]. */
 typedef struct {
   uint8_t status;        /* GRIMB_ST_*                                                   */
   uint8_t plan_umug;     /* GRIMB_PLAN_*                                                 */
@@ -186,21 +189,63 @@ typedef struct {
   uint64_t pop_off;      /* first UMUG pop row in pop_rows; the PMUG pop rows follow     */
 } GrimbSubjectResult;
 
+/* ABI v4: ONE 16-byte record per subject, in input order.  Subjects that the warp-per-subject kernels
+ * finish -- every locus typed, one allele per chromosome side, Plan A (the bulk of BASELINE configs 2, 3
+ * and 5) -- are described completely by this record plus a few 8-byte words: their single UMUG genotype is
+ * the subject's own allele pairs and the two haplotypes of a PMUG row follow from the subject's alleles and
+ * the row's phase id (gen_phases, impute.py:274-303: bit m of the id = locus m takes its side-2 allele in
+ * the first haplotype), so no packed keys travel back.  Everything else (ambiguity, missing loci, Plan B /
+ * C, EM modes) keeps the 48-byte GrimbSubjectResult + row arrays above, appended to `general`.
+ *   kind_flags: bits 0-1 GRIMB_KIND_*, bit 2 GRIMB_KIND_WORDS, bit 3 "has results" (else the reference
+ *               writes .miss), bits 4-7 n_pmug = PMUG rows written (SIMPLE / TYPED: <= 4)
+ *   GENERAL: off = index of the subject's GrimbSubjectResult in `general` (0xFFFFFFFF: none, skipped subject)
+ *   SIMPLE : one population.  total = probability of the UMUG genotype = the population row's value;
+ *            phases = phase ids of the PMUG rows in rank order, 4 bits each; with GRIMB_KIND_WORDS
+ *            words[off + k] = probability of PMUG row k, without it (a single accepted phase) the one
+ *            PMUG row's probability is `total`
+ *   TYPED  : P <= 32 populations.  words[off] = header: n_pops (bits 0-15), then the PMUG rows' phase ids,
+ *            12 bits each from bit 16; words[off + 1 + k] = probability of PMUG row k; then n_pops
+ *            probabilities of the population-pair rows in rank order (the same rows serve .umug.pops and
+ *            .pmug.pops), then their pair codes, one uint16 each ((first-seen pop_a << 8) | pop_b), packed
+ *            four per word. */
+#define GRIMB_KIND_GENERAL 0
+#define GRIMB_KIND_SIMPLE 1
+#define GRIMB_KIND_TYPED 2
+#define GRIMB_KIND_WORDS 4        /* SIMPLE: the PMUG probabilities are words[off ...] */
+#define GRIMB_KIND_HAS_RESULTS 8
 typedef struct {
-  GrimbSubjectResult* subjects; /* [S]                                                   */
-  GrimbHapRow* hap_rows;  int64_t hap_capacity;
+  uint8_t status;        /* GRIMB_ST_*                                                   */
+  uint8_t kind_flags;
+  uint16_t phases;
+  uint32_t off;
+  double total;
+} GrimbCompact;
+
+typedef struct {
+  GrimbCompact* compact;        /* [S]                                                   */
+  uint64_t* words;        int64_t word_capacity;      /* rows of SIMPLE / TYPED subjects          */
+  GrimbSubjectResult* general;  int64_t general_capacity;  /* records of GENERAL subjects, appended */
+  GrimbHapRow* hap_rows;  int64_t hap_capacity;       /* rows of GENERAL subjects                 */
   GrimbPopRow* pop_rows;  int64_t pop_capacity;
-  /* totals written by the call (host memory, always): rows needed; > capacity => GRIMB_E_CAPACITY */
-  int64_t* hap_rows_needed;
-  int64_t* pop_rows_needed;
+  /* totals written by the call (host memory, always): entries needed; > capacity => GRIMB_E_CAPACITY.
+   * [0] words, [1] general records, [2] hap rows, [3] pop rows, [4] pair evaluations of the whole batch
+   * (iterations reaching impute.py:464/573, the metric's second numerator), [5] subjects the
+   * warp-per-subject kernels handed on to the general kernel */
+  int64_t* totals;
 } GrimbResults;
 
 int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes_per_cta, GrimbEngine** out);
 int grimb_engine_free(GrimbEngine* e);
 
-/* Device-pointer form: batch and result arrays already in HBM; asynchronous on `cuda_stream`
- * (a cudaStream_t, 0 = engine stream) except for the two *_needed totals, which are read back
- * (one 16-byte copy) before returning. */
+/* Device-pointer form: batch and result arrays already in HBM.  grimb_impute_device_async enqueues
+ * everything on `cuda_stream` (a cudaStream_t, 0 = engine stream) and returns without synchronising;
+ * grimb_impute_finish waits for that stream and fills res->totals (the counters travel through pinned
+ * memory owned by the engine).  One call may be in flight per engine; calls on one stream queue behind
+ * each other, so a caller can enqueue batch k+1 before finishing batch k only with a second engine.
+ * grimb_impute_device = the two together. */
+int grimb_impute_device_async(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch,
+                              const GrimbResults* res, void* cuda_stream);
+int grimb_impute_finish(GrimbEngine* e, const GrimbResults* res);
 int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch,
                         GrimbResults* res, void* cuda_stream);
 

@@ -43,6 +43,8 @@ extern "C" void grimb_pinned_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 extern "C" const char* grimb_last_error(void) { return g_err.c_str(); }
+// the text pipeline (grimb_text.cpp) reports through the same per-thread message
+extern "C" void grimb_set_error(const char* msg) { g_err = msg ? msg : ""; }
 
 // ------------------------------------------------------------------------------------------
 // table image: one device allocation = header + arrays (so one broadcast replicates it)
@@ -730,15 +732,14 @@ __global__ void k_classify(GrimbBatch B, int L, const uint32_t* list, const unsi
   for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n; w += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t s = list ? list[w] : (uint32_t)w;
     const uint32_t typed = B.typed_mask[s];
-    const uint16_t* cn = B.counts + (uint64_t)s * L * 2;
     // candidates per phase ~ product of the listed alleles; phases = 2^(typed-1); an untyped
     // locus multiplies the hits (top links / whole-label scans in Plan B)
     float a = 1.f, b = 1.f;
     int nt = 0;
     for (int l = 0; l < L; ++l)
       if (typed >> l & 1u) {
-        a *= (float)cn[2 * l];
-        b *= (float)cn[2 * l + 1];
+        a *= (float)batch_count(B, s, L, l, 0);
+        b *= (float)batch_count(B, s, L, l, 1);
         ++nt;
       }
     float cost = (a + b) * (float)(1u << (nt > 0 ? nt - 1 : 0));
@@ -828,14 +829,15 @@ __device__ __forceinline__ void fast_load(FastIn& in, const GrimbBatch& B, uint6
   in.typed = B.typed_mask[s];
   const uint32_t off = B.allele_off[s];
   // the listed counts of one subject are 2L uint16 = L aligned uint32; every count must be 1
-  const uint32_t* c32 = reinterpret_cast<const uint32_t*>(B.counts + s * (uint64_t)L * 2);
-  in.c = i < L ? c32[i] : 0x00010001u;
+  in.c = 0x00010001u;
+  if (B.counts && i < L) in.c = reinterpret_cast<const uint32_t*>(B.counts + s * (uint64_t)L * 2)[i];
   in.pair = 0;
-  if (i < L) {
+  // only inside the subject's own range: a subject that lists fewer than 2L alleles is not of this shape
+  if (i < L && 2u * (uint32_t)i + 2u <= B.allele_off[s + 1] - off) {
     const uint16_t* al = B.alleles + off + 2 * i;
     in.pair = (off & 1u) ? ((uint32_t)al[0] | ((uint32_t)al[1] << 16)) : *reinterpret_cast<const uint32_t*>(al);
   }
-  in.m = __ldg(B.priors + B.prior_index[s]);
+  in.m = __ldg(B.priors + batch_prior(B, s));
 }
 
 // Two independent probes of the full-label region; the first sector of each is requested before
@@ -1093,24 +1095,25 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
     pop_base += npop;
     pop_left -= npop;
     if (i == 0) {
-      uint4 w0, w1, w2;
-      w0.x = (typed ? GRIMB_ST_OK : GRIMB_ST_SKIPPED) | ((typed && want_u) ? (GRIMB_PLAN_A << 8) : 0) |
-             ((typed && want_p) ? (GRIMB_PLAN_A << 16) : 0);
-      w0.y = nu;
-      w0.z = np;
-      w0.w = nup;
-      w1.x = npp;
-      w1.y = (want_u && n_acc) ? 1u : 0u;
-      w1.z = want_p ? n_acc : 0u;
-      w1.w = evals;
-      w2.x = (uint32_t)hb;
-      w2.y = (uint32_t)(hb >> 32);
-      w2.z = (uint32_t)pb;
-      w2.w = (uint32_t)(pb >> 32);
-      uint4* dst = reinterpret_cast<uint4*>(R.subjects + sx);
-      dst[0] = w0;
-      dst[1] = w1;
-      dst[2] = w2;
+      if (!typed) {
+        R.compact[sx] = make_compact(GRIMB_ST_SKIPPED, GRIMB_KIND_GENERAL, 0, 0xFFFFFFFFu, 0.0);
+      } else {
+        GrimbSubjectResult o;
+        o.status = GRIMB_ST_OK;
+        o.plan_umug = want_u ? GRIMB_PLAN_A : GRIMB_PLAN_NONE;
+        o.plan_pmug = want_p ? GRIMB_PLAN_A : GRIMB_PLAN_NONE;
+        o.reserved = 0;
+        o.n_umug = nu;
+        o.n_pmug = np;
+        o.n_umug_pops = nup;
+        o.n_pmug_pops = npp;
+        o.tot_umug = (want_u && n_acc) ? 1u : 0u;
+        o.tot_pmug = want_p ? n_acc : 0u;
+        o.pair_evals = evals;
+        o.hap_off = hb;
+        o.pop_off = pb;
+        publish_general(O, sx, o);
+      }
     }
     if ((int64_t)(hb + nh) <= R.hap_capacity) {
       // the single UMUG genotype, per-locus (min, max) of the two typed alleles: the lane whose
@@ -1153,12 +1156,14 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
 // ------------------------------------------------------------------------------------------
 constexpr int FAST_CMAX = 4;   // candidate phases carried per subject; more -> k_impute_fast over an overflow list
 
+// Header and first candidate share one 32-byte sector: the usual subject (one candidate phase) costs one
+// sector written by the probe kernel and one read by the score kernel.
 struct __align__(16) FastMid {
-  uint64_t k0, k1;       // all side-0 / all side-1 alleles, packed
-  double reserved;
-  uint32_t flags;        // bits 0-1 state (0 not for k_fast_score, 1 ready), 2-4 ncand, 8-12 gsel, 16-31 four phase ids
-  uint32_t typed;
+  uint32_t flags;        // bits 0-1 state (0 not for k_fast_score, 1 ready), 2-4 ncand, 5 both haplotypes equal,
+                         // 16-31 four phase ids (ascending)
+  uint32_t pad[3];
   double f[FAST_CMAX][2];  // (f1, f2) of the candidate phases, ascending phase
+  double tail[2];
 };
 
 #ifndef FASTPROBE_MIN_BLOCKS
@@ -1177,7 +1182,7 @@ __device__ __forceinline__ void probe_load(ProbeIn& in, const GrimbBatch& B, uin
   const uint32_t off = B.allele_off[s];
   in.nall = B.allele_off[s + 1] - off;
   in.pair = 0;
-  if (i < L) {
+  if (i < L && 2u * (uint32_t)i + 2u <= in.nall) {   // only inside the subject's own range
     const uint16_t* al = B.alleles + off + 2 * i;
     in.pair = (off & 1u) ? ((uint32_t)al[0] | ((uint32_t)al[1] << 16)) : *reinterpret_cast<const uint32_t*>(al);
   }
@@ -1209,27 +1214,18 @@ k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid,
     if (s + stride < S && s + stride > s) probe_load(nxt, B, s + stride, L, i);
     const uint32_t typed = in.typed;
     const bool shape = typed == full && nchain_ok && in.nall == 2u * (uint32_t)L;   // uniform in the half-warp
-    uint32_t state = 0, ncand = 0, gsel = 0, phases = 0;
+    uint32_t state = 0, ncand = 0, same = 0, phases = 0;
     if (shape) {
       const uint32_t a0 = in.pair & 0xffffu, a1 = in.pair >> 16;
       const uint64_t k0 = half_or64(hmask, (uint64_t)a0 << my_shift);
       const uint64_t k1 = half_or64(hmask, (uint64_t)a1 << my_shift);
-      if (i == 0) {   // first half of the header now: k0 / k1 need not stay live across the probes
-        uint4 h0;
-        h0.x = (uint32_t)k0;
-        h0.y = (uint32_t)(k0 >> 32);
-        h0.z = (uint32_t)k1;
-        h0.w = (uint32_t)(k1 >> 32);
-        reinterpret_cast<uint4*>(mid + s)[0] = h0;
-      }
       // four per-locus flags in one OR-reduction: byte k of `packed` is the locus mask of flag k
       uint32_t bits = 0;
       if (i < L)
-        bits = ((((a0 - 1u) >= my_nal) ? 1u : 0u) | (((a1 - 1u) >= my_nal) ? 0x100u : 0u) | ((a0 != a1) ? 0x10000u : 0u) |
-                ((a0 > a1) ? 0x1000000u : 0u)) << i;
+        bits = ((((a0 - 1u) >= my_nal) ? 1u : 0u) | (((a1 - 1u) >= my_nal) ? 0x100u : 0u) | ((a0 != a1) ? 0x10000u : 0u)) << i;
       const uint32_t packed = __reduce_or_sync(hmask, bits);
       const uint32_t unk0 = packed & 0xFFu, unk1 = (packed >> 8) & 0xFFu, het = (packed >> 16) & 0xFFu;
-      gsel = packed >> 24;
+      same = het == 0u ? 1u : 0u;
       const uint64_t D = k0 ^ k1;
       const uint64_t key = k0 ^ (D & Mi), key2 = key ^ D;
       const uint32_t ib = (uint32_t)i;
@@ -1268,21 +1264,12 @@ k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid,
       if (i == 0) worklist[atomicAdd(worklist_n, 1u)] = s;
     }
     if (i == 0) {
-      if (typed == 0) {   // GRIMB_ST_SKIPPED: finished here
-        uint4 z = make_uint4(0, 0, 0, 0);
-        uint4 w0 = z;
-        w0.x = GRIMB_ST_SKIPPED;
-        uint4* dst = reinterpret_cast<uint4*>(O.r.subjects + s);
-        dst[0] = w0;
-        dst[1] = z;
-        dst[2] = z;
-      }
-      uint4 h1;   // second half of the header: state and candidate bookkeeping
-      h1.x = 0;
-      h1.y = 0;
-      h1.z = state | (ncand << 2) | ((gsel & 31u) << 8) | (phases << 16);
-      h1.w = typed;
-      reinterpret_cast<uint4*>(mid + s)[1] = h1;
+      if (typed == 0)   // GRIMB_ST_SKIPPED: finished here
+        O.r.compact[s] = make_compact(GRIMB_ST_SKIPPED, GRIMB_KIND_GENERAL, 0, 0xFFFFFFFFu, 0.0);
+      uint4 h1;   // header: state and candidate bookkeeping
+      h1.x = state | (ncand << 2) | (same << 5) | (phases << 16);
+      h1.y = h1.z = h1.w = 0;
+      reinterpret_cast<uint4*>(mid + s)[0] = h1;
     }
   }
 }
@@ -1295,13 +1282,10 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
              const FastMid* __restrict__ mid, uint32_t* worklist, unsigned int* worklist_n) {
   __shared__ double s_chain[FAST_MAX_ROUNDS];
   __shared__ int s_nchain;
-  __shared__ uint64_t s_mask[16];
   const int lane = threadIdx.x & 31;
-  const int L = T.L;
-  const int nphase = 1 << (L - 1);
   GrimbResults& R = O.r;
   const bool want_u = cfg->output_umug != 0, want_p = cfg->output_pmug != 0, planb = cfg->planb != 0;
-  const uint32_t lim_r = (uint32_t)cfg->n_results, lim_p = (uint32_t)cfg->n_pop_results;
+  const uint32_t lim_r = (uint32_t)cfg->n_results;
   if (threadIdx.x == 0) {
     double e = cfg->epsilon;
     int n = 0;
@@ -1312,22 +1296,15 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
     }
     s_nchain = (e > 0) ? -1 : n;
   }
-  if (threadIdx.x < 16) {   // field mask of the loci phase i flips
-    uint64_t mk = 0;
-    for (int l = 0; l < L; ++l)
-      if ((threadIdx.x >> l) & 1) mk |= ((1ull << T.width[l]) - 1ull) << T.shift[l];
-    s_mask[threadIdx.x] = mk;
-  }
   __syncthreads();
   const int nchain = s_nchain;
-  const uint64_t Mlast = ((1ull << T.width[L - 1]) - 1ull) << T.shift[L - 1];
   const uint64_t S = (uint64_t)B.n_subjects;
   const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
-  // whole warps iterate together (the row-space claim is a warp scan)
+  unsigned long long evals_sum = 0;
+  // whole warps iterate together (the word-space claim is a warp scan)
   for (uint64_t s0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; s0 < S; s0 += nthreads) {
     const uint64_t s = s0 + lane;
     bool ready = false;
-    uint64_t k0 = 0, k1 = 0;
     double m = 0.0;
     uint32_t fl = 0;
     double2 f0 = make_double2(0.0, 0.0);
@@ -1335,19 +1312,15 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
       // everything that does not depend on the header is requested with it: the prior (P == 1: one
       // double per subject) and the first candidate's frequencies
       const uint4* src = reinterpret_cast<const uint4*>(mid + s);
-      const uint4 h0 = src[0], h1 = src[1];
-      const uint32_t pi = B.prior_index[s];
-      f0 = *reinterpret_cast<const double2*>(&mid[s].f[0][0]);   // garbage unless ncand >= 1
+      const uint4 h1 = src[0];
+      const uint32_t pi = batch_prior(B, s);
+      f0 = *reinterpret_cast<const double2*>(&mid[s].f[0][0]);   // same sector as the header; garbage unless ncand >= 1
       m = __ldg(B.priors + pi);
-      k0 = (uint64_t)h0.x | ((uint64_t)h0.y << 32);
-      k1 = (uint64_t)h0.z | ((uint64_t)h0.w << 32);
-      fl = h1.z;
+      fl = h1.x;
       ready = (fl & 3u) == 1u;
     }
     const uint32_t ncand = ready ? ((fl >> 2) & 7u) : 0u;
-    const uint32_t gsel = (fl >> 8) & 31u;
-    const uint64_t D = k0 ^ k1;
-    const bool same = D == 0;
+    const bool same = (fl >> 5) & 1u;
     const bool mpos = m > 0;
     double pf[FAST_CMAX], pf2[FAST_CMAX], prob[FAST_CMAX];
     uint32_t rq[FAST_CMAX];
@@ -1430,93 +1403,55 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
       }
     if (want_u && want_p) evals *= 2;
     bool done = ready;
-    if (ready && n_acc == 0 && planb) {   // Plan B / C: general kernel
+    if (ready && n_acc == 0 && planb) {   // Plan B / C: general kernel (which counts its own evaluations)
       worklist[atomicAdd(worklist_n, 1u)] = (uint32_t)s;
       done = false;
     }
-    const bool rows = done && n_acc != 0;
-    const uint32_t nu = (rows && want_u) ? (lim_r < 1u ? lim_r : 1u) : 0u;
-    const uint32_t np = (rows && want_p) ? (n_acc < lim_r ? n_acc : lim_r) : 0u;
-    const uint32_t nup = (rows && want_u) ? (lim_p < 1u ? lim_p : 1u) : 0u;
-    const uint32_t npp = (rows && want_p) ? (lim_p < 1u ? lim_p : 1u) : 0u;
-    const uint32_t nh = nu + np, npop = nup + npp;
-    // one claim of row space per warp: inclusive scans of the two counts
-    uint32_t sh_ = nh, sp_ = npop;
+    if (done) evals_sum += evals;
+    const uint32_t np = (done && n_acc != 0 && want_p) ? (n_acc < lim_r ? n_acc : lim_r) : 0u;
+    // PMUG probabilities travel as 8-byte words only when several phases were accepted (with one accepted
+    // phase the row's probability is `total`); one claim of word space per warp, and none at all for the
+    // usual warp whose subjects all have a single accepted phase
+    const uint32_t nw = (np != 0u && n_acc >= 2u) ? np : 0u;
+    uint32_t sc = nw;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, sh_, d), b = __shfl_up_sync(0xFFFFFFFFu, sp_, d);
-      if (lane >= d) {
-        sh_ += a;
-        sp_ += b;
-      }
+      const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, sc, d);
+      if (lane >= d) sc += a;
     }
-    unsigned long long hbw = 0, pbw = 0;
-    if (lane == 31) {
-      if (sh_) hbw = atomicAdd(O.hap_counter, (unsigned long long)sh_);
-      if (sp_) pbw = atomicAdd(O.pop_counter, (unsigned long long)sp_);
+    const uint32_t wtot = __shfl_sync(0xFFFFFFFFu, sc, 31);
+    unsigned long long wb = 0;
+    if (wtot) {
+      if (lane == 31) wb = atomicAdd(O.word_counter, (unsigned long long)wtot);
+      wb = __shfl_sync(0xFFFFFFFFu, wb, 31);
     }
-    hbw = __shfl_sync(0xFFFFFFFFu, hbw, 31);
-    pbw = __shfl_sync(0xFFFFFFFFu, pbw, 31);
     if (!done) continue;
-    const uint64_t hb = hbw + (sh_ - nh), pb = pbw + (sp_ - npop);
-    {
-      uint4 w0, w1, w2;
-      w0.x = GRIMB_ST_OK | (want_u ? (GRIMB_PLAN_A << 8) : 0) | (want_p ? (GRIMB_PLAN_A << 16) : 0);
-      w0.y = nu;
-      w0.z = np;
-      w0.w = nup;
-      w1.x = npp;
-      w1.y = (want_u && n_acc) ? 1u : 0u;
-      w1.z = want_p ? n_acc : 0u;
-      w1.w = evals;
-      w2.x = (uint32_t)hb;
-      w2.y = (uint32_t)(hb >> 32);
-      w2.z = (uint32_t)pb;
-      w2.w = (uint32_t)(pb >> 32);
-      uint4* dst = reinterpret_cast<uint4*>(R.subjects + s);
-      dst[0] = w0;
-      dst[1] = w1;
-      dst[2] = w2;
-    }
-    if ((int64_t)(hb + nh) <= R.hap_capacity) {
-      if (nu) {
-        // the single UMUG genotype: per-locus (min, max) of the two typed alleles
-        const uint64_t mg = s_mask[gsel & ((uint32_t)nphase - 1u)] | (((gsel >> (L - 1)) & 1u) ? Mlast : 0ull);
-        GrimbHapRow o;
-        o.a = k0 ^ (D & mg);
-        o.b = o.a ^ D;
-        o.prob = total;
-        R.hap_rows[hb] = o;
-      }
+    const uint64_t my = wb + (sc - nw);
+    const bool fits = (int64_t)(wb + wtot) <= R.word_capacity;
+    uint32_t phases = 0;
 #pragma unroll
-      for (int q = 0; q < FAST_CMAX; ++q)
-        if (acc[q]) {
-          // rank by (probability desc, phase asc); candidates are stored in ascending phase order
-          uint32_t rank = 0;
+    for (int q = 0; q < FAST_CMAX; ++q)
+      if (acc[q]) {
+        // rank by (probability desc, phase asc); candidates are stored in ascending phase order
+        uint32_t rank = 0;
 #pragma unroll
-          for (int j = 0; j < FAST_CMAX; ++j)
-            if (acc[j] && (prob[j] > prob[q] || (prob[j] == prob[q] && j < q))) ++rank;
-          if (rank < np) {
-            const uint32_t ph = (fl >> (16 + 4 * q)) & 15u;
-            GrimbHapRow o;
-            o.a = k0 ^ (D & s_mask[ph]);
-            o.b = o.a ^ D;
-            o.prob = prob[q];
-            R.hap_rows[hb + nu + rank] = o;
-          }
+        for (int j = 0; j < FAST_CMAX; ++j)
+          if (acc[j] && (prob[j] > prob[q] || (prob[j] == prob[q] && j < q))) ++rank;
+        if (rank < np) {
+          phases |= ((fl >> (16 + 4 * q)) & 15u) << (4 * rank);
+          if (nw && fits) R.words[my + rank] = (uint64_t)__double_as_longlong(prob[q]);
         }
-    }
-    if ((int64_t)(pb + npop) <= R.pop_capacity) {
-      for (uint32_t r = 0; r < npop; ++r) {
-        GrimbPopRow o;
-        o.pop_a = 0;
-        o.pop_b = 0;
-        o.pad = 0;
-        o.prob = total;
-        R.pop_rows[pb + r] = o;
       }
-    }
+    // the UMUG genotype and the two haplotypes of every PMUG row follow from the subject's own alleles and
+    // the phase ids (include/grimb200.h, GRIMB_KIND_SIMPLE): one 16-byte store per subject
+    const GrimbCompact c = make_compact(GRIMB_ST_OK, GRIMB_KIND_SIMPLE | (n_acc ? GRIMB_KIND_HAS_RESULTS : 0u) |
+                                        (nw ? GRIMB_KIND_WORDS : 0u) | (np << 4), phases, (uint32_t)my, total);
+    *reinterpret_cast<uint4*>(R.compact + s) = *reinterpret_cast<const uint4*>(&c);
   }
+  // pair evaluations of the subjects finished here: one atomic per warp for the whole launch
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) evals_sum += __shfl_xor_sync(0xFFFFFFFFu, evals_sum, d);
+  if (lane == 0 && evals_sum) atomicAdd(O.evals_counter, evals_sum);
 }
 
 #endif  // GRIMB_KW == 1
@@ -1549,7 +1484,8 @@ constexpr int TY_VP = 4;
 constexpr int TY_MAX_ROUNDS = 40;
 
 struct __align__(16) TyLists {
-  hkey hk[TY_VP][2];
+  uint16_t ph[TY_VP];     // phase id of the kept phase (bit m: locus m takes its side-2 allele in haplotype 1)
+  uint16_t ph_pad[4];
   double f1s[TY_VP][32];
   double f2s[TY_VP][32];
   double pm2[TY_VP][32];
@@ -1597,31 +1533,20 @@ k_impute_typed(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, 
   const uint32_t full = (1u << L) - 1u;
   const uint32_t nphase = 1u << (L - 1);
   const uint64_t S = (uint64_t)B.n_subjects;
+  unsigned long long evals_sum = 0;   // pair evaluations of the subjects this warp finishes (warp-uniform)
   for (uint64_t s = (uint64_t)blockIdx.x * TY_WARPS + warp; s < S; s += (uint64_t)gridDim.x * TY_WARPS) {
     const uint32_t typed = B.typed_mask[s];
     if (typed == 0) {   // GRIMB_ST_SKIPPED
-      if (lane == 0) {
-        uint4 z = make_uint4(0, 0, 0, 0);
-        uint4 w0 = z;
-        w0.x = GRIMB_ST_SKIPPED;
-        uint4* dst = reinterpret_cast<uint4*>(R.subjects + s);
-        dst[0] = w0;
-        dst[1] = z;
-        dst[2] = z;
-      }
+      if (lane == 0) R.compact[s] = make_compact(GRIMB_ST_SKIPPED, GRIMB_KIND_GENERAL, 0, 0xFFFFFFFFu, 0.0);
       continue;
     }
-    bool shape = typed == full && nchain >= 0;
-    {
-      const uint16_t* cn = B.counts + s * (uint64_t)L * 2;
-      bool ones = true;
-      for (int q = lane; q < 2 * L; q += 32) ones = ones && cn[q] == 1;
-      shape = __all_sync(FULLM, ones) && shape;
-    }
+    // one allele per side at every locus: every typed side lists >= 1 allele, so the total says it all
+    const uint32_t al_off = B.allele_off[s];
+    const bool shape = typed == full && nchain >= 0 && B.allele_off[s + 1] - al_off == 2u * (uint32_t)L;
     uint32_t pairs[GRIMB_MAX_LOCI];
     uint32_t het = 0;
     if (shape) {
-      const uint16_t* al = B.alleles + B.allele_off[s];
+      const uint16_t* al = B.alleles + al_off;
 #pragma unroll
       for (int l = 0; l < GRIMB_MAX_LOCI; ++l) {
         pairs[l] = 0;
@@ -1638,7 +1563,7 @@ k_impute_typed(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, 
     const bool same = het == 0;
     int nvp = 0;
     bool punt = !shape;
-    const double* M = B.priors + (uint64_t)B.prior_index[s] * P * P;
+    const double* M = B.priors + (uint64_t)batch_prior(B, s) * P * P;
     if (!punt) {
       const double mdiag = lane < P ? __ldg(M + lane * P + lane) : 0.0;
       const uint32_t low = het & (nphase - 1u);
@@ -1693,8 +1618,7 @@ k_impute_typed(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, 
             W.f2s[nvp][r2] = f2;
             W.p2s[nvp][r2] = (uint8_t)lane;
           }
-          if (lane == b) W.hk[nvp][0] = key;
-          if (lane == 16 + b) W.hk[nvp][1] = key;
+          if (lane == 0) W.ph[nvp] = (uint16_t)(base + (uint32_t)b);
           __syncwarp();
           double pmv = lane < n2 ? W.f2s[nvp][lane] : 0.0;
 #pragma unroll
@@ -1865,63 +1789,40 @@ k_impute_typed(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, 
       if (lane == 0) worklist[atomicAdd(worklist_n, 1u)] = (uint32_t)s;
       continue;
     }
-    // ---- publish
-    const uint32_t nu = want_u ? (lim_r < 1u ? lim_r : 1u) : 0u;
+    // ---- publish (include/grimb200.h, GRIMB_KIND_TYPED): record + header word, PMUG probabilities,
+    // population-pair probabilities in rank order, their pair codes four per word.  The UMUG genotype and
+    // the haplotypes of the PMUG rows follow from the subject's alleles and the phase ids.
     const uint32_t np = want_p ? (nrows < lim_r ? nrows : lim_r) : 0u;
     const uint32_t npg = ng < lim_p ? ng : lim_p;
-    const uint32_t nup = want_u ? npg : 0u, npp = want_p ? npg : 0u;
-    const uint32_t nh = nu + np, npop = nup + npp;
-    unsigned long long hb = 0, pb = 0;
-    if (lane == 0) {
-      if (nh) hb = atomicAdd(O.hap_counter, (unsigned long long)nh);
-      if (npop) pb = atomicAdd(O.pop_counter, (unsigned long long)npop);
-    }
-    hb = __shfl_sync(FULLM, hb, 0);
-    pb = __shfl_sync(FULLM, pb, 0);
+    const uint32_t nwords = 1u + np + npg + ((npg + 3u) >> 2);
+    unsigned long long wb = 0;
+    if (lane == 0) wb = atomicAdd(O.word_counter, (unsigned long long)nwords);
+    wb = __shfl_sync(FULLM, wb, 0);
     if (want_u && want_p) evals *= 2;   // the reference evaluates once per output kind
-    if (lane == 0) {
-      uint4 w0, w1, w2;
-      w0.x = GRIMB_ST_OK | (want_u ? (GRIMB_PLAN_A << 8) : 0) | (want_p ? (GRIMB_PLAN_A << 16) : 0);
-      w0.y = nu;
-      w0.z = np;
-      w0.w = nup;
-      w1.x = npp;
-      w1.y = want_u ? 1u : 0u;
-      w1.z = want_p ? E : 0u;
-      w1.w = evals;
-      w2.x = (uint32_t)hb;
-      w2.y = (uint32_t)(hb >> 32);
-      w2.z = (uint32_t)pb;
-      w2.w = (uint32_t)(pb >> 32);
-      uint4* dst = reinterpret_cast<uint4*>(R.subjects + s);
-      dst[0] = w0;
-      dst[1] = w1;
-      dst[2] = w2;
+    evals_sum += evals;                 // warp-uniform
+    const bool fits = (int64_t)(wb + nwords) <= R.word_capacity;
+    // PMUG rows: one per phase with accepted pairs, by (sum desc, phase asc)
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < nrows; ++j) {
+      const double sj = __shfl_sync(FULLM, my_sum, (int)j);
+      if (sj > my_sum || (sj == my_sum && (int)j < lane)) ++rank;
     }
-    if ((int64_t)(hb + nh) <= R.hap_capacity) {
-      if (lane == 0 && nu) {
-        hkey glo = 0, ghi = 0;   // the single UMUG genotype: per-locus (min, max)
+    const bool my_row = lane < (int)nrows && rank < np;
+    uint64_t hdr = my_row ? ((uint64_t)W.ph[my_vp] << (16 + 12 * rank)) : 0ull;
 #pragma unroll
-        for (int l = 0; l < GRIMB_MAX_LOCI; ++l)
-          if (l < L) {
-            const uint32_t a0 = pairs[l] & 0xffffu, a1 = pairs[l] >> 16;
-            glo |= (hkey)(a0 < a1 ? a0 : a1) << T.shift[l];
-            ghi |= (hkey)(a0 < a1 ? a1 : a0) << T.shift[l];
-          }
-        R.hap_rows[hb] = make_hap_row(glo, ghi, total);
-      }
-      // PMUG rows: one per phase with accepted pairs, by (sum desc, phase asc)
-      uint32_t rank = 0;
-      for (uint32_t j = 0; j < nrows; ++j) {
-        const double sj = __shfl_sync(FULLM, my_sum, (int)j);
-        if (sj > my_sum || (sj == my_sum && (int)j < lane)) ++rank;
-      }
-      if (lane < (int)nrows && rank < np) R.hap_rows[hb + nu + rank] = make_hap_row(W.hk[my_vp][0], W.hk[my_vp][1], my_sum);
+    for (int d = 16; d > 0; d >>= 1) hdr |= __shfl_xor_sync(FULLM, hdr, d);
+    if (fits) {
+      if (lane == 0) R.words[wb] = hdr | (uint64_t)npg;
+      if (my_row) R.words[wb + 1 + rank] = (uint64_t)__double_as_longlong(my_sum);
     }
+    if (lane == 0)
+      R.compact[s] = make_compact(GRIMB_ST_OK, GRIMB_KIND_TYPED | GRIMB_KIND_HAS_RESULTS | (np << 4), 0, (uint32_t)wb, total);
     __syncwarp();
-    if ((int64_t)(pb + npop) <= R.pop_capacity && npg) {
-      // population rows by (sum desc, first encounter asc); same rows for both output kinds
-      // each lane ranks up to 4 groups per sweep over the list (one shared-memory read per comparand)
+    if (npg) {
+      // population rows by (sum desc, first encounter asc); the same rows serve both output kinds.  Each
+      // lane ranks up to 4 groups per sweep over the list (one shared-memory read per comparand); the
+      // group-lookup table is free by now and takes the pair codes in rank order.
+      uint16_t* codes = gslot;
       for (uint32_t t0 = lane; t0 < ng; t0 += 128) {
         double vt[4];
         uint32_t rk[4];
@@ -1941,22 +1842,44 @@ k_impute_typed(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, 
         for (int q = 0; q < 4; ++q) {
           const uint32_t t = t0 + 32u * q;
           if (t < ng && rk[q] < npg) {
-            GrimbPopRow o;
-            o.pop_a = (uint16_t)(gpair[t] >> 8);
-            o.pop_b = (uint16_t)(gpair[t] & 0xffu);
-            o.pad = 0;
-            o.prob = vt[q];
-            if (nup) R.pop_rows[pb + rk[q]] = o;
-            if (npp) R.pop_rows[pb + nup + rk[q]] = o;
+            codes[rk[q]] = gpair[t];
+            if (fits) R.words[wb + 1 + np + rk[q]] = (uint64_t)__double_as_longlong(vt[q]);
           }
         }
       }
+      __syncwarp();
+      if (fits)
+        for (uint32_t w = lane; w < ((npg + 3u) >> 2); w += 32) {
+          uint64_t v = 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (4 * w + q < npg) v |= (uint64_t)codes[4 * w + q] << (16 * q);
+          R.words[wb + 1 + np + npg + w] = v;
+        }
     }
     __syncwarp();
   }
+  if (lane == 0 && evals_sum) atomicAdd(O.evals_counter, evals_sum);
 }
 
 constexpr int GRIMB_MAX_CHUNKS = 64;
+
+// Device counters of one call (unsigned long long each).  The first eight are per launch group (one
+// chunk of a host batch) and are cleared between chunks; the rest keep running across the chunks of one
+// ABI call, so the rows / words / records of a chunk occupy one contiguous range of their arrays.
+enum {
+  CNT_WORK = 0,       // tickets of the general kernel's persistent CTAs
+  CNT_WORKLIST = 1,   // (u32) subjects handed from a warp-per-subject kernel to the general kernel
+  CNT_BUCKETS = 2,    // (4 x u32) cost buckets of the general kernel's work
+  CNT_OVERFLOW = 4,   // (u32) subjects with more candidate phases than a hand-over record holds
+  CNT_CHUNK_END = 8,
+  CNT_HAP = 8,
+  CNT_POP = 9,
+  CNT_WORDS = 10,
+  CNT_GENERAL = 11,
+  CNT_EVALS = 12,
+  CNT_N = 16
+};
 
 struct GrimbEngine {
   const GrimbTables* tables;
@@ -1967,23 +1890,27 @@ struct GrimbEngine {
   char* arena = nullptr;
   double* ones = nullptr;
   GrimbConfig* d_cfg = nullptr;
-  unsigned long long* d_counters = nullptr;  // [0] work, [1] hap rows, [2] pop rows
+  unsigned long long* d_counters = nullptr;  // [CNT_N]
   cudaStream_t stream = nullptr;
   cudaStream_t s_in = nullptr, s_out = nullptr;   // copy-in / copy-out streams of the pipelined host call
   cudaEvent_t ev_in[GRIMB_MAX_CHUNKS], ev_k[GRIMB_MAX_CHUNKS];
-  unsigned long long* h_cnt = nullptr;            // pinned: counters after every chunk [GRIMB_MAX_CHUNKS][4]
-  int64_t host_chunk = 131072;                    // subjects per pipeline chunk (GRIMB_HOST_CHUNK)
+  unsigned long long* h_cnt = nullptr;            // pinned: counters after every chunk [GRIMB_MAX_CHUNKS][CNT_N]
+  int64_t host_chunk = 262144;                    // subjects per pipeline chunk (GRIMB_HOST_CHUNK)
   GrimbConfig cfg_host;                           // the configuration d_cfg holds (valid when cfg_sent)
   int cfg_sent = 0;
-  unsigned long long* h_tail = nullptr;           // pinned: the 8 counters as read by the device-pointer call
+  unsigned long long* h_tail = nullptr;           // pinned: the counters as read by the device-pointer call
+  cudaStream_t pending_stream = nullptr;          // grimb_impute_device_async: stream of the call in flight
+  int pending = 0;
   int64_t launches = 0;
   // staging for the host-pointer form (grow-only)
-  DevBuf in[6], outb[3], in_mask;
+  DevBuf in[6], outb[5], in_mask;
   DevBuf worklist;   // subjects the fast kernel hands to the general kernel
   DevBuf buckets;    // the general kernel's work, by cost bucket (heaviest first)
   int sm_count = 0;
   int fast_path = 1; // GRIMB_FAST=0 disables the warp-per-subject kernel (debugging / A-B runs)
   int fast_split = 1; // k_fast_probe + k_fast_score (default); GRIMB_FAST_SPLIT=0: the fused k_impute_fast
+  int timing = 1;     // CUDA events around the kernels in the device-pointer form (GRIMB_KERNEL_EVENTS=0: none)
+  int timing_host = 0;   // ... in the chunked host-pointer form (GRIMB_HOST_EVENTS=1)
   DevBuf mid;         // hand-over records of the split fast path
   DevBuf overflow;    // subjects with more candidate phases than a hand-over record holds
   cudaEvent_t ev_score[2] = {nullptr, nullptr};
@@ -1996,20 +1923,32 @@ struct GrimbEngine {
   uint32_t typed_per_warp = 0;
 };
 
+extern "C" int grimb_engine_free(GrimbEngine* e);
+
 extern "C" int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes_per_cta, GrimbEngine** out) {
   if (!t || !out || workspace_bytes_per_cta < (1 << 16)) return fail(GRIMB_E_ARG, "bad engine arguments");
   CK(cudaSetDevice(t->device));
   GrimbEngine* e = new GrimbEngine();
+  for (int i = 0; i < GRIMB_MAX_CHUNKS; ++i) e->ev_in[i] = e->ev_k[i] = nullptr;
   e->tables = t;
   e->device = t->device;
   e->threads = 128;
+  // every failure below releases what was created so far
+#define CKE(call)                                                                          \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      grimb_engine_free(e);                                                                \
+      return fail(GRIMB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+    }                                                                                      \
+  } while (0)
   cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, t->device));
+  CKE(cudaGetDeviceProperties(&prop, t->device));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_impute, e->threads, 0));
+  CKE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_impute, e->threads, 0));
   if (per_sm < 1) per_sm = 1;
   size_t free_b = 0, total_b = 0;
-  CK(cudaMemGetInfo(&free_b, &total_b));
+  CKE(cudaMemGetInfo(&free_b, &total_b));
   int64_t n = (int64_t)prop.multiProcessorCount * per_sm;
   e->arena_per_cta = ((uint64_t)workspace_bytes_per_cta + 255ull) & ~255ull;
   while (n > prop.multiProcessorCount && (uint64_t)n * e->arena_per_cta > free_b / 2) n -= prop.multiProcessorCount;
@@ -2017,50 +1956,55 @@ extern "C" int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes
   e->n_ctas = (int)n;
   cudaError_t ce = cudaMalloc((void**)&e->arena, (uint64_t)e->n_ctas * e->arena_per_cta);
   if (ce != cudaSuccess) {
-    delete e;
+    grimb_engine_free(e);
     return fail(GRIMB_E_NOMEM, std::string("engine arena: ") + cudaGetErrorString(ce));
   }
   const int P = t->h.P;
   std::vector<double> one((size_t)P * P, 1.0);
-  CK(cudaMalloc((void**)&e->ones, one.size() * 8));
-  CK(cudaMemcpy(e->ones, one.data(), one.size() * 8, cudaMemcpyHostToDevice));
-  CK(cudaMalloc((void**)&e->d_cfg, sizeof(GrimbConfig)));
-  CK(cudaMalloc((void**)&e->d_counters, 64));
-  CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+  CKE(cudaMalloc((void**)&e->ones, one.size() * 8));
+  CKE(cudaMemcpy(e->ones, one.data(), one.size() * 8, cudaMemcpyHostToDevice));
+  CKE(cudaMalloc((void**)&e->d_cfg, sizeof(GrimbConfig)));
+  CKE(cudaMalloc((void**)&e->d_counters, CNT_N * sizeof(unsigned long long)));
+  CKE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CKE(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+  CKE(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
   for (int i = 0; i < GRIMB_MAX_CHUNKS; ++i) {
-    CK(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&e->ev_k[i], cudaEventDisableTiming));
+    CKE(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
+    CKE(cudaEventCreateWithFlags(&e->ev_k[i], cudaEventDisableTiming));
   }
-  CK(cudaMallocHost((void**)&e->h_cnt, GRIMB_MAX_CHUNKS * 4 * sizeof(unsigned long long)));
-  CK(cudaMallocHost((void**)&e->h_tail, 8 * sizeof(unsigned long long)));
+  CKE(cudaMallocHost((void**)&e->h_cnt, GRIMB_MAX_CHUNKS * CNT_N * sizeof(unsigned long long)));
+  CKE(cudaMallocHost((void**)&e->h_tail, CNT_N * sizeof(unsigned long long)));
   if (const char* hc = getenv("GRIMB_HOST_CHUNK")) {
     const long long v = atoll(hc);
     if (v >= 1024) e->host_chunk = v;
   }
-  for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&e->ev[i]));
+  for (int i = 0; i < 6; ++i) CKE(cudaEventCreate(&e->ev[i]));
   e->sm_count = prop.multiProcessorCount;
   if (P <= 32) {
     e->typed_per_warp = (uint32_t)ty_bytes_per_warp(P);
     const size_t dyn = (size_t)e->typed_per_warp * TY_WARPS;
     // the attribute is per function, not per engine: always allow the largest layout (P = 32)
-    CK(cudaFuncSetAttribute(k_impute_typed, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(ty_bytes_per_warp(32) * TY_WARPS)));
+    CKE(cudaFuncSetAttribute(k_impute_typed, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(ty_bytes_per_warp(32) * TY_WARPS)));
     int tb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tb, k_impute_typed, TY_WARPS * 32, dyn));
+    CKE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tb, k_impute_typed, TY_WARPS * 32, dyn));
     e->typed_ctas = (tb < 1 ? 1 : tb) * prop.multiProcessorCount;
   }
   const char* fp = getenv("GRIMB_FAST");
   if (fp && fp[0] == '0') e->fast_path = 0;
   const char* fsp = getenv("GRIMB_FAST_SPLIT");
   if (fsp && fsp[0] == '0') e->fast_split = 0;
-  for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&e->ev_score[i]));
+  const char* kev = getenv("GRIMB_KERNEL_EVENTS");
+  if (kev && kev[0] == '0') e->timing = 0;
+  const char* hev = getenv("GRIMB_HOST_EVENTS");
+  if (hev && hev[0] == '1') e->timing_host = 1;
+  for (int i = 0; i < 2; ++i) CKE(cudaEventCreate(&e->ev_score[i]));
   const char* th = getenv("GRIMB_THREADS");
   if (th) {
     int v = atoi(th);
     if (v >= 32 && v <= MAXT && v % 32 == 0) e->threads = v;
   }
+#undef CKE
   *out = e;
   return GRIMB_OK;
 }
@@ -2068,6 +2012,7 @@ extern "C" int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes
 extern "C" int grimb_engine_free(GrimbEngine* e) {
   if (!e) return GRIMB_OK;
   cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
   cudaFree(e->arena);
   cudaFree(e->ones);
   cudaFree(e->d_cfg);
@@ -2079,20 +2024,25 @@ extern "C" int grimb_engine_free(GrimbEngine* e) {
     if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
     if (e->ev_k[i]) cudaEventDestroy(e->ev_k[i]);
   }
+  for (int i = 0; i < 6; ++i)
+    if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  for (int i = 0; i < 2; ++i)
+    if (e->ev_score[i]) cudaEventDestroy(e->ev_score[i]);
   if (e->h_cnt) cudaFreeHost(e->h_cnt);
   if (e->h_tail) cudaFreeHost(e->h_tail);
+  cudaGetLastError();
   delete e;
   return GRIMB_OK;
 }
 
 extern "C" int64_t grimb_engine_launches(const GrimbEngine* e) { return e ? e->launches : 0; }
 
-// Device time (CUDA events on the launching stream) of the last launch of k_impute_fast (which = 0),
-// k_impute (which = 1) or k_impute_typed (which = 2); valid after the call that launched it has
-// returned.  < 0 if not launched.
+// Device time (CUDA events on the launching stream) of the last launch of k_fast_probe / k_impute_fast
+// (which = 0), k_impute (1), k_impute_typed (2), k_fast_score (4); valid after the call that launched it
+// has finished.  < 0 if not launched.  which = 3: subjects the last call handed on to k_impute.
 extern "C" double grimb_engine_kernel_ms(const GrimbEngine* e, int which) {
-  if (e && which == 3) return e->last_worklist;   // diagnostic: subjects handed to k_impute by the last call
-  if (e && which == 4) {                           // k_fast_score of the split fast path
+  if (e && which == 3) return e->last_worklist;
+  if (e && which == 4) {
     float ms4 = -1.f;
     if (!e->ev_score_valid || cudaEventElapsedTime(&ms4, e->ev_score[0], e->ev_score[1]) != cudaSuccess) {
       cudaGetLastError();
@@ -2134,10 +2084,20 @@ static int upload_cfg(GrimbEngine* e, const GrimbConfig* cfg, cudaStream_t st) {
   return GRIMB_OK;
 }
 
-// Launches the kernels for one batch view (device pointers) on `st`; no synchronisation.  The row
-// counters d_counters[1..2] keep running across calls of one ABI call (chunks of one host batch).
+static OutArrays out_arrays(GrimbEngine* e, const GrimbResults& r) {
+  OutArrays O;
+  O.r = r;
+  O.hap_counter = e->d_counters + CNT_HAP;
+  O.pop_counter = e->d_counters + CNT_POP;
+  O.word_counter = e->d_counters + CNT_WORDS;
+  O.general_counter = e->d_counters + CNT_GENERAL;
+  O.evals_counter = e->d_counters + CNT_EVALS;
+  return O;
+}
+
+// Launches the kernels for one batch view (device pointers) on `st`; no synchronisation.
 static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch, const OutArrays& O,
-                          cudaStream_t st) {
+                          cudaStream_t st, bool timed) {
   e->ev_valid[0] = e->ev_valid[1] = e->ev_valid[2] = 0;
   e->ev_score_valid = 0;
   if (batch->n_subjects <= 0) return GRIMB_OK;
@@ -2147,17 +2107,15 @@ static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBat
   const uint32_t* wl = nullptr;
   const unsigned int* wl_n = nullptr;
   const uint64_t stride = (uint64_t)batch->n_subjects;
+  const bool tm = timed;   // CUDA events around the kernels (one API call each: off in the chunked host path)
   CK(e->buckets.reserve((size_t)stride * 4 * GRIMB_BUCKETS + 16));
-  unsigned int* bucket_n = (unsigned int*)(e->d_counters + 4);
+  unsigned int* bucket_n = (unsigned int*)(e->d_counters + CNT_BUCKETS);
+  unsigned int* cnt = (unsigned int*)(e->d_counters + CNT_WORKLIST);
 #if GRIMB_KW == 1
   if (warp_kernels && tv.L <= 5 && tv.P == 1) {
-    // warp-per-subject kernel first; what it cannot finish goes through the general kernel
+    // warp-per-subject kernels first; what they cannot finish goes through the general kernel
     CK(e->worklist.reserve((size_t)batch->n_subjects * 4 + 16));
-    unsigned int* cnt = (unsigned int*)(e->d_counters + 3);
     const uint64_t groups = ((uint64_t)batch->n_subjects + FAST_WARPS * 2 - 1) / (FAST_WARPS * 2);
-    uint64_t fg = (uint64_t)e->sm_count * FAST_MIN_BLOCKS;  // resident CTAs only: each warp strides over subjects
-    if (fg > groups) fg = groups;
-#if GRIMB_KW == 1
     if (e->fast_split) {
       CK(e->mid.reserve((size_t)batch->n_subjects * sizeof(FastMid) + 16));
       double eps = cfg->epsilon;
@@ -2169,38 +2127,38 @@ static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBat
       }
       uint64_t fgp = (uint64_t)e->sm_count * FASTPROBE_MIN_BLOCKS;
       if (fgp > groups) fgp = groups;
-      CK(cudaEventRecord(e->ev[0], st));
       CK(e->overflow.reserve((size_t)batch->n_subjects * 4 + 16));
-      unsigned int* ovf_n = (unsigned int*)(e->d_counters + 6);
+      unsigned int* ovf_n = (unsigned int*)(e->d_counters + CNT_OVERFLOW);
+      if (tm) CK(cudaEventRecord(e->ev[0], st));
       k_fast_probe<<<(unsigned)fgp, FAST_WARPS * 32, 0, st>>>(tv, *batch, O, (FastMid*)e->mid.p, (uint32_t*)e->worklist.p,
                                                             cnt, (uint32_t*)e->overflow.p, ovf_n, eps > 0 ? 0 : 1);
       CK(cudaGetLastError());
-      CK(cudaEventRecord(e->ev[1], st));
+      if (tm) CK(cudaEventRecord(e->ev[1], st));
       uint64_t sg = ((uint64_t)batch->n_subjects + 127) / 128;
       if (sg > (uint64_t)e->sm_count * 16) sg = (uint64_t)e->sm_count * 16;
-      CK(cudaEventRecord(e->ev_score[0], st));
+      if (tm) CK(cudaEventRecord(e->ev_score[0], st));
       k_fast_score<<<(unsigned)sg, 128, 0, st>>>(tv, e->d_cfg, *batch, O, (const FastMid*)e->mid.p,
                                                 (uint32_t*)e->worklist.p, cnt);
       CK(cudaGetLastError());
-      CK(cudaEventRecord(e->ev_score[1], st));
-      e->ev_score_valid = 1;
-      e->ev_valid[0] = 1;
+      if (tm) CK(cudaEventRecord(e->ev_score[1], st));
+      e->ev_score_valid = tm;
+      e->ev_valid[0] = tm;
       e->launches += 2;
       // subjects with more than FAST_CMAX candidate phases: the fused kernel over the overflow list
       k_impute_fast<true><<<32u, FAST_WARPS * 32, 0, st>>>(tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt,
                                                                      (const uint32_t*)e->overflow.p, ovf_n);
       CK(cudaGetLastError());
       e->launches += 1;
-    } else
-#endif
-    {
-    CK(cudaEventRecord(e->ev[0], st));
-    k_impute_fast<false><<<(unsigned)fg, FAST_WARPS * 32, 0, st>>>(tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt, nullptr,
-                                                           nullptr);
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(e->ev[1], st));
-    e->ev_valid[0] = 1;
-    e->launches += 1;
+    } else {
+      uint64_t fg = (uint64_t)e->sm_count * FAST_MIN_BLOCKS;  // resident CTAs only: each warp strides over subjects
+      if (fg > groups) fg = groups;
+      if (tm) CK(cudaEventRecord(e->ev[0], st));
+      k_impute_fast<false><<<(unsigned)fg, FAST_WARPS * 32, 0, st>>>(tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt,
+                                                                    nullptr, nullptr);
+      CK(cudaGetLastError());
+      if (tm) CK(cudaEventRecord(e->ev[1], st));
+      e->ev_valid[0] = tm;
+      e->launches += 1;
     }
     wl = (const uint32_t*)e->worklist.p;
     wl_n = cnt;
@@ -2209,15 +2167,14 @@ static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBat
   if (warp_kernels && e->typed_ctas > 0) {
     // warp-per-subject kernel for fully typed unambiguous subjects, any P <= 32 / L / key width
     CK(e->worklist.reserve((size_t)batch->n_subjects * 4 + 16));
-    unsigned int* cnt = (unsigned int*)(e->d_counters + 3);
     uint64_t tg = ((uint64_t)batch->n_subjects + TY_WARPS - 1) / TY_WARPS;
     if (tg > (uint64_t)e->typed_ctas) tg = (uint64_t)e->typed_ctas;
-    CK(cudaEventRecord(e->ev[4], st));
+    if (tm) CK(cudaEventRecord(e->ev[4], st));
     k_impute_typed<<<(unsigned)tg, TY_WARPS * 32, (size_t)e->typed_per_warp * TY_WARPS, st>>>(
         tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt, e->typed_per_warp);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(e->ev[5], st));
-    e->ev_valid[2] = 1;
+    if (tm) CK(cudaEventRecord(e->ev[5], st));
+    e->ev_valid[2] = tm;
     e->launches += 1;
     wl = (const uint32_t*)e->worklist.p;
     wl_n = cnt;
@@ -2225,81 +2182,112 @@ static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBat
   {
     uint64_t cg = (stride + 255) / 256;
     if (cg > (uint64_t)e->sm_count * 4) cg = (uint64_t)e->sm_count * 4;
+    if (wl) cg = cg < 64 ? cg : 64;   // a hand-over list is short (or empty)
     k_classify<<<(unsigned)cg, 256, 0, st>>>(*batch, tv.L, wl, wl_n, (uint32_t*)e->buckets.p, bucket_n, stride);
     CK(cudaGetLastError());
     e->launches += 1;
   }
   int grid = e->n_ctas;
   if ((int64_t)grid > batch->n_subjects) grid = (int)batch->n_subjects;
-  CK(cudaEventRecord(e->ev[2], st));
-  k_impute<<<grid, e->threads, 0, st>>>(tv, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones, e->d_counters,
+  if (tm) CK(cudaEventRecord(e->ev[2], st));
+  k_impute<<<grid, e->threads, 0, st>>>(tv, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones, e->d_counters + CNT_WORK,
                                        (const uint32_t*)e->buckets.p, bucket_n, stride);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(e->ev[3], st));
-  e->ev_valid[1] = 1;
+  if (tm) CK(cudaEventRecord(e->ev[3], st));
+  e->ev_valid[1] = tm;
   e->launches += 1;
   return GRIMB_OK;
 }
 
-extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch, GrimbResults* res,
-                                   void* cuda_stream) {
+static int check_results(const GrimbResults* r) {
+  if (!r->compact || !r->totals) return fail(GRIMB_E_ARG, "GrimbResults.compact / totals missing");
+  if (r->word_capacity < 0 || r->general_capacity < 0 || r->hap_capacity < 0 || r->pop_capacity < 0)
+    return fail(GRIMB_E_ARG, "negative result capacity");
+  return GRIMB_OK;
+}
+
+static int totals_from(const unsigned long long* c, double handed, const GrimbResults* r) {
+  int64_t* t = r->totals;
+  t[0] = (int64_t)c[CNT_WORDS];
+  t[1] = (int64_t)c[CNT_GENERAL];
+  t[2] = (int64_t)c[CNT_HAP];
+  t[3] = (int64_t)c[CNT_POP];
+  t[4] = (int64_t)c[CNT_EVALS];
+  t[5] = (int64_t)handed;
+  if (t[0] > r->word_capacity || t[1] > r->general_capacity || t[2] > r->hap_capacity || t[3] > r->pop_capacity)
+    return fail(GRIMB_E_CAPACITY, "result buffers too small (see GrimbResults.totals)");
+  return GRIMB_OK;
+}
+
+extern "C" int grimb_impute_device_async(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch,
+                                         const GrimbResults* res, void* cuda_stream) {
   if (!e || !cfg || !batch || !res) return fail(GRIMB_E_ARG, "null argument");
   int rc = check_cfg(cfg, e->tables);
+  if (rc) return rc;
+  rc = check_results(res);
   if (rc) return rc;
   CK(cudaSetDevice(e->device));
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
   rc = upload_cfg(e, cfg, st);
   if (rc) return rc;
-  CK(cudaMemsetAsync(e->d_counters, 0, 64, st));
-  OutArrays O;
-  O.r = *res;
-  O.hap_counter = e->d_counters + 1;
-  O.pop_counter = e->d_counters + 2;
-  rc = launch_kernels(e, cfg, batch, O, st);
+  CK(cudaMemsetAsync(e->d_counters, 0, CNT_N * sizeof(unsigned long long), st));
+  rc = launch_kernels(e, cfg, batch, out_arrays(e, *res), st, e->timing != 0);
   if (rc) return rc;
-  unsigned long long cnt[4];
-  CK(cudaMemcpyAsync(e->h_tail, e->d_counters, 32, cudaMemcpyDeviceToHost, st));   // pinned: no staging copy
-  CK(cudaStreamSynchronize(st));
-  for (int k = 0; k < 4; ++k) cnt[k] = e->h_tail[k];
-  e->last_worklist = (double)(unsigned int)(cnt[3] & 0xFFFFFFFFull);
-  *res->hap_rows_needed = (int64_t)cnt[1];
-  *res->pop_rows_needed = (int64_t)cnt[2];
-  if ((int64_t)cnt[1] > res->hap_capacity || (int64_t)cnt[2] > res->pop_capacity)
-    return fail(GRIMB_E_CAPACITY, "result row buffers too small");
+  CK(cudaMemcpyAsync(e->h_tail, e->d_counters, CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  e->pending_stream = st;
+  e->pending = 1;
   return GRIMB_OK;
 }
 
+extern "C" int grimb_impute_finish(GrimbEngine* e, const GrimbResults* res) {
+  if (!e || !res || !res->totals) return fail(GRIMB_E_ARG, "null argument");
+  if (!e->pending) return fail(GRIMB_E_ARG, "no call in flight");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->pending_stream));
+  e->pending = 0;
+  e->last_worklist = (double)(unsigned int)(e->h_tail[CNT_WORKLIST] & 0xFFFFFFFFull);
+  return totals_from(e->h_tail, e->last_worklist, res);
+}
+
+extern "C" int grimb_impute_device(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch, GrimbResults* res,
+                                   void* cuda_stream) {
+  int rc = grimb_impute_device_async(e, cfg, batch, res, cuda_stream);
+  if (rc) return rc;
+  return grimb_impute_finish(e, res);
+}
+
 // Host-pointer form.  Large batches are pipelined in chunks over three streams: while chunk c is
-// imputed, chunk c+1 is copied in and the rows of chunk c-1 are copied out (PCIe is full duplex),
-// so the call costs about max(H2D, kernels, D2H) instead of their sum.  Rows of one chunk occupy
-// one contiguous range of the row arrays (launches of one stream serialise and the row counters
-// keep running), so each chunk's D2H is three plain copies once its counters are known.
+// imputed, chunk c+1 is copied in and the results of chunk c-1 are copied out (PCIe is full duplex),
+// so the call costs about max(H2D, kernels, D2H) instead of their sum.  What one chunk appends to each
+// result array is one contiguous range (launches of one stream serialise and the counters keep
+// running), so each chunk's D2H is a handful of plain copies once its counters are known.
 extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* b, GrimbResults* r) {
   if (!e || !cfg || !b || !r) return fail(GRIMB_E_ARG, "null argument");
   int rc = check_cfg(cfg, e->tables);
+  if (rc) return rc;
+  rc = check_results(r);
   if (rc) return rc;
   CK(cudaSetDevice(e->device));
   const int L = e->tables->h.L, P = e->tables->h.P;
   const int64_t S = b->n_subjects;
   cudaStream_t st = e->stream;
-  const size_t in_bytes[6] = {(size_t)S * 2, (size_t)S * L * 2 * 2, (size_t)(S + 1) * 4, (size_t)b->n_alleles_total * 2,
-                              (size_t)S * 4, (size_t)b->n_priors * P * P * 8};
-  for (int i = 0; i < 6; ++i) CK(e->in[i].reserve(in_bytes[i] + 16));
+  const size_t in_bytes[6] = {(size_t)S * 2, b->counts ? (size_t)S * L * 2 * 2 : 0, (size_t)(S + 1) * 4,
+                              (size_t)b->n_alleles_total * 2, b->prior_index ? (size_t)S * 4 : 0,
+                              (size_t)b->n_priors * P * P * 8};
+  for (int i = 0; i < 6; ++i) CK(e->in[i].reserve(in_bytes[i] + 64));
   if (b->phase_mask) CK(e->in_mask.reserve((size_t)S * 2 + 16));
-  const size_t ob[3] = {(size_t)S * sizeof(GrimbSubjectResult), (size_t)r->hap_capacity * sizeof(GrimbHapRow),
-                        (size_t)r->pop_capacity * sizeof(GrimbPopRow)};
-  for (int i = 0; i < 3; ++i) CK(e->outb[i].reserve(ob[i] + 16));
+  const size_t ob[5] = {(size_t)S * sizeof(GrimbCompact), (size_t)r->word_capacity * 8,
+                        (size_t)r->general_capacity * sizeof(GrimbSubjectResult),
+                        (size_t)r->hap_capacity * sizeof(GrimbHapRow), (size_t)r->pop_capacity * sizeof(GrimbPopRow)};
+  for (int i = 0; i < 5; ++i) CK(e->outb[i].reserve(ob[i] + 16));
   GrimbResults dr = *r;
-  dr.subjects = (GrimbSubjectResult*)e->outb[0].p;
-  dr.hap_rows = (GrimbHapRow*)e->outb[1].p;
-  dr.pop_rows = (GrimbPopRow*)e->outb[2].p;
-  OutArrays O;
-  O.hap_counter = e->d_counters + 1;
-  O.pop_counter = e->d_counters + 2;
-  // chunking.  Measured on 2^20 config-2 subjects (52 MB in, 135 MB out; the link alone moves those
-  // bytes in 2.58 ms with both directions busy, tools/pcie_peak.py): 3.00 ms at 131,072 subjects per
-  // chunk, 3.08 at 262,144, 3.70 at 65,536, 5.07 at 32,768 (the ~20 API calls per chunk become the
-  // critical path).  Smaller leading chunks and a second copy-out stream were tried and bought nothing.
+  dr.compact = (GrimbCompact*)e->outb[0].p;
+  dr.words = (uint64_t*)e->outb[1].p;
+  dr.general = (GrimbSubjectResult*)e->outb[2].p;
+  dr.hap_rows = (GrimbHapRow*)e->outb[3].p;
+  dr.pop_rows = (GrimbPopRow*)e->outb[4].p;
+  // chunking: the ~15 API calls per chunk become the critical path when chunks are small, the pipeline
+  // fill / drain (first copy-in, last copy-out not overlapped) when they are large
   int64_t chunk = e->host_chunk;
   if (S > chunk * GRIMB_MAX_CHUNKS) chunk = (S + GRIMB_MAX_CHUNKS - 1) / GRIMB_MAX_CHUNKS;
   int64_t bound[GRIMB_MAX_CHUNKS + 1];
@@ -2311,29 +2299,33 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
   }
   rc = upload_cfg(e, cfg, st);
   if (rc) return rc;
-  CK(cudaMemsetAsync(e->d_counters, 0, 64, st));
+  CK(cudaMemsetAsync(e->d_counters, 0, CNT_N * sizeof(unsigned long long), st));
   if (in_bytes[5]) CK(cudaMemcpyAsync(e->in[5].p, b->priors, in_bytes[5], cudaMemcpyHostToDevice, st));
-  unsigned long long hap_prev = 0, pop_prev = 0, hap_end = 0, pop_end = 0;
+  // what has been copied out so far / the counters after the chunk being copied out
+  unsigned long long prev[4] = {0, 0, 0, 0}, end[CNT_N];
+  memset(end, 0, sizeof(end));
+  const unsigned long long cap[4] = {(unsigned long long)r->word_capacity, (unsigned long long)r->general_capacity,
+                                     (unsigned long long)r->hap_capacity, (unsigned long long)r->pop_capacity};
+  static const int which[4] = {CNT_WORDS, CNT_GENERAL, CNT_HAP, CNT_POP};
+  const size_t esz[4] = {8, sizeof(GrimbSubjectResult), sizeof(GrimbHapRow), sizeof(GrimbPopRow)};
+  char* const hdst[4] = {(char*)r->words, (char*)r->general, (char*)r->hap_rows, (char*)r->pop_rows};
+  const char* const dsrc[4] = {(const char*)dr.words, (const char*)dr.general, (const char*)dr.hap_rows, (const char*)dr.pop_rows};
   double wl = 0;
-  // copy-out of one chunk, once its counters have arrived (rows of a chunk are one contiguous range)
   auto copy_out = [&](int c) -> int {
     const int64_t s0 = bound[c], n = bound[c + 1] - s0;
     CK(cudaEventSynchronize(e->ev_k[c]));
-    hap_end = e->h_cnt[4 * c + 1];
-    pop_end = e->h_cnt[4 * c + 2];
-    wl += (double)(unsigned int)(e->h_cnt[4 * c + 3] & 0xFFFFFFFFull);
+    memcpy(end, e->h_cnt + (size_t)CNT_N * c, sizeof(end));
+    wl += (double)(unsigned int)(end[CNT_WORKLIST] & 0xFFFFFFFFull);
     cudaStream_t so = nch > 1 ? e->s_out : st;
-    CK(cudaMemcpyAsync(r->subjects + s0, dr.subjects + s0, (size_t)n * sizeof(GrimbSubjectResult), cudaMemcpyDeviceToHost, so));
-    const unsigned long long hcap = (unsigned long long)r->hap_capacity, pcap = (unsigned long long)r->pop_capacity;
-    const unsigned long long h1 = hap_end < hcap ? hap_end : hcap, p1 = pop_end < pcap ? pop_end : pcap;
-    if (h1 > hap_prev)
-      CK(cudaMemcpyAsync(r->hap_rows + hap_prev, dr.hap_rows + hap_prev, (size_t)(h1 - hap_prev) * sizeof(GrimbHapRow),
-                         cudaMemcpyDeviceToHost, so));
-    if (p1 > pop_prev)
-      CK(cudaMemcpyAsync(r->pop_rows + pop_prev, dr.pop_rows + pop_prev, (size_t)(p1 - pop_prev) * sizeof(GrimbPopRow),
-                         cudaMemcpyDeviceToHost, so));
-    hap_prev = h1 > hap_prev ? h1 : hap_prev;
-    pop_prev = p1 > pop_prev ? p1 : pop_prev;
+    CK(cudaMemcpyAsync(r->compact + s0, dr.compact + s0, (size_t)n * sizeof(GrimbCompact), cudaMemcpyDeviceToHost, so));
+    for (int k = 0; k < 4; ++k) {
+      const unsigned long long hi = end[which[k]] < cap[k] ? end[which[k]] : cap[k];
+      if (hi > prev[k]) {
+        CK(cudaMemcpyAsync(hdst[k] + prev[k] * esz[k], dsrc[k] + prev[k] * esz[k], (size_t)(hi - prev[k]) * esz[k],
+                           cudaMemcpyDeviceToHost, so));
+        prev[k] = hi;
+      }
+    }
     return GRIMB_OK;
   };
   for (int c = 0; c < nch; ++c) {
@@ -2341,11 +2333,13 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
     const uint32_t a0 = b->allele_off[s0], a1 = b->allele_off[s1];
     cudaStream_t si = nch > 1 ? e->s_in : st;
     CK(cudaMemcpyAsync((uint16_t*)e->in[0].p + s0, b->typed_mask + s0, (size_t)n * 2, cudaMemcpyHostToDevice, si));
-    CK(cudaMemcpyAsync((uint16_t*)e->in[1].p + s0 * L * 2, b->counts + s0 * L * 2, (size_t)n * L * 4, cudaMemcpyHostToDevice, si));
+    if (b->counts)
+      CK(cudaMemcpyAsync((uint16_t*)e->in[1].p + s0 * L * 2, b->counts + s0 * L * 2, (size_t)n * L * 4, cudaMemcpyHostToDevice, si));
     CK(cudaMemcpyAsync((uint32_t*)e->in[2].p + s0, b->allele_off + s0, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, si));
     if (a1 > a0)
       CK(cudaMemcpyAsync((uint16_t*)e->in[3].p + a0, b->alleles + a0, (size_t)(a1 - a0) * 2, cudaMemcpyHostToDevice, si));
-    CK(cudaMemcpyAsync((uint32_t*)e->in[4].p + s0, b->prior_index + s0, (size_t)n * 4, cudaMemcpyHostToDevice, si));
+    if (b->prior_index)
+      CK(cudaMemcpyAsync((uint32_t*)e->in[4].p + s0, b->prior_index + s0, (size_t)n * 4, cudaMemcpyHostToDevice, si));
     if (b->phase_mask)
       CK(cudaMemcpyAsync((uint16_t*)e->in_mask.p + s0, b->phase_mask + s0, (size_t)n * 2, cudaMemcpyHostToDevice, si));
     if (nch > 1) {
@@ -2355,24 +2349,21 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
     GrimbBatch db = *b;
     db.n_subjects = n;
     db.typed_mask = (const uint16_t*)e->in[0].p + s0;
-    db.counts = (const uint16_t*)e->in[1].p + s0 * L * 2;
+    db.counts = b->counts ? (const uint16_t*)e->in[1].p + s0 * L * 2 : nullptr;
     db.allele_off = (const uint32_t*)e->in[2].p + s0;   // offsets stay absolute into `alleles`
     db.alleles = (const uint16_t*)e->in[3].p;
-    db.prior_index = (const uint32_t*)e->in[4].p + s0;
+    db.prior_index = b->prior_index ? (const uint32_t*)e->in[4].p + s0 : nullptr;
     db.priors = (const double*)e->in[5].p;
     db.phase_mask = b->phase_mask ? (const uint16_t*)e->in_mask.p + s0 : nullptr;
-    O.r = dr;
-    O.r.subjects = dr.subjects + s0;
-    if (c > 0) {   // per-chunk counters: work tickets, worklist size, cost buckets (row counters keep running)
-      CK(cudaMemsetAsync(e->d_counters, 0, 8, st));
-      CK(cudaMemsetAsync(e->d_counters + 3, 0, 40, st));
-    }
-    rc = launch_kernels(e, cfg, &db, O, st);
+    GrimbResults cr = dr;
+    cr.compact = dr.compact + s0;
+    if (c > 0) CK(cudaMemsetAsync(e->d_counters, 0, CNT_CHUNK_END * sizeof(unsigned long long), st));   // per-chunk counters
+    rc = launch_kernels(e, cfg, &db, out_arrays(e, cr), st, e->timing_host != 0);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(e->h_cnt + 4 * c, e->d_counters, 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(e->h_cnt + (size_t)CNT_N * c, e->d_counters, CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(e->ev_k[c], st));
     // with chunk c in the queue, hand chunk c-1 to the copy-out stream: enqueueing every chunk first
-    // (about 20 API calls each) would hold the first copy-out back by the whole enqueue time
+    // would hold the first copy-out back by the whole enqueue time
     if (c > 0) {
       rc = copy_out(c - 1);
       if (rc) return rc;
@@ -2385,9 +2376,5 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
   if (nch > 1) CK(cudaStreamSynchronize(e->s_out));
   CK(cudaStreamSynchronize(st));
   e->last_worklist = wl;
-  *r->hap_rows_needed = (int64_t)hap_end;
-  *r->pop_rows_needed = (int64_t)pop_end;
-  if ((int64_t)hap_end > r->hap_capacity || (int64_t)pop_end > r->pop_capacity)
-    return fail(GRIMB_E_CAPACITY, "result row buffers too small");
-  return GRIMB_OK;
+  return totals_from(end, wl, r);
 }

@@ -1024,14 +1024,14 @@ GD void run_subject(Subject& S, const GrimbBatch& B, const OutArrays& O, uint64_
     if (g.tid == 0) {
       sh->fault = 0;
       const uint16_t* cur = B.alleles + B.allele_off[s];
-      const uint16_t* cn = B.counts + s * (uint64_t)L * 2;
       int t = 0;
       for (int l = 0; l < L; ++l)
         if (S.typed >> l & 1u) {
           for (int x = 0; x < 2; ++x) {
+            const uint32_t c = batch_count(B, s, L, l, x);
             sh->lptr[VAR_ORIG][t][x] = cur;
-            sh->lcnt[VAR_ORIG][t][x] = cn[l * 2 + x];
-            cur += cn[l * 2 + x];
+            sh->lcnt[VAR_ORIG][t][x] = (uint16_t)c;
+            cur += c;
           }
           ++t;
         }
@@ -1086,7 +1086,7 @@ GD void run_subject(Subject& S, const GrimbBatch& B, const OutArrays& O, uint64_
     S.st_pop[1] = S.alloc<GrimbPopRow>(cfg->n_pop_results > 0 ? cfg->n_pop_results : 1);
     S.st_pair = S.alloc<GrimbPopRow>(cfg->hap_pop_pair ? (cfg->n_results > 0 ? cfg->n_results : 1) : 1);
     S.st_cnt = S.alloc<uint32_t>(4);
-    S.Msubj = B.priors + (uint64_t)B.prior_index[s] * P * P;
+    S.Msubj = B.priors + (uint64_t)batch_prior(B, s) * P * P;
     S.M = S.Msubj;
     if (!S.ws_fail) {
       if (g.tid == 0) {
@@ -1209,7 +1209,7 @@ GD void run_subject(Subject& S, const GrimbBatch& B, const OutArrays& O, uint64_
     o.pair_evals = evals > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)evals;
     o.hap_off = hb;
     o.pop_off = pb;
-    R.subjects[s] = o;
+    publish_general(O, s, o);
     sh->cnt[6] = (uint32_t)(hb & 0xFFFFFFFFu);
     sh->cnt[7] = (uint32_t)(hb >> 32);
     sh->cnt[0] = (uint32_t)(pb & 0xFFFFFFFFu);

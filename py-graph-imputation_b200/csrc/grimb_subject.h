@@ -83,11 +83,41 @@ struct Shared {
   double dmax;
 };
 
-struct OutArrays {  // device pointers of GrimbResults + global row counters
+struct OutArrays {  // device pointers of GrimbResults + global counters
   GrimbResults r;
   unsigned long long* hap_counter;
   unsigned long long* pop_counter;
+  unsigned long long* word_counter;      // 8-byte words of SIMPLE / TYPED subjects
+  unsigned long long* general_counter;   // GrimbSubjectResult records appended to r.general
+  unsigned long long* evals_counter;     // pair evaluations of the whole batch
 };
+
+// batch accessors: `counts` and `prior_index` may be NULL (ABI v4: all ones / all zero)
+GD uint32_t batch_count(const GrimbBatch& B, uint64_t s, int L, int l, int x) {
+  return B.counts ? (uint32_t)B.counts[s * (uint64_t)L * 2 + (uint64_t)l * 2 + x] : 1u;
+}
+GD uint32_t batch_prior(const GrimbBatch& B, uint64_t s) { return B.prior_index ? B.prior_index[s] : 0u; }
+
+GD GrimbCompact make_compact(uint32_t status, uint32_t kind_flags, uint32_t phases, uint32_t off, double total) {
+  GrimbCompact c;
+  c.status = (uint8_t)status;
+  c.kind_flags = (uint8_t)kind_flags;
+  c.phases = (uint16_t)phases;
+  c.off = off;
+  c.total = total;
+  return c;
+}
+
+// Publishes the 48-byte record of a GENERAL subject: appended to r.general, the subject's compact
+// record points at it.  One thread calls this.
+GD void publish_general(const OutArrays& O, uint64_t s, const GrimbSubjectResult& o) {
+  GrimbResults& R = const_cast<GrimbResults&>(O.r);
+  const unsigned long long gi = atom_add64(O.general_counter, 1ull);
+  if ((int64_t)gi < R.general_capacity) R.general[gi] = o;
+  const bool has = o.tot_umug != 0 || o.tot_pmug != 0;
+  R.compact[s] = make_compact(o.status, GRIMB_KIND_GENERAL | (has ? GRIMB_KIND_HAS_RESULTS : 0), 0, (uint32_t)gi, 0.0);
+  if (o.pair_evals) atom_add64(O.evals_counter, (unsigned long long)o.pair_evals);
+}
 
 GD GrimbHapRow make_hap_row(hkey a, hkey b, double prob) {
   GrimbHapRow o;

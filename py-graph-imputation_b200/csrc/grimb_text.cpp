@@ -20,14 +20,14 @@
 
 extern "C" void* grimb_pinned_alloc(size_t bytes);  // grimb200.cu: cudaMallocHost or nullptr
 extern "C" void grimb_pinned_free(void* p);
+extern "C" void grimb_set_error(const char* msg);   // grimb200.cu: the message grimb_last_error() returns
 
 namespace {
 
 using sv = std::string_view;
 
-thread_local std::string t_err;
 int tfail(int code, const std::string& m) {
-  t_err = m;
+  grimb_set_error(m.c_str());
   return code;
 }
 
@@ -199,8 +199,8 @@ struct GrimbText {
     }
     ~HostBuf() { release(); }
   };
-  HostBuf hb_subj, hb_hap, hb_pop;
-  double hap_per_subject = 3.0, pop_per_subject = 2.5;
+  HostBuf hb_compact, hb_words, hb_general, hb_hap, hb_pop;
+  double per_subject[4] = {0.5, 0.05, 0.3, 0.3};   // words, general records, hap rows, pop rows
 
   template <class F>
   void parallel(size_t n, F f) const {
@@ -487,6 +487,112 @@ struct GrimbText {
 
   sv pop_name(uint16_t p) const { return p == 0xFFFF ? sv("all_pops") : sv(pops[p]); }
 
+  static void put_row_tail(double prob, uint32_t k, std::string& s) {
+    s += ',';
+    py_float(prob, s);
+    s += ',';
+    put_uint(k, s);
+    s += '\n';
+  }
+
+  void put_pop_row(sv sid, sv x, sv y, double prob, uint32_t k, bool sorted, std::string& s) const {
+    if (sorted && y < x) std::swap(x, y);
+    s += sid;
+    s += ',';
+    s += x;
+    s += ',';
+    s += y;
+    put_row_tail(prob, k, s);
+  }
+
+  // Rows of a subject the warp-per-subject kernels finished (GRIMB_KIND_SIMPLE / GRIMB_KIND_TYPED, ABI v4):
+  // every locus typed with one allele per side, so the single UMUG genotype is the subject's own allele
+  // pairs and a PMUG row's haplotypes follow from its phase id (bit m: locus m takes its side-2 allele in
+  // the first haplotype).  Same row order and text as the general layout below.
+  void format_compact(const Line& ln, const GrimbCompact& c, const uint64_t* words, const GrimbConfig* cfg,
+                      std::string* o) const {
+    const uint16_t* ids = t_ids[ln.thread].data() + ln.ids_off;   // [L][2]
+    const uint32_t kind = c.kind_flags & 3u, n_pmug = c.kind_flags >> 4;
+    const bool has = (c.kind_flags & GRIMB_KIND_HAS_RESULTS) != 0;
+    const uint64_t* w = words + c.off;
+    uint32_t n_pops = 0;
+    uint32_t phase[4] = {0, 0, 0, 0};
+    const uint64_t* pmug_prob = nullptr;   // nullptr: the single PMUG row carries `total`
+    const uint64_t* pop_prob = nullptr;
+    const uint64_t* pop_code = nullptr;
+    if (kind == GRIMB_KIND_SIMPLE) {
+      for (uint32_t k = 0; k < n_pmug; ++k) phase[k] = (c.phases >> (4 * k)) & 15u;
+      if (c.kind_flags & GRIMB_KIND_WORDS) pmug_prob = w;
+      n_pops = (has && cfg->n_pop_results >= 1) ? 1u : 0u;
+    } else {
+      const uint64_t hdr = w[0];
+      n_pops = (uint32_t)(hdr & 0xFFFFu);
+      for (uint32_t k = 0; k < n_pmug; ++k) phase[k] = (uint32_t)(hdr >> (16 + 12 * k)) & 0xFFFu;
+      pmug_prob = w + 1;
+      pop_prob = w + 1 + n_pmug;
+      pop_code = pop_prob + n_pops;
+    }
+    auto dbl = [](uint64_t u) {
+      double d;
+      memcpy(&d, &u, 8);
+      return d;
+    };
+    auto pop_pair = [&](uint32_t k, sv& x, sv& y, double& p) {
+      if (!pop_code) {
+        x = y = sv(pops[0]);
+        p = c.total;
+        return;
+      }
+      const uint32_t code = (uint32_t)(pop_code[k >> 2] >> (16 * (k & 3u))) & 0xFFFFu;
+      x = sv(pops[code >> 8]);
+      y = sv(pops[code & 0xFFu]);
+      p = dbl(pop_prob[k]);
+    };
+    if (cfg->output_pmug) {
+      for (uint32_t k = 0; k < n_pmug; ++k) {
+        std::string& s = o[GRIMB_OUT_PMUG];
+        s += ln.sid;
+        s += ',';
+        for (int side = 0; side < 2; ++side) {
+          if (side) s += '+';
+          for (int l = 0; l < L; ++l) {
+            if (l) s += '~';
+            s += allele_name(l, ids[2 * l + (int)(((phase[k] >> l) & 1u) ^ (uint32_t)side)], ln);
+          }
+        }
+        put_row_tail(pmug_prob ? dbl(pmug_prob[k]) : c.total, k, s);
+      }
+      for (uint32_t k = 0; k < n_pops; ++k) {
+        sv x, y;
+        double p;
+        pop_pair(k, x, y, p);
+        put_pop_row(ln.sid, x, y, p, k, false, o[GRIMB_OUT_PMUG_POPS]);
+      }
+    }
+    if (cfg->output_umug && has) {
+      if (cfg->n_results >= 1) {
+        std::string& s = o[GRIMB_OUT_UMUG];
+        s += ln.sid;
+        s += ',';
+        for (int l = 0; l < L; ++l) {
+          sv x = allele_name(l, ids[2 * l], ln), y = allele_name(l, ids[2 * l + 1], ln);
+          if (y < x) std::swap(x, y);
+          if (l) s += '^';
+          s += x;
+          s += '+';
+          s += y;
+        }
+        put_row_tail(c.total, 0, s);
+      }
+      for (uint32_t k = 0; k < n_pops; ++k) {
+        sv x, y;
+        double p;
+        pop_pair(k, x, y, p);
+        put_pop_row(ln.sid, x, y, p, k, true, o[GRIMB_OUT_UMUG_POPS]);
+      }
+    }
+  }
+
   void format_subject(const Line& ln, const GrimbSubjectResult& r, const GrimbHapRow* hr, const GrimbPopRow* pr,
                       const GrimbConfig* cfg, std::string* o) const {
     if (cfg->output_pmug) {
@@ -498,25 +604,11 @@ struct GrimbText {
         put_hap(row.a, ln, s);
         s += '+';
         put_hap(row.b, ln, s);
-        s += ',';
-        py_float(row.prob, s);
-        s += ',';
-        put_uint(k, s);
-        s += '\n';
+        put_row_tail(row.prob, k, s);
       }
       for (uint32_t k = 0; k < r.n_pmug_pops; ++k) {
         const GrimbPopRow& row = pr[r.pop_off + r.n_umug_pops + k];
-        std::string& s = o[GRIMB_OUT_PMUG_POPS];
-        s += ln.sid;
-        s += ',';
-        s += pop_name(row.pop_a);
-        s += ',';
-        s += pop_name(row.pop_b);
-        s += ',';
-        py_float(row.prob, s);
-        s += ',';
-        put_uint(k, s);
-        s += '\n';
+        put_pop_row(ln.sid, pop_name(row.pop_a), pop_name(row.pop_b), row.prob, k, false, o[GRIMB_OUT_PMUG_POPS]);
       }
     }
     if (cfg->output_umug) {
@@ -537,11 +629,7 @@ struct GrimbText {
           s += '+';
           s += y;
         }
-        s += ',';
-        py_float(row.prob, s);
-        s += ',';
-        put_uint(k, s);
-        s += '\n';
+        put_row_tail(row.prob, k, s);
       }
       const bool planc_empty = r.plan_umug == GRIMB_PLAN_C && r.tot_umug == 0;
       for (uint32_t k = 0; k < r.n_umug_pops; ++k) {
@@ -564,8 +652,6 @@ struct GrimbText {
     }
   }
 };
-
-extern "C" const char* grimb_text_last_error_internal(void) { return t_err.c_str(); }
 
 extern "C" int grimb_text_create(const GrimbTextDesc* d, GrimbText** out) {
   if (!d || !out || d->n_loci < 1 || d->n_loci > GRIMB_MAX_LOCI || d->n_pops < 1) return tfail(GRIMB_E_ARG, "bad text descriptor");
@@ -669,13 +755,21 @@ extern "C" int grimb_text_tokenise(GrimbText* t, const GrimbConfig* cfg, const c
       std::copy(idv.begin() + ln.ids_off, idv.begin() + ln.ids_off + ln.ids_cnt, t->b_alleles.begin() + t->b_off[i]);
     }
   });
+  // ABI v4: the counts travel only when some subject lists several alleles on a side (every typed side
+  // lists at least one), the prior indices only when more than one prior matrix is in use
+  bool all_single = true, one_prior = true;
+  for (size_t i = 0; i < S && (all_single || one_prior); ++i) {
+    const Line& ln = t->lines[i];
+    if (t->b_prior[i] != 0) one_prior = false;
+    if (ln.hclass == H_OK && ln.mask && ln.ids_cnt != 2u * (uint32_t)__builtin_popcount(ln.mask)) all_single = false;
+  }
   b->n_subjects = (int64_t)S;
   b->typed_mask = t->b_typed.data();
-  b->counts = t->b_counts.data();
+  b->counts = all_single ? nullptr : t->b_counts.data();
   b->allele_off = t->b_off.data();
   b->alleles = t->b_alleles.data();
   b->n_alleles_total = (int64_t)total;
-  b->prior_index = t->b_prior.data();
+  b->prior_index = one_prior ? nullptr : t->b_prior.data();
   b->priors = t->priors.data();
   b->n_priors = (int32_t)(t->priors.size() / ((size_t)t->P * t->P));
   b->phase_mask = nullptr;   // default phase enumeration; masks are served by the numpy host front end
@@ -683,15 +777,15 @@ extern "C" int grimb_text_tokenise(GrimbText* t, const GrimbConfig* cfg, const c
 }
 
 extern "C" int grimb_text_format(GrimbText* t, const GrimbConfig* cfg, const GrimbResults* res, GrimbTextOut* out) {
-  if (!t || !cfg || !res || !out) return tfail(GRIMB_E_ARG, "null argument");
+  if (!t || !cfg || !res || !out || !res->compact) return tfail(GRIMB_E_ARG, "null argument");
   const size_t S = t->lines.size();
   const int nt = t->n_threads;
   // per-thread output pieces live in the GrimbText so their capacity is reused from call to call
   std::vector<std::string>& parts = t->fmt_parts;
   parts.resize((size_t)nt * 6);
   for (auto& ps : parts) ps.clear();
-  std::vector<int64_t> evals((size_t)nt, 0);
   std::vector<int64_t> plans((size_t)nt * 4, 0);
+  static const GrimbSubjectResult kNoRecord = {};   // a skipped subject: nothing was computed
   t->parallel(S, [&](int th, size_t lo, size_t hi) {
     std::string* o = &parts[(size_t)th * 6];
     for (size_t i = lo; i < hi; ++i) {
@@ -709,14 +803,13 @@ extern "C" int grimb_text_format(GrimbText* t, const GrimbConfig* cfg, const Gri
         o[GRIMB_OUT_PROBLEM] += '\n';
         continue;
       }
-      const GrimbSubjectResult& r = res->subjects[i];
-      evals[th] += r.pair_evals;
-      if (r.status == GRIMB_ST_FAULT) {
+      const GrimbCompact& c = res->compact[i];
+      if (c.status == GRIMB_ST_FAULT) {
         o[GRIMB_OUT_PROBLEM] += ln.raw;
         o[GRIMB_OUT_PROBLEM] += '\n';
         continue;
       }
-      if (r.status == GRIMB_ST_NO_PHASES) {
+      if (c.status == GRIMB_ST_NO_PHASES) {
         // nothing opens: the reference returns its defaults and the PMUG writer then raises
         if (cfg->output_pmug) {
           o[GRIMB_OUT_PROBLEM] += ln.raw;
@@ -724,6 +817,19 @@ extern "C" int grimb_text_format(GrimbText* t, const GrimbConfig* cfg, const Gri
         }
         continue;
       }
+      const uint32_t kind = c.kind_flags & 3u;
+      if (kind != GRIMB_KIND_GENERAL) {
+        plans[(size_t)th * 4 + GRIMB_PLAN_A] += 1;
+        if (cfg->output_pmug && !(c.kind_flags & GRIMB_KIND_HAS_RESULTS)) {
+          put_uint(idx, o[GRIMB_OUT_MISS]);
+          o[GRIMB_OUT_MISS] += ',';
+          o[GRIMB_OUT_MISS] += ln.sid;
+          o[GRIMB_OUT_MISS] += '\n';
+        }
+        t->format_compact(ln, c, res->words, cfg, o);
+        continue;
+      }
+      const GrimbSubjectResult& r = c.off == 0xFFFFFFFFu ? kNoRecord : res->general[c.off];
       plans[(size_t)th * 4 + ((cfg->output_umug ? r.plan_umug : r.plan_pmug) & 3)] += 1;
       const bool pm_empty = cfg->output_pmug ? r.tot_pmug == 0 : false;
       if (pm_empty && r.tot_umug == 0) {
@@ -735,7 +841,7 @@ extern "C" int grimb_text_format(GrimbText* t, const GrimbConfig* cfg, const Gri
       t->format_subject(ln, r, res->hap_rows, res->pop_rows, cfg, o);
     }
   });
-  out->pair_evals = 0;
+  out->pair_evals = res->totals ? res->totals[4] : 0;
   for (int k = 0; k < 4; ++k) out->plan_count[k] = 0;
   // concatenate the pieces of every output in thread order, the copies themselves in parallel
   std::vector<size_t> offs((size_t)nt * 6, 0);
@@ -756,10 +862,8 @@ extern "C" int grimb_text_format(GrimbText* t, const GrimbConfig* cfg, const Gri
         if (!ps.empty()) memcpy(&t->out[k][offs[th * 6 + k]], ps.data(), ps.size());
       }
   });
-  for (int th = 0; th < nt; ++th) {
-    out->pair_evals += evals[th];
+  for (int th = 0; th < nt; ++th)
     for (int k = 0; k < 4; ++k) out->plan_count[k] += plans[(size_t)th * 4 + k];
-  }
   out->n_lines = (int64_t)S;
   return GRIMB_OK;
 }
@@ -775,108 +879,128 @@ extern "C" int grimb_impute_text(GrimbText* t, GrimbEngine* const* engines, int3
   auto t1 = clk::now();
   const size_t S = (size_t)b.n_subjects;
   const int L = t->L;
-  // final per-subject records + rows, re-based as tiers complete
-  std::vector<GrimbSubjectResult> subj;
-  subj.reserve(S);
-  subj.resize(S);
-  std::vector<GrimbHapRow> hap;
-  std::vector<GrimbPopRow> pop;
-  std::vector<uint32_t> todo(S);
-  for (size_t i = 0; i < S; ++i) todo[i] = (uint32_t)i;
-  int64_t retries = 0;
-  for (int tier = 0; tier < n_engines && !todo.empty(); ++tier) {
+  // One ABI call per workspace tier.  Tier 0 takes the whole batch and its results are formatted straight
+  // from the pinned staging buffers; only when some subject overflowed its workspace (rare) are the tiers'
+  // results merged into one set of arrays first.
+  std::vector<GrimbCompact> m_compact;
+  std::vector<uint64_t> m_words;
+  std::vector<GrimbSubjectResult> m_general;
+  std::vector<GrimbHapRow> m_hap;
+  std::vector<GrimbPopRow> m_pop;
+  std::vector<uint32_t> todo;
+  int64_t retries = 0, evals = 0;
+  int64_t tot[6] = {0, 0, 0, 0, 0, 0};
+  GrimbResults fin;
+  memset(&fin, 0, sizeof(fin));
+  for (int tier = 0; tier < n_engines && (tier == 0 || !todo.empty()); ++tier) {
     // gather the sub-batch (tier 0: the whole batch as is)
     GrimbBatch sb = b;
     std::vector<uint16_t> g_typed, g_counts, g_all;
     std::vector<uint32_t> g_off, g_prior;
-    const size_t n = todo.size();
+    const size_t n = tier == 0 ? S : todo.size();
     if (tier > 0) {
       g_typed.resize(n);
       g_counts.resize(n * (size_t)L * 2);
       g_off.resize(n + 1);
       g_prior.resize(n);
-      size_t tot = 0;
+      size_t tot_al = 0;
       for (size_t k = 0; k < n; ++k) {
         const uint32_t s = todo[k];
         g_typed[k] = b.typed_mask[s];
-        g_prior[k] = b.prior_index[s];
-        memcpy(&g_counts[k * (size_t)L * 2], b.counts + (size_t)s * L * 2, (size_t)L * 4);
-        g_off[k] = (uint32_t)tot;
-        tot += b.allele_off[s + 1] - b.allele_off[s];
+        g_prior[k] = b.prior_index ? b.prior_index[s] : 0u;
+        if (b.counts) memcpy(&g_counts[k * (size_t)L * 2], b.counts + (size_t)s * L * 2, (size_t)L * 4);
+        g_off[k] = (uint32_t)tot_al;
+        tot_al += b.allele_off[s + 1] - b.allele_off[s];
       }
-      g_off[n] = (uint32_t)tot;
-      g_all.resize(tot ? tot : 1);
+      g_off[n] = (uint32_t)tot_al;
+      g_all.resize(tot_al ? tot_al : 1);
       for (size_t k = 0; k < n; ++k) {
         const uint32_t s = todo[k];
         std::copy(b.alleles + b.allele_off[s], b.alleles + b.allele_off[s + 1], g_all.begin() + g_off[k]);
       }
       sb.n_subjects = (int64_t)n;
       sb.typed_mask = g_typed.data();
-      sb.counts = g_counts.data();
+      sb.counts = b.counts ? g_counts.data() : nullptr;
       sb.allele_off = g_off.data();
       sb.alleles = g_all.data();
-      sb.n_alleles_total = (int64_t)tot;
+      sb.n_alleles_total = (int64_t)tot_al;
       sb.prior_index = g_prior.data();
     }
-    // pinned, grow-only staging; row capacity follows the rows/subject seen so far (+25 %)
-    GrimbSubjectResult* rs = (GrimbSubjectResult*)t->hb_subj.reserve(n * sizeof(GrimbSubjectResult));
-    int64_t hap_cap = std::max<int64_t>(1024, (int64_t)((double)n * t->hap_per_subject * 1.25) + 64);
-    int64_t pop_cap = std::max<int64_t>(1024, (int64_t)((double)n * t->pop_per_subject * 1.25) + 64);
-    GrimbHapRow* rh = nullptr;
-    GrimbPopRow* rp = nullptr;
-    int64_t need_h = 0, need_p = 0;
+    // pinned, grow-only staging; capacities follow what the previous call needed per subject (+25 %)
+    GrimbCompact* rc_ = (GrimbCompact*)t->hb_compact.reserve((n + 1) * sizeof(GrimbCompact));
+    int64_t cap[4];
+    for (int k = 0; k < 4; ++k) cap[k] = std::max<int64_t>(1024, (int64_t)((double)n * t->per_subject[k] * 1.25) + 64);
+    GrimbResults r;
     for (;;) {
-      rh = (GrimbHapRow*)t->hb_hap.reserve((size_t)hap_cap * sizeof(GrimbHapRow));
-      rp = (GrimbPopRow*)t->hb_pop.reserve((size_t)pop_cap * sizeof(GrimbPopRow));
-      if (!rs || !rh || !rp) return tfail(GRIMB_E_NOMEM, "host staging allocation failed");
-      GrimbResults r;
-      r.subjects = rs;
-      r.hap_rows = rh;
-      r.hap_capacity = hap_cap;
-      r.pop_rows = rp;
-      r.pop_capacity = pop_cap;
-      r.hap_rows_needed = &need_h;
-      r.pop_rows_needed = &need_p;
+      r.compact = rc_;
+      r.words = (uint64_t*)t->hb_words.reserve((size_t)cap[0] * 8);
+      r.word_capacity = cap[0];
+      r.general = (GrimbSubjectResult*)t->hb_general.reserve((size_t)cap[1] * sizeof(GrimbSubjectResult));
+      r.general_capacity = cap[1];
+      r.hap_rows = (GrimbHapRow*)t->hb_hap.reserve((size_t)cap[2] * sizeof(GrimbHapRow));
+      r.hap_capacity = cap[2];
+      r.pop_rows = (GrimbPopRow*)t->hb_pop.reserve((size_t)cap[3] * sizeof(GrimbPopRow));
+      r.pop_capacity = cap[3];
+      r.totals = tot;
+      if (!rc_ || !r.words || !r.general || !r.hap_rows || !r.pop_rows) return tfail(GRIMB_E_NOMEM, "host staging allocation failed");
       rc = grimb_impute_host(engines[tier], cfg, &sb, &r);
       if (rc == GRIMB_E_CAPACITY) {
-        hap_cap = std::max(hap_cap, need_h);
-        pop_cap = std::max(pop_cap, need_p);
+        for (int k = 0; k < 4; ++k) cap[k] = std::max(cap[k], tot[k]);
         continue;
       }
       if (rc) return rc;
       break;
     }
-    if (tier == 0 && n > 0) {
-      t->hap_per_subject = std::max(1.0, (double)need_h / (double)n);
-      t->pop_per_subject = std::max(1.0, (double)need_p / (double)n);
-    }
-    const uint64_t hbase = hap.size(), pbase = pop.size();
-    hap.insert(hap.end(), rh, rh + need_h);
-    pop.insert(pop.end(), rp, rp + need_p);
+    if (tier == 0 && n > 0)
+      for (int k = 0; k < 4; ++k) t->per_subject[k] = std::max(k == 1 ? 0.01 : 0.1, (double)tot[k] / (double)n);
+    evals += tot[4];
+    // subjects whose workspace overflowed (counted in parallel: the records are only 16 bytes each)
+    std::vector<std::vector<uint32_t>> again_t((size_t)t->n_threads);
+    t->parallel(n, [&](int th, size_t lo, size_t hi) {
+      for (size_t k = lo; k < hi; ++k)
+        if (rc_[k].status == GRIMB_ST_WORKSPACE) again_t[th].push_back(tier == 0 ? (uint32_t)k : todo[k]);
+    });
     std::vector<uint32_t> again;
-    for (size_t k = 0; k < n; ++k) {
-      if (rs[k].status == GRIMB_ST_WORKSPACE) {
-        again.push_back(todo[k]);
-        continue;
-      }
-      GrimbSubjectResult o = rs[k];
+    for (auto& v : again_t) again.insert(again.end(), v.begin(), v.end());
+    if (tier == 0 && again.empty()) {
+      fin = r;   // the usual case: format from the staging buffers
+      break;
+    }
+    // merge this tier into the final arrays, re-basing the offsets
+    if (tier == 0) m_compact.assign(rc_, rc_ + n);
+    const uint32_t wbase = (uint32_t)m_words.size(), gbase = (uint32_t)m_general.size();
+    const uint64_t hbase = m_hap.size(), pbase = m_pop.size();
+    m_words.insert(m_words.end(), r.words, r.words + tot[0]);
+    for (int64_t k = 0; k < tot[1]; ++k) {
+      GrimbSubjectResult o = r.general[k];
       o.hap_off += hbase;
       o.pop_off += pbase;
-      subj[todo[k]] = o;
+      m_general.push_back(o);
+    }
+    m_hap.insert(m_hap.end(), r.hap_rows, r.hap_rows + tot[2]);
+    m_pop.insert(m_pop.end(), r.pop_rows, r.pop_rows + tot[3]);
+    for (size_t k = 0; k < n; ++k) {
+      GrimbCompact c = rc_[k];
+      if (c.status == GRIMB_ST_WORKSPACE) continue;
+      if ((c.kind_flags & 3u) == GRIMB_KIND_GENERAL) {
+        if (c.off != 0xFFFFFFFFu) c.off += gbase;
+      } else {
+        c.off += wbase;
+      }
+      m_compact[tier == 0 ? k : todo[k]] = c;
     }
     retries += (int64_t)again.size();
     todo.swap(again);
+    fin.compact = m_compact.data();
+    fin.words = m_words.data();
+    fin.general = m_general.data();
+    fin.hap_rows = m_hap.data();
+    fin.pop_rows = m_pop.data();
   }
   if (!todo.empty()) return tfail(GRIMB_E_NOMEM, "a subject exceeds the largest workspace tier");
   auto t2 = clk::now();
-  GrimbResults fin;
-  fin.subjects = subj.data();
-  fin.hap_rows = hap.data();
-  fin.hap_capacity = (int64_t)hap.size();
-  fin.pop_rows = pop.data();
-  fin.pop_capacity = (int64_t)pop.size();
-  fin.hap_rows_needed = nullptr;
-  fin.pop_rows_needed = nullptr;
+  int64_t ftot[6] = {0, 0, 0, 0, evals, 0};
+  fin.totals = ftot;
   rc = grimb_text_format(t, cfg, &fin, out);
   auto t3 = clk::now();
   out->workspace_retries = retries;

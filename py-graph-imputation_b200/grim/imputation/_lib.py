@@ -74,13 +74,54 @@ def hap_row_dtype(kw=1):
 POP_ROW_DTYPE = [("pa", "<u2"), ("pb", "<u2"), ("pad", "<u4"), ("prob", "<f8")]
 
 
+COMPACT_DTYPE = [("status", "u1"), ("kind_flags", "u1"), ("phases", "<u2"), ("off", "<u4"), ("total", "<f8")]  # GrimbCompact
+KIND_GENERAL, KIND_SIMPLE, KIND_TYPED, KIND_WORDS, KIND_HAS_RESULTS = 0, 1, 2, 4, 8
+NO_RECORD = 0xFFFFFFFF
+
+
 class Results(C.Structure):
     _fields_ = [
-        ("subjects", C.c_void_p),
+        ("compact", C.c_void_p),
+        ("words", C.c_void_p), ("word_capacity", C.c_int64),
+        ("general", C.c_void_p), ("general_capacity", C.c_int64),
         ("hap_rows", C.c_void_p), ("hap_capacity", C.c_int64),
         ("pop_rows", C.c_void_p), ("pop_capacity", C.c_int64),
-        ("hap_rows_needed", C.c_void_p), ("pop_rows_needed", C.c_void_p),
+        ("totals", C.c_void_p),
     ]
+
+
+class ResultArrays(object):
+    """Host result buffers of one ABI call (numpy) + the GrimbResults struct pointing at them.
+    totals: [words, general records, hap rows, pop rows, pair evaluations, handed to the general kernel]."""
+
+    def __init__(self, n_subjects, kw=1, words=1024, general=1024, hap=1024, pop=1024):
+        import numpy as np
+        self.np = np
+        self.kw = kw
+        self.compact = np.zeros(max(1, n_subjects), dtype=COMPACT_DTYPE)
+        self.totals = np.zeros(6, np.int64)
+        self.caps = [max(16, int(words)), max(16, int(general)), max(16, int(hap)), max(16, int(pop))]
+        self._alloc()
+
+    def _alloc(self):
+        np = self.np
+        self.words = np.zeros(self.caps[0], np.uint64)
+        self.general = np.zeros(self.caps[1], dtype=SUBJECT_DTYPE)
+        self.hap_rows = np.zeros(self.caps[2], dtype=hap_row_dtype(self.kw))
+        self.pop_rows = np.zeros(self.caps[3], dtype=POP_ROW_DTYPE)
+        r = Results()
+        r.compact = self.compact.ctypes.data
+        r.words, r.word_capacity = self.words.ctypes.data, self.caps[0]
+        r.general, r.general_capacity = self.general.ctypes.data, self.caps[1]
+        r.hap_rows, r.hap_capacity = self.hap_rows.ctypes.data, self.caps[2]
+        r.pop_rows, r.pop_capacity = self.pop_rows.ctypes.data, self.caps[3]
+        r.totals = self.totals.ctypes.data
+        self.struct = r
+
+    def grow(self):
+        """After GRIMB_E_CAPACITY: enlarge every array to what the call reported."""
+        self.caps = [max(c, int(t)) for c, t in zip(self.caps, self.totals[:4])]
+        self._alloc()
 
 
 class TextDesc(C.Structure):
@@ -146,6 +187,8 @@ def load(kw=1):
     lib.grimb_engine_kernel_ms.argtypes = [C.c_void_p, C.c_int]
     lib.grimb_engine_kernel_ms.restype = C.c_double
     lib.grimb_impute_device.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Batch), C.POINTER(Results), C.c_void_p]
+    lib.grimb_impute_device_async.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Batch), C.POINTER(Results), C.c_void_p]
+    lib.grimb_impute_finish.argtypes = [C.c_void_p, C.POINTER(Results)]
     lib.grimb_impute_host.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Batch), C.POINTER(Results)]
     lib.grimb_text_create.argtypes = [C.POINTER(TextDesc), C.POINTER(C.c_void_p)]
     lib.grimb_text_free.argtypes = [C.c_void_p]
@@ -153,7 +196,7 @@ def load(kw=1):
     lib.grimb_text_format.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Results), C.POINTER(TextOut)]
     lib.grimb_impute_text.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(Config), C.c_char_p,
                                       C.c_int64, C.c_int64, C.POINTER(TextOut)]
-    if lib.grimb_abi_version() != 3:
+    if lib.grimb_abi_version() != 4:
         raise RuntimeError("libgrimb200.so ABI mismatch")
     _LIB[kw] = lib
     return lib
@@ -169,6 +212,6 @@ EXPORTED = [
     "grimb_abi_version", "grimb_last_error", "grimb_tables_build", "grimb_tables_free",
     "grimb_tables_info", "grimb_tables_export", "grimb_tables_image_size", "grimb_tables_image_ptr",
     "grimb_tables_image_copy", "grimb_tables_from_image", "grimb_engine_create", "grimb_engine_free", "grimb_engine_launches", "grimb_engine_kernel_ms",
-    "grimb_impute_device", "grimb_impute_host",
+    "grimb_impute_device", "grimb_impute_device_async", "grimb_impute_finish", "grimb_impute_host",
     "grimb_text_create", "grimb_text_free", "grimb_text_tokenise", "grimb_text_format", "grimb_impute_text",
 ]

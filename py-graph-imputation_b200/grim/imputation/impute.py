@@ -254,7 +254,7 @@ class Imputation(object):
         return lib.grimb_impute_host(eng, C.byref(cfg), C.byref(batch), C.byref(res))
 
     def _run_batch(self, enc, workspace):
-        """enc: list of (mask, counts, flat ids, prior index, phase mask).  -> dict of numpy result arrays."""
+        """enc: list of (mask, counts, flat ids, prior index, phase mask).  -> _lib.ResultArrays of the call."""
         S, L = len(enc), self.L
         typed = np.zeros(S, np.uint16)
         counts = np.zeros((S, L, 2), np.uint16)
@@ -278,34 +278,22 @@ class Imputation(object):
         b.alleles, b.n_alleles_total = alle.ctypes.data, int(off[S])
         b.prior_index, b.priors, b.n_priors = pri.ctypes.data, priors.ctypes.data, priors.shape[0]
         b.phase_mask = pmask.ctypes.data if self.phase_masks is not None else None
-        subj = np.zeros(S, dtype=_lib.SUBJECT_DTYPE)
         hap_cap = max(1024, S * 2 * min(self.cfg.n_results, 16))
         pop_cap = max(1024, S * 2 * min(self.cfg.n_pop_results, 4))
         if self._em_mr:
             pop_cap += S * min(self.cfg.n_results, 16)
-        needed = np.zeros(2, np.int64)
+        res = _lib.ResultArrays(S, self.netGraph.kw, words=max(1024, S * 8), general=max(1024, S), hap=hap_cap, pop=pop_cap)
         while True:
-            hap_rows = np.zeros(hap_cap, dtype=_lib.hap_row_dtype(self.netGraph.kw))
-            pop_rows = np.zeros(pop_cap, dtype=_lib.POP_ROW_DTYPE)
-            r = _lib.Results()
-            r.subjects = subj.ctypes.data
-            r.hap_rows, r.hap_capacity = hap_rows.ctypes.data, hap_cap
-            r.pop_rows, r.pop_capacity = pop_rows.ctypes.data, pop_cap
-            r.hap_rows_needed = needed[0:].ctypes.data
-            r.pop_rows_needed = needed[1:].ctypes.data
             t0 = time.perf_counter()
-            rc = self._backend(self.cfg, b, r, workspace)
+            rc = self._backend(self.cfg, b, res.struct, workspace)
             self.stats["abi_seconds"] = self.stats.get("abi_seconds", 0.0) + time.perf_counter() - t0
             if rc == _lib.E_CAPACITY:
-                hap_cap = max(hap_cap, int(needed[0]))
-                pop_cap = max(pop_cap, int(needed[1]))
+                res.grow()
                 continue
             if rc != 0:
                 _lib.check(rc, "grimb_impute_host", self.netGraph.lib)
             break
-        out = {k: subj[k] for k, _ in _lib.SUBJECT_DTYPE}
-        out["hap_rows"], out["pop_rows"] = hap_rows, pop_rows
-        return out
+        return res
 
     # ------------------------------------------------------------------ formatting
     def _allele_name(self, l, i, unknown):
@@ -329,47 +317,104 @@ class Imputation(object):
     def _pop_name(self, p):
         return "all_pops" if p == _lib.ALL_POPS else self.populations[p]
 
-    def _format_subject(self, sid, res, s, unknown, files):
-        cfgd = self.config
-        ho, po = int(res["hap_off"][s]), int(res["pop_off"][s])
-        nu, np_, nup, npp = (int(res[k][s]) for k in ("n_umug", "n_pmug", "n_umug_pops", "n_pmug_pops"))
-        hr, pr = res["hap_rows"], res["pop_rows"]
-        if cfgd["output_haplotypes"]:
-            rows = files["pmug"]
-            for k in range(np_):
-                row = hr[ho + nu + k]
-                h1 = "~".join(x for x in self._decode(row["a"], unknown) if x is not None)
-                h2 = "~".join(x for x in self._decode(row["b"], unknown) if x is not None)
+    def _subject_rows(self, res, k, ids, unknown):
+        """Result of subject k of one ABI call as plain Python rows (include/grimb200.h, ABI v4):
+        -> dict(status, plan_umug, plan_pmug, tot_umug, tot_pmug, evals, umug [(loci pairs, prob)],
+        umug_pops / pmug_pops [(pop a, pop b, prob)], pmug [(hap 1 names, hap 2 names, prob)],
+        pmug_pairs [(pop a, pop b)] (the hap_pop_pair companions))."""
+        c = res.compact[k]
+        kf = int(c["kind_flags"])
+        kind, has, n_pmug = kf & 3, bool(kf & _lib.KIND_HAS_RESULTS), kf >> 4
+        out = {"status": int(c["status"]), "umug": [], "umug_pops": [], "pmug": [], "pmug_pops": [], "pmug_pairs": []}
+        if kind == _lib.KIND_GENERAL:
+            if int(c["off"]) == _lib.NO_RECORD:
+                out.update(plan_umug=0, plan_pmug=0, tot_umug=0, tot_pmug=0)
+                return out
+            r = res.general[int(c["off"])]
+            ho, po = int(r["hap_off"]), int(r["pop_off"])
+            nu, np_, nup, npp = (int(r[f]) for f in ("n_umug", "n_pmug", "n_umug_pops", "n_pmug_pops"))
+            out.update(plan_umug=int(r["plan_umug"]), plan_pmug=int(r["plan_pmug"]), tot_umug=int(r["tot_umug"]),
+                       tot_pmug=int(r["tot_pmug"]))
+            hr, pr = res.hap_rows, res.pop_rows
+            for q in range(nu):
+                row = hr[ho + q]
+                a, b = self._decode(row["a"], unknown), self._decode(row["b"], unknown)
+                out["umug"].append(([(x, y) for x, y in zip(a, b) if x is not None], float(row["prob"])))
+            for q in range(np_):
+                row = hr[ho + nu + q]
+                out["pmug"].append(([x for x in self._decode(row["a"], unknown) if x is not None],
+                                    [x for x in self._decode(row["b"], unknown) if x is not None], float(row["prob"])))
                 if self._em_mr:
-                    # write_best_hap_race_pairs (impute.py:79-99): "hap;pop,hap;pop"; the populations of PMUG
-                    # row k are the companion row after the regular population rows
-                    pp = pr[po + nup + npp + k]
-                    rows.append(sid + "," + h1 + ";" + self._pop_name(int(pp["pa"])) + "," + h2 + ";"
-                                + self._pop_name(int(pp["pb"])) + "," + str(float(row["prob"])) + "," + str(k) + "\n")
+                    pp = pr[po + nup + npp + q]
+                    out["pmug_pairs"].append((self._pop_name(int(pp["pa"])), self._pop_name(int(pp["pb"]))))
+            for q in range(nup):
+                row = pr[po + q]
+                out["umug_pops"].append((self._pop_name(int(row["pa"])), self._pop_name(int(row["pb"])), float(row["prob"])))
+            for q in range(npp):
+                row = pr[po + nup + q]
+                out["pmug_pops"].append((self._pop_name(int(row["pa"])), self._pop_name(int(row["pb"])), float(row["prob"])))
+            return out
+        # SIMPLE / TYPED: every locus typed, one allele per side; rows follow from the subject's own alleles
+        L = self.L
+        names = [(self._allele_name(l, ids[2 * l], unknown), self._allele_name(l, ids[2 * l + 1], unknown)) for l in range(L)]
+        total, off = float(c["total"]), int(c["off"])
+        w = res.words
+        cfg = self.cfg
+        if kind == _lib.KIND_SIMPLE:
+            phases = [(int(c["phases"]) >> (4 * q)) & 15 for q in range(n_pmug)]
+            probs = [float(w[off + q:off + q + 1].view(np.float64)[0]) for q in range(n_pmug)] if kf & _lib.KIND_WORDS \
+                else [total] * n_pmug
+            pops = [(self.populations[0], self.populations[0], total)] if (has and cfg.n_pop_results >= 1) else []
+        else:
+            hdr = int(w[off])
+            n_pops = hdr & 0xFFFF
+            phases = [(hdr >> (16 + 12 * q)) & 0xFFF for q in range(n_pmug)]
+            probs = [float(x) for x in w[off + 1:off + 1 + n_pmug].view(np.float64)]
+            pp = w[off + 1 + n_pmug:off + 1 + n_pmug + n_pops].view(np.float64)
+            codes = w[off + 1 + n_pmug + n_pops:off + 1 + n_pmug + n_pops + (n_pops + 3) // 4].view(np.uint16)
+            pops = [(self.populations[int(codes[q]) >> 8], self.populations[int(codes[q]) & 0xFF], float(pp[q]))
+                    for q in range(n_pops)]
+        out.update(plan_umug=_lib.PLAN_A if cfg.output_umug else 0, plan_pmug=_lib.PLAN_A if cfg.output_pmug else 0,
+                   tot_umug=1 if (has and cfg.output_umug) else 0, tot_pmug=(max(1, n_pmug) if has else 0) if cfg.output_pmug else 0)
+        if cfg.output_pmug:
+            for ph, pr_ in zip(phases, probs):
+                out["pmug"].append(([names[l][(ph >> l) & 1] for l in range(L)],
+                                    [names[l][1 - ((ph >> l) & 1)] for l in range(L)], pr_))
+            out["pmug_pops"] = list(pops)
+        if cfg.output_umug and has:
+            if cfg.n_results >= 1:
+                out["umug"].append((list(names), total))
+            out["umug_pops"] = list(pops)
+        return out
+
+    def _format_subject(self, sid, rows, files):
+        cfgd = self.config
+        if cfgd["output_haplotypes"]:
+            dst = files["pmug"]
+            for k, (h1, h2, prob) in enumerate(rows["pmug"]):
+                if self._em_mr:
+                    # write_best_hap_race_pairs (impute.py:79-99): "hap;pop,hap;pop"
+                    pa, pb = rows["pmug_pairs"][k]
+                    dst.append(sid + "," + "~".join(h1) + ";" + pa + "," + "~".join(h2) + ";" + pb + "," + str(prob)
+                               + "," + str(k) + "\n")
                     continue
-                rows.append(sid + "," + h1 + "+" + h2 + "," + str(float(row["prob"])) + "," + str(k) + "\n")
-            rows = files["pmug_pops"]
-            for k in range(npp):
-                row = pr[po + nup + k]
-                rows.append(sid + "," + self._pop_name(int(row["pa"])) + "," + self._pop_name(int(row["pb"])) + ","
-                            + str(float(row["prob"])) + "," + str(k) + "\n")
+                dst.append(sid + "," + "~".join(h1) + "+" + "~".join(h2) + "," + str(prob) + "," + str(k) + "\n")
+            dst = files["pmug_pops"]
+            for k, (pa, pb, prob) in enumerate(rows["pmug_pops"]):
+                dst.append(sid + "," + pa + "," + pb + "," + str(prob) + "," + str(k) + "\n")
         if cfgd["output_MUUG"]:
-            rows = files["umug"]
-            for k in range(nu):
-                row = hr[ho + k]
-                a = self._decode(row["a"], unknown)
-                b = self._decode(row["b"], unknown)
-                geno = "^".join("+".join(sorted([x, y])) for x, y in zip(a, b) if x is not None)
-                rows.append(sid + "," + geno + "," + str(float(row["prob"])) + "," + str(k) + "\n")
-            rows = files["umug_pops"]
-            planc = int(res["plan_umug"][s]) == _lib.PLAN_C
-            for k in range(nup):
-                row = pr[po + k]
-                names = sorted([self._pop_name(int(row["pa"])), self._pop_name(int(row["pb"]))])
-                prob = str(float(row["prob"]))
-                if planc and int(res["tot_umug"][s]) == 0:
-                    prob = "0"  # sum() of an empty dict is the int 0 (impute.py:1376)
-                rows.append(sid + "," + names[0] + "," + names[1] + "," + prob + "," + str(k) + "\n")
+            dst = files["umug"]
+            for k, (pairs, prob) in enumerate(rows["umug"]):
+                geno = "^".join("+".join(sorted([x, y])) for x, y in pairs)
+                dst.append(sid + "," + geno + "," + str(prob) + "," + str(k) + "\n")
+            dst = files["umug_pops"]
+            planc = rows["plan_umug"] == _lib.PLAN_C
+            for k, (pa, pb, prob) in enumerate(rows["umug_pops"]):
+                names = sorted([pa, pb])
+                text = str(prob)
+                if planc and rows["tot_umug"] == 0:
+                    text = "0"  # sum() of an empty dict is the int 0 (impute.py:1376)
+                dst.append(sid + "," + names[0] + "," + names[1] + "," + text + "," + str(k) + "\n")
 
     # ------------------------------------------------------------------ public entry points
     def impute_lines(self, lines, first_index=0, em_mr=False, em=False):
@@ -431,9 +476,10 @@ class Imputation(object):
         todo = list(range(len(enc)))
         for tier in self.workspaces:
             out = self._run_batch([enc[s] for s in todo], tier)
+            self.stats["pair_evals"] += int(out.totals[4])
             again = []
             for k, s in enumerate(todo):
-                if out["status"][k] == _lib.ST_WORKSPACE:
+                if out.compact["status"][k] == _lib.ST_WORKSPACE:
                     again.append(s)
                 else:
                     where[s] = (out, k)
@@ -452,8 +498,8 @@ class Imputation(object):
                 files["problem"].append(raw + "\n")
                 continue
             r, k = where[s]
-            st = int(r["status"][k])
-            self.stats["pair_evals"] += int(r["pair_evals"][k])
+            rows = self._subject_rows(r, k, enc[s][2], unknown)
+            st = rows["status"]
             if st == _lib.ST_FAULT:
                 files["problem"].append(raw + "\n")
                 continue
@@ -462,12 +508,12 @@ class Imputation(object):
                 if cfgd["output_haplotypes"]:
                     files["problem"].append(raw + "\n")
                 continue
-            tot_u, tot_p = int(r["tot_umug"][k]), int(r["tot_pmug"][k])
-            self.stats["plan"][int(r["plan_umug"][k] if cfgd["output_MUUG"] else r["plan_pmug"][k])] += 1
+            tot_u, tot_p = rows["tot_umug"], rows["tot_pmug"]
+            self.stats["plan"][rows["plan_umug"] if cfgd["output_MUUG"] else rows["plan_pmug"]] += 1
             pm_empty = (tot_p == 0) if cfgd["output_haplotypes"] else False
             if pm_empty and tot_u == 0:
                 files["miss"].append(str(i) + "," + str(sid) + "\n")
-            self._format_subject(sid, r, k, unknown, files)
+            self._format_subject(sid, rows, files)
 
     # ------------------------------------------------------------------ EM helpers (host only)
     # open_gl_string / open_phases_for_em (impute.py:305-351 of the reference) are list-building

@@ -73,14 +73,22 @@ int grimb_emu_impute(const GrimbEmuTables* t, const GrimbConfig* cfg, const Grim
   S.ar_cap = arena_bytes;
   OutArrays O;
   O.r = *res;
-  unsigned long long hc = 0, pc = 0;
+  unsigned long long hc = 0, pc = 0, wc = 0, gc = 0, ec = 0;
   O.hap_counter = &hc;
   O.pop_counter = &pc;
+  O.word_counter = &wc;
+  O.general_counter = &gc;
+  O.evals_counter = &ec;
   for (int64_t s = 0; s < batch->n_subjects; ++s) run_subject(S, *batch, O, (uint64_t)s);
-  *res->hap_rows_needed = (int64_t)hc;
-  *res->pop_rows_needed = (int64_t)pc;
+  res->totals[0] = (int64_t)wc;
+  res->totals[1] = (int64_t)gc;
+  res->totals[2] = (int64_t)hc;
+  res->totals[3] = (int64_t)pc;
+  res->totals[4] = (int64_t)ec;
+  res->totals[5] = 0;
   free(S.ar_base);
   free(ones);
-  return (int64_t)hc > res->hap_capacity || (int64_t)pc > res->pop_capacity ? GRIMB_E_CAPACITY : 0;
+  return (int64_t)gc > res->general_capacity || (int64_t)hc > res->hap_capacity || (int64_t)pc > res->pop_capacity
+             ? GRIMB_E_CAPACITY : 0;
 }
 }

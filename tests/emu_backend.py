@@ -202,21 +202,12 @@ def emu_impute_text(imp, emu_graph, data, first_index=0, arena=64 << 20):
     b = _lib.Batch()
     _lib.check(lib.grimb_text_tokenise(t, C.byref(imp.cfg), data, len(data), first_index, C.byref(b)), "tokenise")
     S = b.n_subjects
-    subj = np.zeros(max(1, S), dtype=_lib.SUBJECT_DTYPE)
-    hap_cap, pop_cap = 4096, 4096
-    needed = np.zeros(2, np.int64)
+    res = _lib.ResultArrays(S, 1, general=S + 16, hap=4096, pop=4096)
     while True:
-        hap = np.zeros(hap_cap, dtype=_lib.HAP_ROW_DTYPE)
-        pop = np.zeros(pop_cap, dtype=_lib.POP_ROW_DTYPE)
-        r = _lib.Results()
-        r.subjects = subj.ctypes.data
-        r.hap_rows, r.hap_capacity = hap.ctypes.data, hap_cap
-        r.pop_rows, r.pop_capacity = pop.ctypes.data, pop_cap
-        r.hap_rows_needed = needed[0:].ctypes.data
-        r.pop_rows_needed = needed[1:].ctypes.data
+        r = res.struct
         rc = emu_graph.emu.grimb_emu_impute(C.byref(emu_graph.tables), C.byref(imp.cfg), C.byref(b), C.byref(r), arena)
         if rc == _lib.E_CAPACITY:
-            hap_cap, pop_cap = max(hap_cap, int(needed[0])), max(pop_cap, int(needed[1]))
+            res.grow()
             continue
         assert rc == 0
         break

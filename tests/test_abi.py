@@ -40,8 +40,10 @@ def test_binding_lists_header_symbols():
 def test_abi_version_and_struct_sizes(lib):
     import numpy as np
     lib.grimb_abi_version.restype = ctypes.c_int
-    assert lib.grimb_abi_version() == 3
+    assert lib.grimb_abi_version() == 4
     assert np.dtype(_lib.SUBJECT_DTYPE).itemsize == 48
+    assert np.dtype(_lib.COMPACT_DTYPE).itemsize == 16
+    assert ctypes.sizeof(_lib.Results) == 10 * 8
     assert np.dtype(_lib.hap_row_dtype(1)).itemsize == 24
     assert np.dtype(_lib.hap_row_dtype(2)).itemsize == 40
     assert np.dtype(_lib.POP_ROW_DTYPE).itemsize == 16

@@ -21,6 +21,7 @@ def _both(conf, hpf, cnt, lines, tmp_path, monkeypatch, wide=False):
     from grim.run_impute_def import load_config
     if wide:
         monkeypatch.setenv("GRIMB_KEY_WORDS", "2")
+    monkeypatch.setenv("GRIMB_HOST_EVENTS", "1")   # kernel timing events in the host-pointer path
     d = str(tmp_path)
     open(d + "/hpf.csv", "w").write(hpf)
     open(d + "/cnt.txt", "w").write(cnt)

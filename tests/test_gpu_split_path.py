@@ -62,7 +62,8 @@ CONFIGS = [
 
 
 @pytest.mark.parametrize("over", CONFIGS, ids=[json.dumps(c, sort_keys=True) for c in CONFIGS])
-def test_split_fast_path_matches_oracle(over, tmp_path):
+def test_split_fast_path_matches_oracle(over, tmp_path, monkeypatch):
+    monkeypatch.setenv("GRIMB_HOST_EVENTS", "1")   # kernel timing events in the host-pointer path (read at engine creation)
     from grim.imputation.impute import Imputation
     from grim.imputation.networkx_graph import Graph
     from grim.run_impute_def import load_config

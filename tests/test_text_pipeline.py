@@ -70,17 +70,15 @@ def test_float_formatter_equals_python_repr():
     data = "".join("S%d,A*01:01+A*01:01\n" % i for i in range(n)).encode()
     b = _lib.Batch()
     _lib.check(lib.grimb_text_tokenise(t, C.byref(imp.cfg), data, len(data), 0, C.byref(b)), "tokenise")
-    subj = np.zeros(n, dtype=_lib.SUBJECT_DTYPE)
-    subj["plan_umug"] = 1
-    subj["n_umug_pops"] = 1
-    subj["tot_umug"] = 1
-    subj["pop_off"] = np.arange(n)
-    pop = np.zeros(n, dtype=_lib.POP_ROW_DTYPE)
-    pop["prob"] = vals
-    hap = np.zeros(1, dtype=_lib.HAP_ROW_DTYPE)
-    r = _lib.Results()
-    r.subjects, r.hap_rows, r.pop_rows = subj.ctypes.data, hap.ctypes.data, pop.ctypes.data
-    r.hap_capacity, r.pop_capacity = 1, n
+    res = _lib.ResultArrays(n, 1, general=n, pop=n)
+    res.general["plan_umug"] = 1
+    res.general["n_umug_pops"] = 1
+    res.general["tot_umug"] = 1
+    res.general["pop_off"] = np.arange(n)
+    res.pop_rows["prob"] = vals
+    res.compact["kind_flags"] = _lib.KIND_GENERAL | _lib.KIND_HAS_RESULTS
+    res.compact["off"] = np.arange(n)
+    r = res.struct
     out = _lib.TextOut()
     _lib.check(lib.grimb_text_format(t, C.byref(imp.cfg), C.byref(r), C.byref(out)), "format")
     rows = C.string_at(out.data[1], out.size[1]).decode().splitlines()

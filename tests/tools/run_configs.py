@@ -58,7 +58,7 @@ def run(name, conf, hpf_text, counts_text, lines, sample, tmp, oracle_marginals=
         assert only_a[2] == 0 and only_a[3] == 0, "sample left Plan A: %s" % only_a
     info = g.info()
     eng = g.engine(imp.workspaces[0])
-    kms = [g.lib.grimb_engine_kernel_ms(eng, w) for w in (0, 1, 2, 3)]
+    kms = [g.lib.grimb_engine_kernel_ms(eng, w) for w in (0, 1, 2, 3)]   # needs GRIMB_HOST_EVENTS=1
     rec = {
         "config": name, "subjects": len(lines), "gpu_subjects_per_s": len(lines) / dt,
         "gpu_abi_seconds": imp.stats.get("abi_seconds"), "gpu_total_seconds": dt,
