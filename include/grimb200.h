@@ -316,6 +316,34 @@ int grimb_text_format(GrimbText* t, const GrimbConfig* cfg, const GrimbResults* 
 int grimb_impute_text(GrimbText* t, GrimbEngine* const* engines, int32_t n_engines, const GrimbConfig* cfg,
                       const char* text, int64_t len, int64_t first_line_index, GrimbTextOut* out);
 
+/* ------------------------------------------------------------------------------------------
+ * File pipeline.  Replaces Imputation.impute_file (impute.py:1985-2155) for a whole input file (or
+ * the byte range [byte_lo, byte_hi) of it: the lines that START in the range; byte_hi < 0 = to the
+ * end): the input is memory-mapped and cut into chunks of about chunk_bytes (0 = default) at line
+ * boundaries, and four host threads overlap tokenise(c+1) | GPU(c) | format(c-1) | write(c-2).
+ * out_paths[k] (GRIMB_OUT_* order) non-NULL: that output is streamed to the file (created /
+ * truncated); NULL (or out_paths == NULL): it is kept in memory and returned through `out` (valid
+ * until the next call on the same GrimbText) -- what a multi-process caller needs to place its
+ * rows at an offset of a shared file with grimb_file_write_at.  first_line_index: number of the
+ * first line of the range in the whole input (.miss / .problem rows carry line numbers).
+ * grimb_file_count_lines: lines starting in the byte range (multi-threaded) and the range adjusted
+ * to line boundaries.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t n_lines, n_chunks, in_bytes, pair_evals, workspace_retries;
+  int64_t plan_count[4];
+  int64_t out_bytes[6];
+  double seconds_total;                 /* wall clock of the call                              */
+  double seconds_tokenise, seconds_gpu, seconds_format, seconds_write;   /* busy time per stage */
+} GrimbFileStats;
+
+int grimb_impute_file(GrimbText* t, GrimbEngine* const* engines, int32_t n_engines, const GrimbConfig* cfg,
+                      const char* in_path, int64_t byte_lo, int64_t byte_hi, int64_t first_line_index,
+                      const char* const* out_paths, int64_t chunk_bytes, GrimbTextOut* out, GrimbFileStats* stats);
+int grimb_file_count_lines(const char* path, int64_t byte_lo, int64_t byte_hi, int32_t n_threads,
+                           int64_t* n_lines, int64_t* lo_adj, int64_t* hi_adj);
+int grimb_file_write_at(const char* path, int64_t offset, const void* data, int64_t size);
+
 #ifdef __cplusplus
 }
 #endif

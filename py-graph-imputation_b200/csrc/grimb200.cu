@@ -2328,6 +2328,8 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
     }
     return GRIMB_OK;
   };
+  // copy-in of every chunk is queued first (nothing on the device holds it back), so the in-stream streams
+  // the whole batch back to back while the kernels and the copy-out trail one chunk behind
   for (int c = 0; c < nch; ++c) {
     const int64_t s0 = bound[c], s1 = bound[c + 1], n = s1 - s0;
     const uint32_t a0 = b->allele_off[s0], a1 = b->allele_off[s1];
@@ -2342,10 +2344,11 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
       CK(cudaMemcpyAsync((uint32_t*)e->in[4].p + s0, b->prior_index + s0, (size_t)n * 4, cudaMemcpyHostToDevice, si));
     if (b->phase_mask)
       CK(cudaMemcpyAsync((uint16_t*)e->in_mask.p + s0, b->phase_mask + s0, (size_t)n * 2, cudaMemcpyHostToDevice, si));
-    if (nch > 1) {
-      CK(cudaEventRecord(e->ev_in[c], si));
-      CK(cudaStreamWaitEvent(st, e->ev_in[c], 0));
-    }
+    if (nch > 1) CK(cudaEventRecord(e->ev_in[c], si));
+  }
+  for (int c = 0; c < nch; ++c) {
+    const int64_t s0 = bound[c], s1 = bound[c + 1], n = s1 - s0;
+    if (nch > 1) CK(cudaStreamWaitEvent(st, e->ev_in[c], 0));
     GrimbBatch db = *b;
     db.n_subjects = n;
     db.typed_mask = (const uint16_t*)e->in[0].p + s0;
@@ -2362,8 +2365,7 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
     if (rc) return rc;
     CK(cudaMemcpyAsync(e->h_cnt + (size_t)CNT_N * c, e->d_counters, CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(e->ev_k[c], st));
-    // with chunk c in the queue, hand chunk c-1 to the copy-out stream: enqueueing every chunk first
-    // would hold the first copy-out back by the whole enqueue time
+    // with chunk c in the queue, hand chunk c-1 to the copy-out stream
     if (c > 0) {
       rc = copy_out(c - 1);
       if (rc) return rc;

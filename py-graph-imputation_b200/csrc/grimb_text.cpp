@@ -6,10 +6,14 @@
 // grim/imputation/impute.py:24-118,246-272,1844-1975,1985-2155).  No CUDA calls in this file
 // except through grimb_impute_host.
 #include <algorithm>
+#include <cerrno>
 #include <charconv>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <string_view>
 #include <thread>
@@ -21,6 +25,7 @@
 extern "C" void* grimb_pinned_alloc(size_t bytes);  // grimb200.cu: cudaMallocHost or nullptr
 extern "C" void grimb_pinned_free(void* p);
 extern "C" void grimb_set_error(const char* msg);   // grimb200.cu: the message grimb_last_error() returns
+extern "C" const char* grimb_last_error(void);
 
 namespace {
 
@@ -163,18 +168,18 @@ struct GrimbText {
   // priors (memoised across calls)
   std::unordered_map<PriorKey, uint32_t, PriorKeyHash> prior_index;
   std::vector<double> priors;
-  // state of the current call
-  std::string text;   // private copy of the input (string_views point into it)
-  int64_t first_index = 0;
-  std::vector<Line> lines;
-  std::vector<std::string> fmt_parts;   // per-thread pieces of the six outputs (capacity reused)
-  std::vector<std::vector<uint16_t>> t_ids;
-  std::vector<std::vector<Unknown>> t_unk;
-  std::vector<std::string> t_clean;  // unused placeholder (cleaned GL strings are per-call locals)
-  std::vector<uint16_t> b_typed, b_counts, b_alleles;
-  std::vector<uint32_t> b_off, b_prior;
-  std::string out[6];
-  // pinned staging for grimb_impute_text (grow-only) and the adaptive row-capacity estimate
+  // fast name lookup of the tokeniser: every table allele of every locus in one open-addressing table
+  struct NameEnt {
+    uint64_t h;
+    const char* s;
+    uint16_t len, id;
+    uint8_t locus;
+  };
+  std::vector<NameEnt> name_ent;
+  std::vector<uint32_t> name_slot;   // entry index + 1, 0 = empty
+  uint32_t name_mask = 0;
+  bool fast_path = true;             // GRIMB_TEXT_FAST=0: every line through the general parser (A/B, tests)
+  // pinned staging (grow-only)
   struct HostBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -199,8 +204,39 @@ struct GrimbText {
     }
     ~HostBuf() { release(); }
   };
-  HostBuf hb_compact, hb_words, hb_general, hb_hap, hb_pop;
-  double per_subject[4] = {0.5, 0.05, 0.3, 0.3};   // words, general records, hap rows, pop rows
+  // State of one chunk of input in flight: the single-call entry points use slot0, the file pipeline
+  // (grimb_impute_file) keeps several so that tokenising, the GPU, formatting and file writes overlap.
+  struct Slot {
+    const char* text = nullptr;   // the chunk's bytes (string_views of `lines` point into them)
+    size_t text_len = 0;
+    std::string own;              // private copy when the caller's buffer may go away
+    int64_t first_index = 0;
+    std::vector<Line> lines;
+    std::vector<std::vector<uint16_t>> t_ids;
+    std::vector<std::vector<Unknown>> t_unk;
+    std::vector<uint16_t> b_typed, b_counts, b_alleles;
+    std::vector<uint32_t> b_off, b_prior;
+    std::vector<double> priors;   // snapshot of the memoised prior matrices at tokenise time
+    GrimbBatch batch;
+    HostBuf hb_compact, hb_words, hb_general, hb_hap, hb_pop;
+    std::vector<GrimbCompact> m_compact;      // merged results when a workspace tier overflowed
+    std::vector<uint64_t> m_words;
+    std::vector<GrimbSubjectResult> m_general;
+    std::vector<GrimbHapRow> m_hap;
+    std::vector<GrimbPopRow> m_pop;
+    GrimbResults fin;
+    int64_t totals[6] = {0, 0, 0, 0, 0, 0};
+    int64_t retries = 0;
+    std::vector<std::string> fmt_parts;   // per-thread pieces of the six outputs (capacity reused)
+    std::string out[6];
+    int64_t out_size[6] = {0, 0, 0, 0, 0, 0};
+    int64_t plan_count[4] = {0, 0, 0, 0};
+    double sec_tok = 0, sec_gpu = 0, sec_fmt = 0;
+  };
+  Slot slot0;
+  std::vector<std::unique_ptr<Slot>> pipe;   // slots of the file pipeline (grimb_impute_file)
+  std::string file_acc[6];                   // outputs of grimb_impute_file that are kept in memory
+  double per_subject[4] = {0.5, 0.05, 0.3, 0.3};   // words, general records, hap rows, pop rows (adaptive capacities)
 
   template <class F>
   void parallel(size_t n, F f) const {
@@ -291,6 +327,12 @@ struct GrimbText {
     return idx;
   }
 
+  std::mutex prior_m;   // the memo is shared by the tokeniser's worker threads
+  uint32_t prior_lookup_locked(const Line& ln) {
+    std::lock_guard<std::mutex> g(prior_m);
+    return prior_lookup(ln);
+  }
+
   uint32_t prior_lookup(const Line& ln) {
     PriorKey k{ln.has_race, std::string(ln.race1), std::string(ln.race2)};
     auto it = prior_index.find(k);
@@ -322,8 +364,176 @@ struct GrimbText {
     return idx;
   }
 
+  // ---- fast name lookup
+  static uint64_t name_hash(const char* s, size_t n) {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)n;
+    while (n >= 8) {
+      uint64_t w;
+      memcpy(&w, s, 8);
+      h = (h ^ w) * 0xff51afd7ed558ccdULL;
+      h ^= h >> 32;
+      s += 8;
+      n -= 8;
+    }
+    if (n) {
+      uint64_t w = 0;
+      memcpy(&w, s, n);
+      h = (h ^ w) * 0xff51afd7ed558ccdULL;
+      h ^= h >> 32;
+    }
+    return h;
+  }
+
+  void build_name_table() {
+    size_t n = 0;
+    for (auto& a : alleles) n += a.size();
+    uint32_t sz = 16;
+    while (sz < n * 2 + 2) sz <<= 1;
+    name_mask = sz - 1;
+    name_slot.assign(sz, 0);
+    name_ent.clear();
+    name_ent.reserve(n);
+    for (int l = 0; l < L; ++l)
+      for (size_t i = 0; i < alleles[l].size(); ++i) {
+        const std::string& nm = alleles[l][i];
+        // the general parser decides the locus from the prefix before '*': only names that carry their own
+        // locus prefix may take the fast path
+        if (nm.size() > 0xFFFF || sv(nm).substr(0, nm.find('*')) != sv(loci[l])) continue;
+        NameEnt e;
+        e.h = name_hash(nm.data(), nm.size());
+        e.s = nm.data();
+        e.len = (uint16_t)nm.size();
+        e.id = (uint16_t)(i + 1);
+        e.locus = (uint8_t)l;
+        uint32_t h = (uint32_t)e.h & name_mask;
+        bool dup = false;
+        while (name_slot[h]) {
+          const NameEnt& o = name_ent[name_slot[h] - 1];
+          if (o.h == e.h && o.len == e.len && memcmp(o.s, e.s, e.len) == 0) dup = true;   // same name under two loci
+          h = (h + 1) & name_mask;
+        }
+        if (dup) {
+          fast_path = false;
+          continue;
+        }
+        name_ent.push_back(e);
+        name_slot[h] = (uint32_t)name_ent.size();
+      }
+  }
+
+  const NameEnt* find_name(const char* s, size_t n) const {
+    const uint64_t hv = name_hash(s, n);
+    uint32_t h = (uint32_t)hv & name_mask;
+    for (;;) {
+      const uint32_t k = name_slot[h];
+      if (!k) return nullptr;
+      const NameEnt& e = name_ent[k - 1];
+      if (e.h == hv && e.len == n && memcmp(e.s, s, n) == 0) return &e;
+      h = (h + 1) & name_mask;
+    }
+  }
+
+  // Fast path of the tokeniser: one pass over a line of the regular shape
+  //     id,LOC*a[/LOC*b...]+LOC*c[/...]^LOC2*...+...[,race1,race2[,...]]
+  // with the loci in ascending loci_map order, every listed allele a table allele carrying its locus prefix,
+  // and none of the characters clean_up_gl (impute.py:105-118) reacts to ('g', 'L', 'U').  For such a line
+  // the general parser below does exactly this: the per-side sorts (gl2haps, impute.py:271) are no-ops
+  // because every string starts with its locus prefix and the prefixes ascend, the locus of a chunk is
+  // that of its first name, and ids are listed locus by locus, side 0 then side 1, duplicates dropped.
+  // Anything else returns false with nothing changed, and the general parser takes the line.
+  bool parse_fast(Slot& S, sv raw_line, Line& ln, int thread) const {
+    size_t e = raw_line.size();
+    while (e > 0 && py_space((unsigned char)raw_line[e - 1])) --e;
+    const char* p = raw_line.data();
+    const char* end = p + e;
+    const char* c1 = (const char*)memchr(p, ',', e);
+    if (!c1) return false;
+    const char* g0 = c1 + 1;
+    const char* c2 = (const char*)memchr(g0, ',', (size_t)(end - g0));
+    const char* g1 = c2 ? c2 : end;
+    sv race1, race2;
+    if (c2) {
+      const char* r1 = c2 + 1;
+      const char* c3 = (const char*)memchr(r1, ',', (size_t)(end - r1));
+      if (!c3) return false;   // exactly three fields: the reference's parser raises
+      const char* r2 = c3 + 1;
+      const char* c4 = (const char*)memchr(r2, ',', (size_t)(end - r2));
+      race1 = sv(r1, (size_t)(c3 - r1));
+      race2 = sv(r2, (size_t)((c4 ? c4 : end) - r2));
+    }
+    if (g0 == g1) return false;
+    std::vector<uint16_t>& idv = S.t_ids[thread];
+    const size_t ids_off = idv.size();
+    uint16_t counts[GRIMB_MAX_LOCI * 2];
+    memset(counts, 0, sizeof(counts));
+    uint32_t mask = 0;
+    int last_l = -1;
+    const char* q = g0;
+    for (;;) {   // one locus chunk: side '+' side
+      int l = -1;
+      for (int side = 0; side < 2; ++side) {
+        const size_t lst = idv.size();
+        for (;;) {   // one allele name
+          const char* n0 = q;
+          while (q < g1) {
+            const char ch = *q;
+            if (ch == '/' || ch == '+' || ch == '^') break;
+            if (ch == 'g' || ch == 'L' || ch == 'U') goto slow;
+            ++q;
+          }
+          if (q == n0) goto slow;
+          const NameEnt* ne = find_name(n0, (size_t)(q - n0));
+          if (!ne) goto slow;
+          if (l < 0) {
+            l = ne->locus;
+            if (l <= last_l) goto slow;
+          } else if (ne->locus != l) {
+            goto slow;
+          }
+          bool seen = false;
+          for (size_t k = lst; k < idv.size(); ++k) seen = seen || idv[k] == ne->id;
+          if (!seen) idv.push_back(ne->id);
+          if (q < g1 && *q == '/') {
+            ++q;
+            continue;
+          }
+          break;
+        }
+        counts[2 * l + side] = (uint16_t)(idv.size() - lst);
+        if (side == 0) {
+          if (q >= g1 || *q != '+') goto slow;
+          ++q;
+        }
+      }
+      mask |= 1u << l;
+      last_l = l;
+      if (q == g1) break;
+      if (*q != '^') goto slow;   // e.g. a third side
+      ++q;
+      if (q == g1) goto slow;     // trailing '^'
+    }
+    ln.raw = sv(p, e);
+    ln.sid = sv(p, (size_t)(c1 - p));
+    ln.has_race = c2 != nullptr;
+    ln.race1 = race1;
+    ln.race2 = race2;
+    ln.no_fields = false;
+    ln.hclass = H_OK;
+    ln.thread = (uint32_t)thread;
+    ln.mask = (uint16_t)mask;
+    memcpy(ln.counts, counts, sizeof(counts));
+    ln.ids_off = (uint32_t)ids_off;
+    ln.ids_cnt = (uint32_t)(idv.size() - ids_off);
+    ln.unk_off = (uint32_t)S.t_unk[thread].size();
+    ln.unk_cnt = 0;
+    return true;
+  slow:
+    idv.resize(ids_off);
+    return false;
+  }
+
   // one input line -> Line (reference impute.py:2022-2036 + clean_up_gl + gl2haps)
-  void parse_line(sv raw_line, Line& ln, int thread, bool planb, std::string& clean, std::vector<sv>& f1,
+  void parse_line(Slot& S, sv raw_line, Line& ln, int thread, bool planb, std::string& clean, std::vector<sv>& f1,
                   std::vector<sv>& f2, std::vector<sv>& t1, std::vector<sv>& t2, std::vector<sv>& names,
                   std::vector<uint16_t>& scr) {
     size_t e = raw_line.size();
@@ -386,8 +596,8 @@ struct GrimbText {
     }
     std::sort(t1.begin(), t1.end());
     std::sort(t2.begin(), t2.end());
-    std::vector<uint16_t>& idv = t_ids[thread];
-    std::vector<Unknown>& unk = t_unk[thread];
+    std::vector<uint16_t>& idv = S.t_ids[thread];
+    std::vector<Unknown>& unk = S.t_unk[thread];
     const uint32_t ids_off = (uint32_t)idv.size(), unk_off = (uint32_t)unk.size();
     // the id lists of this line, built in a reused scratch vector: [off, off + cnt) per locus and side
     scr.clear();
@@ -454,9 +664,9 @@ struct GrimbText {
     ln.unk_cnt = (uint32_t)unk.size() - unk_off;
   }
 
-  sv allele_name(int l, uint32_t id, const Line& ln) const {
+  sv allele_name(const Slot& S, int l, uint32_t id, const Line& ln) const {
     if (id >= 1 && id <= alleles[l].size()) return alleles[l][id - 1];
-    const std::vector<Unknown>& u = t_unk[ln.thread];
+    const std::vector<Unknown>& u = S.t_unk[ln.thread];
     for (uint32_t i = 0; i < ln.unk_cnt; ++i)
       if (u[ln.unk_off + i].locus == l && u[ln.unk_off + i].id == id) return u[ln.unk_off + i].name;
     return "?";
@@ -474,14 +684,14 @@ struct GrimbText {
   }
 #endif
 
-  void put_hap(keyref key, const Line& ln, std::string& o) const {
+  void put_hap(const Slot& S, keyref key, const Line& ln, std::string& o) const {
     bool first = true;
     for (int l = 0; l < L; ++l) {
       uint32_t id = field(key, l);
       if (!id) continue;
       if (!first) o += '~';
       first = false;
-      o += allele_name(l, id, ln);
+      o += allele_name(S, l, id, ln);
     }
   }
 
@@ -509,9 +719,9 @@ struct GrimbText {
   // every locus typed with one allele per side, so the single UMUG genotype is the subject's own allele
   // pairs and a PMUG row's haplotypes follow from its phase id (bit m: locus m takes its side-2 allele in
   // the first haplotype).  Same row order and text as the general layout below.
-  void format_compact(const Line& ln, const GrimbCompact& c, const uint64_t* words, const GrimbConfig* cfg,
+  void format_compact(const Slot& S, const Line& ln, const GrimbCompact& c, const uint64_t* words, const GrimbConfig* cfg,
                       std::string* o) const {
-    const uint16_t* ids = t_ids[ln.thread].data() + ln.ids_off;   // [L][2]
+    const uint16_t* ids = S.t_ids[ln.thread].data() + ln.ids_off;   // [L][2]
     const uint32_t kind = c.kind_flags & 3u, n_pmug = c.kind_flags >> 4;
     const bool has = (c.kind_flags & GRIMB_KIND_HAS_RESULTS) != 0;
     const uint64_t* w = words + c.off;
@@ -557,7 +767,7 @@ struct GrimbText {
           if (side) s += '+';
           for (int l = 0; l < L; ++l) {
             if (l) s += '~';
-            s += allele_name(l, ids[2 * l + (int)(((phase[k] >> l) & 1u) ^ (uint32_t)side)], ln);
+            s += allele_name(S, l, ids[2 * l + (int)(((phase[k] >> l) & 1u) ^ (uint32_t)side)], ln);
           }
         }
         put_row_tail(pmug_prob ? dbl(pmug_prob[k]) : c.total, k, s);
@@ -575,7 +785,7 @@ struct GrimbText {
         s += ln.sid;
         s += ',';
         for (int l = 0; l < L; ++l) {
-          sv x = allele_name(l, ids[2 * l], ln), y = allele_name(l, ids[2 * l + 1], ln);
+          sv x = allele_name(S, l, ids[2 * l], ln), y = allele_name(S, l, ids[2 * l + 1], ln);
           if (y < x) std::swap(x, y);
           if (l) s += '^';
           s += x;
@@ -593,7 +803,7 @@ struct GrimbText {
     }
   }
 
-  void format_subject(const Line& ln, const GrimbSubjectResult& r, const GrimbHapRow* hr, const GrimbPopRow* pr,
+  void format_subject(const Slot& S, const Line& ln, const GrimbSubjectResult& r, const GrimbHapRow* hr, const GrimbPopRow* pr,
                       const GrimbConfig* cfg, std::string* o) const {
     if (cfg->output_pmug) {
       for (uint32_t k = 0; k < r.n_pmug; ++k) {
@@ -601,9 +811,9 @@ struct GrimbText {
         std::string& s = o[GRIMB_OUT_PMUG];
         s += ln.sid;
         s += ',';
-        put_hap(row.a, ln, s);
+        put_hap(S, row.a, ln, s);
         s += '+';
-        put_hap(row.b, ln, s);
+        put_hap(S, row.b, ln, s);
         put_row_tail(row.prob, k, s);
       }
       for (uint32_t k = 0; k < r.n_pmug_pops; ++k) {
@@ -621,7 +831,7 @@ struct GrimbText {
         for (int l = 0; l < L; ++l) {
           uint32_t a = field(row.a, l), b = field(row.b, l);
           if (!a) continue;
-          sv x = allele_name(l, a, ln), y = allele_name(l, b, ln);
+          sv x = allele_name(S, l, a, ln), y = allele_name(S, l, b, ln);
           if (y < x) std::swap(x, y);
           if (!first) s += '^';
           first = false;
@@ -684,6 +894,12 @@ extern "C" int grimb_text_create(const GrimbTextDesc* d, GrimbText** out) {
   t->gamma = d->gamma;
   t->delta = d->delta;
   t->mr = d->unk_priors_mr != 0;
+  if (const char* fp = getenv("GRIMB_TEXT_FAST"))
+    if (fp[0] == '0') t->fast_path = false;
+  // the fast path relies on the loci ascending in loci_map order == ascending string order of "LOC*"
+  for (int l = 1; l < t->L; ++l)
+    if (!(t->loci[l - 1] + "*" < t->loci[l] + "*")) t->fast_path = false;
+  t->build_name_table();
   *out = t;
   return GRIMB_OK;
 }
@@ -693,104 +909,191 @@ extern "C" int grimb_text_free(GrimbText* t) {
   return GRIMB_OK;
 }
 
-extern "C" int grimb_text_tokenise(GrimbText* t, const GrimbConfig* cfg, const char* text, int64_t len,
-                                   int64_t first_line_index, GrimbBatch* b) {
-  if (!t || !cfg || !text || !b || len < 0) return tfail(GRIMB_E_ARG, "null argument");
-  t->text.assign(text, (size_t)len);
-  t->first_index = first_line_index;
-  // line boundaries (Python file iteration: split on '\n', a final line without '\n' counts)
-  std::vector<std::pair<size_t, size_t>> bounds;
-  {
-    const char* p = t->text.data();
-    size_t n = t->text.size(), b0 = 0;
-    while (b0 < n) {
-      const void* q = memchr(p + b0, '\n', n - b0);
-      size_t e = q ? (size_t)((const char*)q - p) + 1 : n;
-      bounds.emplace_back(b0, e);
-      b0 = e;
-    }
+namespace {
+
+using Slot = GrimbText::Slot;
+using clk = std::chrono::steady_clock;
+inline double secs(clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); }
+
+// input bytes -> Lines + the GrimbBatch arrays of the slot.  `borrow`: the caller keeps `text` alive until
+// the slot has been formatted; otherwise the slot takes a private copy.
+int tokenise_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const char* text, int64_t len, int64_t first_line_index,
+                  bool borrow) {
+  auto t0 = clk::now();
+  if (borrow) {
+    S.text = text;
+  } else {
+    S.own.assign(text, (size_t)len);
+    S.text = S.own.data();
   }
-  const size_t S = bounds.size();
-  t->lines.assign(S, Line());
-  t->t_ids.assign((size_t)t->n_threads, {});
-  t->t_unk.assign((size_t)t->n_threads, {});
-  t->last_valid = false;   // the remembered race fields point into the previous call's text
+  S.text_len = (size_t)len;
+  S.first_index = first_line_index;
+  const char* p = S.text;
+  const size_t n = S.text_len;
+  const int nt = t->n_threads;
+  // line boundaries (Python file iteration: split on '\n', a final line without '\n' counts): every thread
+  // counts the newlines of its byte range, then parses the lines that START in its range
+  std::vector<size_t> cut((size_t)nt + 1, 0), nl((size_t)nt + 1, 0);
+  for (int k = 0; k <= nt; ++k) cut[k] = n * (size_t)k / (size_t)nt;
+  // a range starts at the first line start at or after cut[k]
+  for (int k = 1; k < nt; ++k) {
+    size_t b0 = cut[k];
+    if (b0 > 0 && b0 < n && p[b0 - 1] != '\n') {
+      const void* q = memchr(p + b0, '\n', n - b0);
+      b0 = q ? (size_t)((const char*)q - p) + 1 : n;
+    }
+    cut[k] = b0;
+  }
+  for (int k = 1; k <= nt; ++k)
+    if (cut[k] < cut[k - 1]) cut[k] = cut[k - 1];
+  t->parallel((size_t)nt, [&](int, size_t lo, size_t hi) {
+    for (size_t k = lo; k < hi; ++k) {
+      size_t c = 0;
+      const char* q = p + cut[k];
+      const char* e = p + cut[k + 1];
+      while (q < e) {
+        const void* f = memchr(q, '\n', (size_t)(e - q));
+        ++c;   // a line (terminated here, or the unterminated tail of the range)
+        if (!f) break;
+        q = (const char*)f + 1;
+      }
+      nl[k + 1] = c;
+    }
+  });
+  for (int k = 0; k < nt; ++k) nl[k + 1] += nl[k];
+  const size_t NS = nl[nt];
+  auto tA = clk::now();
+  S.lines.assign(NS, Line());
+  S.t_ids.resize((size_t)nt);
+  S.t_unk.resize((size_t)nt);
+  for (auto& v : S.t_ids) v.clear();
+  for (auto& v : S.t_unk) v.clear();
   const bool planb = cfg->planb != 0;
-  // the cleaned GL strings must outlive the call for unknown-allele names: names are copied
-  t->parallel(S, [&](int th, size_t lo, size_t hi) {
+  const bool fast = t->fast_path;
+  const int L = t->L;
+  S.b_typed.resize(NS);
+  S.b_off.resize(NS + 1);
+  S.b_prior.resize(NS);
+  std::vector<size_t> r_ids((size_t)nt + 1, 0);
+  std::vector<uint8_t> r_multi((size_t)nt, 0), r_prior((size_t)nt, 0);
+  // parse: every range its own lines; b_off is written relative to the range and re-based below
+  t->parallel((size_t)nt, [&](int, size_t klo, size_t khi) {
     std::string clean;
     std::vector<sv> f1, f2, t1, t2, names;
     std::vector<uint16_t> scr;
-    for (size_t i = lo; i < hi; ++i)
-      t->parse_line(sv(t->text.data() + bounds[i].first, bounds[i].second - bounds[i].first), t->lines[i], th, planb,
-                    clean, f1, f2, t1, t2, names, scr);
-  });
-  // sequential: prior indices (memoised) + flat batch arrays
-  const int L = t->L;
-  t->b_typed.assign(S, 0);
-  t->b_counts.assign(S * (size_t)L * 2, 0);
-  t->b_off.assign(S + 1, 0);
-  t->b_prior.assign(S, 0);
-  size_t total = 0;
-  for (size_t i = 0; i < S; ++i) {
-    Line& ln = t->lines[i];
-    if (!ln.no_fields) ln.prior = t->prior_for(ln);  // the reference computes the prior before looking at the GL
-    t->b_off[i] = (uint32_t)total;
-    if (ln.hclass == H_OK && ln.mask) total += ln.ids_cnt;
-  }
-  t->b_off[S] = (uint32_t)total;
-  if (t->priors.empty()) {
-    Line dummy;
-    t->prior_for(dummy);
-  }
-  t->b_alleles.assign(total ? total : 1, 0);
-  t->parallel(S, [&](int, size_t lo, size_t hi) {
-    for (size_t i = lo; i < hi; ++i) {
-      const Line& ln = t->lines[i];
-      t->b_prior[i] = ln.prior;
-      if (ln.hclass != H_OK || !ln.mask) continue;
-      t->b_typed[i] = ln.mask;
-      for (int q = 0; q < L * 2; ++q) t->b_counts[i * (size_t)L * 2 + q] = ln.counts[q];
-      const std::vector<uint16_t>& idv = t->t_ids[ln.thread];
-      std::copy(idv.begin() + ln.ids_off, idv.begin() + ln.ids_off + ln.ids_cnt, t->b_alleles.begin() + t->b_off[i]);
+    for (size_t k = klo; k < khi; ++k) {
+      size_t i = nl[k];
+      const char* q = p + cut[k];
+      const char* e = p + cut[k + 1];
+      // consecutive lines mostly repeat the race fields: remember the last key of this range
+      bool lv = false, l_has = false;
+      sv l_r1, l_r2;
+      uint32_t l_prior = 0;
+      size_t run = 0;
+      bool multi = false, other_prior = false;
+      while (q < e) {
+        const void* f = memchr(q, '\n', (size_t)(e - q));
+        const char* le = f ? (const char*)f + 1 : e;
+        const sv line(q, (size_t)(le - q));
+        Line& ln = S.lines[i];
+        if (!(fast && t->parse_fast(S, line, ln, (int)k)))
+          t->parse_line(S, line, ln, (int)k, planb, clean, f1, f2, t1, t2, names, scr);
+        if (!ln.no_fields) {   // the reference computes the prior before looking at the GL
+          if (!(lv && ln.has_race == l_has && ln.race1 == l_r1 && ln.race2 == l_r2)) {
+            l_prior = t->prior_lookup_locked(ln);
+            lv = true;
+            l_has = ln.has_race;
+            l_r1 = ln.race1;
+            l_r2 = ln.race2;
+          }
+          ln.prior = l_prior;
+        }
+        S.b_prior[i] = ln.prior;
+        other_prior = other_prior || ln.prior != 0;
+        S.b_off[i] = (uint32_t)run;
+        const bool valid = ln.hclass == H_OK && ln.mask;
+        S.b_typed[i] = valid ? ln.mask : (uint16_t)0;
+        if (valid) {
+          run += ln.ids_cnt;
+          multi = multi || ln.ids_cnt != 2u * (uint32_t)__builtin_popcount(ln.mask);
+        }
+        ++i;
+        q = le;
+      }
+      r_ids[k + 1] = run;   // == S.t_ids[k].size(): only valid lines leave ids behind
+      r_multi[k] = multi;
+      r_prior[k] = other_prior;
     }
   });
+  auto tB = clk::now();
+  bool all_single = true, one_prior = true;
+  for (int k = 0; k < nt; ++k) {
+    r_ids[k + 1] += r_ids[k];
+    all_single = all_single && !r_multi[k];
+    one_prior = one_prior && !r_prior[k];
+  }
+  const size_t total = r_ids[nt];
+  S.b_off[NS] = (uint32_t)total;
+  {
+    std::lock_guard<std::mutex> g(t->prior_m);
+    if (t->priors.empty()) {   // no line carried fields: the kernels still expect matrix 0
+      Line dummy;
+      t->prior_lookup(dummy);
+    }
+    S.priors = t->priors;   // snapshot: a later chunk may add matrices while this one is still on the GPU
+  }
+  auto tC = clk::now();
+  S.b_alleles.resize(total ? total : 1);
   // ABI v4: the counts travel only when some subject lists several alleles on a side (every typed side
   // lists at least one), the prior indices only when more than one prior matrix is in use
-  bool all_single = true, one_prior = true;
-  for (size_t i = 0; i < S && (all_single || one_prior); ++i) {
-    const Line& ln = t->lines[i];
-    if (t->b_prior[i] != 0) one_prior = false;
-    if (ln.hclass == H_OK && ln.mask && ln.ids_cnt != 2u * (uint32_t)__builtin_popcount(ln.mask)) all_single = false;
-  }
-  b->n_subjects = (int64_t)S;
-  b->typed_mask = t->b_typed.data();
-  b->counts = all_single ? nullptr : t->b_counts.data();
-  b->allele_off = t->b_off.data();
-  b->alleles = t->b_alleles.data();
-  b->n_alleles_total = (int64_t)total;
-  b->prior_index = one_prior ? nullptr : t->b_prior.data();
-  b->priors = t->priors.data();
-  b->n_priors = (int32_t)(t->priors.size() / ((size_t)t->P * t->P));
-  b->phase_mask = nullptr;   // default phase enumeration; masks are served by the numpy host front end
+  if (!all_single) S.b_counts.assign(NS * (size_t)L * 2, 0);
+  t->parallel((size_t)nt, [&](int, size_t klo, size_t khi) {
+    for (size_t k = klo; k < khi; ++k) {
+      const uint32_t base = (uint32_t)r_ids[k];
+      if (!S.t_ids[k].empty()) memcpy(&S.b_alleles[base], S.t_ids[k].data(), S.t_ids[k].size() * 2);
+      for (size_t i = nl[k]; i < nl[k + 1]; ++i) {
+        S.b_off[i] += base;
+        if (!all_single) {
+          const Line& ln = S.lines[i];
+          if (ln.hclass == H_OK && ln.mask)
+            for (int q = 0; q < L * 2; ++q) S.b_counts[i * (size_t)L * 2 + q] = ln.counts[q];
+        }
+      }
+    }
+  });
+  GrimbBatch& b = S.batch;
+  b.n_subjects = (int64_t)NS;
+  b.typed_mask = S.b_typed.data();
+  b.counts = all_single ? nullptr : S.b_counts.data();
+  b.allele_off = S.b_off.data();
+  b.alleles = S.b_alleles.data();
+  b.n_alleles_total = (int64_t)total;
+  b.prior_index = one_prior ? nullptr : S.b_prior.data();
+  b.priors = S.priors.data();
+  b.n_priors = (int32_t)(S.priors.size() / ((size_t)t->P * t->P));
+  b.phase_mask = nullptr;   // default phase enumeration; masks are served by the numpy host front end
+  S.sec_tok = secs(t0, clk::now());
+  if (getenv("GRIMB_TEXT_TRACE"))
+    fprintf(stderr, "tokenise: count %.1f ms, parse %.1f ms, seq %.1f ms, fill %.1f ms\n", secs(t0, tA) * 1e3, secs(tA, tB) * 1e3,
+            secs(tB, tC) * 1e3, secs(tC, clk::now()) * 1e3);
   return GRIMB_OK;
 }
 
-extern "C" int grimb_text_format(GrimbText* t, const GrimbConfig* cfg, const GrimbResults* res, GrimbTextOut* out) {
-  if (!t || !cfg || !res || !out || !res->compact) return tfail(GRIMB_E_ARG, "null argument");
-  const size_t S = t->lines.size();
+// results of the slot's batch -> the six texts (S.out / S.out_size), plan histogram
+int format_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const GrimbResults* res) {
+  auto t0 = clk::now();
+  const size_t NS = S.lines.size();
   const int nt = t->n_threads;
-  // per-thread output pieces live in the GrimbText so their capacity is reused from call to call
-  std::vector<std::string>& parts = t->fmt_parts;
+  std::vector<std::string>& parts = S.fmt_parts;
   parts.resize((size_t)nt * 6);
   for (auto& ps : parts) ps.clear();
   std::vector<int64_t> plans((size_t)nt * 4, 0);
   static const GrimbSubjectResult kNoRecord = {};   // a skipped subject: nothing was computed
-  t->parallel(S, [&](int th, size_t lo, size_t hi) {
+  t->parallel(NS, [&](int th, size_t lo, size_t hi) {
     std::string* o = &parts[(size_t)th * 6];
     for (size_t i = lo; i < hi; ++i) {
-      const Line& ln = t->lines[i];
-      const uint64_t idx = (uint64_t)t->first_index + i;
+      const Line& ln = S.lines[i];
+      const uint64_t idx = (uint64_t)S.first_index + i;
       if (ln.hclass == H_PROBLEM) {
         put_uint(idx, o[GRIMB_OUT_PROBLEM]);
         o[GRIMB_OUT_PROBLEM] += ',';
@@ -826,7 +1129,7 @@ extern "C" int grimb_text_format(GrimbText* t, const GrimbConfig* cfg, const Gri
           o[GRIMB_OUT_MISS] += ln.sid;
           o[GRIMB_OUT_MISS] += '\n';
         }
-        t->format_compact(ln, c, res->words, cfg, o);
+        t->format_compact(S, ln, c, res->words, cfg, o);
         continue;
       }
       const GrimbSubjectResult& r = c.off == 0xFFFFFFFFu ? kNoRecord : res->general[c.off];
@@ -838,11 +1141,9 @@ extern "C" int grimb_text_format(GrimbText* t, const GrimbConfig* cfg, const Gri
         o[GRIMB_OUT_MISS] += ln.sid;
         o[GRIMB_OUT_MISS] += '\n';
       }
-      t->format_subject(ln, r, res->hap_rows, res->pop_rows, cfg, o);
+      t->format_subject(S, ln, r, res->hap_rows, res->pop_rows, cfg, o);
     }
   });
-  out->pair_evals = res->totals ? res->totals[4] : 0;
-  for (int k = 0; k < 4; ++k) out->plan_count[k] = 0;
   // concatenate the pieces of every output in thread order, the copies themselves in parallel
   std::vector<size_t> offs((size_t)nt * 6, 0);
   for (int k = 0; k < 6; ++k) {
@@ -851,53 +1152,48 @@ extern "C" int grimb_text_format(GrimbText* t, const GrimbConfig* cfg, const Gri
       offs[(size_t)th * 6 + k] = n;
       n += parts[(size_t)th * 6 + k].size();
     }
-    if (t->out[k].size() < n) t->out[k].resize(n);   // grow-only buffer; size[k] carries the valid length
-    out->data[k] = t->out[k].data();
-    out->size[k] = (int64_t)n;
+    if (S.out[k].size() < n) S.out[k].resize(n);   // grow-only buffer; out_size[k] carries the valid length
+    S.out_size[k] = (int64_t)n;
   }
   t->parallel((size_t)nt, [&](int, size_t lo, size_t hi) {
     for (size_t th = lo; th < hi; ++th)
       for (int k = 0; k < 6; ++k) {
         const std::string& ps = parts[th * 6 + k];
-        if (!ps.empty()) memcpy(&t->out[k][offs[th * 6 + k]], ps.data(), ps.size());
+        if (!ps.empty()) memcpy(&S.out[k][offs[th * 6 + k]], ps.data(), ps.size());
       }
   });
+  for (int k = 0; k < 4; ++k) S.plan_count[k] = 0;
   for (int th = 0; th < nt; ++th)
-    for (int k = 0; k < 4; ++k) out->plan_count[k] += plans[(size_t)th * 4 + k];
-  out->n_lines = (int64_t)S;
+    for (int k = 0; k < 4; ++k) S.plan_count[k] += plans[(size_t)th * 4 + k];
+  S.sec_fmt = secs(t0, clk::now());
   return GRIMB_OK;
 }
 
-extern "C" int grimb_impute_text(GrimbText* t, GrimbEngine* const* engines, int32_t n_engines, const GrimbConfig* cfg,
-                                 const char* text, int64_t len, int64_t first_line_index, GrimbTextOut* out) {
-  if (!t || !engines || n_engines < 1 || !cfg || !out) return tfail(GRIMB_E_ARG, "null argument");
-  using clk = std::chrono::steady_clock;
+// One ABI call per workspace tier.  Tier 0 takes the whole batch and its results are used straight from
+// the pinned staging buffers; only when some subject overflowed its workspace (rare) are the tiers'
+// results merged into one set of arrays first.  Leaves S.fin / S.totals[4] (pair evaluations) / S.retries.
+int run_slot(GrimbText* t, Slot& S, GrimbEngine* const* engines, int32_t n_engines, const GrimbConfig* cfg) {
   auto t0 = clk::now();
-  GrimbBatch b;
-  int rc = grimb_text_tokenise(t, cfg, text, len, first_line_index, &b);
-  if (rc) return rc;
-  auto t1 = clk::now();
-  const size_t S = (size_t)b.n_subjects;
+  const GrimbBatch& b = S.batch;
+  const size_t NS = (size_t)b.n_subjects;
   const int L = t->L;
-  // One ABI call per workspace tier.  Tier 0 takes the whole batch and its results are formatted straight
-  // from the pinned staging buffers; only when some subject overflowed its workspace (rare) are the tiers'
-  // results merged into one set of arrays first.
-  std::vector<GrimbCompact> m_compact;
-  std::vector<uint64_t> m_words;
-  std::vector<GrimbSubjectResult> m_general;
-  std::vector<GrimbHapRow> m_hap;
-  std::vector<GrimbPopRow> m_pop;
+  S.m_compact.clear();
+  S.m_words.clear();
+  S.m_general.clear();
+  S.m_hap.clear();
+  S.m_pop.clear();
   std::vector<uint32_t> todo;
-  int64_t retries = 0, evals = 0;
+  int64_t evals = 0;
   int64_t tot[6] = {0, 0, 0, 0, 0, 0};
-  GrimbResults fin;
-  memset(&fin, 0, sizeof(fin));
+  S.retries = 0;
+  memset(&S.fin, 0, sizeof(S.fin));
+  int rc = GRIMB_OK;
   for (int tier = 0; tier < n_engines && (tier == 0 || !todo.empty()); ++tier) {
     // gather the sub-batch (tier 0: the whole batch as is)
     GrimbBatch sb = b;
     std::vector<uint16_t> g_typed, g_counts, g_all;
     std::vector<uint32_t> g_off, g_prior;
-    const size_t n = tier == 0 ? S : todo.size();
+    const size_t n = tier == 0 ? NS : todo.size();
     if (tier > 0) {
       g_typed.resize(n);
       g_counts.resize(n * (size_t)L * 2);
@@ -927,19 +1223,19 @@ extern "C" int grimb_impute_text(GrimbText* t, GrimbEngine* const* engines, int3
       sb.prior_index = g_prior.data();
     }
     // pinned, grow-only staging; capacities follow what the previous call needed per subject (+25 %)
-    GrimbCompact* rc_ = (GrimbCompact*)t->hb_compact.reserve((n + 1) * sizeof(GrimbCompact));
+    GrimbCompact* rc_ = (GrimbCompact*)S.hb_compact.reserve((n + 1) * sizeof(GrimbCompact));
     int64_t cap[4];
     for (int k = 0; k < 4; ++k) cap[k] = std::max<int64_t>(1024, (int64_t)((double)n * t->per_subject[k] * 1.25) + 64);
     GrimbResults r;
     for (;;) {
       r.compact = rc_;
-      r.words = (uint64_t*)t->hb_words.reserve((size_t)cap[0] * 8);
+      r.words = (uint64_t*)S.hb_words.reserve((size_t)cap[0] * 8);
       r.word_capacity = cap[0];
-      r.general = (GrimbSubjectResult*)t->hb_general.reserve((size_t)cap[1] * sizeof(GrimbSubjectResult));
+      r.general = (GrimbSubjectResult*)S.hb_general.reserve((size_t)cap[1] * sizeof(GrimbSubjectResult));
       r.general_capacity = cap[1];
-      r.hap_rows = (GrimbHapRow*)t->hb_hap.reserve((size_t)cap[2] * sizeof(GrimbHapRow));
+      r.hap_rows = (GrimbHapRow*)S.hb_hap.reserve((size_t)cap[2] * sizeof(GrimbHapRow));
       r.hap_capacity = cap[2];
-      r.pop_rows = (GrimbPopRow*)t->hb_pop.reserve((size_t)cap[3] * sizeof(GrimbPopRow));
+      r.pop_rows = (GrimbPopRow*)S.hb_pop.reserve((size_t)cap[3] * sizeof(GrimbPopRow));
       r.pop_capacity = cap[3];
       r.totals = tot;
       if (!rc_ || !r.words || !r.general || !r.hap_rows || !r.pop_rows) return tfail(GRIMB_E_NOMEM, "host staging allocation failed");
@@ -954,7 +1250,7 @@ extern "C" int grimb_impute_text(GrimbText* t, GrimbEngine* const* engines, int3
     if (tier == 0 && n > 0)
       for (int k = 0; k < 4; ++k) t->per_subject[k] = std::max(k == 1 ? 0.01 : 0.1, (double)tot[k] / (double)n);
     evals += tot[4];
-    // subjects whose workspace overflowed (counted in parallel: the records are only 16 bytes each)
+    // subjects whose workspace overflowed (found in parallel: the records are only 16 bytes each)
     std::vector<std::vector<uint32_t>> again_t((size_t)t->n_threads);
     t->parallel(n, [&](int th, size_t lo, size_t hi) {
       for (size_t k = lo; k < hi; ++k)
@@ -963,22 +1259,22 @@ extern "C" int grimb_impute_text(GrimbText* t, GrimbEngine* const* engines, int3
     std::vector<uint32_t> again;
     for (auto& v : again_t) again.insert(again.end(), v.begin(), v.end());
     if (tier == 0 && again.empty()) {
-      fin = r;   // the usual case: format from the staging buffers
+      S.fin = r;   // the usual case: format from the staging buffers
       break;
     }
-    // merge this tier into the final arrays, re-basing the offsets
-    if (tier == 0) m_compact.assign(rc_, rc_ + n);
-    const uint32_t wbase = (uint32_t)m_words.size(), gbase = (uint32_t)m_general.size();
-    const uint64_t hbase = m_hap.size(), pbase = m_pop.size();
-    m_words.insert(m_words.end(), r.words, r.words + tot[0]);
+    // merge this tier into the slot's arrays, re-basing the offsets
+    if (tier == 0) S.m_compact.assign(rc_, rc_ + n);
+    const uint32_t wbase = (uint32_t)S.m_words.size(), gbase = (uint32_t)S.m_general.size();
+    const uint64_t hbase = S.m_hap.size(), pbase = S.m_pop.size();
+    S.m_words.insert(S.m_words.end(), r.words, r.words + tot[0]);
     for (int64_t k = 0; k < tot[1]; ++k) {
       GrimbSubjectResult o = r.general[k];
       o.hap_off += hbase;
       o.pop_off += pbase;
-      m_general.push_back(o);
+      S.m_general.push_back(o);
     }
-    m_hap.insert(m_hap.end(), r.hap_rows, r.hap_rows + tot[2]);
-    m_pop.insert(m_pop.end(), r.pop_rows, r.pop_rows + tot[3]);
+    S.m_hap.insert(S.m_hap.end(), r.hap_rows, r.hap_rows + tot[2]);
+    S.m_pop.insert(S.m_pop.end(), r.pop_rows, r.pop_rows + tot[3]);
     for (size_t k = 0; k < n; ++k) {
       GrimbCompact c = rc_[k];
       if (c.status == GRIMB_ST_WORKSPACE) continue;
@@ -987,25 +1283,370 @@ extern "C" int grimb_impute_text(GrimbText* t, GrimbEngine* const* engines, int3
       } else {
         c.off += wbase;
       }
-      m_compact[tier == 0 ? k : todo[k]] = c;
+      S.m_compact[tier == 0 ? k : todo[k]] = c;
     }
-    retries += (int64_t)again.size();
+    S.retries += (int64_t)again.size();
     todo.swap(again);
-    fin.compact = m_compact.data();
-    fin.words = m_words.data();
-    fin.general = m_general.data();
-    fin.hap_rows = m_hap.data();
-    fin.pop_rows = m_pop.data();
+    S.fin.compact = S.m_compact.data();
+    S.fin.words = S.m_words.data();
+    S.fin.general = S.m_general.data();
+    S.fin.hap_rows = S.m_hap.data();
+    S.fin.pop_rows = S.m_pop.data();
   }
   if (!todo.empty()) return tfail(GRIMB_E_NOMEM, "a subject exceeds the largest workspace tier");
-  auto t2 = clk::now();
-  int64_t ftot[6] = {0, 0, 0, 0, evals, 0};
-  fin.totals = ftot;
-  rc = grimb_text_format(t, cfg, &fin, out);
-  auto t3 = clk::now();
-  out->workspace_retries = retries;
-  out->seconds_tokenise = std::chrono::duration<double>(t1 - t0).count();
-  out->seconds_gpu = std::chrono::duration<double>(t2 - t1).count();
-  out->seconds_format = std::chrono::duration<double>(t3 - t2).count();
-  return rc;
+  S.totals[4] = evals;
+  S.fin.totals = S.totals;
+  S.sec_gpu = secs(t0, clk::now());
+  return GRIMB_OK;
+}
+
+void fill_out(const Slot& S, GrimbTextOut* out) {
+  for (int k = 0; k < 6; ++k) {
+    out->data[k] = S.out[k].data();
+    out->size[k] = S.out_size[k];
+  }
+  out->n_lines = (int64_t)S.lines.size();
+  for (int k = 0; k < 4; ++k) out->plan_count[k] = S.plan_count[k];
+}
+
+}  // namespace
+
+extern "C" int grimb_text_tokenise(GrimbText* t, const GrimbConfig* cfg, const char* text, int64_t len,
+                                   int64_t first_line_index, GrimbBatch* b) {
+  if (!t || !cfg || !text || !b || len < 0) return tfail(GRIMB_E_ARG, "null argument");
+  int rc = tokenise_slot(t, t->slot0, cfg, text, len, first_line_index, false);
+  if (rc) return rc;
+  *b = t->slot0.batch;
+  return GRIMB_OK;
+}
+
+extern "C" int grimb_text_format(GrimbText* t, const GrimbConfig* cfg, const GrimbResults* res, GrimbTextOut* out) {
+  if (!t || !cfg || !res || !out || !res->compact) return tfail(GRIMB_E_ARG, "null argument");
+  int rc = format_slot(t, t->slot0, cfg, res);
+  if (rc) return rc;
+  fill_out(t->slot0, out);
+  out->pair_evals = res->totals ? res->totals[4] : 0;
+  return GRIMB_OK;
+}
+
+extern "C" int grimb_impute_text(GrimbText* t, GrimbEngine* const* engines, int32_t n_engines, const GrimbConfig* cfg,
+                                 const char* text, int64_t len, int64_t first_line_index, GrimbTextOut* out) {
+  if (!t || !engines || n_engines < 1 || !cfg || !text || !out || len < 0) return tfail(GRIMB_E_ARG, "null argument");
+  Slot& S = t->slot0;
+  int rc = tokenise_slot(t, S, cfg, text, len, first_line_index, true);   // `text` outlives this call
+  if (rc) return rc;
+  rc = run_slot(t, S, engines, n_engines, cfg);
+  if (rc) return rc;
+  rc = format_slot(t, S, cfg, &S.fin);
+  if (rc) return rc;
+  fill_out(S, out);
+  out->pair_evals = S.totals[4];
+  out->workspace_retries = S.retries;
+  out->seconds_tokenise = S.sec_tok;
+  out->seconds_gpu = S.sec_gpu;
+  out->seconds_format = S.sec_fmt;
+  return GRIMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// File pipeline: what Imputation.impute_file (reference impute.py:1985-2155) does for a whole
+// input file, as four overlapped stages over chunks of lines -- tokenise(c+1) | GPU(c) |
+// format(c-1) | write(c-2) -- each on its own host thread (the tokeniser and the formatter fan out
+// over worker threads themselves).  The input is memory-mapped, never copied.
+// ------------------------------------------------------------------------------------------
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
+
+namespace {
+
+struct Channel {   // a small blocking queue of slot indices; -1 closes it
+  std::mutex m;
+  std::condition_variable cv;
+  std::deque<int> q;
+  void push(int v) {
+    {
+      std::lock_guard<std::mutex> g(m);
+      q.push_back(v);
+    }
+    cv.notify_one();
+  }
+  int pop() {
+    std::unique_lock<std::mutex> g(m);
+    cv.wait(g, [&] { return !q.empty(); });
+    int v = q.front();
+    q.pop_front();
+    return v;
+  }
+};
+
+bool write_all(int fd, const char* p, size_t n) {
+  while (n) {
+    ssize_t w = write(fd, p, n);
+    if (w < 0) {
+      if (errno == EINTR) continue;
+      return false;
+    }
+    p += w;
+    n -= (size_t)w;
+  }
+  return true;
+}
+
+// first line start at or after `pos` (a line starts at 0 or right after a '\n')
+size_t line_start_at(const char* p, size_t n, size_t pos) {
+  if (pos == 0) return 0;
+  if (pos >= n) return n;
+  const void* q = memchr(p + pos - 1, '\n', n - (pos - 1));
+  return q ? (size_t)((const char*)q - p) + 1 : n;
+}
+
+}  // namespace
+
+extern "C" int grimb_file_count_lines(const char* path, int64_t byte_lo, int64_t byte_hi, int32_t n_threads,
+                                      int64_t* n_lines, int64_t* lo_adj, int64_t* hi_adj) {
+  if (!path || !n_lines) return tfail(GRIMB_E_ARG, "null argument");
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) return tfail(GRIMB_E_ARG, std::string("cannot open ") + path);
+  struct stat st;
+  if (fstat(fd, &st) != 0) {
+    close(fd);
+    return tfail(GRIMB_E_ARG, "fstat failed");
+  }
+  const size_t n = (size_t)st.st_size;
+  *n_lines = 0;
+  if (lo_adj) *lo_adj = 0;
+  if (hi_adj) *hi_adj = 0;
+  if (n == 0) {
+    close(fd);
+    return GRIMB_OK;
+  }
+  const char* p = (const char*)mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) return tfail(GRIMB_E_NOMEM, "mmap failed");
+  const size_t lo = line_start_at(p, n, (size_t)std::max<int64_t>(0, byte_lo));
+  const size_t hi = byte_hi < 0 || (size_t)byte_hi >= n ? n : line_start_at(p, n, (size_t)byte_hi);
+  int nt = n_threads > 0 ? n_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+  std::vector<int64_t> cnt((size_t)nt, 0);
+  std::vector<std::thread> th;
+  for (int k = 0; k < nt; ++k)
+    th.emplace_back([&, k]() {
+      const size_t a = lo + (hi - lo) * (size_t)k / (size_t)nt, b = lo + (hi - lo) * (size_t)(k + 1) / (size_t)nt;
+      int64_t c = 0;
+      const char* q = p + a;
+      const char* e = p + b;
+      while (q < e) {
+        const void* f = memchr(q, '\n', (size_t)(e - q));
+        if (!f) break;
+        ++c;
+        q = (const char*)f + 1;
+      }
+      cnt[k] = c;
+    });
+  for (auto& x : th) x.join();
+  int64_t total = 0;
+  for (int64_t c : cnt) total += c;
+  if (hi > lo && p[hi - 1] != '\n') ++total;   // an unterminated last line
+  munmap((void*)p, n);
+  *n_lines = total;
+  if (lo_adj) *lo_adj = (int64_t)lo;
+  if (hi_adj) *hi_adj = (int64_t)hi;
+  return GRIMB_OK;
+}
+
+extern "C" int grimb_file_write_at(const char* path, int64_t offset, const void* data, int64_t size) {
+  if (!path || (!data && size) || offset < 0 || size < 0) return tfail(GRIMB_E_ARG, "bad argument");
+  int fd = open(path, O_WRONLY | O_CREAT, 0644);
+  if (fd < 0) return tfail(GRIMB_E_ARG, std::string("cannot open ") + path);
+  const char* p = (const char*)data;
+  int64_t done = 0;
+  while (done < size) {
+    ssize_t w = pwrite(fd, p + done, (size_t)(size - done), (off_t)(offset + done));
+    if (w < 0) {
+      if (errno == EINTR) continue;
+      close(fd);
+      return tfail(GRIMB_E_ARG, std::string("write failed: ") + path);
+    }
+    done += w;
+  }
+  close(fd);
+  return GRIMB_OK;
+}
+
+extern "C" int grimb_impute_file(GrimbText* t, GrimbEngine* const* engines, int32_t n_engines, const GrimbConfig* cfg,
+                                 const char* in_path, int64_t byte_lo, int64_t byte_hi, int64_t first_line_index,
+                                 const char* const* out_paths, int64_t chunk_bytes, GrimbTextOut* out, GrimbFileStats* stats) {
+  if (!t || !engines || n_engines < 1 || !cfg || !in_path || !out || !stats) return tfail(GRIMB_E_ARG, "null argument");
+  auto t_begin = clk::now();
+  memset(stats, 0, sizeof(*stats));
+  memset(out, 0, sizeof(*out));
+  int fd = open(in_path, O_RDONLY);
+  if (fd < 0) return tfail(GRIMB_E_ARG, std::string("cannot open ") + in_path);
+  struct stat st;
+  if (fstat(fd, &st) != 0) {
+    close(fd);
+    return tfail(GRIMB_E_ARG, "fstat failed");
+  }
+  const size_t fsize = (size_t)st.st_size;
+  const char* base = nullptr;
+  if (fsize) {
+    base = (const char*)mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (base == MAP_FAILED) {
+      close(fd);
+      return tfail(GRIMB_E_NOMEM, "mmap of the input failed");
+    }
+    madvise((void*)base, fsize, MADV_SEQUENTIAL);
+  }
+  close(fd);
+  const size_t lo = fsize ? line_start_at(base, fsize, (size_t)std::max<int64_t>(0, byte_lo)) : 0;
+  const size_t hi = !fsize ? 0 : (byte_hi < 0 || (size_t)byte_hi >= fsize ? fsize : line_start_at(base, fsize, (size_t)byte_hi));
+  // outputs: a path = streamed to that file (created / truncated here); NULL = kept in memory and returned
+  int ofd[6];
+  for (int k = 0; k < 6; ++k) {
+    ofd[k] = -1;
+    t->file_acc[k].clear();
+    if (out_paths && out_paths[k]) {
+      ofd[k] = open(out_paths[k], O_WRONLY | O_CREAT | O_TRUNC, 0644);
+      if (ofd[k] < 0) {
+        for (int j = 0; j < k; ++j)
+          if (ofd[j] >= 0) close(ofd[j]);
+        if (fsize) munmap((void*)base, fsize);
+        return tfail(GRIMB_E_ARG, std::string("cannot create ") + out_paths[k]);
+      }
+    }
+  }
+  if (chunk_bytes <= 0) chunk_bytes = 16 << 20;
+  constexpr int NSLOT = 4;
+  if (t->pipe.size() < (size_t)NSLOT)
+    for (size_t k = t->pipe.size(); k < (size_t)NSLOT; ++k) t->pipe.emplace_back(new Slot());
+  Channel free_q, to_gpu, to_fmt, to_write;
+  for (int k = 0; k < NSLOT; ++k) free_q.push(k);
+  std::mutex err_m;
+  int err_rc = GRIMB_OK;
+  std::string err_msg;
+  auto set_err = [&](int rc) {
+    std::lock_guard<std::mutex> g(err_m);
+    if (err_rc == GRIMB_OK) {
+      err_rc = rc;
+      err_msg = grimb_last_error();   // the failing thread's message
+    }
+  };
+  auto failed = [&]() {
+    std::lock_guard<std::mutex> g(err_m);
+    return err_rc != GRIMB_OK;
+  };
+  double s_tok = 0, s_gpu = 0, s_fmt = 0, s_wr = 0;
+  std::thread th_tok([&]() {
+    size_t pos = lo;
+    int64_t first = first_line_index;
+    while (pos < hi && !failed()) {
+      size_t e = pos + (size_t)chunk_bytes;
+      e = e >= hi ? hi : line_start_at(base, fsize, e);
+      if (e > hi) e = hi;
+      const int k = free_q.pop();
+      Slot& S = *t->pipe[(size_t)k];
+      int rc = tokenise_slot(t, S, cfg, base + pos, (int64_t)(e - pos), first, true);
+      if (rc) {
+        set_err(rc);
+        free_q.push(k);
+        break;
+      }
+      s_tok += S.sec_tok;
+      first += (int64_t)S.lines.size();
+      pos = e;
+      to_gpu.push(k);
+    }
+    to_gpu.push(-1);
+  });
+  std::thread th_gpu([&]() {
+    for (;;) {
+      const int k = to_gpu.pop();
+      if (k < 0) break;
+      Slot& S = *t->pipe[(size_t)k];
+      if (!failed()) {
+        int rc = run_slot(t, S, engines, n_engines, cfg);
+        if (rc) set_err(rc);
+        s_gpu += S.sec_gpu;
+      }
+      to_fmt.push(k);
+    }
+    to_fmt.push(-1);
+  });
+  std::thread th_fmt([&]() {
+    for (;;) {
+      const int k = to_fmt.pop();
+      if (k < 0) break;
+      Slot& S = *t->pipe[(size_t)k];
+      if (!failed()) {
+        int rc = format_slot(t, S, cfg, &S.fin);
+        if (rc) set_err(rc);
+        s_fmt += S.sec_fmt;
+      }
+      to_write.push(k);
+    }
+    to_write.push(-1);
+  });
+  std::thread th_wr([&]() {
+    for (;;) {
+      const int k = to_write.pop();
+      if (k < 0) break;
+      Slot& S = *t->pipe[(size_t)k];
+      if (!failed()) {
+        auto w0 = clk::now();
+        // the six outputs of the chunk in parallel: streamed to their files, or appended in memory
+        std::vector<std::thread> ws;
+        bool ok[6] = {true, true, true, true, true, true};
+        for (int o = 0; o < 6; ++o) {
+          if (S.out_size[o] == 0) continue;
+          ws.emplace_back([&, o]() {
+            if (ofd[o] >= 0) ok[o] = write_all(ofd[o], S.out[o].data(), (size_t)S.out_size[o]);
+            else t->file_acc[o].append(S.out[o].data(), (size_t)S.out_size[o]);
+          });
+        }
+        for (auto& x : ws) x.join();
+        for (int o = 0; o < 6; ++o)
+          if (!ok[o]) {
+            tfail(GRIMB_E_ARG, "write to an output file failed");
+            set_err(GRIMB_E_ARG);
+          }
+        stats->n_lines += (int64_t)S.lines.size();
+        stats->pair_evals += S.totals[4];
+        stats->workspace_retries += S.retries;
+        for (int q = 0; q < 4; ++q) stats->plan_count[q] += S.plan_count[q];
+        for (int o = 0; o < 6; ++o) stats->out_bytes[o] += S.out_size[o];
+        stats->n_chunks += 1;
+        s_wr += secs(w0, clk::now());
+      }
+      free_q.push(k);
+    }
+  });
+  th_tok.join();
+  th_gpu.join();
+  th_fmt.join();
+  th_wr.join();
+  for (int k = 0; k < 6; ++k)
+    if (ofd[k] >= 0) close(ofd[k]);
+  if (fsize) munmap((void*)base, fsize);
+  if (err_rc != GRIMB_OK) return tfail(err_rc, err_msg);
+  for (int k = 0; k < 6; ++k) {
+    out->data[k] = t->file_acc[k].data();
+    out->size[k] = ofd[k] >= 0 ? 0 : (int64_t)t->file_acc[k].size();
+  }
+  out->n_lines = stats->n_lines;
+  out->pair_evals = stats->pair_evals;
+  out->workspace_retries = stats->workspace_retries;
+  for (int q = 0; q < 4; ++q) out->plan_count[q] = stats->plan_count[q];
+  out->seconds_tokenise = stats->seconds_tokenise = s_tok;
+  out->seconds_gpu = stats->seconds_gpu = s_gpu;
+  out->seconds_format = stats->seconds_format = s_fmt;
+  stats->seconds_write = s_wr;
+  stats->in_bytes = (int64_t)(hi - lo);
+  stats->seconds_total = secs(t_begin, clk::now());
+  return GRIMB_OK;
 }

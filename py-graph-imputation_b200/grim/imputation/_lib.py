@@ -144,6 +144,15 @@ class TextOut(C.Structure):
     ]
 
 
+class FileStats(C.Structure):
+    _fields_ = [
+        ("n_lines", C.c_int64), ("n_chunks", C.c_int64), ("in_bytes", C.c_int64), ("pair_evals", C.c_int64),
+        ("workspace_retries", C.c_int64), ("plan_count", C.c_int64 * 4), ("out_bytes", C.c_int64 * 6),
+        ("seconds_total", C.c_double), ("seconds_tokenise", C.c_double), ("seconds_gpu", C.c_double),
+        ("seconds_format", C.c_double), ("seconds_write", C.c_double),
+    ]
+
+
 OUT_KEYS = ("umug", "umug_pops", "pmug", "pmug_pops", "miss", "problem")  # GRIMB_OUT_* order
 
 _LIB = {}
@@ -196,6 +205,12 @@ def load(kw=1):
     lib.grimb_text_format.argtypes = [C.c_void_p, C.POINTER(Config), C.POINTER(Results), C.POINTER(TextOut)]
     lib.grimb_impute_text.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(Config), C.c_char_p,
                                       C.c_int64, C.c_int64, C.POINTER(TextOut)]
+    lib.grimb_impute_file.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(Config), C.c_char_p,
+                                      C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_char_p), C.c_int64,
+                                      C.POINTER(TextOut), C.POINTER(FileStats)]
+    lib.grimb_file_count_lines.argtypes = [C.c_char_p, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_int64),
+                                           C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.grimb_file_write_at.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_int64]
     if lib.grimb_abi_version() != 4:
         raise RuntimeError("libgrimb200.so ABI mismatch")
     _LIB[kw] = lib
@@ -214,4 +229,5 @@ EXPORTED = [
     "grimb_tables_image_copy", "grimb_tables_from_image", "grimb_engine_create", "grimb_engine_free", "grimb_engine_launches", "grimb_engine_kernel_ms",
     "grimb_impute_device", "grimb_impute_device_async", "grimb_impute_finish", "grimb_impute_host",
     "grimb_text_create", "grimb_text_free", "grimb_text_tokenise", "grimb_text_format", "grimb_impute_text",
+    "grimb_impute_file", "grimb_file_count_lines", "grimb_file_write_at",
 ]

@@ -673,11 +673,55 @@ class Imputation(object):
             self.stats[k] = self.stats.get(k, 0.0) + v
         return {k: C.string_at(out.data[i], out.size[i]) for i, k in enumerate(_lib.OUT_KEYS)}
 
+    def impute_file_native(self, in_path, out_paths=None, byte_lo=0, byte_hi=-1, first_index=0, chunk_bytes=0):
+        """The whole file (or the lines starting in [byte_lo, byte_hi)) through grimb_impute_file: memory-mapped
+        input, tokenise | GPU | format | write overlapped on host threads.  out_paths: dict key -> path of the
+        outputs to stream to files; the others are returned as bytes.  -> (dict of bytes, _lib.FileStats)."""
+        lib = self.netGraph.lib
+        t = self._text_handle()
+        chunk_bytes = chunk_bytes or int(os.environ.get("GRIMB_FILE_CHUNK", "0"))
+        engines = (C.c_void_p * len(self.workspaces))(*[self.netGraph.engine(w) for w in self.workspaces[:1]])
+        n_eng = 1
+        paths = (C.c_char_p * 6)(*[(out_paths[k].encode("utf8") if out_paths and out_paths.get(k) else None)
+                                   for k in _lib.OUT_KEYS])
+        out, st = _lib.TextOut(), _lib.FileStats()
+        while True:
+            rc = lib.grimb_impute_file(t, engines, n_eng, C.byref(self.cfg), in_path.encode("utf8"), byte_lo, byte_hi,
+                                       first_index, paths, chunk_bytes, C.byref(out), C.byref(st))
+            if rc == -3 and n_eng < len(self.workspaces):   # GRIMB_E_NOMEM: a subject overflowed the last tier
+                engines[n_eng] = self.netGraph.engine(self.workspaces[n_eng])
+                n_eng += 1
+                continue
+            _lib.check(rc, "grimb_impute_file", lib)
+            break
+        self.stats["subjects"] += st.n_lines
+        self.stats["pair_evals"] += st.pair_evals
+        self.stats["workspace_retries"] += st.workspace_retries
+        for k in range(4):
+            self.stats["plan"][k] += st.plan_count[k]
+        for k, v in (("tokenise_seconds", st.seconds_tokenise), ("abi_seconds", st.seconds_gpu),
+                     ("format_seconds", st.seconds_format), ("write_seconds", st.seconds_write)):
+            self.stats[k] = self.stats.get(k, 0.0) + v
+        self._last_file_out = out   # keeps the pointers' owner (the GrimbText) in view; valid until the next call
+        return out, st
+
     def impute_file(self, config, planb=None, em_mr=False, em=False):
         """Reads config["imputation_input_file"], writes the six output files
         (impute.py:1985-2155 of the reference)."""
-        if planb is not None and bool(planb) != bool(config["planb"]):
-            self.cfg.planb = 1 if planb else 0
+        # the planb argument overrides the configuration for this call only (impute.py:1985,2046 of the reference)
+        eff_planb = bool(config["planb"]) if planb is None else bool(planb)
+        saved = (self.cfg.planb, self.config["planb"])
+        self.cfg.planb = 1 if eff_planb else 0
+        if self.config["planb"] != eff_planb:
+            self.config = dict(self.config, planb=eff_planb)   # the numpy front end classifies foreign loci by it
+        try:
+            self._impute_file(config, em_mr, em)
+        finally:
+            self.cfg.planb = saved[0]
+            if self.config["planb"] != saved[1]:
+                self.config = dict(self.config, planb=saved[1])
+
+    def _impute_file(self, config, em_mr, em):
         targets = {"miss": "imputation_out_miss_file", "problem": "imputation_out_problem_file"}
         # the EM-facing modes (hap_pop_pair rows, em, per-subject phase masks) go through the numpy
         # host front end; the C++ text pipeline serves the default mode
@@ -693,16 +737,8 @@ class Imputation(object):
             if config["output_haplotypes"]:
                 targets["pmug"] = "imputation_out_hap_freq_file"
                 targets["pmug_pops"] = "imputation_out_hap_pops_file"
-            outs = {k: open(config[ck], "wb") for k, ck in targets.items()}
-            try:
-                with open(config["imputation_input_file"], "rb") as f:
-                    for chunk, first in self._byte_chunks(f):
-                        texts = self.impute_text(chunk, first)
-                        for k, fo in outs.items():
-                            fo.write(texts[k])
-            finally:
-                for fo in outs.values():
-                    fo.close()
+            # outputs that are switched off are produced empty by the formatter and discarded
+            self.impute_file_native(config["imputation_input_file"], {k: config[ck] for k, ck in targets.items()})
             return
         with open(config["imputation_input_file"]) as f:
             files = self.impute_lines(f, em_mr=em_mr, em=em)

@@ -133,48 +133,63 @@ def _run_impute_sharded(dist, config, hap_pop_pair, graph):
     # the ranks share the host's cores: split them for the C++ tokeniser / formatter threads
     os.environ.setdefault("GRIMB_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
     imputation = Imputation(graph, config)
-    with open(config["imputation_input_file"], "rb") as f:
-        data = f.read()
-    # contiguous byte ranges cut at line boundaries; .miss / .problem rows carry global line indices
-    n = len(data)
-
-    def cut(pos):
-        if pos <= 0:
-            return 0
-        if pos >= n:
-            return n
-        j = data.find(b"\n", pos - 1)
-        return n if j < 0 else j + 1
-
-    lo_b, hi_b = cut(n * rank // world), cut(n * (rank + 1) // world)
-    first = data.count(b"\n", 0, lo_b)
-    if hap_pop_pair or imputation.phase_masks is not None:
-        # EM-facing modes go through the numpy host front end (see Imputation.impute_file)
-        lines = data[lo_b:hi_b].decode("utf8").splitlines(True)
-        rows = imputation.impute_lines(lines, first_index=first, em_mr=hap_pop_pair)
-        mine = {k: "".join(v).encode("utf8") for k, v in rows.items()}
-    else:
-        mine = imputation.impute_text_stream(data[lo_b:hi_b], first_index=first)
-    del data
     targets = {"miss": "imputation_out_miss_file", "problem": "imputation_out_problem_file"}
     if config["output_MUUG"]:
         targets.update(umug="imputation_out_umug_freq_file", umug_pops="imputation_out_umug_pops_file")
     if config["output_haplotypes"]:
         targets.update(pmug="imputation_out_hap_freq_file", pmug_pops="imputation_out_hap_pops_file")
+    in_path = config["imputation_input_file"]
+    size = os.path.getsize(in_path)
+    lib = graph.lib
+    import ctypes as C
+    from .imputation import _lib
+    # every rank takes the lines that START in its byte range of the input (memory-mapped by the library: no
+    # rank reads the whole file); the ranks count their own lines and exchange the counts, because .miss /
+    # .problem rows carry global line indices
+    lo_b, hi_b = size * rank // world, size * (rank + 1) // world
+    n_lines, lo_adj, hi_adj = C.c_int64(), C.c_int64(), C.c_int64()
+    _lib.check(lib.grimb_file_count_lines(in_path.encode("utf8"), lo_b, hi_b if rank + 1 < world else -1, 0,
+                                          C.byref(n_lines), C.byref(lo_adj), C.byref(hi_adj)), "grimb_file_count_lines", lib)
+    counts = [None] * world
+    dist.all_gather_object(counts, int(n_lines.value))
+    first = sum(counts[:rank])
+    if hap_pop_pair or imputation.phase_masks is not None:
+        # EM-facing modes go through the numpy host front end (see Imputation.impute_file)
+        with open(in_path, "rb") as f:
+            f.seek(lo_adj.value)
+            data = f.read(hi_adj.value - lo_adj.value)
+        rows = imputation.impute_lines(data.decode("utf8").splitlines(True), first_index=first, em_mr=hap_pop_pair)
+        mine = {k: "".join(v).encode("utf8") for k, v in rows.items()}
+        ptr = {k: (mine[k], len(mine[k])) for k in targets}
+    else:
+        out, _st = imputation.impute_file_native(in_path, None, lo_b, hi_b if rank + 1 < world else -1, first)
+        ptr = {k: (out.data[i], int(out.size[i])) for i, k in enumerate(_lib.OUT_KEYS) if k in targets}
     # every rank writes its rows straight into the final files at its offset (rank order == input order):
     # only the sizes are exchanged, not the gigabytes of text
     sizes = [None] * world
-    dist.all_gather_object(sizes, {k: len(mine[k]) for k in targets})
+    dist.all_gather_object(sizes, {k: ptr[k][1] for k in targets})
     if rank == 0:
         pathlib.Path(config["imputation_out_path"]).mkdir(parents=False, exist_ok=True)
         for k, ck in targets.items():
             with open(config[ck], "wb") as f:
                 f.truncate(sum(sz[k] for sz in sizes))
     dist.barrier()
-    for k, ck in targets.items():
-        if len(mine[k]):
-            with open(config[ck], "r+b") as f:
-                f.seek(sum(sz[k] for sz in sizes[:rank]))
-                f.write(mine[k])
+    import threading
+    errs = []
+
+    def put(k, ck):
+        data, n = ptr[k]
+        if n:
+            rc = lib.grimb_file_write_at(config[ck].encode("utf8"), sum(sz[k] for sz in sizes[:rank]), data, n)
+            if rc != 0:
+                errs.append((k, rc))
+
+    ths = [threading.Thread(target=put, args=kv) for kv in targets.items()]   # ctypes releases the GIL in the call
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    if errs:
+        raise RuntimeError("writing the output files failed: %s" % errs)
     dist.barrier()
     return graph

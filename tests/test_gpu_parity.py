@@ -265,3 +265,35 @@ def test_em_modes_match_oracle_on_seeded_inputs(mode, tmp_path):
     ref, _ = go.impute_file(conf, graph=_oracle_graph("pop3", conf), lines=lines, em_mr=em_mr)
     for k in goldenlib.KEYS:
         assert out[k] == ref[k], "%s differs" % k
+
+
+@pytest.mark.parametrize("name", ["g5_messy_cau", "g2_edges", "g3_pop3_typed"])
+def test_file_pipeline_many_chunks_files_and_memory(name, tmp_path):
+    """grimb_impute_file: the input cut into many small chunks (tokenise | GPU | format | write overlapped on
+    host threads), outputs streamed to files and, separately, returned in memory for a byte range."""
+    import ctypes as C
+    from grim.imputation import _lib
+    from grim.imputation.impute import Imputation
+    from grim.run_impute_def import load_config
+    table, conf, lines, exp = goldenlib.load_case(name)
+    cfg = load_config(conf)
+    imp = Imputation(_graph(table, conf), cfg)
+    src = str(tmp_path / "in.csv")
+    open(src, "w").write("".join(lines))
+    paths = {k: str(tmp_path / ("out." + k)) for k in goldenlib.KEYS}
+    _out, st = imp.impute_file_native(src, paths, chunk_bytes=2048)
+    assert st.n_chunks > 3 and st.n_lines == len(lines)
+    for k in goldenlib.KEYS:
+        assert open(paths[k]).read() == exp[k], "%s: %s differs" % (name, k)
+    # two byte ranges, kept in memory, global line indices: concatenation == whole file
+    size = len("".join(lines).encode("utf8"))
+    cut = size // 2
+    lib = imp.netGraph.lib
+    n0 = C.c_int64()
+    _lib.check(lib.grimb_file_count_lines(src.encode(), 0, cut, 0, C.byref(n0), None, None), "count")
+    parts = []
+    for lo, hi, first in ((0, cut, 0), (cut, -1, n0.value)):
+        out, _ = imp.impute_file_native(src, None, lo, hi, first, chunk_bytes=4096)
+        parts.append({k: C.string_at(out.data[i], out.size[i]).decode("utf8") for i, k in enumerate(_lib.OUT_KEYS)})
+    for k in goldenlib.KEYS:
+        assert parts[0][k] + parts[1][k] == exp[k], "%s: %s differs (byte ranges)" % (name, k)

@@ -85,3 +85,119 @@ def test_float_formatter_equals_python_repr():
     assert len(rows) == n
     for v, row in zip(vals, rows):
         assert row.split(",")[3] == repr(v), (v, row)
+
+
+def _tokenise_arrays(imp, data, fast):
+    """Batch arrays of grimb_text_tokenise for `data` with the fast path of the tokeniser on or off."""
+    import numpy as np
+    from grim.imputation import _lib
+    os.environ["GRIMB_TEXT_FAST"] = "1" if fast else "0"
+    try:
+        imp._text = None
+        t = imp._text_handle()          # the switch is read when the GrimbText is created
+    finally:
+        os.environ.pop("GRIMB_TEXT_FAST", None)
+    lib = _lib.load()
+    b = _lib.Batch()
+    _lib.check(lib.grimb_text_tokenise(t, C.byref(imp.cfg), data, len(data), 7, C.byref(b)), "tokenise")
+    S, L = b.n_subjects, imp.L
+
+    def arr(ptr, n, ct):
+        return None if not ptr else np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,)).copy()
+
+    off = arr(b.allele_off, S + 1, C.c_uint32)
+    counts = arr(b.counts, S * L * 2, C.c_uint16)
+    typed = arr(b.typed_mask, S, C.c_uint16)
+    if counts is None:   # all ones where typed
+        counts = np.repeat(np.array([[(m >> l) & 1 for l in range(L)] for m in typed], np.uint16), 2, axis=1).reshape(-1)
+    pri = arr(b.prior_index, S, C.c_uint32)
+    priors = arr(b.priors, b.n_priors * imp.P * imp.P, C.c_double).reshape(b.n_priors, -1)
+    pm = priors[pri] if pri is not None else np.repeat(priors[:1], S, axis=0)
+    # classification of every line, as the formatter sees it: format an all-skipped result
+    res = _lib.ResultArrays(S, 1)
+    res.compact["status"] = _lib.ST_SKIPPED
+    res.compact["off"] = _lib.NO_RECORD
+    out = _lib.TextOut()
+    _lib.check(lib.grimb_text_format(t, C.byref(imp.cfg), C.byref(res.struct), C.byref(out)), "format")
+    texts = [C.string_at(out.data[i], out.size[i]) for i in range(6)]
+    return {"typed": typed, "counts": counts, "off": off, "alleles": arr(b.alleles, int(off[S]), C.c_uint16), "priors": pm,
+            "texts": texts}
+
+
+@pytest.mark.parametrize("table", ["cau", "pop3"])
+def test_fast_tokeniser_path_equals_the_general_parser(table):
+    """The single-pass fast path of the tokeniser accepts only lines for which it does exactly what the general
+    parser does; everything else falls through.  Same batch arrays, same per-line classification, on clean,
+    ambiguous and deliberately dirty lines (LF and CRLF)."""
+    import numpy as np
+    import synth
+    sys_path = os.path.join(goldenlib.GOLD, "..", "golden")
+    import sys
+    if sys_path not in sys.path:
+        sys.path.insert(0, sys_path)
+    from fuzz_random_tables import dirty
+    name = {"cau": "g5_messy_cau", "pop3": "g3_pop3_messy"}[table]
+    _t, conf, lines, _exp = goldenlib.load_case(name)
+    eg = _setup(table, conf)
+    imp = emu_imputation(eg, load_config(conf))
+    tab = synth.Table(open(conf["freq_file"]).read(), conf["populations"][0])
+    rng = np.random.RandomState(3)
+    races = synth.race_fields(conf["populations"])
+    base = synth.typed_subjects(tab, 400, 1, races) + synth.messy_subjects(tab, 400, 2, races=races) + list(lines)
+    cases = base + dirty(base, rng, synth.LOCI5, False) + dirty(base[:300], rng, synth.LOCI5, True)
+    cases += ["X1,A*01:01+A*02:01^^B*07:02+B*08:01\n", "X2,+A*01:01+A*02:01\n", "X3,A*01:01+A*02:01+A*03:01\n",
+              "X4,A*01:01/A*01:01+A*02:01,CAU,CAU,extra\n", "X5%A*01:01+A*02:01\n", "X6,A*01:01+A*02:01^\n",
+              "X7, A*01:01+A*02:01\n", "X8,A*01:01+A*02:01 ,CAU,CAU \n", "X9,B*07:02+B*08:01^A*01:01+A*02:01\n", "\n",
+              "X10,A*01:01+B*07:02\n", "X11,A*01:01/B*07:02+A*02:01\n", "X12,A*01:01+A*02:01,CAU\n", "X13"]
+    data = "".join(cases).encode("utf8")
+    a = _tokenise_arrays(imp, data, True)
+    b = _tokenise_arrays(imp, data, False)
+    for k in ("typed", "counts", "off", "alleles"):
+        assert np.array_equal(a[k], b[k]), k
+    live = a["typed"] != 0     # the prior of a line that is not imputed is never read (and its index is arbitrary)
+    assert np.array_equal(a["priors"][live], b["priors"][live])
+    assert a["texts"] == b["texts"]
+    assert (a["typed"] != 0).sum() > 1000
+
+
+@pytest.mark.parametrize("tail_newline", [True, False])
+def test_byte_range_line_counts_tile_the_file(tmp_path, tail_newline):
+    """grimb_file_count_lines: what every rank of the sharded public API calls on its byte range -- the ranges,
+    adjusted to line starts, tile the file and the counts add up to the file's line count."""
+    from grim.imputation import _lib
+    lib = _lib.load()
+    rnd = random.Random(11)
+    lines = ["S%d,%s\n" % (i, "x" * rnd.randint(0, 90)) for i in range(5000)] + ["\n", "last,line\n"]
+    text = "".join(lines)
+    if not tail_newline:
+        text = text[:-1]
+    path = str(tmp_path / "in.csv")
+    open(path, "w").write(text)
+    size = len(text)
+    for world in (1, 2, 3, 8, 61):
+        prev_hi, total = 0, 0
+        for rank in range(world):
+            lo, hi = size * rank // world, (size * (rank + 1) // world if rank + 1 < world else -1)
+            n, a, b = C.c_int64(), C.c_int64(), C.c_int64()
+            _lib.check(lib.grimb_file_count_lines(path.encode(), lo, hi, 3, C.byref(n), C.byref(a), C.byref(b)), "count")
+            assert a.value == prev_hi
+            assert n.value == len(text[a.value:b.value].splitlines())
+            prev_hi = b.value
+            total += n.value
+        assert prev_hi == size and total == len(lines)
+    # a range inside one long line holds no line start
+    n, a, b = C.c_int64(), C.c_int64(), C.c_int64()
+    first_len = len(lines[0])
+    _lib.check(lib.grimb_file_count_lines(path.encode(), 1, first_len - 1, 2, C.byref(n), C.byref(a), C.byref(b)), "count")
+    assert n.value == 0 and a.value == b.value == first_len
+
+
+def test_write_at_places_bytes(tmp_path):
+    from grim.imputation import _lib
+    lib = _lib.load()
+    path = str(tmp_path / "out.bin")
+    with open(path, "wb") as f:
+        f.truncate(10)
+    assert lib.grimb_file_write_at(path.encode(), 4, b"abc", 3) == 0
+    assert lib.grimb_file_write_at(path.encode(), 0, b"zz", 2) == 0
+    assert open(path, "rb").read() == b"zz\x00\x00abc\x00\x00\x00"
