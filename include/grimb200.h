@@ -230,7 +230,9 @@ typedef struct {
   /* totals written by the call (host memory, always): entries needed; > capacity => GRIMB_E_CAPACITY.
    * [0] words, [1] general records, [2] hap rows, [3] pop rows, [4] pair evaluations of the whole batch
    * (iterations reaching impute.py:464/573, the metric's second numerator), [5] subjects the
-   * warp-per-subject kernels handed on to the general kernel */
+   * warp-per-subject kernels handed on to the general kernel, [6] hash probes issued, [7] probes answered
+   * with a node, [8] frequency vectors read by the probes' expansions (general and typed kernels; the
+   * single-population fast path issues two probes per kept phase and is not instrumented).  9 entries. */
   int64_t* totals;
 } GrimbResults;
 

@@ -1534,6 +1534,7 @@ k_impute_typed(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, 
   const uint32_t nphase = 1u << (L - 1);
   const uint64_t S = (uint64_t)B.n_subjects;
   unsigned long long evals_sum = 0;   // pair evaluations of the subjects this warp finishes (warp-uniform)
+  unsigned long long n_probes = 0, n_hits = 0, n_vecs = 0;   // of every subject this warp looked at (warp-uniform)
   for (uint64_t s = (uint64_t)blockIdx.x * TY_WARPS + warp; s < S; s += (uint64_t)gridDim.x * TY_WARPS) {
     const uint32_t typed = B.typed_mask[s];
     if (typed == 0) {   // GRIMB_ST_SKIPPED
@@ -1583,6 +1584,8 @@ k_impute_typed(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, 
           }
         const uint32_t node = (kept && known) ? ht_lookup(T, full, key) : GRIMB_NONE;
         const uint32_t hits = __ballot_sync(FULLM, node != GRIMB_NONE);
+        n_probes += __popc(__ballot_sync(FULLM, kept && known));
+        n_hits += __popc(hits);
         uint32_t both = hits & (hits >> 16) & 0xFFFFu;
         while (both) {
           const int b = __ffs(both) - 1;
@@ -1592,6 +1595,7 @@ k_impute_typed(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, 
             break;
           }
           const uint32_t nd1 = __shfl_sync(FULLM, node, b), nd2 = __shfl_sync(FULLM, node, 16 + b);
+          n_vecs += 2;
           double f1 = 0.0, f2 = 0.0;
           if (lane < P) {
             f1 = __ldg(T.freq + (uint64_t)nd1 * P + lane);
@@ -1859,7 +1863,12 @@ k_impute_typed(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, 
     }
     __syncwarp();
   }
-  if (lane == 0 && evals_sum) atomicAdd(O.evals_counter, evals_sum);
+  if (lane == 0) {
+    if (evals_sum) atomicAdd(O.evals_counter, evals_sum);
+    if (n_probes) atomicAdd(O.probe_counters + 0, n_probes);
+    if (n_hits) atomicAdd(O.probe_counters + 1, n_hits);
+    if (n_vecs) atomicAdd(O.probe_counters + 2, n_vecs);
+  }
 }
 
 constexpr int GRIMB_MAX_CHUNKS = 64;
@@ -1878,6 +1887,7 @@ enum {
   CNT_WORDS = 10,
   CNT_GENERAL = 11,
   CNT_EVALS = 12,
+  CNT_PROBES = 13,    // probes issued, probes answered, frequency vectors read (general and typed kernels)
   CNT_N = 16
 };
 
@@ -2092,6 +2102,7 @@ static OutArrays out_arrays(GrimbEngine* e, const GrimbResults& r) {
   O.word_counter = e->d_counters + CNT_WORDS;
   O.general_counter = e->d_counters + CNT_GENERAL;
   O.evals_counter = e->d_counters + CNT_EVALS;
+  O.probe_counters = e->d_counters + CNT_PROBES;
   return O;
 }
 
@@ -2214,6 +2225,9 @@ static int totals_from(const unsigned long long* c, double handed, const GrimbRe
   t[3] = (int64_t)c[CNT_POP];
   t[4] = (int64_t)c[CNT_EVALS];
   t[5] = (int64_t)handed;
+  t[6] = (int64_t)c[CNT_PROBES];
+  t[7] = (int64_t)c[CNT_PROBES + 1];
+  t[8] = (int64_t)c[CNT_PROBES + 2];
   if (t[0] > r->word_capacity || t[1] > r->general_capacity || t[2] > r->hap_capacity || t[3] > r->pop_capacity)
     return fail(GRIMB_E_CAPACITY, "result buffers too small (see GrimbResults.totals)");
   return GRIMB_OK;

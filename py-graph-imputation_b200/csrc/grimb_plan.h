@@ -57,6 +57,8 @@ struct Subject : Ctx {
   GD bool allele_node(int l, uint32_t id, uint32_t& node) const {
     if (id == 0 || id > T.n_alleles[l]) return false;
     node = ht_lookup(T, 1u << l, (hkey)id << T.shift[l]);
+    ++c_probes;
+    if (node != GRIMB_NONE) ++c_hits;
     return node != GRIMB_NONE;
   }
 
@@ -314,7 +316,11 @@ struct Subject : Ctx {
           } else {
             key = T.node_key[sd.filt[dd_first[q]]] & km;
           }
-          if (known) node = ht_lookup(T, tp, key);
+          if (known) {
+            node = ht_lookup(T, tp, key);
+            ++c_probes;
+            if (node != GRIMB_NONE) ++c_hits;
+          }
           if (node != GRIMB_NONE) {
             if (nup == 0) deg = 1;
             else if (nup == 1) {
@@ -565,7 +571,11 @@ struct Subject : Ctx {
           decode(sd, slot, c, ids);
           hkey key;
           uint32_t label;
-          if (pack(ids, keepmask, key, label)) node = ht_lookup(T, label, key);
+          if (pack(ids, keepmask, key, label)) {
+            node = ht_lookup(T, label, key);
+            ++c_probes;
+            if (node != GRIMB_NONE) ++c_hits;
+          }
           for (int t = 0; t < n; ++t)
             if (!(keepmask >> t & 1u)) ex |= (hkey)ids[t] << T.shift[loc[t]];
           if (node != GRIMB_NONE) {
@@ -1008,6 +1018,8 @@ GD void run_subject(Subject& S, const GrimbBatch& B, const OutArrays& O, uint64_
   S.ar_used = 0;
   S.ws_fail = false;
   S.pair_evals = 0;
+  S.c_probes = S.c_hits = 0;
+  S.c_vecs = 0;
   S.plan_c_single = false;
   S.ent_n = 0;
   S.full = (1u << L) - 1u;
@@ -1178,7 +1190,11 @@ GD void run_subject(Subject& S, const GrimbBatch& B, const OutArrays& O, uint64_
   // ---- publish
   g.sync();
   uint64_t evals = g.sum64(S.pair_evals);
+  const uint64_t n_probes = g.sum64((uint64_t)S.c_probes), n_hits = g.sum64((uint64_t)S.c_hits);
   if (g.tid == 0) {
+    if (n_probes) atom_add64(O.probe_counters + 0, (unsigned long long)n_probes);
+    if (n_hits) atom_add64(O.probe_counters + 1, (unsigned long long)n_hits);
+    if (S.c_vecs) atom_add64(O.probe_counters + 2, (unsigned long long)S.c_vecs);
     sh->cnt[4] = tot_u;
     sh->cnt[5] = tot_p;
   }

@@ -90,6 +90,9 @@ struct OutArrays {  // device pointers of GrimbResults + global counters
   unsigned long long* word_counter;      // 8-byte words of SIMPLE / TYPED subjects
   unsigned long long* general_counter;   // GrimbSubjectResult records appended to r.general
   unsigned long long* evals_counter;     // pair evaluations of the whole batch
+  unsigned long long* probe_counters;    // [3] probes issued, probes answered, frequency vectors read
+                                         // (general and typed kernels; the single-population fast path
+                                         // issues 2 probes per kept phase and is not instrumented)
 };
 
 // batch accessors: `counts` and `prior_index` may be NULL (ABI v4: all ones / all zero)
@@ -174,6 +177,8 @@ struct Ctx {
   Entry* ent;
   uint32_t ent_cap, ent_n;
   uint64_t pair_evals;
+  mutable uint32_t c_probes, c_hits;   // per-thread: hash probes issued / answered with a node (metric numerators)
+  uint64_t c_vecs;             // group-wide (thread 0): frequency vectors the probes' expansions read
   bool plan_c_single;  // P_eff = 1 (Plan C: vectors summed over populations)
 
   template <class X>
@@ -313,6 +318,7 @@ struct Ctx {
                        Extra extra, bool scaled, double scale) {
     const int P = T.P;
     uint64_t items = (uint64_t)total * (uint64_t)P;
+    if (g.tid == 0) c_vecs += total;
     for (uint64_t q0 = 0; q0 < items; q0 += g.n) {
       sel_reserve();
       uint64_t q = q0 + g.tid;
@@ -354,7 +360,11 @@ struct Ctx {
           decode(sd, slot, c, ids);
           hkey key;
           uint32_t label;
-          if (pack(ids, (1u << n) - 1u, key, label)) node = ht_lookup(T, label, key);
+          if (pack(ids, (1u << n) - 1u, key, label)) {
+            node = ht_lookup(T, label, key);
+            ++c_probes;
+            if (node != GRIMB_NONE) ++c_hits;
+          }
         }
         if (node != GRIMB_NONE) {
           deg = isfull ? 1u : T.tl_cnt[node];

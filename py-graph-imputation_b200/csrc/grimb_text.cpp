@@ -78,60 +78,81 @@ void split(sv s, char d, std::vector<sv>& out) {
 }
 
 // Python's repr(float) / str(float): shortest round-trip digits, fixed notation iff
-// -4 < decpt <= 16 (Python/pystrtod.c format_float_short, mode 'r')
-void py_float(double x, std::string& out) {
-  if (x == 0.0) {
-    out += std::signbit(x) ? "-0.0" : "0.0";
-    return;
-  }
-  if (std::isnan(x)) { out += "nan"; return; }
-  if (std::isinf(x)) { out += x < 0 ? "-inf" : "inf"; return; }
+// -4 < decpt <= 16 (Python/pystrtod.c format_float_short, mode 'r').  Writes at most 32 bytes.
+int py_float_buf(double x, char* out) {
+  char* o = out;
+  auto lit = [&](const char* t) {
+    size_t n = strlen(t);
+    memcpy(o, t, n);
+    return (int)n;
+  };
+  if (x == 0.0) return lit(std::signbit(x) ? "-0.0" : "0.0");
+  if (std::isnan(x)) return lit("nan");
+  if (std::isinf(x)) return lit(x < 0 ? "-inf" : "inf");
   char buf[48];
   auto r = std::to_chars(buf, buf + sizeof(buf), x, std::chars_format::scientific);
-  sv s(buf, (size_t)(r.ptr - buf));
+  const char* s = buf;
+  size_t n = (size_t)(r.ptr - buf);
   if (s[0] == '-') {
-    out += '-';
-    s.remove_prefix(1);
+    *o++ = '-';
+    ++s;
+    --n;
   }
-  size_t e = s.find('e');
+  size_t e = 0;
+  while (s[e] != 'e') ++e;
   int exp10 = 0;
-  std::from_chars(s.data() + e + 1 + (s[e + 1] == '+' ? 1 : 0), s.data() + s.size(), exp10);
+  std::from_chars(s + e + 1 + (s[e + 1] == '+' ? 1 : 0), s + n, exp10);
   char digits[24];
   int nd = 0;
   for (size_t i = 0; i < e; ++i)
     if (s[i] != '.') digits[nd++] = s[i];
   const int decpt = exp10 + 1;
   if (decpt <= -4 || decpt > 16) {
-    out += digits[0];
+    *o++ = digits[0];
     if (nd > 1) {
-      out += '.';
-      out.append(digits + 1, (size_t)(nd - 1));
+      *o++ = '.';
+      memcpy(o, digits + 1, (size_t)(nd - 1));
+      o += nd - 1;
     }
-    out += 'e';
+    *o++ = 'e';
     int ex = decpt - 1;
-    out += ex < 0 ? '-' : '+';
+    *o++ = ex < 0 ? '-' : '+';
     if (ex < 0) ex = -ex;
     char eb[8];
-    int n = 0;
+    int k = 0;
     do {
-      eb[n++] = (char)('0' + ex % 10);
+      eb[k++] = (char)('0' + ex % 10);
       ex /= 10;
     } while (ex);
-    if (n < 2) eb[n++] = '0';
-    while (n) out += eb[--n];
+    if (k < 2) eb[k++] = '0';
+    while (k) *o++ = eb[--k];
   } else if (decpt <= 0) {
-    out += "0.";
-    out.append((size_t)(-decpt), '0');
-    out.append(digits, (size_t)nd);
+    *o++ = '0';
+    *o++ = '.';
+    memset(o, '0', (size_t)(-decpt));
+    o += -decpt;
+    memcpy(o, digits, (size_t)nd);
+    o += nd;
   } else if (decpt >= nd) {
-    out.append(digits, (size_t)nd);
-    out.append((size_t)(decpt - nd), '0');
-    out += ".0";
+    memcpy(o, digits, (size_t)nd);
+    o += nd;
+    memset(o, '0', (size_t)(decpt - nd));
+    o += decpt - nd;
+    *o++ = '.';
+    *o++ = '0';
   } else {
-    out.append(digits, (size_t)decpt);
-    out += '.';
-    out.append(digits + decpt, (size_t)(nd - decpt));
+    memcpy(o, digits, (size_t)decpt);
+    o += decpt;
+    *o++ = '.';
+    memcpy(o, digits + decpt, (size_t)(nd - decpt));
+    o += nd - decpt;
   }
+  return (int)(o - out);
+}
+
+void py_float(double x, std::string& out) {
+  char b[40];
+  out.append(b, (size_t)py_float_buf(x, b));
 }
 
 void put_uint(uint64_t v, std::string& out) {
@@ -225,7 +246,7 @@ struct GrimbText {
     std::vector<GrimbHapRow> m_hap;
     std::vector<GrimbPopRow> m_pop;
     GrimbResults fin;
-    int64_t totals[6] = {0, 0, 0, 0, 0, 0};
+    int64_t totals[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int64_t retries = 0;
     std::vector<std::string> fmt_parts;   // per-thread pieces of the six outputs (capacity reused)
     std::string out[6];
@@ -441,6 +462,16 @@ struct GrimbText {
   // because every string starts with its locus prefix and the prefixes ascend, the locus of a chunk is
   // that of its first name, and ids are listed locus by locus, side 0 then side 1, duplicates dropped.
   // Anything else returns false with nothing changed, and the general parser takes the line.
+  struct CharClass {   // 0 name character, 1 delimiter of the GL grammar, 2 'g' / 'L' / 'U'
+    uint8_t c[256];
+    CharClass() {
+      memset(c, 0, sizeof(c));
+      c[(unsigned char)'/'] = c[(unsigned char)'+'] = c[(unsigned char)'^'] = 1;
+      c[(unsigned char)'g'] = c[(unsigned char)'L'] = c[(unsigned char)'U'] = 2;
+    }
+  };
+  static inline const CharClass kCharClass{};
+
   bool parse_fast(Slot& S, sv raw_line, Line& ln, int thread) const {
     size_t e = raw_line.size();
     while (e > 0 && py_space((unsigned char)raw_line[e - 1])) --e;
@@ -475,12 +506,9 @@ struct GrimbText {
         const size_t lst = idv.size();
         for (;;) {   // one allele name
           const char* n0 = q;
-          while (q < g1) {
-            const char ch = *q;
-            if (ch == '/' || ch == '+' || ch == '^') break;
-            if (ch == 'g' || ch == 'L' || ch == 'U') goto slow;
-            ++q;
-          }
+          uint8_t cls = 0;
+          while (q < g1 && (cls = kCharClass.c[(unsigned char)*q]) == 0) ++q;
+          if (q < g1 && cls == 2) goto slow;   // a character clean_up_gl reacts to
           if (q == n0) goto slow;
           const NameEnt* ne = find_name(n0, (size_t)(q - n0));
           if (!ne) goto slow;
@@ -512,6 +540,7 @@ struct GrimbText {
       ++q;
       if (q == g1) goto slow;     // trailing '^'
     }
+    ln = Line();
     ln.raw = sv(p, e);
     ln.sid = sv(p, (size_t)(c1 - p));
     ln.has_race = c2 != nullptr;
@@ -539,6 +568,7 @@ struct GrimbText {
     size_t e = raw_line.size();
     while (e > 0 && py_space((unsigned char)raw_line[e - 1])) --e;
     sv raw = raw_line.substr(0, e);
+    ln = Line();
     ln.raw = raw;
     ln.thread = (uint32_t)thread;
     split(raw, raw.find(',') != sv::npos ? ',' : '%', f1);
@@ -705,14 +735,35 @@ struct GrimbText {
     s += '\n';
   }
 
-  void put_pop_row(sv sid, sv x, sv y, double prob, uint32_t k, bool sorted, std::string& s) const {
+  // a probability with its text (most rows of a subject of the single-population path repeat one value)
+  struct ProbText {
+    double v;
+    char t[40];
+    int n;
+  };
+  static void put_row_tail(const ProbText& pt, double prob, uint32_t k, std::string& s) {
+    if (dbits_equal(prob, pt.v)) {
+      s += ',';
+      s.append(pt.t, (size_t)pt.n);
+      s += ',';
+      put_uint(k, s);
+      s += '\n';
+    } else {
+      put_row_tail(prob, k, s);
+    }
+  }
+  static bool dbits_equal(double a, double b) { return memcmp(&a, &b, 8) == 0; }
+
+  void put_pop_row(sv sid, sv x, sv y, double prob, uint32_t k, bool sorted, std::string& s,
+                   const ProbText* pt = nullptr) const {
     if (sorted && y < x) std::swap(x, y);
     s += sid;
     s += ',';
     s += x;
     s += ',';
     s += y;
-    put_row_tail(prob, k, s);
+    if (pt) put_row_tail(*pt, prob, k, s);
+    else put_row_tail(prob, k, s);
   }
 
   // Rows of a subject the warp-per-subject kernels finished (GRIMB_KIND_SIMPLE / GRIMB_KIND_TYPED, ABI v4):
@@ -747,6 +798,9 @@ struct GrimbText {
       memcpy(&d, &u, 8);
       return d;
     };
+    ProbText pt;
+    pt.v = c.total;
+    pt.n = py_float_buf(c.total, pt.t);
     auto pop_pair = [&](uint32_t k, sv& x, sv& y, double& p) {
       if (!pop_code) {
         x = y = sv(pops[0]);
@@ -770,13 +824,13 @@ struct GrimbText {
             s += allele_name(S, l, ids[2 * l + (int)(((phase[k] >> l) & 1u) ^ (uint32_t)side)], ln);
           }
         }
-        put_row_tail(pmug_prob ? dbl(pmug_prob[k]) : c.total, k, s);
+        put_row_tail(pt, pmug_prob ? dbl(pmug_prob[k]) : c.total, k, s);
       }
       for (uint32_t k = 0; k < n_pops; ++k) {
         sv x, y;
         double p;
         pop_pair(k, x, y, p);
-        put_pop_row(ln.sid, x, y, p, k, false, o[GRIMB_OUT_PMUG_POPS]);
+        put_pop_row(ln.sid, x, y, p, k, false, o[GRIMB_OUT_PMUG_POPS], &pt);
       }
     }
     if (cfg->output_umug && has) {
@@ -792,13 +846,13 @@ struct GrimbText {
           s += '+';
           s += y;
         }
-        put_row_tail(c.total, 0, s);
+        put_row_tail(pt, c.total, 0, s);
       }
       for (uint32_t k = 0; k < n_pops; ++k) {
         sv x, y;
         double p;
         pop_pair(k, x, y, p);
-        put_pop_row(ln.sid, x, y, p, k, true, o[GRIMB_OUT_UMUG_POPS]);
+        put_pop_row(ln.sid, x, y, p, k, true, o[GRIMB_OUT_UMUG_POPS], &pt);
       }
     }
   }
@@ -963,7 +1017,7 @@ int tokenise_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const char* tex
   for (int k = 0; k < nt; ++k) nl[k + 1] += nl[k];
   const size_t NS = nl[nt];
   auto tA = clk::now();
-  S.lines.assign(NS, Line());
+  S.lines.resize(NS);   // every Line is reset by the parser that fills it
   S.t_ids.resize((size_t)nt);
   S.t_unk.resize((size_t)nt);
   for (auto& v : S.t_ids) v.clear();
@@ -1073,7 +1127,7 @@ int tokenise_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const char* tex
   b.n_priors = (int32_t)(S.priors.size() / ((size_t)t->P * t->P));
   b.phase_mask = nullptr;   // default phase enumeration; masks are served by the numpy host front end
   S.sec_tok = secs(t0, clk::now());
-  if (getenv("GRIMB_TEXT_TRACE"))
+  if (getenv("GRIMB_TEXT_TRACE") && getenv("GRIMB_TEXT_TRACE")[0] == '2')
     fprintf(stderr, "tokenise: count %.1f ms, parse %.1f ms, seq %.1f ms, fill %.1f ms\n", secs(t0, tA) * 1e3, secs(tA, tB) * 1e3,
             secs(tB, tC) * 1e3, secs(tC, clk::now()) * 1e3);
   return GRIMB_OK;
@@ -1184,8 +1238,9 @@ int run_slot(GrimbText* t, Slot& S, GrimbEngine* const* engines, int32_t n_engin
   S.m_pop.clear();
   std::vector<uint32_t> todo;
   int64_t evals = 0;
-  int64_t tot[6] = {0, 0, 0, 0, 0, 0};
+  int64_t tot[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   S.retries = 0;
+  S.totals[6] = S.totals[7] = S.totals[8] = 0;
   memset(&S.fin, 0, sizeof(S.fin));
   int rc = GRIMB_OK;
   for (int tier = 0; tier < n_engines && (tier == 0 || !todo.empty()); ++tier) {
@@ -1250,6 +1305,7 @@ int run_slot(GrimbText* t, Slot& S, GrimbEngine* const* engines, int32_t n_engin
     if (tier == 0 && n > 0)
       for (int k = 0; k < 4; ++k) t->per_subject[k] = std::max(k == 1 ? 0.01 : 0.1, (double)tot[k] / (double)n);
     evals += tot[4];
+    for (int k = 6; k < 9; ++k) S.totals[k] += tot[k];
     // subjects whose workspace overflowed (found in parallel: the records are only 16 bytes each)
     std::vector<std::vector<uint32_t>> again_t((size_t)t->n_threads);
     t->parallel(n, [&](int th, size_t lo, size_t hi) {
@@ -1648,5 +1704,8 @@ extern "C" int grimb_impute_file(GrimbText* t, GrimbEngine* const* engines, int3
   stats->seconds_write = s_wr;
   stats->in_bytes = (int64_t)(hi - lo);
   stats->seconds_total = secs(t_begin, clk::now());
+  if (getenv("GRIMB_TEXT_TRACE"))
+    fprintf(stderr, "impute_file: %lld lines, %lld chunks, %.3f s wall; busy: tokenise %.3f, gpu %.3f, format %.3f, write %.3f s\n",
+            (long long)stats->n_lines, (long long)stats->n_chunks, stats->seconds_total, s_tok, s_gpu, s_fmt, s_wr);
   return GRIMB_OK;
 }

@@ -92,14 +92,15 @@ class Results(C.Structure):
 
 class ResultArrays(object):
     """Host result buffers of one ABI call (numpy) + the GrimbResults struct pointing at them.
-    totals: [words, general records, hap rows, pop rows, pair evaluations, handed to the general kernel]."""
+    totals: [words, general records, hap rows, pop rows, pair evaluations, handed to the general kernel,
+    probes issued, probes answered, frequency vectors read]."""
 
     def __init__(self, n_subjects, kw=1, words=1024, general=1024, hap=1024, pop=1024):
         import numpy as np
         self.np = np
         self.kw = kw
         self.compact = np.zeros(max(1, n_subjects), dtype=COMPACT_DTYPE)
-        self.totals = np.zeros(6, np.int64)
+        self.totals = np.zeros(9, np.int64)
         self.caps = [max(16, int(words)), max(16, int(general)), max(16, int(hap)), max(16, int(pop))]
         self._alloc()
 

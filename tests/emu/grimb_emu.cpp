@@ -73,7 +73,8 @@ int grimb_emu_impute(const GrimbEmuTables* t, const GrimbConfig* cfg, const Grim
   S.ar_cap = arena_bytes;
   OutArrays O;
   O.r = *res;
-  unsigned long long hc = 0, pc = 0, wc = 0, gc = 0, ec = 0;
+  unsigned long long hc = 0, pc = 0, wc = 0, gc = 0, ec = 0, prc[3] = {0, 0, 0};
+  O.probe_counters = prc;
   O.hap_counter = &hc;
   O.pop_counter = &pc;
   O.word_counter = &wc;
@@ -86,6 +87,9 @@ int grimb_emu_impute(const GrimbEmuTables* t, const GrimbConfig* cfg, const Grim
   res->totals[3] = (int64_t)pc;
   res->totals[4] = (int64_t)ec;
   res->totals[5] = 0;
+  res->totals[6] = (int64_t)prc[0];
+  res->totals[7] = (int64_t)prc[1];
+  res->totals[8] = (int64_t)prc[2];
   free(S.ar_base);
   free(ones);
   return (int64_t)gc > res->general_capacity || (int64_t)hc > res->hap_capacity || (int64_t)pc > res->pop_capacity

@@ -281,7 +281,7 @@ def test_file_pipeline_many_chunks_files_and_memory(name, tmp_path):
     src = str(tmp_path / "in.csv")
     open(src, "w").write("".join(lines))
     paths = {k: str(tmp_path / ("out." + k)) for k in goldenlib.KEYS}
-    _out, st = imp.impute_file_native(src, paths, chunk_bytes=2048)
+    _out, st = imp.impute_file_native(src, paths, chunk_bytes=300)
     assert st.n_chunks > 3 and st.n_lines == len(lines)
     for k in goldenlib.KEYS:
         assert open(paths[k]).read() == exp[k], "%s: %s differs" % (name, k)
@@ -293,7 +293,7 @@ def test_file_pipeline_many_chunks_files_and_memory(name, tmp_path):
     _lib.check(lib.grimb_file_count_lines(src.encode(), 0, cut, 0, C.byref(n0), None, None), "count")
     parts = []
     for lo, hi, first in ((0, cut, 0), (cut, -1, n0.value)):
-        out, _ = imp.impute_file_native(src, None, lo, hi, first, chunk_bytes=4096)
+        out, _ = imp.impute_file_native(src, None, lo, hi, first, chunk_bytes=700)
         parts.append({k: C.string_at(out.data[i], out.size[i]).decode("utf8") for i, k in enumerate(_lib.OUT_KEYS)})
     for k in goldenlib.KEYS:
         assert parts[0][k] + parts[1][k] == exp[k], "%s: %s differs (byte ranges)" % (name, k)
