@@ -229,6 +229,13 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=12000, help="cpu_baseline: subjects on 1 core")
     ap.add_argument("--text-subjects", type=int, default=1 << 18, help="subjects of the text-to-text measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C3 / C4 / C5 / K0 sub-records")
+    ap.add_argument("--c3-subjects", type=int, default=1 << 18)
+    ap.add_argument("--c4-subjects", type=int, default=4000)
+    ap.add_argument("--c4-heavy-subjects", type=int, default=400)
+    ap.add_argument("--c5-haps", type=int, default=100000)
+    ap.add_argument("--c5-subjects", type=int, default=1 << 16)
+    ap.add_argument("--config-sample", type=int, default=300, help="subjects per configuration checked against the oracle")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -328,7 +335,7 @@ def main():
     # device-resident leg
     d_in = {k: tens(as_signed(batch[k])).to(dev) for k in keys_in}
     d_out = {k: torch.zeros(CAP[k] * SZ[k], dtype=torch.uint8, device=dev) for k in SZ}
-    tot_dev = np.zeros(6, np.int64)
+    tot_dev = np.zeros(9, np.int64)
     db, dr = make_structs(d_in, d_out, tot_dev)
     # a stream of our own: the library takes a raw cudaStream_t (0 would select the engine's stream) and the
     # timing events must be recorded on the stream the kernels are launched on
@@ -354,7 +361,7 @@ def main():
     # host leg (pinned buffers; copies inside the timed region)
     h_in = {k: tens(as_signed(batch[k]), pin=True) for k in keys_in}
     h_out = {k: torch.zeros(CAP[k] * SZ[k], dtype=torch.uint8).pin_memory() for k in SZ}
-    tot_host = np.zeros(6, np.int64)
+    tot_host = np.zeros(9, np.int64)
     hb, hr = make_structs(h_in, h_out, tot_host)
 
     def step_host():
@@ -551,6 +558,20 @@ def main():
             "parity_sample_identical": parity,
             "e2e_text": e2e_text,
         }
+        line["pair_evals_note"] = ("reference-equivalent count: iterations reaching impute.py:464 / :573 in the reference's "
+                                   "schedule (rounds x candidates x output kinds), not operations the GPU performs")
+        if world == 1 and not args.no_configs:
+            # every other kernel of the path in the same run: C3 / C5 (k_impute_typed), C4 (k_impute), K0
+            import bench_configs
+            eng = None
+            g.close()
+            try:
+                line["configs"] = bench_configs.run_all(args, names, fa, ff, torch, dev, stream, peak)
+                line["configs"]["K0"]["C2_table"] = {"n_full": info["n_full"], "n_nodes": info["n_nodes"],
+                                                     "device_bytes": info["device_bytes"], "build_s": t_build,
+                                                     "note": "includes the host-side staging of bench.py's arrays"}
+            except Exception as exc:   # the headline line must survive a failing sub-record
+                line["configs"] = {"error": repr(exc)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

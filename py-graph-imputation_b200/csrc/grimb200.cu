@@ -68,6 +68,7 @@ struct GrimbTables {
   char* image;  // device
   ImageHeader h;
   TablesView view;
+  int build_launches = 0;   // kernel launches of grimb_tables_build (0 for a table made from an image)
 };
 
 static void make_view(GrimbTables* t) {
@@ -107,53 +108,6 @@ __global__ void k_pack_full(const uint16_t* al, int L, const uint8_t* shift, uin
   keys[i] = k;
 }
 
-__global__ void k_project(const hkey* keys, hkey mask, uint32_t base, uint32_t n, hkey* out, uint32_t* idx) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  out[i] = keys[i] & mask;
-  idx[i] = base + i;
-}
-
-__global__ void k_heads(const hkey* sorted, uint32_t n, uint32_t* flag) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  flag[i] = (i == 0 || sorted[i] != sorted[i - 1]) ? 1u : 0u;
-}
-
-// segment s (in key-sorted order) starts at position head_pos[s]; its first member's rank orders
-// the label's nodes (first appearance in hpf order)
-__global__ void k_seg_heads(const uint32_t* flag, const uint32_t* seg_of, const uint32_t* sorted_idx, uint32_t n,
-                            uint32_t* head_pos, uint32_t* first_rank, uint32_t* seg_iota) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || !flag[i]) return;
-  uint32_t s = seg_of[i];
-  head_pos[s] = i;
-  first_rank[s] = sorted_idx[i];
-  seg_iota[s] = s;
-}
-
-// node r of the label (r = rank of the segment by first appearance): key, top-link range and the
-// SEQUENTIAL sum of the members' frequency vectors in hpf order (generate_neo4j_multi_hpf.py:405)
-__global__ void k_label_nodes(const uint32_t* seg_by_rank, const uint32_t* head_pos, uint32_t nseg, uint32_t n,
-                              const hkey* sorted_keys, const uint32_t* sorted_idx, const double* full_freq, int P,
-                              uint32_t node_base, uint32_t tl_base, hkey* node_key, double* freq,
-                              uint32_t* tl_start, uint32_t* tl_cnt) {
-  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= nseg * (uint32_t)P) return;
-  uint32_t r = q / P, p = q % P;
-  uint32_t s = seg_by_rank[r];
-  uint32_t b0 = head_pos[s], b1 = (s + 1 < nseg) ? head_pos[s + 1] : n;
-  double acc = 0.0 + full_freq[(uint64_t)sorted_idx[b0] * P + p];
-  for (uint32_t i = b0 + 1; i < b1; ++i) acc = acc + full_freq[(uint64_t)sorted_idx[i] * P + p];
-  uint32_t node = node_base + r;
-  freq[(uint64_t)node * P + p] = acc;
-  if (p == 0) {
-    node_key[node] = sorted_keys[b0];
-    tl_start[node] = tl_base + b0;
-    tl_cnt[node] = b1 - b0;
-  }
-}
-
 __global__ void k_full_nodes(const hkey* keys, const double* full_freq, uint32_t n, int P, hkey* node_key,
                              double* freq, uint32_t* tl_start, uint32_t* tl_cnt) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -172,53 +126,6 @@ __global__ void k_init_slots(HSlot* s, uint64_t n) {
   e.key = ~(hkey)0;
   e.node = GRIMB_NONE;
   s[i] = e;
-}
-
-// All keys of a region are distinct, so an insert only has to claim an empty slot (CAS on the node
-// field); lookups run in later launches.
-__global__ void k_insert(HSlot* slots, uint64_t off, uint32_t mask, const hkey* node_key, uint32_t first, uint32_t cnt) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= cnt) return;
-  uint32_t node = first + i;
-  hkey key = node_key[node];
-  HSlot* base = slots + off;
-  uint32_t h = ht_home(key, mask);
-  for (;;) {
-    unsigned int old = atomicCAS(&base[h].node, GRIMB_NONE, node);
-    if (old == GRIMB_NONE) {
-      base[h].key = key;
-      return;
-    }
-    h = (h + 1) & mask;
-  }
-}
-
-// connector segments: child key -> (child node, added locus) CSR entry
-__global__ void k_conn_heads(const uint32_t* flag, const hkey* sorted_child, uint32_t n, TablesView T, uint32_t child_label,
-                             int locus, uint32_t cn_base, uint32_t* cn_start, uint32_t* cn_cnt, const uint32_t* next_head,
-                             unsigned int* n_conn) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || !flag[i]) return;
-  uint32_t child = ht_lookup(T, child_label, sorted_child[i]);
-  if (child == GRIMB_NONE) return;  // cannot happen: every projection of a node is a node
-  uint32_t end = next_head[i];
-  cn_start[(uint64_t)child * T.L + locus] = cn_base + i;
-  cn_cnt[(uint64_t)child * T.L + locus] = end - i;
-  atomicAdd(n_conn, 1u);
-}
-
-// next_head[i] for head positions: position of the following head (or n)
-__global__ void k_next_head(const uint32_t* flag, uint32_t n, uint32_t* next_head) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || !flag[i]) return;
-  uint32_t j = i + 1;
-  while (j < n && !flag[j]) ++j;
-  next_head[i] = j;
-}
-
-__global__ void k_add_u32(uint32_t* a, uint32_t n, uint32_t v) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) a[i] += v;
 }
 
 static inline unsigned nblk(uint64_t n, unsigned t = 256) { return (unsigned)((n + t - 1) / t); }
@@ -262,76 +169,6 @@ static std::vector<uint32_t> label_order(int L) {
   return out;
 }
 
-static hkey host_key_mask(const ImageHeader& h, uint32_t label) {
-  hkey m = 0;
-  for (int l = 0; l < h.L; ++l)
-    if (label >> l & 1u) m |= (hkey)((1ull << h.width[l]) - 1ull) << h.shift[l];
-  return m;
-}
-
-// Stable sort of (key, idx) pairs by the low `bits` bits of the key.  64-bit keys: one CUB radix
-// sort.  128-bit keys: two stable LSD passes (low word, then high word) over a position
-// permutation, then one gather.
-#if GRIMB_KW == 2
-__global__ void k_key_word(const hkey* keys, const uint32_t* pos, int word, uint32_t n, uint64_t* out, uint32_t* iota) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const hkey k = keys[pos ? pos[i] : i];
-  out[i] = word ? (uint64_t)(k >> 64) : (uint64_t)k;
-  if (iota) iota[i] = i;
-}
-__global__ void k_gather_pairs(const hkey* kin, const uint32_t* iin, const uint32_t* pos, uint32_t n, hkey* kout, uint32_t* iout) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  kout[i] = kin[pos[i]];
-  iout[i] = iin[pos[i]];
-}
-#endif
-struct SortScratch {
-  DevBuf tmp, w0, w1, p0, p1, p2;
-  cudaError_t reserve(uint32_t n) {
-    size_t tb1 = 0, tb2 = 0, tb3 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb1, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
-    cub::DeviceRadixSort::SortPairs(nullptr, tb2, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
-    cub::DeviceScan::ExclusiveSum(nullptr, tb3, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
-    size_t tb = tb1 > tb2 ? tb1 : tb2;
-    tb = tb > tb3 ? tb : tb3;
-    cudaError_t e = tmp.reserve(tb + 16);
-#if GRIMB_KW == 2
-    if (e == cudaSuccess) e = w0.reserve((size_t)n * 8);
-    if (e == cudaSuccess) e = w1.reserve((size_t)n * 8);
-    if (e == cudaSuccess) e = p0.reserve((size_t)n * 4);
-    if (e == cudaSuccess) e = p1.reserve((size_t)n * 4);
-    if (e == cudaSuccess) e = p2.reserve((size_t)n * 4);
-#endif
-    return e;
-  }
-  cudaError_t sort(const hkey* kin, hkey* kout, const uint32_t* iin, uint32_t* iout, uint32_t n, int bits) {
-    size_t tbx = tmp.cap;
-#if GRIMB_KW == 1
-    return cub::DeviceRadixSort::SortPairs(tmp.p, tbx, kin, kout, iin, iout, (int)n, 0, bits);
-#else
-    if (n == 0) return cudaSuccess;
-    const unsigned g = (n + 255) / 256;
-    k_key_word<<<g, 256>>>(kin, nullptr, 0, n, (uint64_t*)w0.p, (uint32_t*)p0.p);
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp.p, tbx, (uint64_t*)w0.p, (uint64_t*)w1.p, (uint32_t*)p0.p,
-                                                    (uint32_t*)p1.p, (int)n, 0, bits < 64 ? bits : 64);
-    if (e != cudaSuccess) return e;
-    const uint32_t* pos = (const uint32_t*)p1.p;
-    if (bits > 64) {
-      k_key_word<<<g, 256>>>(kin, (const uint32_t*)p1.p, 1, n, (uint64_t*)w0.p, nullptr);
-      tbx = tmp.cap;
-      e = cub::DeviceRadixSort::SortPairs(tmp.p, tbx, (uint64_t*)w0.p, (uint64_t*)w1.p, (uint32_t*)p1.p, (uint32_t*)p2.p,
-                                          (int)n, 0, bits - 64);
-      if (e != cudaSuccess) return e;
-      pos = (const uint32_t*)p2.p;
-    }
-    k_gather_pairs<<<g, 256>>>(kin, iin, pos, n, kout, iout);
-    return cudaGetLastError();
-#endif
-  }
-};
-
 // reference quirk: the closing CSR sentinel is len(Vertices) (networkx_graph.py:195-196)
 static uint32_t sentinel_count(uint64_t own, uint64_t n_edges, uint64_t n_vertices) {
   uint64_t start = n_edges - own;
@@ -339,6 +176,221 @@ static uint32_t sentinel_count(uint64_t own, uint64_t n_edges, uint64_t n_vertic
   if (n_vertices > n_edges) return GRIMB_ADJ_FAULT;
   return (uint32_t)(n_vertices - start);
 }
+
+// ------------------------------------------------------------------------------------------
+// K0: table build, batched over labels.  All marginal labels are grouped with ONE stable sort-by-key:
+// element (label li, full haplotype i) carries the composite key  li || projected haplotype  (the
+// projection re-packed at minimal field widths so that the composite usually fits 64 bits; two LSD
+// passes over 64-bit words otherwise).  Equal keys stay in hpf order, so a segment's first member is
+// the node's first appearance, its members in sorted order are its top links (ascending full id), and
+// the ordered segmented sum adds the members' frequency vectors exactly as
+// generate_neo4j_multi_hpf.py:405 does.  Node ids follow from a second sort of the segments by
+// (label, first member).  Connectors are grouped the same way, one element per (parent label B, dropped
+// locus l, node of B).  Large tables are processed in groups of labels / pairs of bounded size.
+// ------------------------------------------------------------------------------------------
+struct CompactLayout {
+  uint8_t cshift[9];
+  uint8_t cwidth[9];
+  int32_t cbits;
+};
+
+typedef unsigned __int128 u128;
+
+__device__ __forceinline__ u128 compact_of(hkey key, const uint8_t* shift, const uint8_t* width, const CompactLayout& C, int L,
+                                           uint32_t label) {
+  u128 c = 0;
+  for (int l = 0; l < L; ++l)
+    if (label >> l & 1u) c |= (u128)((uint64_t)(key >> shift[l]) & ((1ull << width[l]) - 1ull)) << C.cshift[l];
+  return c;
+}
+
+struct K0Meta {   // small per-build tables, device resident
+  uint32_t label_mask[512];   // label index (build order) -> locus mask
+};
+
+// elements of one group of labels [li0, li0 + nl): e -> (li0 + e / N, e % N)
+__global__ void k0_make_keys(const hkey* __restrict__ full_keys, TablesView T, CompactLayout C, const uint32_t* __restrict__ label_mask,
+                             uint32_t li0, uint64_t N, uint64_t E, uint64_t* lo, uint64_t* hi, uint32_t* val) {
+  const uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const uint32_t li = li0 + (uint32_t)(e / N);
+  const uint32_t i = (uint32_t)(e % N);
+  const u128 c = ((u128)li << C.cbits) | compact_of(full_keys[i], T.shift, T.width, C, T.L, label_mask[li]);
+  lo[e] = (uint64_t)c;
+  if (hi) hi[e] = (uint64_t)(c >> 64);
+  val[e] = i;
+}
+
+__global__ void k0_gather64(const uint64_t* in, const uint32_t* pos, uint64_t n, uint64_t* out) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[pos[i]];
+}
+__global__ void k0_gather32(const uint32_t* in, const uint32_t* pos, uint64_t n, uint32_t* out) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[pos[i]];
+}
+__global__ void k0_iota(uint32_t* a, uint64_t n) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) a[i] = (uint32_t)i;
+}
+
+__global__ void k0_heads(const uint64_t* lo, const uint64_t* hi, uint64_t n, uint32_t* flag) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  flag[i] = (i == 0 || lo[i] != lo[i - 1] || (hi && hi[i] != hi[i - 1])) ? 1u : 0u;
+}
+
+// per segment head of a label group: position, ordering key (label, first member) and the label's node count
+__global__ void k0_seg_heads(const uint32_t* flag, const uint32_t* seg_of, const uint32_t* val, uint64_t E, uint64_t N, uint32_t li0,
+                             uint64_t pos_base, uint32_t seg_base, uint64_t* head_pos, uint64_t* seg_key, uint32_t* lcount) {
+  const uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (e >= E || !flag[e]) return;
+  const uint32_t s = seg_base + seg_of[e];
+  const uint32_t li = li0 + (uint32_t)(e / N);
+  head_pos[s] = pos_base + e;
+  seg_key[s] = ((uint64_t)li << 32) | (uint64_t)val[e];
+  atomicAdd(&lcount[li], 1u);
+}
+
+// node r (r-th segment by (label, first member)): key, top-link range and the SEQUENTIAL sum of the members'
+// frequency vectors in hpf order (generate_neo4j_multi_hpf.py:405)
+__global__ void k0_label_nodes(const uint32_t* seg_by_rank, const uint64_t* head_pos, uint32_t nseg, uint64_t E_total, uint64_t N,
+                               const uint32_t* sorted_val, const hkey* full_keys, const double* full_freq, int P,
+                               const uint32_t* label_mask, TablesView T, hkey* node_key, double* freq, uint32_t* tl_start,
+                               uint32_t* tl_cnt) {
+  const uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (q >= (uint64_t)nseg * (uint64_t)P) return;
+  const uint32_t r = (uint32_t)(q / P), p = (uint32_t)(q % P);
+  const uint32_t s = seg_by_rank[r];
+  const uint64_t b0 = head_pos[s], b1 = (s + 1 < nseg) ? head_pos[s + 1] : E_total;
+  double acc = 0.0 + full_freq[(uint64_t)sorted_val[b0] * P + p];
+  for (uint64_t i = b0 + 1; i < b1; ++i) acc = acc + full_freq[(uint64_t)sorted_val[i] * P + p];
+  const uint32_t node = (uint32_t)N + r;
+  freq[(uint64_t)node * P + p] = acc;
+  if (p == 0) {
+    const uint32_t li = 1u + (uint32_t)(b0 / N);
+    node_key[node] = full_keys[sorted_val[b0]] & key_mask_of(T, label_mask[li]);
+    tl_start[node] = (uint32_t)b0;
+    tl_cnt[node] = (uint32_t)(b1 - b0);
+  }
+}
+
+// hash insert of every node: the label (= region) of a node follows from the label's node-id range
+__global__ void k0_insert(HSlot* slots, const uint64_t* ht_off, const uint32_t* ht_mask, const hkey* node_key, uint32_t n_nodes,
+                          const uint32_t* label_first_by_index, const uint32_t* label_mask, int n_labels) {
+  const uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= n_nodes) return;
+  int lo = 0, hi = n_labels - 1;   // largest label index whose first node id <= node
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (label_first_by_index[mid] <= node) lo = mid; else hi = mid - 1;
+  }
+  const uint32_t m = label_mask[lo];
+  const hkey key = node_key[node];
+  const uint32_t mask = ht_mask[m];
+  HSlot* base = slots + ht_off[m];
+  uint32_t h = ht_home(key, mask);
+  for (;;) {
+    const unsigned int old = atomicCAS(&base[h].node, GRIMB_NONE, node);
+    if (old == GRIMB_NONE) {
+      base[h].key = key;
+      return;
+    }
+    h = (h + 1) & mask;
+  }
+}
+
+// connector elements of one group of (parent label, dropped locus) pairs: e -> (pair, node of the parent label)
+__global__ void k0_conn_keys(TablesView T, CompactLayout C, const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ pair_child,
+                             const uint32_t* __restrict__ pair_first, uint32_t pi0, uint32_t npairs, uint64_t e0, uint64_t E,
+                             uint64_t* lo, uint64_t* hi, uint32_t* val) {
+  const uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const uint64_t ge = e0 + e;
+  uint32_t a = pi0, b = pi0 + npairs - 1;   // largest pair with pair_off <= ge
+  while (a < b) {
+    const uint32_t mid = (a + b + 1) >> 1;
+    if (pair_off[mid] <= ge) a = mid; else b = mid - 1;
+  }
+  const uint32_t node = pair_first[a] + (uint32_t)(ge - pair_off[a]);
+  const u128 c = ((u128)a << C.cbits) | compact_of(T.node_key[node], T.shift, T.width, C, T.L, pair_child[a]);
+  lo[e] = (uint64_t)c;
+  if (hi) hi[e] = (uint64_t)(c >> 64);
+  val[e] = node;
+}
+
+// head of a connector group -> CSR entry of (child node, added locus)
+__global__ void k0_conn_heads(const uint32_t* flag, const uint32_t* next_head, const uint32_t* sorted_node, uint64_t E, uint64_t e0,
+                              TablesView T, const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ pair_child,
+                              const uint8_t* __restrict__ pair_locus, uint32_t pi0, uint32_t npairs, uint32_t* cn_start,
+                              uint32_t* cn_cnt, unsigned int* n_conn) {
+  const uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (e >= E || !flag[e]) return;
+  const uint64_t ge = e0 + e;
+  uint32_t a = pi0, b = pi0 + npairs - 1;
+  while (a < b) {
+    const uint32_t mid = (a + b + 1) >> 1;
+    if (pair_off[mid] <= ge) a = mid; else b = mid - 1;
+  }
+  const uint32_t A = pair_child[a];
+  const hkey ck = T.node_key[sorted_node[e]] & key_mask_of(T, A);
+  const uint32_t child = ht_lookup(T, A, ck);
+  if (child == GRIMB_NONE) return;  // cannot happen: every projection of a node is a node
+  cn_start[(uint64_t)child * T.L + pair_locus[a]] = (uint32_t)ge;
+  cn_cnt[(uint64_t)child * T.L + pair_locus[a]] = next_head[e] - (uint32_t)e;
+  atomicAdd(n_conn, 1u);
+}
+
+// next_head[i] for head positions: position of the following head (or n)
+__global__ void k0_next_head(const uint32_t* flag, uint64_t n, uint32_t* next_head) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  uint64_t j = i + 1;
+  while (j < n && !flag[j]) ++j;
+  next_head[i] = (uint32_t)j;
+}
+
+// Stable sort of n composite keys (lo, optional hi) with their 32-bit values; results in lo_out / hi_out / val_out.
+struct K0Sorter {
+  DevBuf tmp, pos0, pos1, pos2, g64;
+  cudaError_t reserve(uint64_t n, bool two) {
+    size_t t1 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
+    size_t t2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, t2, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
+    cudaError_t e = tmp.reserve((t1 > t2 ? t1 : t2) + 64);
+    if (two) {
+      if (e == cudaSuccess) e = pos0.reserve(n * 4);
+      if (e == cudaSuccess) e = pos1.reserve(n * 4);
+      if (e == cudaSuccess) e = pos2.reserve(n * 4);
+      if (e == cudaSuccess) e = g64.reserve(n * 8);
+    }
+    return e;
+  }
+  cudaError_t sort(const uint64_t* lo, const uint64_t* hi, const uint32_t* val, uint64_t* lo_out, uint64_t* hi_out, uint32_t* val_out,
+                   uint64_t n, int bits, int* launches) {
+    if (n == 0) return cudaSuccess;
+    size_t tb = tmp.cap;
+    const unsigned g = nblk(n);
+    if (!hi) {
+      *launches += 1 + (bits + 7) / 8;
+      return cub::DeviceRadixSort::SortPairs(tmp.p, tb, lo, lo_out, val, val_out, (int)n, 0, bits < 64 ? bits : 64);
+    }
+    // LSD over the two 64-bit words, carrying a position permutation
+    k0_iota<<<g, 256>>>((uint32_t*)pos0.p, n);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp.p, tb, lo, lo_out, (const uint32_t*)pos0.p, (uint32_t*)pos1.p, (int)n, 0, 64);
+    if (e != cudaSuccess) return e;
+    k0_gather64<<<g, 256>>>(hi, (const uint32_t*)pos1.p, n, (uint64_t*)g64.p);
+    tb = tmp.cap;
+    e = cub::DeviceRadixSort::SortPairs(tmp.p, tb, (const uint64_t*)g64.p, hi_out, (const uint32_t*)pos1.p, (uint32_t*)pos2.p, (int)n, 0,
+                                        bits - 64);
+    if (e != cudaSuccess) return e;
+    k0_gather64<<<g, 256>>>(lo, (const uint32_t*)pos2.p, n, lo_out);
+    k0_gather32<<<g, 256>>>(val, (const uint32_t*)pos2.p, n, val_out);
+    *launches += 5 + 9 + (bits - 64 + 7) / 8 + 1;
+    return cudaGetLastError();
+  }
+};
 
 extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
   if (!d || !out) return fail(GRIMB_E_ARG, "null argument");
@@ -355,8 +407,12 @@ extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
     return fail(GRIMB_E_LAYOUT, GRIMB_KW == 1 ? "packed key exceeds 63 bits (use libgrimb200w.so: 128-bit keys)"
                                               : "packed key exceeds 127 bits");
   CK(cudaSetDevice(d->device));
-  const uint32_t N = (uint32_t)d->n_full;
+  const uint64_t N = (uint64_t)d->n_full;
   const uint32_t NL = 1u << L;
+  const std::vector<uint32_t> order = label_order(L);
+  const uint32_t n_labels = (uint32_t)order.size();   // full label + marginals
+  // 32-bit offsets everywhere (tl_start, cn_start, row indices): reject what would not fit
+  if (N * (uint64_t)(n_labels - 1) > 0xFFFFFFF0ull) return fail(GRIMB_E_ARG, "too many top links (n_full x marginal labels >= 2^32)");
 
   GrimbTables* t = new GrimbTables();
   t->device = d->device;
@@ -366,121 +422,158 @@ extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
   h.magic = IMAGE_MAGIC;
   h.L = L;
   h.P = P;
-  h.n_full = N;
-  int sh = 0;
+  h.n_full = (uint32_t)N;
+  CompactLayout CL;
+  memset(&CL, 0, sizeof(CL));
+  int sh = 0, csh = 0;
   for (int l = 0; l < L; ++l) {
     h.shift[l] = (uint8_t)sh;
     h.width[l] = (uint8_t)d->key_bits[l];
     h.n_alleles[l] = (uint32_t)d->n_alleles[l];
     sh += d->key_bits[l];
+    int w = 1;
+    while ((1ll << w) <= d->n_alleles[l]) ++w;   // minimal width for the table ids 1..n
+    CL.cshift[l] = (uint8_t)csh;
+    CL.cwidth[l] = (uint8_t)w;
+    csh += w;
   }
-
-  // ---- stage inputs
-  DevBuf b_al, b_ff, b_keys, b_shift;
-  cudaError_t e;
-#define CKB(call)                                                                                 \
-  do {                                                                                            \
-    e = (call);                                                                                   \
-    if (e != cudaSuccess) {                                                                       \
-      delete t;                                                                                   \
-      return fail(GRIMB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e));               \
-    }                                                                                             \
-  } while (0)
-  CKB(b_al.reserve((size_t)N * L * 2));
-  CKB(b_ff.reserve((size_t)N * P * 8));
-  CKB(b_keys.reserve((size_t)N * sizeof(hkey)));
-  CKB(b_shift.reserve(16));
-  CKB(cudaMemcpy(b_al.p, d->full_alleles, (size_t)N * L * 2, cudaMemcpyHostToDevice));
-  CKB(cudaMemcpy(b_ff.p, d->full_freqs, (size_t)N * P * 8, cudaMemcpyHostToDevice));
-  CKB(cudaMemcpy(b_shift.p, h.shift, 9, cudaMemcpyHostToDevice));
-  if (N) k_pack_full<<<nblk(N), 256>>>((const uint16_t*)b_al.p, L, (const uint8_t*)b_shift.p, N, (hkey*)b_keys.p);
-  CKB(cudaGetLastError());
-
-  // ---- pass 1 over labels: sort projections, count nodes, keep per-label results
-  const std::vector<uint32_t> order = label_order(L);
-  struct PerLabel {
-    uint32_t nseg = 0;
-    hkey* keys = nullptr;       // [nseg] node keys in node order
-    double* freq = nullptr;     // [nseg][P]
-    uint32_t* tls = nullptr;    // [nseg] top-link start relative to the label's block
-    uint32_t* tlc = nullptr;    // [nseg]
-    uint32_t* adj = nullptr;    // [N] sorted full ids
-  };
-  std::vector<PerLabel> pl(order.size());
-  auto free_pl = [&]() {
-    for (auto& x : pl) {
-      cudaFree(x.keys);
-      cudaFree(x.freq);
-      cudaFree(x.tls);
-      cudaFree(x.tlc);
-      cudaFree(x.adj);
+  CL.cbits = csh;
+  int launches = 0;
+  std::vector<void*> owned;   // device allocations released on every exit path
+  unsigned int* d_nconn = nullptr;
+  auto cleanup = [&](bool ok) {
+    for (void* p : owned) cudaFree(p);
+    if (d_nconn) cudaFree(d_nconn);
+    if (!ok) {
+      if (t->image) cudaFree(t->image);
+      delete t;
     }
   };
-  DevBuf b_pk, b_pi, b_sk, b_si, b_flag, b_seg, b_head, b_rank, b_iota, b_rank2, b_iota2;
-  SortScratch ss;
-  DevBuf& b_tmp = ss.tmp;
-  CKB(b_pk.reserve((size_t)N * sizeof(hkey)));
-  CKB(b_pi.reserve((size_t)N * 4));
-  CKB(b_sk.reserve((size_t)N * sizeof(hkey)));
-  CKB(b_si.reserve((size_t)N * 4));
-  CKB(b_flag.reserve((size_t)N * 4));
-  CKB(b_seg.reserve((size_t)N * 4));
-  CKB(b_head.reserve((size_t)N * 4));
-  CKB(b_rank.reserve((size_t)N * 4));
-  CKB(b_iota.reserve((size_t)N * 4));
-  CKB(b_rank2.reserve((size_t)N * 4));
-  CKB(b_iota2.reserve((size_t)N * 4));
-  CKB(ss.reserve(N));
+  cudaError_t e;
+#define CKT(call)                                                                   \
+  do {                                                                              \
+    e = (call);                                                                     \
+    if (e != cudaSuccess) {                                                         \
+      cleanup(false);                                                               \
+      return fail(e == cudaErrorMemoryAllocation ? GRIMB_E_NOMEM : GRIMB_E_CUDA,    \
+                  std::string(#call) + ": " + cudaGetErrorString(e));               \
+    }                                                                               \
+  } while (0)
+  auto dalloc = [&](void** p, size_t bytes) -> cudaError_t {
+    cudaError_t r = cudaMalloc(p, bytes ? bytes : 16);
+    if (r == cudaSuccess) owned.push_back(*p);
+    return r;
+  };
 
-  uint64_t n_nodes = N;
-  for (size_t li = 1; li < order.size() && N > 0; ++li) {
-    const hkey km = host_key_mask(h, order[li]);
-    k_project<<<nblk(N), 256>>>((const hkey*)b_keys.p, km, 0u, N, (hkey*)b_pk.p, (uint32_t*)b_pi.p);
-    CKB(ss.sort((const hkey*)b_pk.p, (hkey*)b_sk.p, (const uint32_t*)b_pi.p, (uint32_t*)b_si.p, N, sh));
-    k_heads<<<nblk(N), 256>>>((const hkey*)b_sk.p, N, (uint32_t*)b_flag.p);
-    size_t tbx = b_tmp.cap;
-    CKB(cub::DeviceScan::ExclusiveSum(b_tmp.p, tbx, (uint32_t*)b_flag.p, (uint32_t*)b_seg.p, (int)N));
-    uint32_t last_flag = 0, last_seg = 0;
-    CKB(cudaMemcpy(&last_flag, (uint32_t*)b_flag.p + (N - 1), 4, cudaMemcpyDeviceToHost));
-    CKB(cudaMemcpy(&last_seg, (uint32_t*)b_seg.p + (N - 1), 4, cudaMemcpyDeviceToHost));
-    const uint32_t nseg = last_seg + last_flag;
-    PerLabel& x = pl[li];
-    x.nseg = nseg;
-    k_seg_heads<<<nblk(N), 256>>>((const uint32_t*)b_flag.p, (const uint32_t*)b_seg.p, (const uint32_t*)b_si.p, N,
-                                  (uint32_t*)b_head.p, (uint32_t*)b_rank.p, (uint32_t*)b_iota.p);
-    tbx = b_tmp.cap;
-    CKB(cub::DeviceRadixSort::SortPairs(b_tmp.p, tbx, (uint32_t*)b_rank.p, (uint32_t*)b_rank2.p, (uint32_t*)b_iota.p,
-                                        (uint32_t*)b_iota2.p, (int)nseg));
-    CKB(cudaMalloc(&x.keys, (size_t)nseg * sizeof(hkey)));
-    CKB(cudaMalloc(&x.freq, (size_t)nseg * P * 8));
-    CKB(cudaMalloc(&x.tls, (size_t)nseg * 4));
-    CKB(cudaMalloc(&x.tlc, (size_t)nseg * 4));
-    CKB(cudaMalloc(&x.adj, (size_t)N * 4));
-    k_label_nodes<<<nblk((uint64_t)nseg * P), 256>>>((const uint32_t*)b_iota2.p, (const uint32_t*)b_head.p, nseg, N,
-                                                     (const hkey*)b_sk.p, (const uint32_t*)b_si.p,
-                                                     (const double*)b_ff.p, P, 0u, 0u, x.keys, x.freq, x.tls, x.tlc);
-    CKB(cudaMemcpy(x.adj, b_si.p, (size_t)N * 4, cudaMemcpyDeviceToDevice));
-    CKB(cudaGetLastError());
-    n_nodes += nseg;
+  // ---- stage inputs
+  uint16_t* d_al = nullptr;
+  double* d_ff = nullptr;
+  hkey* d_keys = nullptr;
+  uint8_t* d_shift = nullptr;
+  uint32_t* d_lmask = nullptr;
+  CKT(dalloc((void**)&d_al, N * L * 2));
+  CKT(dalloc((void**)&d_ff, N * P * 8));
+  CKT(dalloc((void**)&d_keys, N * sizeof(hkey)));
+  CKT(dalloc((void**)&d_shift, 16));
+  CKT(dalloc((void**)&d_lmask, 512 * 4));
+  CKT(cudaMemcpy(d_al, d->full_alleles, N * L * 2, cudaMemcpyHostToDevice));
+  CKT(cudaMemcpy(d_ff, d->full_freqs, N * P * 8, cudaMemcpyHostToDevice));
+  CKT(cudaMemcpy(d_shift, h.shift, 9, cudaMemcpyHostToDevice));
+  {
+    std::vector<uint32_t> lm(512, 0);
+    for (uint32_t li = 0; li < n_labels; ++li) lm[li] = order[li];
+    CKT(cudaMemcpy(d_lmask, lm.data(), 512 * 4, cudaMemcpyHostToDevice));
   }
+  if (N) {
+    k_pack_full<<<nblk(N), 256>>>(d_al, L, d_shift, N, d_keys);
+    ++launches;
+  }
+  CKT(cudaGetLastError());
+  // a view good enough for key_mask_of / compact_of before the image exists
+  TablesView pv;
+  memset(&pv, 0, sizeof(pv));
+  pv.L = L;
+  pv.P = P;
+  memcpy(pv.shift, h.shift, 9);
+  memcpy(pv.width, h.width, 9);
+
+  // ---- pass 1: group the marginal labels (bounded groups of labels)
+  int lbits = 1;
+  while ((1u << lbits) < n_labels) ++lbits;
+  const int tot_bits = CL.cbits + lbits;
+  const bool two = tot_bits > 64;
+  const uint64_t E_total = N * (uint64_t)(n_labels - 1);
+  uint64_t budget = 1ull << 28;   // elements per group
+  if (const char* gb = getenv("GRIMB_K0_GROUP")) {
+    const long long v = atoll(gb);
+    if (v >= 1024) budget = (uint64_t)v;
+  }
+  uint32_t labels_per_group = N ? (uint32_t)std::max<uint64_t>(1, budget / N) : n_labels;
+  if (labels_per_group > n_labels - 1) labels_per_group = n_labels > 1 ? n_labels - 1 : 1;
+  const uint64_t Eg = N * (uint64_t)labels_per_group;   // largest group
+  uint64_t *g_lo = nullptr, *g_hi = nullptr, *s_lo = nullptr, *s_hi = nullptr, *d_head_pos = nullptr, *d_seg_key = nullptr;
+  uint32_t *g_val = nullptr, *d_sorted_val = nullptr, *d_flag = nullptr, *d_seg = nullptr, *d_lcount = nullptr;
+  K0Sorter sorter;
+  std::vector<uint32_t> lcount_i(n_labels, 0);   // nodes per label index
+  uint32_t nseg_total = 0;
+  if (E_total) {
+    CKT(dalloc((void**)&g_lo, Eg * 8));
+    CKT(dalloc((void**)&s_lo, Eg * 8));
+    if (two) {
+      CKT(dalloc((void**)&g_hi, Eg * 8));
+      CKT(dalloc((void**)&s_hi, Eg * 8));
+    }
+    CKT(dalloc((void**)&g_val, Eg * 4));
+    CKT(dalloc((void**)&d_sorted_val, E_total * 4));     // becomes tl_adj
+    CKT(dalloc((void**)&d_flag, Eg * 4));
+    CKT(dalloc((void**)&d_seg, Eg * 4));
+    CKT(dalloc((void**)&d_head_pos, (E_total + 1) * 8)); // worst case: every element its own segment
+    CKT(dalloc((void**)&d_seg_key, (E_total + 1) * 8));
+    CKT(dalloc((void**)&d_lcount, 512 * 4));
+    CKT(cudaMemset(d_lcount, 0, 512 * 4));
+    CKT(sorter.reserve(Eg > E_total ? E_total : Eg, two));
+    for (uint32_t li0 = 1; li0 < n_labels; li0 += labels_per_group) {
+      const uint32_t nl = std::min(labels_per_group, n_labels - li0);
+      const uint64_t E = N * (uint64_t)nl, pos_base = N * (uint64_t)(li0 - 1);
+      k0_make_keys<<<nblk(E), 256>>>(d_keys, pv, CL, d_lmask, li0, N, E, g_lo, g_hi, g_val);
+      CKT(sorter.sort(g_lo, g_hi, g_val, s_lo, s_hi, d_sorted_val + pos_base, E, tot_bits, &launches));
+      k0_heads<<<nblk(E), 256>>>(s_lo, s_hi, E, d_flag);
+      size_t tb = sorter.tmp.cap;
+      CKT(cub::DeviceScan::ExclusiveSum(sorter.tmp.p, tb, d_flag, d_seg, (int)E));
+      k0_seg_heads<<<nblk(E), 256>>>(d_flag, d_seg, d_sorted_val + pos_base, E, N, li0, pos_base, nseg_total, d_head_pos,
+                                     d_seg_key, d_lcount);
+      launches += 5;
+      // segments of this group (one small read-back per GROUP of labels, not per label)
+      uint32_t last_flag = 0, last_seg = 0;
+      CKT(cudaMemcpy(&last_flag, d_flag + (E - 1), 4, cudaMemcpyDeviceToHost));
+      CKT(cudaMemcpy(&last_seg, d_seg + (E - 1), 4, cudaMemcpyDeviceToHost));
+      if ((uint64_t)nseg_total + last_seg + last_flag > 0x7FFFFFF0ull) {
+        cleanup(false);
+        return fail(GRIMB_E_ARG, "too many nodes");
+      }
+      nseg_total += last_seg + last_flag;
+    }
+    CKT(cudaMemcpy(lcount_i.data(), d_lcount, n_labels * 4, cudaMemcpyDeviceToHost));
+  }
+  lcount_i[0] = (uint32_t)N;
+  const uint64_t n_nodes = N + nseg_total;
   if (n_nodes > 0x7FFFFFF0ull) {
-    free_pl();
-    delete t;
+    cleanup(false);
     return fail(GRIMB_E_ARG, "too many nodes");
   }
   h.n_nodes = (uint32_t)n_nodes;
-  h.n_toplinks = (uint64_t)N * (order.size() - 1);
+  h.n_toplinks = E_total;
 
-  // ---- hash region sizes, connector edge count
-  std::vector<uint32_t> lfirst(NL, 0), lcount(NL, 0), hmask(NL, 1);
+  // ---- label ranges, hash region sizes, connector pairs
+  std::vector<uint32_t> lfirst(NL, 0), lcount(NL, 0), hmask(NL, 1), lfirst_i(n_labels, 0);
   std::vector<uint64_t> hoff(NL, 0);
   {
     uint32_t nb = 0;
-    for (size_t li = 0; li < order.size(); ++li) {
-      uint32_t c = li == 0 ? N : pl[li].nseg;
+    for (uint32_t li = 0; li < n_labels; ++li) {
       lfirst[order[li]] = nb;
-      lcount[order[li]] = c;
-      nb += c;
+      lfirst_i[li] = nb;
+      lcount[order[li]] = lcount_i[li];
+      nb += lcount_i[li];
     }
     uint64_t so = 0;
     for (uint32_t m = 0; m < NL; ++m) {
@@ -500,10 +593,30 @@ extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
     }
     h.n_slots = so;
   }
+  // pairs (parent label B, dropped locus l) in the order the reference scans edges.csv
+  std::vector<uint64_t> pair_off;
+  std::vector<uint32_t> pair_child, pair_first;
+  std::vector<uint8_t> pair_locus;
   uint64_t n_cn = 0;
-  for (uint32_t m = 1; m < NL; ++m)
-    if (__builtin_popcount(m) >= 2) n_cn += (uint64_t)__builtin_popcount(m) * lcount[m];
+  for (uint32_t li = 0; li < n_labels; ++li) {
+    const uint32_t B = order[li];
+    if (__builtin_popcount(B) < 2 || lcount[B] == 0) continue;
+    for (int l = 0; l < L; ++l) {
+      if (!(B >> l & 1u)) continue;
+      pair_off.push_back(n_cn);
+      pair_child.push_back(B & ~(1u << l));
+      pair_first.push_back(lfirst[B]);
+      pair_locus.push_back((uint8_t)l);
+      n_cn += lcount[B];
+    }
+  }
+  const uint32_t n_pairs = (uint32_t)pair_off.size();
+  pair_off.push_back(n_cn);
   h.n_conn_edges = n_cn;
+  if (n_cn + n_nodes * (uint64_t)L > 0xFFFFFFF0ull || n_nodes * (uint64_t)P > (1ull << 40)) {
+    cleanup(false);
+    return fail(GRIMB_E_ARG, "table too large for 32-bit connector offsets");
+  }
 
   // ---- image layout
   auto al16 = [](uint64_t x) { return (x + 255ull) & ~255ull; };
@@ -524,88 +637,124 @@ extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
   h.bytes = o;
   e = cudaMalloc((void**)&t->image, h.bytes);
   if (e != cudaSuccess) {
-    free_pl();
-    delete t;
+    t->image = nullptr;
+    cleanup(false);
     return fail(GRIMB_E_NOMEM, std::string("table image: ") + cudaGetErrorString(e));
   }
   make_view(t);
   TablesView& v = t->view;
-#define CKT(call)                                                                   \
-  do {                                                                              \
-    e = (call);                                                                     \
-    if (e != cudaSuccess) {                                                         \
-      free_pl();                                                                    \
-      cudaFree(t->image);                                                           \
-      delete t;                                                                     \
-      return fail(GRIMB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e)); \
-    }                                                                               \
-  } while (0)
-  CKT(cudaMemset(t->image, 0, h.bytes));
+  // everything except the slots (initialised below) and the arrays written in full starts at zero
+  CKT(cudaMemsetAsync(t->image, 0, h.o_slots, 0));
+  CKT(cudaMemsetAsync((char*)t->image + h.o_tl_start, 0, h.o_tl_adj - h.o_tl_start, 0));
+  CKT(cudaMemsetAsync((char*)t->image + h.o_cn_start, 0, h.o_cn_adj - h.o_cn_start, 0));
   CKT(cudaMemcpy((void*)v.label_first, lfirst.data(), (size_t)NL * 4, cudaMemcpyHostToDevice));
   CKT(cudaMemcpy((void*)v.label_count, lcount.data(), (size_t)NL * 4, cudaMemcpyHostToDevice));
   CKT(cudaMemcpy((void*)v.ht_off, hoff.data(), (size_t)NL * 8, cudaMemcpyHostToDevice));
   CKT(cudaMemcpy((void*)v.ht_mask, hmask.data(), (size_t)NL * 4, cudaMemcpyHostToDevice));
 
-  // ---- assemble node arrays
-  if (N)
-    k_full_nodes<<<nblk(N), 256>>>((const hkey*)b_keys.p, (const double*)b_ff.p, N, P, (hkey*)v.node_key,
-                                   (double*)v.freq, (uint32_t*)v.tl_start, (uint32_t*)v.tl_cnt);
-  {
-    uint64_t tl_base = 0;
-    for (size_t li = 1; li < order.size() && N > 0; ++li) {
-      PerLabel& x = pl[li];
-      uint32_t nb = lfirst[order[li]];
-      CKT(cudaMemcpy((hkey*)v.node_key + nb, x.keys, (size_t)x.nseg * sizeof(hkey), cudaMemcpyDeviceToDevice));
-      CKT(cudaMemcpy((double*)v.freq + (uint64_t)nb * P, x.freq, (size_t)x.nseg * P * 8, cudaMemcpyDeviceToDevice));
-      CKT(cudaMemcpy((uint32_t*)v.tl_cnt + nb, x.tlc, (size_t)x.nseg * 4, cudaMemcpyDeviceToDevice));
-      CKT(cudaMemcpy((uint32_t*)v.tl_adj + tl_base, x.adj, (size_t)N * 4, cudaMemcpyDeviceToDevice));
-      // starts are relative to the label's block: copy, then rebase
-      CKT(cudaMemcpy((uint32_t*)v.tl_start + nb, x.tls, (size_t)x.nseg * 4, cudaMemcpyDeviceToDevice));
-      if (tl_base) k_add_u32<<<nblk(x.nseg), 256>>>((uint32_t*)v.tl_start + nb, x.nseg, (uint32_t)tl_base);
-      tl_base += N;
-    }
+  // ---- pass 2: node ids (segments by (label, first member)), node arrays, top links
+  if (N) {
+    k_full_nodes<<<nblk(N), 256>>>(d_keys, d_ff, (uint32_t)N, P, (hkey*)v.node_key, (double*)v.freq, (uint32_t*)v.tl_start,
+                                   (uint32_t*)v.tl_cnt);
+    ++launches;
+  }
+  if (nseg_total) {
+    uint64_t* d_seg_key2 = nullptr;
+    uint32_t *d_iota = nullptr, *d_by_rank = nullptr;
+    CKT(dalloc((void**)&d_seg_key2, (uint64_t)nseg_total * 8));
+    CKT(dalloc((void**)&d_iota, (uint64_t)nseg_total * 4));
+    CKT(dalloc((void**)&d_by_rank, (uint64_t)nseg_total * 4));
+    k0_iota<<<nblk(nseg_total), 256>>>(d_iota, nseg_total);
+    K0Sorter s2;
+    CKT(s2.reserve(nseg_total, false));
+    CKT(s2.sort(d_seg_key, nullptr, d_iota, d_seg_key2, nullptr, d_by_rank, nseg_total, 32 + lbits, &launches));
+    k0_label_nodes<<<nblk((uint64_t)nseg_total * P), 256>>>(d_by_rank, d_head_pos, nseg_total, E_total, N, d_sorted_val, d_keys, d_ff,
+                                                           P, d_lmask, pv, (hkey*)v.node_key, (double*)v.freq,
+                                                           (uint32_t*)v.tl_start, (uint32_t*)v.tl_cnt);
+    CKT(cudaMemcpyAsync((void*)v.tl_adj, d_sorted_val, E_total * 4, cudaMemcpyDeviceToDevice, 0));
+    launches += 3;
   }
   CKT(cudaGetLastError());
-  free_pl();
 
-  // ---- hash insert
+  // ---- hash insert: one launch over all nodes
+  uint32_t* d_lfirst_i = nullptr;
+  CKT(dalloc((void**)&d_lfirst_i, 512 * 4));
+  CKT(cudaMemcpy(d_lfirst_i, lfirst_i.data(), n_labels * 4, cudaMemcpyHostToDevice));
   k_init_slots<<<nblk(h.n_slots), 256>>>((HSlot*)v.slots, h.n_slots);
-  for (uint32_t m = 1; m < NL; ++m)
-    if (lcount[m])
-      k_insert<<<nblk(lcount[m]), 256>>>((HSlot*)v.slots, hoff[m], hmask[m], v.node_key, lfirst[m], lcount[m]);
+  if (n_nodes)
+    k0_insert<<<nblk(n_nodes), 256>>>((HSlot*)v.slots, v.ht_off, v.ht_mask, v.node_key, (uint32_t)n_nodes, d_lfirst_i, d_lmask,
+                                      (int)n_labels);
+  launches += 2;
   CKT(cudaGetLastError());
-  CKT(cudaDeviceSynchronize());
 
   // ---- connectors: for every label B (>= 2 loci) and locus l in B, group B's nodes by B \ l
-  unsigned int* d_nconn = nullptr;
   CKT(cudaMalloc(&d_nconn, 4));
   CKT(cudaMemset(d_nconn, 0, 4));
-  {
-    uint64_t cn_base = 0;
-    for (size_t li = 0; li < order.size(); ++li) {
-      const uint32_t B = order[li];
-      const uint32_t nB = lcount[B];
-      if (__builtin_popcount(B) < 2 || nB == 0) continue;
-      for (int l = 0; l < L; ++l) {
-        if (!(B >> l & 1u)) continue;
-        const uint32_t A = B & ~(1u << l);
-        const hkey km = host_key_mask(h, A);
-        k_project<<<nblk(nB), 256>>>(v.node_key + lfirst[B], km, lfirst[B], nB, (hkey*)b_pk.p, (uint32_t*)b_pi.p);
-        CKT(ss.sort((const hkey*)b_pk.p, (hkey*)b_sk.p, (const uint32_t*)b_pi.p, (uint32_t*)b_si.p, nB, sh));
-        k_heads<<<nblk(nB), 256>>>((const hkey*)b_sk.p, nB, (uint32_t*)b_flag.p);
-        k_next_head<<<nblk(nB), 256>>>((const uint32_t*)b_flag.p, nB, (uint32_t*)b_head.p);
-        k_conn_heads<<<nblk(nB), 256>>>((const uint32_t*)b_flag.p, (const hkey*)b_sk.p, nB, v, A, l, (uint32_t)cn_base,
-                                        (uint32_t*)v.cn_start, (uint32_t*)v.cn_cnt, (const uint32_t*)b_head.p, d_nconn);
-        CKT(cudaMemcpy((uint32_t*)v.cn_adj + cn_base, b_si.p, (size_t)nB * 4, cudaMemcpyDeviceToDevice));
-        cn_base += nB;
+  if (n_cn) {
+    uint64_t* d_pair_off = nullptr;
+    uint32_t *d_pair_child = nullptr, *d_pair_first = nullptr, *d_next = nullptr;
+    uint8_t* d_pair_locus = nullptr;
+    CKT(dalloc((void**)&d_pair_off, (n_pairs + 1) * 8));
+    CKT(dalloc((void**)&d_pair_child, n_pairs * 4));
+    CKT(dalloc((void**)&d_pair_first, n_pairs * 4));
+    CKT(dalloc((void**)&d_pair_locus, n_pairs));
+    CKT(cudaMemcpy(d_pair_off, pair_off.data(), (n_pairs + 1) * 8, cudaMemcpyHostToDevice));
+    CKT(cudaMemcpy(d_pair_child, pair_child.data(), n_pairs * 4, cudaMemcpyHostToDevice));
+    CKT(cudaMemcpy(d_pair_first, pair_first.data(), n_pairs * 4, cudaMemcpyHostToDevice));
+    CKT(cudaMemcpy(d_pair_locus, pair_locus.data(), n_pairs, cudaMemcpyHostToDevice));
+    int pbits = 1;
+    while ((1u << pbits) < n_pairs) ++pbits;
+    const int cbits_tot = CL.cbits + pbits;
+    const bool ctwo = cbits_tot > 64;
+    // groups of consecutive pairs with a bounded number of elements (a pair is never split)
+    uint64_t gmax = 0;
+    {
+      uint32_t a = 0;
+      while (a < n_pairs) {
+        uint32_t b = a + 1;
+        while (b < n_pairs && pair_off[b + 1] - pair_off[a] <= budget) ++b;
+        gmax = std::max(gmax, pair_off[b] - pair_off[a]);
+        a = b;
       }
+    }
+    // the label-pass buffers are reused when they are large enough
+    uint64_t *c_lo = g_lo, *c_hi = g_hi, *cs_lo = s_lo, *cs_hi = s_hi;
+    uint32_t *c_val = g_val, *c_flag = d_flag;
+    if (gmax > Eg || (ctwo && !two)) {
+      CKT(dalloc((void**)&c_lo, gmax * 8));
+      CKT(dalloc((void**)&cs_lo, gmax * 8));
+      CKT(dalloc((void**)&c_val, gmax * 4));
+      CKT(dalloc((void**)&c_flag, gmax * 4));
+      if (ctwo) {
+        CKT(dalloc((void**)&c_hi, gmax * 8));
+        CKT(dalloc((void**)&cs_hi, gmax * 8));
+      }
+    }
+    if (!ctwo) c_hi = cs_hi = nullptr;
+    CKT(dalloc((void**)&d_next, gmax * 4));
+    K0Sorter cs;
+    CKT(cs.reserve(gmax, ctwo));
+    uint32_t a = 0;
+    while (a < n_pairs) {
+      uint32_t b = a + 1;
+      while (b < n_pairs && pair_off[b + 1] - pair_off[a] <= budget) ++b;
+      const uint64_t e0 = pair_off[a], E = pair_off[b] - pair_off[a];
+      if (E) {
+        k0_conn_keys<<<nblk(E), 256>>>(v, CL, d_pair_off, d_pair_child, d_pair_first, a, b - a, e0, E, c_lo, c_hi, c_val);
+        CKT(cs.sort(c_lo, c_hi, c_val, cs_lo, cs_hi, (uint32_t*)v.cn_adj + e0, E, cbits_tot, &launches));
+        k0_heads<<<nblk(E), 256>>>(cs_lo, cs_hi, E, c_flag);
+        k0_next_head<<<nblk(E), 256>>>(c_flag, E, d_next);
+        k0_conn_heads<<<nblk(E), 256>>>(c_flag, d_next, (const uint32_t*)v.cn_adj + e0, E, e0, v, d_pair_off, d_pair_child,
+                                       d_pair_locus, a, b - a, (uint32_t*)v.cn_start, (uint32_t*)v.cn_cnt, d_nconn);
+        launches += 4;
+      }
+      a = b;
     }
   }
   CKT(cudaGetLastError());
   CKT(cudaDeviceSynchronize());
   unsigned int n_conn = 0;
   CKT(cudaMemcpy(&n_conn, d_nconn, 4, cudaMemcpyDeviceToHost));
-  cudaFree(d_nconn);
 
   // ---- reference CSR sentinel quirk (networkx_graph.py:195-196; SURVEY trap T1)
   if (n_nodes > N && N > 0) {
@@ -624,8 +773,11 @@ extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
   }
   CKT(cudaMemcpy(t->image, &h, sizeof(h), cudaMemcpyHostToDevice));
   CKT(cudaDeviceSynchronize());
+  t->build_launches = launches;
+  cleanup(true);
   *out = t;
   return GRIMB_OK;
+#undef CKT
 }
 
 
@@ -636,6 +788,8 @@ extern "C" int grimb_tables_free(GrimbTables* t) {
   delete t;
   return GRIMB_OK;
 }
+
+extern "C" int64_t grimb_tables_build_launches(const GrimbTables* t) { return t ? t->build_launches : 0; }
 
 extern "C" int grimb_tables_info(const GrimbTables* t, GrimbTableInfo* info) {
   if (!t || !info) return fail(GRIMB_E_ARG, "null argument");
@@ -752,12 +906,9 @@ __global__ void k_classify(GrimbBatch B, int L, const uint32_t* list, const unsi
 #ifndef KI_MIN_BLOCKS
 #define KI_MIN_BLOCKS 4   /* 64 registers: 8 CTAs of 128 threads per SM; measured 13-18 % faster on C4 than 124 registers / 4 CTAs */
 #endif
-__global__ void __launch_bounds__(MAXT, KI_MIN_BLOCKS)
-k_impute(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O, char* arena, uint64_t arena_per_cta,
-         const double* ones, unsigned long long* work, const uint32_t* buckets, const unsigned int* bucket_n,
-         uint64_t stride) {
-  __shared__ Shared sh;
-  Subject S;
+
+static __device__ __forceinline__ void init_subject(Subject& S, Shared& sh, const TablesView& T, const GrimbConfig* cfg,
+                                                    const double* ones, char* arena, uint64_t arena_per_cta) {
   S.g.tid = threadIdx.x;
   S.g.n = blockDim.x;
   S.g.scratch = sh.scratch;
@@ -767,6 +918,54 @@ k_impute(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArr
   S.ones = ones;
   S.ar_base = arena + (uint64_t)blockIdx.x * arena_per_cta;
   S.ar_cap = arena_per_cta;
+  S.pre = nullptr;
+  S.pre_j = 0xFFFFFFFFu;
+}
+
+// Cooperative CTA group for the heaviest subjects (cost bucket 0 of k_classify: long allele lists,
+// Cartesian products of up to number_of_options_threshold candidates per phase and side).  The unit of
+// work of this kernel is one (subject, phase, side) slot, drawn from a global ticket counter, so up to
+// 2^L CTAs open, probe and reduce the slots of ONE subject at the same time (open_phases + adjs_query +
+// convert_list_to_one_dim, impute.py:914-989, nxg.py:253-278, impute.py:424-442); k_impute, launched next,
+// starts such a subject from the finished top-K lists instead of walking its slots one after the other.
+// (It is the same entry point as k_impute, launched with mode = 1: ptxas 12.9 crashes when the per-subject
+// routines are reachable from two different kernels.)
+static __device__ __forceinline__ void impute_slots(Subject& S, Shared& sh, const TablesView& T, const GrimbConfig* __restrict__ cfg,
+                                                    const GrimbBatch& B, const OutArrays& O, unsigned long long* ticket,
+                                                    const uint32_t* buckets, const unsigned int* bucket_n, const PreView& pv) {
+  uint32_t nheavy = bucket_n[0];
+  if (nheavy > pv.max_subjects) nheavy = pv.max_subjects;
+  if (nheavy == 0) return;   // uniform over the grid
+  const uint64_t items = (uint64_t)nheavy * pv.slots_per_subject;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned long long w = atomicAdd(ticket, 1ull);
+      sh.work = (uint32_t)(w < items ? w : 0xFFFFFFFFull);
+    }
+    __syncthreads();
+    const uint32_t w = sh.work;
+    if (w == 0xFFFFFFFFu) break;
+    const uint32_t j = w / pv.slots_per_subject;
+    const int slot = (int)(w % pv.slots_per_subject);
+    const uint64_t s = buckets[j];   // bucket 0
+    run_slot_item(S, B, O, s, j, slot, pv);
+  }
+}
+
+__global__ void __launch_bounds__(MAXT, KI_MIN_BLOCKS)
+k_impute(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O, char* arena, uint64_t arena_per_cta,
+         const double* ones, unsigned long long* work, const uint32_t* buckets, const unsigned int* bucket_n,
+         uint64_t stride, PreView pv, int mode) {
+  __shared__ Shared sh;
+  Subject S;
+  init_subject(S, sh, T, cfg, ones, arena, arena_per_cta);
+  const PreView pvl = pv;   // a local copy: the subject keeps a pointer to it
+  if (mode == 1) {          // cooperative slot pass over the heaviest subjects (`work` = its ticket counter)
+    impute_slots(S, sh, T, cfg, B, O, work, buckets, bucket_n, pvl);
+    return;
+  }
+  S.pre = &pvl;
   uint64_t bound[GRIMB_BUCKETS + 1];
   bound[0] = 0;
   for (int k = 0; k < GRIMB_BUCKETS; ++k) bound[k + 1] = bound[k] + bucket_n[k];
@@ -779,6 +978,8 @@ k_impute(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArr
     if (w >= bound[GRIMB_BUCKETS]) break;
     int k = 0;
     while (w >= bound[k + 1]) ++k;
+    // the heaviest subjects come first: bucket 0, entry w -> its lists from the cooperative slot kernel
+    S.pre_j = (k == 0 && w < pv.max_subjects && pv.top != nullptr) ? (uint32_t)w : 0xFFFFFFFFu;
     run_subject(S, B, O, (uint64_t)buckets[(uint64_t)k * stride + (w - bound[k])]);
   }
 }
@@ -1881,6 +2082,7 @@ enum {
   CNT_WORKLIST = 1,   // (u32) subjects handed from a warp-per-subject kernel to the general kernel
   CNT_BUCKETS = 2,    // (4 x u32) cost buckets of the general kernel's work
   CNT_OVERFLOW = 4,   // (u32) subjects with more candidate phases than a hand-over record holds
+  CNT_SLOT_TICKET = 5,   // tickets of the cooperative slot kernel
   CNT_CHUNK_END = 8,
   CNT_HAP = 8,
   CNT_POP = 9,
@@ -1916,6 +2118,9 @@ struct GrimbEngine {
   DevBuf in[6], outb[5], in_mask;
   DevBuf worklist;   // subjects the fast kernel hands to the general kernel
   DevBuf buckets;    // the general kernel's work, by cost bucket (heaviest first)
+  DevBuf pre_top, pre_meta;   // Plan A side lists of the heaviest subjects (cooperative slot kernel)
+  uint32_t pre_max = 0;       // subjects the buffers hold (GRIMB_GROUP_SUBJECTS; 0 disables the slot kernel)
+  int pre_K = 0;
   int sm_count = 0;
   int fast_path = 1; // GRIMB_FAST=0 disables the warp-per-subject kernel (debugging / A-B runs)
   int fast_split = 1; // k_fast_probe + k_fast_score (default); GRIMB_FAST_SPLIT=0: the fused k_impute_fast
@@ -1925,6 +2130,8 @@ struct GrimbEngine {
   DevBuf overflow;    // subjects with more candidate phases than a hand-over record holds
   cudaEvent_t ev_score[2] = {nullptr, nullptr};
   int ev_score_valid = 0;
+  cudaEvent_t ev_slots[2] = {nullptr, nullptr};
+  int ev_slots_valid = 0;
   // CUDA events around the last launch of k_impute_fast [0,1], k_impute [2,3], k_impute_typed [4,5]
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int ev_valid[3] = {0, 0, 0};
@@ -2009,6 +2216,12 @@ extern "C" int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes
   const char* hev = getenv("GRIMB_HOST_EVENTS");
   if (hev && hev[0] == '1') e->timing_host = 1;
   for (int i = 0; i < 2; ++i) CKE(cudaEventCreate(&e->ev_score[i]));
+  for (int i = 0; i < 2; ++i) CKE(cudaEventCreate(&e->ev_slots[i]));
+  e->pre_max = 4096;
+  if (const char* gs = getenv("GRIMB_GROUP_SUBJECTS")) {
+    const long long v = atoll(gs);
+    if (v >= 0 && v <= (1 << 20)) e->pre_max = (uint32_t)v;
+  }
   const char* th = getenv("GRIMB_THREADS");
   if (th) {
     int v = atoi(th);
@@ -2038,6 +2251,8 @@ extern "C" int grimb_engine_free(GrimbEngine* e) {
     if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   for (int i = 0; i < 2; ++i)
     if (e->ev_score[i]) cudaEventDestroy(e->ev_score[i]);
+  for (int i = 0; i < 2; ++i)
+    if (e->ev_slots[i]) cudaEventDestroy(e->ev_slots[i]);
   if (e->h_cnt) cudaFreeHost(e->h_cnt);
   if (e->h_tail) cudaFreeHost(e->h_tail);
   cudaGetLastError();
@@ -2052,6 +2267,14 @@ extern "C" int64_t grimb_engine_launches(const GrimbEngine* e) { return e ? e->l
 // has finished.  < 0 if not launched.  which = 3: subjects the last call handed on to k_impute.
 extern "C" double grimb_engine_kernel_ms(const GrimbEngine* e, int which) {
   if (e && which == 3) return e->last_worklist;
+  if (e && which == 5) {   // k_impute_slots
+    float ms5 = -1.f;
+    if (!e->ev_slots_valid || cudaEventElapsedTime(&ms5, e->ev_slots[0], e->ev_slots[1]) != cudaSuccess) {
+      cudaGetLastError();
+      return -1.0;
+    }
+    return (double)ms5;
+  }
   if (e && which == 4) {
     float ms4 = -1.f;
     if (!e->ev_score_valid || cudaEventElapsedTime(&ms4, e->ev_score[0], e->ev_score[1]) != cudaSuccess) {
@@ -2111,6 +2334,7 @@ static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBat
                           cudaStream_t st, bool timed) {
   e->ev_valid[0] = e->ev_valid[1] = e->ev_valid[2] = 0;
   e->ev_score_valid = 0;
+  e->ev_slots_valid = 0;
   if (batch->n_subjects <= 0) return GRIMB_OK;
   // the warp-per-subject kernels implement the default phase enumeration and row layout only
   const bool warp_kernels = e->fast_path && !batch->phase_mask && !cfg->hap_pop_pair;
@@ -2200,9 +2424,40 @@ static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBat
   }
   int grid = e->n_ctas;
   if ((int64_t)grid > batch->n_subjects) grid = (int)batch->n_subjects;
+  // cooperative slot kernel for the heaviest subjects (bucket 0), then the general kernel
+  PreView pv;
+  memset(&pv, 0, sizeof(pv));
+  if (e->pre_max > 0 && !batch->phase_mask) {
+    const uint32_t spp = 1u << tv.L;
+    const uint32_t K = (uint32_t)cfg->max_haps_in_phase;
+    uint64_t fit = e->pre_max;
+    const uint64_t budget = 1ull << 31;   // bytes of top lists
+    const uint64_t per_subject = (uint64_t)spp * K * sizeof(TopItem);
+    if (fit * per_subject > budget) fit = budget / per_subject;
+    if ((int64_t)fit > batch->n_subjects) fit = (uint64_t)batch->n_subjects;
+    if (fit > 0) {
+      CK(e->pre_top.reserve(fit * per_subject + 16));
+      CK(e->pre_meta.reserve(fit * spp * 12 + 16));
+      pv.top = (TopItem*)e->pre_top.p;
+      pv.n = (uint32_t*)e->pre_meta.p;
+      pv.ne = pv.n + fit * spp;
+      pv.ready = pv.ne + fit * spp;
+      pv.max_subjects = (uint32_t)fit;
+      pv.slots_per_subject = spp;
+      pv.K = K;
+      if (tm) CK(cudaEventRecord(e->ev_slots[0], st));
+      k_impute<<<grid, e->threads, 0, st>>>(tv, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones,
+                                           e->d_counters + CNT_SLOT_TICKET, (const uint32_t*)e->buckets.p, bucket_n, stride, pv, 1);
+      CK(cudaGetLastError());
+      if (tm) CK(cudaEventRecord(e->ev_slots[1], st));
+      e->ev_slots_valid = tm;
+      e->launches += 1;
+    }
+  }
+  if (getenv("GRIMB_GROUP_LOAD") && getenv("GRIMB_GROUP_LOAD")[0] == '0') pv.top = nullptr;   // debugging: lists computed, not used
   if (tm) CK(cudaEventRecord(e->ev[2], st));
   k_impute<<<grid, e->threads, 0, st>>>(tv, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones, e->d_counters + CNT_WORK,
-                                       (const uint32_t*)e->buckets.p, bucket_n, stride);
+                                       (const uint32_t*)e->buckets.p, bucket_n, stride, pv, 0);
   CK(cudaGetLastError());
   if (tm) CK(cudaEventRecord(e->ev[3], st));
   e->ev_valid[1] = tm;

@@ -15,7 +15,23 @@ struct BlockList {
   uint32_t n;
 };
 
+// Plan A side lists computed ahead of the subject's own CTA by the cooperative slot kernel
+// (k_impute_slots in grimb200.cu): for the heaviest subjects of a batch every (phase, side) "slot" is
+// opened, probed and reduced to its top-K list by a CTA of its own, so that up to 2^L CTAs work on one
+// subject at once; the subject's CTA then starts from the finished lists.
+struct PreView {
+  TopItem* top;            // [max_subjects][slots_per_subject][K]
+  uint32_t* n;             // [max_subjects][slots_per_subject] list length
+  uint32_t* ne;            // ... the probe returned anything (sh->nonempty)
+  uint32_t* ready;         // ... 1: list valid (slot opened in its original variant, no workspace overflow)
+  uint32_t max_subjects;
+  uint32_t slots_per_subject;   // 2^L
+  uint32_t K;
+};
+
 struct Subject : Ctx {
+  const PreView* pre;   // nullptr: none
+  uint32_t pre_j;       // this subject's index in the pre-computed lists (0xFFFFFFFF: none)
   hkey* chunk_extra;  // [g.n] arena: key bits re-inserted by the missing-data path
   GrimbHapRow* st_hap[2];
   GrimbPopRow* st_pop[2];
@@ -152,46 +168,53 @@ struct Subject : Ctx {
   }
 
   // Returns the number of opened phases.
+  // opens one (phase, side): Cartesian mode below the options threshold, else the filter of the typed
+  // label's nodes (open_phases, impute.py:914-989)
+  GDN void open_slot(int slot) {
+    const uint64_t thr_opt = (uint64_t)cfg->options_threshold;
+    SlotDesc sd = slots[slot];
+    uint64_t opt = slot_options(slot, sd.var);
+    if (opt < thr_opt) {
+      g.sync();
+      if (g.tid == 0) {
+        sd.mode = 0;
+        sd.ncand = opt;
+        sd.filt = nullptr;
+        slots[slot] = sd;
+      }
+    } else {
+      const uint32_t first = T.label_first[typed], cnt = T.label_count[typed];
+      uint32_t found = 0;
+      for (uint32_t b = 0; b < cnt; b += g.n) {
+        uint32_t i = b + g.tid;
+        found += g.sum((i < cnt && node_in_lists(first + i, slot, sd.var)) ? 1u : 0u);
+      }
+      uint32_t* lst = alloc<uint32_t>(found ? found : 1);
+      if (ws_fail) return;
+      uint32_t w = 0;
+      for (uint32_t b = 0; b < cnt; b += g.n) {
+        uint32_t i = b + g.tid;
+        bool in = i < cnt && node_in_lists(first + i, slot, sd.var);
+        uint32_t total;
+        uint32_t pos = g.scan_excl(in ? 1u : 0u, total);
+        if (in) lst[w + pos] = first + i;
+        w += total;
+      }
+      g.sync();
+      if (g.tid == 0) {
+        sd.mode = 1;
+        sd.ncand = found;
+        sd.filt = lst;
+        slots[slot] = sd;
+      }
+    }
+  }
+
   GDN int open_all() {
     g.sync();
-    const uint64_t thr_opt = (uint64_t)cfg->options_threshold;
     for (int slot = 0; slot < 2 * nph; ++slot) {
-      SlotDesc sd = slots[slot];
-      uint64_t opt = slot_options(slot, sd.var);
-      if (opt < thr_opt) {
-        g.sync();
-        if (g.tid == 0) {
-          sd.mode = 0;
-          sd.ncand = opt;
-          sd.filt = nullptr;
-          slots[slot] = sd;
-        }
-      } else {
-        const uint32_t first = T.label_first[typed], cnt = T.label_count[typed];
-        uint32_t found = 0;
-        for (uint32_t b = 0; b < cnt; b += g.n) {
-          uint32_t i = b + g.tid;
-          found += g.sum((i < cnt && node_in_lists(first + i, slot, sd.var)) ? 1u : 0u);
-        }
-        uint32_t* lst = alloc<uint32_t>(found ? found : 1);
-        if (ws_fail) return 0;
-        uint32_t w = 0;
-        for (uint32_t b = 0; b < cnt; b += g.n) {
-          uint32_t i = b + g.tid;
-          bool in = i < cnt && node_in_lists(first + i, slot, sd.var);
-          uint32_t total;
-          uint32_t pos = g.scan_excl(in ? 1u : 0u, total);
-          if (in) lst[w + pos] = first + i;
-          w += total;
-        }
-        g.sync();
-        if (g.tid == 0) {
-          sd.mode = 1;
-          sd.ncand = found;
-          sd.filt = lst;
-          slots[slot] = sd;
-        }
-      }
+      open_slot(slot);
+      if (ws_fail) return 0;
     }
     g.sync();
     int nvalid = 0;
@@ -873,6 +896,132 @@ struct Subject : Ctx {
     plan_c_single = false;
   }
 
+  // ------------------------------------------------------------------ per-subject set-up
+  // lists in GL-string order, phases (gen_phases, impute.py:274-303) and the arena allocations every
+  // later step relies on; `typed` must be set.  Uniform over the group.
+  GDN void setup(const GrimbBatch& B, uint64_t s) {
+    const int L = T.L, P = T.P;
+    // lists (original GL string order)
+    if (g.tid == 0) {
+      sh->fault = 0;
+      const uint16_t* cur = B.alleles + B.allele_off[s];
+      int t = 0;
+      for (int l = 0; l < L; ++l)
+        if (typed >> l & 1u) {
+          for (int x = 0; x < 2; ++x) {
+            const uint32_t c = batch_count(B, s, L, l, x);
+            sh->lptr[VAR_ORIG][t][x] = cur;
+            sh->lcnt[VAR_ORIG][t][x] = (uint16_t)c;
+            cur += c;
+          }
+          ++t;
+        }
+      for (int v = 0; v < NVAR; ++v) sh->lhave[v] = v == VAR_ORIG;
+    }
+    n = 0;
+    for (int l = 0; l < L; ++l)
+      if (typed >> l & 1u) loc[n++] = l;
+    g.sync();
+    // phases (gen_phases impute.py:274-303): keep i unless both orientations were seen
+    if (g.tid == 0) {
+      uint32_t het = 0;
+      for (int t = 0; t < n; ++t) {
+        bool same = sh->lcnt[0][t][0] == sh->lcnt[0][t][1];
+        for (uint32_t i = 0; same && i < sh->lcnt[0][t][0]; ++i) same = sh->lptr[0][t][0][i] == sh->lptr[0][t][1][i];
+        if (!same) het |= 1u << t;
+      }
+      const uint32_t low = het & ((1u << (n - 1)) - 1u);
+      const bool last_het = het >> (n - 1) & 1u;
+      // per-subject phase mask (impute.py:277-290): only the positions in pm may switch sides.  The
+      // first index producing a flip set c is c itself; its mirror image (c ^ low, both
+      // orientations equal when the last locus is homozygous) is only ever produced if low fits pm.
+      const uint32_t pm = B.phase_mask ? (uint32_t)B.phase_mask[s] : 0xFFFFu;
+      const uint32_t eff = low & pm;
+      const bool mirror = !last_het && (low & ~pm) == 0;
+      int k = 0;
+      for (uint32_t i = 0; i < (1u << (n - 1)); ++i) {
+        if (i & ~eff) continue;
+        if (mirror && i > (low ^ i)) continue;
+        sh->ph[k++] = (uint16_t)i;
+      }
+      sh->cnt[0] = k;
+    }
+    g.sync();
+    nph = sh->cnt[0];
+    g.sync();
+    const int ns = 2 * nph;
+    slots = alloc<SlotDesc>(ns);
+    top = alloc<TopItem>((uint64_t)ns * K);
+    top_n = alloc<uint32_t>(ns);
+    slot_ne = alloc<uint32_t>(ns);
+    capsel = (uint32_t)(2 * K + (int)SEL_IPT * g.n + 64);
+    if (capsel < 2048) capsel = 2048;
+    sel = alloc<SelItem>(capsel);
+    sel2 = alloc<SelItem>(capsel);
+    sel_idx = alloc<uint32_t>(capsel);
+    chunk_extra = alloc<hkey>(g.n);
+    st_hap[0] = alloc<GrimbHapRow>(cfg->n_results);
+    st_hap[1] = alloc<GrimbHapRow>(cfg->n_results);
+    st_pop[0] = alloc<GrimbPopRow>(cfg->n_pop_results > 0 ? cfg->n_pop_results : 1);
+    st_pop[1] = alloc<GrimbPopRow>(cfg->n_pop_results > 0 ? cfg->n_pop_results : 1);
+    st_pair = alloc<GrimbPopRow>(cfg->hap_pop_pair ? (cfg->n_results > 0 ? cfg->n_results : 1) : 1);
+    st_cnt = alloc<uint32_t>(4);
+    Msubj = B.priors + (uint64_t)batch_prior(B, s) * P * P;
+    M = Msubj;
+    if (!ws_fail) {
+      if (g.tid == 0) {
+        for (int q = 0; q < ns; ++q) {
+          SlotDesc sd;
+          sd.ncand = 0;
+          sd.filt = nullptr;
+          sd.var = VAR_ORIG;
+          sd.mode = 0;
+          sd.valid = 0;
+          sd.pad = 0;
+          sd.first_row = NEVER_ROW;
+          sd.cached_row = 0xFFFFFFFFu;
+          slots[q] = sd;
+        }
+        for (int q = 0; q < 4; ++q) st_cnt[q] = 0;
+      }
+    }
+  }
+
+  // one slot for the cooperative slot kernel: opens the slot and its partner (a phase only counts when both
+  // of its sides open, impute.py:987-988), then the Plan A probe + top-K of the slot.  false: not usable.
+  GDN bool prepass_slot(int slot) {
+    g.sync();   // the slot descriptors were initialised by one thread (setup)
+    open_slot(slot);
+    if (!ws_fail) open_slot(slot ^ 1);
+    g.sync();
+    if (ws_fail || slots[slot].ncand == 0 || slots[slot ^ 1].ncand == 0) return false;
+    if (g.tid == 0) {
+      top_n[slot] = 0;
+      slot_ne[slot] = 0;
+    }
+    slot_plan_a(slot);
+    g.sync();
+    return !ws_fail && sh->fault == 0;
+  }
+
+  // the slot's Plan A list as computed by the cooperative slot kernel, if there is one (uniform over the group)
+  GD bool load_pre(int slot) {
+    if (pre == nullptr || pre_j == 0xFFFFFFFFu || slots[slot].var != VAR_ORIG) return false;
+    const uint64_t idx = (uint64_t)pre_j * pre->slots_per_subject + (uint32_t)slot;
+    if ((uint32_t)slot >= pre->slots_per_subject || !pre->ready[idx]) return false;
+    g.sync();
+    const uint32_t cnt = pre->n[idx];
+    const TopItem* src = pre->top + idx * pre->K;
+    TopItem* dst = top + (uint64_t)slot * K;
+    for (uint32_t i = g.tid; i < cnt; i += g.n) dst[i] = src[i];
+    if (g.tid == 0) {
+      top_n[slot] = cnt;
+      slot_ne[slot] = pre->ne[idx];
+    }
+    g.sync();
+    return true;
+  }
+
   // ------------------------------------------------------------------ epsilon schedule
   // call_comp_phase_prob (impute.py:1658-1724).  Leaves the final (deduplicated) accepted
   // pairs in ent[0..ent_n) and returns the plan that produced them.
@@ -886,10 +1035,10 @@ struct Subject : Ctx {
     g.sync();
     for (int p = 0; p < nph; ++p) {
       if (!slots[2 * p].valid) continue;
-      slot_plan_a(2 * p);
+      if (!load_pre(2 * p)) slot_plan_a(2 * p);
       if (ws_fail) return GRIMB_PLAN_A;
       g.sync();
-      if (slot_ne[2 * p]) slot_plan_a(2 * p + 1);  // side 2 only if side 1 returned anything
+      if (slot_ne[2 * p] && !load_pre(2 * p + 1)) slot_plan_a(2 * p + 1);  // side 2 only if side 1 returned anything
       if (ws_fail) return GRIMB_PLAN_A;
     }
     double eps = cfg->epsilon;
@@ -1032,90 +1181,8 @@ GD void run_subject(Subject& S, const GrimbBatch& B, const OutArrays& O, uint64_
   if (S.typed == 0) {
     status = GRIMB_ST_SKIPPED;
   } else {
-    // lists (original GL string order)
-    if (g.tid == 0) {
-      sh->fault = 0;
-      const uint16_t* cur = B.alleles + B.allele_off[s];
-      int t = 0;
-      for (int l = 0; l < L; ++l)
-        if (S.typed >> l & 1u) {
-          for (int x = 0; x < 2; ++x) {
-            const uint32_t c = batch_count(B, s, L, l, x);
-            sh->lptr[VAR_ORIG][t][x] = cur;
-            sh->lcnt[VAR_ORIG][t][x] = (uint16_t)c;
-            cur += c;
-          }
-          ++t;
-        }
-      for (int v = 0; v < NVAR; ++v) sh->lhave[v] = v == VAR_ORIG;
-    }
-    S.n = 0;
-    for (int l = 0; l < L; ++l)
-      if (S.typed >> l & 1u) S.loc[S.n++] = l;
-    g.sync();
-    // phases (gen_phases impute.py:274-303): keep i unless both orientations were seen
-    if (g.tid == 0) {
-      const int n = S.n;
-      uint32_t het = 0;
-      for (int t = 0; t < n; ++t) {
-        bool same = sh->lcnt[0][t][0] == sh->lcnt[0][t][1];
-        for (uint32_t i = 0; same && i < sh->lcnt[0][t][0]; ++i) same = sh->lptr[0][t][0][i] == sh->lptr[0][t][1][i];
-        if (!same) het |= 1u << t;
-      }
-      const uint32_t low = het & ((1u << (n - 1)) - 1u);
-      const bool last_het = het >> (n - 1) & 1u;
-      // per-subject phase mask (impute.py:277-290): only the positions in pm may switch sides.  The
-      // first index producing a flip set c is c itself; its mirror image (c ^ low, both
-      // orientations equal when the last locus is homozygous) is only ever produced if low fits pm.
-      const uint32_t pm = B.phase_mask ? (uint32_t)B.phase_mask[s] : 0xFFFFu;
-      const uint32_t eff = low & pm;
-      const bool mirror = !last_het && (low & ~pm) == 0;
-      int k = 0;
-      for (uint32_t i = 0; i < (1u << (n - 1)); ++i) {
-        if (i & ~eff) continue;
-        if (mirror && i > (low ^ i)) continue;
-        sh->ph[k++] = (uint16_t)i;
-      }
-      sh->cnt[0] = k;
-    }
-    g.sync();
-    S.nph = sh->cnt[0];
-    g.sync();
-    const int ns = 2 * S.nph;
-    S.slots = S.alloc<SlotDesc>(ns);
-    S.top = S.alloc<TopItem>((uint64_t)ns * S.K);
-    S.top_n = S.alloc<uint32_t>(ns);
-    S.slot_ne = S.alloc<uint32_t>(ns);
-    S.capsel = (uint32_t)(2 * S.K + (int)SEL_IPT * g.n + 64);
-    if (S.capsel < 2048) S.capsel = 2048;
-    S.sel = S.alloc<SelItem>(S.capsel);
-    S.sel2 = S.alloc<SelItem>(S.capsel);
-    S.sel_idx = S.alloc<uint32_t>(S.capsel);
-    S.chunk_extra = S.alloc<hkey>(g.n);
-    S.st_hap[0] = S.alloc<GrimbHapRow>(cfg->n_results);
-    S.st_hap[1] = S.alloc<GrimbHapRow>(cfg->n_results);
-    S.st_pop[0] = S.alloc<GrimbPopRow>(cfg->n_pop_results > 0 ? cfg->n_pop_results : 1);
-    S.st_pop[1] = S.alloc<GrimbPopRow>(cfg->n_pop_results > 0 ? cfg->n_pop_results : 1);
-    S.st_pair = S.alloc<GrimbPopRow>(cfg->hap_pop_pair ? (cfg->n_results > 0 ? cfg->n_results : 1) : 1);
-    S.st_cnt = S.alloc<uint32_t>(4);
-    S.Msubj = B.priors + (uint64_t)batch_prior(B, s) * P * P;
-    S.M = S.Msubj;
+    S.setup(B, s);
     if (!S.ws_fail) {
-      if (g.tid == 0) {
-        for (int q = 0; q < ns; ++q) {
-          SlotDesc sd;
-          sd.ncand = 0;
-          sd.filt = nullptr;
-          sd.var = VAR_ORIG;
-          sd.mode = 0;
-          sd.valid = 0;
-          sd.pad = 0;
-          sd.first_row = NEVER_ROW;
-          sd.cached_row = 0xFFFFFFFFu;
-          S.slots[q] = sd;
-        }
-        for (int q = 0; q < 4; ++q) S.st_cnt[q] = 0;
-      }
       g.sync();
       S.compute_exist(VAR_ORIG);
       // the rest of the arena holds the accepted pairs of the evaluation in progress
@@ -1244,6 +1311,55 @@ GD void run_subject(Subject& S, const GrimbBatch& B, const OutArrays& O, uint64_
     for (uint32_t i = g.tid; i < npair; i += g.n) R.pop_rows[pb + nup + npp + i] = S.st_pair[i];
   }
   g.sync();
+}
+
+// One work item of the cooperative slot pass: slot `slot` of the subject at position j of the heavy list.
+// All threads of the group call it with identical arguments.
+GD void run_slot_item(Subject& S, const GrimbBatch& B, const OutArrays& O, uint64_t s, uint32_t j, int slot, const PreView& pv) {
+  const Grp& g = S.g;
+  const GrimbConfig* cfg = S.cfg;
+  const uint64_t idx = (uint64_t)j * pv.slots_per_subject + (uint32_t)slot;
+  g.sync();
+  S.ar_used = 0;
+  S.ws_fail = false;
+  S.pair_evals = 0;
+  S.c_probes = S.c_hits = 0;
+  S.c_vecs = 0;
+  S.plan_c_single = false;
+  S.ent_n = 0;
+  S.full = (1u << S.T.L) - 1u;
+  S.typed = B.typed_mask[s];
+  S.K = cfg->max_haps_in_phase;
+  bool ok = S.typed != 0;
+  if (ok) {
+    S.setup(B, s);
+    ok = !S.ws_fail && slot < 2 * S.nph;
+  }
+  if (ok) ok = S.prepass_slot(slot);
+  if (ok) {
+    const uint32_t cnt = S.top_n[slot];
+    const TopItem* src = S.top + (uint64_t)slot * S.K;
+    TopItem* dst = pv.top + idx * pv.K;
+    for (uint32_t i = g.tid; i < cnt; i += g.n) dst[i] = src[i];
+    if (g.tid == 0) {
+      pv.n[idx] = cnt;
+      pv.ne[idx] = S.slot_ne[slot];
+    }
+    // the probes of this slot are counted here; the subject's own CTA loads the list instead of probing
+    const uint64_t np = g.sum64((uint64_t)S.c_probes), nh = g.sum64((uint64_t)S.c_hits);
+    if (g.tid == 0) {
+      if (np) atom_add64(O.probe_counters + 0, (unsigned long long)np);
+      if (nh) atom_add64(O.probe_counters + 1, (unsigned long long)nh);
+      if (S.c_vecs) atom_add64(O.probe_counters + 2, (unsigned long long)S.c_vecs);
+    }
+  }
+  g.sync();
+  if (g.tid == 0) {
+#if GRIMB_DEVICE
+    __threadfence();
+#endif
+    pv.ready[idx] = ok ? 1u : 0u;
+  }
 }
 
 }  // namespace grimb

@@ -80,7 +80,33 @@ int grimb_emu_impute(const GrimbEmuTables* t, const GrimbConfig* cfg, const Grim
   O.word_counter = &wc;
   O.general_counter = &gc;
   O.evals_counter = &ec;
-  for (int64_t s = 0; s < batch->n_subjects; ++s) run_subject(S, *batch, O, (uint64_t)s);
+  // GRIMB_EMU_GROUP=1: the cooperative slot pass (run_slot_item for every slot of every subject) first, then
+  // every subject starts from the pre-computed Plan A lists -- the CPU twin of k_impute's mode 1 / mode 0
+  PreView pv;
+  memset(&pv, 0, sizeof(pv));
+  const char* grp = getenv("GRIMB_EMU_GROUP");
+  if (grp && grp[0] == '1' && !batch->phase_mask && batch->n_subjects > 0) {
+    const uint32_t spp = 1u << t->L, K = (uint32_t)cfg->max_haps_in_phase;
+    const uint64_t nS = (uint64_t)batch->n_subjects;
+    pv.top = (TopItem*)malloc(nS * spp * K * sizeof(TopItem));
+    pv.n = (uint32_t*)calloc(nS * spp, 4);
+    pv.ne = (uint32_t*)calloc(nS * spp, 4);
+    pv.ready = (uint32_t*)calloc(nS * spp, 4);
+    pv.max_subjects = (uint32_t)nS;
+    pv.slots_per_subject = spp;
+    pv.K = K;
+    for (uint64_t s = 0; s < nS; ++s)
+      for (uint32_t q = 0; q < spp; ++q) run_slot_item(S, *batch, O, s, (uint32_t)s, (int)q, pv);
+    S.pre = &pv;
+  }
+  for (int64_t s = 0; s < batch->n_subjects; ++s) {
+    S.pre_j = pv.top ? (uint32_t)s : 0xFFFFFFFFu;
+    run_subject(S, *batch, O, (uint64_t)s);
+  }
+  free(pv.top);
+  free(pv.n);
+  free(pv.ne);
+  free(pv.ready);
   res->totals[0] = (int64_t)wc;
   res->totals[1] = (int64_t)gc;
   res->totals[2] = (int64_t)hc;

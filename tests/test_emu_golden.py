@@ -34,3 +34,15 @@ def test_emulated_kernel_matches_reference_files(name):
     out, exp = run_case(name)
     for k in goldenlib.KEYS:
         assert out[k] == exp[k], "%s: %s differs" % (name, k)
+
+
+@pytest.mark.parametrize("name", ["g1_readme_donor", "g2_edges", "g4_amb6", "g4_amb12_over_threshold", "g4_low_threshold",
+                                  "g4_unknown_heavy", "g5_messy_cau", "g3_pop3_messy", "g6_nine_loci"])
+def test_cooperative_slot_pass_gives_the_same_files(name, monkeypatch):
+    """The cooperative CTA group of the heaviest subjects (k_impute mode 1: every (phase, side) slot opened,
+    probed and reduced to its top-K list by a group of its own; mode 0 then starts from the lists) -- here with
+    EVERY subject sent through it, on the emulation build: same files as the reference."""
+    monkeypatch.setenv("GRIMB_EMU_GROUP", "1")
+    out, exp = run_case(name)
+    for k in goldenlib.KEYS:
+        assert out[k] == exp[k], "%s: %s differs" % (name, k)
