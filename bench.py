@@ -60,6 +60,23 @@ def make_table(n_full):
     return names, (tup + 1).astype(np.uint16), f.reshape(n, 1).astype(np.float64)
 
 
+def pack_batch(alleles, key_bits, n_alleles):
+    """ABI v4 packed form of fully typed, unambiguous subjects: [S][2] keys (side-0 / side-1 alleles packed with
+    the tables' key layout) + [S] flag words (bits 0-4 heterozygous, 5-9 / 10-14 allele absent from the table)."""
+    S, L = alleles.shape[0], alleles.shape[1]
+    keys = np.zeros((S, 2), np.uint64)
+    flags = np.zeros(S, np.uint16)
+    shift = 0
+    for l in range(L):
+        a0, a1 = alleles[:, l, 0].astype(np.uint64), alleles[:, l, 1].astype(np.uint64)
+        keys[:, 0] |= a0 << np.uint64(shift)
+        keys[:, 1] |= a1 << np.uint64(shift)
+        flags |= ((a0 != a1).astype(np.uint16) << l) | ((a0 > n_alleles[l]).astype(np.uint16) << (5 + l)) \
+            | ((a1 > n_alleles[l]).astype(np.uint16) << (10 + l))
+        shift += int(key_bits[l])
+    return np.ascontiguousarray(keys.reshape(-1)), flags
+
+
 def make_subjects(full_alleles, freqs, n_subj, seed):
     """Encoded batch (GrimbBatch arrays) of fully typed unambiguous subjects."""
     rng = np.random.RandomState(seed)
@@ -179,6 +196,88 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------- reference arm
+def _reference_graph(names, full_alleles, freqs):
+    """The UNMODIFIED reference's Graph (oracle/_ref/grim/imputation/networkx_graph.py), filled in memory with
+    the full-haplotype nodes of the synthetic table instead of being loaded from nodes/edges CSV files (the
+    reference's own generator needs ~10 minutes for a table of this size).  Every subject of this workload is
+    served by Plan A, whose only store access is the full-label dict lookup of Graph.adjs_query, so the
+    per-subject work the reference performs is unchanged."""
+    from grim.imputation.networkx_graph import Graph
+    g = Graph({"full_loci": "12345", "nodes_for_plan_A": []})
+    cols = [np.array(names[l], dtype=object)[full_alleles[:, l] - 1] for l in range(5)]
+    verts = []
+    for i in range(len(full_alleles)):
+        nm = "~".join(c[i] for c in cols)
+        g.Vertices_attributes[nm] = ("12345", [float(freqs[i, 0])], i)
+        verts.append(nm)
+    g.Whole_Vertices_attributes = g.Vertices_attributes
+    g.Vertices = np.array(verts, dtype=np.object_)
+    g.Whole_Vertices = g.Vertices
+    g.Edges = np.zeros(0, np.uint32)
+    g.Whole_Edges = np.zeros(0, np.uint32)
+    g.Neighbors_start = np.zeros(len(verts) + 1, np.uint32)
+    g.Whole_Neighbors_start = g.Neighbors_start
+    return g
+
+
+def reference_rate(g, lines, procs):
+    """subjects/s of the reference's own Imputation.impute_file over `lines`, one forked process per core on
+    a contiguous chunk with the graph inherited by fork (the strategy of the reference's scripts/runfile_mp.py)."""
+    import contextlib
+    import multiprocessing as mp
+    import tempfile
+
+    from grim.imputation.impute import Imputation
+    tmp = tempfile.mkdtemp(prefix="grimref_")
+    conf = base_conf()
+    per = (len(lines) + procs - 1) // procs
+
+    def work(w, q):
+        sub = lines[w * per:(w + 1) * per]
+        inp = os.path.join(tmp, "in%d.csv" % w)
+        with open(inp, "w") as f:
+            f.writelines(sub)
+        lm = dict(conf["loci_map"])
+        config = {
+            "planb": True, "pops": conf["populations"], "priority": conf["priority"], "epsilon": conf["epsilon"],
+            "number_of_results": conf["number_of_results"], "number_of_pop_results": conf["number_of_pop_results"],
+            "output_MUUG": True, "output_haplotypes": True, "imputation_input_file": inp,
+            "imputation_out_umug_freq_file": os.path.join(tmp, "o%d.umug" % w),
+            "imputation_out_umug_pops_file": os.path.join(tmp, "o%d.umug.pops" % w),
+            "imputation_out_hap_freq_file": os.path.join(tmp, "o%d.pmug" % w),
+            "imputation_out_hap_pops_file": os.path.join(tmp, "o%d.pmug.pops" % w),
+            "imputation_out_miss_file": os.path.join(tmp, "o%d.miss" % w),
+            "imputation_out_problem_file": os.path.join(tmp, "o%d.problem" % w),
+            "factor_missing_data": conf.get("factor_missing_data", 0.01), "loci_map": lm,
+            "matrix_planb": conf["Plan_B_Matrix"], "pops_count_file": "", "use_pops_count_file": False,
+            "number_of_options_threshold": 100000, "max_haplotypes_number_in_phase": 100,
+            "bin_imputation_input_file": "None", "nodes_for_plan_A": [], "save_mode": False, "UNK_priors": "MR",
+            "full_loci": "12345",
+        }
+        imp = Imputation(g, config)
+        t = time.time()
+        with open(os.devnull, "w") as null, contextlib.redirect_stdout(null):   # two prints + a timing per subject
+            imp.impute_file(config)
+        rows = sum(1 for _ in open(config["imputation_out_umug_freq_file"]))
+        prob = sum(1 for _ in open(config["imputation_out_problem_file"]))
+        q.put((time.time() - t, rows, prob))
+
+    q = mp.Queue()
+    t0 = time.time()
+    ps = [mp.Process(target=work, args=(w, q)) for w in range(procs) if w * per < len(lines)]
+    for p_ in ps:
+        p_.start()
+    res = [q.get() for _ in ps]
+    for p_ in ps:
+        p_.join()
+    wall = time.time() - t0
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    if sum(r[1] for r in res) < len(lines) * 0.9 or sum(r[2] for r in res):
+        raise RuntimeError("the reference did not impute the sample: %s" % (res[:3],))
+    return len(lines) / wall, wall
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -186,11 +285,28 @@ def run_reference(args, rank):
     _batch, alleles = make_subjects(fa, ff, args.subjects, SUBJECT_SEED)
     cores = os.cpu_count() or 1
     n_sample = min(args.subjects, args.ref_sample * cores)
-    g = _FullOnlyGraph(names, fa, ff)
     lines = subject_lines(names, alleles, 0, n_sample)
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    kind = "port"
+    if os.path.isdir(os.path.join(ref_dir, "grim")):
+        # the reference itself, vendored by oracle/build_ref.sh (no product module is imported in this arm)
+        sys.path.insert(0, ref_dir)
+        try:
+            g = _reference_graph(names, fa, ff)
+            reference_rate(g, lines[:cores * 8], cores)     # import / fork check
+            kind = "reference"
+        except Exception as exc:   # e.g. a Python minor version the prebuilt cutils does not load on
+            sys.stderr.write("reference arm: falling back to the port (%r)\n" % (exc,))
+            sys.path.remove(ref_dir)
+    if kind == "port":
+        g = _FullOnlyGraph(names, fa, ff)
     vals = []
     for _ in range(args.warmup + args.steps):
-        rate, erate, wall, prob = cpu_port_rate(g, lines, cores)
+        if kind == "reference":
+            rate, wall = reference_rate(g, lines, cores)
+            erate = 0.0
+        else:
+            rate, erate, wall, prob = cpu_port_rate(g, lines, cores)
         vals.append((rate, erate, wall))
     vals = vals[args.warmup:]
     rate = float(np.mean([v[0] for v in vals]))
@@ -198,11 +314,13 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "subjects_per_sec", "value": rate, "unit": "subjects/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * float(np.mean([v[2] for v in vals])),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "pair_evals_per_sec": float(np.mean([v[1] for v in vals])),
+        "pair_evals_per_sec": (float(np.mean([v[1] for v in vals])) if kind == "port" else None),
         "config": workload_config(args),
-        "cpu_baseline": {"value": rate, "unit": "subjects/s", "cores": cores, "kind": "port",
-                         "sample": "first %d of the %d subjects, %d forked processes (oracle/grim_oracle.py; the "
-                                   "reference is pure Python and cannot travel to the GPU box)" % (n_sample, args.subjects, cores)},
+        "cpu_baseline": {"value": rate, "unit": "subjects/s", "cores": cores, "kind": kind,
+                         "sample": ("first %d of the %d subjects, %d forked processes, " % (n_sample, args.subjects, cores))
+                         + ("the unmodified reference (oracle/_ref, vendored by oracle/build_ref.sh): its own "
+                            "Imputation.impute_file per chunk, Graph filled in memory with the table's full-haplotype nodes"
+                            if kind == "reference" else "oracle/grim_oracle.py (oracle/_ref absent)")},
         "e2e": {"value": rate, "unit": "subjects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -233,6 +351,7 @@ def main():
     ap.add_argument("--c3-subjects", type=int, default=1 << 18)
     ap.add_argument("--c4-subjects", type=int, default=4000)
     ap.add_argument("--c4-heavy-subjects", type=int, default=400)
+    ap.add_argument("--c4-wide-subjects", type=int, default=16)
     ap.add_argument("--c5-haps", type=int, default=100000)
     ap.add_argument("--c5-subjects", type=int, default=1 << 16)
     ap.add_argument("--config-sample", type=int, default=300, help="subjects per configuration checked against the oracle")
@@ -306,7 +425,15 @@ def main():
         t = torch.from_numpy(a)
         return t.pin_memory() if pin else t
 
-    keys_in = ["typed_mask", "allele_off", "alleles", "priors"]
+    # the batch in the packed form of ABI v4 (18 bytes per subject: two packed keys + a flag word), which is
+    # what the tokeniser emits for input of this shape; GRIMB_BENCH_PACKED=0 measures the general form
+    use_packed = os.environ.get("GRIMB_BENCH_PACKED", "1") != "0"
+    if use_packed:
+        pk, pf = pack_batch(alleles, g.key_bits, [len(a) for a in names])
+        batch = {"packed_keys": pk.view(np.int64), "packed_flags": pf, "priors": batch["priors"]}
+        keys_in = ["packed_keys", "packed_flags", "priors"]
+    else:
+        keys_in = ["typed_mask", "allele_off", "alleles", "priors"]
     # result capacities: 16-byte records for everybody, a few 8-byte words for subjects with several accepted
     # phases, and room for the subjects the general kernel serves (none in this workload)
     word_cap, gen_cap, hap_cap, pop_cap = S * 2, S // 8 + 1024, S // 4 + 1024, S // 4 + 1024
@@ -318,7 +445,7 @@ def main():
         b.n_subjects = S
         for k in keys_in:
             setattr(b, k, inputs[k].data_ptr())
-        b.n_alleles_total = S * 10
+        b.n_alleles_total = 0 if use_packed else S * 10
         b.n_priors = 1
         r = _lib.Results()
         r.compact = outs["compact"].data_ptr()
@@ -455,11 +582,11 @@ def main():
 
     if rank == 0:
         total = S * world
-        # algorithmic bytes (DESIGN.md "Measurement"): per subject its input (26 B: typed mask, offset, ten
-        # allele ids), 2^L = 32 probes x one 32 B sector, per hit a 32 B frequency sector [the probe kernel];
+        # algorithmic bytes (DESIGN.md "Measurement"): per subject its input (packed: 18 B = two keys + flags),
+        # 2^L = 32 probes x one 32 B sector, per hit a 32 B frequency sector [the probe kernel];
         # the 16 B result record plus the words written [the score kernel].  The hand-over record between the
         # two is not counted.
-        in_bytes_subject = (batch["typed_mask"].nbytes + batch["allele_off"].nbytes + batch["alleles"].nbytes) / S
+        in_bytes_subject = sum(batch[k].nbytes for k in keys_in if k != "priors") / S
         out_bytes = sum(out_n[k] * SZ[k] for k in SZ)
         algo_probe = int(S * (in_bytes_subject + 32 * 32) + hits * 2 * 32)
         algo_path = algo_probe + out_bytes

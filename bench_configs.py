@@ -230,6 +230,11 @@ def run_all(args, names, fa, ff1, torch, dev, stream, peak):
                               peak, steps=3, workspace=[512 << 20, 4 << 30],
                               note="6-40 alleles per side, products on both sides of the 100,000-option threshold, "
                                    "0-3 missing loci; README table; 512 MB workspace tier")
+    wide = synth.wide_subjects(tab, args.c4_wide_subjects, 45, races=["CAU,CAU"])
+    out["C4_wide"] = measure("C4_wide", g4, cfg4, cbp4, wide, og4, conf4, min(8, args.config_sample), torch, dev, stream, peak,
+                             steps=3, workspace=[128 << 20, 4 << 30],
+                             note="fully typed, 7-9 alleles per side: Cartesian products of 16,807-59,049 candidates per "
+                                  "phase and side, under the threshold (cooperative slot pass); README table")
     g4.close()
     # ---- C5
     loci = ["A", "B", "C", "DPA1", "DPB1", "DQA1", "DQB1", "DRB1", "DRBX"]

@@ -156,6 +156,16 @@ typedef struct {
   const uint16_t* phase_mask;   /* optional [S] (NULL = none): bit m set = the m-th TYPED locus may switch
                                    sides when phases are enumerated (bin_imputation_in_file,
                                    impute.py:277-290,2001-2005,2030-2032)                              */
+  /* ABI v4, PACKED form (optional; 64-bit-key build, L <= 5): for a batch in which every subject is typed
+   * at every locus with exactly one allele per chromosome side -- or is to be skipped -- the subject is
+   * 18 bytes: packed_keys[s] = {k0, k1}, its side-0 / side-1 alleles packed with the tables' key layout
+   * (field of locus l at bit sum(key_bits[0..l)); subject-local ids of unknown alleles included), and
+   * packed_flags[s]: bits 0..4 locus heterozygous (a0 != a1), bits 5..9 side-0 allele not a table allele,
+   * bits 10..14 side-1 allele not a table allele, bit 15 skip the subject (GRIMB_ST_SKIPPED).  When
+   * packed_keys is non-NULL, typed_mask / counts / allele_off / alleles / phase_mask are ignored (may be
+   * NULL) and n_alleles_total is 0. */
+  const uint64_t* packed_keys;  /* [S][2] or NULL                                                    */
+  const uint16_t* packed_flags; /* [S]                                                               */
 } GrimbBatch;
 
 /* Result rows.  A hap row is two packed keys + probability: for UMUG the per-locus (min id,

@@ -885,7 +885,7 @@ __global__ void k_classify(GrimbBatch B, int L, const uint32_t* list, const unsi
   const uint64_t n = list ? (uint64_t)*list_n : (uint64_t)B.n_subjects;
   for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n; w += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t s = list ? list[w] : (uint32_t)w;
-    const uint32_t typed = B.typed_mask[s];
+    const uint32_t typed = batch_typed(B, s, (1u << L) - 1u);
     // candidates per phase ~ product of the listed alleles; phases = 2^(typed-1); an untyped
     // locus multiplies the hits (top links / whole-label scans in Plan B)
     float a = 1.f, b = 1.f;
@@ -1026,7 +1026,19 @@ struct FastIn {
   double m;
 };
 
-__device__ __forceinline__ void fast_load(FastIn& in, const GrimbBatch& B, uint64_t s, int L, int i) {
+__device__ __forceinline__ void fast_load(FastIn& in, const GrimbBatch& B, uint64_t s, int L, int i, const TablesView& T) {
+  if (B.packed_keys) {   // packed form: lane l takes the two alleles of locus l out of the subject's keys
+    const uint32_t fl = B.packed_flags[s];
+    in.typed = (fl & 0x8000u) ? 0u : ((1u << L) - 1u);
+    in.c = 0x00010001u;
+    in.pair = 0;
+    if (i < L) {
+      const uint64_t k0 = B.packed_keys[2 * s], k1 = B.packed_keys[2 * s + 1];
+      in.pair = (uint32_t)key_field(T, k0, i) | ((uint32_t)key_field(T, k1, i) << 16);
+    }
+    in.m = __ldg(B.priors + batch_prior(B, s));
+    return;
+  }
   in.typed = B.typed_mask[s];
   const uint32_t off = B.allele_off[s];
   // the listed counts of one subject are 2L uint16 = L aligned uint32; every count must be 1
@@ -1156,14 +1168,14 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
   uint64_t sx_next = 0;
   if (s < S) {
     sx_next = LIST ? (uint64_t)list[s] : s;
-    fast_load(nxt, B, sx_next, L, i);
+    fast_load(nxt, B, sx_next, L, i, T);
   }
   for (; s < S; s += stride) {   // the two halves may leave the loop one iteration apart
     const FastIn in = nxt;
     const uint64_t sx = sx_next;   // the subject this iteration serves
     if (s + stride < S) {
       sx_next = LIST ? (uint64_t)list[s + stride] : s + stride;
-      fast_load(nxt, B, sx_next, L, i);
+      fast_load(nxt, B, sx_next, L, i, T);
     }
     bool done = false;  // finished here (rows, an empty result, or a skipped subject)
     uint32_t acc = 0, rank = 0, n_acc = 0, evals = 0, gsel = 0;
@@ -1376,9 +1388,22 @@ struct __align__(16) FastMid {
 // allele_off[s+1] - allele_off[s] == 2L and the counts need not be read.
 struct ProbeIn {
   uint32_t typed, nall, pair;
+  uint64_t k0, k1;   // packed form only
 };
 
+// PACKED (include/grimb200.h): the subject is its two packed haplotype keys and a flag word -- no cooperative
+// key build, no cross-lane reduction before the probes
+template <bool PACKED>
 __device__ __forceinline__ void probe_load(ProbeIn& in, const GrimbBatch& B, uint32_t s, int L, int i) {
+  if (PACKED) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(B.packed_keys) + s);   // the same 16 bytes for the half-warp
+    in.k0 = (uint64_t)v.x | ((uint64_t)v.y << 32);
+    in.k1 = (uint64_t)v.z | ((uint64_t)v.w << 32);
+    in.typed = B.packed_flags[s];
+    in.nall = in.pair = 0;
+    return;
+  }
+  in.k0 = in.k1 = 0;
   in.typed = B.typed_mask[s];
   const uint32_t off = B.allele_off[s];
   in.nall = B.allele_off[s + 1] - off;
@@ -1389,6 +1414,7 @@ __device__ __forceinline__ void probe_load(ProbeIn& in, const GrimbBatch& B, uin
   }
 }
 
+template <bool PACKED>
 __global__ void __launch_bounds__(FAST_WARPS * 32, FASTPROBE_MIN_BLOCKS)
 k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid, uint32_t* worklist,
              unsigned int* worklist_n, uint32_t* overflow, unsigned int* overflow_n, int nchain_ok) {
@@ -1409,23 +1435,36 @@ k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid,
   const uint32_t stride = gridDim.x * FAST_WARPS * 2;
   uint32_t s = (blockIdx.x * FAST_WARPS + warp) * 2 + half;
   ProbeIn nxt;
-  if (s < S) probe_load(nxt, B, s, L, i);
+  if (s < S) probe_load<PACKED>(nxt, B, s, L, i);
   for (; s < S; s += stride) {
     const ProbeIn in = nxt;
-    if (s + stride < S && s + stride > s) probe_load(nxt, B, s + stride, L, i);
-    const uint32_t typed = in.typed;
-    const bool shape = typed == full && nchain_ok && in.nall == 2u * (uint32_t)L;   // uniform in the half-warp
+    if (s + stride < S && s + stride > s) probe_load<PACKED>(nxt, B, s + stride, L, i);
+    // packed form: in.typed is the flag word (bit 15 = skip); every subject that is not skipped has the shape
+    const uint32_t typed = PACKED ? ((in.typed & 0x8000u) ? 0u : full) : in.typed;
+    const bool shape = typed == full && nchain_ok && (PACKED || in.nall == 2u * (uint32_t)L);   // uniform in the half-warp
     uint32_t state = 0, ncand = 0, same = 0, phases = 0;
     if (shape) {
-      const uint32_t a0 = in.pair & 0xffffu, a1 = in.pair >> 16;
-      const uint64_t k0 = half_or64(hmask, (uint64_t)a0 << my_shift);
-      const uint64_t k1 = half_or64(hmask, (uint64_t)a1 << my_shift);
-      // four per-locus flags in one OR-reduction: byte k of `packed` is the locus mask of flag k
-      uint32_t bits = 0;
-      if (i < L)
-        bits = ((((a0 - 1u) >= my_nal) ? 1u : 0u) | (((a1 - 1u) >= my_nal) ? 0x100u : 0u) | ((a0 != a1) ? 0x10000u : 0u)) << i;
-      const uint32_t packed = __reduce_or_sync(hmask, bits);
-      const uint32_t unk0 = packed & 0xFFu, unk1 = (packed >> 8) & 0xFFu, het = (packed >> 16) & 0xFFu;
+      uint64_t k0, k1;
+      uint32_t unk0, unk1, het;
+      if (PACKED) {
+        k0 = in.k0;
+        k1 = in.k1;
+        het = in.typed & 31u;
+        unk0 = (in.typed >> 5) & 31u;
+        unk1 = (in.typed >> 10) & 31u;
+      } else {
+        const uint32_t a0 = in.pair & 0xffffu, a1 = in.pair >> 16;
+        k0 = half_or64(hmask, (uint64_t)a0 << my_shift);
+        k1 = half_or64(hmask, (uint64_t)a1 << my_shift);
+        // three per-locus flags in one OR-reduction: byte k of `packed` is the locus mask of flag k
+        uint32_t bits = 0;
+        if (i < L)
+          bits = ((((a0 - 1u) >= my_nal) ? 1u : 0u) | (((a1 - 1u) >= my_nal) ? 0x100u : 0u) | ((a0 != a1) ? 0x10000u : 0u)) << i;
+        const uint32_t packed = __reduce_or_sync(hmask, bits);
+        unk0 = packed & 0xFFu;
+        unk1 = (packed >> 8) & 0xFFu;
+        het = (packed >> 16) & 0xFFu;
+      }
       same = het == 0u ? 1u : 0u;
       const uint64_t D = k0 ^ k1;
       const uint64_t key = k0 ^ (D & Mi), key2 = key ^ D;
@@ -1737,23 +1776,32 @@ k_impute_typed(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, 
   unsigned long long evals_sum = 0;   // pair evaluations of the subjects this warp finishes (warp-uniform)
   unsigned long long n_probes = 0, n_hits = 0, n_vecs = 0;   // of every subject this warp looked at (warp-uniform)
   for (uint64_t s = (uint64_t)blockIdx.x * TY_WARPS + warp; s < S; s += (uint64_t)gridDim.x * TY_WARPS) {
-    const uint32_t typed = B.typed_mask[s];
+    const uint32_t typed = batch_typed(B, s, full);
     if (typed == 0) {   // GRIMB_ST_SKIPPED
       if (lane == 0) R.compact[s] = make_compact(GRIMB_ST_SKIPPED, GRIMB_KIND_GENERAL, 0, 0xFFFFFFFFu, 0.0);
       continue;
     }
     // one allele per side at every locus: every typed side lists >= 1 allele, so the total says it all
-    const uint32_t al_off = B.allele_off[s];
-    const bool shape = typed == full && nchain >= 0 && B.allele_off[s + 1] - al_off == 2u * (uint32_t)L;
+    const bool is_packed = B.packed_keys != nullptr;
+    const uint32_t al_off = is_packed ? 0u : B.allele_off[s];
+    const bool shape = typed == full && nchain >= 0 && (is_packed || B.allele_off[s + 1] - al_off == 2u * (uint32_t)L);
     uint32_t pairs[GRIMB_MAX_LOCI];
     uint32_t het = 0;
     if (shape) {
       const uint16_t* al = B.alleles + al_off;
+#if GRIMB_KW == 1
+      const uint64_t pk0 = is_packed ? B.packed_keys[2 * s] : 0ull, pk1 = is_packed ? B.packed_keys[2 * s + 1] : 0ull;
+#endif
 #pragma unroll
       for (int l = 0; l < GRIMB_MAX_LOCI; ++l) {
         pairs[l] = 0;
         if (l < L) {
+#if GRIMB_KW == 1
+          const uint32_t a0 = is_packed ? (uint32_t)key_field(T, pk0, l) : al[2 * l];
+          const uint32_t a1 = is_packed ? (uint32_t)key_field(T, pk1, l) : al[2 * l + 1];
+#else
           const uint32_t a0 = al[2 * l], a1 = al[2 * l + 1];
+#endif
           pairs[l] = a0 | (a1 << 16);
           if (a0 != a1) het |= 1u << l;
         }
@@ -2337,7 +2385,7 @@ static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBat
   e->ev_slots_valid = 0;
   if (batch->n_subjects <= 0) return GRIMB_OK;
   // the warp-per-subject kernels implement the default phase enumeration and row layout only
-  const bool warp_kernels = e->fast_path && !batch->phase_mask && !cfg->hap_pop_pair;
+  const bool warp_kernels = e->fast_path && (!batch->phase_mask || batch->packed_keys) && !cfg->hap_pop_pair;
   const TablesView& tv = e->tables->view;
   const uint32_t* wl = nullptr;
   const unsigned int* wl_n = nullptr;
@@ -2365,8 +2413,12 @@ static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBat
       CK(e->overflow.reserve((size_t)batch->n_subjects * 4 + 16));
       unsigned int* ovf_n = (unsigned int*)(e->d_counters + CNT_OVERFLOW);
       if (tm) CK(cudaEventRecord(e->ev[0], st));
-      k_fast_probe<<<(unsigned)fgp, FAST_WARPS * 32, 0, st>>>(tv, *batch, O, (FastMid*)e->mid.p, (uint32_t*)e->worklist.p,
-                                                            cnt, (uint32_t*)e->overflow.p, ovf_n, eps > 0 ? 0 : 1);
+      if (batch->packed_keys)
+        k_fast_probe<true><<<(unsigned)fgp, FAST_WARPS * 32, 0, st>>>(tv, *batch, O, (FastMid*)e->mid.p, (uint32_t*)e->worklist.p,
+                                                                    cnt, (uint32_t*)e->overflow.p, ovf_n, eps > 0 ? 0 : 1);
+      else
+        k_fast_probe<false><<<(unsigned)fgp, FAST_WARPS * 32, 0, st>>>(tv, *batch, O, (FastMid*)e->mid.p, (uint32_t*)e->worklist.p,
+                                                                     cnt, (uint32_t*)e->overflow.p, ovf_n, eps > 0 ? 0 : 1);
       CK(cudaGetLastError());
       if (tm) CK(cudaEventRecord(e->ev[1], st));
       uint64_t sg = ((uint64_t)batch->n_subjects + 127) / 128;
@@ -2427,7 +2479,7 @@ static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBat
   // cooperative slot kernel for the heaviest subjects (bucket 0), then the general kernel
   PreView pv;
   memset(&pv, 0, sizeof(pv));
-  if (e->pre_max > 0 && !batch->phase_mask) {
+  if (e->pre_max > 0 && (!batch->phase_mask || batch->packed_keys)) {
     const uint32_t spp = 1u << tv.L;
     const uint32_t K = (uint32_t)cfg->max_haps_in_phase;
     uint64_t fit = e->pre_max;
@@ -2465,6 +2517,18 @@ static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBat
   return GRIMB_OK;
 }
 
+static int check_batch(const GrimbBatch* b, const GrimbTables* t) {
+  if (b->n_subjects < 0 || b->n_subjects > 0x7FFFFFF0ll) return fail(GRIMB_E_ARG, "bad n_subjects");
+  if (b->n_subjects == 0) return GRIMB_OK;
+  if (b->packed_keys) {
+    if (GRIMB_KW != 1 || t->h.L > 5) return fail(GRIMB_E_ARG, "packed batches need the 64-bit-key build and L <= 5");
+    if (!b->packed_flags || !b->priors) return fail(GRIMB_E_ARG, "packed batch: packed_flags / priors missing");
+    return GRIMB_OK;
+  }
+  if (!b->typed_mask || !b->allele_off || !b->alleles || !b->priors) return fail(GRIMB_E_ARG, "batch arrays missing");
+  return GRIMB_OK;
+}
+
 static int check_results(const GrimbResults* r) {
   if (!r->compact || !r->totals) return fail(GRIMB_E_ARG, "GrimbResults.compact / totals missing");
   if (r->word_capacity < 0 || r->general_capacity < 0 || r->hap_capacity < 0 || r->pop_capacity < 0)
@@ -2494,6 +2558,8 @@ extern "C" int grimb_impute_device_async(GrimbEngine* e, const GrimbConfig* cfg,
   int rc = check_cfg(cfg, e->tables);
   if (rc) return rc;
   rc = check_results(res);
+  if (rc) return rc;
+  rc = check_batch(batch, e->tables);
   if (rc) return rc;
   CK(cudaSetDevice(e->device));
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
@@ -2536,15 +2602,18 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
   if (rc) return rc;
   rc = check_results(r);
   if (rc) return rc;
+  rc = check_batch(b, e->tables);
+  if (rc) return rc;
   CK(cudaSetDevice(e->device));
   const int L = e->tables->h.L, P = e->tables->h.P;
   const int64_t S = b->n_subjects;
   cudaStream_t st = e->stream;
-  const size_t in_bytes[6] = {(size_t)S * 2, b->counts ? (size_t)S * L * 2 * 2 : 0, (size_t)(S + 1) * 4,
-                              (size_t)b->n_alleles_total * 2, b->prior_index ? (size_t)S * 4 : 0,
+  const bool packed = b->packed_keys != nullptr;   // in[0]: flags, in[3]: keys
+  const size_t in_bytes[6] = {(size_t)S * 2, (b->counts && !packed) ? (size_t)S * L * 2 * 2 : 0, packed ? 0 : (size_t)(S + 1) * 4,
+                              packed ? (size_t)S * 16 : (size_t)b->n_alleles_total * 2, b->prior_index ? (size_t)S * 4 : 0,
                               (size_t)b->n_priors * P * P * 8};
   for (int i = 0; i < 6; ++i) CK(e->in[i].reserve(in_bytes[i] + 64));
-  if (b->phase_mask) CK(e->in_mask.reserve((size_t)S * 2 + 16));
+  if (b->phase_mask && !packed) CK(e->in_mask.reserve((size_t)S * 2 + 16));
   const size_t ob[5] = {(size_t)S * sizeof(GrimbCompact), (size_t)r->word_capacity * 8,
                         (size_t)r->general_capacity * sizeof(GrimbSubjectResult),
                         (size_t)r->hap_capacity * sizeof(GrimbHapRow), (size_t)r->pop_capacity * sizeof(GrimbPopRow)};
@@ -2601,8 +2670,16 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
   // the whole batch back to back while the kernels and the copy-out trail one chunk behind
   for (int c = 0; c < nch; ++c) {
     const int64_t s0 = bound[c], s1 = bound[c + 1], n = s1 - s0;
-    const uint32_t a0 = b->allele_off[s0], a1 = b->allele_off[s1];
     cudaStream_t si = nch > 1 ? e->s_in : st;
+    if (packed) {
+      CK(cudaMemcpyAsync((uint64_t*)e->in[3].p + 2 * s0, b->packed_keys + 2 * s0, (size_t)n * 16, cudaMemcpyHostToDevice, si));
+      CK(cudaMemcpyAsync((uint16_t*)e->in[0].p + s0, b->packed_flags + s0, (size_t)n * 2, cudaMemcpyHostToDevice, si));
+      if (b->prior_index)
+        CK(cudaMemcpyAsync((uint32_t*)e->in[4].p + s0, b->prior_index + s0, (size_t)n * 4, cudaMemcpyHostToDevice, si));
+      if (nch > 1) CK(cudaEventRecord(e->ev_in[c], si));
+      continue;
+    }
+    const uint32_t a0 = b->allele_off[s0], a1 = b->allele_off[s1];
     CK(cudaMemcpyAsync((uint16_t*)e->in[0].p + s0, b->typed_mask + s0, (size_t)n * 2, cudaMemcpyHostToDevice, si));
     if (b->counts)
       CK(cudaMemcpyAsync((uint16_t*)e->in[1].p + s0 * L * 2, b->counts + s0 * L * 2, (size_t)n * L * 4, cudaMemcpyHostToDevice, si));
@@ -2621,12 +2698,19 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
     GrimbBatch db = *b;
     db.n_subjects = n;
     db.typed_mask = (const uint16_t*)e->in[0].p + s0;
-    db.counts = b->counts ? (const uint16_t*)e->in[1].p + s0 * L * 2 : nullptr;
+    db.counts = (b->counts && !packed) ? (const uint16_t*)e->in[1].p + s0 * L * 2 : nullptr;
     db.allele_off = (const uint32_t*)e->in[2].p + s0;   // offsets stay absolute into `alleles`
     db.alleles = (const uint16_t*)e->in[3].p;
+    if (packed) {
+      db.packed_keys = (const uint64_t*)e->in[3].p + 2 * s0;
+      db.packed_flags = (const uint16_t*)e->in[0].p + s0;
+      db.typed_mask = nullptr;
+      db.allele_off = nullptr;
+      db.alleles = nullptr;
+    }
     db.prior_index = b->prior_index ? (const uint32_t*)e->in[4].p + s0 : nullptr;
     db.priors = (const double*)e->in[5].p;
-    db.phase_mask = b->phase_mask ? (const uint16_t*)e->in_mask.p + s0 : nullptr;
+    db.phase_mask = (b->phase_mask && !packed) ? (const uint16_t*)e->in_mask.p + s0 : nullptr;
     GrimbResults cr = dr;
     cr.compact = dr.compact + s0;
     if (c > 0) CK(cudaMemsetAsync(e->d_counters, 0, CNT_CHUNK_END * sizeof(unsigned long long), st));   // per-chunk counters

@@ -8,6 +8,7 @@ namespace grimb {
 
 
 constexpr uint32_t SEL_IPT = 8;  // items per thread between two selector barriers in the streaming loops
+constexpr uint64_t PRE_MIN_CANDIDATES = 2048;   // cooperative slot pass: smallest Cartesian product worth a CTA
 
 struct BlockList {
   const uint32_t* ids;  // nullptr: implicit node-id range
@@ -32,6 +33,11 @@ struct PreView {
 struct Subject : Ctx {
   const PreView* pre;   // nullptr: none
   uint32_t pre_j;       // this subject's index in the pre-computed lists (0xFFFFFFFF: none)
+  // allele-membership bitmasks of the subject's lists, per list variant (arena; built on first use by the
+  // over-threshold filter): bit id of the mask of (typed position t, side x) = table allele id is listed
+  uint32_t* lmask[NVAR];
+  uint32_t lmask_off[MAXL];   // first word of position t's two masks
+  uint32_t lmask_w[MAXL];     // words per mask of position t
   hkey* chunk_extra;  // [g.n] arena: key bits re-inserted by the missing-data path
   GrimbHapRow* st_hap[2];
   GrimbPopRow* st_pop[2];
@@ -95,6 +101,7 @@ struct Subject : Ctx {
   // reduce_phase_to_valid_allels :864-879 (VALID), reduce_phase_to_commons_alleles :881-912
   // (C10: ten best, C1: the best) -- a function of the original list and the prior diagonal.
   GDN void make_variant(int var) {
+    lmask[var] = nullptr;   // the lists of this variant are about to change
     uint32_t total = 0;
     for (int t = 0; t < n; ++t) total += sh->lcnt[VAR_ORIG][t][0] + sh->lcnt[VAR_ORIG][t][1];
     uint16_t* buf = alloc<uint16_t>(total);
@@ -153,18 +160,44 @@ struct Subject : Ctx {
   }
 
   // ------------------------------------------------------------------ opening (open_phases)
+  // every allele of the node is in the slot's lists (cutils.create_hap_list, cutils.pyx:35-51): one bit test
+  // per locus against the membership masks of the variant (ensure_masks)
   GD bool node_in_lists(uint32_t node, int slot, int var) const {
-    hkey k = T.node_key[node];
+    const hkey k = T.node_key[node];
+    const uint32_t* mk = lmask[var];
     for (int t = 0; t < n; ++t) {
-      uint16_t id = (uint16_t)key_field(T, k, loc[t]);
-      int x = side_of(slot, t);
-      const uint16_t* lst = sh->lptr[var][t][x];
-      uint32_t cn = sh->lcnt[var][t][x];
-      bool in = false;
-      for (uint32_t i = 0; i < cn && !in; ++i) in = lst[i] == id;
-      if (!in) return false;
+      const uint32_t id = (uint32_t)key_field(T, k, loc[t]);
+      const uint32_t* w = mk + lmask_off[t] + (uint32_t)side_of(slot, t) * lmask_w[t];
+      if (!((w[id >> 5] >> (id & 31u)) & 1u)) return false;
     }
     return true;
+  }
+
+  // builds the membership masks of a list variant once per subject (uniform over the group)
+  GDN void ensure_masks(int var) {
+    if (lmask[var] != nullptr) return;
+    uint32_t words = 0;
+    for (int t = 0; t < n; ++t) {
+      lmask_w[t] = (T.n_alleles[loc[t]] + 32u) >> 5;
+      lmask_off[t] = words;
+      words += 2u * lmask_w[t];
+    }
+    uint32_t* mk = alloc<uint32_t>(words ? words : 1);
+    if (ws_fail) return;
+    for (uint32_t i = g.tid; i < words; i += g.n) mk[i] = 0;
+    g.sync();
+    for (int t = 0; t < n; ++t)
+      for (int x = 0; x < 2; ++x) {
+        const uint16_t* lst = sh->lptr[var][t][x];
+        const uint32_t cn = sh->lcnt[var][t][x];
+        uint32_t* w = mk + lmask_off[t] + (uint32_t)x * lmask_w[t];
+        for (uint32_t i = g.tid; i < cn; i += g.n) {
+          const uint32_t id = lst[i];
+          if (id >= 1 && id <= T.n_alleles[loc[t]]) atom_or(&w[id >> 5], 1u << (id & 31u));
+        }
+      }
+    g.sync();
+    lmask[var] = mk;
   }
 
   // Returns the number of opened phases.
@@ -183,6 +216,8 @@ struct Subject : Ctx {
         slots[slot] = sd;
       }
     } else {
+      ensure_masks(sd.var);
+      if (ws_fail) return;
       const uint32_t first = T.label_first[typed], cnt = T.label_count[typed];
       uint32_t found = 0;
       for (uint32_t b = 0; b < cnt; b += g.n) {
@@ -901,10 +936,24 @@ struct Subject : Ctx {
   // later step relies on; `typed` must be set.  Uniform over the group.
   GDN void setup(const GrimbBatch& B, uint64_t s) {
     const int L = T.L, P = T.P;
-    // lists (original GL string order)
+    // lists (original GL string order); a packed batch carries the two alleles of every locus inside the
+    // subject's two keys: they are unpacked into the arena
+    uint16_t* unpacked = nullptr;
+#if GRIMB_KW == 1
+    if (B.packed_keys) {
+      unpacked = alloc<uint16_t>(2 * GRIMB_MAX_LOCI);
+      if (g.tid == 0 && !ws_fail) {
+        const uint64_t k0 = B.packed_keys[2 * s], k1 = B.packed_keys[2 * s + 1];
+        for (int l = 0; l < L; ++l) {
+          unpacked[2 * l] = (uint16_t)key_field(T, k0, l);
+          unpacked[2 * l + 1] = (uint16_t)key_field(T, k1, l);
+        }
+      }
+    }
+#endif
     if (g.tid == 0) {
       sh->fault = 0;
-      const uint16_t* cur = B.alleles + B.allele_off[s];
+      const uint16_t* cur = unpacked ? unpacked : B.alleles + B.allele_off[s];
       int t = 0;
       for (int l = 0; l < L; ++l)
         if (typed >> l & 1u) {
@@ -918,6 +967,7 @@ struct Subject : Ctx {
         }
       for (int v = 0; v < NVAR; ++v) sh->lhave[v] = v == VAR_ORIG;
     }
+    for (int v = 0; v < NVAR; ++v) lmask[v] = nullptr;
     n = 0;
     for (int l = 0; l < L; ++l)
       if (typed >> l & 1u) loc[n++] = l;
@@ -935,7 +985,7 @@ struct Subject : Ctx {
       // per-subject phase mask (impute.py:277-290): only the positions in pm may switch sides.  The
       // first index producing a flip set c is c itself; its mirror image (c ^ low, both
       // orientations equal when the last locus is homozygous) is only ever produced if low fits pm.
-      const uint32_t pm = B.phase_mask ? (uint32_t)B.phase_mask[s] : 0xFFFFu;
+      const uint32_t pm = (B.phase_mask && !B.packed_keys) ? (uint32_t)B.phase_mask[s] : 0xFFFFu;
       const uint32_t eff = low & pm;
       const bool mirror = !last_het && (low & ~pm) == 0;
       int k = 0;
@@ -991,6 +1041,10 @@ struct Subject : Ctx {
   // of its sides open, impute.py:987-988), then the Plan A probe + top-K of the slot.  false: not usable.
   GDN bool prepass_slot(int slot) {
     g.sync();   // the slot descriptors were initialised by one thread (setup)
+    // worth a CTA of its own only when the slot is a large Cartesian product: an over-threshold slot is
+    // a short filtered list, a small product is done faster than it is handed over
+    const uint64_t opt = slot_options(slot, VAR_ORIG);
+    if (opt >= (uint64_t)cfg->options_threshold || opt < PRE_MIN_CANDIDATES) return false;
     open_slot(slot);
     if (!ws_fail) open_slot(slot ^ 1);
     g.sync();
@@ -1172,7 +1226,7 @@ GD void run_subject(Subject& S, const GrimbBatch& B, const OutArrays& O, uint64_
   S.plan_c_single = false;
   S.ent_n = 0;
   S.full = (1u << L) - 1u;
-  S.typed = B.typed_mask[s];
+  S.typed = batch_typed(B, s, S.full);
   S.K = cfg->max_haps_in_phase;
   uint8_t status = GRIMB_ST_OK, plan_u = GRIMB_PLAN_NONE, plan_p = GRIMB_PLAN_NONE;
   uint32_t tot_u = 0, tot_p = 0;
@@ -1328,7 +1382,7 @@ GD void run_slot_item(Subject& S, const GrimbBatch& B, const OutArrays& O, uint6
   S.plan_c_single = false;
   S.ent_n = 0;
   S.full = (1u << S.T.L) - 1u;
-  S.typed = B.typed_mask[s];
+  S.typed = batch_typed(B, s, S.full);
   S.K = cfg->max_haps_in_phase;
   bool ok = S.typed != 0;
   if (ok) {

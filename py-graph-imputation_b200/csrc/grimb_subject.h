@@ -97,9 +97,14 @@ struct OutArrays {  // device pointers of GrimbResults + global counters
 
 // batch accessors: `counts` and `prior_index` may be NULL (ABI v4: all ones / all zero)
 GD uint32_t batch_count(const GrimbBatch& B, uint64_t s, int L, int l, int x) {
-  return B.counts ? (uint32_t)B.counts[s * (uint64_t)L * 2 + (uint64_t)l * 2 + x] : 1u;
+  return (B.counts && !B.packed_keys) ? (uint32_t)B.counts[s * (uint64_t)L * 2 + (uint64_t)l * 2 + x] : 1u;
 }
 GD uint32_t batch_prior(const GrimbBatch& B, uint64_t s) { return B.prior_index ? B.prior_index[s] : 0u; }
+// packed form (include/grimb200.h): every subject typed at every locus, one allele per side, or skipped
+GD uint32_t batch_typed(const GrimbBatch& B, uint64_t s, uint32_t full) {
+  if (B.packed_keys) return (B.packed_flags[s] & 0x8000u) ? 0u : full;
+  return B.typed_mask[s];
+}
 
 GD GrimbCompact make_compact(uint32_t status, uint32_t kind_flags, uint32_t phases, uint32_t off, double total) {
   GrimbCompact c;

@@ -200,6 +200,7 @@ struct GrimbText {
   std::vector<uint32_t> name_slot;   // entry index + 1, 0 = empty
   uint32_t name_mask = 0;
   bool fast_path = true;             // GRIMB_TEXT_FAST=0: every line through the general parser (A/B, tests)
+  bool packed_ok = true;             // GRIMB_TEXT_PACKED=0: never the packed batch form (A/B, tests)
   // pinned staging (grow-only)
   struct HostBuf {
     void* p = nullptr;
@@ -237,6 +238,8 @@ struct GrimbText {
     std::vector<std::vector<Unknown>> t_unk;
     std::vector<uint16_t> b_typed, b_counts, b_alleles;
     std::vector<uint32_t> b_off, b_prior;
+    std::vector<uint64_t> b_keys;    // packed form of the batch (include/grimb200.h): [S][2] keys ...
+    std::vector<uint16_t> b_flags;   // ... and [S] flag words
     std::vector<double> priors;   // snapshot of the memoised prior matrices at tokenise time
     GrimbBatch batch;
     HostBuf hb_compact, hb_words, hb_general, hb_hap, hb_pop;
@@ -950,6 +953,8 @@ extern "C" int grimb_text_create(const GrimbTextDesc* d, GrimbText** out) {
   t->mr = d->unk_priors_mr != 0;
   if (const char* fp = getenv("GRIMB_TEXT_FAST"))
     if (fp[0] == '0') t->fast_path = false;
+  if (const char* pk = getenv("GRIMB_TEXT_PACKED"))
+    if (pk[0] == '0') t->packed_ok = false;
   // the fast path relies on the loci ascending in loci_map order == ascending string order of "LOC*"
   for (int l = 1; l < t->L; ++l)
     if (!(t->loci[l - 1] + "*" < t->loci[l] + "*")) t->fast_path = false;
@@ -1029,7 +1034,8 @@ int tokenise_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const char* tex
   S.b_off.resize(NS + 1);
   S.b_prior.resize(NS);
   std::vector<size_t> r_ids((size_t)nt + 1, 0);
-  std::vector<uint8_t> r_multi((size_t)nt, 0), r_prior((size_t)nt, 0);
+  std::vector<uint8_t> r_multi((size_t)nt, 0), r_prior((size_t)nt, 0), r_part((size_t)nt, 0);
+  const uint32_t full_mask = (1u << L) - 1u;
   // parse: every range its own lines; b_off is written relative to the range and re-based below
   t->parallel((size_t)nt, [&](int, size_t klo, size_t khi) {
     std::string clean;
@@ -1044,7 +1050,7 @@ int tokenise_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const char* tex
       sv l_r1, l_r2;
       uint32_t l_prior = 0;
       size_t run = 0;
-      bool multi = false, other_prior = false;
+      bool multi = false, other_prior = false, partial = false;
       while (q < e) {
         const void* f = memchr(q, '\n', (size_t)(e - q));
         const char* le = f ? (const char*)f + 1 : e;
@@ -1070,6 +1076,7 @@ int tokenise_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const char* tex
         if (valid) {
           run += ln.ids_cnt;
           multi = multi || ln.ids_cnt != 2u * (uint32_t)__builtin_popcount(ln.mask);
+          partial = partial || ln.mask != full_mask;
         }
         ++i;
         q = le;
@@ -1077,15 +1084,20 @@ int tokenise_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const char* tex
       r_ids[k + 1] = run;   // == S.t_ids[k].size(): only valid lines leave ids behind
       r_multi[k] = multi;
       r_prior[k] = other_prior;
+      r_part[k] = partial;
     }
   });
   auto tB = clk::now();
-  bool all_single = true, one_prior = true;
+  bool all_single = true, one_prior = true, all_full = true;
   for (int k = 0; k < nt; ++k) {
     r_ids[k + 1] += r_ids[k];
     all_single = all_single && !r_multi[k];
     one_prior = one_prior && !r_prior[k];
+    all_full = all_full && !r_part[k];
   }
+  // packed form (ABI v4): every imputable line is typed at every locus with one allele per side -> the
+  // subject travels as its two packed keys + a flag word (18 bytes) instead of mask, offset and 2L ids
+  const bool packed = GRIMB_KEY_WORDS == 1 && L <= 5 && all_single && all_full && t->packed_ok;
   const size_t total = r_ids[nt];
   S.b_off[NS] = (uint32_t)total;
   {
@@ -1101,11 +1113,36 @@ int tokenise_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const char* tex
   // ABI v4: the counts travel only when some subject lists several alleles on a side (every typed side
   // lists at least one), the prior indices only when more than one prior matrix is in use
   if (!all_single) S.b_counts.assign(NS * (size_t)L * 2, 0);
+  if (packed) {
+    S.b_keys.resize(NS * 2 + 2);
+    S.b_flags.resize(NS + 1);
+  }
   t->parallel((size_t)nt, [&](int, size_t klo, size_t khi) {
     for (size_t k = klo; k < khi; ++k) {
       const uint32_t base = (uint32_t)r_ids[k];
       if (!S.t_ids[k].empty()) memcpy(&S.b_alleles[base], S.t_ids[k].data(), S.t_ids[k].size() * 2);
       for (size_t i = nl[k]; i < nl[k + 1]; ++i) {
+        if (packed) {
+          const Line& ln = S.lines[i];
+          uint64_t k0 = 0, k1 = 0;
+          uint32_t fl = 0x8000u;   // skip
+          if (ln.hclass == H_OK && ln.mask) {
+            const uint16_t* ids = S.t_ids[k].data() + ln.ids_off;
+            fl = 0;
+            for (int l = 0; l < L; ++l) {
+              const uint32_t a0 = ids[2 * l], a1 = ids[2 * l + 1];
+              k0 |= (uint64_t)a0 << t->shift[l];
+              k1 |= (uint64_t)a1 << t->shift[l];
+              const uint32_t ntab = (uint32_t)t->alleles[l].size();
+              fl |= (a0 != a1 ? 1u : 0u) << l;
+              fl |= (a0 > ntab ? 1u : 0u) << (5 + l);
+              fl |= (a1 > ntab ? 1u : 0u) << (10 + l);
+            }
+          }
+          S.b_keys[2 * i] = k0;
+          S.b_keys[2 * i + 1] = k1;
+          S.b_flags[i] = (uint16_t)fl;
+        }
         S.b_off[i] += base;
         if (!all_single) {
           const Line& ln = S.lines[i];
@@ -1126,6 +1163,8 @@ int tokenise_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const char* tex
   b.priors = S.priors.data();
   b.n_priors = (int32_t)(S.priors.size() / ((size_t)t->P * t->P));
   b.phase_mask = nullptr;   // default phase enumeration; masks are served by the numpy host front end
+  b.packed_keys = packed ? S.b_keys.data() : nullptr;
+  b.packed_flags = packed ? S.b_flags.data() : nullptr;
   S.sec_tok = secs(t0, clk::now());
   if (getenv("GRIMB_TEXT_TRACE") && getenv("GRIMB_TEXT_TRACE")[0] == '2')
     fprintf(stderr, "tokenise: count %.1f ms, parse %.1f ms, seq %.1f ms, fill %.1f ms\n", secs(t0, tA) * 1e3, secs(tA, tB) * 1e3,
@@ -1276,6 +1315,8 @@ int run_slot(GrimbText* t, Slot& S, GrimbEngine* const* engines, int32_t n_engin
       sb.alleles = g_all.data();
       sb.n_alleles_total = (int64_t)tot_al;
       sb.prior_index = g_prior.data();
+      sb.packed_keys = nullptr;    // the re-issued subjects travel in the general form
+      sb.packed_flags = nullptr;
     }
     // pinned, grow-only staging; capacities follow what the previous call needed per subject (+25 %)
     GrimbCompact* rc_ = (GrimbCompact*)S.hb_compact.reserve((n + 1) * sizeof(GrimbCompact));

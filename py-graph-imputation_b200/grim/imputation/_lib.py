@@ -56,7 +56,7 @@ class Batch(C.Structure):
         ("n_subjects", C.c_int64), ("typed_mask", C.c_void_p), ("counts", C.c_void_p),
         ("allele_off", C.c_void_p), ("alleles", C.c_void_p), ("n_alleles_total", C.c_int64),
         ("prior_index", C.c_void_p), ("priors", C.c_void_p), ("n_priors", C.c_int32),
-        ("phase_mask", C.c_void_p),
+        ("phase_mask", C.c_void_p), ("packed_keys", C.c_void_p), ("packed_flags", C.c_void_p),
     ]
 
 

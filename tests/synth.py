@@ -324,3 +324,34 @@ def zipf_arrays(n_full, n_alleles, seed, loci):
         fa[:, l] = remap[tup[:, l]]
         out_names.append([names[l][a] for a in used])
     return out_names, fa, f
+
+
+def wide_subjects(table, n, seed, sizes=(7, 8, 9), races=None, prefix="W"):
+    """Fully typed subjects whose every locus side lists `sizes` alleles (the true one first, then random table
+    alleles): Cartesian products of 16,807-59,049 candidates per phase and side, all below the 100,000-option
+    threshold -- the shape for which the reference spends seconds per subject and for which
+    the cooperative slot pass spreads one subject over up to 2^L CTAs."""
+    rng = np.random.RandomState(seed)
+    nl = len(table.loci)
+    out = []
+    for s in range(n):
+        i1, i2 = rng.choice(len(table.haps), size=2, p=table.p)
+        hh = (table.haps[i1], table.haps[i2])
+        sides = []
+        for l in range(nl):
+            pair = []
+            for h in hh:
+                want = int(sizes[rng.randint(len(sizes))])
+                lst = [h[l]]
+                while len(lst) < min(want, len(table.alleles[l])):
+                    b = table.alleles[l][rng.randint(len(table.alleles[l]))]
+                    if b not in lst:
+                        lst.append(b)
+                rng.shuffle(lst)
+                pair.append(lst)
+            sides.append((pair[0], pair[1]))
+        line = "%s%d,%s" % (prefix, s, _gl(sides))
+        if races is not None:
+            line += "," + races[rng.randint(len(races))]
+        out.append(line + "\n")
+    return out

@@ -195,3 +195,30 @@ def test_c5_nine_loci_wide_keys_beyond_plan_a():
     _compare(mine, ref, "C5")
     assert imp.stats["pair_evals"] == evals
     assert imp.stats["plan"][2] + imp.stats["plan"][3] > 0 and imp.stats["plan"][1] > 0
+
+
+def test_c4_wide_subjects_through_the_cooperative_slot_pass():
+    """Fully typed subjects with 7-9 alleles per locus side: Cartesian products of tens of thousands of candidates
+    per phase and side, below the options threshold -- the subjects the cooperative slot pass (k_impute mode 1)
+    spreads over one CTA per (phase, side).  Same files as the oracle, with the pass on and off."""
+    _t, conf, _l, _e = goldenlib.load_case("g1_readme_donor")
+    tab = synth.Table(open(conf["freq_file"]).read())
+    lines = synth.wide_subjects(tab, int(16 * SCALE), 45, races=["CAU,CAU"])
+    from grim.imputation.networkx_graph import Graph
+    from grim.run_impute_def import load_config
+    cfg = load_config(conf)
+    og = go.graph_from_config(conf)
+    ref, evals = oracle_par.oracle_texts(og, conf, lines, go.count_by_prob_from_file(1, conf["pops_count_file"]), warm=0)
+    for group in ("4096", "0"):
+        os.environ["GRIMB_GROUP_SUBJECTS"] = group      # read when an engine is created
+        try:
+            g = Graph(cfg).build_graph()
+            try:
+                mine, imp = _gpu_texts(g, cfg, lines, None)
+                eng = g.engine(imp.workspaces[0])
+            finally:
+                g.close()
+        finally:
+            os.environ.pop("GRIMB_GROUP_SUBJECTS", None)
+        _compare(mine, ref, "C4 wide (slot pass %s)" % ("on" if group != "0" else "off"))
+        assert imp.stats["pair_evals"] == evals
