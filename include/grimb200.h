@@ -249,11 +249,14 @@ typedef struct {
 int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes_per_cta, GrimbEngine** out);
 int grimb_engine_free(GrimbEngine* e);
 
-/* Device-pointer form: batch and result arrays already in HBM.  grimb_impute_device_async enqueues
- * everything on `cuda_stream` (a cudaStream_t, 0 = engine stream) and returns without synchronising;
- * grimb_impute_finish waits for that stream and fills res->totals (the counters travel through pinned
- * memory owned by the engine).  One call may be in flight per engine; calls on one stream queue behind
- * each other, so a caller can enqueue batch k+1 before finishing batch k only with a second engine.
+/* Device-pointer form: batch and result arrays already in HBM.  grimb_impute_device_async enqueues the
+ * warp-per-subject kernels on `cuda_stream` (a cudaStream_t, 0 = engine stream) and returns without
+ * synchronising; grimb_impute_finish waits for that call (an event: work of other engines queued behind it
+ * on the same stream keeps running), launches the tail kernels (overflow list, cost classification,
+ * cooperative slot pass, general kernel) only if some subject was handed on -- or if no warp-per-subject
+ * kernel serves this table / mode -- and fills res->totals.  One call may be in flight per engine: a caller
+ * that wants batch k+1 queued while batch k runs alternates between two engines.  The batch, result and
+ * configuration structs are copied by the async call; the arrays they point at must stay valid until finish.
  * grimb_impute_device = the two together. */
 int grimb_impute_device_async(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch,
                               const GrimbResults* res, void* cuda_stream);

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -1123,7 +1125,8 @@ constexpr uint32_t FAST_CHUNK = GRIMB_FAST_CHUNK;
 template <bool LIST>
 __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_BLOCKS)
 k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O, uint32_t* worklist,
-              unsigned int* worklist_n, const uint32_t* __restrict__ list, const unsigned int* __restrict__ list_n) {
+              unsigned int* worklist_n, const uint32_t* __restrict__ list, const unsigned int* __restrict__ list_n,
+              uint32_t s_begin) {
   __shared__ double s_chain[FAST_MAX_ROUNDS];
   __shared__ int s_nchain;
   if (LIST && *list_n == 0u) return;   // empty overflow list (the usual case): nothing to set up
@@ -1163,7 +1166,8 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
   const uint64_t stride = (uint64_t)gridDim.x * FAST_WARPS * 2;
   uint64_t hap_base = 0, pop_base = 0;   // this half-warp's current chunks (uniform within the half)
   uint32_t hap_left = 0, pop_left = 0;
-  uint64_t s = ((uint64_t)blockIdx.x * FAST_WARPS + warp) * 2 + half;
+  // without a list the kernel serves the subjects [s_begin, n_subjects)
+  uint64_t s = (LIST ? 0ull : (uint64_t)s_begin) + ((uint64_t)blockIdx.x * FAST_WARPS + warp) * 2 + half;
   FastIn nxt;
   uint64_t sx_next = 0;
   if (s < S) {
@@ -1417,7 +1421,7 @@ __device__ __forceinline__ void probe_load(ProbeIn& in, const GrimbBatch& B, uin
 template <bool PACKED>
 __global__ void __launch_bounds__(FAST_WARPS * 32, FASTPROBE_MIN_BLOCKS)
 k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid, uint32_t* worklist,
-             unsigned int* worklist_n, uint32_t* overflow, unsigned int* overflow_n, int nchain_ok) {
+             unsigned int* worklist_n, uint32_t* overflow, unsigned int* overflow_n, int nchain_ok, uint32_t s_begin) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int half = lane >> 4, i = lane & 15, hbase = half << 4;
   const uint32_t hmask = 0xFFFFu << hbase;
@@ -1433,7 +1437,7 @@ k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid,
   const HSlot* __restrict__ ht_base = T.slots + T.ht_off[full];
   const uint32_t S = (uint32_t)B.n_subjects;               // subject indices fit 32 bits (worklists are uint32)
   const uint32_t stride = gridDim.x * FAST_WARPS * 2;
-  uint32_t s = (blockIdx.x * FAST_WARPS + warp) * 2 + half;
+  uint32_t s = s_begin + (blockIdx.x * FAST_WARPS + warp) * 2 + half;   // subjects [s_begin, n_subjects)
   ProbeIn nxt;
   if (s < S) probe_load<PACKED>(nxt, B, s, L, i);
   for (; s < S; s += stride) {
@@ -1519,7 +1523,7 @@ k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid,
 #endif
 __global__ void __launch_bounds__(128, FASTSCORE_MIN_BLOCKS)
 k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O,
-             const FastMid* __restrict__ mid, uint32_t* worklist, unsigned int* worklist_n) {
+             const FastMid* __restrict__ mid, uint32_t* worklist, unsigned int* worklist_n, uint32_t s_begin) {
   __shared__ double s_chain[FAST_MAX_ROUNDS];
   __shared__ int s_nchain;
   const int lane = threadIdx.x & 31;
@@ -1542,7 +1546,8 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
   const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
   unsigned long long evals_sum = 0;
   // whole warps iterate together (the word-space claim is a warp scan)
-  for (uint64_t s0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; s0 < S; s0 += nthreads) {
+  // subjects [s_begin, n_subjects); s_begin is a multiple of 32
+  for (uint64_t s0 = (uint64_t)s_begin + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; s0 < S; s0 += nthreads) {
     const uint64_t s = s0 + lane;
     bool ready = false;
     double m = 0.0;
@@ -1742,7 +1747,7 @@ static inline size_t ty_bytes_per_warp(int P) {
 
 __global__ void __launch_bounds__(TY_WARPS * 32, TY_MIN_BLOCKS)
 k_impute_typed(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O, uint32_t* worklist,
-               unsigned int* worklist_n, uint32_t per_warp) {
+               unsigned int* worklist_n, uint32_t per_warp, uint32_t s_begin) {
   extern __shared__ __align__(16) unsigned char ty_smem[];
   __shared__ double s_chain[TY_MAX_ROUNDS];
   __shared__ int s_nchain;
@@ -1775,7 +1780,7 @@ k_impute_typed(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, 
   const uint64_t S = (uint64_t)B.n_subjects;
   unsigned long long evals_sum = 0;   // pair evaluations of the subjects this warp finishes (warp-uniform)
   unsigned long long n_probes = 0, n_hits = 0, n_vecs = 0;   // of every subject this warp looked at (warp-uniform)
-  for (uint64_t s = (uint64_t)blockIdx.x * TY_WARPS + warp; s < S; s += (uint64_t)gridDim.x * TY_WARPS) {
+  for (uint64_t s = (uint64_t)s_begin + (uint64_t)blockIdx.x * TY_WARPS + warp; s < S; s += (uint64_t)gridDim.x * TY_WARPS) {
     const uint32_t typed = batch_typed(B, s, full);
     if (typed == 0) {   // GRIMB_ST_SKIPPED
       if (lane == 0) R.compact[s] = make_compact(GRIMB_ST_SKIPPED, GRIMB_KIND_GENERAL, 0, 0xFFFFFFFFu, 0.0);
@@ -2122,6 +2127,24 @@ k_impute_typed(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, 
 
 constexpr int GRIMB_MAX_CHUNKS = 64;
 
+// The counters of a chunk reach the host through mapped pinned memory, written by this one-warp kernel on the
+// compute stream: a cudaMemcpyAsync there would queue behind the copy-out stream's large transfers on the
+// device-to-host copy engine and stall the kernels that follow it.
+// the records of the subjects on a hand-over list, gathered for one small copy-out
+__global__ void k_gather_compact(const uint32_t* __restrict__ list, uint32_t n, const GrimbCompact* __restrict__ compact,
+                                 GrimbCompact* __restrict__ out, uint32_t* __restrict__ out_idx) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t s = list[i];
+  out[i] = compact[s];
+  out_idx[i] = s;
+}
+
+__global__ void k_snapshot(const unsigned long long* __restrict__ cnt, unsigned long long* out, int n) {
+  if ((int)threadIdx.x < n) out[threadIdx.x] = cnt[threadIdx.x];
+  __threadfence_system();
+}
+
 // Device counters of one call (unsigned long long each).  The first eight are per launch group (one
 // chunk of a host batch) and are cleared between chunks; the rest keep running across the chunks of one
 // ABI call, so the rows / words / records of a chunk occupy one contiguous range of their arrays.
@@ -2154,18 +2177,27 @@ struct GrimbEngine {
   cudaStream_t stream = nullptr;
   cudaStream_t s_in = nullptr, s_out = nullptr;   // copy-in / copy-out streams of the pipelined host call
   cudaEvent_t ev_in[GRIMB_MAX_CHUNKS], ev_k[GRIMB_MAX_CHUNKS];
-  unsigned long long* h_cnt = nullptr;            // pinned: counters after every chunk [GRIMB_MAX_CHUNKS][CNT_N]
+  unsigned long long* h_cnt = nullptr;            // pinned + mapped: counters after every chunk [GRIMB_MAX_CHUNKS + 1][CNT_N]
+  unsigned long long* h_cnt_dev = nullptr;        // its device address
   int64_t host_chunk = 262144;                    // subjects per pipeline chunk (GRIMB_HOST_CHUNK)
   GrimbConfig cfg_host;                           // the configuration d_cfg holds (valid when cfg_sent)
   int cfg_sent = 0;
   unsigned long long* h_tail = nullptr;           // pinned: the counters as read by the device-pointer call
   cudaStream_t pending_stream = nullptr;          // grimb_impute_device_async: stream of the call in flight
   int pending = 0;
+  cudaEvent_t ev_done = nullptr;                  // ... recorded behind its last operation
+  int tail_queued = 0;                            // ... the tail kernels were queued with it
+  int tail_expected = 0;                          // the previous call of this engine handed subjects on
+  GrimbBatch pend_batch;                          // ... its batch / result views (for the tail, if one is needed)
+  GrimbResults pend_res;
   int64_t launches = 0;
   // staging for the host-pointer form (grow-only)
   DevBuf in[6], outb[5], in_mask;
   DevBuf worklist;   // subjects the fast kernel hands to the general kernel
   DevBuf buckets;    // the general kernel's work, by cost bucket (heaviest first)
+  DevBuf gather;              // records of handed-on subjects, gathered for the copy-out of the host form
+  void* h_gather = nullptr;   // ... their pinned landing buffer
+  size_t h_gather_cap = 0;
   DevBuf pre_top, pre_meta;   // Plan A side lists of the heaviest subjects (cooperative slot kernel)
   uint32_t pre_max = 0;       // subjects the buffers hold (GRIMB_GROUP_SUBJECTS; 0 disables the slot kernel)
   int pre_K = 0;
@@ -2237,7 +2269,8 @@ extern "C" int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes
     CKE(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
     CKE(cudaEventCreateWithFlags(&e->ev_k[i], cudaEventDisableTiming));
   }
-  CKE(cudaMallocHost((void**)&e->h_cnt, GRIMB_MAX_CHUNKS * CNT_N * sizeof(unsigned long long)));
+  CKE(cudaHostAlloc((void**)&e->h_cnt, (GRIMB_MAX_CHUNKS + 1) * CNT_N * sizeof(unsigned long long), cudaHostAllocMapped));
+  CKE(cudaHostGetDevicePointer((void**)&e->h_cnt_dev, e->h_cnt, 0));
   CKE(cudaMallocHost((void**)&e->h_tail, CNT_N * sizeof(unsigned long long)));
   if (const char* hc = getenv("GRIMB_HOST_CHUNK")) {
     const long long v = atoll(hc);
@@ -2265,6 +2298,7 @@ extern "C" int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes
   if (hev && hev[0] == '1') e->timing_host = 1;
   for (int i = 0; i < 2; ++i) CKE(cudaEventCreate(&e->ev_score[i]));
   for (int i = 0; i < 2; ++i) CKE(cudaEventCreate(&e->ev_slots[i]));
+  CKE(cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming));
   e->pre_max = 4096;
   if (const char* gs = getenv("GRIMB_GROUP_SUBJECTS")) {
     const long long v = atoll(gs);
@@ -2301,6 +2335,8 @@ extern "C" int grimb_engine_free(GrimbEngine* e) {
     if (e->ev_score[i]) cudaEventDestroy(e->ev_score[i]);
   for (int i = 0; i < 2; ++i)
     if (e->ev_slots[i]) cudaEventDestroy(e->ev_slots[i]);
+  if (e->ev_done) cudaEventDestroy(e->ev_done);
+  if (e->h_gather) cudaFreeHost(e->h_gather);
   if (e->h_cnt) cudaFreeHost(e->h_cnt);
   if (e->h_tail) cudaFreeHost(e->h_tail);
   cudaGetLastError();
@@ -2377,28 +2413,34 @@ static OutArrays out_arrays(GrimbEngine* e, const GrimbResults& r) {
   return O;
 }
 
-// Launches the kernels for one batch view (device pointers) on `st`; no synchronisation.
-static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch, const OutArrays& O,
-                          cudaStream_t st, bool timed) {
-  e->ev_valid[0] = e->ev_valid[1] = e->ev_valid[2] = 0;
-  e->ev_score_valid = 0;
-  e->ev_slots_valid = 0;
-  if (batch->n_subjects <= 0) return GRIMB_OK;
+// The kernels of one call come in two parts.  launch_warp: the warp-per-subject kernels over the subjects
+// [s_begin, s_end) of the batch (device pointers) -- what they cannot finish is appended to the engine's
+// hand-over lists, which keep growing across the ranges of one call.  launch_tail, once per call after the
+// last range: the fused kernel over the overflow list, the cost classification, the cooperative slot pass
+// and the general kernel over everything that was handed on (or over the whole batch when no
+// warp-per-subject kernel serves this table / mode).  No synchronisation in either.
+static bool warp_kernels_apply(const GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch) {
   // the warp-per-subject kernels implement the default phase enumeration and row layout only
-  const bool warp_kernels = e->fast_path && (!batch->phase_mask || batch->packed_keys) && !cfg->hap_pop_pair;
+  if (!(e->fast_path && (!batch->phase_mask || batch->packed_keys) && !cfg->hap_pop_pair)) return false;
   const TablesView& tv = e->tables->view;
-  const uint32_t* wl = nullptr;
-  const unsigned int* wl_n = nullptr;
-  const uint64_t stride = (uint64_t)batch->n_subjects;
-  const bool tm = timed;   // CUDA events around the kernels (one API call each: off in the chunked host path)
-  CK(e->buckets.reserve((size_t)stride * 4 * GRIMB_BUCKETS + 16));
-  unsigned int* bucket_n = (unsigned int*)(e->d_counters + CNT_BUCKETS);
+#if GRIMB_KW == 1
+  if (tv.L <= 5 && tv.P == 1) return true;
+#endif
+  return e->typed_ctas > 0;
+}
+
+static int launch_warp(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch, const OutArrays& O, cudaStream_t st,
+                       bool tm, int64_t s_begin, int64_t s_end) {
+  const int64_t n = s_end - s_begin;
+  if (n <= 0 || !warp_kernels_apply(e, cfg, batch)) return GRIMB_OK;
+  const TablesView& tv = e->tables->view;
+  GrimbBatch rb = *batch;
+  rb.n_subjects = s_end;   // the kernels walk [s_begin, n_subjects)
+  CK(e->worklist.reserve((size_t)batch->n_subjects * 4 + 16));
   unsigned int* cnt = (unsigned int*)(e->d_counters + CNT_WORKLIST);
 #if GRIMB_KW == 1
-  if (warp_kernels && tv.L <= 5 && tv.P == 1) {
-    // warp-per-subject kernels first; what they cannot finish goes through the general kernel
-    CK(e->worklist.reserve((size_t)batch->n_subjects * 4 + 16));
-    const uint64_t groups = ((uint64_t)batch->n_subjects + FAST_WARPS * 2 - 1) / (FAST_WARPS * 2);
+  if (tv.L <= 5 && tv.P == 1) {
+    const uint64_t groups = ((uint64_t)n + FAST_WARPS * 2 - 1) / (FAST_WARPS * 2);
     if (e->fast_split) {
       CK(e->mid.reserve((size_t)batch->n_subjects * sizeof(FastMid) + 16));
       double eps = cfg->epsilon;
@@ -2414,58 +2456,71 @@ static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBat
       unsigned int* ovf_n = (unsigned int*)(e->d_counters + CNT_OVERFLOW);
       if (tm) CK(cudaEventRecord(e->ev[0], st));
       if (batch->packed_keys)
-        k_fast_probe<true><<<(unsigned)fgp, FAST_WARPS * 32, 0, st>>>(tv, *batch, O, (FastMid*)e->mid.p, (uint32_t*)e->worklist.p,
-                                                                    cnt, (uint32_t*)e->overflow.p, ovf_n, eps > 0 ? 0 : 1);
+        k_fast_probe<true><<<(unsigned)fgp, FAST_WARPS * 32, 0, st>>>(tv, rb, O, (FastMid*)e->mid.p, (uint32_t*)e->worklist.p, cnt,
+                                                                    (uint32_t*)e->overflow.p, ovf_n, eps > 0 ? 0 : 1, (uint32_t)s_begin);
       else
-        k_fast_probe<false><<<(unsigned)fgp, FAST_WARPS * 32, 0, st>>>(tv, *batch, O, (FastMid*)e->mid.p, (uint32_t*)e->worklist.p,
-                                                                     cnt, (uint32_t*)e->overflow.p, ovf_n, eps > 0 ? 0 : 1);
+        k_fast_probe<false><<<(unsigned)fgp, FAST_WARPS * 32, 0, st>>>(tv, rb, O, (FastMid*)e->mid.p, (uint32_t*)e->worklist.p, cnt,
+                                                                     (uint32_t*)e->overflow.p, ovf_n, eps > 0 ? 0 : 1, (uint32_t)s_begin);
       CK(cudaGetLastError());
       if (tm) CK(cudaEventRecord(e->ev[1], st));
-      uint64_t sg = ((uint64_t)batch->n_subjects + 127) / 128;
+      uint64_t sg = ((uint64_t)n + 127) / 128;
       if (sg > (uint64_t)e->sm_count * 16) sg = (uint64_t)e->sm_count * 16;
       if (tm) CK(cudaEventRecord(e->ev_score[0], st));
-      k_fast_score<<<(unsigned)sg, 128, 0, st>>>(tv, e->d_cfg, *batch, O, (const FastMid*)e->mid.p,
-                                                (uint32_t*)e->worklist.p, cnt);
+      k_fast_score<<<(unsigned)sg, 128, 0, st>>>(tv, e->d_cfg, rb, O, (const FastMid*)e->mid.p, (uint32_t*)e->worklist.p, cnt,
+                                                (uint32_t)s_begin);
       CK(cudaGetLastError());
       if (tm) CK(cudaEventRecord(e->ev_score[1], st));
       e->ev_score_valid = tm;
       e->ev_valid[0] = tm;
       e->launches += 2;
-      // subjects with more than FAST_CMAX candidate phases: the fused kernel over the overflow list
-      k_impute_fast<true><<<32u, FAST_WARPS * 32, 0, st>>>(tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt,
-                                                                     (const uint32_t*)e->overflow.p, ovf_n);
-      CK(cudaGetLastError());
-      e->launches += 1;
     } else {
       uint64_t fg = (uint64_t)e->sm_count * FAST_MIN_BLOCKS;  // resident CTAs only: each warp strides over subjects
       if (fg > groups) fg = groups;
       if (tm) CK(cudaEventRecord(e->ev[0], st));
-      k_impute_fast<false><<<(unsigned)fg, FAST_WARPS * 32, 0, st>>>(tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt,
-                                                                    nullptr, nullptr);
+      k_impute_fast<false><<<(unsigned)fg, FAST_WARPS * 32, 0, st>>>(tv, e->d_cfg, rb, O, (uint32_t*)e->worklist.p, cnt, nullptr,
+                                                                    nullptr, (uint32_t)s_begin);
       CK(cudaGetLastError());
       if (tm) CK(cudaEventRecord(e->ev[1], st));
       e->ev_valid[0] = tm;
       e->launches += 1;
     }
-    wl = (const uint32_t*)e->worklist.p;
-    wl_n = cnt;
-  } else
-#endif
-  if (warp_kernels && e->typed_ctas > 0) {
-    // warp-per-subject kernel for fully typed unambiguous subjects, any P <= 32 / L / key width
-    CK(e->worklist.reserve((size_t)batch->n_subjects * 4 + 16));
-    uint64_t tg = ((uint64_t)batch->n_subjects + TY_WARPS - 1) / TY_WARPS;
-    if (tg > (uint64_t)e->typed_ctas) tg = (uint64_t)e->typed_ctas;
-    if (tm) CK(cudaEventRecord(e->ev[4], st));
-    k_impute_typed<<<(unsigned)tg, TY_WARPS * 32, (size_t)e->typed_per_warp * TY_WARPS, st>>>(
-        tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt, e->typed_per_warp);
-    CK(cudaGetLastError());
-    if (tm) CK(cudaEventRecord(e->ev[5], st));
-    e->ev_valid[2] = tm;
-    e->launches += 1;
-    wl = (const uint32_t*)e->worklist.p;
-    wl_n = cnt;
+    return GRIMB_OK;
   }
+#endif
+  // warp-per-subject kernel for fully typed unambiguous subjects, any P <= 32 / L / key width
+  uint64_t tg = ((uint64_t)n + TY_WARPS - 1) / TY_WARPS;
+  if (tg > (uint64_t)e->typed_ctas) tg = (uint64_t)e->typed_ctas;
+  if (tm) CK(cudaEventRecord(e->ev[4], st));
+  k_impute_typed<<<(unsigned)tg, TY_WARPS * 32, (size_t)e->typed_per_warp * TY_WARPS, st>>>(
+      tv, e->d_cfg, rb, O, (uint32_t*)e->worklist.p, cnt, e->typed_per_warp, (uint32_t)s_begin);
+  CK(cudaGetLastError());
+  if (tm) CK(cudaEventRecord(e->ev[5], st));
+  e->ev_valid[2] = tm;
+  e->launches += 1;
+  return GRIMB_OK;
+}
+
+static int launch_tail(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch, const OutArrays& O, cudaStream_t st,
+                       bool tm) {
+  if (batch->n_subjects <= 0) return GRIMB_OK;
+  const TablesView& tv = e->tables->view;
+  const bool warp = warp_kernels_apply(e, cfg, batch);
+  const uint32_t* wl = warp ? (const uint32_t*)e->worklist.p : nullptr;
+  unsigned int* cnt = (unsigned int*)(e->d_counters + CNT_WORKLIST);
+  const unsigned int* wl_n = warp ? cnt : nullptr;
+  const uint64_t stride = (uint64_t)batch->n_subjects;
+  CK(e->buckets.reserve((size_t)stride * 4 * GRIMB_BUCKETS + 16));
+  unsigned int* bucket_n = (unsigned int*)(e->d_counters + CNT_BUCKETS);
+#if GRIMB_KW == 1
+  if (warp && tv.L <= 5 && tv.P == 1 && e->fast_split) {
+    // subjects with more than FAST_CMAX candidate phases: the fused kernel over the overflow list
+    unsigned int* ovf_n = (unsigned int*)(e->d_counters + CNT_OVERFLOW);
+    k_impute_fast<true><<<32u, FAST_WARPS * 32, 0, st>>>(tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt,
+                                                        (const uint32_t*)e->overflow.p, ovf_n, 0u);
+    CK(cudaGetLastError());
+    e->launches += 1;
+  }
+#endif
   {
     uint64_t cg = (stride + 255) / 256;
     if (cg > (uint64_t)e->sm_count * 4) cg = (uint64_t)e->sm_count * 4;
@@ -2506,7 +2561,6 @@ static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBat
       e->launches += 1;
     }
   }
-  if (getenv("GRIMB_GROUP_LOAD") && getenv("GRIMB_GROUP_LOAD")[0] == '0') pv.top = nullptr;   // debugging: lists computed, not used
   if (tm) CK(cudaEventRecord(e->ev[2], st));
   k_impute<<<grid, e->threads, 0, st>>>(tv, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones, e->d_counters + CNT_WORK,
                                        (const uint32_t*)e->buckets.p, bucket_n, stride, pv, 0);
@@ -2515,6 +2569,12 @@ static int launch_kernels(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBat
   e->ev_valid[1] = tm;
   e->launches += 1;
   return GRIMB_OK;
+}
+
+static void reset_event_flags(GrimbEngine* e) {
+  e->ev_valid[0] = e->ev_valid[1] = e->ev_valid[2] = 0;
+  e->ev_score_valid = 0;
+  e->ev_slots_valid = 0;
 }
 
 static int check_batch(const GrimbBatch* b, const GrimbTables* t) {
@@ -2552,9 +2612,17 @@ static int totals_from(const unsigned long long* c, double handed, const GrimbRe
   return GRIMB_OK;
 }
 
+// Asynchronous device-pointer form.  The call enqueues the warp-per-subject kernels (and a copy of the
+// counters into pinned memory) and returns; grimb_impute_finish waits for THIS call (an event, not the
+// stream: other engines' calls queued behind it on the same stream keep running), and only if something was
+// handed on -- or no warp-per-subject kernel serves the table / mode -- launches the tail (overflow list,
+// classification, cooperative slot pass, general kernel) and waits for it.  The usual batch of BASELINE
+// config 2 therefore costs two kernels.  One call may be in flight per engine; a caller that wants batch
+// k+1 queued while batch k runs alternates between two engines.
 extern "C" int grimb_impute_device_async(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch,
                                          const GrimbResults* res, void* cuda_stream) {
   if (!e || !cfg || !batch || !res) return fail(GRIMB_E_ARG, "null argument");
+  if (e->pending) return fail(GRIMB_E_ARG, "a call is in flight on this engine: grimb_impute_finish first");
   int rc = check_cfg(cfg, e->tables);
   if (rc) return rc;
   rc = check_results(res);
@@ -2566,10 +2634,22 @@ extern "C" int grimb_impute_device_async(GrimbEngine* e, const GrimbConfig* cfg,
   rc = upload_cfg(e, cfg, st);
   if (rc) return rc;
   CK(cudaMemsetAsync(e->d_counters, 0, CNT_N * sizeof(unsigned long long), st));
-  rc = launch_kernels(e, cfg, batch, out_arrays(e, *res), st, e->timing != 0);
+  reset_event_flags(e);
+  const OutArrays O = out_arrays(e, *res);
+  rc = launch_warp(e, cfg, batch, O, st, e->timing != 0, 0, batch->n_subjects);
   if (rc) return rc;
+  // the tail is queued right away when the previous call of this engine needed one (a steady stream of
+  // batches with a few handed-on subjects each then never waits twice); otherwise it is left to finish
+  e->tail_queued = e->tail_expected || !warp_kernels_apply(e, cfg, batch);
+  if (e->tail_queued) {
+    rc = launch_tail(e, cfg, batch, O, st, e->timing != 0);
+    if (rc) return rc;
+  }
   CK(cudaMemcpyAsync(e->h_tail, e->d_counters, CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(e->ev_done, st));
   e->pending_stream = st;
+  e->pend_batch = *batch;
+  e->pend_res = *res;
   e->pending = 1;
   return GRIMB_OK;
 }
@@ -2578,8 +2658,19 @@ extern "C" int grimb_impute_finish(GrimbEngine* e, const GrimbResults* res) {
   if (!e || !res || !res->totals) return fail(GRIMB_E_ARG, "null argument");
   if (!e->pending) return fail(GRIMB_E_ARG, "no call in flight");
   CK(cudaSetDevice(e->device));
-  CK(cudaStreamSynchronize(e->pending_stream));
   e->pending = 0;
+  CK(cudaEventSynchronize(e->ev_done));
+  const bool warp = warp_kernels_apply(e, &e->cfg_host, &e->pend_batch);
+  const unsigned long long handed = (e->h_tail[CNT_WORKLIST] & 0xFFFFFFFFull) + (e->h_tail[CNT_OVERFLOW] & 0xFFFFFFFFull);
+  e->tail_expected = handed > 0;
+  if (!e->tail_queued && (!warp || handed > 0)) {
+    cudaStream_t st = e->pending_stream;
+    int rc = launch_tail(e, &e->cfg_host, &e->pend_batch, out_arrays(e, e->pend_res), st, e->timing != 0);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(e->h_tail, e->d_counters, CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(e->ev_done, st));
+    CK(cudaEventSynchronize(e->ev_done));
+  }
   e->last_worklist = (double)(unsigned int)(e->h_tail[CNT_WORKLIST] & 0xFFFFFFFFull);
   return totals_from(e->h_tail, e->last_worklist, res);
 }
@@ -2604,6 +2695,10 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
   if (rc) return rc;
   rc = check_batch(b, e->tables);
   if (rc) return rc;
+  using hclk = std::chrono::steady_clock;
+  const auto h0 = hclk::now();
+  double hmark[6] = {0, 0, 0, 0, 0, 0};
+  auto mark = [&](int k) { hmark[k] = std::chrono::duration<double, std::milli>(hclk::now() - h0).count(); };
   CK(cudaSetDevice(e->device));
   const int L = e->tables->h.L, P = e->tables->h.P;
   const int64_t S = b->n_subjects;
@@ -2628,6 +2723,7 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
   // fill / drain (first copy-in, last copy-out not overlapped) when they are large
   int64_t chunk = e->host_chunk;
   if (S > chunk * GRIMB_MAX_CHUNKS) chunk = (S + GRIMB_MAX_CHUNKS - 1) / GRIMB_MAX_CHUNKS;
+  chunk = (chunk + 31) & ~(int64_t)31;   // the warp-per-lane kernel starts its ranges on warp boundaries
   int64_t bound[GRIMB_MAX_CHUNKS + 1];
   int nch = 0;
   bound[0] = 0;
@@ -2637,33 +2733,37 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
   }
   rc = upload_cfg(e, cfg, st);
   if (rc) return rc;
+  // GRIMB_HOST_TRACE=1: timeline of the pipeline (CUDA events per chunk; diagnostic only)
+  static const bool trace = getenv("GRIMB_HOST_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tev;
+  if (trace) {
+    tev.resize(1 + 3 * (size_t)nch);
+    for (auto& x : tev) CK(cudaEventCreate(&x));
+    CK(cudaEventRecord(tev[0], st));
+    if (nch > 1) {
+      CK(cudaStreamWaitEvent(e->s_in, tev[0], 0));
+    }
+  }
   CK(cudaMemsetAsync(e->d_counters, 0, CNT_N * sizeof(unsigned long long), st));
   if (in_bytes[5]) CK(cudaMemcpyAsync(e->in[5].p, b->priors, in_bytes[5], cudaMemcpyHostToDevice, st));
-  // what has been copied out so far / the counters after the chunk being copied out
-  unsigned long long prev[4] = {0, 0, 0, 0}, end[CNT_N];
+  // Per chunk: the 16-byte records of its subjects and the words its warp kernels appended (one contiguous
+  // range: the counters keep running).  After the last chunk the tail runs once (launch_tail); what it wrote
+  // -- general records, their rows, and the records of the subjects it served -- is copied out at the end.
+  unsigned long long words_prev = 0, end[CNT_N];
   memset(end, 0, sizeof(end));
-  const unsigned long long cap[4] = {(unsigned long long)r->word_capacity, (unsigned long long)r->general_capacity,
-                                     (unsigned long long)r->hap_capacity, (unsigned long long)r->pop_capacity};
-  static const int which[4] = {CNT_WORDS, CNT_GENERAL, CNT_HAP, CNT_POP};
-  const size_t esz[4] = {8, sizeof(GrimbSubjectResult), sizeof(GrimbHapRow), sizeof(GrimbPopRow)};
-  char* const hdst[4] = {(char*)r->words, (char*)r->general, (char*)r->hap_rows, (char*)r->pop_rows};
-  const char* const dsrc[4] = {(const char*)dr.words, (const char*)dr.general, (const char*)dr.hap_rows, (const char*)dr.pop_rows};
-  double wl = 0;
+  const unsigned long long wcap = (unsigned long long)r->word_capacity;
   auto copy_out = [&](int c) -> int {
     const int64_t s0 = bound[c], n = bound[c + 1] - s0;
     CK(cudaEventSynchronize(e->ev_k[c]));
-    memcpy(end, e->h_cnt + (size_t)CNT_N * c, sizeof(end));
-    wl += (double)(unsigned int)(end[CNT_WORKLIST] & 0xFFFFFFFFull);
+    const unsigned long long* hc = e->h_cnt + (size_t)CNT_N * c;
     cudaStream_t so = nch > 1 ? e->s_out : st;
     CK(cudaMemcpyAsync(r->compact + s0, dr.compact + s0, (size_t)n * sizeof(GrimbCompact), cudaMemcpyDeviceToHost, so));
-    for (int k = 0; k < 4; ++k) {
-      const unsigned long long hi = end[which[k]] < cap[k] ? end[which[k]] : cap[k];
-      if (hi > prev[k]) {
-        CK(cudaMemcpyAsync(hdst[k] + prev[k] * esz[k], dsrc[k] + prev[k] * esz[k], (size_t)(hi - prev[k]) * esz[k],
-                           cudaMemcpyDeviceToHost, so));
-        prev[k] = hi;
-      }
+    const unsigned long long hi = hc[CNT_WORDS] < wcap ? hc[CNT_WORDS] : wcap;
+    if (hi > words_prev) {
+      CK(cudaMemcpyAsync(r->words + words_prev, dr.words + words_prev, (size_t)(hi - words_prev) * 8, cudaMemcpyDeviceToHost, so));
+      words_prev = hi;
     }
+    if (trace) CK(cudaEventRecord(tev[3 + 3 * c], so));
     return GRIMB_OK;
   };
   // copy-in of every chunk is queued first (nothing on the device holds it back), so the in-stream streams
@@ -2677,6 +2777,7 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
       if (b->prior_index)
         CK(cudaMemcpyAsync((uint32_t*)e->in[4].p + s0, b->prior_index + s0, (size_t)n * 4, cudaMemcpyHostToDevice, si));
       if (nch > 1) CK(cudaEventRecord(e->ev_in[c], si));
+      if (trace) CK(cudaEventRecord(tev[1 + 3 * c], si));
       continue;
     }
     const uint32_t a0 = b->allele_off[s0], a1 = b->allele_off[s1];
@@ -2692,44 +2793,113 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
       CK(cudaMemcpyAsync((uint16_t*)e->in_mask.p + s0, b->phase_mask + s0, (size_t)n * 2, cudaMemcpyHostToDevice, si));
     if (nch > 1) CK(cudaEventRecord(e->ev_in[c], si));
   }
+  mark(0);   // copy-in of every chunk queued
+  // the batch as the kernels see it: device arrays of the whole call, subjects addressed by their index in it
+  GrimbBatch db = *b;
+  db.typed_mask = (const uint16_t*)e->in[0].p;
+  db.counts = (b->counts && !packed) ? (const uint16_t*)e->in[1].p : nullptr;
+  db.allele_off = (const uint32_t*)e->in[2].p;
+  db.alleles = (const uint16_t*)e->in[3].p;
+  if (packed) {
+    db.packed_keys = (const uint64_t*)e->in[3].p;
+    db.packed_flags = (const uint16_t*)e->in[0].p;
+    db.typed_mask = nullptr;
+    db.allele_off = nullptr;
+    db.alleles = nullptr;
+  }
+  db.prior_index = b->prior_index ? (const uint32_t*)e->in[4].p : nullptr;
+  db.priors = (const double*)e->in[5].p;
+  db.phase_mask = (b->phase_mask && !packed) ? (const uint16_t*)e->in_mask.p : nullptr;
+  const OutArrays O = out_arrays(e, dr);
+  const bool tm = e->timing_host != 0;
+  reset_event_flags(e);
+  const bool warp = warp_kernels_apply(e, cfg, &db);
   for (int c = 0; c < nch; ++c) {
-    const int64_t s0 = bound[c], s1 = bound[c + 1], n = s1 - s0;
     if (nch > 1) CK(cudaStreamWaitEvent(st, e->ev_in[c], 0));
-    GrimbBatch db = *b;
-    db.n_subjects = n;
-    db.typed_mask = (const uint16_t*)e->in[0].p + s0;
-    db.counts = (b->counts && !packed) ? (const uint16_t*)e->in[1].p + s0 * L * 2 : nullptr;
-    db.allele_off = (const uint32_t*)e->in[2].p + s0;   // offsets stay absolute into `alleles`
-    db.alleles = (const uint16_t*)e->in[3].p;
-    if (packed) {
-      db.packed_keys = (const uint64_t*)e->in[3].p + 2 * s0;
-      db.packed_flags = (const uint16_t*)e->in[0].p + s0;
-      db.typed_mask = nullptr;
-      db.allele_off = nullptr;
-      db.alleles = nullptr;
-    }
-    db.prior_index = b->prior_index ? (const uint32_t*)e->in[4].p + s0 : nullptr;
-    db.priors = (const double*)e->in[5].p;
-    db.phase_mask = (b->phase_mask && !packed) ? (const uint16_t*)e->in_mask.p + s0 : nullptr;
-    GrimbResults cr = dr;
-    cr.compact = dr.compact + s0;
-    if (c > 0) CK(cudaMemsetAsync(e->d_counters, 0, CNT_CHUNK_END * sizeof(unsigned long long), st));   // per-chunk counters
-    rc = launch_kernels(e, cfg, &db, out_arrays(e, cr), st, e->timing_host != 0);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(e->h_cnt + (size_t)CNT_N * c, e->d_counters, CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(e->ev_k[c], st));
-    // with chunk c in the queue, hand chunk c-1 to the copy-out stream
-    if (c > 0) {
-      rc = copy_out(c - 1);
+    if (warp) {
+      rc = launch_warp(e, cfg, &db, O, st, tm, bound[c], bound[c + 1]);
       if (rc) return rc;
+      k_snapshot<<<1, 32, 0, st>>>(e->d_counters, e->h_cnt_dev + (size_t)CNT_N * c, CNT_N);
+      CK(cudaEventRecord(e->ev_k[c], st));
+      if (trace) CK(cudaEventRecord(tev[2 + 3 * c], st));
+      // with chunk c in the queue, hand chunk c-1 to the copy-out stream
+      if (c > 0) {
+        rc = copy_out(c - 1);
+        if (rc) return rc;
+      }
     }
   }
-  if (nch > 0) {
+  mark(1);   // warp kernels of every chunk queued, copy-out of all but the last chunk handed over
+  // the tail, once: everything the warp kernels handed on (or the whole batch when none serves it)
+  rc = launch_tail(e, cfg, &db, O, st, tm);
+  if (rc) return rc;
+  k_snapshot<<<1, 32, 0, st>>>(e->d_counters, e->h_cnt_dev + (size_t)CNT_N * GRIMB_MAX_CHUNKS, CNT_N);
+  CK(cudaGetLastError());
+  if (warp && nch > 0) {
     rc = copy_out(nch - 1);
     if (rc) return rc;
   }
+  mark(2);   // tail queued, last chunk handed to the copy-out stream
+  CK(cudaStreamSynchronize(st));
+  mark(3);   // compute stream idle
+  memcpy(end, e->h_cnt + (size_t)CNT_N * GRIMB_MAX_CHUNKS, sizeof(end));
+  const double wl = (double)(unsigned int)(end[CNT_WORKLIST] & 0xFFFFFFFFull);
+  {
+    const unsigned long long tail_subjects = (end[CNT_WORKLIST] & 0xFFFFFFFFull) + (end[CNT_OVERFLOW] & 0xFFFFFFFFull);
+    // records written by the tail: every subject's when no warp kernel ran, else those of the handed-on ones
+    // (scattered: the array is copied again as a whole, 16 bytes per subject)
+    if (!warp || tail_subjects > (unsigned long long)S / 8) {
+      CK(cudaMemcpyAsync(r->compact, dr.compact, (size_t)S * sizeof(GrimbCompact), cudaMemcpyDeviceToHost, st));
+    } else if (tail_subjects > 0) {
+      // few subjects: their records are gathered on the device and scattered into place here
+      const uint32_t nw = (uint32_t)(end[CNT_WORKLIST] & 0xFFFFFFFFull), no = (uint32_t)(end[CNT_OVERFLOW] & 0xFFFFFFFFull);
+      const size_t nt = (size_t)nw + no, bytes = nt * (sizeof(GrimbCompact) + 4);
+      CK(e->gather.reserve(bytes + 64));
+      if (e->h_gather_cap < bytes) {
+        if (e->h_gather) cudaFreeHost(e->h_gather);
+        e->h_gather = nullptr;
+        e->h_gather_cap = 0;
+        CK(cudaMallocHost(&e->h_gather, bytes * 2 + 4096));
+        e->h_gather_cap = bytes * 2 + 4096;
+      }
+      GrimbCompact* gc = (GrimbCompact*)e->gather.p;
+      uint32_t* gi = (uint32_t*)(gc + nt);
+      if (nw) k_gather_compact<<<nblk(nw), 256, 0, st>>>((const uint32_t*)e->worklist.p, nw, dr.compact, gc, gi);
+      if (no) k_gather_compact<<<nblk(no), 256, 0, st>>>((const uint32_t*)e->overflow.p, no, dr.compact, gc + nw, gi + nw);
+      CK(cudaMemcpyAsync(e->h_gather, e->gather.p, bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      const GrimbCompact* hc = (const GrimbCompact*)e->h_gather;
+      const uint32_t* hi = (const uint32_t*)(hc + nt);
+      if (nch > 1) CK(cudaStreamSynchronize(e->s_out));   // the per-chunk copies of the same records come first
+      for (size_t k = 0; k < nt; ++k) r->compact[hi[k]] = hc[k];
+    }
+    const unsigned long long whi = end[CNT_WORDS] < wcap ? end[CNT_WORDS] : wcap;
+    if (whi > words_prev)
+      CK(cudaMemcpyAsync(r->words + words_prev, dr.words + words_prev, (size_t)(whi - words_prev) * 8, cudaMemcpyDeviceToHost, st));
+    const unsigned long long ng = std::min<unsigned long long>(end[CNT_GENERAL], (unsigned long long)r->general_capacity);
+    const unsigned long long nh = std::min<unsigned long long>(end[CNT_HAP], (unsigned long long)r->hap_capacity);
+    const unsigned long long np = std::min<unsigned long long>(end[CNT_POP], (unsigned long long)r->pop_capacity);
+    if (ng) CK(cudaMemcpyAsync(r->general, dr.general, (size_t)ng * sizeof(GrimbSubjectResult), cudaMemcpyDeviceToHost, st));
+    if (nh) CK(cudaMemcpyAsync(r->hap_rows, dr.hap_rows, (size_t)nh * sizeof(GrimbHapRow), cudaMemcpyDeviceToHost, st));
+    if (np) CK(cudaMemcpyAsync(r->pop_rows, dr.pop_rows, (size_t)np * sizeof(GrimbPopRow), cudaMemcpyDeviceToHost, st));
+  }
   if (nch > 1) CK(cudaStreamSynchronize(e->s_out));
   CK(cudaStreamSynchronize(st));
+  mark(4);
+  if (trace) {
+    fprintf(stderr, "impute_host host clock (ms since entry): copy-in queued %.3f, chunks queued %.3f, tail queued %.3f, compute idle %.3f, all done %.3f\n",
+            hmark[0], hmark[1], hmark[2], hmark[3], hmark[4]);
+    fprintf(stderr, "impute_host trace (ms after the call's first event): chunk: copy-in done / kernels done / copy-out done\n");
+    for (int c = 0; c < nch; ++c) {
+      float a = -1, k = -1, o = -1;
+      if (packed) cudaEventElapsedTime(&a, tev[0], tev[1 + 3 * c]);
+      if (warp) cudaEventElapsedTime(&k, tev[0], tev[2 + 3 * c]);
+      if (warp) cudaEventElapsedTime(&o, tev[0], tev[3 + 3 * c]);
+      fprintf(stderr, "  %d: %.3f / %.3f / %.3f\n", c, a, k, o);
+    }
+    cudaGetLastError();
+    for (auto& x : tev) cudaEventDestroy(x);
+  }
   e->last_worklist = wl;
   return totals_from(end, wl, r);
 }
