@@ -175,7 +175,7 @@ def table_record(g, n_full, P, L, build_s, peak):
     labels = (1 << L) - 2
     algo = labels * n_full * (24 + 8 * P) + info["device_bytes"]
     return {"n_full": n_full, "n_nodes": info["n_nodes"], "populations": P, "loci": L, "device_bytes": info["device_bytes"],
-            "build_s": build_s, "algorithmic_bytes": algo,
+            "build_s": build_s, "kernel_launches": int(g.lib.grimb_tables_build_launches(g.handle)), "algorithmic_bytes": algo,
             "roofline": {"bound": "hbm", "achieved": algo / build_s / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": algo / build_s / 1e9 / peak}}
 

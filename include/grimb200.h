@@ -84,6 +84,9 @@ typedef struct {
   int64_t n_nodes, n_full, n_toplinks, n_conn_edges, n_slots, device_bytes;
 } GrimbTableInfo;
 int grimb_tables_info(const GrimbTables* t, GrimbTableInfo* info);
+/* Kernel launches grimb_tables_build issued for this table (0 for a table made from an image): the build is
+ * batched over labels, about 60 launches for a 5-locus table whatever its size. */
+int64_t grimb_tables_build_launches(const GrimbTables* t);
 
 /* Copies table arrays to host buffers (any pointer may be NULL).  node_key: packed alleles of
  * node id i; node_freq [n_nodes][P]; tl_start/tl_cnt [n_nodes] and tl_adj [n_toplinks] = top
@@ -212,7 +215,9 @@ typedef struct {
  *   SIMPLE : one population.  total = probability of the UMUG genotype = the population row's value;
  *            phases = phase ids of the PMUG rows in rank order, 4 bits each; with GRIMB_KIND_WORDS
  *            words[off + k] = probability of PMUG row k, without it (a single accepted phase) the one
- *            PMUG row's probability is `total`
+ *            PMUG row's probability is `total`.  n_pmug == 15 marks the long form (more than four PMUG
+ *            rows): words[off] = number of rows, words[off + 1] = their phase ids (4 bits each, rank order),
+ *            words[off + 2 + k] = probability of row k
  *   TYPED  : P <= 32 populations.  words[off] = header: n_pops (bits 0-15), then the PMUG rows' phase ids,
  *            12 bits each from bit 16; words[off + 1 + k] = probability of PMUG row k; then n_pops
  *            probabilities of the population-pair rows in rank order (the same rows serve .umug.pops and

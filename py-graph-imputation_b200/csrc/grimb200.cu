@@ -1371,16 +1371,21 @@ k_impute_fast(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, O
 // what is typically one or two candidate phases -- shrinks to a few instructions per subject.
 // Hand-over record: 96 bytes per subject in a device buffer owned by the engine.
 // ------------------------------------------------------------------------------------------
-constexpr int FAST_CMAX = 4;   // candidate phases carried per subject; more -> k_impute_fast over an overflow list
+constexpr int FAST_CMAX = 4;    // candidate phases k_fast_score keeps in registers (the usual subject has one or two)
+constexpr int FAST_CALL = 16;   // candidate phases a hand-over record holds (= every phase of a 5-locus subject)
 
 // Header and first candidate share one 32-byte sector: the usual subject (one candidate phase) costs one
-// sector written by the probe kernel and one read by the score kernel.
-struct __align__(16) FastMid {
-  uint32_t flags;        // bits 0-1 state (0 not for k_fast_score, 1 ready), 2-4 ncand, 5 both haplotypes equal,
-                         // 16-31 four phase ids (ascending)
-  uint32_t pad[3];
-  double f[FAST_CMAX][2];  // (f1, f2) of the candidate phases, ascending phase
+// sector written by the probe kernel and one read by the score kernel.  96 bytes = 3 sectors.  A subject with
+// more than FAST_CMAX candidate phases (rare) keeps them in a side record claimed from `extra`.
+struct __align__(32) FastMid {
+  uint32_t flags;        // bits 0-1 state (0 not for k_fast_score, 1 ready), 2-6 ncand, 7 both haplotypes equal
+  uint32_t extra;        // ncand > FAST_CMAX: index of the subject's FastExtra
+  uint64_t phases;       // phase ids of the candidates, ascending, 4 bits each
+  double f[FAST_CMAX][2];  // (f1, f2) of the candidate phases, ascending phase (ncand <= FAST_CMAX)
   double tail[2];
+};
+struct __align__(32) FastExtra {
+  double f[FAST_CALL][2];
 };
 
 #ifndef FASTPROBE_MIN_BLOCKS
@@ -1421,7 +1426,8 @@ __device__ __forceinline__ void probe_load(ProbeIn& in, const GrimbBatch& B, uin
 template <bool PACKED>
 __global__ void __launch_bounds__(FAST_WARPS * 32, FASTPROBE_MIN_BLOCKS)
 k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid, uint32_t* worklist,
-             unsigned int* worklist_n, uint32_t* overflow, unsigned int* overflow_n, int nchain_ok, uint32_t s_begin) {
+             unsigned int* worklist_n, FastExtra* __restrict__ extra, unsigned int* extra_n, uint32_t extra_cap, int nchain_ok,
+             uint32_t s_begin) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int half = lane >> 4, i = lane & 15, hbase = half << 4;
   const uint32_t hmask = 0xFFFFu << hbase;
@@ -1446,7 +1452,8 @@ k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid,
     // packed form: in.typed is the flag word (bit 15 = skip); every subject that is not skipped has the shape
     const uint32_t typed = PACKED ? ((in.typed & 0x8000u) ? 0u : full) : in.typed;
     const bool shape = typed == full && nchain_ok && (PACKED || in.nall == 2u * (uint32_t)L);   // uniform in the half-warp
-    uint32_t state = 0, ncand = 0, same = 0, phases = 0;
+    uint32_t state = 0, ncand = 0, same = 0, xslot = 0;
+    uint64_t phases = 0;
     if (shape) {
       uint64_t k0, k1;
       uint32_t unk0, unk1, het;
@@ -1484,24 +1491,31 @@ k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid,
       const bool cand = kept && f1 > 0 && f2 > 0;
       const uint32_t cmask = (__ballot_sync(hmask, cand) >> hbase) & 0xFFFFu;
       ncand = __popc(cmask);
-      if (ncand > FAST_CMAX) {
-        // more candidate phases than a hand-over record holds: the fused kernel serves this subject
-        if (i == 0) overflow[atomicAdd(overflow_n, 1u)] = s;
-      } else {
-        state = 1;
-        // phase ids of the candidates, ascending, 4 bits each
-        uint32_t mm = cmask;
-        for (uint32_t q = 0; q < ncand; ++q) {
-          phases |= (uint32_t)(__ffs(mm) - 1) << (4 * q);
-          mm &= mm - 1;
+      state = 1;
+      // phase ids of the candidates, ascending, 4 bits each
+      uint32_t mm = cmask;
+      for (uint32_t q = 0; q < ncand; ++q) {
+        phases |= (uint64_t)(__ffs(mm) - 1) << (4 * q);
+        mm &= mm - 1;
+      }
+      double2* dst = &reinterpret_cast<double2*>(&mid[s].f[0][0])[0];
+      if (ncand > FAST_CMAX) {   // rare: a side record (uniform in the half-warp)
+        unsigned int x = 0;
+        if (i == 0) x = atomicAdd(extra_n, 1u);
+        x = __shfl_sync(hmask, x, hbase);
+        xslot = x;
+        if (x >= extra_cap) {    // no side record left: the general kernel serves the subject
+          state = 0;
+          if (i == 0) worklist[atomicAdd(worklist_n, 1u)] = s;
         }
-        if (cand) {
-          const uint32_t slot = __popc(cmask & ((1u << i) - 1u));
-          double2 v;
-          v.x = f1;
-          v.y = f2;
-          *reinterpret_cast<double2*>(&mid[s].f[slot][0]) = v;
-        }
+        dst = reinterpret_cast<double2*>(&extra[x < extra_cap ? x : 0].f[0][0]);
+      }
+      if (cand && state) {
+        const uint32_t slot = __popc(cmask & ((1u << i) - 1u));
+        double2 v;
+        v.x = f1;
+        v.y = f2;
+        dst[slot] = v;
       }
     }
     if (!shape && typed != 0) {
@@ -1511,11 +1525,107 @@ k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid,
       if (typed == 0)   // GRIMB_ST_SKIPPED: finished here
         O.r.compact[s] = make_compact(GRIMB_ST_SKIPPED, GRIMB_KIND_GENERAL, 0, 0xFFFFFFFFu, 0.0);
       uint4 h1;   // header: state and candidate bookkeeping
-      h1.x = state | (ncand << 2) | (same << 5) | (phases << 16);
-      h1.y = h1.z = h1.w = 0;
+      h1.x = state | (ncand << 2) | (same << 7);
+      h1.y = xslot;
+      h1.z = (uint32_t)phases;
+      h1.w = (uint32_t)(phases >> 32);
       reinterpret_cast<uint4*>(mid + s)[0] = h1;
     }
   }
+}
+
+// ---- more than FAST_CMAX candidate phases (rare): the same schedule as below with the candidates re-read from
+// the subject's side record instead of kept in registers; out of line so that the common path keeps its registers
+__device__ __forceinline__ void score_cand(const FastExtra* ex, uint32_t q, double m, bool same, FastPair& pr, double& p) {
+  const double2 v = *reinterpret_cast<const double2*>(&ex->f[q][0]);
+  pr.f = v.x;
+  pr.f2 = v.y;
+  pr.same = same;
+  pr.mpos = m > 0;
+  pr.y = m * pr.f2;
+  const double t = fmin(pr.f2, same ? pr.y * 0.5 : pr.y);
+  const double b = pr.f * t;
+  const bool tiny = !(b > 1.0e-280);
+  pr.lo = tiny ? -1.0 : b * (1.0 - 0x1p-50);
+  pr.hi = tiny ? __longlong_as_double(0x7ff0000000000000LL) : b * (1.0 + 0x1p-50);
+  p = v.x * v.y * m;
+  if (!same) p = p * 2;
+}
+
+struct ScoreLong {
+  double total, e_fin;
+  uint32_t n_acc, evals;
+};
+
+__device__ __noinline__ void score_long_eval(const FastExtra* ex, uint32_t ncand, double m, bool same, const double* chain, int nchain,
+                                             ScoreLong& o) {
+  o.total = 0.0;
+  o.e_fin = 0.0;
+  o.n_acc = 0;
+  uint32_t rs = 99;
+  for (uint32_t q = 0; q < ncand; ++q) {
+    FastPair pr;
+    double p;
+    score_cand(ex, q, m, same, pr, p);
+    if (pr.mpos) {
+      int r = 0;
+      while (r < nchain && chain[r] >= pr.hi) ++r;
+      while (r < nchain && !pr.accept(chain[r])) ++r;
+      if (r < nchain && (uint32_t)r < rs) rs = (uint32_t)r;
+    }
+  }
+  if (rs == 99) {
+    o.evals = ncand * (uint32_t)nchain;
+    return;
+  }
+  o.evals = ncand * (rs + 1);
+  if (chain[rs] > 0) {   // MaxProb of that round -> epsilon = MaxProb / 100000, one more evaluation
+    double mx = 0.0;
+    for (uint32_t q = 0; q < ncand; ++q) {
+      FastPair pr;
+      double p;
+      score_cand(ex, q, m, same, pr, p);
+      if (pr.accept(chain[rs]) && p > mx) mx = p;
+    }
+    o.e_fin = mx / 100000;
+    o.evals += ncand;
+  }
+  bool first = true;
+  for (uint32_t q = 0; q < ncand; ++q) {   // += in phase order
+    FastPair pr;
+    double p;
+    score_cand(ex, q, m, same, pr, p);
+    if (pr.accept(o.e_fin)) {
+      o.total = first ? p : o.total + p;
+      first = false;
+      ++o.n_acc;
+    }
+  }
+}
+
+// rows of the long form: words[0] = number of rows, words[1] = their phase ids (rank order), words[2 + k] = probability
+__device__ __noinline__ void score_long_rows(const FastExtra* ex, uint32_t ncand, double m, bool same, double e_fin, uint64_t ph64,
+                                             uint32_t np, uint64_t* words) {
+  uint64_t ph_out = 0;
+  for (uint32_t q = 0; q < ncand; ++q) {
+    FastPair pr;
+    double p;
+    score_cand(ex, q, m, same, pr, p);
+    if (!pr.accept(e_fin)) continue;
+    uint32_t rank = 0;   // by (probability desc, phase asc)
+    for (uint32_t j = 0; j < ncand; ++j) {
+      FastPair pj;
+      double pp;
+      score_cand(ex, j, m, same, pj, pp);
+      if (pj.accept(e_fin) && (pp > p || (pp == p && j < q))) ++rank;
+    }
+    if (rank < np) {
+      ph_out |= ((ph64 >> (4 * q)) & 15ull) << (4 * rank);
+      words[2 + rank] = (uint64_t)__double_as_longlong(p);
+    }
+  }
+  words[0] = (uint64_t)np;
+  words[1] = ph_out;
 }
 
 #ifndef FASTSCORE_MIN_BLOCKS
@@ -1523,7 +1633,8 @@ k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid,
 #endif
 __global__ void __launch_bounds__(128, FASTSCORE_MIN_BLOCKS)
 k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O,
-             const FastMid* __restrict__ mid, uint32_t* worklist, unsigned int* worklist_n, uint32_t s_begin) {
+             const FastMid* __restrict__ mid, const FastExtra* __restrict__ extra, uint32_t* worklist, unsigned int* worklist_n,
+             uint32_t s_begin) {
   __shared__ double s_chain[FAST_MAX_ROUNDS];
   __shared__ int s_nchain;
   const int lane = threadIdx.x & 31;
@@ -1551,7 +1662,8 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
     const uint64_t s = s0 + lane;
     bool ready = false;
     double m = 0.0;
-    uint32_t fl = 0;
+    uint32_t fl = 0, xslot = 0;
+    uint64_t ph64 = 0;
     double2 f0 = make_double2(0.0, 0.0);
     if (s < S) {
       // everything that does not depend on the header is requested with it: the prior (P == 1: one
@@ -1562,10 +1674,14 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
       f0 = *reinterpret_cast<const double2*>(&mid[s].f[0][0]);   // same sector as the header; garbage unless ncand >= 1
       m = __ldg(B.priors + pi);
       fl = h1.x;
+      xslot = h1.y;
+      ph64 = (uint64_t)h1.z | ((uint64_t)h1.w << 32);
       ready = (fl & 3u) == 1u;
     }
-    const uint32_t ncand = ready ? ((fl >> 2) & 7u) : 0u;
-    const bool same = (fl >> 5) & 1u;
+    const uint32_t ncand_all = ready ? ((fl >> 2) & 31u) : 0u;
+    const bool long_form = ncand_all > (uint32_t)FAST_CMAX;   // rare: more candidate phases than the register path keeps
+    const uint32_t ncand = long_form ? 0u : ncand_all;
+    const bool same = (fl >> 7) & 1u;
     const bool mpos = m > 0;
     double pf[FAST_CMAX], pf2[FAST_CMAX], prob[FAST_CMAX];
     uint32_t rq[FAST_CMAX];
@@ -1646,6 +1762,15 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
         first = false;
         ++n_acc;
       }
+    double e_fin = 0.0;
+    if (long_form) {
+      ScoreLong sl;
+      score_long_eval(extra + xslot, ncand_all, m, same, s_chain, nchain, sl);
+      total = sl.total;
+      n_acc = sl.n_acc;
+      evals = sl.evals;
+      e_fin = sl.e_fin;
+    }
     if (want_u && want_p) evals *= 2;
     bool done = ready;
     if (ready && n_acc == 0 && planb) {   // Plan B / C: general kernel (which counts its own evaluations)
@@ -1657,7 +1782,8 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
     // PMUG probabilities travel as 8-byte words only when several phases were accepted (with one accepted
     // phase the row's probability is `total`); one claim of word space per warp, and none at all for the
     // usual warp whose subjects all have a single accepted phase
-    const uint32_t nw = (np != 0u && n_acc >= 2u) ? np : 0u;
+    // (long form: a count word, a word of phase ids, then the probabilities)
+    const uint32_t nw = long_form ? (np ? np + 2u : 0u) : ((np != 0u && n_acc >= 2u) ? np : 0u);
     uint32_t sc = nw;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -1683,14 +1809,16 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
         for (int j = 0; j < FAST_CMAX; ++j)
           if (acc[j] && (prob[j] > prob[q] || (prob[j] == prob[q] && j < q))) ++rank;
         if (rank < np) {
-          phases |= ((fl >> (16 + 4 * q)) & 15u) << (4 * rank);
+          phases |= ((uint32_t)(ph64 >> (4 * q)) & 15u) << (4 * rank);
           if (nw && fits) R.words[my + rank] = (uint64_t)__double_as_longlong(prob[q]);
         }
       }
+    if (long_form && np && fits) score_long_rows(extra + xslot, ncand_all, m, same, e_fin, ph64, np, R.words + my);
     // the UMUG genotype and the two haplotypes of every PMUG row follow from the subject's own alleles and
     // the phase ids (include/grimb200.h, GRIMB_KIND_SIMPLE): one 16-byte store per subject
     const GrimbCompact c = make_compact(GRIMB_ST_OK, GRIMB_KIND_SIMPLE | (n_acc ? GRIMB_KIND_HAS_RESULTS : 0u) |
-                                        (nw ? GRIMB_KIND_WORDS : 0u) | (np << 4), phases, (uint32_t)my, total);
+                                        (nw ? GRIMB_KIND_WORDS : 0u) | ((long_form ? (np ? 15u : 0u) : np) << 4), phases,
+                                        (uint32_t)my, total);
     *reinterpret_cast<uint4*>(R.compact + s) = *reinterpret_cast<const uint4*>(&c);
   }
   // pair evaluations of the subjects finished here: one atomic per warp for the whole launch
@@ -2152,7 +2280,7 @@ enum {
   CNT_WORK = 0,       // tickets of the general kernel's persistent CTAs
   CNT_WORKLIST = 1,   // (u32) subjects handed from a warp-per-subject kernel to the general kernel
   CNT_BUCKETS = 2,    // (4 x u32) cost buckets of the general kernel's work
-  CNT_OVERFLOW = 4,   // (u32) subjects with more candidate phases than a hand-over record holds
+  CNT_OVERFLOW = 4,   // (u32) side records claimed by subjects with more candidate phases than a hand-over record holds
   CNT_SLOT_TICKET = 5,   // tickets of the cooperative slot kernel
   CNT_CHUNK_END = 8,
   CNT_HAP = 8,
@@ -2207,7 +2335,7 @@ struct GrimbEngine {
   int timing = 1;     // CUDA events around the kernels in the device-pointer form (GRIMB_KERNEL_EVENTS=0: none)
   int timing_host = 0;   // ... in the chunked host-pointer form (GRIMB_HOST_EVENTS=1)
   DevBuf mid;         // hand-over records of the split fast path
-  DevBuf overflow;    // subjects with more candidate phases than a hand-over record holds
+  DevBuf overflow;    // side records (FastExtra) of subjects with more candidate phases than a hand-over record holds
   cudaEvent_t ev_score[2] = {nullptr, nullptr};
   int ev_score_valid = 0;
   cudaEvent_t ev_slots[2] = {nullptr, nullptr};
@@ -2452,22 +2580,23 @@ static int launch_warp(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch*
       }
       uint64_t fgp = (uint64_t)e->sm_count * FASTPROBE_MIN_BLOCKS;
       if (fgp > groups) fgp = groups;
-      CK(e->overflow.reserve((size_t)batch->n_subjects * 4 + 16));
+      const uint32_t extra_cap = (uint32_t)(batch->n_subjects / 16 + 1024);   // side records for subjects with > 4 candidate phases
+      CK(e->overflow.reserve((size_t)extra_cap * sizeof(FastExtra) + 64));
       unsigned int* ovf_n = (unsigned int*)(e->d_counters + CNT_OVERFLOW);
       if (tm) CK(cudaEventRecord(e->ev[0], st));
       if (batch->packed_keys)
         k_fast_probe<true><<<(unsigned)fgp, FAST_WARPS * 32, 0, st>>>(tv, rb, O, (FastMid*)e->mid.p, (uint32_t*)e->worklist.p, cnt,
-                                                                    (uint32_t*)e->overflow.p, ovf_n, eps > 0 ? 0 : 1, (uint32_t)s_begin);
+                                                                    (FastExtra*)e->overflow.p, ovf_n, extra_cap, eps > 0 ? 0 : 1, (uint32_t)s_begin);
       else
         k_fast_probe<false><<<(unsigned)fgp, FAST_WARPS * 32, 0, st>>>(tv, rb, O, (FastMid*)e->mid.p, (uint32_t*)e->worklist.p, cnt,
-                                                                     (uint32_t*)e->overflow.p, ovf_n, eps > 0 ? 0 : 1, (uint32_t)s_begin);
+                                                                     (FastExtra*)e->overflow.p, ovf_n, extra_cap, eps > 0 ? 0 : 1, (uint32_t)s_begin);
       CK(cudaGetLastError());
       if (tm) CK(cudaEventRecord(e->ev[1], st));
       uint64_t sg = ((uint64_t)n + 127) / 128;
       if (sg > (uint64_t)e->sm_count * 16) sg = (uint64_t)e->sm_count * 16;
       if (tm) CK(cudaEventRecord(e->ev_score[0], st));
-      k_fast_score<<<(unsigned)sg, 128, 0, st>>>(tv, e->d_cfg, rb, O, (const FastMid*)e->mid.p, (uint32_t*)e->worklist.p, cnt,
-                                                (uint32_t)s_begin);
+      k_fast_score<<<(unsigned)sg, 128, 0, st>>>(tv, e->d_cfg, rb, O, (const FastMid*)e->mid.p, (const FastExtra*)e->overflow.p,
+                                                (uint32_t*)e->worklist.p, cnt, (uint32_t)s_begin);
       CK(cudaGetLastError());
       if (tm) CK(cudaEventRecord(e->ev_score[1], st));
       e->ev_score_valid = tm;
@@ -2511,16 +2640,6 @@ static int launch_tail(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch*
   const uint64_t stride = (uint64_t)batch->n_subjects;
   CK(e->buckets.reserve((size_t)stride * 4 * GRIMB_BUCKETS + 16));
   unsigned int* bucket_n = (unsigned int*)(e->d_counters + CNT_BUCKETS);
-#if GRIMB_KW == 1
-  if (warp && tv.L <= 5 && tv.P == 1 && e->fast_split) {
-    // subjects with more than FAST_CMAX candidate phases: the fused kernel over the overflow list
-    unsigned int* ovf_n = (unsigned int*)(e->d_counters + CNT_OVERFLOW);
-    k_impute_fast<true><<<32u, FAST_WARPS * 32, 0, st>>>(tv, e->d_cfg, *batch, O, (uint32_t*)e->worklist.p, cnt,
-                                                        (const uint32_t*)e->overflow.p, ovf_n, 0u);
-    CK(cudaGetLastError());
-    e->launches += 1;
-  }
-#endif
   {
     uint64_t cg = (stride + 255) / 256;
     if (cg > (uint64_t)e->sm_count * 4) cg = (uint64_t)e->sm_count * 4;
@@ -2661,7 +2780,7 @@ extern "C" int grimb_impute_finish(GrimbEngine* e, const GrimbResults* res) {
   e->pending = 0;
   CK(cudaEventSynchronize(e->ev_done));
   const bool warp = warp_kernels_apply(e, &e->cfg_host, &e->pend_batch);
-  const unsigned long long handed = (e->h_tail[CNT_WORKLIST] & 0xFFFFFFFFull) + (e->h_tail[CNT_OVERFLOW] & 0xFFFFFFFFull);
+  const unsigned long long handed = e->h_tail[CNT_WORKLIST] & 0xFFFFFFFFull;
   e->tail_expected = handed > 0;
   if (!e->tail_queued && (!warp || handed > 0)) {
     cudaStream_t st = e->pending_stream;
@@ -2845,14 +2964,14 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
   memcpy(end, e->h_cnt + (size_t)CNT_N * GRIMB_MAX_CHUNKS, sizeof(end));
   const double wl = (double)(unsigned int)(end[CNT_WORKLIST] & 0xFFFFFFFFull);
   {
-    const unsigned long long tail_subjects = (end[CNT_WORKLIST] & 0xFFFFFFFFull) + (end[CNT_OVERFLOW] & 0xFFFFFFFFull);
+    const unsigned long long tail_subjects = end[CNT_WORKLIST] & 0xFFFFFFFFull;
     // records written by the tail: every subject's when no warp kernel ran, else those of the handed-on ones
     // (scattered: the array is copied again as a whole, 16 bytes per subject)
     if (!warp || tail_subjects > (unsigned long long)S / 8) {
       CK(cudaMemcpyAsync(r->compact, dr.compact, (size_t)S * sizeof(GrimbCompact), cudaMemcpyDeviceToHost, st));
     } else if (tail_subjects > 0) {
       // few subjects: their records are gathered on the device and scattered into place here
-      const uint32_t nw = (uint32_t)(end[CNT_WORKLIST] & 0xFFFFFFFFull), no = (uint32_t)(end[CNT_OVERFLOW] & 0xFFFFFFFFull);
+      const uint32_t nw = (uint32_t)(end[CNT_WORKLIST] & 0xFFFFFFFFull), no = 0u;
       const size_t nt = (size_t)nw + no, bytes = nt * (sizeof(GrimbCompact) + 4);
       CK(e->gather.reserve(bytes + 64));
       if (e->h_gather_cap < bytes) {
@@ -2865,7 +2984,6 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
       GrimbCompact* gc = (GrimbCompact*)e->gather.p;
       uint32_t* gi = (uint32_t*)(gc + nt);
       if (nw) k_gather_compact<<<nblk(nw), 256, 0, st>>>((const uint32_t*)e->worklist.p, nw, dr.compact, gc, gi);
-      if (no) k_gather_compact<<<nblk(no), 256, 0, st>>>((const uint32_t*)e->overflow.p, no, dr.compact, gc + nw, gi + nw);
       CK(cudaMemcpyAsync(e->h_gather, e->gather.p, bytes, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       const GrimbCompact* hc = (const GrimbCompact*)e->h_gather;

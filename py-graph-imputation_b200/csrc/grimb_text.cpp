@@ -776,15 +776,22 @@ struct GrimbText {
   void format_compact(const Slot& S, const Line& ln, const GrimbCompact& c, const uint64_t* words, const GrimbConfig* cfg,
                       std::string* o) const {
     const uint16_t* ids = S.t_ids[ln.thread].data() + ln.ids_off;   // [L][2]
-    const uint32_t kind = c.kind_flags & 3u, n_pmug = c.kind_flags >> 4;
+    const uint32_t kind = c.kind_flags & 3u;
+    uint32_t n_pmug = c.kind_flags >> 4;
     const bool has = (c.kind_flags & GRIMB_KIND_HAS_RESULTS) != 0;
     const uint64_t* w = words + c.off;
     uint32_t n_pops = 0;
-    uint32_t phase[4] = {0, 0, 0, 0};
+    uint32_t phase[16];
     const uint64_t* pmug_prob = nullptr;   // nullptr: the single PMUG row carries `total`
     const uint64_t* pop_prob = nullptr;
     const uint64_t* pop_code = nullptr;
-    if (kind == GRIMB_KIND_SIMPLE) {
+    if (kind == GRIMB_KIND_SIMPLE && n_pmug == 15u) {
+      // long form (more than four PMUG rows): a count word, a word of phase ids, then the probabilities
+      n_pmug = (uint32_t)w[0] > 16u ? 16u : (uint32_t)w[0];
+      for (uint32_t k = 0; k < n_pmug; ++k) phase[k] = (uint32_t)(w[1] >> (4 * k)) & 15u;
+      pmug_prob = w + 2;
+      n_pops = (has && cfg->n_pop_results >= 1) ? 1u : 0u;
+    } else if (kind == GRIMB_KIND_SIMPLE) {
       for (uint32_t k = 0; k < n_pmug; ++k) phase[k] = (c.phases >> (4 * k)) & 15u;
       if (c.kind_flags & GRIMB_KIND_WORDS) pmug_prob = w;
       n_pops = (has && cfg->n_pop_results >= 1) ? 1u : 0u;

@@ -185,6 +185,8 @@ def load(kw=1):
     lib.grimb_tables_build.argtypes = [C.POINTER(TableDesc), C.POINTER(C.c_void_p)]
     lib.grimb_tables_free.argtypes = [C.c_void_p]
     lib.grimb_tables_info.argtypes = [C.c_void_p, C.POINTER(TableInfo)]
+    lib.grimb_tables_build_launches.argtypes = [C.c_void_p]
+    lib.grimb_tables_build_launches.restype = C.c_int64
     lib.grimb_tables_export.argtypes = [C.c_void_p] + [C.c_void_p] * 10
     lib.grimb_tables_image_size.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     lib.grimb_tables_image_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
@@ -226,7 +228,7 @@ def check(rc, what, lib=None):
 
 EXPORTED = [
     "grimb_abi_version", "grimb_last_error", "grimb_tables_build", "grimb_tables_free",
-    "grimb_tables_info", "grimb_tables_export", "grimb_tables_image_size", "grimb_tables_image_ptr",
+    "grimb_tables_info", "grimb_tables_build_launches", "grimb_tables_export", "grimb_tables_image_size", "grimb_tables_image_ptr",
     "grimb_tables_image_copy", "grimb_tables_from_image", "grimb_engine_create", "grimb_engine_free", "grimb_engine_launches", "grimb_engine_kernel_ms",
     "grimb_impute_device", "grimb_impute_device_async", "grimb_impute_finish", "grimb_impute_host",
     "grimb_text_create", "grimb_text_free", "grimb_text_tokenise", "grimb_text_format", "grimb_impute_text",

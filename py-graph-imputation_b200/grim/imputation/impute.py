@@ -360,7 +360,13 @@ class Imputation(object):
         total, off = float(c["total"]), int(c["off"])
         w = res.words
         cfg = self.cfg
-        if kind == _lib.KIND_SIMPLE:
+        if kind == _lib.KIND_SIMPLE and n_pmug == 15:
+            # long form (more than four PMUG rows): a count word, a word of phase ids, then the probabilities
+            n_pmug = min(16, int(w[off]))
+            phases = [(int(w[off + 1]) >> (4 * q)) & 15 for q in range(n_pmug)]
+            probs = [float(x) for x in w[off + 2:off + 2 + n_pmug].view(np.float64)]
+            pops = [(self.populations[0], self.populations[0], total)] if (has and cfg.n_pop_results >= 1) else []
+        elif kind == _lib.KIND_SIMPLE:
             phases = [(int(c["phases"]) >> (4 * q)) & 15 for q in range(n_pmug)]
             probs = [float(w[off + q:off + q + 1].view(np.float64)[0]) for q in range(n_pmug)] if kf & _lib.KIND_WORDS \
                 else [total] * n_pmug
