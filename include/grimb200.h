@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define GRIMB_ABI_VERSION 4
+#define GRIMB_ABI_VERSION 5
 #define GRIMB_MAX_LOCI 9
 #define GRIMB_MAX_ROWS 16
 #define GRIMB_MAX_BLOCKS 9
@@ -34,6 +34,7 @@ extern "C" {
 #define GRIMB_E_NOMEM (-3)
 #define GRIMB_E_LAYOUT (-4)   /* allele ids do not fit the packed key */
 #define GRIMB_E_CAPACITY (-5) /* caller-provided result buffers too small; see grimb_impute_* */
+#define GRIMB_E_UNDEFINED (-6) /* the reference has no defined behaviour for this input (Plan B under a Plan_A_Matrix) */
 
 /* per-subject status (GrimbResults.status) */
 #define GRIMB_ST_OK 0          /* rows written (possibly zero rows: reference writes .miss) */
@@ -70,6 +71,15 @@ typedef struct {
   int32_t key_bits[GRIMB_MAX_LOCI];       /* packed-key field width per locus (sum <= 63)     */
   int32_t last_parent_locus;              /* locus whose connector is created last (T1), or -1 to derive L-2 */
   int32_t device;                         /* CUDA device ordinal                              */
+  /* "Plan_A_Matrix" (generate_neo4j_multi_hpf.py:101-192, networkx_graph.py:32-66): NULL = every locus subset.
+   * Else the labels to build, as locus bit masks in node-id order, the full label first: the first
+   * n_plan_a_labels are the matrix rows (the vertices of the reference's Plan-A CSR, sentinel quirk included),
+   * the rest are labels kept for look-ups only (the single-locus labels the allele-existence checks read).  A
+   * restricted store has no connectors: it serves Plan A, which is all the reference computes reliably under
+   * a matrix. */
+  const uint32_t* label_masks;            /* [n_labels] or NULL                               */
+  int32_t n_labels;
+  int32_t n_plan_a_labels;
 } GrimbTableDesc;
 
 int grimb_abi_version(void);
@@ -137,6 +147,10 @@ typedef struct {
                                          GrimbPopRow with its two populations at
                                          pop_rows[pop_off + n_umug_pops + n_pmug_pops + k]; one PMUG pop row   */
   int32_t em;                         /* impute_file(em=True): no Plan C for the haplotype output (impute.py:1648) */
+  int32_t plan_a_only;                /* "Plan_A_Matrix" in force (tables built from a label list): the kernels run
+                                         Plan A only whatever `planb` says.  With planb set, the text pipeline
+                                         fails with GRIMB_E_UNDEFINED when a subject leaves Plan A without a result:
+                                         the reference's Plan B is not well defined under a matrix */
 } GrimbConfig;
 
 /* A batch of subjects, tokenised by the host (replaces the string handling of
@@ -303,6 +317,9 @@ typedef struct {
   int32_t unk_priors_mr;             /* "UNK_priors" == "MR" (ones) else identity                 */
   int32_t key_bits[GRIMB_MAX_LOCI];  /* the tables' packed-key layout                             */
   int32_t n_threads;                 /* 0 = hardware concurrency                                  */
+  const uint8_t* type_allowed;       /* "Plan_A_Matrix": [1 << L], non-zero where the typed-locus pattern (bit l =
+                                        locus l typed) is a matrix row -- other subjects go to .problem
+                                        (impute.py:1592-1596); NULL = no matrix                                  */
 } GrimbTextDesc;
 
 /* the six output texts of one call; pointers stay valid until the next call on the same GrimbText */

@@ -57,12 +57,43 @@ def _checked(adj):
     return adj
 
 
+class PlanBUnderMatrix(NotImplementedError):
+    """A subject leaves Plan A while a Plan_A_Matrix is in force.  The reference's Plan B then indexes its
+    second vertex list (nxg.py:32-66: nodes of the Plan-B labels only) with node ids of the CSV files
+    (nxg.py:91-130,285-306): it reads the adjacency of unrelated nodes, and the ids involved depend on
+    PYTHONHASHSEED (gen.py:181).  Nothing to be exact against: the oracle refuses instead of guessing."""
+
+
+def plan_a_labels(matrix, full_label):
+    """gen.py:101-164 (labels_for_grap), the Plan-A part: label strings of the matrix rows in matrix order, the
+    full label appended when absent.  Only what has a defined behaviour downstream is accepted: rows strictly
+    ascending (input_type, impute.py:1574-1579, yields ascending lists, and a permuted row would also permute the
+    alleles inside the node names, gen.py:367-368) and the full label FIRST (full haplotypes always get ids
+    0..N-1, gen.py:341-358, while nodes.csv lists labels in matrix order: with the full label anywhere else the
+    position of a vertex in nxg.py's filtered list no longer equals its id, nxg.py:49-57 vs :262-270)."""
+    labels = []
+    for row in matrix:
+        row = [int(x) for x in row]
+        if row != sorted(set(row)) or not row or any(str(x) not in full_label for x in row):
+            raise NotImplementedError("Plan_A_Matrix rows must be strictly ascending lists of loci_map indices")
+        lab = "".join(str(x) for x in row)
+        if lab in labels:
+            raise NotImplementedError("Plan_A_Matrix lists a label twice")
+        labels.append(lab)
+    if labels[0] != full_label:
+        raise NotImplementedError("Plan_A_Matrix must list the full label first (see plan_a_labels)")
+    if len(labels) < 2:
+        # nxg.py:134: np.vstack of an empty edge list
+        raise ValueError("need at least one array to concatenate")
+    return labels
+
+
 class OracleGraph:
     """Restates gen.py:209-486 (trim, node ids, sequential marginal sums, top links, parent
     edges) fused with nxg.py:42-213 (dict + CSR load, including the sentinel quirk at
     :195-196), without going through the CSV files."""
 
-    def __init__(self, hpf_lines, pops, loci_map, freq_trim, pop_count_lines=None, marginals=True):
+    def __init__(self, hpf_lines, pops, loci_map, freq_trim, pop_count_lines=None, marginals=True, plan_a_matrix=None):
         # marginals=False (checker speed only, not a reference feature): keep just the full
         # haplotype label.  Exact for subjects typed at every locus whose Plan A succeeds -- the
         # only queries are full-label lookups (nxg.py:262-266) -- which is how the big 9-locus
@@ -79,6 +110,14 @@ class OracleGraph:
             self.labels.extend("".join(c) for c in itertools.combinations(full, r))
         if not marginals:
             self.labels = [full]
+        # Plan_A_Matrix (gen.py:101-192, nxg.py:32-66): Plan A sees the labels of the matrix only, ids in matrix
+        # order.  The single-locus labels always exist in the reference's second vertex list (gen.py:166-170), which
+        # is where allele-existence checks look (nxg.py:309-316); they follow the Plan-A labels here and take no part
+        # in the CSR.  No connectors: Plan B is refused under a matrix (PlanBUnderMatrix).
+        self.plan_a = None
+        if plan_a_matrix:
+            self.plan_a = plan_a_labels(plan_a_matrix, full)
+            self.labels = self.plan_a + [ch for ch in full if ch not in self.plan_a]
 
         # gen.py:259-266 trim threshold per population
         trim = {}
@@ -142,8 +181,17 @@ class OracleGraph:
         self.n_nodes = len(self.names)
 
         # nxg.py:71-88,149-201 CSR of top links (partial -> full, ascending id)
-        n_edges = sum(len(v) for v in tl.values())
         self.toplinks = tl
+        if self.plan_a is not None:
+            # the CSR holds the Plan-A vertices only (nxg.py:49-57,71-88)
+            n_vertices = sum(len(self.by_label[lab]) for lab in self.plan_a)
+            n_edges = sum(len(tl[n]) for lab in self.plan_a[1:] for n in self.by_label[lab])
+            last = self.names[n_vertices - 1]
+            self.toplinks[last] = _sentinel_slice(tl[last], n_edges, n_vertices)
+            self.n_plan_a_nodes = n_vertices
+            self.conn = {}
+            return
+        n_edges = sum(len(v) for v in tl.values())
         if tl:
             last = self.names[-1]
             self.toplinks[last] = _sentinel_slice(tl[last], n_edges, self.n_nodes)
@@ -261,6 +309,7 @@ def load_config(json_conf):
         "UNK_priors": c.get("UNK_priors", "MR"),
         # run_impute_def.py:124-125: optional JSON {subject id: [0/1 per typed position]} phase masks
         "bin_imputation_input_file": c.get("bin_imputation_in_file", "None"),
+        "nodes_for_plan_A": c.get("Plan_A_Matrix", []),      # run_impute_def.py:126
     }
 
 
@@ -280,6 +329,7 @@ def graph_from_config(json_conf, base_dir="", marginals=True):
         json_conf["freq_trim_threshold"],
         pc,
         marginals,
+        json_conf.get("Plan_A_Matrix") or None,
     )
 
 
@@ -790,6 +840,8 @@ class OracleImputation:
             if level == 1:
                 self.M = np.ones((npop, npop))
             if planb and len(res["Haps"]) == 0:
+                if self.cfg.get("nodes_for_plan_A"):
+                    raise PlanBUnderMatrix("a subject leaves Plan A under a Plan_A_Matrix")
                 self.plan = "b"
                 eps = 1e-14
                 n_res = 0
@@ -806,6 +858,11 @@ class OracleImputation:
         chrom = self.gl2haps(gl)
         if chrom == []:
             return None, None
+        if self.cfg.get("nodes_for_plan_A"):
+            # impute.py:1592-1596 with input_type (:1574-1579): the typed loci, in the order of the sorted side
+            geno_type = [self.index[x.split("*")[0]] for x in chrom["Genotype"][0]]
+            if geno_type not in self.cfg["nodes_for_plan_A"]:
+                return None, None
         n_loci = chrom["N_Loc"]
         pmags = self.gen_phases(chrom["Genotype"], n_loci, self.binary)
         if pmags == []:
@@ -948,6 +1005,8 @@ class OracleImputation:
                 if self.cfg["output_MUUG"]:
                     _write_dict(sid, res_muugs["Haps"], n_res, out["umug"])
                     _write_dict(sid, res_muugs["Pops"], n_pop, out["umug_pops"])
+            except PlanBUnderMatrix:
+                raise
             except Exception:
                 out["problem"].append(str(raw) + "\n")
                 continue

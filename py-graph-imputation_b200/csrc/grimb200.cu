@@ -411,8 +411,22 @@ extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
   CK(cudaSetDevice(d->device));
   const uint64_t N = (uint64_t)d->n_full;
   const uint32_t NL = 1u << L;
-  const std::vector<uint32_t> order = label_order(L);
+  // labels of the store: every locus subset in the reference's order, or (Plan_A_Matrix) the caller's list
+  std::vector<uint32_t> order = label_order(L);
+  const bool restricted = d->label_masks != nullptr;
+  if (restricted) {
+    if (d->n_labels < 2 || d->n_labels > (int32_t)(NL - 1) || d->n_plan_a_labels < 2 || d->n_plan_a_labels > d->n_labels)
+      return fail(GRIMB_E_ARG, "bad label list");
+    order.assign(d->label_masks, d->label_masks + d->n_labels);
+    std::vector<uint8_t> seen(NL, 0);
+    for (uint32_t m : order) {
+      if (m == 0 || m >= NL || seen[m]) return fail(GRIMB_E_ARG, "label list: masks must be distinct locus subsets");
+      seen[m] = 1;
+    }
+    if (order[0] != NL - 1) return fail(GRIMB_E_ARG, "label list: the full label comes first");
+  }
   const uint32_t n_labels = (uint32_t)order.size();   // full label + marginals
+  const uint32_t n_csr_labels = restricted ? (uint32_t)d->n_plan_a_labels : n_labels;   // labels whose nodes are CSR vertices
   // 32-bit offsets everywhere (tl_start, cn_start, row indices): reject what would not fit
   if (N * (uint64_t)(n_labels - 1) > 0xFFFFFFF0ull) return fail(GRIMB_E_ARG, "too many top links (n_full x marginal labels >= 2^32)");
 
@@ -600,7 +614,7 @@ extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
   std::vector<uint32_t> pair_child, pair_first;
   std::vector<uint8_t> pair_locus;
   uint64_t n_cn = 0;
-  for (uint32_t li = 0; li < n_labels; ++li) {
+  for (uint32_t li = 0; li < n_labels && !restricted; ++li) {   // a restricted store serves Plan A only: no connectors
     const uint32_t B = order[li];
     if (__builtin_popcount(B) < 2 || lcount[B] == 0) continue;
     for (int l = 0; l < L; ++l) {
@@ -760,12 +774,15 @@ extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
 
   // ---- reference CSR sentinel quirk (networkx_graph.py:195-196; SURVEY trap T1)
   if (n_nodes > N && N > 0) {
-    const uint32_t last = (uint32_t)n_nodes - 1;
+    // vertices of the reference's CSR: every node, or (restricted) the nodes of the Plan-A labels, which come first
+    uint64_t n_vertices = n_nodes;
+    if (restricted) n_vertices = (uint64_t)lfirst_i[n_csr_labels - 1] + lcount_i[n_csr_labels - 1];
+    const uint32_t last = (uint32_t)n_vertices - 1;
     uint32_t deg = 0;
     CKT(cudaMemcpy(&deg, v.tl_cnt + last, 4, cudaMemcpyDeviceToHost));
-    uint32_t nc = sentinel_count(deg, h.n_toplinks, n_nodes);
+    uint32_t nc = sentinel_count(deg, N * (uint64_t)(n_csr_labels - 1), n_vertices);
     CKT(cudaMemcpy((uint32_t*)v.tl_cnt + last, &nc, 4, cudaMemcpyHostToDevice));
-    if (L >= 2) {
+    if (L >= 2 && !restricted) {
       int pl_locus = d->last_parent_locus >= 0 ? d->last_parent_locus : L - 2;
       uint64_t idx = (uint64_t)last * L + pl_locus;
       CKT(cudaMemcpy(&deg, v.cn_cnt + idx, 4, cudaMemcpyDeviceToHost));
@@ -1534,22 +1551,38 @@ k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid,
   }
 }
 
-// ---- more than FAST_CMAX candidate phases (rare): the same schedule as below with the candidates re-read from
-// the subject's side record instead of kept in registers; out of line so that the common path keeps its registers
-__device__ __forceinline__ void score_cand(const FastExtra* ex, uint32_t q, double m, bool same, FastPair& pr, double& p) {
-  const double2 v = *reinterpret_cast<const double2*>(&ex->f[q][0]);
-  pr.f = v.x;
-  pr.f2 = v.y;
-  pr.same = same;
-  pr.mpos = m > 0;
-  pr.y = m * pr.f2;
-  const double t = fmin(pr.f2, same ? pr.y * 0.5 : pr.y);
-  const double b = pr.f * t;
+// ---- more than FAST_CMAX candidate phases (rare): the WARP serves such a subject together, lane q = candidate q
+// (ascending phase), each lane reading its own (f1, f2) from the subject's side record once.  Same schedule as the
+// per-lane path below: first accepting round per candidate, minimum over the candidates, MaxProb / 100000, one more
+// evaluation, += in phase order, ranks by (probability desc, phase asc).
+struct LongCand {
+  FastPair pr;
+  double p;
+  bool valid;
+};
+
+__device__ __forceinline__ void long_cand(LongCand& c, const FastExtra* ex, uint32_t q, uint32_t ncand, double m, bool same) {
+  c.valid = q < ncand;
+  double2 v = make_double2(0.0, 0.0);
+  if (c.valid) v = *reinterpret_cast<const double2*>(&ex->f[q][0]);
+  c.pr.f = v.x;
+  c.pr.f2 = v.y;
+  c.pr.same = same;
+  c.pr.mpos = c.valid && m > 0;
+  c.pr.y = m * c.pr.f2;
+  const double t = fmin(c.pr.f2, same ? c.pr.y * 0.5 : c.pr.y);
+  const double b = c.pr.f * t;
   const bool tiny = !(b > 1.0e-280);
-  pr.lo = tiny ? -1.0 : b * (1.0 - 0x1p-50);
-  pr.hi = tiny ? __longlong_as_double(0x7ff0000000000000LL) : b * (1.0 + 0x1p-50);
-  p = v.x * v.y * m;
-  if (!same) p = p * 2;
+  c.pr.lo = tiny ? -1.0 : b * (1.0 - 0x1p-50);
+  c.pr.hi = tiny ? __longlong_as_double(0x7ff0000000000000LL) : b * (1.0 + 0x1p-50);
+  c.p = v.x * v.y * m;
+  if (!same) c.p = c.p * 2;
+}
+
+__device__ __forceinline__ double shfl_double(double v, int src) {
+  const long long b = __double_as_longlong(v);
+  const int lo = __shfl_sync(0xFFFFFFFFu, (int)(b & 0xFFFFFFFFll), src), hi = __shfl_sync(0xFFFFFFFFu, (int)(b >> 32), src);
+  return __longlong_as_double(((long long)hi << 32) | (unsigned int)lo);
 }
 
 struct ScoreLong {
@@ -1557,79 +1590,84 @@ struct ScoreLong {
   uint32_t n_acc, evals;
 };
 
+// called by all 32 lanes; every lane returns the same values
 __device__ __noinline__ void score_long_eval(const FastExtra* ex, uint32_t ncand, double m, bool same, const double* chain, int nchain,
                                              ScoreLong& o) {
+  const int lane = threadIdx.x & 31;
+  LongCand c;
+  long_cand(c, ex, (uint32_t)lane, ncand, m, same);
+  uint32_t rq = 99;
+  if (c.pr.mpos) {
+    int r = 0;
+    while (r < nchain && chain[r] >= c.pr.hi) ++r;
+    while (r < nchain && !c.pr.accept(chain[r])) ++r;
+    if (r < nchain) rq = (uint32_t)r;
+  }
+  const uint32_t rs = __reduce_min_sync(0xFFFFFFFFu, rq);
   o.total = 0.0;
   o.e_fin = 0.0;
   o.n_acc = 0;
-  uint32_t rs = 99;
-  for (uint32_t q = 0; q < ncand; ++q) {
-    FastPair pr;
-    double p;
-    score_cand(ex, q, m, same, pr, p);
-    if (pr.mpos) {
-      int r = 0;
-      while (r < nchain && chain[r] >= pr.hi) ++r;
-      while (r < nchain && !pr.accept(chain[r])) ++r;
-      if (r < nchain && (uint32_t)r < rs) rs = (uint32_t)r;
-    }
-  }
   if (rs == 99) {
     o.evals = ncand * (uint32_t)nchain;
     return;
   }
   o.evals = ncand * (rs + 1);
+  bool acc = rq <= rs;
   if (chain[rs] > 0) {   // MaxProb of that round -> epsilon = MaxProb / 100000, one more evaluation
-    double mx = 0.0;
-    for (uint32_t q = 0; q < ncand; ++q) {
-      FastPair pr;
-      double p;
-      score_cand(ex, q, m, same, pr, p);
-      if (pr.accept(chain[rs]) && p > mx) mx = p;
+    double mx = acc ? c.p : 0.0;   // probabilities are >= 0: the larger value has the larger bit pattern
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const double y = shfl_double(mx, lane ^ d);
+      mx = y > mx ? y : mx;
     }
     o.e_fin = mx / 100000;
+    acc = c.pr.accept(o.e_fin);
     o.evals += ncand;
   }
+  uint32_t am = __ballot_sync(0xFFFFFFFFu, acc);
+  o.n_acc = (uint32_t)__popc(am);
   bool first = true;
-  for (uint32_t q = 0; q < ncand; ++q) {   // += in phase order
-    FastPair pr;
-    double p;
-    score_cand(ex, q, m, same, pr, p);
-    if (pr.accept(o.e_fin)) {
-      o.total = first ? p : o.total + p;
-      first = false;
-      ++o.n_acc;
-    }
+  while (am) {   // += in phase order
+    const int j = __ffs(am) - 1;
+    am &= am - 1;
+    const double pj = shfl_double(c.p, j);
+    o.total = first ? pj : o.total + pj;
+    first = false;
   }
 }
 
 // rows of the long form: words[0] = number of rows, words[1] = their phase ids (rank order), words[2 + k] = probability
 __device__ __noinline__ void score_long_rows(const FastExtra* ex, uint32_t ncand, double m, bool same, double e_fin, uint64_t ph64,
                                              uint32_t np, uint64_t* words) {
-  uint64_t ph_out = 0;
-  for (uint32_t q = 0; q < ncand; ++q) {
-    FastPair pr;
-    double p;
-    score_cand(ex, q, m, same, pr, p);
-    if (!pr.accept(e_fin)) continue;
-    uint32_t rank = 0;   // by (probability desc, phase asc)
-    for (uint32_t j = 0; j < ncand; ++j) {
-      FastPair pj;
-      double pp;
-      score_cand(ex, j, m, same, pj, pp);
-      if (pj.accept(e_fin) && (pp > p || (pp == p && j < q))) ++rank;
-    }
-    if (rank < np) {
-      ph_out |= ((ph64 >> (4 * q)) & 15ull) << (4 * rank);
-      words[2 + rank] = (uint64_t)__double_as_longlong(p);
-    }
+  const int lane = threadIdx.x & 31;
+  LongCand c;
+  long_cand(c, ex, (uint32_t)lane, ncand, m, same);
+  const bool acc = c.pr.accept(e_fin);
+  uint32_t am = __ballot_sync(0xFFFFFFFFu, acc);
+  uint32_t rank = 0;   // by (probability desc, phase asc)
+  while (am) {
+    const int j = __ffs(am) - 1;
+    am &= am - 1;
+    const double pj = shfl_double(c.p, j);
+    if (pj > c.p || (pj == c.p && j < lane)) ++rank;
   }
-  words[0] = (uint64_t)np;
-  words[1] = ph_out;
+  uint32_t lo = 0, hi = 0;
+  if (acc && rank < np) {
+    const uint32_t id = (uint32_t)(ph64 >> (4 * lane)) & 15u;
+    if (rank < 8) lo = id << (4 * rank);
+    else hi = id << (4 * (rank - 8));
+    words[2 + rank] = (uint64_t)__double_as_longlong(c.p);
+  }
+  lo = __reduce_or_sync(0xFFFFFFFFu, lo);
+  hi = __reduce_or_sync(0xFFFFFFFFu, hi);
+  if (lane == 0) {
+    words[0] = (uint64_t)np;
+    words[1] = (uint64_t)lo | ((uint64_t)hi << 32);
+  }
 }
 
 #ifndef FASTSCORE_MIN_BLOCKS
-#define FASTSCORE_MIN_BLOCKS 1
+#define FASTSCORE_MIN_BLOCKS 8   /* 64 registers (a few spilled words): 0.046 ms per 2^20 subjects vs 0.048 at 6 CTAs, 0.052 unbounded (96) */
 #endif
 __global__ void __launch_bounds__(128, FASTSCORE_MIN_BLOCKS)
 k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O,
@@ -1683,6 +1721,16 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
     const uint32_t ncand = long_form ? 0u : ncand_all;
     const bool same = (fl >> 7) & 1u;
     const bool mpos = m > 0;
+    ScoreLong sl;   // long form: the warp serves its long-form subjects one after the other
+    sl.total = sl.e_fin = 0.0;
+    sl.n_acc = sl.evals = 0;
+    for (uint32_t lm = __ballot_sync(0xFFFFFFFFu, long_form); lm; lm &= lm - 1) {
+      const int o = __ffs(lm) - 1;
+      ScoreLong r;
+      score_long_eval(extra + __shfl_sync(0xFFFFFFFFu, xslot, o), __shfl_sync(0xFFFFFFFFu, ncand_all, o), shfl_double(m, o),
+                      __shfl_sync(0xFFFFFFFFu, (int)same, o) != 0, s_chain, nchain, r);
+      if (lane == o) sl = r;
+    }
     double pf[FAST_CMAX], pf2[FAST_CMAX], prob[FAST_CMAX];
     uint32_t rq[FAST_CMAX];
     bool acc[FAST_CMAX];
@@ -1762,14 +1810,10 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
         first = false;
         ++n_acc;
       }
-    double e_fin = 0.0;
     if (long_form) {
-      ScoreLong sl;
-      score_long_eval(extra + xslot, ncand_all, m, same, s_chain, nchain, sl);
       total = sl.total;
       n_acc = sl.n_acc;
       evals = sl.evals;
-      e_fin = sl.e_fin;
     }
     if (want_u && want_p) evals *= 2;
     bool done = ready;
@@ -1796,9 +1840,19 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
       if (lane == 31) wb = atomicAdd(O.word_counter, (unsigned long long)wtot);
       wb = __shfl_sync(0xFFFFFFFFu, wb, 31);
     }
-    if (!done) continue;
     const uint64_t my = wb + (sc - nw);
     const bool fits = (int64_t)(wb + wtot) <= R.word_capacity;
+    for (uint32_t lm = __ballot_sync(0xFFFFFFFFu, long_form && done && np && fits); lm; lm &= lm - 1) {
+      const int o = __ffs(lm) - 1;
+      const uint64_t ph = (uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)ph64, o) |
+                          ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(ph64 >> 32), o) << 32);
+      const uint64_t at = (uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)my, o) |
+                          ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(my >> 32), o) << 32);
+      score_long_rows(extra + __shfl_sync(0xFFFFFFFFu, xslot, o), __shfl_sync(0xFFFFFFFFu, ncand_all, o), shfl_double(m, o),
+                      __shfl_sync(0xFFFFFFFFu, (int)same, o) != 0, shfl_double(sl.e_fin, o), ph, __shfl_sync(0xFFFFFFFFu, np, o),
+                      R.words + at);
+    }
+    if (!done) continue;
     uint32_t phases = 0;
 #pragma unroll
     for (int q = 0; q < FAST_CMAX; ++q)
@@ -1813,7 +1867,6 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
           if (nw && fits) R.words[my + rank] = (uint64_t)__double_as_longlong(prob[q]);
         }
       }
-    if (long_form && np && fits) score_long_rows(extra + xslot, ncand_all, m, same, e_fin, ph64, np, R.words + my);
     // the UMUG genotype and the two haplotypes of every PMUG row follow from the subject's own alleles and
     // the phase ids (include/grimb200.h, GRIMB_KIND_SIMPLE): one 16-byte store per subject
     const GrimbCompact c = make_compact(GRIMB_ST_OK, GRIMB_KIND_SIMPLE | (n_acc ? GRIMB_KIND_HAS_RESULTS : 0u) |
@@ -2309,6 +2362,7 @@ struct GrimbEngine {
   unsigned long long* h_cnt_dev = nullptr;        // its device address
   int64_t host_chunk = 262144;                    // subjects per pipeline chunk (GRIMB_HOST_CHUNK)
   GrimbConfig cfg_host;                           // the configuration d_cfg holds (valid when cfg_sent)
+  GrimbConfig cfg_dev;                            // ... as the kernels see it
   int cfg_sent = 0;
   unsigned long long* h_tail = nullptr;           // pinned: the counters as read by the device-pointer call
   cudaStream_t pending_stream = nullptr;          // grimb_impute_device_async: stream of the call in flight
@@ -2523,7 +2577,9 @@ static int upload_cfg(GrimbEngine* e, const GrimbConfig* cfg, cudaStream_t st) {
   e->cfg_sent = 0;
   CK(cudaStreamSynchronize(e->stream));   // an earlier call on the engine stream may still read d_cfg
   e->cfg_host = *cfg;
-  CK(cudaMemcpyAsync(e->d_cfg, &e->cfg_host, sizeof(GrimbConfig), cudaMemcpyHostToDevice, st));
+  e->cfg_dev = *cfg;
+  if (cfg->plan_a_only) e->cfg_dev.planb = 0;   // a restricted store serves Plan A only (include/grimb200.h)
+  CK(cudaMemcpyAsync(e->d_cfg, &e->cfg_dev, sizeof(GrimbConfig), cudaMemcpyHostToDevice, st));
   CK(cudaStreamSynchronize(st));
   e->cfg_sent = 1;
   return GRIMB_OK;

@@ -201,6 +201,7 @@ struct GrimbText {
   uint32_t name_mask = 0;
   bool fast_path = true;             // GRIMB_TEXT_FAST=0: every line through the general parser (A/B, tests)
   bool packed_ok = true;             // GRIMB_TEXT_PACKED=0: never the packed batch form (A/B, tests)
+  std::vector<uint8_t> type_allowed; // Plan_A_Matrix: [1 << L] typed-locus patterns that are matrix rows (empty: no matrix)
   // pinned staging (grow-only)
   struct HostBuf {
     void* p = nullptr;
@@ -234,8 +235,13 @@ struct GrimbText {
     std::string own;              // private copy when the caller's buffer may go away
     int64_t first_index = 0;
     std::vector<Line> lines;
-    std::vector<std::vector<uint16_t>> t_ids;
-    std::vector<std::vector<Unknown>> t_unk;
+    // one per tokeniser thread, each on its own cache line: push_back rewrites the vector's end pointer, and with
+    // the 24-byte headers packed side by side every thread invalidated its neighbours' lines on every allele id
+    // (the tokeniser ran SLOWER on 4 threads than on 1)
+    struct alignas(64) IdVec : std::vector<uint16_t> {};
+    struct alignas(64) UnkVec : std::vector<Unknown> {};
+    std::vector<IdVec> t_ids;
+    std::vector<UnkVec> t_unk;
     std::vector<uint16_t> b_typed, b_counts, b_alleles;
     std::vector<uint32_t> b_off, b_prior;
     std::vector<uint64_t> b_keys;    // packed form of the batch (include/grimb200.h): [S][2] keys ...
@@ -642,6 +648,26 @@ struct GrimbText {
       ln.hclass = planb ? H_FAULT : H_OK;  // mask stays 0: nothing is imputed
       ln.mask = 0;
     };
+    if (!type_allowed.empty()) {
+      // Plan_A_Matrix: input_type (impute.py:1574-1579) looks every typed locus up before anything else --
+      // an unknown locus raises (raw line in .problem); a repeated locus gives a pattern that is no matrix row
+      bool repeated = false;
+      bool seen_l[GRIMB_MAX_LOCI] = {false};
+      for (size_t k = 0; k < t1.size(); ++k) {
+        sv first = t1[k].substr(0, t1[k].find('/'));
+        auto li = locus_index.find(first.substr(0, first.find('*')));
+        if (li == locus_index.end()) {
+          ln.hclass = H_FAULT;
+          return;
+        }
+        repeated = repeated || seen_l[li->second];
+        seen_l[li->second] = true;
+      }
+      if (repeated) {
+        ln.hclass = H_PROBLEM;
+        return;
+      }
+    }
     for (size_t k = 0; k < t1.size(); ++k) {
       sv first = t1[k].substr(0, t1[k].find('/'));
       sv prefix = first.substr(0, first.find('*'));
@@ -958,6 +984,7 @@ extern "C" int grimb_text_create(const GrimbTextDesc* d, GrimbText** out) {
   t->gamma = d->gamma;
   t->delta = d->delta;
   t->mr = d->unk_priors_mr != 0;
+  if (d->type_allowed) t->type_allowed.assign(d->type_allowed, d->type_allowed + ((size_t)1 << t->L));
   if (const char* fp = getenv("GRIMB_TEXT_FAST"))
     if (fp[0] == '0') t->fast_path = false;
   if (const char* pk = getenv("GRIMB_TEXT_PACKED"))
@@ -1065,6 +1092,13 @@ int tokenise_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const char* tex
         Line& ln = S.lines[i];
         if (!(fast && t->parse_fast(S, line, ln, (int)k)))
           t->parse_line(S, line, ln, (int)k, planb, clean, f1, f2, t1, t2, names, scr);
+        if (!t->type_allowed.empty() && ln.hclass == H_OK && ln.mask && !t->type_allowed[ln.mask]) {
+          // Plan_A_Matrix: the typed-locus pattern is no matrix row (impute.py:1592-1596) -> .problem "i,id"
+          S.t_ids[k].resize(ln.ids_off);
+          S.t_unk[k].resize(ln.unk_off);
+          ln.hclass = H_PROBLEM;
+          ln.mask = 0;
+        }
         if (!ln.no_fields) {   // the reference computes the prior before looking at the GL
           if (!(lv && ln.has_race == l_has && ln.race1 == l_r1 && ln.race2 == l_r2)) {
             l_prior = t->prior_lookup_locked(ln);
@@ -1189,8 +1223,13 @@ int format_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const GrimbResult
   for (auto& ps : parts) ps.clear();
   std::vector<int64_t> plans((size_t)nt * 4, 0);
   static const GrimbSubjectResult kNoRecord = {};   // a skipped subject: nothing was computed
+  // Plan_A_Matrix with Plan B on: a subject that leaves Plan A empty-handed would enter the reference's Plan B,
+  // which is not well defined under a matrix -> the call fails
+  const bool guard_planb = cfg->plan_a_only && cfg->planb;
+  std::vector<int64_t> undefined_first((size_t)nt, -1), undefined_n((size_t)nt, 0);
   t->parallel(NS, [&](int th, size_t lo, size_t hi) {
     std::string* o = &parts[(size_t)th * 6];
+    int64_t my_plans[4] = {0, 0, 0, 0};   // (a shared array of counters, one slot per thread, is a false-sharing trap)
     for (size_t i = lo; i < hi; ++i) {
       const Line& ln = S.lines[i];
       const uint64_t idx = (uint64_t)S.first_index + i;
@@ -1222,7 +1261,10 @@ int format_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const GrimbResult
       }
       const uint32_t kind = c.kind_flags & 3u;
       if (kind != GRIMB_KIND_GENERAL) {
-        plans[(size_t)th * 4 + GRIMB_PLAN_A] += 1;
+        my_plans[GRIMB_PLAN_A] += 1;
+        if (guard_planb && !(c.kind_flags & GRIMB_KIND_HAS_RESULTS)) {
+          if (undefined_n[(size_t)th]++ == 0) undefined_first[(size_t)th] = (int64_t)i;
+        }
         if (cfg->output_pmug && !(c.kind_flags & GRIMB_KIND_HAS_RESULTS)) {
           put_uint(idx, o[GRIMB_OUT_MISS]);
           o[GRIMB_OUT_MISS] += ',';
@@ -1233,8 +1275,12 @@ int format_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const GrimbResult
         continue;
       }
       const GrimbSubjectResult& r = c.off == 0xFFFFFFFFu ? kNoRecord : res->general[c.off];
-      plans[(size_t)th * 4 + ((cfg->output_umug ? r.plan_umug : r.plan_pmug) & 3)] += 1;
+      my_plans[(cfg->output_umug ? r.plan_umug : r.plan_pmug) & 3] += 1;
       const bool pm_empty = cfg->output_pmug ? r.tot_pmug == 0 : false;
+      if (guard_planb && c.status == GRIMB_ST_OK && c.off != 0xFFFFFFFFu &&
+          ((cfg->output_umug && r.tot_umug == 0) || (cfg->output_pmug && r.tot_pmug == 0))) {
+        if (undefined_n[(size_t)th]++ == 0) undefined_first[(size_t)th] = (int64_t)i;
+      }
       if (pm_empty && r.tot_umug == 0) {
         put_uint(idx, o[GRIMB_OUT_MISS]);
         o[GRIMB_OUT_MISS] += ',';
@@ -1243,6 +1289,7 @@ int format_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const GrimbResult
       }
       t->format_subject(S, ln, r, res->hap_rows, res->pop_rows, cfg, o);
     }
+    for (int k = 0; k < 4; ++k) plans[(size_t)th * 4 + k] = my_plans[k];
   });
   // concatenate the pieces of every output in thread order, the copies themselves in parallel
   std::vector<size_t> offs((size_t)nt * 6, 0);
@@ -1266,6 +1313,19 @@ int format_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const GrimbResult
   for (int th = 0; th < nt; ++th)
     for (int k = 0; k < 4; ++k) S.plan_count[k] += plans[(size_t)th * 4 + k];
   S.sec_fmt = secs(t0, clk::now());
+  {
+    int64_t n_undef = 0, first = -1;
+    for (int th = 0; th < nt; ++th) {
+      n_undef += undefined_n[(size_t)th];
+      if (first < 0 && undefined_first[(size_t)th] >= 0) first = undefined_first[(size_t)th];
+    }
+    if (n_undef) {
+      const Line& ln = S.lines[(size_t)first];
+      return tfail(GRIMB_E_UNDEFINED, std::to_string(n_undef) + " subject(s) leave Plan A without a result under a Plan_A_Matrix (first: line " +
+                                          std::to_string((uint64_t)S.first_index + (uint64_t)first) + ", id " + std::string(ln.sid) +
+                                          "): the reference's Plan B is not well defined there; set \"planb\": false to write them to the .miss file");
+    }
+  }
   return GRIMB_OK;
 }
 

@@ -18,6 +18,7 @@ MAX_BLOCKS = 9
 ST_OK, ST_FAULT, ST_WORKSPACE, ST_SKIPPED, ST_NO_PHASES = 0, 2, 3, 4, 5
 PLAN_NONE, PLAN_A, PLAN_B, PLAN_C = 0, 1, 2, 3
 E_CAPACITY = -5
+E_UNDEFINED = -6
 ALL_POPS = 0xFFFF
 
 
@@ -27,6 +28,7 @@ class TableDesc(C.Structure):
         ("full_alleles", C.c_void_p), ("full_freqs", C.c_void_p),
         ("n_alleles", C.c_int32 * MAX_LOCI), ("key_bits", C.c_int32 * MAX_LOCI),
         ("last_parent_locus", C.c_int32), ("device", C.c_int32),
+        ("label_masks", C.c_void_p), ("n_labels", C.c_int32), ("n_plan_a_labels", C.c_int32),
     ]
 
 
@@ -47,7 +49,7 @@ class Config(C.Structure):
         ("n_rows", C.c_int32),
         ("row_blocks", C.c_int32 * MAX_ROWS), ("block_mask", (C.c_uint16 * MAX_BLOCKS) * MAX_ROWS),
         ("row_is_plan_a", C.c_uint8 * MAX_ROWS),
-        ("hap_pop_pair", C.c_int32), ("em", C.c_int32),
+        ("hap_pop_pair", C.c_int32), ("em", C.c_int32), ("plan_a_only", C.c_int32),
     ]
 
 
@@ -133,6 +135,7 @@ class TextDesc(C.Structure):
         ("count_by_prob", C.POINTER(C.c_double)),
         ("alpha", C.c_double), ("eta", C.c_double), ("beta", C.c_double), ("gamma", C.c_double), ("delta", C.c_double),
         ("unk_priors_mr", C.c_int32), ("key_bits", C.c_int32 * MAX_LOCI), ("n_threads", C.c_int32),
+        ("type_allowed", C.c_void_p),
     ]
 
 
@@ -214,7 +217,7 @@ def load(kw=1):
     lib.grimb_file_count_lines.argtypes = [C.c_char_p, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_int64),
                                            C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.grimb_file_write_at.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_int64]
-    if lib.grimb_abi_version() != 4:
+    if lib.grimb_abi_version() != 5:
         raise RuntimeError("libgrimb200.so ABI mismatch")
     _LIB[kw] = lib
     return lib
@@ -223,6 +226,8 @@ def load(kw=1):
 def check(rc, what, lib=None):
     if rc != 0:
         msg = (lib or load()).grimb_last_error().decode("utf8", "replace")
+        if rc == E_UNDEFINED:
+            raise NotImplementedError("%s: %s" % (what, msg))
         raise RuntimeError("%s failed (%d): %s" % (what, rc, msg))
 
 

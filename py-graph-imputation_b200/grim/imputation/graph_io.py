@@ -71,6 +71,10 @@ def node_names(graph, arrays):
 
 def write_csv(graph, out_dir, node_csv="nodes.csv", edges_csv="edges.csv", top_links_csv="top_links.csv",
               info_node_csv="info_node.csv"):
+    if graph.plan_a_masks:
+        # the reference's generator also writes Plan-B labels whose order (hence node ids) follows the hash seed of
+        # the Python process (generate_neo4j_multi_hpf.py:181): there is no file to be equal to
+        raise NotImplementedError("graph CSV export under a Plan_A_Matrix")
     os.makedirs(out_dir, exist_ok=True)
     a = graph.export()
     L, P = len(graph.loci), len(graph.pops)
@@ -166,7 +170,8 @@ def save_cache(graph, path):
     """Binary table cache: <path> = device image, <path>.json = dictionaries + layout."""
     img = graph.image_to_host()
     img.tofile(path)
-    meta = {"loci": graph.loci, "pops": graph.pops, "alleles": graph.alleles, "bytes": int(img.nbytes)}
+    meta = {"loci": graph.loci, "pops": graph.pops, "alleles": graph.alleles, "bytes": int(img.nbytes),
+            "plan_a_masks": graph.plan_a_masks}
     with open(path + ".json", "w") as f:
         json.dump(meta, f)
 
@@ -176,6 +181,8 @@ def load_cache(graph, path):
         meta = json.load(f)
     if meta["loci"] != graph.loci or meta["pops"] != graph.pops:
         raise ValueError("table cache was built for other loci / populations")
+    if meta.get("plan_a_masks") != graph.plan_a_masks:
+        raise ValueError("table cache was built for another Plan_A_Matrix")
     img = np.fromfile(path, dtype=np.uint8)
     if img.nbytes != meta["bytes"]:
         raise ValueError("table cache is truncated")

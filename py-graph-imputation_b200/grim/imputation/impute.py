@@ -65,6 +65,7 @@ def make_config(conf, loci, n_pops):
                 m |= 1 << (i - 1)
             c.block_mask[r][b] = m
         c.row_is_plan_a[r] = 1 if (len(row) > 0 and list(row[0]) == all_indices) else 0
+    c.plan_a_only = 1 if conf.get("plan_a_masks") else 0
     return c
 
 
@@ -88,6 +89,15 @@ class Imputation(object):
         else:
             self.count_by_prob = count_by_prob
         self.cfg = make_config(config, self.loci, self.P)
+        # Plan_A_Matrix: typed-locus patterns that are matrix rows (impute.py:1592-1596 of the reference)
+        self.type_allowed = None
+        if config.get("plan_a_masks"):
+            if getattr(net, "plan_a_masks", None) != config["plan_a_masks"]:
+                raise ValueError("the Graph was not built for this Plan_A_Matrix")
+            self.type_allowed = np.zeros(1 << self.L, dtype=np.uint8)
+            self.type_allowed[config["plan_a_masks"]] = 1
+        elif getattr(net, "plan_a_masks", None):
+            raise ValueError("the Graph was built for a Plan_A_Matrix the configuration does not name")
         self.locus_index = {n: i for i, n in enumerate(self.loci)}
         self.batch_size = int(os.environ.get("GRIMB_BATCH", "65536"))
         self.workspaces = [int(x) for x in os.environ.get(
@@ -207,6 +217,20 @@ class Imputation(object):
         ids_of = self.netGraph.allele_id
         n_tab = [len(a) for a in self.netGraph.alleles]
         cap = [(1 << b) - 1 for b in self.netGraph.key_bits]
+        if self.type_allowed is not None:
+            # input_type (impute.py:1574-1579): every typed locus is looked up first (KeyError -> raw line in
+            # .problem); a pattern that is no matrix row -> comp_cand returns None -> .problem "i,id"
+            pattern = []
+            for a in t1:
+                l = self.locus_index.get(a.split("/")[0].split("*")[0])
+                if l is None:
+                    return H_FAULT, None
+                pattern.append(l)
+            mask = 0
+            for l in pattern:
+                mask |= 1 << l
+            if len(set(pattern)) != len(pattern) or not self.type_allowed[mask]:
+                return H_PROBLEM, None
         for a, b in zip(t1, t2):
             la = a.split("/")
             lb = b.split("/")
@@ -517,6 +541,12 @@ class Imputation(object):
             tot_u, tot_p = rows["tot_umug"], rows["tot_pmug"]
             self.stats["plan"][rows["plan_umug"] if cfgd["output_MUUG"] else rows["plan_pmug"]] += 1
             pm_empty = (tot_p == 0) if cfgd["output_haplotypes"] else False
+            if self.cfg.plan_a_only and self.cfg.planb and (
+                    (cfgd["output_MUUG"] and tot_u == 0) or (cfgd["output_haplotypes"] and tot_p == 0)):
+                raise NotImplementedError(
+                    "subject %s (line %d) leaves Plan A without a result under a Plan_A_Matrix: the reference's "
+                    "Plan B is not well defined there; set \"planb\": false to write such subjects to the .miss file"
+                    % (sid, i))
             if pm_empty and tot_u == 0:
                 files["miss"].append(str(i) + "," + str(sid) + "\n")
             self._format_subject(sid, rows, files)
@@ -616,6 +646,9 @@ class Imputation(object):
         for l in range(self.L):
             d.key_bits[l] = g.key_bits[l]
         d.n_threads = int(os.environ.get("GRIMB_HOST_THREADS", "0"))
+        if self.type_allowed is not None:
+            keep.append(self.type_allowed)
+            d.type_allowed = self.type_allowed.ctypes.data
         h = C.c_void_p()
         _lib.check(lib.grimb_text_create(C.byref(d), C.byref(h)), "grimb_text_create", lib)
         self._text = h

@@ -125,6 +125,8 @@ class Graph(object):
         self.key_bits = None
         self.shift = None
         self.kw = 1           # key words: which of the two library builds serves this table
+        # Plan_A_Matrix rows as locus bit masks (None: every label); the tables are built for it
+        self.plan_a_masks = config.get("plan_a_masks") or None
         self.lib = None
         self._engines = {}
 
@@ -202,6 +204,12 @@ class Graph(object):
         others = list(set(range(L)).difference([L - 1]))
         d.last_parent_locus = others[-1] if others else -1
         d.device = self.device
+        # Plan_A_Matrix: the store holds the matrix labels (+ the single-locus labels), no connectors
+        if self.plan_a_masks:
+            store = np.asarray(self.config["store_label_masks"], dtype=np.uint32)
+            d.label_masks = store.ctypes.data
+            d.n_labels = len(store)
+            d.n_plan_a_labels = len(self.plan_a_masks)
         h = C.c_void_p()
         _lib.check(lib.grimb_tables_build(C.byref(d), C.byref(h)), "grimb_tables_build", lib)
         self.handle = h

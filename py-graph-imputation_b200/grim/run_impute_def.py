@@ -70,11 +70,47 @@ def load_config(json_conf, project_dir_graph="", project_dir_in_file=""):
         "freq_trim_threshold": g("freq_trim_threshold", 1e-5),
         "imputation_out_path": output_dir,
     }
-    if config["nodes_for_plan_A"]:
-        raise NotImplementedError("Plan_A_Matrix label restriction is outside the B200 hot path (SURVEY 8f-3)")
     all_loci = {str(v) for v in config["loci_map"].values()}
     config["full_loci"] = "".join(sorted(all_loci))
+    if config["nodes_for_plan_A"]:
+        config["plan_a_masks"], config["store_label_masks"] = plan_a_label_masks(
+            config["nodes_for_plan_A"], len(config["loci_map"]))
     return config
+
+
+def plan_a_label_masks(matrix, n_loci):
+    """"Plan_A_Matrix" -> (locus bit masks of the matrix rows, masks of the labels the store builds).
+
+    The reference generates graph nodes for the matrix labels only (generate_neo4j_multi_hpf.py:101-192), loads
+    them as the vertex set of Plan A (networkx_graph.py:32-66) and imputes only subjects whose typed-locus
+    pattern is a matrix row (impute.py:1592-1596).  What is accepted here is what has a defined behaviour there:
+    rows strictly ascending (input_type yields ascending lists; a permuted row would also permute the alleles
+    inside node names), no repeated row, the full label FIRST (full haplotypes always take ids 0..N-1 while
+    nodes.csv lists labels in matrix order: with the full label elsewhere a vertex's list position no longer
+    equals its id and every adjacency is read from another node), at least one marginal label (the reference's
+    np.vstack of an empty edge list raises otherwise).  The store also builds the single-locus labels (the
+    reference always generates them, generate_neo4j_multi_hpf.py:166-170; the allele-existence checks of the
+    reduce steps read them)."""
+    full = list(range(1, n_loci + 1))
+    masks = []
+    for row in matrix:
+        row = [int(x) for x in row]
+        if not row or row != sorted(set(row)) or row[0] < 1 or row[-1] > n_loci:
+            raise NotImplementedError("Plan_A_Matrix rows must be strictly ascending lists of loci_map indices")
+        m = 0
+        for i in row:
+            m |= 1 << (i - 1)
+        if m in masks:
+            raise NotImplementedError("Plan_A_Matrix lists a label twice")
+        masks.append(m)
+    if [int(x) for x in matrix[0]] != full:
+        raise NotImplementedError(
+            "Plan_A_Matrix must list the full label first: otherwise the reference reads every adjacency from "
+            "another node (vertex list positions vs. node ids)")
+    if len(masks) < 2:
+        raise ValueError("need at least one array to concatenate")   # what the reference's graph load raises
+    store = list(masks) + [1 << l for l in range(n_loci) if (1 << l) not in masks]
+    return masks, store
 
 
 def run_impute(conf_file="../conf/minimal-configuration.json", project_dir_graph="", project_dir_in_file="",

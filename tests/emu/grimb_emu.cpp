@@ -35,8 +35,11 @@ typedef struct {
   const uint32_t* cn_adj;
 } GrimbEmuTables;
 
-int grimb_emu_impute(const GrimbEmuTables* t, const GrimbConfig* cfg, const GrimbBatch* batch,
+int grimb_emu_impute(const GrimbEmuTables* t, const GrimbConfig* cfg_in, const GrimbBatch* batch,
                      GrimbResults* res, uint64_t arena_bytes) {
+  GrimbConfig cfg_dev = *cfg_in;                // as upload_cfg (grimb200.cu) hands it to the kernels
+  if (cfg_dev.plan_a_only) cfg_dev.planb = 0;
+  const GrimbConfig* cfg = &cfg_dev;
   static Shared sh;
   Subject S;
   memset(&S, 0, sizeof(S));

@@ -180,6 +180,11 @@ class EmuGraph(object):
         self.emu = build_emu()
         self.kw = 1
         self.lib = _lib.load(1)   # host-only halves of the text pipeline (no CUDA calls)
+        # Plan_A_Matrix: the rows as locus bit masks (what networkx_graph.Graph records)
+        self.plan_a_masks = None
+        if getattr(oracle_graph, "plan_a", None):
+            full = oracle_graph.full_label
+            self.plan_a_masks = [sum(1 << full.index(ch) for ch in lab) for lab in oracle_graph.plan_a]
 
 
 def emu_imputation(emu_graph, config, count_by_prob=None, arena=64 << 20):

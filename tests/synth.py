@@ -355,3 +355,30 @@ def wide_subjects(table, n, seed, sizes=(7, 8, 9), races=None, prefix="W"):
             line += "," + races[rng.randint(len(races))]
         out.append(line + "\n")
     return out
+
+
+def subset_subjects(table, n, seed, subsets, races=None, prefix="K", amb=0):
+    """Subjects typed at the loci of one of `subsets` (lists of 0-based locus indices, cycled), both haplotypes
+    drawn from the table so Plan A hits; amb > 0 adds up to `amb` extra table alleles per side (Plan_A_Matrix
+    cases: the typed-locus pattern decides whether the reference imputes the subject at all)."""
+    rng = np.random.RandomState(seed)
+    idx = rng.choice(len(table.haps), size=(n, 2), p=table.p)
+    out = []
+    for s in range(n):
+        h1, h2 = table.haps[idx[s, 0]], table.haps[idx[s, 1]]
+        sides = []
+        for l in subsets[s % len(subsets)]:
+            a, b = [h1[l]], [h2[l]]
+            if rng.rand() < 0.5:
+                a, b = b, a
+            for side in (a, b):
+                for _ in range(rng.randint(0, amb + 1) if amb else 0):
+                    x = table.alleles[l][rng.randint(len(table.alleles[l]))]
+                    if x not in side:
+                        side.append(x)
+            sides.append((a, b))
+        line = "%s%d,%s" % (prefix, s, _gl(sides))
+        if races is not None:
+            line += "," + races[s % len(races)]
+        out.append(line + "\n")
+    return out

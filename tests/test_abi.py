@@ -40,7 +40,7 @@ def test_binding_lists_header_symbols():
 def test_abi_version_and_struct_sizes(lib):
     import numpy as np
     lib.grimb_abi_version.restype = ctypes.c_int
-    assert lib.grimb_abi_version() == 4
+    assert lib.grimb_abi_version() == 5
     assert np.dtype(_lib.SUBJECT_DTYPE).itemsize == 48
     assert np.dtype(_lib.COMPACT_DTYPE).itemsize == 16
     assert ctypes.sizeof(_lib.Results) == 10 * 8

@@ -20,6 +20,9 @@ def _graph(table, conf):
     from grim.imputation.networkx_graph import Graph
     from grim.run_impute_def import load_config
     if table not in _graphs:
+        if "+matrix:" in table:   # of the Plan_A_Matrix graphs only the one in use stays (engine workspaces are GBs)
+            for k in [k for k in _graphs if "+matrix:" in k]:
+                _graphs.pop(k).close()
         g = Graph(load_config(conf)).build_graph()
         assert g.kw == 2 and sum(g.key_bits) > 63
         _graphs[table] = g

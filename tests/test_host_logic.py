@@ -140,3 +140,57 @@ def test_produce_hpf_matches_reference_output(tmp_path):
     generate_hpf.produce_hpf(d + "/conf.json")
     assert open(d + "/hpf.csv", newline="").read() == open(os.path.join(goldenlib.GOLD, "data", "cau_hpf.csv"), newline="").read()
     assert open(d + "/pop_counts_file.txt").read() == open(os.path.join(goldenlib.GOLD, "data", "cau_pop_counts.txt")).read()
+
+
+# ---- Plan_A_Matrix: label restriction, subject filter, the Plan B guard
+def test_plan_a_matrix_validation():
+    from grim.run_impute_def import plan_a_label_masks
+    masks, store = plan_a_label_masks([[1, 2, 3, 4, 5], [1, 2, 3], [4, 5], [2]], 5)
+    assert masks == [31, 7, 24, 2]
+    assert store == [31, 7, 24, 2, 1, 4, 8, 16]      # + the single-locus labels the matrix does not name
+    for bad in ([[1, 2, 3], [1, 2, 3, 4, 5]],          # full label not first: vertex positions != node ids
+                [[1, 2, 3, 4, 5], [3, 2]],             # not ascending
+                [[1, 2, 3, 4, 5], [1, 2], [1, 2]],     # repeated
+                [[1, 2, 3, 4, 5], [6]],                # no such locus
+                [[1, 2, 3, 4, 5], []]):
+        with pytest.raises(NotImplementedError):
+            plan_a_label_masks(bad, 5)
+        with pytest.raises(NotImplementedError):
+            go.plan_a_labels(bad, "12345")
+    with pytest.raises(ValueError):                    # the reference's graph load: np.vstack of no edges
+        plan_a_label_masks([[1, 2, 3, 4, 5]], 5)
+    with pytest.raises(ValueError):
+        go.plan_a_labels([[1, 2, 3, 4, 5]], "12345")
+
+
+def test_plan_b_under_a_matrix_is_refused_not_guessed():
+    """A subject that leaves Plan A empty-handed while Plan B is on: the oracle, the numpy front end and the C++ text
+    pipeline all refuse (the reference reads adjacencies of unrelated nodes there); with Plan B off the same subject
+    is a .miss row everywhere."""
+    from emu_backend import emu_impute_text
+    _, conf, lines, exp = goldenlib.load_case("g8_plan_a_blocks_planb_off")
+    miss_ids = {r.split(",")[1] for r in exp["miss"].splitlines()}
+    assert miss_ids
+    pick = [ln for ln in lines if ln.split(",")[0] in miss_ids][:3] + lines[:5]
+    conf_on = dict(conf, planb=True)
+    og = go.graph_from_config(conf_on)
+    with pytest.raises(go.PlanBUnderMatrix):
+        go.impute_file(conf_on, graph=og, lines=pick)
+    eg = EmuGraph(og, conf["loci_map"])
+    with pytest.raises(NotImplementedError):
+        emu_imputation(eg, load_config(conf_on)).impute_lines(pick)
+    with pytest.raises(NotImplementedError):
+        emu_impute_text(emu_imputation(eg, load_config(conf_on)), eg, "".join(pick).encode("utf8"))
+    off = emu_imputation(eg, load_config(conf)).impute_lines(pick)
+    ref, _ = go.impute_file(conf, graph=og, lines=pick)
+    assert "".join(off["miss"]) == ref["miss"] != ""
+
+
+def test_graph_and_configuration_must_name_the_same_matrix():
+    _, conf, _, _ = goldenlib.load_case("g8_plan_a_blocks")
+    conf_c, og_c, eg_c = _cau()
+    with pytest.raises(ValueError):
+        emu_imputation(eg_c, load_config(conf))         # unrestricted graph, matrix in the configuration
+    eg = EmuGraph(go.graph_from_config(conf), conf["loci_map"])
+    with pytest.raises(ValueError):
+        emu_imputation(eg, load_config(conf_c))

@@ -9,7 +9,7 @@ struct GrimbResults;
 extern "C" void* grimb_pinned_alloc(size_t) { return nullptr; }
 extern "C" void grimb_pinned_free(void*) {}
 extern "C" int grimb_impute_host(GrimbEngine*, const GrimbConfig*, const GrimbBatch*, GrimbResults*) { return -1; }
-extern "C" int grimb_abi_version(void) { return 4; }
+extern "C" int grimb_abi_version(void) { return 5; }
 static thread_local char g_msg[256] = "sanitizer build: no device code";
 extern "C" const char* grimb_last_error(void) { return g_msg; }
 extern "C" void grimb_set_error(const char* m) {
