@@ -354,6 +354,7 @@ def main():
     ap.add_argument("--c4-wide-subjects", type=int, default=16)
     ap.add_argument("--c5-haps", type=int, default=100000)
     ap.add_argument("--c5-subjects", type=int, default=1 << 16)
+    ap.add_argument("--c5m-haps", type=int, default=2000000, help="nine-locus table under a Plan_A_Matrix (0: skip)")
     ap.add_argument("--config-sample", type=int, default=300, help="subjects per configuration checked against the oracle")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -167,17 +167,23 @@ def measure(name, g, cfg, cbp, lines, oracle_graph, conf, sample, torch, dev, st
     return rec
 
 
-def table_record(g, n_full, P, L, build_s, peak):
+def table_record(g, n_full, P, L, build_s, peak, labels=None):
     """K0 as a streaming kernel chain: bytes = per marginal label the (key, index) pairs read and written by the
     sort-by-key (12 B each way) and the members' frequency vectors read by the ordered segmented sum, plus the
     table image written once."""
     info = g.info()
-    labels = (1 << L) - 2
+    labels = (1 << L) - 2 if labels is None else labels
     algo = labels * n_full * (24 + 8 * P) + info["device_bytes"]
-    return {"n_full": n_full, "n_nodes": info["n_nodes"], "populations": P, "loci": L, "device_bytes": info["device_bytes"],
-            "build_s": build_s, "kernel_launches": int(g.lib.grimb_tables_build_launches(g.handle)), "algorithmic_bytes": algo,
-            "roofline": {"bound": "hbm", "achieved": algo / build_s / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": algo / build_s / 1e9 / peak}}
+    dev_s = float(g.lib.grimb_tables_build_ms(g.handle)) * 1e-3     # CUDA events inside grimb_tables_build
+    t = dev_s if dev_s > 0 else build_s
+    return {"n_full": n_full, "n_nodes": info["n_nodes"], "populations": P, "loci": L, "labels_built": labels + 1,
+            "device_bytes": info["device_bytes"],
+            "build_s": build_s, "build_device_s": dev_s, "kernel_launches": int(g.lib.grimb_tables_build_launches(g.handle)),
+            "algorithmic_bytes": algo,
+            "note": "build_s = wall time of Graph.from_arrays (host staging + copies + kernels); the roofline uses the "
+                    "device time of the kernel chain",
+            "roofline": {"bound": "hbm", "achieved": algo / t / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": algo / t / 1e9 / peak}}
 
 
 def run_all(args, names, fa, ff1, torch, dev, stream, peak):
@@ -261,4 +267,27 @@ def run_all(args, names, fa, ff1, torch, dev, stream, peak):
                         note="nine loci (256 phases), 5 populations, %d haplotypes, 128-bit keys" % len(fa9))
     out["K0"]["C5_table"] = table_record(g5, len(fa9), 5, 9, t_build5, peak)
     g5.close()
+    del og5, names9, fa9, ff9
+    # ---- C5 at N_full = 2M: only a Plan_A_Matrix makes a nine-locus table of that size fit (510 marginal labels per
+    # haplotype otherwise); the store holds the matrix labels + the single-locus labels, Plan A only
+    if args.c5m_haps > 0:
+        matrix = [[1, 2, 3, 4, 5, 6, 7, 8, 9], [1, 2, 3, 7, 8], [1, 2, 3], [7, 8], [1, 2, 3, 4, 5, 6, 7, 8]]
+        names9, fa9, base_f = synth.zipf_arrays(args.c5m_haps, n_all, 20261019, loci)
+        ff9 = synth.multipop_freqs(base_f, 5, 9, zero_frac=0.2)
+        conf5m = dict(conf5)
+        conf5m.update({"Plan_A_Matrix": matrix, "planb": False})
+        cfg5m = load_config(conf5m)
+        t0 = time.time()
+        g5 = Graph(cfg5m, device=dev.index).from_arrays(names9, fa9, ff9)
+        torch.cuda.synchronize()
+        t_build5 = time.time() - t0
+        p5 = ff9.mean(axis=1)
+        p5 = p5 / p5.sum()
+        lines5 = synth.array_subject_lines(names9, fa9, p5, args.c5_subjects, 10, synth.race_fields(pops5), variants=False)
+        og5 = NumpyOracleGraph(names9, fa9, ff9, pops5, lm9, plan_a_matrix=matrix)
+        out["C5_matrix"] = measure("C5_matrix", g5, cfg5m, ratio5, lines5, og5, conf5m, min(200, args.config_sample), torch, dev,
+                                   stream, peak, note="nine loci, 5 populations, %d haplotypes, 128-bit keys, Plan_A_Matrix of %d "
+                                   "labels (Plan B off)" % (len(fa9), len(matrix)))
+        out["K0"]["C5_matrix_table"] = table_record(g5, len(fa9), 5, 9, t_build5, peak, labels=len(matrix) + 9 - 1 - 1)
+        g5.close()
     return out

@@ -97,6 +97,8 @@ int grimb_tables_info(const GrimbTables* t, GrimbTableInfo* info);
 /* Kernel launches grimb_tables_build issued for this table (0 for a table made from an image): the build is
  * batched over labels, about 60 launches for a 5-locus table whatever its size. */
 int64_t grimb_tables_build_launches(const GrimbTables* t);
+/* Device time of that build in ms, from the staged inputs to the finished image (CUDA events; 0 for an image). */
+double grimb_tables_build_ms(const GrimbTables* t);
 
 /* Copies table arrays to host buffers (any pointer may be NULL).  node_key: packed alleles of
  * node id i; node_freq [n_nodes][P]; tl_start/tl_cnt [n_nodes] and tl_adj [n_toplinks] = top
@@ -151,6 +153,10 @@ typedef struct {
                                          Plan A only whatever `planb` says.  With planb set, the text pipeline
                                          fails with GRIMB_E_UNDEFINED when a subject leaves Plan A without a result:
                                          the reference's Plan B is not well defined under a matrix */
+  int32_t encounter_order;            /* 1: rows are not ranked -- they come in the order the reference's traversal
+                                         first meets them (the insertion order of its result dicts and lists), which
+                                         is what Imputation.impute_one returns (impute.py:1940-1983); with hap_pop_pair
+                                         the PMUG rows are then the un-merged accepted pairs.  General kernel only. */
 } GrimbConfig;
 
 /* A batch of subjects, tokenised by the host (replaces the string handling of

@@ -53,7 +53,7 @@ class _Label:
 
 
 class NumpyOracleGraph:
-    def __init__(self, allele_names, full_alleles, full_freqs, pops, loci_map):
+    def __init__(self, allele_names, full_alleles, full_freqs, pops, loci_map, plan_a_matrix=None):
         """allele_names[l]: names of locus l (position = loci_map index - 1), id = position + 1;
         full_alleles uint16 [N][L] ids of the full haplotypes in first-appearance order (after the
         trim of gen.py:320-339); full_freqs float64 [N][P] in `pops` order (gen.py:341-358)."""
@@ -68,6 +68,13 @@ class NumpyOracleGraph:
         self.labels = [full]
         for r in range(len(full) - 1, 0, -1):
             self.labels.extend("".join(c) for c in itertools.combinations(full, r))
+        # Plan_A_Matrix: as grim_oracle.OracleGraph -- the matrix labels in matrix order, then the single-locus
+        # labels (look-ups only), no connectors, the CSR sentinel on the last Plan-A node
+        self.plan_a = None
+        if plan_a_matrix:
+            from grim_oracle import plan_a_labels
+            self.plan_a = plan_a_labels(plan_a_matrix, full)
+            self.labels = self.plan_a + [ch for ch in full if ch not in self.plan_a]
         self.allele_names = [list(a) for a in allele_names]
         self.allele_id = [{a: i + 1 for i, a in enumerate(al)} for al in self.allele_names]
         self.fa = np.ascontiguousarray(full_alleles, dtype=np.uint16)
@@ -101,6 +108,13 @@ class NumpyOracleGraph:
             nid += c
         self.n_nodes = nid
         self.n_edges = self.n_full * (len(self.labels) - 1)
+        if self.plan_a is not None:
+            self.n_edges = self.n_full * (len(self.plan_a) - 1)
+            self.n_plan_a_nodes = sum(self._count[self._mask_of(lab)] for lab in self.plan_a)
+            self.n_conn = self.n_whole_edges = 0
+            self._lab, self._conn, self._fname, self._fvec = {}, {}, {}, {}
+            self.last_mask = self._mask_of(self.plan_a[-1])
+            return
         n_conn = 0
         whole = 0
         for lab in self.labels:
@@ -121,7 +135,7 @@ class NumpyOracleGraph:
 
     # ---- construction helpers ----
     @classmethod
-    def from_hpf(cls, hpf_lines, pops, loci_map, freq_trim, pop_count_lines=None):
+    def from_hpf(cls, hpf_lines, pops, loci_map, freq_trim, pop_count_lines=None, plan_a_matrix=None):
         """hpf.csv rows -> arrays, following gen.py:259-266 (trim), :320-339 (rows), :341-358."""
         lm = {k: int(v) for k, v in loci_map.items()}
         L = len(lm)
@@ -161,7 +175,7 @@ class NumpyOracleGraph:
         ff = np.zeros((len(rows), len(pops)), np.float64)
         for j, p in enumerate(pops):
             ff[:, j] = [pop_hap.get((p, r), 0.0) for r in rows]
-        return cls(names, fa, ff, pops, loci_map)
+        return cls(names, fa, ff, pops, loci_map, plan_a_matrix)
 
     def _mask_of(self, label):
         m = 0
@@ -313,7 +327,7 @@ class NumpyOracleGraph:
     def _toplinks(self, lab, i):
         own = lab.tl_perm[lab.tl_start[i]:lab.tl_start[i + 1]]
         if lab.mask == self.last_mask and i == lab.n - 1:
-            c = _sentinel_count(len(own), self.n_edges, self.n_nodes)
+            c = _sentinel_count(len(own), self.n_edges, self.n_nodes if self.plan_a is None else self.n_plan_a_nodes)
             if c is None:
                 raise IndexError("CSR sentinel range past the edge array")
             own = own[:c]
@@ -364,6 +378,8 @@ class NumpyOracleGraph:
         # nxg.py:280-307
         if label_a == label_b:
             return self.node_probs(names)
+        if self.plan_a is not None:
+            return {}       # Plan B is refused under a matrix (grim_oracle.PlanBUnderMatrix) before it gets here
         mb = self._mask_of(label_b)
         out = {}
         for n in names:

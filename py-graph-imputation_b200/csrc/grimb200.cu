@@ -71,6 +71,7 @@ struct GrimbTables {
   ImageHeader h;
   TablesView view;
   int build_launches = 0;   // kernel launches of grimb_tables_build (0 for a table made from an image)
+  float build_ms = 0.0f;    // device time of the build after the inputs were staged (CUDA events on the build's stream)
 };
 
 static void make_view(GrimbTables* t) {
@@ -500,6 +501,10 @@ extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
     for (uint32_t li = 0; li < n_labels; ++li) lm[li] = order[li];
     CKT(cudaMemcpy(d_lmask, lm.data(), 512 * 4, cudaMemcpyHostToDevice));
   }
+  cudaEvent_t ev_b0 = nullptr, ev_b1 = nullptr;
+  cudaEventCreate(&ev_b0);
+  cudaEventCreate(&ev_b1);
+  cudaEventRecord(ev_b0, 0);
   if (N) {
     k_pack_full<<<nblk(N), 256>>>(d_al, L, d_shift, N, d_keys);
     ++launches;
@@ -791,7 +796,11 @@ extern "C" int grimb_tables_build(const GrimbTableDesc* d, GrimbTables** out) {
     }
   }
   CKT(cudaMemcpy(t->image, &h, sizeof(h), cudaMemcpyHostToDevice));
+  cudaEventRecord(ev_b1, 0);
   CKT(cudaDeviceSynchronize());
+  if (ev_b0 && ev_b1) cudaEventElapsedTime(&t->build_ms, ev_b0, ev_b1);
+  if (ev_b0) cudaEventDestroy(ev_b0);
+  if (ev_b1) cudaEventDestroy(ev_b1);
   t->build_launches = launches;
   cleanup(true);
   *out = t;
@@ -809,6 +818,7 @@ extern "C" int grimb_tables_free(GrimbTables* t) {
 }
 
 extern "C" int64_t grimb_tables_build_launches(const GrimbTables* t) { return t ? t->build_launches : 0; }
+extern "C" double grimb_tables_build_ms(const GrimbTables* t) { return t ? (double)t->build_ms : 0.0; }
 
 extern "C" int grimb_tables_info(const GrimbTables* t, GrimbTableInfo* info) {
   if (!t || !info) return fail(GRIMB_E_ARG, "null argument");
@@ -2605,7 +2615,7 @@ static OutArrays out_arrays(GrimbEngine* e, const GrimbResults& r) {
 // warp-per-subject kernel serves this table / mode).  No synchronisation in either.
 static bool warp_kernels_apply(const GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch) {
   // the warp-per-subject kernels implement the default phase enumeration and row layout only
-  if (!(e->fast_path && (!batch->phase_mask || batch->packed_keys) && !cfg->hap_pop_pair)) return false;
+  if (!(e->fast_path && (!batch->phase_mask || batch->packed_keys) && !cfg->hap_pop_pair && !cfg->encounter_order)) return false;
   const TablesView& tv = e->tables->view;
 #if GRIMB_KW == 1
   if (tv.L <= 5 && tv.P == 1) return true;

@@ -1142,6 +1142,7 @@ struct Subject : Ctx {
     for (uint32_t i = g.tid; i < ent_n; i += g.n) ord[i] = i;
     g.sync();
     const Entry* E = ent;
+    if (!cfg->encounter_order)   // (encounter_order: the entries as the traversal met them, impute.py:1940-1983)
     group_sort(
         g, ent_n,
         [=](uint32_t a, uint32_t b) {

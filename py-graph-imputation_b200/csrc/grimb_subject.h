@@ -736,7 +736,11 @@ struct Ctx {
       g.sync();
     }
     uint32_t rows = ng < limit ? ng : limit;
-    if (rows <= 64 && ng > 1024) {
+    if (cfg->encounter_order) {
+      // group ids ARE the first-encounter order (the insertion order of the reference's dicts)
+      for (uint32_t r = g.tid; r < rows; r += g.n) slot_gid[r] = r;
+      g.sync();
+    } else if (rows <= 64 && ng > 1024) {
       // repeated arg-max over (sum desc, group id asc); taken groups are marked in gord
       for (uint32_t r = 0; r < rows; ++r) {
         double best = -1.0;

@@ -50,6 +50,7 @@ class Config(C.Structure):
         ("row_blocks", C.c_int32 * MAX_ROWS), ("block_mask", (C.c_uint16 * MAX_BLOCKS) * MAX_ROWS),
         ("row_is_plan_a", C.c_uint8 * MAX_ROWS),
         ("hap_pop_pair", C.c_int32), ("em", C.c_int32), ("plan_a_only", C.c_int32),
+        ("encounter_order", C.c_int32),
     ]
 
 
@@ -195,6 +196,8 @@ def load(kw=1):
     lib.grimb_tables_image_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     lib.grimb_tables_image_copy.argtypes = [C.c_void_p, C.c_void_p]
     lib.grimb_tables_from_image.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_void_p)]
+    lib.grimb_tables_build_ms.argtypes = [C.c_void_p]
+    lib.grimb_tables_build_ms.restype = C.c_double
     lib.grimb_engine_create.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
     lib.grimb_engine_free.argtypes = [C.c_void_p]
     lib.grimb_engine_launches.argtypes = [C.c_void_p]
@@ -233,7 +236,7 @@ def check(rc, what, lib=None):
 
 EXPORTED = [
     "grimb_abi_version", "grimb_last_error", "grimb_tables_build", "grimb_tables_free",
-    "grimb_tables_info", "grimb_tables_build_launches", "grimb_tables_export", "grimb_tables_image_size", "grimb_tables_image_ptr",
+    "grimb_tables_info", "grimb_tables_build_launches", "grimb_tables_build_ms", "grimb_tables_export", "grimb_tables_image_size", "grimb_tables_image_ptr",
     "grimb_tables_image_copy", "grimb_tables_from_image", "grimb_engine_create", "grimb_engine_free", "grimb_engine_launches", "grimb_engine_kernel_ms",
     "grimb_impute_device", "grimb_impute_device_async", "grimb_impute_finish", "grimb_impute_host",
     "grimb_text_create", "grimb_text_free", "grimb_text_tokenise", "grimb_text_format", "grimb_impute_text",

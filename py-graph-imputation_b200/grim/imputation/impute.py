@@ -465,6 +465,89 @@ class Imputation(object):
             self._process(pending, files)
         return files
 
+    def impute_one(self, subject_id, gl, binary, race1, race2, priority, epsilon, n, MUUG_output, haps_output, planb, em):
+        """The per-subject seam of the reference (impute.py:1940-1983; consumer scripts/parallel-imputation.py):
+        -> (subject_id, res_muugs, res_haps) with the reference's structures --
+            res_muugs = {"MaxProb", "Haps": {genotype: prob}, "Pops": {"pop,pop": prob}}   (dicts in insertion order)
+            res_haps  = {"MaxProb", "Haps": [[hap1, hap2]], "Probs": [prob], "Pops": [[pop1, pop2]]}   (un-merged)
+        or (subject_id, None, None) where comp_cand gives up.  A compatibility mode: one subject per call through
+        the general kernel with GrimbConfig.encounter_order (rows in traversal order, nothing ranked) and
+        hap_pop_pair (the accepted pairs, un-merged); the batch entry points are the fast path.  `n` is accepted
+        and unused, as in the reference.  MaxProb is the largest single-pair probability of the haplotype-pair
+        evaluation (the genotype evaluation meets the same pairs whenever both end in the same plan)."""
+        saved = (self.cfg.epsilon, self.cfg.planb, self.cfg.em, self.cfg.hap_pop_pair, self.cfg.encounter_order,
+                 self.cfg.output_umug, self.cfg.output_pmug, self.cfg.n_results, self.cfg.n_pop_results, self._em_mr,
+                 self.priority, self._prior_index, self._priors)
+        limit = int(os.environ.get("GRIMB_IMPUTE_ONE_ROWS", "200000"))
+        try:
+            self.cfg.epsilon = float(epsilon)
+            self.cfg.planb = 1 if planb else 0
+            self.cfg.em = 1 if em else 0
+            self.cfg.hap_pop_pair, self.cfg.encounter_order = 1, 1
+            self.cfg.output_umug, self.cfg.output_pmug = 1, 1
+            self.cfg.n_results = self.cfg.n_pop_results = limit
+            self._em_mr = True
+            if priority is not None and priority != self.priority:
+                self.priority, self._prior_index, self._priors = priority, {}, []
+            default_muugs = {"MaxProb": 0, "Haps": {}, "Pops": {}}
+            default_haps = {"Haps": "Nan", "Probs": 0, "Pops": {}}
+            pidx = self._prior_for(race1, race2)
+            if not gl:
+                return subject_id, None, None
+            hclass, payload = self._encode_gl(gl)
+            if hclass == H_PROBLEM:
+                return subject_id, None, None
+            if hclass == H_FAULT:
+                raise RuntimeError("the reference raises inside this subject")
+            if payload == "foreign":       # nothing is imputed (Plan B off): the defaults come back
+                return subject_id, default_muugs, default_haps
+            mask, counts, flat, unknown = payload
+            pm = 0xFFFF
+            if binary is not None:
+                pm = 0
+                for m, e in enumerate(binary):
+                    if e == 1 and m < 16:
+                        pm |= 1 << m
+            had_masks = self.phase_masks
+            if binary is not None and had_masks is None:
+                self.phase_masks = {}      # makes _run_batch hand the mask array to the kernels
+            try:
+                rows = None
+                for tier in self.workspaces:
+                    out = self._run_batch([(mask, counts, flat, pidx, pm)], tier)
+                    if out.compact["status"][0] != _lib.ST_WORKSPACE:
+                        rows = self._subject_rows(out, 0, flat, unknown)
+                        break
+                if rows is None:
+                    raise MemoryError("the subject exceeds the largest workspace tier (GRIMB_WORKSPACES)")
+            finally:
+                self.phase_masks = had_masks
+            if rows["status"] == _lib.ST_FAULT:
+                raise RuntimeError("the reference raises inside this subject")
+            if rows["status"] == _lib.ST_NO_PHASES:
+                return subject_id, default_muugs, default_haps
+            if rows["tot_pmug"] > limit or rows["tot_umug"] > limit:
+                raise MemoryError("more than GRIMB_IMPUTE_ONE_ROWS = %d result rows" % limit)
+            max_prob = max([p for _a, _b, p in rows["pmug"]], default=0)
+            res_muugs, res_haps = default_muugs, default_haps
+            if MUUG_output:
+                res_muugs = {"MaxProb": max_prob, "Haps": {}, "Pops": {}}
+                for pairs, prob in rows["umug"]:
+                    res_muugs["Haps"]["^".join("+".join(sorted([x, y])) for x, y in pairs)] = prob
+                for pa, pb, prob in rows["umug_pops"]:
+                    res_muugs["Pops"][",".join(sorted([pa, pb]))] = prob
+            if haps_output:
+                res_haps = {"MaxProb": max_prob, "Haps": [], "Probs": [], "Pops": []}
+                for (h1, h2, prob), (pa, pb) in zip(rows["pmug"], rows["pmug_pairs"]):
+                    res_haps["Haps"].append(["~".join(h1), "~".join(h2)])
+                    res_haps["Probs"].append(prob)
+                    res_haps["Pops"].append([pa, pb])
+            return subject_id, res_muugs, res_haps
+        finally:
+            (self.cfg.epsilon, self.cfg.planb, self.cfg.em, self.cfg.hap_pop_pair, self.cfg.encounter_order,
+             self.cfg.output_umug, self.cfg.output_pmug, self.cfg.n_results, self.cfg.n_pop_results, self._em_mr,
+             self.priority, self._prior_index, self._priors) = saved
+
     def _process(self, pending, files):
         cfgd = self.config
         meta = []   # (line index, id, raw, host class, unknown map)

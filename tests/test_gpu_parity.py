@@ -331,3 +331,16 @@ def test_file_pipeline_many_chunks_files_and_memory(name, tmp_path):
         parts.append({k: C.string_at(out.data[i], out.size[i]).decode("utf8") for i, k in enumerate(_lib.OUT_KEYS)})
     for k in goldenlib.KEYS:
         assert parts[0][k] + parts[1][k] == exp[k], "%s: %s differs (byte ranges)" % (name, k)
+
+
+def test_impute_one_seam_on_the_gpu():
+    """Imputation.impute_one (the reference's per-subject seam): traversal-order dicts and un-merged lists from the
+    general kernel's encounter-order mode, against the oracle."""
+    from impute_one_check import check_impute_one
+    from grim.imputation.impute import Imputation
+    from grim.run_impute_def import load_config
+    for name, sl, binary in (("g2_edges", slice(None), None), ("g3_pop3_messy", slice(0, 40), None),
+                             ("g3_pop3_messy", slice(40, 50), [0, 1, 1, 0]), ("g1_readme_donor", slice(0, 1), None)):
+        table, conf, lines, _ = goldenlib.load_case(name)
+        imp = Imputation(_graph(table, conf), load_config(conf))
+        assert check_impute_one(conf, lines[sl], binary, imp=imp, og=_oracle_graph(table, conf)) >= 1

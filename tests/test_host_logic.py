@@ -194,3 +194,18 @@ def test_graph_and_configuration_must_name_the_same_matrix():
     eg = EmuGraph(go.graph_from_config(conf), conf["loci_map"])
     with pytest.raises(ValueError):
         emu_imputation(eg, load_config(conf_c))
+
+
+# ---- the per-subject seam (impute.py:1940-1983): un-merged lists / dicts in traversal order
+from impute_one_check import check_impute_one as _check_impute_one  # noqa: E402
+
+
+def test_impute_one_returns_the_reference_structures():
+    import synth
+    _, conf, lines, _ = goldenlib.load_case("g2_edges")
+    assert _check_impute_one(conf, lines) >= 8
+    _, conf3, lines3, _ = goldenlib.load_case("g3_pop3_messy")
+    assert _check_impute_one(conf3, lines3[:25]) >= 15
+    assert _check_impute_one(conf3, lines3[25:32], binary=[1, 0, 1, 0]) >= 3
+    _, conf1, lines1, _ = goldenlib.load_case("g1_readme_donor")
+    assert _check_impute_one(conf1, lines1[:1]) == 1          # README donor: 8400 un-merged pairs

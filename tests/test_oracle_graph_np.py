@@ -94,3 +94,17 @@ def test_golden_cases_through_numpy_store(name):
     out, _ = go.impute_file(conf, graph=ng, lines=lines)
     for k in goldenlib.KEYS:
         assert out[k] == exp[k], "%s: %s differs" % (name, k)
+
+
+@pytest.mark.parametrize("name", ["g8_plan_a_blocks", "g8_plan_a_blocks_planb_off", "g8_plan_a_last_node", "g8_plan_a_nine"])
+def test_plan_a_matrix_cases_through_numpy_store(name):
+    """The array-backed store under a Plan_A_Matrix (what bench.py's C5_matrix record is checked with): the
+    reference's files for the g8 cases."""
+    _t, conf, lines, exp = goldenlib.load_case(name)
+    hpf = open(conf["freq_file"]).readlines()
+    pc = open(conf["pops_count_file"]).readlines()
+    ng = NumpyOracleGraph.from_hpf(hpf, conf["populations"], conf["loci_map"], conf["freq_trim_threshold"], pc,
+                                   plan_a_matrix=conf["Plan_A_Matrix"])
+    out, _ = go.impute_file(conf, graph=ng, lines=lines)
+    for k in goldenlib.KEYS:
+        assert out[k] == exp[k], "%s: %s differs" % (name, k)

@@ -32,3 +32,22 @@ for rep in range(4):
     dt = time.time() - t0
     print("tokenise %d lines (%d bytes): %.1f ms, %.0f ns/line, %.0f MB/s, packed=%s" % (
         n, len(data), dt * 1e3, dt / n * 1e9, len(data) / dt / 1e6, bool(b.packed_keys)))
+
+# formatter: results of the emulated kernel source for the same batch, formatted repeatedly
+S = b.n_subjects
+res = _lib.ResultArrays(S, 1, general=S + 16, hap=4096, pop=4096)
+while True:
+    r = res.struct
+    rc = eg.emu.grimb_emu_impute(C.byref(eg.tables), C.byref(imp.cfg), C.byref(b), C.byref(r), 64 << 20)
+    if rc == _lib.E_CAPACITY:
+        res.grow()
+        continue
+    assert rc == 0
+    break
+out = _lib.TextOut()
+for rep in range(4):
+    t0 = time.time()
+    _lib.check(lib.grimb_text_format(t, C.byref(imp.cfg), C.byref(r), C.byref(out)), "format")
+    dt = time.time() - t0
+    nb = sum(out.size[i] for i in range(6))
+    print("format %d subjects -> %d bytes: %.1f ms, %.0f ns/subject, %.0f MB/s" % (S, nb, dt * 1e3, dt / S * 1e9, nb / dt / 1e6))
