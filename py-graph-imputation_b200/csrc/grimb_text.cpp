@@ -31,6 +31,80 @@ namespace {
 
 using sv = std::string_view;
 
+// Append-only byte buffer of the formatter.  The six outputs are built from some 40 short pieces per row;
+// std::string pays a capacity check, a memcpy call and a terminator store for each.  Here the capacity check is
+// one compare against a slack the buffer always keeps, and pieces up to 16 bytes (allele names, ids, digits) are
+// copied with two overlapping word moves.
+struct OutStr {
+  char* p = nullptr;
+  size_t n = 0, cap = 0;
+  OutStr() = default;
+  OutStr(const OutStr&) = delete;
+  OutStr& operator=(const OutStr&) = delete;
+  OutStr(OutStr&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+  OutStr& operator=(OutStr&& o) noexcept {
+    if (this != &o) {
+      free(p);
+      p = o.p; n = o.n; cap = o.cap;
+      o.p = nullptr; o.n = o.cap = 0;
+    }
+    return *this;
+  }
+  ~OutStr() { free(p); }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  const char* data() const { return p; }
+  void clear() { n = 0; }
+  void grow(size_t need) {
+    size_t c = cap ? cap * 2 : 4096;
+    while (c < n + need + 64) c *= 2;
+    char* q = (char*)realloc(p, c);
+    if (!q) throw std::bad_alloc();
+    p = q;
+    cap = c;
+  }
+  inline void room(size_t need) {
+    if (n + need + 64 > cap) grow(need);
+  }
+  inline OutStr& operator+=(char c) {
+    room(1);
+    p[n++] = c;
+    return *this;
+  }
+  inline void append(const char* s, size_t len) {
+    room(len);
+    char* d = p + n;
+    if (len <= 16) {
+      if (len >= 8) {
+        uint64_t a, b;
+        memcpy(&a, s, 8);
+        memcpy(&b, s + len - 8, 8);
+        memcpy(d, &a, 8);
+        memcpy(d + len - 8, &b, 8);
+      } else if (len >= 4) {
+        uint32_t a, b;
+        memcpy(&a, s, 4);
+        memcpy(&b, s + len - 4, 4);
+        memcpy(d, &a, 4);
+        memcpy(d + len - 4, &b, 4);
+      } else {
+        for (size_t i = 0; i < len; ++i) d[i] = s[i];
+      }
+    } else {
+      memcpy(d, s, len);
+    }
+    n += len;
+  }
+  inline OutStr& operator+=(sv x) {
+    append(x.data(), x.size());
+    return *this;
+  }
+  inline OutStr& operator+=(const std::string& x) {
+    append(x.data(), x.size());
+    return *this;
+  }
+};
+
 int tfail(int code, const std::string& m) {
   grimb_set_error(m.c_str());
   return code;
@@ -150,15 +224,19 @@ int py_float_buf(double x, char* out) {
   return (int)(o - out);
 }
 
-void py_float(double x, std::string& out) {
-  char b[40];
-  out.append(b, (size_t)py_float_buf(x, b));
+void py_float(double x, OutStr& out) {
+  out.room(40);
+  out.n += (size_t)py_float_buf(x, out.p + out.n);
 }
 
-void put_uint(uint64_t v, std::string& out) {
-  char b[24];
-  auto r = std::to_chars(b, b + sizeof(b), v);
-  out.append(b, (size_t)(r.ptr - b));
+void put_uint(uint64_t v, OutStr& out) {
+  out.room(24);
+  if (v < 10) {   // the rank column: mostly one digit
+    out.p[out.n++] = (char)('0' + v);
+    return;
+  }
+  auto r = std::to_chars(out.p + out.n, out.p + out.n + 24, v);
+  out.n = (size_t)(r.ptr - out.p);
 }
 
 struct PriorKey {
@@ -257,7 +335,7 @@ struct GrimbText {
     GrimbResults fin;
     int64_t totals[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int64_t retries = 0;
-    std::vector<std::string> fmt_parts;   // per-thread pieces of the six outputs (capacity reused)
+    std::vector<OutStr> fmt_parts;   // per-thread pieces of the six outputs (capacity reused)
     std::string out[6];
     int64_t out_size[6] = {0, 0, 0, 0, 0, 0};
     int64_t plan_count[4] = {0, 0, 0, 0};
@@ -743,7 +821,7 @@ struct GrimbText {
   }
 #endif
 
-  void put_hap(const Slot& S, keyref key, const Line& ln, std::string& o) const {
+  void put_hap(const Slot& S, keyref key, const Line& ln, OutStr& o) const {
     bool first = true;
     for (int l = 0; l < L; ++l) {
       uint32_t id = field(key, l);
@@ -756,7 +834,7 @@ struct GrimbText {
 
   sv pop_name(uint16_t p) const { return p == 0xFFFF ? sv("all_pops") : sv(pops[p]); }
 
-  static void put_row_tail(double prob, uint32_t k, std::string& s) {
+  static void put_row_tail(double prob, uint32_t k, OutStr& s) {
     s += ',';
     py_float(prob, s);
     s += ',';
@@ -770,7 +848,7 @@ struct GrimbText {
     char t[40];
     int n;
   };
-  static void put_row_tail(const ProbText& pt, double prob, uint32_t k, std::string& s) {
+  static void put_row_tail(const ProbText& pt, double prob, uint32_t k, OutStr& s) {
     if (dbits_equal(prob, pt.v)) {
       s += ',';
       s.append(pt.t, (size_t)pt.n);
@@ -783,7 +861,7 @@ struct GrimbText {
   }
   static bool dbits_equal(double a, double b) { return memcmp(&a, &b, 8) == 0; }
 
-  void put_pop_row(sv sid, sv x, sv y, double prob, uint32_t k, bool sorted, std::string& s,
+  void put_pop_row(sv sid, sv x, sv y, double prob, uint32_t k, bool sorted, OutStr& s,
                    const ProbText* pt = nullptr) const {
     if (sorted && y < x) std::swap(x, y);
     s += sid;
@@ -800,7 +878,7 @@ struct GrimbText {
   // pairs and a PMUG row's haplotypes follow from its phase id (bit m: locus m takes its side-2 allele in
   // the first haplotype).  Same row order and text as the general layout below.
   void format_compact(const Slot& S, const Line& ln, const GrimbCompact& c, const uint64_t* words, const GrimbConfig* cfg,
-                      std::string* o) const {
+                      OutStr* o) const {
     const uint16_t* ids = S.t_ids[ln.thread].data() + ln.ids_off;   // [L][2]
     const uint32_t kind = c.kind_flags & 3u;
     uint32_t n_pmug = c.kind_flags >> 4;
@@ -850,7 +928,7 @@ struct GrimbText {
     };
     if (cfg->output_pmug) {
       for (uint32_t k = 0; k < n_pmug; ++k) {
-        std::string& s = o[GRIMB_OUT_PMUG];
+        OutStr& s = o[GRIMB_OUT_PMUG];
         s += ln.sid;
         s += ',';
         for (int side = 0; side < 2; ++side) {
@@ -871,7 +949,7 @@ struct GrimbText {
     }
     if (cfg->output_umug && has) {
       if (cfg->n_results >= 1) {
-        std::string& s = o[GRIMB_OUT_UMUG];
+        OutStr& s = o[GRIMB_OUT_UMUG];
         s += ln.sid;
         s += ',';
         for (int l = 0; l < L; ++l) {
@@ -894,11 +972,11 @@ struct GrimbText {
   }
 
   void format_subject(const Slot& S, const Line& ln, const GrimbSubjectResult& r, const GrimbHapRow* hr, const GrimbPopRow* pr,
-                      const GrimbConfig* cfg, std::string* o) const {
+                      const GrimbConfig* cfg, OutStr* o) const {
     if (cfg->output_pmug) {
       for (uint32_t k = 0; k < r.n_pmug; ++k) {
         const GrimbHapRow& row = hr[r.hap_off + r.n_umug + k];
-        std::string& s = o[GRIMB_OUT_PMUG];
+        OutStr& s = o[GRIMB_OUT_PMUG];
         s += ln.sid;
         s += ',';
         put_hap(S, row.a, ln, s);
@@ -914,7 +992,7 @@ struct GrimbText {
     if (cfg->output_umug) {
       for (uint32_t k = 0; k < r.n_umug; ++k) {
         const GrimbHapRow& row = hr[r.hap_off + k];
-        std::string& s = o[GRIMB_OUT_UMUG];
+        OutStr& s = o[GRIMB_OUT_UMUG];
         s += ln.sid;
         s += ',';
         bool first = true;
@@ -934,7 +1012,7 @@ struct GrimbText {
       const bool planc_empty = r.plan_umug == GRIMB_PLAN_C && r.tot_umug == 0;
       for (uint32_t k = 0; k < r.n_umug_pops; ++k) {
         const GrimbPopRow& row = pr[r.pop_off + k];
-        std::string& s = o[GRIMB_OUT_UMUG_POPS];
+        OutStr& s = o[GRIMB_OUT_UMUG_POPS];
         sv x = pop_name(row.pop_a), y = pop_name(row.pop_b);
         if (y < x) std::swap(x, y);
         s += ln.sid;
@@ -1218,7 +1296,7 @@ int format_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const GrimbResult
   auto t0 = clk::now();
   const size_t NS = S.lines.size();
   const int nt = t->n_threads;
-  std::vector<std::string>& parts = S.fmt_parts;
+  std::vector<OutStr>& parts = S.fmt_parts;
   parts.resize((size_t)nt * 6);
   for (auto& ps : parts) ps.clear();
   std::vector<int64_t> plans((size_t)nt * 4, 0);
@@ -1228,7 +1306,7 @@ int format_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const GrimbResult
   const bool guard_planb = cfg->plan_a_only && cfg->planb;
   std::vector<int64_t> undefined_first((size_t)nt, -1), undefined_n((size_t)nt, 0);
   t->parallel(NS, [&](int th, size_t lo, size_t hi) {
-    std::string* o = &parts[(size_t)th * 6];
+    OutStr* o = &parts[(size_t)th * 6];
     int64_t my_plans[4] = {0, 0, 0, 0};   // (a shared array of counters, one slot per thread, is a false-sharing trap)
     for (size_t i = lo; i < hi; ++i) {
       const Line& ln = S.lines[i];
@@ -1291,6 +1369,7 @@ int format_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const GrimbResult
     }
     for (int k = 0; k < 4; ++k) plans[(size_t)th * 4 + k] = my_plans[k];
   });
+  auto tR = clk::now();
   // concatenate the pieces of every output in thread order, the copies themselves in parallel
   std::vector<size_t> offs((size_t)nt * 6, 0);
   for (int k = 0; k < 6; ++k) {
@@ -1305,7 +1384,7 @@ int format_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const GrimbResult
   t->parallel((size_t)nt, [&](int, size_t lo, size_t hi) {
     for (size_t th = lo; th < hi; ++th)
       for (int k = 0; k < 6; ++k) {
-        const std::string& ps = parts[th * 6 + k];
+        const OutStr& ps = parts[th * 6 + k];
         if (!ps.empty()) memcpy(&S.out[k][offs[th * 6 + k]], ps.data(), ps.size());
       }
   });
@@ -1313,6 +1392,8 @@ int format_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const GrimbResult
   for (int th = 0; th < nt; ++th)
     for (int k = 0; k < 4; ++k) S.plan_count[k] += plans[(size_t)th * 4 + k];
   S.sec_fmt = secs(t0, clk::now());
+  if (getenv("GRIMB_TEXT_TRACE") && getenv("GRIMB_TEXT_TRACE")[0] == '2')
+    fprintf(stderr, "format: rows %.1f ms, concatenate %.1f ms\n", secs(t0, tR) * 1e3, secs(tR, clk::now()) * 1e3);
   {
     int64_t n_undef = 0, first = -1;
     for (int th = 0; th < nt; ++th) {
