@@ -2414,9 +2414,25 @@ struct GrimbEngine {
 
 extern "C" int grimb_engine_free(GrimbEngine* e);
 
+// A probe wants ONE 32-byte sector of a hash region far larger than a cache line's worth of locality.  The L2's
+// default fetch granularity is 64 bytes: every miss pulls the neighbouring sector (another bucket, useless) from
+// DRAM as well -- ncu of k_fast_probe: 32.1 M read requests from the SMs looked up 70.5 M sectors, DRAM read
+// 1.29 GB for 0.65 GB of missing sectors.  cudaLimitMaxL2FetchGranularity = 32 asks for sector-sized fetches
+// (a hint; GRIMB_L2_FETCH=64|128 restores a larger granularity for A/B runs).
+static void set_l2_fetch_granularity() {
+  size_t g = 32;
+  if (const char* v = getenv("GRIMB_L2_FETCH")) {
+    const long x = atol(v);
+    if (x == 32 || x == 64 || x == 128) g = (size_t)x;
+    else if (x == 0) return;   // leave the device default
+  }
+  if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g) != cudaSuccess) cudaGetLastError();
+}
+
 extern "C" int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes_per_cta, GrimbEngine** out) {
   if (!t || !out || workspace_bytes_per_cta < (1 << 16)) return fail(GRIMB_E_ARG, "bad engine arguments");
   CK(cudaSetDevice(t->device));
+  set_l2_fetch_granularity();
   GrimbEngine* e = new GrimbEngine();
   for (int i = 0; i < GRIMB_MAX_CHUNKS; ++i) e->ev_in[i] = e->ev_k[i] = nullptr;
   e->tables = t;
