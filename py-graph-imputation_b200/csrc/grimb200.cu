@@ -1404,12 +1404,21 @@ constexpr int FAST_CALL = 16;   // candidate phases a hand-over record holds (= 
 // Header and first candidate share one 32-byte sector: the usual subject (one candidate phase) costs one
 // sector written by the probe kernel and one read by the score kernel.  96 bytes = 3 sectors.  A subject with
 // more than FAST_CMAX candidate phases (rare) keeps them in a side record claimed from `extra`.
-struct __align__(32) FastMid {
+// (round 2, later: the record is split -- a dense array of 32-byte heads, which is all the usual subject touches,
+// and a second array for candidates 2..4)
+struct __align__(32) FastHead {
   uint32_t flags;        // bits 0-1 state (0 not for k_fast_score, 1 ready), 2-6 ncand, 7 both haplotypes equal
   uint32_t extra;        // ncand > FAST_CMAX: index of the subject's FastExtra
-  uint64_t phases;       // phase ids of the candidates, ascending, 4 bits each
-  double f[FAST_CMAX][2];  // (f1, f2) of the candidate phases, ascending phase (ncand <= FAST_CMAX)
-  double tail[2];
+  uint64_t phases;       // bit i: phase i is a candidate (candidates are stored in ascending phase order)
+  double f0[2];          // (f1, f2) of the first candidate phase
+};
+struct __align__(64) FastMore {
+  double f[FAST_CMAX - 1][2];   // candidates 2..FAST_CMAX (ncand <= FAST_CMAX)
+  double pad[2];
+};
+struct FastMid {
+  FastHead* head;
+  FastMore* more;
 };
 struct __align__(32) FastExtra {
   double f[FAST_CALL][2];
@@ -1452,7 +1461,7 @@ __device__ __forceinline__ void probe_load(ProbeIn& in, const GrimbBatch& B, uin
 
 template <bool PACKED>
 __global__ void __launch_bounds__(FAST_WARPS * 32, FASTPROBE_MIN_BLOCKS)
-k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid, uint32_t* worklist,
+k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid mid, uint32_t* worklist,
              unsigned int* worklist_n, FastExtra* __restrict__ extra, unsigned int* extra_n, uint32_t extra_cap, int nchain_ok,
              uint32_t s_begin) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1479,8 +1488,7 @@ k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid,
     // packed form: in.typed is the flag word (bit 15 = skip); every subject that is not skipped has the shape
     const uint32_t typed = PACKED ? ((in.typed & 0x8000u) ? 0u : full) : in.typed;
     const bool shape = typed == full && nchain_ok && (PACKED || in.nall == 2u * (uint32_t)L);   // uniform in the half-warp
-    uint32_t state = 0, ncand = 0, same = 0, xslot = 0;
-    uint64_t phases = 0;
+    uint32_t state = 0, ncand = 0, same = 0, xslot = 0, phases = 0;
     if (shape) {
       uint64_t k0, k1;
       uint32_t unk0, unk1, het;
@@ -1519,13 +1527,8 @@ k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid,
       const uint32_t cmask = (__ballot_sync(hmask, cand) >> hbase) & 0xFFFFu;
       ncand = __popc(cmask);
       state = 1;
-      // phase ids of the candidates, ascending, 4 bits each
-      uint32_t mm = cmask;
-      for (uint32_t q = 0; q < ncand; ++q) {
-        phases |= (uint64_t)(__ffs(mm) - 1) << (4 * q);
-        mm &= mm - 1;
-      }
-      double2* dst = &reinterpret_cast<double2*>(&mid[s].f[0][0])[0];
+      phases = cmask;   // the candidates' phase ids: k_fast_score reads them off the mask (q-th set bit)
+      double2* dst = nullptr;    // the side record of a long-form subject
       if (ncand > FAST_CMAX) {   // rare: a side record (uniform in the half-warp)
         unsigned int x = 0;
         if (i == 0) x = atomicAdd(extra_n, 1u);
@@ -1542,7 +1545,9 @@ k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid,
         double2 v;
         v.x = f1;
         v.y = f2;
-        dst[slot] = v;
+        if (dst) dst[slot] = v;
+        else if (slot == 0) *reinterpret_cast<double2*>(&mid.head[s].f0[0]) = v;
+        else *reinterpret_cast<double2*>(&mid.more[s].f[slot - 1][0]) = v;
       }
     }
     if (!shape && typed != 0) {
@@ -1554,9 +1559,9 @@ k_fast_probe(TablesView T, GrimbBatch B, OutArrays O, FastMid* __restrict__ mid,
       uint4 h1;   // header: state and candidate bookkeeping
       h1.x = state | (ncand << 2) | (same << 7);
       h1.y = xslot;
-      h1.z = (uint32_t)phases;
-      h1.w = (uint32_t)(phases >> 32);
-      reinterpret_cast<uint4*>(mid + s)[0] = h1;
+      h1.z = phases;
+      h1.w = 0;
+      reinterpret_cast<uint4*>(mid.head + s)[0] = h1;
     }
   }
 }
@@ -1647,7 +1652,7 @@ __device__ __noinline__ void score_long_eval(const FastExtra* ex, uint32_t ncand
 }
 
 // rows of the long form: words[0] = number of rows, words[1] = their phase ids (rank order), words[2 + k] = probability
-__device__ __noinline__ void score_long_rows(const FastExtra* ex, uint32_t ncand, double m, bool same, double e_fin, uint64_t ph64,
+__device__ __noinline__ void score_long_rows(const FastExtra* ex, uint32_t ncand, double m, bool same, double e_fin, uint32_t cmask,
                                              uint32_t np, uint64_t* words) {
   const int lane = threadIdx.x & 31;
   LongCand c;
@@ -1663,7 +1668,7 @@ __device__ __noinline__ void score_long_rows(const FastExtra* ex, uint32_t ncand
   }
   uint32_t lo = 0, hi = 0;
   if (acc && rank < np) {
-    const uint32_t id = (uint32_t)(ph64 >> (4 * lane)) & 15u;
+    const uint32_t id = __fns(cmask, 0, lane + 1) & 15u;   // phase of candidate `lane`: the lane-th set bit
     if (rank < 8) lo = id << (4 * rank);
     else hi = id << (4 * (rank - 8));
     words[2 + rank] = (uint64_t)__double_as_longlong(c.p);
@@ -1681,7 +1686,7 @@ __device__ __noinline__ void score_long_rows(const FastExtra* ex, uint32_t ncand
 #endif
 __global__ void __launch_bounds__(128, FASTSCORE_MIN_BLOCKS)
 k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArrays O,
-             const FastMid* __restrict__ mid, const FastExtra* __restrict__ extra, uint32_t* worklist, unsigned int* worklist_n,
+             const FastMid mid, const FastExtra* __restrict__ extra, uint32_t* worklist, unsigned int* worklist_n,
              uint32_t s_begin) {
   __shared__ double s_chain[FAST_MAX_ROUNDS];
   __shared__ int s_nchain;
@@ -1711,19 +1716,19 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
     bool ready = false;
     double m = 0.0;
     uint32_t fl = 0, xslot = 0;
-    uint64_t ph64 = 0;
+    uint32_t cmask = 0;    // candidate phases (bit i: phase i); candidate q is the q-th set bit
     double2 f0 = make_double2(0.0, 0.0);
     if (s < S) {
       // everything that does not depend on the header is requested with it: the prior (P == 1: one
       // double per subject) and the first candidate's frequencies
-      const uint4* src = reinterpret_cast<const uint4*>(mid + s);
+      const uint4* src = reinterpret_cast<const uint4*>(mid.head + s);
       const uint4 h1 = src[0];
       const uint32_t pi = batch_prior(B, s);
-      f0 = *reinterpret_cast<const double2*>(&mid[s].f[0][0]);   // same sector as the header; garbage unless ncand >= 1
+      f0 = *reinterpret_cast<const double2*>(&mid.head[s].f0[0]);   // same sector as the header; garbage unless ncand >= 1
       m = __ldg(B.priors + pi);
       fl = h1.x;
       xslot = h1.y;
-      ph64 = (uint64_t)h1.z | ((uint64_t)h1.w << 32);
+      cmask = h1.z;
       ready = (fl & 3u) == 1u;
     }
     const uint32_t ncand_all = ready ? ((fl >> 2) & 31u) : 0u;
@@ -1751,7 +1756,7 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
       rq[q] = 99;
       acc[q] = false;
       if ((uint32_t)q < ncand) {
-        const double2 v = q == 0 ? f0 : *reinterpret_cast<const double2*>(&mid[s].f[q][0]);
+        const double2 v = q == 0 ? f0 : *reinterpret_cast<const double2*>(&mid.more[s].f[q - 1][0]);
         FastPair pr;
         pr.f = v.x;
         pr.f2 = v.y;
@@ -1854,8 +1859,7 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
     const bool fits = (int64_t)(wb + wtot) <= R.word_capacity;
     for (uint32_t lm = __ballot_sync(0xFFFFFFFFu, long_form && done && np && fits); lm; lm &= lm - 1) {
       const int o = __ffs(lm) - 1;
-      const uint64_t ph = (uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)ph64, o) |
-                          ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(ph64 >> 32), o) << 32);
+      const uint32_t ph = __shfl_sync(0xFFFFFFFFu, cmask, o);
       const uint64_t at = (uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)my, o) |
                           ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(my >> 32), o) << 32);
       score_long_rows(extra + __shfl_sync(0xFFFFFFFFu, xslot, o), __shfl_sync(0xFFFFFFFFu, ncand_all, o), shfl_double(m, o),
@@ -1864,8 +1868,11 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
     }
     if (!done) continue;
     uint32_t phases = 0;
+    uint32_t mm = cmask;
 #pragma unroll
-    for (int q = 0; q < FAST_CMAX; ++q)
+    for (int q = 0; q < FAST_CMAX; ++q) {
+      const uint32_t pid = (uint32_t)(__ffs(mm) - 1) & 15u;   // phase id of candidate q
+      mm &= mm - 1;
       if (acc[q]) {
         // rank by (probability desc, phase asc); candidates are stored in ascending phase order
         uint32_t rank = 0;
@@ -1873,10 +1880,11 @@ k_fast_score(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, Ou
         for (int j = 0; j < FAST_CMAX; ++j)
           if (acc[j] && (prob[j] > prob[q] || (prob[j] == prob[q] && j < q))) ++rank;
         if (rank < np) {
-          phases |= ((uint32_t)(ph64 >> (4 * q)) & 15u) << (4 * rank);
+          phases |= pid << (4 * rank);
           if (nw && fits) R.words[my + rank] = (uint64_t)__double_as_longlong(prob[q]);
         }
       }
+    }
     // the UMUG genotype and the two haplotypes of every PMUG row follow from the subject's own alleles and
     // the phase ids (include/grimb200.h, GRIMB_KIND_SIMPLE): one 16-byte store per subject
     const GrimbCompact c = make_compact(GRIMB_ST_OK, GRIMB_KIND_SIMPLE | (n_acc ? GRIMB_KIND_HAS_RESULTS : 0u) |
@@ -2414,19 +2422,17 @@ struct GrimbEngine {
 
 extern "C" int grimb_engine_free(GrimbEngine* e);
 
-// A probe wants ONE 32-byte sector of a hash region far larger than a cache line's worth of locality.  The L2's
-// default fetch granularity is 64 bytes: every miss pulls the neighbouring sector (another bucket, useless) from
-// DRAM as well -- ncu of k_fast_probe: 32.1 M read requests from the SMs looked up 70.5 M sectors, DRAM read
-// 1.29 GB for 0.65 GB of missing sectors.  cudaLimitMaxL2FetchGranularity = 32 asks for sector-sized fetches
-// (a hint; GRIMB_L2_FETCH=64|128 restores a larger granularity for A/B runs).
+// A probe wants ONE 32-byte sector, but the memory side works in 64-byte units: ncu of k_fast_probe shows 32.1 M
+// read requests from the SMs looked up as 70.5 M sectors at the L2 (+ 30.7 M again on the far die's slices for the
+// half homed there: the "2.9x algorithmic" lts__t_sectors of the round-1 review) and DRAM reading 64 B per missing
+// request.  cudaLimitMaxL2FetchGranularity = 32 is the documented knob; on B200 it changed nothing
+// (0.2507 ms with 32, 0.2508 ms with 64), so it is only applied on request (GRIMB_L2_FETCH=32|64|128).
 static void set_l2_fetch_granularity() {
-  size_t g = 32;
-  if (const char* v = getenv("GRIMB_L2_FETCH")) {
-    const long x = atol(v);
-    if (x == 32 || x == 64 || x == 128) g = (size_t)x;
-    else if (x == 0) return;   // leave the device default
-  }
-  if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g) != cudaSuccess) cudaGetLastError();
+  const char* v = getenv("GRIMB_L2_FETCH");
+  if (!v) return;
+  const long x = atol(v);
+  if (x != 32 && x != 64 && x != 128) return;
+  if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)x) != cudaSuccess) cudaGetLastError();
 }
 
 extern "C" int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes_per_cta, GrimbEngine** out) {
@@ -2652,7 +2658,10 @@ static int launch_warp(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch*
   if (tv.L <= 5 && tv.P == 1) {
     const uint64_t groups = ((uint64_t)n + FAST_WARPS * 2 - 1) / (FAST_WARPS * 2);
     if (e->fast_split) {
-      CK(e->mid.reserve((size_t)batch->n_subjects * sizeof(FastMid) + 16));
+      CK(e->mid.reserve((size_t)batch->n_subjects * (sizeof(FastHead) + sizeof(FastMore)) + 256));
+      FastMid midv;
+      midv.head = (FastHead*)e->mid.p;
+      midv.more = (FastMore*)((char*)e->mid.p + (((size_t)batch->n_subjects * sizeof(FastHead) + 127) & ~(size_t)127));
       double eps = cfg->epsilon;
       int nr = 0;
       while (eps > 0 && nr < FAST_MAX_ROUNDS) {
@@ -2667,17 +2676,17 @@ static int launch_warp(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch*
       unsigned int* ovf_n = (unsigned int*)(e->d_counters + CNT_OVERFLOW);
       if (tm) CK(cudaEventRecord(e->ev[0], st));
       if (batch->packed_keys)
-        k_fast_probe<true><<<(unsigned)fgp, FAST_WARPS * 32, 0, st>>>(tv, rb, O, (FastMid*)e->mid.p, (uint32_t*)e->worklist.p, cnt,
+        k_fast_probe<true><<<(unsigned)fgp, FAST_WARPS * 32, 0, st>>>(tv, rb, O, midv, (uint32_t*)e->worklist.p, cnt,
                                                                     (FastExtra*)e->overflow.p, ovf_n, extra_cap, eps > 0 ? 0 : 1, (uint32_t)s_begin);
       else
-        k_fast_probe<false><<<(unsigned)fgp, FAST_WARPS * 32, 0, st>>>(tv, rb, O, (FastMid*)e->mid.p, (uint32_t*)e->worklist.p, cnt,
+        k_fast_probe<false><<<(unsigned)fgp, FAST_WARPS * 32, 0, st>>>(tv, rb, O, midv, (uint32_t*)e->worklist.p, cnt,
                                                                      (FastExtra*)e->overflow.p, ovf_n, extra_cap, eps > 0 ? 0 : 1, (uint32_t)s_begin);
       CK(cudaGetLastError());
       if (tm) CK(cudaEventRecord(e->ev[1], st));
       uint64_t sg = ((uint64_t)n + 127) / 128;
       if (sg > (uint64_t)e->sm_count * 16) sg = (uint64_t)e->sm_count * 16;
       if (tm) CK(cudaEventRecord(e->ev_score[0], st));
-      k_fast_score<<<(unsigned)sg, 128, 0, st>>>(tv, e->d_cfg, rb, O, (const FastMid*)e->mid.p, (const FastExtra*)e->overflow.p,
+      k_fast_score<<<(unsigned)sg, 128, 0, st>>>(tv, e->d_cfg, rb, O, midv, (const FastExtra*)e->overflow.p,
                                                 (uint32_t*)e->worklist.p, cnt, (uint32_t)s_begin);
       CK(cudaGetLastError());
       if (tm) CK(cudaEventRecord(e->ev_score[1], st));

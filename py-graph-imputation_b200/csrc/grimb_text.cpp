@@ -339,6 +339,7 @@ struct GrimbText {
     GrimbResults fin;
     int64_t totals[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int64_t retries = 0;
+    int fmt_threads = 0;          // pieces per output in fmt_parts (thread order)
     std::vector<OutStr> fmt_parts;   // per-thread pieces of the six outputs (capacity reused)
     std::string out[6];
     int64_t out_size[6] = {0, 0, 0, 0, 0, 0};
@@ -1353,7 +1354,9 @@ int tokenise_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const char* tex
 }
 
 // results of the slot's batch -> the six texts (S.out / S.out_size), plan histogram
-int format_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const GrimbResults* res) {
+// `concat` false (file pipeline): the per-thread pieces stay as they are (S.fmt_parts, thread order) and the writer
+// streams them out one after the other -- one copy of every output byte less
+int format_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const GrimbResults* res, bool concat = true) {
   auto t0 = clk::now();
   const size_t NS = S.lines.size();
   const int nt = t->n_threads;
@@ -1439,16 +1442,18 @@ int format_slot(GrimbText* t, Slot& S, const GrimbConfig* cfg, const GrimbResult
       offs[(size_t)th * 6 + k] = n;
       n += parts[(size_t)th * 6 + k].size();
     }
-    if (S.out[k].size() < n) S.out[k].resize(n);   // grow-only buffer; out_size[k] carries the valid length
+    if (concat && S.out[k].size() < n) S.out[k].resize(n);   // grow-only buffer; out_size[k] carries the valid length
     S.out_size[k] = (int64_t)n;
   }
-  t->parallel((size_t)nt, [&](int, size_t lo, size_t hi) {
-    for (size_t th = lo; th < hi; ++th)
-      for (int k = 0; k < 6; ++k) {
-        const OutStr& ps = parts[th * 6 + k];
-        if (!ps.empty()) memcpy(&S.out[k][offs[th * 6 + k]], ps.data(), ps.size());
-      }
-  });
+  S.fmt_threads = nt;
+  if (concat)
+    t->parallel((size_t)nt, [&](int, size_t lo, size_t hi) {
+      for (size_t th = lo; th < hi; ++th)
+        for (int k = 0; k < 6; ++k) {
+          const OutStr& ps = parts[th * 6 + k];
+          if (!ps.empty()) memcpy(&S.out[k][offs[th * 6 + k]], ps.data(), ps.size());
+        }
+    });
   for (int k = 0; k < 4; ++k) S.plan_count[k] = 0;
   for (int th = 0; th < nt; ++th)
     for (int k = 0; k < 4; ++k) S.plan_count[k] += plans[(size_t)th * 4 + k];
@@ -1902,7 +1907,7 @@ extern "C" int grimb_impute_file(GrimbText* t, GrimbEngine* const* engines, int3
       if (k < 0) break;
       Slot& S = *t->pipe[(size_t)k];
       if (!failed()) {
-        int rc = format_slot(t, S, cfg, &S.fin);
+        int rc = format_slot(t, S, cfg, &S.fin, false);
         if (rc) set_err(rc);
         s_fmt += S.sec_fmt;
       }
@@ -1923,8 +1928,12 @@ extern "C" int grimb_impute_file(GrimbText* t, GrimbEngine* const* engines, int3
         for (int o = 0; o < 6; ++o) {
           if (S.out_size[o] == 0) continue;
           ws.emplace_back([&, o]() {
-            if (ofd[o] >= 0) ok[o] = write_all(ofd[o], S.out[o].data(), (size_t)S.out_size[o]);
-            else t->file_acc[o].append(S.out[o].data(), (size_t)S.out_size[o]);
+            for (int th = 0; th < S.fmt_threads && ok[o]; ++th) {   // the formatter's pieces, in thread order
+              const OutStr& ps = S.fmt_parts[(size_t)th * 6 + o];
+              if (ps.empty()) continue;
+              if (ofd[o] >= 0) ok[o] = write_all(ofd[o], ps.data(), ps.size());
+              else t->file_acc[o].append(ps.data(), ps.size());
+            }
           });
         }
         for (auto& x : ws) x.join();
