@@ -178,7 +178,24 @@ def _run_impute_sharded(dist, config, hap_pop_pair, graph):
     size = os.path.getsize(in_path)
     lib = graph.lib
     import ctypes as C
+    import threading
     from .imputation import _lib
+    # outputs of an earlier run: moved aside now and deleted in the background while the subjects are imputed
+    # (truncating gigabytes in place frees their page-cache pages synchronously, on the critical path)
+    cleaner = None
+    if rank == 0:
+        old = []
+        for ck in targets.values():
+            try:
+                if os.path.isfile(config[ck]) and os.path.getsize(config[ck]) > (1 << 20):
+                    aside = "%s.old.%d" % (config[ck], os.getpid())
+                    os.rename(config[ck], aside)
+                    old.append(aside)
+            except OSError:
+                pass
+        if old:
+            cleaner = threading.Thread(target=lambda: [os.unlink(f) for f in old])
+            cleaner.start()
     # every rank takes the lines that START in its byte range of the input (memory-mapped by the library: no
     # rank reads the whole file); the ranks count their own lines and exchange the counts, because .miss /
     # .problem rows carry global line indices
@@ -210,7 +227,6 @@ def _run_impute_sharded(dist, config, hap_pop_pair, graph):
             with open(config[ck], "wb") as f:
                 f.truncate(sum(sz[k] for sz in sizes))
     dist.barrier()
-    import threading
     errs = []
 
     def put(k, ck):
@@ -225,6 +241,8 @@ def _run_impute_sharded(dist, config, hap_pop_pair, graph):
         th.start()
     for th in ths:
         th.join()
+    if cleaner is not None:
+        cleaner.join()
     if errs:
         raise RuntimeError("writing the output files failed: %s" % errs)
     dist.barrier()
