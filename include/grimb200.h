@@ -387,6 +387,18 @@ int grimb_file_count_lines(const char* path, int64_t byte_lo, int64_t byte_hi, i
                            int64_t* n_lines, int64_t* lo_adj, int64_t* hi_adj);
 int grimb_file_write_at(const char* path, int64_t offset, const void* data, int64_t size);
 
+/* One input file shared by the ranks of a host (one process per GPU).  The ranks take the input's chunks
+ * round-robin (chunk c -> rank c % world) and stream their rows straight into the SAME six final files: a board
+ * in a small memory-mapped file carries every chunk's line count (for the global line indices of the .miss /
+ * .problem rows) and the sizes of its six output pieces (for the file offsets), so nothing is accumulated in
+ * memory, gathered between the ranks or written after the computation.  Rank 0 creates the six output files
+ * (empty) and the board file (grimb_file_board_bytes() zero bytes) before any rank calls; all ranks pass the same
+ * chunk_bytes.  A rank that fails marks the board and the others return an error instead of waiting. */
+int64_t grimb_file_board_bytes(int64_t file_bytes, int64_t chunk_bytes);
+int grimb_impute_file_sharded(GrimbText* t, GrimbEngine* const* engines, int32_t n_engines, const GrimbConfig* cfg,
+                              const char* in_path, const char* const* out_paths, int64_t chunk_bytes, int32_t rank,
+                              int32_t world, const char* board_path, GrimbFileStats* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -339,6 +339,7 @@ struct GrimbText {
     GrimbResults fin;
     int64_t totals[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int64_t retries = 0;
+    int64_t chunk_id = 0;         // grimb_impute_file_sharded: index of the input chunk
     int fmt_threads = 0;          // pieces per output in fmt_parts (thread order)
     std::vector<OutStr> fmt_parts;   // per-thread pieces of the six outputs (capacity reused)
     std::string out[6];
@@ -1718,6 +1719,55 @@ size_t line_start_at(const char* p, size_t n, size_t pos) {
   return q ? (size_t)((const char*)q - p) + 1 : n;
 }
 
+// ---- sharing one input file between the ranks of a host (grimb_impute_file_sharded) ------------------------
+// The ranks take the input's chunks round-robin (chunk c -> rank c % world) and meet on a small board in a
+// memory-mapped file: per chunk its line count (published after tokenising: the formatter of a later chunk needs
+// the global index of its first line for the .miss / .problem rows) and the sizes of its six output pieces
+// (published after formatting: the writer of a later chunk needs its file offsets).  Every rank streams its
+// pieces straight into the final files with pwrite -- nothing is accumulated, gathered or written afterwards.
+struct Board {
+  int64_t* p = nullptr;
+  size_t bytes = 0;
+  int64_t n_chunks = 0;
+  int rank = 0, world = 1;
+  static constexpr int64_t MAGIC = 0x4752494d42424f41ll;
+  enum { HDR = 8, ENT = 16, F_LINES_READY = 0, F_LINES = 1, F_SIZES_READY = 2, F_SIZE0 = 3 };
+  int64_t* ent(int64_t c) const { return p + HDR + ENT * c; }
+  void fail() const { __atomic_store_n(p + 2, (int64_t)1, __ATOMIC_RELEASE); }
+  bool failed() const { return __atomic_load_n(p + 2, __ATOMIC_ACQUIRE) != 0; }
+  void publish(int64_t c, int ready_field) const { __atomic_store_n(ent(c) + ready_field, (int64_t)1, __ATOMIC_RELEASE); }
+  // waits until chunk c has published `ready_field`; false: another rank failed, or nothing happened for 10 minutes
+  bool wait(int64_t c, int ready_field) const {
+    auto t0 = clk::now();
+    for (unsigned spin = 0;; ++spin) {
+      if (__atomic_load_n(ent(c) + ready_field, __ATOMIC_ACQUIRE) != 0) return true;
+      if (failed()) return false;
+      if (spin > 200) {
+        std::this_thread::sleep_for(std::chrono::microseconds(50));
+        if ((spin & 1023) == 0 && secs(t0, clk::now()) > 600.0) return false;
+      }
+    }
+  }
+};
+
+bool pwrite_all(int fd, const char* p, size_t n, int64_t off) {
+  while (n) {
+    ssize_t w = pwrite(fd, p, n, (off_t)off);
+    if (w < 0) {
+      if (errno == EINTR) continue;
+      return false;
+    }
+    p += w;
+    n -= (size_t)w;
+    off += w;
+  }
+  return true;
+}
+
+int impute_file_impl(GrimbText* t, GrimbEngine* const* engines, int32_t n_engines, const GrimbConfig* cfg, const char* in_path,
+                     int64_t byte_lo, int64_t byte_hi, int64_t first_line_index, const char* const* out_paths, int64_t chunk_bytes,
+                     GrimbTextOut* out, GrimbFileStats* stats, const Board* board);
+
 }  // namespace
 
 extern "C" int grimb_file_count_lines(const char* path, int64_t byte_lo, int64_t byte_hi, int32_t n_threads,
@@ -1793,6 +1843,48 @@ extern "C" int grimb_file_write_at(const char* path, int64_t offset, const void*
 extern "C" int grimb_impute_file(GrimbText* t, GrimbEngine* const* engines, int32_t n_engines, const GrimbConfig* cfg,
                                  const char* in_path, int64_t byte_lo, int64_t byte_hi, int64_t first_line_index,
                                  const char* const* out_paths, int64_t chunk_bytes, GrimbTextOut* out, GrimbFileStats* stats) {
+  return impute_file_impl(t, engines, n_engines, cfg, in_path, byte_lo, byte_hi, first_line_index, out_paths, chunk_bytes, out,
+                          stats, nullptr);
+}
+
+// Size of the board file for an input of `file_bytes` cut into chunks of `chunk_bytes`; rank 0 creates the file
+// zero-filled before the ranks call grimb_impute_file_sharded.
+extern "C" int64_t grimb_file_board_bytes(int64_t file_bytes, int64_t chunk_bytes) {
+  if (chunk_bytes <= 0) chunk_bytes = 16 << 20;
+  const int64_t n = (file_bytes + chunk_bytes - 1) / chunk_bytes;
+  return (int64_t)sizeof(int64_t) * (Board::HDR + Board::ENT * (n > 0 ? n : 1));
+}
+
+extern "C" int grimb_impute_file_sharded(GrimbText* t, GrimbEngine* const* engines, int32_t n_engines, const GrimbConfig* cfg,
+                                         const char* in_path, const char* const* out_paths, int64_t chunk_bytes, int32_t rank,
+                                         int32_t world, const char* board_path, GrimbFileStats* stats) {
+  if (!board_path || !out_paths || rank < 0 || world < 1 || rank >= world || !stats) return tfail(GRIMB_E_ARG, "bad shard arguments");
+  if (chunk_bytes <= 0) chunk_bytes = 16 << 20;
+  int fd = open(board_path, O_RDWR);
+  if (fd < 0) return tfail(GRIMB_E_ARG, std::string("cannot open the board ") + board_path);
+  struct stat st;
+  if (fstat(fd, &st) != 0 || (size_t)st.st_size < sizeof(int64_t) * (Board::HDR + Board::ENT)) {
+    close(fd);
+    return tfail(GRIMB_E_ARG, "board file too small");
+  }
+  Board b;
+  b.bytes = (size_t)st.st_size;
+  b.p = (int64_t*)mmap(nullptr, b.bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (b.p == MAP_FAILED) return tfail(GRIMB_E_NOMEM, "mmap of the board failed");
+  b.rank = rank;
+  b.world = world;
+  GrimbTextOut out;
+  int rc = impute_file_impl(t, engines, n_engines, cfg, in_path, 0, -1, 0, out_paths, chunk_bytes, &out, stats, &b);
+  if (rc != GRIMB_OK) b.fail();
+  munmap(b.p, b.bytes);
+  return rc;
+}
+
+namespace {
+int impute_file_impl(GrimbText* t, GrimbEngine* const* engines, int32_t n_engines, const GrimbConfig* cfg, const char* in_path,
+                     int64_t byte_lo, int64_t byte_hi, int64_t first_line_index, const char* const* out_paths, int64_t chunk_bytes,
+                     GrimbTextOut* out, GrimbFileStats* stats, const Board* board) {
   if (!t || !engines || n_engines < 1 || !cfg || !in_path || !out || !stats) return tfail(GRIMB_E_ARG, "null argument");
   auto t_begin = clk::now();
   memset(stats, 0, sizeof(*stats));
@@ -1825,6 +1917,16 @@ extern "C" int grimb_impute_file(GrimbText* t, GrimbEngine* const* engines, int3
   for (int k = 0; k < 6; ++k) {
     ofd[k] = -1;
     t->file_acc[k].clear();
+    if (board && out_paths && out_paths[k]) {
+      ofd[k] = open(out_paths[k], O_WRONLY);
+      if (ofd[k] < 0) {
+        for (int j = 0; j < k; ++j)
+          if (ofd[j] >= 0) close(ofd[j]);
+        if (fsize) munmap((void*)base, fsize);
+        return tfail(GRIMB_E_ARG, std::string("cannot open ") + out_paths[k]);
+      }
+      continue;
+    }
     if (out_paths && out_paths[k]) {
       struct stat ost;
       if (stat(out_paths[k], &ost) == 0 && S_ISREG(ost.st_mode) && ost.st_size > (1 << 20) && ost.st_nlink == 1) {
@@ -1856,6 +1958,7 @@ extern "C" int grimb_impute_file(GrimbText* t, GrimbEngine* const* engines, int3
       err_rc = rc;
       err_msg = grimb_last_error();   // the failing thread's message
     }
+    if (board) board->fail();         // the other ranks stop waiting for this one's chunks
   };
   auto failed = [&]() {
     std::lock_guard<std::mutex> g(err_m);
@@ -1865,7 +1968,43 @@ extern "C" int grimb_impute_file(GrimbText* t, GrimbEngine* const* engines, int3
   std::thread th_old([&]() {
     for (const std::string& f : old_files) unlink(f.c_str());
   });
+  const int64_t n_chunks = board ? (int64_t)((fsize + (size_t)chunk_bytes - 1) / (size_t)chunk_bytes) : 0;
+  if (board && (int64_t)(board->bytes / sizeof(int64_t)) < Board::HDR + Board::ENT * (n_chunks > 0 ? n_chunks : 1)) {
+    for (int k = 0; k < 6; ++k)
+      if (ofd[k] >= 0) close(ofd[k]);
+    if (fsize) munmap((void*)base, fsize);
+    return tfail(GRIMB_E_ARG, "board file too small for this input / chunk size");
+  }
   std::thread th_tok([&]() {
+    if (board) {
+      // chunk c = bytes [c * chunk_bytes, (c + 1) * chunk_bytes), both ends moved to the next line start
+      for (int64_t c = board->rank; c < n_chunks && !failed() && !board->failed(); c += board->world) {
+        const size_t pos = line_start_at(base, fsize, (size_t)c * (size_t)chunk_bytes);
+        const size_t e = c + 1 >= n_chunks ? fsize : line_start_at(base, fsize, (size_t)(c + 1) * (size_t)chunk_bytes);
+        if (e <= pos) {   // a line longer than a chunk: nothing starts here
+          int64_t* en = board->ent(c);
+          for (int q = 0; q < Board::ENT; ++q) en[q] = 0;
+          board->publish(c, Board::F_LINES_READY);
+          board->publish(c, Board::F_SIZES_READY);
+          continue;
+        }
+        const int k = free_q.pop();
+        Slot& S = *t->pipe[(size_t)k];
+        int rc = tokenise_slot(t, S, cfg, base + pos, (int64_t)(e - pos), 0, true);
+        if (rc) {
+          set_err(rc);
+          free_q.push(k);
+          break;
+        }
+        S.chunk_id = c;
+        board->ent(c)[Board::F_LINES] = (int64_t)S.lines.size();
+        board->publish(c, Board::F_LINES_READY);
+        s_tok += S.sec_tok;
+        to_gpu.push(k);
+      }
+      to_gpu.push(-1);
+      return;
+    }
     size_t pos = lo;
     int64_t first = first_line_index;
     while (pos < hi && !failed()) {
@@ -1902,24 +2041,55 @@ extern "C" int grimb_impute_file(GrimbText* t, GrimbEngine* const* engines, int3
     to_fmt.push(-1);
   });
   std::thread th_fmt([&]() {
+    int64_t line_cursor = 0, next_c = 0;   // board: lines of the chunks [0, next_c)
     for (;;) {
       const int k = to_fmt.pop();
       if (k < 0) break;
       Slot& S = *t->pipe[(size_t)k];
       if (!failed()) {
-        int rc = format_slot(t, S, cfg, &S.fin, false);
-        if (rc) set_err(rc);
-        s_fmt += S.sec_fmt;
+        if (board) {
+          for (; next_c < S.chunk_id && !failed(); ++next_c) {
+            if (!board->wait(next_c, Board::F_LINES_READY)) {
+              tfail(GRIMB_E_ARG, "another rank failed (or stalled) before publishing its line counts");
+              set_err(GRIMB_E_ARG);
+              break;
+            }
+            line_cursor += board->ent(next_c)[Board::F_LINES];
+          }
+          S.first_index = line_cursor;
+          line_cursor += (int64_t)S.lines.size();
+          next_c = S.chunk_id + 1;
+        }
+        if (!failed()) {
+          int rc = format_slot(t, S, cfg, &S.fin, false);
+          if (rc) set_err(rc);
+          s_fmt += S.sec_fmt;
+        }
+        if (board && !failed()) {
+          for (int o = 0; o < 6; ++o) board->ent(S.chunk_id)[Board::F_SIZE0 + o] = S.out_size[o];
+          board->publish(S.chunk_id, Board::F_SIZES_READY);
+        }
       }
       to_write.push(k);
     }
     to_write.push(-1);
   });
   std::thread th_wr([&]() {
+    int64_t off_cursor[6] = {0, 0, 0, 0, 0, 0}, next_c = 0;   // board: output bytes of the chunks [0, next_c)
     for (;;) {
       const int k = to_write.pop();
       if (k < 0) break;
       Slot& S = *t->pipe[(size_t)k];
+      if (board && !failed()) {
+        for (; next_c < S.chunk_id && !failed(); ++next_c) {
+          if (!board->wait(next_c, Board::F_SIZES_READY)) {
+            tfail(GRIMB_E_ARG, "another rank failed (or stalled) before publishing its output sizes");
+            set_err(GRIMB_E_ARG);
+            break;
+          }
+          for (int o = 0; o < 6; ++o) off_cursor[o] += board->ent(next_c)[Board::F_SIZE0 + o];
+        }
+      }
       if (!failed()) {
         auto w0 = clk::now();
         // the six outputs of the chunk in parallel: streamed to their files, or appended in memory
@@ -1928,11 +2098,14 @@ extern "C" int grimb_impute_file(GrimbText* t, GrimbEngine* const* engines, int3
         for (int o = 0; o < 6; ++o) {
           if (S.out_size[o] == 0) continue;
           ws.emplace_back([&, o]() {
+            int64_t at = off_cursor[o];
             for (int th = 0; th < S.fmt_threads && ok[o]; ++th) {   // the formatter's pieces, in thread order
               const OutStr& ps = S.fmt_parts[(size_t)th * 6 + o];
               if (ps.empty()) continue;
-              if (ofd[o] >= 0) ok[o] = write_all(ofd[o], ps.data(), ps.size());
+              if (board && ofd[o] >= 0) ok[o] = pwrite_all(ofd[o], ps.data(), ps.size(), at);
+              else if (ofd[o] >= 0) ok[o] = write_all(ofd[o], ps.data(), ps.size());
               else t->file_acc[o].append(ps.data(), ps.size());
+              at += (int64_t)ps.size();
             }
           });
         }
@@ -1949,6 +2122,10 @@ extern "C" int grimb_impute_file(GrimbText* t, GrimbEngine* const* engines, int3
         for (int o = 0; o < 6; ++o) stats->out_bytes[o] += S.out_size[o];
         stats->n_chunks += 1;
         s_wr += secs(w0, clk::now());
+        if (board) {
+          for (int o = 0; o < 6; ++o) off_cursor[o] += S.out_size[o];
+          next_c = S.chunk_id + 1;
+        }
       }
       free_q.push(k);
     }
@@ -1981,3 +2158,4 @@ extern "C" int grimb_impute_file(GrimbText* t, GrimbEngine* const* engines, int3
             (long long)stats->n_lines, (long long)stats->n_chunks, stats->seconds_total, s_tok, s_gpu, s_fmt, s_wr);
   return GRIMB_OK;
 }
+}  // namespace

@@ -220,6 +220,11 @@ def load(kw=1):
     lib.grimb_file_count_lines.argtypes = [C.c_char_p, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_int64),
                                            C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.grimb_file_write_at.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_int64]
+    lib.grimb_file_board_bytes.argtypes = [C.c_int64, C.c_int64]
+    lib.grimb_file_board_bytes.restype = C.c_int64
+    lib.grimb_impute_file_sharded.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.POINTER(Config), C.c_char_p,
+                                              C.POINTER(C.c_char_p), C.c_int64, C.c_int32, C.c_int32, C.c_char_p,
+                                              C.POINTER(FileStats)]
     if lib.grimb_abi_version() != 5:
         raise RuntimeError("libgrimb200.so ABI mismatch")
     _LIB[kw] = lib
@@ -240,5 +245,6 @@ EXPORTED = [
     "grimb_tables_image_copy", "grimb_tables_from_image", "grimb_engine_create", "grimb_engine_free", "grimb_engine_launches", "grimb_engine_kernel_ms",
     "grimb_impute_device", "grimb_impute_device_async", "grimb_impute_finish", "grimb_impute_host",
     "grimb_text_create", "grimb_text_free", "grimb_text_tokenise", "grimb_text_format", "grimb_impute_text",
-    "grimb_impute_file", "grimb_file_count_lines", "grimb_file_write_at",
+    "grimb_impute_file", "grimb_file_count_lines", "grimb_file_write_at", "grimb_file_board_bytes",
+    "grimb_impute_file_sharded",
 ]

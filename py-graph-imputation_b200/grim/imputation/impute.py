@@ -795,6 +795,29 @@ class Imputation(object):
             self.stats[k] = self.stats.get(k, 0.0) + v
         return {k: C.string_at(out.data[i], out.size[i]) for i, k in enumerate(_lib.OUT_KEYS)}
 
+    def impute_file_sharded(self, in_path, out_paths, chunk_bytes, rank, world, board_path, n_tiers=1):
+        """This rank's share of one input file (chunks rank, rank + world, ...), streamed into the shared final files
+        at the offsets the ranks agree on through the board file (include/grimb200.h: grimb_impute_file_sharded).
+        n_tiers: workspace tiers to offer (a subject that overflows the last one fails the call with
+        GRIMB_E_NOMEM; the caller restarts all ranks with one more tier)."""
+        lib = self.netGraph.lib
+        t = self._text_handle()
+        n_eng = max(1, min(n_tiers, len(self.workspaces)))
+        engines = (C.c_void_p * len(self.workspaces))(*[self.netGraph.engine(w) for w in self.workspaces[:n_eng]])
+        paths = (C.c_char_p * 6)(*[(out_paths[k].encode("utf8") if k in out_paths else None) for k in _lib.OUT_KEYS])
+        st = _lib.FileStats()
+        self.cfg.hap_pop_pair = 0
+        self.cfg.em = 0
+        rc = lib.grimb_impute_file_sharded(t, engines, n_eng, C.byref(self.cfg), in_path.encode("utf8"), paths, chunk_bytes,
+                                           rank, world, board_path.encode("utf8"), C.byref(st))
+        _lib.check(rc, "grimb_impute_file_sharded", lib)
+        self.stats["subjects"] += st.n_lines
+        self.stats["pair_evals"] += st.pair_evals
+        self.stats["workspace_retries"] += st.workspace_retries
+        for k in range(4):
+            self.stats["plan"][k] += st.plan_count[k]
+        return st
+
     def impute_file_native(self, in_path, out_paths=None, byte_lo=0, byte_hi=-1, first_index=0, chunk_bytes=0):
         """The whole file (or the lines starting in [byte_lo, byte_hi)) through grimb_impute_file: memory-mapped
         input, tokenise | GPU | format | write overlapped on host threads.  out_paths: dict key -> path of the

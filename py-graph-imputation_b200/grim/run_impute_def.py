@@ -196,6 +196,43 @@ def _run_impute_sharded(dist, config, hap_pop_pair, graph):
         if old:
             cleaner = threading.Thread(target=lambda: [os.unlink(f) for f in old])
             cleaner.start()
+    if not (hap_pop_pair or imputation.phase_masks is not None) and os.environ.get("GRIMB_SHARD_BOARD", "1") != "0":
+        # default mode: the ranks take the input's chunks round-robin and stream their rows straight into the six
+        # final files (grimb_impute_file_sharded: line counts and piece sizes meet on a small memory-mapped board)
+        chunk = int(os.environ.get("GRIMB_FILE_CHUNK", "0")) or (16 << 20)
+        board = os.path.join(config["imputation_out_path"], ".grimb_board.%s" % os.environ.get("MASTER_PORT", "0"))
+        n_tiers = 1
+        while True:
+            if rank == 0:
+                pathlib.Path(config["imputation_out_path"]).mkdir(parents=False, exist_ok=True)
+                for ck in targets.values():
+                    open(config[ck], "wb").close()
+                with open(board, "wb") as f:
+                    f.truncate(int(lib.grimb_file_board_bytes(size, chunk)))
+            dist.barrier()
+            err = None
+            try:
+                imputation.impute_file_sharded(in_path, {k: config[ck] for k, ck in targets.items()}, chunk, rank, world,
+                                               board, n_tiers)
+            except (RuntimeError, NotImplementedError) as e:      # every rank must reach the exchange below
+                err = (type(e).__name__, str(e))
+            errs = [None] * world
+            dist.all_gather_object(errs, err)
+            if rank == 0:
+                os.unlink(board)
+            if all(e is None for e in errs):
+                break
+            # a subject overflowed the last workspace tier on some rank: all ranks start over with one more
+            if any(e is not None and "(-3)" in e[1] for e in errs) and n_tiers < len(imputation.workspaces):
+                n_tiers += 1
+                continue
+            first = next(e for e in errs if e is not None)
+            if cleaner is not None:
+                cleaner.join()
+            raise (NotImplementedError if first[0] == "NotImplementedError" else RuntimeError)(first[1])
+        if cleaner is not None:
+            cleaner.join()
+        return graph
     # every rank takes the lines that START in its byte range of the input (memory-mapped by the library: no
     # rank reads the whole file); the ranks count their own lines and exchange the counts, because .miss /
     # .problem rows carry global line indices

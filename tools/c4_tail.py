@@ -30,6 +30,12 @@ def run(ls):
     return time.time() - t, out
 
 
+if os.environ.get("C4_ONLY"):       # one subject, for an ncu capture of its launch
+    i = int(os.environ["C4_ONLY"])
+    for _ in range(2):
+        dt, _o = run(lines[i:i + 1])
+        print("subject #%d alone: %.2f ms" % (i, dt * 1e3))
+    sys.exit(0)
 run(lines[:8])
 for m in (n, n // 2, n // 4, n // 8, n // 16):
     dt, _ = run(lines[:m])
