@@ -685,7 +685,10 @@ def main():
             "config": workload_config(args),
             "pair_evals_per_sec": evals * world / (ms_dev * 1e-3),
             "e2e": {"value": total / (ms_host * 1e-3), "unit": "subjects/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_host, "link": link},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_host, "link": link,
+                    # what the host's memory system / PCIe complex moves for the whole job (all ranks, both
+                    # directions): the limiter of e2e scaling on one host (SCALE: 8 ranks share it)
+                    "host_gbs_aggregate": (h2d + d2h) * world / (ms_host * 1e-3) / 1e9},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback",

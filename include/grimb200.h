@@ -84,6 +84,10 @@ typedef struct {
 
 int grimb_abi_version(void);
 const char* grimb_last_error(void);
+/* sizeof of an ABI struct as the library was compiled, for bindings to check their mirror of it: 0 GrimbConfig,
+ * 1 GrimbTableDesc, 2 GrimbTextDesc, 3 GrimbBatch, 4 GrimbResults, 5 GrimbTextOut, 6 GrimbFileStats,
+ * 7 GrimbTableInfo; -1 otherwise. */
+int64_t grimb_struct_size(int32_t which);
 
 int grimb_tables_build(const GrimbTableDesc* desc, GrimbTables** out);
 int grimb_tables_free(GrimbTables* t);

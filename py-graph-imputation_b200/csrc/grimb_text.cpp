@@ -1138,6 +1138,23 @@ extern "C" int grimb_text_create(const GrimbTextDesc* d, GrimbText** out) {
   return GRIMB_OK;
 }
 
+// sizeof of the ABI structs as this library was compiled (bindings check their own layouts against it):
+// 0 GrimbConfig, 1 GrimbTableDesc, 2 GrimbTextDesc, 3 GrimbBatch, 4 GrimbResults, 5 GrimbTextOut, 6 GrimbFileStats,
+// 7 GrimbTableInfo
+extern "C" int64_t grimb_struct_size(int32_t which) {
+  switch (which) {
+    case 0: return (int64_t)sizeof(GrimbConfig);
+    case 1: return (int64_t)sizeof(GrimbTableDesc);
+    case 2: return (int64_t)sizeof(GrimbTextDesc);
+    case 3: return (int64_t)sizeof(GrimbBatch);
+    case 4: return (int64_t)sizeof(GrimbResults);
+    case 5: return (int64_t)sizeof(GrimbTextOut);
+    case 6: return (int64_t)sizeof(GrimbFileStats);
+    case 7: return (int64_t)sizeof(GrimbTableInfo);
+    default: return -1;
+  }
+}
+
 extern "C" int grimb_text_free(GrimbText* t) {
   delete t;
   return GRIMB_OK;

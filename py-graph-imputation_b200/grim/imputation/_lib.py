@@ -227,6 +227,12 @@ def load(kw=1):
                                               C.POINTER(FileStats)]
     if lib.grimb_abi_version() != 5:
         raise RuntimeError("libgrimb200.so ABI mismatch")
+    lib.grimb_struct_size.argtypes = [C.c_int32]
+    lib.grimb_struct_size.restype = C.c_int64
+    for which, ct in enumerate((Config, TableDesc, TextDesc, Batch, Results, TextOut, FileStats, TableInfo)):
+        if lib.grimb_struct_size(which) != C.sizeof(ct):
+            raise RuntimeError("libgrimb200.so: layout of %s differs from the binding (%d vs %d bytes)"
+                               % (ct.__name__, lib.grimb_struct_size(which), C.sizeof(ct)))
     _LIB[kw] = lib
     return lib
 
@@ -240,7 +246,7 @@ def check(rc, what, lib=None):
 
 
 EXPORTED = [
-    "grimb_abi_version", "grimb_last_error", "grimb_tables_build", "grimb_tables_free",
+    "grimb_abi_version", "grimb_last_error", "grimb_struct_size", "grimb_tables_build", "grimb_tables_free",
     "grimb_tables_info", "grimb_tables_build_launches", "grimb_tables_build_ms", "grimb_tables_export", "grimb_tables_image_size", "grimb_tables_image_ptr",
     "grimb_tables_image_copy", "grimb_tables_from_image", "grimb_engine_create", "grimb_engine_free", "grimb_engine_launches", "grimb_engine_kernel_ms",
     "grimb_impute_device", "grimb_impute_device_async", "grimb_impute_finish", "grimb_impute_host",

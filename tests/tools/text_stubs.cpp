@@ -22,3 +22,4 @@ STUB(grimb_tables_build) STUB(grimb_tables_free) STUB(grimb_tables_info) STUB(gr
 STUB(grimb_tables_image_size) STUB(grimb_tables_image_ptr) STUB(grimb_tables_image_copy) STUB(grimb_tables_from_image)
 STUB(grimb_engine_create) STUB(grimb_engine_free) STUB(grimb_engine_launches) STUB(grimb_engine_kernel_ms)
 STUB(grimb_impute_device) STUB(grimb_impute_device_async) STUB(grimb_impute_finish)
+STUB(grimb_tables_build_launches) STUB(grimb_tables_build_ms)
