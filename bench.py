@@ -632,8 +632,8 @@ def main():
         achieved = algo / (ms_kernel * 1e-3) / 1e9
         traffic = None   # DRAM bytes per launch from the committed ncu --set full capture of this kernel
         try:
-            txt = open(os.path.join(ROOT, "profiles", "r01_ncu_summary_k_fast_probe_final.txt" if split
-                                    else "r01_ncu_summary_k_impute_fast_final.txt")).read().splitlines()
+            name = "r02_ncu_summary_k_fast_probe_final.txt" if split else "r01_ncu_summary_k_impute_fast_final.txt"
+            txt = open(os.path.join(ROOT, "profiles", name)).read().splitlines()
             rd = [l for l in txt if l.startswith("dram__bytes_read.sum")][0].split()
             wr = [l for l in txt if l.startswith("dram__bytes_write.sum")][0].split()
             unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}

@@ -12,6 +12,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -352,6 +354,63 @@ struct GrimbText {
   std::string file_acc[6];                   // outputs of grimb_impute_file that are kept in memory
   double per_subject[4] = {0.5, 0.05, 0.3, 0.3};   // words, general records, hap rows, pop rows (adaptive capacities)
 
+  // Worker threads of one calling thread (the tokeniser, the formatter and the GPU stage of the file pipeline
+  // each call parallel() from their own thread, concurrently): created on first use, parked on a condition
+  // variable between regions -- a region costs a wake-up instead of n thread creations and joins.
+  struct Pool {
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv_go, cv_done;
+    const std::function<void(int)>* job = nullptr;
+    uint64_t gen = 0;
+    int active = 0, pending = 0;
+    bool stop = false;
+    void worker(int t) {
+      uint64_t seen = 0;
+      for (;;) {
+        const std::function<void(int)>* j = nullptr;
+        {
+          std::unique_lock<std::mutex> g(m);
+          cv_go.wait(g, [&] { return stop || gen != seen; });
+          if (stop) return;
+          seen = gen;
+          if (t < active) j = job;
+        }
+        if (j) {
+          (*j)(t);
+          std::lock_guard<std::mutex> g(m);
+          if (--pending == 0) cv_done.notify_one();
+        }
+      }
+    }
+    void run(int nt, const std::function<void(int)>& f) {
+      while ((int)th.size() < nt - 1) {
+        const int t = (int)th.size() + 1;   // the calling thread is worker 0
+        th.emplace_back([this, t]() { worker(t); });
+      }
+      {
+        std::lock_guard<std::mutex> g(m);
+        job = &f;
+        active = nt;
+        pending = nt - 1;
+        ++gen;
+      }
+      cv_go.notify_all();
+      f(0);
+      std::unique_lock<std::mutex> g(m);
+      cv_done.wait(g, [&] { return pending == 0; });
+      job = nullptr;
+    }
+    ~Pool() {
+      {
+        std::lock_guard<std::mutex> g(m);
+        stop = true;
+      }
+      cv_go.notify_all();
+      for (auto& x : th) x.join();
+    }
+  };
+
   template <class F>
   void parallel(size_t n, F f) const {
     int nt = n_threads;
@@ -360,13 +419,16 @@ struct GrimbText {
       f(0, (size_t)0, n);
       return;
     }
-    std::vector<std::thread> th;
-    size_t per = (n + nt - 1) / nt;
-    for (int t = 0; t < nt; ++t) {
-      size_t lo = std::min(n, per * t), hi = std::min(n, per * (t + 1));
-      th.emplace_back([=]() { f(t, lo, hi); });
-    }
-    for (auto& x : th) x.join();
+    const size_t per = (n + nt - 1) / nt;
+    const std::function<void(int)> body = [&](int t) {
+      const size_t lo = std::min(n, per * (size_t)t), hi = std::min(n, per * (size_t)(t + 1));
+      f(t, lo, hi);
+    };
+    tls_pool().run(nt, body);
+  }
+  static Pool& tls_pool() {   // one pool per calling thread, whatever the region (not one per template instance)
+    static thread_local Pool pool;
+    return pool;
   }
 
   // calc_priority_matrix (reference impute.py:1844-1924), same operation order
