@@ -990,7 +990,7 @@ k_impute(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArr
   Subject S;
   init_subject(S, sh, T, cfg, ones, arena, arena_per_cta);
   const PreView pvl = pv;   // a local copy: the subject keeps a pointer to it
-  if (mode == 1) {          // cooperative slot pass over the heaviest subjects (`work` = its ticket counter)
+  if ((mode & 3) == 1) {    // cooperative slot pass over the heaviest subjects (`work` = its ticket counter)
     impute_slots(S, sh, T, cfg, B, O, work, buckets, bucket_n, pvl);
     return;
   }
@@ -999,12 +999,16 @@ k_impute(TablesView T, const GrimbConfig* __restrict__ cfg, GrimbBatch B, OutArr
   bound[0] = 0;
   for (int k = 0; k < GRIMB_BUCKETS; ++k) bound[k + 1] = bound[k] + bucket_n[k];
   if (bound[GRIMB_BUCKETS] == 0) return;   // nothing was handed to the general kernel (uniform over the grid)
+  // mode 0: every bucket.  mode 2 + 16 * hb: the heavy buckets [0, hb) only; mode 3 + 16 * hb: the others
+  // (launch_tail runs the heavy buckets first, on wide CTAs and with the SMs to themselves)
+  const int hb = mode >> 4;
+  const uint64_t w_lo = (mode & 3) == 3 ? bound[hb] : 0, w_hi = (mode & 3) == 2 ? bound[hb] : bound[GRIMB_BUCKETS];
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) sh.work = (uint32_t)atomicAdd(work, 1ull);
     __syncthreads();
-    const uint64_t w = sh.work;
-    if (w >= bound[GRIMB_BUCKETS]) break;
+    const uint64_t w = w_lo + sh.work;
+    if (w >= w_hi) break;
     int k = 0;
     while (w >= bound[k + 1]) ++k;
     // the heaviest subjects come first: bucket 0, entry w -> its lists from the cooperative slot kernel
@@ -2353,6 +2357,7 @@ enum {
   CNT_BUCKETS = 2,    // (4 x u32) cost buckets of the general kernel's work
   CNT_OVERFLOW = 4,   // (u32) side records claimed by subjects with more candidate phases than a hand-over record holds
   CNT_SLOT_TICKET = 5,   // tickets of the cooperative slot kernel
+  CNT_WORK2 = 6,      // tickets of the second general-kernel launch when the heavy buckets run first
   CNT_CHUNK_END = 8,
   CNT_HAP = 8,
   CNT_POP = 9,
@@ -2367,6 +2372,9 @@ struct GrimbEngine {
   const GrimbTables* tables;
   int device;
   int threads;
+  int threads_fixed = 0;          // GRIMB_THREADS given: no switching
+  int64_t wide_cta_below = 2048;  // general-kernel lists up to this length run MAXT threads per CTA (GRIMB_WIDE_CTA_BELOW)
+  int split_heavy = 0;            // longer lists: cost buckets [0, split_heavy) run first, on wide CTAs (GRIMB_SPLIT_HEAVY; 0 off)
   int n_ctas;
   uint64_t arena_per_cta;
   char* arena = nullptr;
@@ -2521,7 +2529,15 @@ extern "C" int grimb_engine_create(const GrimbTables* t, int64_t workspace_bytes
   const char* th = getenv("GRIMB_THREADS");
   if (th) {
     int v = atoi(th);
-    if (v >= 32 && v <= MAXT && v % 32 == 0) e->threads = v;
+    if (v >= 32 && v <= MAXT && v % 32 == 0) {
+      e->threads = v;
+      e->threads_fixed = 1;
+    }
+  }
+  if (const char* wc = getenv("GRIMB_WIDE_CTA_BELOW")) e->wide_cta_below = atoll(wc);
+  if (const char* sh = getenv("GRIMB_SPLIT_HEAVY")) {
+    const int v = atoi(sh);
+    if (v >= 0 && v < GRIMB_BUCKETS) e->split_heavy = v;
   }
 #undef CKE
   *out = e;
@@ -2720,8 +2736,10 @@ static int launch_warp(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch*
   return GRIMB_OK;
 }
 
+// n_tail: subjects the general kernel will serve when the caller knows (the whole batch without warp kernels, the
+// length of the hand-over list once it has been read back), -1 otherwise.
 static int launch_tail(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch* batch, const OutArrays& O, cudaStream_t st,
-                       bool tm) {
+                       bool tm, int64_t n_tail = -1) {
   if (batch->n_subjects <= 0) return GRIMB_OK;
   const TablesView& tv = e->tables->view;
   const bool warp = warp_kernels_apply(e, cfg, batch);
@@ -2741,6 +2759,16 @@ static int launch_tail(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch*
   }
   int grid = e->n_ctas;
   if ((int64_t)grid > batch->n_subjects) grid = (int)batch->n_subjects;
+  // A small batch is bound by its slowest subjects, each alone on one CTA at a few per cent of the SM's issue
+  // rate: twice the threads per CTA halve that subject's time (53 -> 26 ms for the slowest of the C4 messy
+  // set) at the price of half the resident CTAs, which a short list does not fill anyway (cross-over measured
+  // near 3,000 subjects: 250 / 1,000 / 2,000 / 4,000 messy subjects take 45 / 59 / 95 / 179 ms at 256 threads,
+  // 53 / 66 / 112 / 162 ms at 128).
+  int threads = e->threads;
+  if (!e->threads_fixed && n_tail >= 0 && n_tail <= e->wide_cta_below && e->n_ctas >= 2) {
+    threads = MAXT;
+    if (grid > e->n_ctas / 2) grid = e->n_ctas / 2;
+  }
   // cooperative slot kernel for the heaviest subjects (bucket 0), then the general kernel
   PreView pv;
   memset(&pv, 0, sizeof(pv));
@@ -2763,8 +2791,8 @@ static int launch_tail(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch*
       pv.slots_per_subject = spp;
       pv.K = K;
       if (tm) CK(cudaEventRecord(e->ev_slots[0], st));
-      k_impute<<<grid, e->threads, 0, st>>>(tv, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones,
-                                           e->d_counters + CNT_SLOT_TICKET, (const uint32_t*)e->buckets.p, bucket_n, stride, pv, 1);
+      k_impute<<<grid, threads, 0, st>>>(tv, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones,
+                                        e->d_counters + CNT_SLOT_TICKET, (const uint32_t*)e->buckets.p, bucket_n, stride, pv, 1);
       CK(cudaGetLastError());
       if (tm) CK(cudaEventRecord(e->ev_slots[1], st));
       e->ev_slots_valid = tm;
@@ -2772,8 +2800,21 @@ static int launch_tail(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch*
     }
   }
   if (tm) CK(cudaEventRecord(e->ev[2], st));
-  k_impute<<<grid, e->threads, 0, st>>>(tv, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones, e->d_counters + CNT_WORK,
-                                       (const uint32_t*)e->buckets.p, bucket_n, stride, pv, 0);
+  if (e->split_heavy > 0 && threads != MAXT && !e->threads_fixed && e->n_ctas >= 2) {
+    // a long list: its heavy buckets first, alone on the GPU and on wide CTAs, then the rest
+    const int hb = e->split_heavy;
+    int gh = e->n_ctas / 2;
+    if ((int64_t)gh > batch->n_subjects) gh = (int)batch->n_subjects;
+    k_impute<<<gh, MAXT, 0, st>>>(tv, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones, e->d_counters + CNT_WORK,
+                                 (const uint32_t*)e->buckets.p, bucket_n, stride, pv, 2 + 16 * hb);
+    CK(cudaGetLastError());
+    k_impute<<<grid, threads, 0, st>>>(tv, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones, e->d_counters + CNT_WORK2,
+                                      (const uint32_t*)e->buckets.p, bucket_n, stride, pv, 3 + 16 * hb);
+    e->launches += 1;
+  } else {
+    k_impute<<<grid, threads, 0, st>>>(tv, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones, e->d_counters + CNT_WORK,
+                                      (const uint32_t*)e->buckets.p, bucket_n, stride, pv, 0);
+  }
   CK(cudaGetLastError());
   if (tm) CK(cudaEventRecord(e->ev[3], st));
   e->ev_valid[1] = tm;
@@ -2852,7 +2893,7 @@ extern "C" int grimb_impute_device_async(GrimbEngine* e, const GrimbConfig* cfg,
   // batches with a few handed-on subjects each then never waits twice); otherwise it is left to finish
   e->tail_queued = e->tail_expected || !warp_kernels_apply(e, cfg, batch);
   if (e->tail_queued) {
-    rc = launch_tail(e, cfg, batch, O, st, e->timing != 0);
+    rc = launch_tail(e, cfg, batch, O, st, e->timing != 0, warp_kernels_apply(e, cfg, batch) ? -1 : batch->n_subjects);
     if (rc) return rc;
   }
   CK(cudaMemcpyAsync(e->h_tail, e->d_counters, CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -2875,7 +2916,8 @@ extern "C" int grimb_impute_finish(GrimbEngine* e, const GrimbResults* res) {
   e->tail_expected = handed > 0;
   if (!e->tail_queued && (!warp || handed > 0)) {
     cudaStream_t st = e->pending_stream;
-    int rc = launch_tail(e, &e->cfg_host, &e->pend_batch, out_arrays(e, e->pend_res), st, e->timing != 0);
+    int rc = launch_tail(e, &e->cfg_host, &e->pend_batch, out_arrays(e, e->pend_res), st, e->timing != 0,
+                         warp ? (int64_t)handed : e->pend_batch.n_subjects);
     if (rc) return rc;
     CK(cudaMemcpyAsync(e->h_tail, e->d_counters, CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(e->ev_done, st));
@@ -3040,9 +3082,20 @@ extern "C" int grimb_impute_host(GrimbEngine* e, const GrimbConfig* cfg, const G
     }
   }
   mark(1);   // warp kernels of every chunk queued, copy-out of all but the last chunk handed over
-  // the tail, once: everything the warp kernels handed on (or the whole batch when none serves it)
-  rc = launch_tail(e, cfg, &db, O, st, tm);
-  if (rc) return rc;
+  // the tail, once: everything the warp kernels handed on (or the whole batch when none serves it).  The length
+  // of the hand-over list is read first (the last chunk's counters, through mapped memory): an empty list needs no
+  // tail at all, a short one runs on wide CTAs (launch_tail).  The last chunk's copy-out is queued BEHIND the
+  // tail: with a single chunk it shares the compute stream, and ahead of the tail it would hold the kernels back
+  // (and block this thread when the caller's buffers are pageable).
+  int64_t n_tail = warp ? -1 : (int64_t)S;
+  if (warp && nch > 0) {
+    CK(cudaEventSynchronize(e->ev_k[nch - 1]));
+    n_tail = (int64_t)(e->h_cnt[(size_t)CNT_N * (nch - 1) + CNT_WORKLIST] & 0xFFFFFFFFull);
+  }
+  if (!(warp && n_tail == 0)) {
+    rc = launch_tail(e, cfg, &db, O, st, tm, n_tail);
+    if (rc) return rc;
+  }
   k_snapshot<<<1, 32, 0, st>>>(e->d_counters, e->h_cnt_dev + (size_t)CNT_N * GRIMB_MAX_CHUNKS, CNT_N);
   CK(cudaGetLastError());
   if (warp && nch > 0) {

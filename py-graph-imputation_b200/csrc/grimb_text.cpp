@@ -424,7 +424,15 @@ struct GrimbText {
       const size_t lo = std::min(n, per * (size_t)t), hi = std::min(n, per * (size_t)(t + 1));
       f(t, lo, hi);
     };
-    tls_pool().run(nt, body);
+    static const bool use_pool = !(getenv("GRIMB_POOL") && getenv("GRIMB_POOL")[0] == '0');
+    if (use_pool) {
+      tls_pool().run(nt, body);
+      return;
+    }
+    std::vector<std::thread> th;   // GRIMB_POOL=0: a thread per slice, created and joined per region
+    for (int t = 1; t < nt; ++t) th.emplace_back([&body, t]() { body(t); });
+    body(0);
+    for (auto& x : th) x.join();
   }
   static Pool& tls_pool() {   // one pool per calling thread, whatever the region (not one per template instance)
     static thread_local Pool pool;
