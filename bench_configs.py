@@ -88,9 +88,19 @@ def measure(name, g, cfg, cbp, lines, oracle_graph, conf, sample, torch, dev, st
     if workspace:
         imp.workspaces = workspace
     imp._text = warm._text                      # same GrimbText: its staging is sized by the warm-up pass
-    t0 = time.time()
-    texts = imp.impute_text(data)
-    t_text = time.time() - t0
+    # three calls, the median reported (single calls of the nine-locus configurations showed sporadic stalls of
+    # 0.1-1 s inside the ABI call that are not understood yet: all three times are kept in the record)
+    text_runs = []
+    for _rep in range(3):
+        imp = Imputation(g, cfg, cbp)
+        if workspace:
+            imp.workspaces = workspace
+        imp._text = warm._text
+        t0 = time.time()
+        texts = imp.impute_text(data)
+        text_runs.append((time.time() - t0, imp))
+    text_runs.sort(key=lambda x: x[0])
+    t_text, imp = text_runs[1]
     # device-resident leg
     db, keep, S, in_bytes = device_batch(lib, imp, data, torch, dev)
     caps = {"words": 0, "general": 0, "hap_rows": 0, "pop_rows": 0}
@@ -157,7 +167,11 @@ def measure(name, g, cfg, cbp, lines, oracle_graph, conf, sample, torch, dev, st
                      "frac": (algo / (k_ms * 1e-3) / 1e9 / peak) if k_ms > 0 else None},
         "e2e_text": {"subjects_per_s": S / t_text, "out_bytes": sum(len(v) for v in texts.values()),
                      "tokenise_s": imp.stats.get("tokenise_seconds"), "abi_s": imp.stats.get("abi_seconds"),
-                     "format_s": imp.stats.get("format_seconds")},
+                     "format_s": imp.stats.get("format_seconds"),
+                     # subjects re-issued on a bigger workspace tier in this call (the first use of a tier creates its
+                     # engine: a device allocation of tens of GB, 0.2-0.6 s, inside the call)
+                     "workspace_retries": imp.stats.get("workspace_retries"),
+                     "seconds_of_three_calls": [round(x[0], 4) for x in text_runs]},
         "plans": imp.stats["plan"],
         "oracle": {"sample": ns, "identical": all(mine[k] == ref[k] for k in ref), "subjects_per_s_all_cores": ns / t_cpu,
                    "cores": os.cpu_count()},

@@ -112,8 +112,7 @@ GD void load_sector(const HSlot* p, HSlot& s0, HSlot& s1) {
 #endif
 
 // Home slot of a key: always the first slot of a 32-byte sector (two 16-byte slots), so a probe
-// reads whole sectors -- both slots of a sector are fetched by two adjacent 128-bit loads that
-// resolve to one memory transaction.
+// reads whole sectors -- both slots of a sector come with ONE 256-bit load (load_sector: LDG.E.256).
 #if GRIMB_KW == 1
 GD uint32_t ht_home(hkey key, uint32_t mask) { return hash_key(key) & mask & ~1u; }
 
