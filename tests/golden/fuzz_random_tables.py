@@ -202,6 +202,59 @@ def main_modes(n_tables, n, seed):
     return 0 if ok else 1
 
 
+def main_matrix(n_tables, n, seed):
+    """Plan_A_Matrix on random dense five-locus tables: random matrices (the full label first, a random
+    set of marginal labels in random order), Plan B off -- everything the reference does is then defined -- plus a
+    Plan-B-on case restricted to subjects that finish in Plan A (checked: the oracle refuses otherwise)."""
+    import itertools
+    rng = np.random.RandomState(seed)
+    ok = True
+    all_labels = [list(c) for r in range(4, 0, -1) for c in itertools.combinations([1, 2, 3, 4, 5], r)]
+    for t in range(n_tables):
+        n_full = int(rng.choice([30, 120, 500]))
+        n_alleles = [int(x) for x in (rng.randint(2, 6, size=5) if t % 2 == 0 else rng.randint(3, 13, size=5))]
+        pops = [["CAU"], ["AAA", "BBB"], ["AAA", "BBB", "CCC", "DDD"]][t % 3]
+        tseed = int(rng.randint(1, 1 << 30))
+        hpf = synth.zipf_table(n_full, n_alleles, tseed, pops=tuple(pops))
+        cnt = 1000.0 / np.arange(1, len(pops) + 1) ** 1.1
+        counts = "".join("%s,%s,%s\n" % (p, repr(float(c)), repr(float(c / cnt.sum()))) for p, c in zip(pops, cnt))
+        k = int(rng.randint(1, 9))
+        pick = [all_labels[i] for i in rng.choice(len(all_labels), size=k, replace=False)]
+        matrix = [[1, 2, 3, 4, 5]] + pick
+        conf = dict(BASE_CONF)
+        conf.update({"populations": pops, "UNK_priors": "MR", "Plan_A_Matrix": matrix, "planb": False})
+        tab = synth.Table(hpf, pops[0])
+        races = synth.race_fields(pops) if len(pops) > 1 else None
+        kw = {"races": races} if races else {}
+        print("== matrix table %d: %d haplotypes, alleles/locus %s, pops %s, matrix %s (seed %d)" % (
+            t, len(tab.haps), n_alleles, pops, matrix, tseed), flush=True)
+        og = go.OracleGraph(hpf.splitlines(True), pops, conf["loci_map"], conf["freq_trim_threshold"], counts.splitlines(True),
+                            plan_a_matrix=matrix)
+        eg = EmuGraph(og, conf["loci_map"])
+        cbp = np.array([float(l.split(",")[2]) for l in counts.splitlines()])
+        subsets = [[x - 1 for x in row] for row in matrix] + [[0, 1], [2, 3, 4]]
+        mixed = (synth.typed_subjects(tab, n, tseed + 1, races) + synth.messy_subjects(tab, n, tseed + 2, **kw)
+                 + synth.subset_subjects(tab, 2 * n, tseed + 3, subsets, races, amb=2))
+        # Plan B on: keep the subjects the oracle finishes in Plan A (it raises on the first that would not)
+        plan_a_only = []
+        oimp = go.OracleImputation(og, go.load_config(dict(conf, planb=True)), cbp)
+        for ln in mixed:
+            try:
+                oimp.impute_lines([ln])
+                plan_a_only.append(ln)
+            except go.PlanBUnderMatrix:
+                pass
+        cases = [
+            ("matrix planb off", mixed, {}),
+            ("matrix low threshold", mixed, {"number_of_options_threshold": 40}),
+            ("matrix pmug only nres=3", mixed, {"output_MUUG": False, "number_of_results": 3}),
+            ("matrix planb on (Plan A only)", plan_a_only, {"planb": True}),
+        ]
+        ok &= run_cases(conf, hpf, counts, cases, og, eg, cbp, text_too=True)
+    print("ALL OK" if ok else "SOME MISMATCH")
+    return 0 if ok else 1
+
+
 def main_heavy(n, seed, rounds):
     """Highly ambiguous subjects on the README table: 6-40 alleles per locus side, 0-3
     missing loci, products on both sides of number_of_options_threshold (default 100,000 and 2,000)."""
@@ -302,6 +355,9 @@ def main():
         a = sys.argv[2:]
         return main_dirty(int(a[0]) if a else 4, int(a[1]) if len(a) > 1 else 20, int(a[2]) if len(a) > 2 else 1,
                           crlf=sys.argv[1] == "--dirty-crlf")
+    if len(sys.argv) > 1 and sys.argv[1] == "--matrix":
+        a = sys.argv[2:]
+        return main_matrix(int(a[0]) if a else 6, int(a[1]) if len(a) > 1 else 20, int(a[2]) if len(a) > 2 else 1)
     if len(sys.argv) > 1 and sys.argv[1] == "--heavy":
         a = sys.argv[2:]
         return main_heavy(int(a[0]) if a else 10, int(a[1]) if len(a) > 1 else 1, int(a[2]) if len(a) > 2 else 1)
