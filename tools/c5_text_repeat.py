@@ -34,9 +34,15 @@ p5 = ff9.mean(axis=1)
 p5 = p5 / p5.sum()
 lines5 = synth.array_subject_lines(names9, fa9, p5, 1 << 16, 9, synth.race_fields(pops5), variants=False)
 data = "".join(lines5).encode()
+warm = Imputation(g5, cfg5, ratio5)
+warm.impute_text(data)
+eng = g5.engine(warm.workspaces[0])
 for c in range(calls):
     imp = Imputation(g5, cfg5, ratio5)
+    imp._text = warm._text            # the same GrimbText (pinned staging sized by the warm-up), as bench_configs does
     t0 = time.time()
     imp.impute_text(data)
-    print("call %d: %.1f ms wall, abi %.4f s, workspace retries %d, engines %s" % (
-        c, (time.time() - t0) * 1e3, imp.stats.get("abi_seconds", 0.0), imp.stats["workspace_retries"], sorted(g5._engines)))
+    print("call %d: %.1f ms wall, tokenise %.4f abi %.4f format %.4f s, retries %d, k_impute %.3f ms, k_impute_typed %.3f ms, slots %.3f ms" % (
+        c, (time.time() - t0) * 1e3, imp.stats.get("tokenise_seconds", 0.0), imp.stats.get("abi_seconds", 0.0),
+        imp.stats.get("format_seconds", 0.0), imp.stats["workspace_retries"], g5.lib.grimb_engine_kernel_ms(eng, 1),
+        g5.lib.grimb_engine_kernel_ms(eng, 2), g5.lib.grimb_engine_kernel_ms(eng, 5)), flush=True)
