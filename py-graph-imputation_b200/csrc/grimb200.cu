@@ -933,7 +933,7 @@ __global__ void k_classify(GrimbBatch B, int L, const uint32_t* list, const unsi
 }
 
 #ifndef KI_MIN_BLOCKS
-#define KI_MIN_BLOCKS 4   /* 64 registers: 8 CTAs of 128 threads per SM; measured 13-18 % faster on C4 than 124 registers / 4 CTAs */
+#define KI_MIN_BLOCKS 2   /* x MAXT = 512 threads: 64 registers, i.e. 8 CTAs of 128 threads per SM; measured 13-18 % faster on C4 than 124 registers / 4 CTAs */
 #endif
 
 static __device__ __forceinline__ void init_subject(Subject& S, Shared& sh, const TablesView& T, const GrimbConfig* cfg,
@@ -2765,9 +2765,11 @@ static int launch_tail(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch*
   // near 3,000 subjects: 250 / 1,000 / 2,000 / 4,000 messy subjects take 45 / 59 / 95 / 179 ms at 256 threads,
   // 53 / 66 / 112 / 162 ms at 128).
   int threads = e->threads;
-  if (!e->threads_fixed && n_tail >= 0 && n_tail <= e->wide_cta_below && e->n_ctas >= 2) {
-    threads = MAXT;
-    if (grid > e->n_ctas / 2) grid = e->n_ctas / 2;
+  if (!e->threads_fixed && n_tail >= 0 && n_tail <= e->wide_cta_below && e->n_ctas >= 4) {
+    // 256 threads, or 512 for a very short list (an eighth of the threshold: 256 subjects)
+    threads = n_tail <= e->wide_cta_below / 8 ? 512 : 256;
+    const int div = threads / 128;
+    if (grid > e->n_ctas / div) grid = e->n_ctas / div;
   }
   // cooperative slot kernel for the heaviest subjects (bucket 0), then the general kernel
   PreView pv;
@@ -2800,13 +2802,13 @@ static int launch_tail(GrimbEngine* e, const GrimbConfig* cfg, const GrimbBatch*
     }
   }
   if (tm) CK(cudaEventRecord(e->ev[2], st));
-  if (e->split_heavy > 0 && threads != MAXT && !e->threads_fixed && e->n_ctas >= 2) {
+  if (e->split_heavy > 0 && threads == e->threads && !e->threads_fixed && e->n_ctas >= 2) {
     // a long list: its heavy buckets first, alone on the GPU and on wide CTAs, then the rest
     const int hb = e->split_heavy;
     int gh = e->n_ctas / 2;
     if ((int64_t)gh > batch->n_subjects) gh = (int)batch->n_subjects;
-    k_impute<<<gh, MAXT, 0, st>>>(tv, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones, e->d_counters + CNT_WORK,
-                                 (const uint32_t*)e->buckets.p, bucket_n, stride, pv, 2 + 16 * hb);
+    k_impute<<<gh, 256, 0, st>>>(tv, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones, e->d_counters + CNT_WORK,
+                                (const uint32_t*)e->buckets.p, bucket_n, stride, pv, 2 + 16 * hb);
     CK(cudaGetLastError());
     k_impute<<<grid, threads, 0, st>>>(tv, e->d_cfg, *batch, O, e->arena, e->arena_per_cta, e->ones, e->d_counters + CNT_WORK2,
                                       (const uint32_t*)e->buckets.p, bucket_n, stride, pv, 3 + 16 * hb);

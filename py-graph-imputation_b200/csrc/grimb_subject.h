@@ -27,7 +27,7 @@
 
 namespace grimb {
 
-constexpr int MAXT = 256;   // max threads per group
+constexpr int MAXT = 512;   // max threads per group
 constexpr int MAXL = GRIMB_MAX_LOCI;
 constexpr int MAXPH = 256;  // 2^(MAXL-1)
 constexpr int NVAR = 4;
