@@ -21,6 +21,7 @@
 #include <thread>
 #include <unordered_map>
 #include <vector>
+#include <unistd.h>
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
@@ -365,6 +366,22 @@ struct GrimbText {
     uint64_t gen = 0;
     int active = 0, pending = 0;
     bool stop = false;
+    pid_t owner = getpid();
+    // after fork() the child has this object but none of its threads: forget them (the handles are leaked on
+    // purpose -- joining or destroying a std::thread whose thread does not exist in this process is undefined)
+    void forget_if_forked() {
+      if (getpid() == owner) return;
+      new std::vector<std::thread>(std::move(th));
+      th.clear();
+      // the parent's parked workers were waiting on these: their internal waiter state is meaningless here
+      new (&m) std::mutex();
+      new (&cv_go) std::condition_variable();
+      new (&cv_done) std::condition_variable();
+      owner = getpid();
+      job = nullptr;
+      gen = 0;
+      active = pending = 0;
+    }
     void worker(int t) {
       uint64_t seen = 0;
       for (;;) {
@@ -384,6 +401,7 @@ struct GrimbText {
       }
     }
     void run(int nt, const std::function<void(int)>& f) {
+      forget_if_forked();
       while ((int)th.size() < nt - 1) {
         const int t = (int)th.size() + 1;   // the calling thread is worker 0
         th.emplace_back([this, t]() { worker(t); });
@@ -402,6 +420,7 @@ struct GrimbText {
       job = nullptr;
     }
     ~Pool() {
+      forget_if_forked();
       {
         std::lock_guard<std::mutex> g(m);
         stop = true;

@@ -201,3 +201,57 @@ def test_write_at_places_bytes(tmp_path):
     assert lib.grimb_file_write_at(path.encode(), 4, b"abc", 3) == 0
     assert lib.grimb_file_write_at(path.encode(), 0, b"zz", 2) == 0
     assert open(path, "rb").read() == b"zz\x00\x00abc\x00\x00\x00"
+
+
+_FORK_SCRIPT = r"""
+import ctypes as C, os, sys, time
+import goldenlib, synth
+import grim_oracle as go
+from emu_backend import EmuGraph, emu_imputation
+from grim.imputation import _lib
+from grim.run_impute_def import load_config
+table, conf, _l, _e = goldenlib.load_case("g1_readme_donor")
+eg = EmuGraph(go.graph_from_config(conf), conf["loci_map"])
+imp = emu_imputation(eg, load_config(conf))
+tab = synth.Table(open(conf["freq_file"]).read())
+data = "".join(synth.typed_subjects(tab, 3000, 5, ["CAU,CAU"])).encode()
+lib = _lib.load()
+t = imp._text_handle()
+def tokenise():
+    b = _lib.Batch()
+    _lib.check(lib.grimb_text_tokenise(t, C.byref(imp.cfg), data, len(data), 0, C.byref(b)), "tokenise")
+    return b.n_subjects
+assert tokenise() == 3000                               # the pool's workers exist now
+pid = os.fork()
+if pid == 0:
+    import faulthandler
+    faulthandler.dump_traceback_later(60, exit=True)    # a hang becomes a failure, not a stuck test run
+    assert tokenise() == 3000                           # the child: same pool object, no threads
+    faulthandler.cancel_dump_traceback_later()
+    sys.exit(0)                                         # a NORMAL exit: thread_local destructors run
+t_end = time.time() + 120
+status = None
+while time.time() < t_end:
+    p, st = os.waitpid(pid, os.WNOHANG)
+    if p:
+        status = st
+        break
+    time.sleep(0.05)
+if status is None:
+    os.kill(pid, 9)
+    raise SystemExit("the forked child hangs")
+assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0, status
+assert tokenise() == 3000
+print("FORK-OK")
+"""
+
+
+def test_worker_pool_survives_a_fork():
+    """The text pipeline parks its worker threads between parallel regions.  A forked child has the pool object but
+    none of its threads (and condition variables with the parent's waiters recorded): it must start afresh, use the
+    pipeline and exit normally, and the parent must carry on."""
+    import subprocess
+    import sys
+    env = dict(os.environ, GRIMB_HOST_THREADS="4", PYTHONPATH=os.pathsep.join(sys.path))
+    r = subprocess.run([sys.executable, "-W", "ignore", "-c", _FORK_SCRIPT], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "FORK-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
