@@ -571,7 +571,7 @@ def main():
     parity = None
     cpu = None
     e2e_text = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:   # the CPU baseline is an N = 1 record
         import grim_oracle as go
         from grim.imputation.impute import Imputation
         n_c = min(S, args.cpu_sample)
