@@ -226,7 +226,9 @@ def _run_impute_sharded(dist, config, hap_pop_pair, graph):
             if any(e is not None and "(-3)" in e[1] for e in errs) and n_tiers < len(imputation.workspaces):
                 n_tiers += 1
                 continue
-            first = next(e for e in errs if e is not None)
+            # the rank that hit the problem names it; the others only report that a rank failed
+            found = [e for e in errs if e is not None]
+            first = next((e for e in found if "another rank failed" not in e[1]), found[0])
             if cleaner is not None:
                 cleaner.join()
             raise (NotImplementedError if first[0] == "NotImplementedError" else RuntimeError)(first[1])
